@@ -1,0 +1,182 @@
+/*
+ * ntsynt_b200.h -- C-ABI of libntsynt_b200.so: the B200-native (sm_100a) replacement for
+ * ntSynt's minimizer-sketch -> common-Bloom-filter -> minimizer-graph hot path.
+ *
+ * The reference (bcgsc/ntSynt v1.0.4, paths below are relative to its tree) has no
+ * in-process FFI for this path: its seam is three executables plus the files between them
+ * (bin/ntsynt_run_pipeline.smk:48-103).  Each entry point below names the reference call
+ * site it replaces; INTEGRATION.md shows the ctypes binding and the drop-in executables.
+ *
+ * Conventions: every function returns 0 on success and a negative nts_status on failure;
+ * nts_last_error() gives the message of the last failure on the calling thread.  All
+ * pointers are HOST pointers owned by the caller unless the name says `_dev`.  One CUDA
+ * stream per context; calls are synchronous unless named `_async`.  A context is
+ * thread-compatible (distinct contexts on distinct threads), not thread-safe.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef NTSYNT_B200_H
+#define NTSYNT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    NTS_OK = 0,
+    NTS_ERR_CUDA = -1,     /* a CUDA runtime call failed */
+    NTS_ERR_ARG = -2,      /* invalid argument */
+    NTS_ERR_NOMEM = -3,    /* host or device allocation failed */
+    NTS_ERR_OVERFLOW = -4, /* an output did not fit its capacity even after the retry */
+    NTS_ERR_NCCL = -5,     /* NCCL not loadable or a NCCL call failed */
+    NTS_ERR_STATE = -6     /* call sequence error */
+} nts_status;
+
+typedef struct nts_ctx nts_ctx;       /* one per GPU / host thread */
+typedef struct nts_genome nts_genome; /* 2-bit packed contigs + N runs, resident in HBM */
+typedef struct nts_bf nts_bf;         /* Bloom filter bit array in HBM (1 hash function) */
+typedef struct nts_mxs nts_mxs;       /* minimizer table (h1, pos, contig) in HBM */
+
+/* -------------------------------------------------------------------------------- library */
+const char* nts_version(void);
+const char* nts_last_error(void);
+int nts_device_count(int* out);
+
+/* -------------------------------------------------------------------------------- context */
+int nts_ctx_create(int device, nts_ctx** out);
+void nts_ctx_destroy(nts_ctx* ctx);
+int nts_ctx_sync(nts_ctx* ctx);
+/* CUDA-event timer on the context's stream (used by bench.py for device-side timing). */
+int nts_timer_start(nts_ctx* ctx);
+int nts_timer_stop(nts_ctx* ctx, float* ms_out);
+/* number of kernel launches issued by this library on this context since creation */
+uint64_t nts_launch_count(const nts_ctx* ctx);
+/* free / total device memory in bytes */
+int nts_mem_info(nts_ctx* ctx, uint64_t* free_b, uint64_t* total_b);
+
+/* -------------------------------------------------------------------------------- ingest
+ * Replaces btllib::SeqReader as used at src/ntsynt_make_common_bf.cpp:32-36,125,143 and
+ * inside indexlr.  Packed layout: 2 bits per base (A=0,C=1,G=2,T=3; anything else is stored
+ * as 0 and recorded as an N run), 32 bases per little-endian uint64 word, base i of a contig
+ * at bits [2*(i%32), 2*(i%32)+1] of word i/32.  Lower-case acgt pack like upper case.
+ */
+/* number of uint64 words a contig of n bases occupies (rounded up to a 16-byte multiple) */
+uint64_t nts_packed_words(uint64_t n_bases);
+/* Pack one ASCII sequence.  nrun_start/nrun_len receive maximal runs of non-ACGT characters
+ * (capacity nrun_cap each); *n_nruns gets the number found (may exceed nrun_cap: call again
+ * with larger buffers).  words_out must hold nts_packed_words(n) words. */
+int nts_pack_ascii(const char* seq, uint64_t n, uint64_t* words_out, uint64_t* nrun_start, uint64_t* nrun_len,
+                   uint64_t nrun_cap, uint64_t* n_nruns);
+/* Inverse (for --seq output and tests): bases [start, start+n) of a packed contig -> ASCII ACGT. */
+int nts_unpack_ascii(const uint64_t* words, uint64_t start, uint64_t n, char* out);
+
+/* Upload a genome.  contig c occupies nts_packed_words(contig_len[c]) words starting at word
+ * contig_word_off[c] of `words` (caller lays contigs out back to back in that order).
+ * N runs of contig c are entries [nrun_off[c], nrun_off[c+1]) of nrun_start/nrun_len (sorted,
+ * contig-local coordinates). */
+int nts_genome_upload(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const uint64_t* contig_word_off,
+                      const uint64_t* words, uint64_t n_words, const uint64_t* nrun_off, const uint64_t* nrun_start,
+                      const uint64_t* nrun_len, nts_genome** out);
+void nts_genome_destroy(nts_genome* g);
+/* total bases, Ns included (the `n` of approximate_bf_size, cpp:34-36) */
+uint64_t nts_genome_size(const nts_genome* g);
+uint32_t nts_genome_contigs(const nts_genome* g);
+/* copy the packed words of one contig back to the host (nts_packed_words(len) words) */
+int nts_genome_download_contig(nts_genome* g, uint32_t contig, uint64_t* words_out);
+/* N runs of the whole genome, same layout as nts_genome_upload's arguments */
+int nts_genome_nruns(nts_genome* g, uint64_t* nrun_off /*[n_contigs+1]*/, uint64_t* nrun_start, uint64_t* nrun_len,
+                     uint64_t cap, uint64_t* n_out);
+
+/* Synthetic genome materialised on the device from a segment table (bench.py).
+ * Output base j of contig c = ancestor base (or its complement for strand -1) addressed by the
+ * segment covering j, then substituted with probability sub_rate (Philox-keyed by seed,j).
+ * seg_* arrays: [n_seg] sorted by (contig, dst_start); anc_contig < 0 means "random insert",
+ * anc_contig == -2 means "N run".  The ancestor itself is a pure function of (anc_seed, contig,
+ * position): i.i.d. bases with P(A)=P(T)=0.295, P(C)=P(G)=0.205 overlaid with repeat copies. */
+typedef struct {
+    uint32_t dst_contig;
+    int32_t anc_contig;   /* >=0 ancestor contig; -1 random insert; -2 N run */
+    uint64_t dst_start;   /* contig-local start in the new genome */
+    uint64_t anc_start;   /* ancestor coordinate of the segment's FIRST output base */
+    uint64_t len;
+    int32_t strand;       /* +1 forward, -1 reverse complement (anc_start then decreases) */
+    uint32_t pad;
+} nts_synth_seg;
+int nts_genome_synthesize(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const nts_synth_seg* segs,
+                          uint64_t n_seg, uint64_t anc_seed, uint64_t genome_seed, double sub_rate,
+                          uint32_t n_repeat_fam, double repeat_frac, nts_genome** out);
+
+/* -------------------------------------------------------------------------------- Bloom filter
+ * Replaces btllib::KmerBloomFilter(bytes, 1, k) as used by src/ntsynt_make_common_bf.cpp. */
+/* a1: approximate_bf_size (cpp:28-40) + btllib's round-up to a multiple of 8 bytes */
+uint64_t nts_bf_bytes(int64_t genome_size, double fpr);
+int nts_bf_create(nts_ctx* ctx, uint64_t bytes, nts_bf** out); /* zero-filled */
+void nts_bf_destroy(nts_bf* bf);
+uint64_t nts_bf_size_bytes(const nts_bf* bf);
+int nts_bf_clear(nts_bf* bf);
+/* a2: bf->insert(record.seq) for every record (cpp:128-131): sets bit ntHash2_h0(kmer) mod m
+ * for every all-ACGT k-mer (kernels i + iii-a). */
+int nts_bf_insert_genome(nts_bf* bf, const nts_genome* g, uint32_t k);
+/* a3: the cascade of cpp:136-160 with one hash function == dst &= src (kernel iii-b) */
+int nts_bf_and(nts_bf* dst, const nts_bf* src);
+int nts_bf_or(nts_bf* dst, const nts_bf* src);
+/* repeat filter, bin/ntsynt_make_repeat_bfs.py:56-69: rep |= k-mers seen >= 2x in g (kernel iii-d).
+ * `scratch` is a per-genome filter of the same size that the call clears and uses. */
+int nts_bf_insert_repeats(nts_bf* rep, nts_bf* scratch, const nts_genome* g, uint32_t k);
+int nts_bf_popcount(nts_bf* bf, uint64_t* bits_set); /* for the "Bloom filter FPR" log lines */
+int nts_bf_download(nts_bf* bf, uint8_t* bytes_out);
+int nts_bf_upload(nts_bf* bf, const uint8_t* bytes_in);
+/* Multi-GPU merge (north star: counting filters + one NCCL allreduce(sum)).  Every rank holds
+ * `n_local` per-genome filters; after the call filters[0] on every rank holds the AND over all
+ * genomes of all ranks.  comm is an ncclComm_t created by nts_nccl_init. */
+typedef struct nts_comm nts_comm;
+int nts_nccl_unique_id(uint8_t id_out[128]);
+int nts_nccl_init(nts_ctx* ctx, const uint8_t id[128], int rank, int world, nts_comm** out);
+void nts_nccl_destroy(nts_comm* comm);
+int nts_bf_allreduce_and(nts_comm* comm, nts_bf* const* filters, uint32_t n_local, uint32_t n_total_genomes);
+
+/* -------------------------------------------------------------------------------- sketch
+ * Replaces `indexlr -k K -w W --long --pos [-s common.bf] [-r repeat.bf]`
+ * (bin/ntsynt_run_pipeline.smk:83-85; subprojects/ntJoin/bin/ntjoin_utils.py:195-202).
+ * mask_*: optional extra N intervals (the synteny-block masks of
+ * bin/ntsynt_synteny.py:134-157), contig c owning entries [mask_off[c], mask_off[c+1]),
+ * sorted, half-open [start, end), contig-local.  Pass mask_off = NULL for none.
+ * Output order: by contig, then by position (== indexlr's emission order). */
+int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common /*nullable*/, const nts_bf* repeat /*nullable*/,
+               uint32_t k, uint32_t w, const uint64_t* mask_off, const uint64_t* mask_start,
+               const uint64_t* mask_end, nts_mxs** out);
+void nts_mxs_destroy(nts_mxs* m);
+uint64_t nts_mxs_count(const nts_mxs* m);
+/* h1 = second ntHash2 hash (what indexlr prints), pos = 0-based k-mer start, contig index */
+int nts_mxs_download(nts_mxs* m, uint64_t* h1, uint32_t* pos, uint32_t* contig);
+/* test hook: canonical h0 and validity of every k-mer start of one contig (kernel i alone) */
+int nts_hash_contig(nts_ctx* ctx, const nts_genome* g, uint32_t contig, uint32_t k, uint64_t* h0_out,
+                    uint8_t* valid_out);
+
+/* -------------------------------------------------------------------------------- graph (kernel iv)
+ * Replaces ntjoin_utils.read_minimizers' duplicate removal (:182-192), filter_minimizers
+ * (:152-165), build_graph's adjacency edges (:97-113,132-135) and, for edges of full weight,
+ * ntjoin.find_paths (ntjoin.py:114-136).  Input: one minimizer table per assembly in the
+ * caller's assembly order.  See nts_graph_* in INTEGRATION.md. */
+typedef struct nts_graph nts_graph;
+int nts_graph_build(nts_ctx* ctx, nts_mxs* const* tables, uint32_t n_asm, nts_graph** out);
+void nts_graph_destroy(nts_graph* g);
+/* number of common (deduplicated, present in all assemblies) minimizers = vertices */
+uint64_t nts_graph_vertices(const nts_graph* g);
+/* Vertex table in the order of assembly `order_asm`'s filtered list (contig, then position):
+ * h1[V]; pos[n_asm*V] and contig[n_asm*V] (assembly-major); rank[n_asm*V] = index of the
+ * vertex in that assembly's filtered list (lists of all contigs concatenated). */
+int nts_graph_download_vertices(nts_graph* g, uint32_t order_asm, uint64_t* h1, uint32_t* pos, uint32_t* contig,
+                                uint32_t* rank);
+/* Edge table: distinct unordered adjacencies in first-insertion order of build_graph
+ * (assembly order, list order); u,v = vertex indices (order_asm numbering of the last
+ * download), support = bitmask of assemblies, first_asm/first_idx = where it was first seen. */
+uint64_t nts_graph_edges(const nts_graph* g);
+int nts_graph_download_edges(nts_graph* g, uint32_t* u, uint32_t* v, uint32_t* support);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTSYNT_B200_H */

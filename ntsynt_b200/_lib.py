@@ -1,0 +1,105 @@
+"""ctypes binding of libntsynt_b200.so (include/ntsynt_b200.h).  No CPU fallback: if the
+library is missing it is built with nvcc; if it cannot be loaded the import fails loudly."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class NtsError(RuntimeError):
+    "A libntsynt_b200 call returned a negative status."
+
+    def __init__(self, status, message):
+        super().__init__(f"[nts status {status}] {message}")
+        self.status = status
+
+
+class SynthSeg(C.Structure):
+    _fields_ = [("dst_contig", C.c_uint32), ("anc_contig", C.c_int32), ("dst_start", C.c_uint64),
+                ("anc_start", C.c_uint64), ("len", C.c_uint64), ("strand", C.c_int32), ("pad", C.c_uint32)]
+
+
+def _load():
+    path = os.environ.get("NTSYNT_B200_LIB") or _build.LIB
+    if not os.path.exists(path) or (not os.environ.get("NTSYNT_B200_LIB") and _build.needs_build()):
+        path = _build.build_lib()
+    try:
+        return C.CDLL(path, mode=C.RTLD_GLOBAL)
+    except OSError as exc:
+        raise ImportError(f"cannot load {path}: {exc}. ntsynt_b200 has no CPU fallback; build it with "
+                          f"`python -m ntsynt_b200.build` (needs nvcc).") from exc
+
+
+lib = _load()
+
+u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
+
+_SIGS = {
+    "nts_version": (C.c_char_p, []),
+    "nts_last_error": (C.c_char_p, []),
+    "nts_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "nts_ctx_create": (C.c_int, [C.c_int, vpp]),
+    "nts_ctx_destroy": (None, [vp]),
+    "nts_ctx_sync": (C.c_int, [vp]),
+    "nts_timer_start": (C.c_int, [vp]),
+    "nts_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "nts_launch_count": (C.c_uint64, [vp]),
+    "nts_mem_info": (C.c_int, [vp, u64p, u64p]),
+    "nts_packed_words": (C.c_uint64, [C.c_uint64]),
+    "nts_pack_ascii": (C.c_int, [C.c_char_p, C.c_uint64, u64p, u64p, u64p, C.c_uint64, u64p]),
+    "nts_unpack_ascii": (C.c_int, [u64p, C.c_uint64, C.c_uint64, C.c_char_p]),
+    "nts_genome_upload": (C.c_int, [vp, C.c_uint32, u64p, u64p, u64p, C.c_uint64, u64p, u64p, u64p, vpp]),
+    "nts_genome_destroy": (None, [vp]),
+    "nts_genome_size": (C.c_uint64, [vp]),
+    "nts_genome_contigs": (C.c_uint32, [vp]),
+    "nts_genome_download_contig": (C.c_int, [vp, C.c_uint32, u64p]),
+    "nts_genome_nruns": (C.c_int, [vp, u64p, u64p, u64p, C.c_uint64, u64p]),
+    "nts_bf_bytes": (C.c_uint64, [C.c_int64, C.c_double]),
+    "nts_bf_create": (C.c_int, [vp, C.c_uint64, vpp]),
+    "nts_bf_destroy": (None, [vp]),
+    "nts_bf_size_bytes": (C.c_uint64, [vp]),
+    "nts_bf_clear": (C.c_int, [vp]),
+    "nts_bf_insert_genome": (C.c_int, [vp, vp, C.c_uint32]),
+    "nts_bf_and": (C.c_int, [vp, vp]),
+    "nts_bf_or": (C.c_int, [vp, vp]),
+    "nts_bf_insert_repeats": (C.c_int, [vp, vp, vp, C.c_uint32]),
+    "nts_bf_popcount": (C.c_int, [vp, u64p]),
+    "nts_bf_download": (C.c_int, [vp, u8p]),
+    "nts_bf_upload": (C.c_int, [vp, u8p]),
+    "nts_sketch": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, u64p, u64p, u64p, vpp]),
+    "nts_mxs_destroy": (None, [vp]),
+    "nts_mxs_count": (C.c_uint64, [vp]),
+    "nts_mxs_download": (C.c_int, [vp, u64p, u32p, u32p]),
+    "nts_hash_contig": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u64p, u8p]),
+}
+
+
+def declared_symbols():
+    "every symbol include/ntsynt_b200.h declares (parsed from the header itself)"
+    import re
+    hdr = os.path.join(_HERE, "..", "include", "ntsynt_b200.h")
+    with open(hdr, encoding="utf-8") as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nts_[a-z0-9_]+)\s*\(", text)))
+
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(status):
+    if status != 0:
+        raise NtsError(status, lib.nts_last_error().decode(errors="replace"))
+
+
+def ptr(arr, ctype):
+    "pointer to a contiguous numpy array (or None)"
+    if arr is None:
+        return None
+    return arr.ctypes.data_as(C.POINTER(ctype))

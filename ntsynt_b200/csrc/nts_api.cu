@@ -1,0 +1,731 @@
+// nts_api.cu -- C-ABI of libntsynt_b200.so: context, ingest, Bloom filter and sketch entry points.
+// See include/ntsynt_b200.h for the contract and the reference call sites each entry replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "nts_internal.h"
+#include "nts_kernels.cuh"
+
+namespace nts {
+
+static thread_local std::string g_err;
+
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+static uint64_t srol_n(uint64_t x, unsigned n) { for (unsigned i = 0; i < n; ++i) x = srol(x); return x; }
+
+static void make_hash_tables(uint32_t k, HashTables* t)
+{
+    std::memset(t, 0, sizeof(*t));
+    for (unsigned in = 0; in < 4; ++in)
+        for (unsigned out = 0; out < 4; ++out) {
+            t->roll_f[in * 4 + out] = seed_of(in) ^ srol_n(seed_of(out), k);
+            t->roll_r[in * 4 + out] = seed_of(3 - out) ^ srol_n(seed_of(3 - in), k);
+        }
+    for (unsigned i = 0; i < k; ++i)
+        for (unsigned c = 0; c < 4; ++c) {
+            t->init_f[i * 4 + c] = srol_n(seed_of(c), k - 1 - i);
+            t->init_r[i * 4 + c] = srol_n(seed_of(3 - c), i);
+        }
+}
+
+static int get_tables(nts_ctx* ctx, uint32_t k, const HashTables** out)
+{
+    if (k < 1 || k > MAX_K) return fail(NTS_ERR_ARG, "k must be in [1, 64]");
+    auto it = ctx->tables.find(k);
+    if (it == ctx->tables.end()) {
+        HashTables host;
+        make_hash_tables(k, &host);
+        HashTables* dev = nullptr;
+        NTS_CUDA(cudaMalloc(reinterpret_cast<void**>(&dev), sizeof(HashTables)));
+        NTS_CUDA(cudaMemcpyAsync(dev, &host, sizeof(HashTables), cudaMemcpyHostToDevice, ctx->stream));
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+        it = ctx->tables.emplace(k, dev).first;
+    }
+    *out = it->second;
+    return NTS_OK;
+}
+
+// Build the valid-k-mer islands of a genome for (k, optional mask) and upload them.
+static int build_view(const nts_genome* g, uint32_t k, const uint64_t* mask_off, const uint64_t* mask_start,
+                      const uint64_t* mask_end, nts_view** out)
+{
+    nts_view* v = new (std::nothrow) nts_view();
+    if (!v) return fail(NTS_ERR_NOMEM, "host allocation failed");
+    v->k = k;
+    std::vector<uint64_t> seg_v, seg_base;
+    seg_v.push_back(0);
+    v->contig_v.assign(g->n_contigs + 1, 0);
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < g->n_contigs; ++c) {
+        v->contig_v[c] = total;
+        const uint64_t len = g->contig_len[c];
+        const uint64_t cbase = g->contig_word_off[c] * 32;
+        // merge the contig's N runs and mask intervals (both sorted) into blocked intervals
+        size_t ni = g->nrun_off[c], ne = g->nrun_off[c + 1];
+        size_t mi = mask_off ? mask_off[c] : 0, me = mask_off ? mask_off[c + 1] : 0;
+        uint64_t clean_from = 0;   // start of the current clean stretch
+        auto emit_clean = [&](uint64_t a, uint64_t b) {   // clean bases [a, b)
+            if (b > a && b - a >= k) {
+                uint64_t n = b - a - k + 1;
+                seg_base.push_back(cbase + a);
+                total += n;
+                seg_v.push_back(total);
+            }
+        };
+        while (ni < ne || mi < me) {
+            uint64_t s, e;
+            bool take_n = (mi >= me) || (ni < ne && g->nrun_start[ni] <= mask_start[mi]);
+            if (take_n) { s = g->nrun_start[ni]; e = s + g->nrun_len[ni]; ++ni; }
+            else { s = mask_start[mi]; e = mask_end[mi]; ++mi; }
+            if (e > len) e = len;
+            if (s >= e) continue;
+            if (s > clean_from) emit_clean(clean_from, s);
+            if (e > clean_from) clean_from = e;
+        }
+        if (len > clean_from) emit_clean(clean_from, len);
+    }
+    v->contig_v[g->n_contigs] = total;
+    v->total_valid = total;
+    v->n_seg = (uint32_t)seg_base.size();
+    if (seg_base.size() > 0xFFFFFFF0ull) { delete v; return fail(NTS_ERR_ARG, "too many islands"); }
+    cudaError_t e1 = v->seg_v.alloc(seg_v.size());
+    cudaError_t e2 = v->seg_base.alloc(seg_base.size() ? seg_base.size() : 1);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { delete v; return fail(NTS_ERR_NOMEM, "device allocation failed (view)"); }
+    cudaStream_t st = g->ctx->stream;
+    cudaError_t e = cudaMemcpyAsync(v->seg_v.p, seg_v.data(), seg_v.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && !seg_base.empty())
+        e = cudaMemcpyAsync(v->seg_base.p, seg_base.data(), seg_base.size() * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { delete v; return fail(NTS_ERR_CUDA, std::string("view upload: ") + cudaGetErrorString(e)); }
+    *out = v;
+    return NTS_OK;
+}
+
+static int get_plain_view(const nts_genome* g, uint32_t k, const nts_view** out)
+{
+    nts_genome* gm = const_cast<nts_genome*>(g);
+    auto it = gm->views.find(k);
+    if (it == gm->views.end()) {
+        nts_view* v = nullptr;
+        int rc = build_view(g, k, nullptr, nullptr, nullptr, &v);
+        if (rc) return rc;
+        it = gm->views.emplace(k, v).first;
+    }
+    *out = it->second;
+    return NTS_OK;
+}
+
+static GenomeView device_view(const nts_genome* g, const nts_view* v)
+{
+    GenomeView gv;
+    gv.packed = g->packed.p;
+    gv.seg_v = v->seg_v.p;
+    gv.seg_base = v->seg_base.p;
+    gv.n_seg = v->n_seg;
+    gv.k = v->k;
+    return gv;
+}
+
+static int grid_for(const nts_ctx* ctx, uint64_t items, int threads, int per_sm)
+{
+    uint64_t want = (items + threads - 1) / threads;
+    uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
+    return (int)std::max<uint64_t>(1, std::min(want, cap));
+}
+
+}  // namespace nts
+
+using namespace nts;
+
+extern "C" {
+
+const char* nts_version(void) { return "ntsynt_b200 0.1 (sm_100a; parity target: ntSynt v1.0.4)"; }
+const char* nts_last_error(void) { return g_err.c_str(); }
+
+int nts_device_count(int* out)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *out = 0; return fail(NTS_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *out = n;
+    return NTS_OK;
+}
+
+// ------------------------------------------------------------------------------------ context
+int nts_ctx_create(int device, nts_ctx** out)
+{
+    if (!out) return fail(NTS_ERR_ARG, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(NTS_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(NTS_ERR_ARG, "device index out of range");
+    NTS_CUDA(cudaSetDevice(device));
+    nts_ctx* ctx = new (std::nothrow) nts_ctx();
+    if (!ctx) return fail(NTS_ERR_NOMEM, "host allocation failed");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    NTS_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    NTS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    NTS_CUDA(cudaEventCreate(&ctx->ev0));
+    NTS_CUDA(cudaEventCreate(&ctx->ev1));
+    *out = ctx;
+    return NTS_OK;
+}
+
+void nts_ctx_destroy(nts_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& kv : ctx->tables) cudaFree(kv.second);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int nts_ctx_sync(nts_ctx* ctx)
+{
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+int nts_timer_start(nts_ctx* ctx)
+{
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    NTS_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    return NTS_OK;
+}
+
+int nts_timer_stop(nts_ctx* ctx, float* ms_out)
+{
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    NTS_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    NTS_CUDA(cudaEventSynchronize(ctx->ev1));
+    NTS_CUDA(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    return NTS_OK;
+}
+
+uint64_t nts_launch_count(const nts_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int nts_mem_info(nts_ctx* ctx, uint64_t* free_b, uint64_t* total_b)
+{
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    size_t f = 0, t = 0;
+    NTS_CUDA(cudaMemGetInfo(&f, &t));
+    *free_b = f; *total_b = t;
+    return NTS_OK;
+}
+
+// ------------------------------------------------------------------------------------ ingest (host)
+uint64_t nts_packed_words(uint64_t n_bases) { return ((n_bases + 63) / 64) * 2; }
+
+int nts_pack_ascii(const char* seq, uint64_t n, uint64_t* words_out, uint64_t* nrun_start, uint64_t* nrun_len,
+                   uint64_t nrun_cap, uint64_t* n_nruns)
+{
+    if (!seq || !words_out || !n_nruns) return fail(NTS_ERR_ARG, "null argument");
+    static const auto lut = [] {
+        struct L { uint8_t v[256]; } l;
+        for (int i = 0; i < 256; ++i) l.v[i] = 4;
+        l.v['A'] = l.v['a'] = 0; l.v['C'] = l.v['c'] = 1; l.v['G'] = l.v['g'] = 2; l.v['T'] = l.v['t'] = 3;
+        return l;
+    }();
+    const uint64_t nw = nts_packed_words(n);
+    uint64_t runs = 0;
+    bool in_run = false;
+    uint64_t run_start = 0;
+    for (uint64_t wi = 0; wi < nw; ++wi) {
+        uint64_t word = 0;
+        const uint64_t b0 = wi * 32, b1 = std::min(n, b0 + 32);
+        for (uint64_t b = b0; b < b1; ++b) {
+            uint8_t c = lut.v[(unsigned char)seq[b]];
+            if (c > 3) {
+                if (!in_run) { in_run = true; run_start = b; }
+                c = 0;
+            } else if (in_run) {
+                if (runs < nrun_cap) { nrun_start[runs] = run_start; nrun_len[runs] = b - run_start; }
+                ++runs;
+                in_run = false;
+            }
+            word |= (uint64_t)c << ((b - b0) * 2);
+        }
+        words_out[wi] = word;
+    }
+    if (in_run) {
+        if (runs < nrun_cap) { nrun_start[runs] = run_start; nrun_len[runs] = n - run_start; }
+        ++runs;
+    }
+    *n_nruns = runs;
+    return NTS_OK;
+}
+
+int nts_unpack_ascii(const uint64_t* words, uint64_t start, uint64_t n, char* out)
+{
+    if (!words || !out) return fail(NTS_ERR_ARG, "null argument");
+    static const char acgt[4] = {'A', 'C', 'G', 'T'};
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t b = start + i;
+        out[i] = acgt[(words[b >> 5] >> ((b & 31) * 2)) & 3];
+    }
+    return NTS_OK;
+}
+
+int nts_genome_upload(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const uint64_t* contig_word_off,
+                      const uint64_t* words, uint64_t n_words, const uint64_t* nrun_off, const uint64_t* nrun_start,
+                      const uint64_t* nrun_len, nts_genome** out)
+{
+    if (!ctx || !out || !contig_len || !contig_word_off || !nrun_off) return fail(NTS_ERR_ARG, "null argument");
+    if (n_words && !words) return fail(NTS_ERR_ARG, "words is null");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    nts_genome* g = new (std::nothrow) nts_genome();
+    if (!g) return fail(NTS_ERR_NOMEM, "host allocation failed");
+    g->ctx = ctx;
+    g->n_contigs = n_contigs;
+    g->contig_len.assign(contig_len, contig_len + n_contigs);
+    g->contig_word_off.assign(contig_word_off, contig_word_off + n_contigs);
+    g->n_words = n_words;
+    for (uint32_t c = 0; c < n_contigs; ++c) {
+        g->total_bases += contig_len[c];
+        if (contig_len[c] > 0xFFFFFFF0ull) { delete g; return fail(NTS_ERR_ARG, "contig longer than 2^32 bases"); }
+        if (contig_word_off[c] + nts_packed_words(contig_len[c]) > n_words || (contig_word_off[c] & 1)) {
+            delete g;
+            return fail(NTS_ERR_ARG, "contig_word_off/n_words inconsistent with contig_len (16-byte aligned contigs)");
+        }
+    }
+    g->nrun_off.assign(nrun_off, nrun_off + n_contigs + 1);
+    const uint64_t nr = nrun_off[n_contigs];
+    if (nr) { g->nrun_start.assign(nrun_start, nrun_start + nr); g->nrun_len.assign(nrun_len, nrun_len + nr); }
+    // two guard words so that cursor pre-loads one word past the last base stay in bounds
+    if (g->packed.alloc(n_words + 2) != cudaSuccess) { delete g; return fail(NTS_ERR_NOMEM, "device allocation failed (genome)"); }
+    cudaError_t e = cudaMemsetAsync(g->packed.p + n_words, 0, 16, ctx->stream);
+    if (e == cudaSuccess && n_words)
+        e = cudaMemcpyAsync(g->packed.p, words, n_words * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { delete g; return fail(NTS_ERR_CUDA, std::string("genome upload: ") + cudaGetErrorString(e)); }
+    *out = g;
+    return NTS_OK;
+}
+
+void nts_genome_destroy(nts_genome* g)
+{
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    for (auto& kv : g->views) delete kv.second;
+    delete g;
+}
+
+uint64_t nts_genome_size(const nts_genome* g) { return g ? g->total_bases : 0; }
+uint32_t nts_genome_contigs(const nts_genome* g) { return g ? g->n_contigs : 0; }
+
+int nts_genome_download_contig(nts_genome* g, uint32_t contig, uint64_t* words_out)
+{
+    if (!g || contig >= g->n_contigs || !words_out) return fail(NTS_ERR_ARG, "bad argument");
+    NTS_CUDA(cudaSetDevice(g->ctx->device));
+    NTS_CUDA(cudaMemcpyAsync(words_out, g->packed.p + g->contig_word_off[contig],
+                             nts_packed_words(g->contig_len[contig]) * 8, cudaMemcpyDeviceToHost, g->ctx->stream));
+    NTS_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    return NTS_OK;
+}
+
+int nts_genome_nruns(nts_genome* g, uint64_t* nrun_off, uint64_t* nrun_start, uint64_t* nrun_len, uint64_t cap,
+                     uint64_t* n_out)
+{
+    if (!g || !nrun_off || !n_out) return fail(NTS_ERR_ARG, "bad argument");
+    std::copy(g->nrun_off.begin(), g->nrun_off.end(), nrun_off);
+    *n_out = g->nrun_start.size();
+    uint64_t n = std::min<uint64_t>(cap, g->nrun_start.size());
+    if (n && nrun_start && nrun_len) {
+        std::copy(g->nrun_start.begin(), g->nrun_start.begin() + n, nrun_start);
+        std::copy(g->nrun_len.begin(), g->nrun_len.begin() + n, nrun_len);
+    }
+    return NTS_OK;
+}
+
+// ------------------------------------------------------------------------------------ Bloom filter
+uint64_t nts_bf_bytes(int64_t genome_size, double fpr)
+{
+    // src/ntsynt_make_common_bf.cpp:38-39, then btllib's round-up to whole 64-bit words
+    long long size_bits = (long long)std::ceil(((double)(-1 * (long long)genome_size)) / std::log(1 - fpr));
+    uint64_t bytes = (uint64_t)(size_bits / 8);
+    bytes = (uint64_t)std::ceil((double)bytes / 8.0) * 8;
+    return bytes;
+}
+
+static int bf_fill(nts_bf* bf, uint32_t v)
+{
+    nts_ctx* ctx = bf->ctx;
+    uint64_t n16 = bf->alloc_bytes / 16;
+    fill_u128_kernel<<<grid_for(ctx, n16, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(bf->words.p), n16, v);
+    ctx->launches++;
+    NTS_CUDA(cudaGetLastError());
+    return NTS_OK;
+}
+
+int nts_bf_create(nts_ctx* ctx, uint64_t bytes, nts_bf** out)
+{
+    if (!ctx || !out) return fail(NTS_ERR_ARG, "null argument");
+    if (bytes == 0 || (bytes & 7)) return fail(NTS_ERR_ARG, "Bloom filter size must be a positive multiple of 8 bytes");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    nts_bf* bf = new (std::nothrow) nts_bf();
+    if (!bf) return fail(NTS_ERR_NOMEM, "host allocation failed");
+    bf->ctx = ctx;
+    bf->bytes = bytes;
+    bf->alloc_bytes = (bytes + 15) & ~15ull;
+    if (bf->words.alloc(bf->alloc_bytes / 4) != cudaSuccess) {
+        delete bf;
+        return fail(NTS_ERR_NOMEM, "device allocation failed (Bloom filter of " + std::to_string(bytes) + " bytes)");
+    }
+    int rc = bf_fill(bf, 0);
+    if (rc == NTS_OK) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = fail(NTS_ERR_CUDA, cudaGetErrorString(e)); }
+    if (rc) { delete bf; return rc; }
+    *out = bf;
+    return NTS_OK;
+}
+
+void nts_bf_destroy(nts_bf* bf)
+{
+    if (!bf) return;
+    cudaSetDevice(bf->ctx->device);
+    delete bf;
+}
+
+uint64_t nts_bf_size_bytes(const nts_bf* bf) { return bf ? bf->bytes : 0; }
+
+int nts_bf_clear(nts_bf* bf)
+{
+    if (!bf) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(bf->ctx->device));
+    int rc = bf_fill(bf, 0);
+    if (rc) return rc;
+    NTS_CUDA(cudaStreamSynchronize(bf->ctx->stream));
+    return NTS_OK;
+}
+
+static int mod_params(const nts_bf* bf, uint64_t* m, uint64_t* mprime)
+{
+    *m = bf->bytes * 8;
+    *mprime = 0xFFFFFFFFFFFFFFFFull / *m;
+    return NTS_OK;
+}
+
+int nts_bf_insert_genome_async(nts_bf* bf, const nts_genome* g, uint32_t k)
+{
+    if (!bf || !g) return fail(NTS_ERR_ARG, "null argument");
+    if (bf->ctx != g->ctx) return fail(NTS_ERR_ARG, "filter and genome live on different contexts");
+    nts_ctx* ctx = bf->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    const HashTables* tabs = nullptr;
+    int rc = get_tables(ctx, k, &tabs);
+    if (rc) return rc;
+    const nts_view* v = nullptr;
+    rc = get_plain_view(g, k, &v);
+    if (rc) return rc;
+    if (v->total_valid == 0) return NTS_OK;
+    uint64_t m, mp;
+    mod_params(bf, &m, &mp);
+    constexpr int THREADS = 256;
+    const uint32_t chunk = 32;
+    uint64_t blocks = (v->total_valid + (uint64_t)THREADS * chunk - 1) / ((uint64_t)THREADS * chunk);
+    if (blocks > 0x7FFFFFFFull) return fail(NTS_ERR_ARG, "genome too large for one launch");
+    bf_insert_kernel<THREADS><<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(device_view(g, v), tabs, bf->words.p, m, mp,
+                                                                            v->total_valid, chunk);
+    ctx->launches++;
+    NTS_CUDA(cudaGetLastError());
+    return NTS_OK;
+}
+
+int nts_bf_insert_genome(nts_bf* bf, const nts_genome* g, uint32_t k)
+{
+    int rc = nts_bf_insert_genome_async(bf, g, k);
+    if (rc) return rc;
+    NTS_CUDA(cudaStreamSynchronize(bf->ctx->stream));
+    return NTS_OK;
+}
+
+static int bf_combine(nts_bf* dst, const nts_bf* src, int op, bool sync)
+{
+    if (!dst || !src) return fail(NTS_ERR_ARG, "null argument");
+    if (dst->bytes != src->bytes) return fail(NTS_ERR_ARG, "Bloom filters differ in size");
+    if (dst->ctx != src->ctx) return fail(NTS_ERR_ARG, "filters live on different contexts");
+    nts_ctx* ctx = dst->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    uint64_t n16 = dst->alloc_bytes / 16;
+    bf_combine_kernel<<<grid_for(ctx, n16 / 4 + 1, 256, 16), 256, 0, ctx->stream>>>(
+        reinterpret_cast<uint4*>(dst->words.p), reinterpret_cast<const uint4*>(src->words.p), n16, op);
+    ctx->launches++;
+    NTS_CUDA(cudaGetLastError());
+    if (sync) NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+int nts_bf_and(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 0, true); }
+int nts_bf_or(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 1, true); }
+int nts_bf_and_async(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 0, false); }
+
+int nts_bf_insert_repeats(nts_bf* rep, nts_bf* scratch, const nts_genome* g, uint32_t k)
+{
+    if (!rep || !scratch || !g) return fail(NTS_ERR_ARG, "null argument");
+    if (rep->bytes != scratch->bytes) return fail(NTS_ERR_ARG, "Bloom filters differ in size");
+    nts_ctx* ctx = rep->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    int rc = bf_fill(scratch, 0);
+    if (rc) return rc;
+    const HashTables* tabs = nullptr;
+    rc = get_tables(ctx, k, &tabs);
+    if (rc) return rc;
+    const nts_view* v = nullptr;
+    rc = get_plain_view(g, k, &v);
+    if (rc) return rc;
+    if (v->total_valid) {
+        uint64_t m, mp;
+        mod_params(rep, &m, &mp);
+        constexpr int THREADS = 256;
+        const uint32_t chunk = 32;
+        uint64_t blocks = (v->total_valid + (uint64_t)THREADS * chunk - 1) / ((uint64_t)THREADS * chunk);
+        bf_repeat_kernel<THREADS><<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(
+            device_view(g, v), tabs, scratch->words.p, rep->words.p, m, mp, v->total_valid, chunk);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+    }
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+int nts_bf_popcount(nts_bf* bf, uint64_t* bits_set)
+{
+    if (!bf || !bits_set) return fail(NTS_ERR_ARG, "null argument");
+    nts_ctx* ctx = bf->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<unsigned long long> acc;
+    if (acc.alloc(1) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed");
+    NTS_CUDA(cudaMemsetAsync(acc.p, 0, 8, ctx->stream));
+    uint64_t n16 = bf->alloc_bytes / 16;
+    bf_popcount_kernel<<<grid_for(ctx, n16, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(bf->words.p),
+                                                                            n16, acc.p);
+    ctx->launches++;
+    NTS_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    NTS_CUDA(cudaMemcpyAsync(&h, acc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *bits_set = h;
+    return NTS_OK;
+}
+
+int nts_bf_download(nts_bf* bf, uint8_t* bytes_out)
+{
+    if (!bf || !bytes_out) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(bf->ctx->device));
+    NTS_CUDA(cudaMemcpyAsync(bytes_out, bf->words.p, bf->bytes, cudaMemcpyDeviceToHost, bf->ctx->stream));
+    NTS_CUDA(cudaStreamSynchronize(bf->ctx->stream));
+    return NTS_OK;
+}
+
+int nts_bf_upload(nts_bf* bf, const uint8_t* bytes_in)
+{
+    if (!bf || !bytes_in) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(bf->ctx->device));
+    NTS_CUDA(cudaMemcpyAsync(bf->words.p, bytes_in, bf->bytes, cudaMemcpyHostToDevice, bf->ctx->stream));
+    NTS_CUDA(cudaStreamSynchronize(bf->ctx->stream));
+    return NTS_OK;
+}
+
+// ------------------------------------------------------------------------------------ sketch
+static size_t sketch_smem_bytes(uint32_t NT, int threads)
+{
+    size_t idx = (size_t)((NT + 3) & ~3u) * 2;
+    return (size_t)NT * 8 + 2 * idx + sizeof(HashTables) + (size_t)(threads / 32) * sizeof(SegAgg) +
+           (size_t)(threads / 32 + 2) * 4;
+}
+
+int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nts_bf* repeat, uint32_t k, uint32_t w,
+               const uint64_t* mask_off, const uint64_t* mask_start, const uint64_t* mask_end, nts_mxs** out)
+{
+    if (!ctx || !g || !out) return fail(NTS_ERR_ARG, "null argument");
+    if (g->ctx != ctx || (common && common->ctx != ctx) || (repeat && repeat->ctx != ctx))
+        return fail(NTS_ERR_ARG, "objects live on different contexts");
+    if (common && repeat && common->bytes != repeat->bytes) return fail(NTS_ERR_ARG, "common and repeat filters differ in size");
+    if (w < 1) return fail(NTS_ERR_ARG, "w must be >= 1");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    constexpr int THREADS = 512;
+    // slots per tile: as many as fit two CTAs per SM; wide windows fall back to one CTA per SM
+    int max_optin = 0;
+    NTS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    uint32_t NT = 8960;
+    if (w > 4096) NT = 18432;
+    if (2ull * w > NT || sketch_smem_bytes(NT, THREADS) > (size_t)max_optin)
+        return fail(NTS_ERR_ARG, "w too large for the shared-memory window selector (max 9216)");
+    const uint32_t T = NT - w;
+
+    const HashTables* tabs = nullptr;
+    int rc = get_tables(ctx, k, &tabs);
+    if (rc) return rc;
+    const nts_view* v = nullptr;
+    nts_view* owned = nullptr;
+    if (mask_off) {
+        rc = build_view(g, k, mask_off, mask_start, mask_end, &owned);
+        if (rc) return rc;
+        v = owned;
+    } else {
+        rc = get_plain_view(g, k, &v);
+        if (rc) return rc;
+    }
+    struct ViewGuard { nts_view* p; ~ViewGuard() { delete p; } } guard{owned};
+
+    // tiles
+    std::vector<TileDesc> tiles;
+    for (uint32_t c = 0; c < g->n_contigs; ++c) {
+        const uint64_t v0 = v->contig_v[c], v1 = v->contig_v[c + 1];
+        const uint64_t nv = v1 - v0;
+        if (nv < w) continue;
+        const uint64_t n_win = nv - w + 1;
+        for (uint64_t t = 0; t * T < n_win; ++t) {
+            TileDesc td;
+            td.vfirst = v0 + t * T;
+            td.vend = v1;
+            td.cbase = g->contig_word_off[c] * 32;
+            td.contig = c;
+            td.has_prev = t > 0;
+            tiles.push_back(td);
+        }
+    }
+    nts_mxs* mx = new (std::nothrow) nts_mxs();
+    if (!mx) return fail(NTS_ERR_NOMEM, "host allocation failed");
+    mx->ctx = ctx;
+    mx->n_contigs = g->n_contigs;
+    struct MxGuard { nts_mxs* p; ~MxGuard() { delete p; } } mguard{mx};
+    if (tiles.empty()) {
+        mx->count = 0;
+        *out = mx; mguard.p = nullptr;
+        return NTS_OK;
+    }
+    const uint32_t n_tiles = (uint32_t)tiles.size();
+    DevBuf<TileDesc> d_tiles;
+    DevBuf<uint32_t> d_off, d_cnt;
+    DevBuf<uint64_t> d_dst;
+    DevBuf<unsigned long long> d_total;
+    if (d_tiles.alloc(n_tiles) != cudaSuccess || d_off.alloc(n_tiles) != cudaSuccess || d_cnt.alloc(n_tiles) != cudaSuccess ||
+        d_dst.alloc(n_tiles) != cudaSuccess || d_total.alloc(1) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (tiles)");
+    NTS_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, ctx->stream));
+
+    uint64_t m = 0, mp = 0;
+    if (common) mod_params(common, &m, &mp); else if (repeat) mod_params(repeat, &m, &mp);
+
+    const size_t smem = sketch_smem_bytes(NT, THREADS);
+    NTS_CUDA(cudaFuncSetAttribute(sketch_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    // expected density of minimizers is 2/(w+1) per window; start with 2.5x that
+    uint64_t n_win_total = 0;
+    for (uint32_t c = 0; c < g->n_contigs; ++c) {
+        uint64_t nv = v->contig_v[c + 1] - v->contig_v[c];
+        if (nv >= w) n_win_total += nv - w + 1;
+    }
+    uint64_t cap = (uint64_t)(5.0 * (double)n_win_total / (double)(w + 1)) + 4096 + n_tiles;
+    cap = std::min<uint64_t>(cap, n_win_total);
+    DevBuf<uint64_t> u_h1;
+    DevBuf<uint32_t> u_pos, u_ctg;
+    unsigned long long total = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (cap > 0xFFFFFFF0ull) return fail(NTS_ERR_OVERFLOW, "more than 2^32 minimizers in one sketch");
+        if (u_h1.alloc(cap) != cudaSuccess || u_pos.alloc(cap) != cudaSuccess || u_ctg.alloc(cap) != cudaSuccess)
+            return fail(NTS_ERR_NOMEM, "device allocation failed (minimizer buffer)");
+        NTS_CUDA(cudaMemsetAsync(d_total.p, 0, 8, ctx->stream));
+        SketchOut so;
+        so.h1 = u_h1.p; so.pos = u_pos.p; so.contig = u_ctg.p;
+        so.tile_off = d_off.p; so.tile_cnt = d_cnt.p; so.total = d_total.p; so.cap = cap;
+        sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(
+            device_view(g, v), tabs, common ? common->words.p : nullptr, repeat ? repeat->words.p : nullptr, m, mp,
+            d_tiles.p, w, T, so);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+        NTS_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (total <= cap) break;
+        if (attempt == 1) return fail(NTS_ERR_OVERFLOW, "minimizer buffer overflow after retry");
+        cap = total;
+    }
+    mx->count = total;
+    if (mx->h1.alloc(total) != cudaSuccess || mx->pos.alloc(total) != cudaSuccess || mx->contig.alloc(total) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (minimizer table)");
+    tile_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt.p, d_dst.p, n_tiles);
+    ctx->launches++;
+    NTS_CUDA(cudaGetLastError());
+    {
+        uint64_t threads_needed = (uint64_t)n_tiles * 32;
+        unsigned blocks = (unsigned)((threads_needed + 255) / 256);
+        sketch_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(u_h1.p, u_pos.p, u_ctg.p, d_off.p, d_cnt.p, d_dst.p, n_tiles,
+                                                             mx->h1.p, mx->pos.p, mx->contig.p);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+    }
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = mx; mguard.p = nullptr;
+    return NTS_OK;
+}
+
+void nts_mxs_destroy(nts_mxs* m)
+{
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    delete m;
+}
+
+uint64_t nts_mxs_count(const nts_mxs* m) { return m ? m->count : 0; }
+
+int nts_mxs_download(nts_mxs* m, uint64_t* h1, uint32_t* pos, uint32_t* contig)
+{
+    if (!m) return fail(NTS_ERR_ARG, "null argument");
+    if (m->count == 0) return NTS_OK;
+    NTS_CUDA(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    if (h1) NTS_CUDA(cudaMemcpyAsync(h1, m->h1.p, m->count * 8, cudaMemcpyDeviceToHost, st));
+    if (pos) NTS_CUDA(cudaMemcpyAsync(pos, m->pos.p, m->count * 4, cudaMemcpyDeviceToHost, st));
+    if (contig) NTS_CUDA(cudaMemcpyAsync(contig, m->contig.p, m->count * 4, cudaMemcpyDeviceToHost, st));
+    NTS_CUDA(cudaStreamSynchronize(st));
+    return NTS_OK;
+}
+
+int nts_hash_contig(nts_ctx* ctx, const nts_genome* g, uint32_t contig, uint32_t k, uint64_t* h0_out, uint8_t* valid_out)
+{
+    if (!ctx || !g || contig >= g->n_contigs || !h0_out || !valid_out) return fail(NTS_ERR_ARG, "bad argument");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    const HashTables* tabs = nullptr;
+    int rc = get_tables(ctx, k, &tabs);
+    if (rc) return rc;
+    const nts_view* v = nullptr;
+    rc = get_plain_view(g, k, &v);
+    if (rc) return rc;
+    const uint64_t len = g->contig_len[contig];
+    const uint64_t nk = len >= k ? len - k + 1 : 0;
+    if (nk == 0) return NTS_OK;
+    DevBuf<uint64_t> d_h;
+    DevBuf<uint8_t> d_v;
+    if (d_h.alloc(nk) != cudaSuccess || d_v.alloc(nk) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed");
+    NTS_CUDA(cudaMemsetAsync(d_h.p, 0, nk * 8, ctx->stream));
+    NTS_CUDA(cudaMemsetAsync(d_v.p, 0, nk, ctx->stream));
+    const uint64_t v0 = v->contig_v[contig], v1 = v->contig_v[contig + 1];
+    if (v1 > v0) {
+        constexpr int THREADS = 256;
+        const uint32_t chunk = 32;
+        uint64_t blocks = (v1 - v0 + (uint64_t)THREADS * chunk - 1) / ((uint64_t)THREADS * chunk);
+        hash_dump_kernel<THREADS><<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(
+            device_view(g, v), tabs, v0, v1, g->contig_word_off[contig] * 32, d_h.p, d_v.p, chunk);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+    }
+    NTS_CUDA(cudaMemcpyAsync(h0_out, d_h.p, nk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NTS_CUDA(cudaMemcpyAsync(valid_out, d_v.p, nk, cudaMemcpyDeviceToHost, ctx->stream));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,448 @@
+// nts_kernels.cuh -- the sm_100a kernels of the sketch / Bloom-filter half of the path.
+//
+//   (i)     ntHash2 over 2-bit packed contigs           -> hash_run() in nts_device.cuh
+//   (ii)    sliding-window rightmost-minimum selector   -> sketch_kernel (van Herk / Gil-Werman
+//           prefix+suffix arg-min over blocks of w keys staged in shared memory, segmented
+//           scans done with warp shuffles), replacing btllib::Indexlr::minimize
+//   (iii-a) Bloom insert                                -> bf_insert_kernel (RED.OR per k-mer)
+//   (iii-b) Bloom merge                                 -> bf_and_kernel (128-bit streaming)
+//   (iii-c) Bloom query                                 -> fused into sketch_kernel phase A2
+//   (iii-d) repeat filter                               -> bf_repeat_kernel
+// All of it is HBM-bound integer work: no tensor cores.
+#pragma once
+#include "nts_device.cuh"
+
+namespace nts {
+
+// ------------------------------------------------------------------------------ streaming helpers
+__global__ void fill_u128_kernel(uint4* __restrict__ p, uint64_t n16, uint32_t v)
+{
+    const uint4 val = make_uint4(v, v, v, v);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = val;
+}
+
+// op: 0 = AND, 1 = OR
+__global__ void bf_combine_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, uint64_t n16, int op)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // 4 independent 128-bit loads per operand in flight per thread
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        uint4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = dst[i + u * stride]; b[u] = __ldg(&src[i + u * stride]); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint4 r;
+            if (op == 0) r = make_uint4(a[u].x & b[u].x, a[u].y & b[u].y, a[u].z & b[u].z, a[u].w & b[u].w);
+            else         r = make_uint4(a[u].x | b[u].x, a[u].y | b[u].y, a[u].z | b[u].z, a[u].w | b[u].w);
+            dst[i + u * stride] = r;
+        }
+    }
+    for (; i < n16; i += stride) {
+        uint4 a = dst[i], b = __ldg(&src[i]);
+        dst[i] = op == 0 ? make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w)
+                         : make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
+    }
+}
+
+__global__ void bf_popcount_kernel(const uint4* __restrict__ p, uint64_t n16, unsigned long long* __restrict__ out)
+{
+    unsigned long long c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 a = __ldg(&p[i]);
+        c += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w);
+    }
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+__device__ __forceinline__ void stage_tables(HashTables* s_tabs, const HashTables* __restrict__ g_tabs, uint32_t k)
+{
+    // roll tables (32 words) + the first k rows of the init tables
+    for (uint32_t i = threadIdx.x; i < 16; i += blockDim.x) {
+        s_tabs->roll_f[i] = g_tabs->roll_f[i];
+        s_tabs->roll_r[i] = g_tabs->roll_r[i];
+    }
+    for (uint32_t i = threadIdx.x; i < k * 4; i += blockDim.x) {
+        s_tabs->init_f[i] = g_tabs->init_f[i];
+        s_tabs->init_r[i] = g_tabs->init_r[i];
+    }
+}
+
+// ------------------------------------------------------------------------------ (i)+(iii-a) insert
+// Each thread hashes `chunk` consecutive valid k-mers and sets bit (h0 mod m) with a
+// fire-and-forget RED.OR on the 32-bit word (byte = idx>>3, bit = idx&7 in little-endian words).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) bf_insert_kernel(GenomeView g, const HashTables* __restrict__ g_tabs,
+                                                             uint32_t* __restrict__ bits, uint64_t m, uint64_t mprime,
+                                                             uint64_t total_valid, uint32_t chunk)
+{
+    __shared__ HashTables s_tabs;
+    stage_tables(&s_tabs, g_tabs, g.k);
+    __syncthreads();
+    uint64_t v0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) * chunk;
+    if (v0 >= total_valid) return;
+    uint32_t cnt = (uint32_t)min((uint64_t)chunk, total_valid - v0);
+    hash_run(g, &s_tabs, v0, cnt, [&](uint32_t, uint64_t h0, uint64_t) {
+        uint64_t idx = fast_mod(h0, m, mprime);
+        atomicOr(&bits[idx >> 5], 1u << (idx & 31));
+    });
+}
+
+// (iii-d) repeat filter: first sighting sets the genome's bit, later sightings set the repeat bit
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) bf_repeat_kernel(GenomeView g, const HashTables* __restrict__ g_tabs,
+                                                             uint32_t* __restrict__ seen, uint32_t* __restrict__ rep,
+                                                             uint64_t m, uint64_t mprime, uint64_t total_valid,
+                                                             uint32_t chunk)
+{
+    __shared__ HashTables s_tabs;
+    stage_tables(&s_tabs, g_tabs, g.k);
+    __syncthreads();
+    uint64_t v0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) * chunk;
+    if (v0 >= total_valid) return;
+    uint32_t cnt = (uint32_t)min((uint64_t)chunk, total_valid - v0);
+    hash_run(g, &s_tabs, v0, cnt, [&](uint32_t, uint64_t h0, uint64_t) {
+        uint64_t idx = fast_mod(h0, m, mprime);
+        uint32_t bit = 1u << (idx & 31);
+        uint32_t old = atomicOr(&seen[idx >> 5], bit);
+        if (old & bit) atomicOr(&rep[idx >> 5], bit);
+    });
+}
+
+// test hook for kernel (i): h0 of every valid k-mer of one contig, scattered to position space
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) hash_dump_kernel(GenomeView g, const HashTables* __restrict__ g_tabs,
+                                                             uint64_t v_begin, uint64_t v_end, uint64_t contig_base,
+                                                             uint64_t* __restrict__ h0_out,
+                                                             uint8_t* __restrict__ valid_out, uint32_t chunk)
+{
+    __shared__ HashTables s_tabs;
+    stage_tables(&s_tabs, g_tabs, g.k);
+    __syncthreads();
+    uint64_t v0 = v_begin + ((uint64_t)blockIdx.x * THREADS + threadIdx.x) * chunk;
+    if (v0 >= v_end) return;
+    uint32_t cnt = (uint32_t)min((uint64_t)chunk, v_end - v0);
+    hash_run(g, &s_tabs, v0, cnt, [&](uint32_t, uint64_t h0, uint64_t b) {
+        h0_out[b - contig_base] = h0;
+        valid_out[b - contig_base] = 1;
+    });
+}
+
+// ------------------------------------------------------------------------------ (ii) sketch
+// One tile = T window ends of one contig, in valid-index space.  Local slot i holds the key of
+// valid index vfirst - 1 + i;  slots [0, T + w).  Windows (of w slots) ending at slots
+// [w, n_end) are owned; the window ending at slot w-1 only supplies "the previous minimum".
+struct TileDesc {
+    uint64_t vfirst;     // global valid index of slot 1
+    uint64_t vend;       // global valid index one past the contig's last valid k-mer
+    uint64_t cbase;      // global base index of the contig's first base
+    uint32_t contig;
+    uint32_t has_prev;   // 0 for the first tile of a contig (slot 0 is a dummy)
+};
+
+struct SketchOut {
+    uint64_t* h1;
+    uint32_t* pos;
+    uint32_t* contig;
+    uint32_t* tile_off;            // [n_tiles] where the tile's run starts in the unordered buffer
+    uint32_t* tile_cnt;            // [n_tiles]
+    unsigned long long* total;     // running total (also the overflow detector)
+    uint64_t cap;
+};
+
+struct KeyIdx { uint64_t key; uint32_t idx; };
+
+// rightmost arg-min: `r` lies to the right of `l`
+__device__ __forceinline__ KeyIdx take_right_if_le(KeyIdx l, KeyIdx r) { return (r.key <= l.key) ? r : l; }
+
+// flag bit0: a block boundary closes this aggregate (nothing flows in from `prev`);
+// flag bit1: the aggregate holds a value (empty chunks past the tile end do not)
+struct SegAgg { uint64_t key; uint32_t idx; uint32_t flag; };
+constexpr uint32_t SEG_CLOSED = 1u, SEG_VALID = 2u;
+
+// inclusive segmented scan across the CTA; dir = +1: left-to-right (carry from lower tids),
+// dir = -1: right-to-left (carry from higher tids).  combine(carry, own) semantics are passed in.
+template <int THREADS, bool LEFT_TO_RIGHT>
+__device__ __forceinline__ SegAgg cta_exclusive_carry(SegAgg own, SegAgg* s_warp /*[THREADS/32]*/)
+{
+    constexpr int NW = THREADS / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // logical lane order: for the right-to-left scan mirror the lanes / warps
+    const int llane = LEFT_TO_RIGHT ? lane : 31 - lane;
+    const int lwid = LEFT_TO_RIGHT ? wid : NW - 1 - wid;
+    auto comb = [](SegAgg prev, SegAgg cur) {  // prev precedes cur in scan order
+        SegAgg r = cur;
+        if (!(cur.flag & SEG_CLOSED) && (prev.flag & SEG_VALID)) {
+            bool take_prev;
+            if (!(cur.flag & SEG_VALID)) take_prev = true;
+            else if (LEFT_TO_RIGHT) take_prev = !(cur.key <= prev.key);   // cur is to the right: wins ties
+            else                    take_prev = (prev.key <= cur.key);    // prev is to the right: wins ties
+            if (take_prev) { r.key = prev.key; r.idx = prev.idx; }
+        }
+        r.flag = cur.flag | prev.flag;
+        return r;
+    };
+    SegAgg inc = own;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        SegAgg o;
+        int src = LEFT_TO_RIGHT ? lane - d : lane + d;
+        o.key = __shfl_sync(0xffffffffu, inc.key, src & 31);
+        o.idx = __shfl_sync(0xffffffffu, inc.idx, src & 31);
+        o.flag = __shfl_sync(0xffffffffu, inc.flag, src & 31);
+        if (llane >= d) inc = comb(o, inc);
+    }
+    if (llane == 31) s_warp[lwid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        SegAgg wv;
+        if (lane < NW) wv = s_warp[lane]; else { wv.key = KEY_MAX; wv.idx = 0xFFFFFFFFu; wv.flag = 0; }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            SegAgg o;
+            o.key = __shfl_up_sync(0xffffffffu, wv.key, d);
+            o.idx = __shfl_up_sync(0xffffffffu, wv.idx, d);
+            o.flag = __shfl_up_sync(0xffffffffu, wv.flag, d);
+            if (lane >= d && lane < NW) wv = comb(o, wv);
+        }
+        if (lane < NW) s_warp[lane] = wv;
+    }
+    __syncthreads();
+    // exclusive value for this thread
+    SegAgg ex;
+    {
+        int src = LEFT_TO_RIGHT ? lane - 1 : lane + 1;
+        ex.key = __shfl_sync(0xffffffffu, inc.key, src & 31);
+        ex.idx = __shfl_sync(0xffffffffu, inc.idx, src & 31);
+        ex.flag = __shfl_sync(0xffffffffu, inc.flag, src & 31);
+    }
+    const bool have_lane = llane > 0, have_warp = lwid > 0;
+    SegAgg res; res.key = KEY_MAX; res.idx = 0xFFFFFFFFu; res.flag = 0;  // flag without SEG_VALID: "no carry"
+    if (have_lane && have_warp) res = comb(s_warp[lwid - 1], ex);
+    else if (have_lane) res = ex;
+    else if (have_warp) res = s_warp[lwid - 1];
+    __syncthreads();   // s_warp is reused by the caller
+    return res;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
+sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
+              const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, const TileDesc* __restrict__ tiles,
+              uint32_t w, uint32_t T, SketchOut out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t NT = T + w;
+    const uint32_t C = (NT + THREADS - 1) / THREADS;   // slots per thread (contiguous)
+    uint64_t* s_key = reinterpret_cast<uint64_t*>(smem_raw);
+    uint16_t* s_P = reinterpret_cast<uint16_t*>(s_key + NT);
+    uint16_t* s_S = s_P + ((NT + 3) & ~3u);
+    HashTables* s_tabs = reinterpret_cast<HashTables*>(s_S + ((NT + 3) & ~3u));
+    SegAgg* s_warp = reinterpret_cast<SegAgg*>(s_tabs + 1);
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_warp + THREADS / 32);   // [THREADS/32 + 2]
+
+    const TileDesc td = tiles[blockIdx.x];
+    stage_tables(s_tabs, g_tabs, g.k);
+    __syncthreads();
+
+    const uint64_t vbase = td.vfirst - 1;                         // valid index of slot 0 (may be "-1")
+    const uint32_t i_lo = td.has_prev ? 0u : 1u;
+    const uint64_t avail = td.vend - td.vfirst + 1;               // slots 0..avail-1 map below vend
+    const uint32_t n_end = (uint32_t)min((uint64_t)NT, avail);    // slots [i_lo, n_end) are real
+
+    // ---- phase A1: hash (kernel i).  thread t owns slots [t*C, t*C + C)
+    const uint32_t c0 = threadIdx.x * C;
+    {
+        uint32_t a = max(c0, i_lo), b = min(c0 + C, n_end);
+        for (uint32_t i = c0; i < min(c0 + C, NT); ++i)
+            if (i < a || i >= b) s_key[i] = KEY_MAX;
+        if (a < b)
+            hash_run(g, s_tabs, vbase + a, b - a, [&](uint32_t j, uint64_t h0, uint64_t) { s_key[a + j] = h0; });
+    }
+    __syncthreads();
+
+    // ---- phase A2: Bloom query (kernel iii-c), 8 independent sector loads in flight per thread
+    if (common != nullptr || repeat != nullptr) {
+        for (uint32_t i0 = threadIdx.x; i0 < n_end; i0 += THREADS * 8) {
+            uint64_t h[8];
+            uint32_t cw[8], rw[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                uint32_t i = i0 + u * THREADS;
+                h[u] = (i < n_end) ? s_key[i] : 0;
+                uint64_t idx = fast_mod(h[u], m, mprime);
+                cw[u] = 0xFFFFFFFFu; rw[u] = 0;
+                if (i < n_end && i >= i_lo) {
+                    if (common) cw[u] = __ldg(&common[idx >> 5]) >> (idx & 31);
+                    if (repeat) rw[u] = __ldg(&repeat[idx >> 5]) >> (idx & 31);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                uint32_t i = i0 + u * THREADS;
+                if (i < n_end && i >= i_lo && (!(cw[u] & 1u) || (rw[u] & 1u))) s_key[i] = KEY_MAX;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase B: van Herk / Gil-Werman over blocks of w slots: [b*w, (b+1)*w)
+    const uint32_t hi = min(c0 + C, NT);
+    // suffix arg-min S[i] over [i, end of i's block]; rightmost wins ties
+    {
+        KeyIdx run; run.key = KEY_MAX; run.idx = 0xFFFFFFFFu;
+        uint32_t closed = 0;
+        for (uint32_t i = hi; i-- > c0;) {          // local right-to-left pass
+            KeyIdx cur; cur.key = s_key[i]; cur.idx = i;
+            if ((i + 1) % w == 0) { closed = 1; run = cur; }          // i is the last slot of its block
+            else if (run.idx == 0xFFFFFFFFu) run = cur;
+            else if (cur.key < run.key) run = cur;                    // run lies to the right: wins ties
+            s_S[i] = (uint16_t)run.idx;
+        }
+        // handed to the threads on the LEFT: arg-min over [c0, first block end in the chunk | chunk end]
+        SegAgg own; own.key = KEY_MAX; own.idx = 0xFFFFFFFFu; own.flag = 0;
+        if (c0 < hi) { own.idx = s_S[c0]; own.key = s_key[own.idx]; own.flag = SEG_VALID | (closed ? SEG_CLOSED : 0u); }
+        SegAgg carry = cta_exclusive_carry<THREADS, false>(own, s_warp);
+        // the carry (arg-min of what lies to the right, up to the block end) reaches the slots after the
+        // last block end inside this chunk
+        if (c0 < hi && (carry.flag & SEG_VALID)) {
+            for (uint32_t i = hi; i-- > c0;) {
+                if ((i + 1) % w == 0) break;
+                if (carry.key <= s_key[s_S[i]]) s_S[i] = (uint16_t)carry.idx;   // carry is to the right: wins ties
+            }
+        }
+    }
+    // prefix arg-min P[i] over [start of i's block, i]; rightmost wins ties
+    {
+        KeyIdx run; run.key = KEY_MAX; run.idx = 0xFFFFFFFFu;
+        uint32_t closed = 0;
+        for (uint32_t i = c0; i < hi; ++i) {        // local left-to-right pass
+            KeyIdx cur; cur.key = s_key[i]; cur.idx = i;
+            if (i % w == 0) { closed = 1; run = cur; }                // i is the first slot of its block
+            else if (run.idx == 0xFFFFFFFFu) run = cur;
+            else if (cur.key <= run.key) run = cur;                   // cur lies to the right: wins ties
+            s_P[i] = (uint16_t)run.idx;
+        }
+        // handed to the threads on the RIGHT: arg-min over [last block start in the chunk | c0, chunk end]
+        SegAgg own; own.key = KEY_MAX; own.idx = 0xFFFFFFFFu; own.flag = 0;
+        if (c0 < hi) { own.idx = s_P[hi - 1]; own.key = s_key[own.idx]; own.flag = SEG_VALID | (closed ? SEG_CLOSED : 0u); }
+        SegAgg carry = cta_exclusive_carry<THREADS, true>(own, s_warp);
+        if (c0 < hi && (carry.flag & SEG_VALID)) {
+            for (uint32_t i = c0; i < hi; ++i) {
+                if (i % w == 0) break;
+                if (carry.key < s_key[s_P[i]]) s_P[i] = (uint16_t)carry.idx;    // carry is to the left: loses ties
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: window minima, change detection, ordered compaction
+    // window ending at slot i covers [i-w+1, i]
+    auto win_min = [&](uint32_t i) -> uint32_t {
+        uint32_t p = s_P[i];
+        if ((i + 1) % w == 0) return p;                 // the window is exactly one block
+        uint32_t s = s_S[i + 1 - w];
+        return (s_key[p] <= s_key[s]) ? p : s;          // p lies to the right: wins ties
+    };
+    // owned window ends: slots [w, n_end); thread t takes a contiguous share
+    const uint32_t n_own = n_end > w ? n_end - w : 0;
+    const uint32_t per = (n_own + THREADS - 1) / THREADS;
+    const uint32_t o0 = w + threadIdx.x * per, o1 = min(o0 + per, n_end);
+    uint32_t cnt = 0;
+    if (o0 < o1) {
+        uint32_t prev = (o0 == w && !td.has_prev) ? 0xFFFFFFFFu : win_min(o0 - 1);
+        for (uint32_t i = o0; i < o1; ++i) {
+            uint32_t a = win_min(i);
+            if (a != prev && s_key[a] != KEY_MAX) ++cnt;
+            prev = a;
+        }
+    }
+    // CTA exclusive scan of cnt
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_misc[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = lane < THREADS / 32 ? s_misc[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += o;
+        }
+        if (lane < THREADS / 32) s_misc[lane] = v;
+        if (lane == THREADS / 32 - 1) {
+            // one allocation per tile in the unordered buffer
+            unsigned long long base = atomicAdd(out.total, (unsigned long long)v);
+            s_misc[THREADS / 32] = (base + v <= out.cap) ? (uint32_t)base : 0xFFFFFFFFu;
+            out.tile_off[blockIdx.x] = (uint32_t)base;
+            out.tile_cnt[blockIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    const uint32_t tile_base = s_misc[THREADS / 32];
+    if (tile_base == 0xFFFFFFFFu || cnt == 0) return;   // overflow: host re-runs with a larger buffer
+    uint32_t off = tile_base + (incl - cnt) + (wid ? s_misc[wid - 1] : 0);
+    {
+        uint32_t prev = (o0 == w && !td.has_prev) ? 0xFFFFFFFFu : win_min(o0 - 1);
+        for (uint32_t i = o0; i < o1; ++i) {
+            uint32_t a = win_min(i);
+            if (a != prev && s_key[a] != KEY_MAX) {
+                uint64_t b = valid_to_base(g, vbase + a);
+                out.h1[off] = ext_hash(s_key[a], 1, g.k);
+                out.pos[off] = (uint32_t)(b - td.cbase);
+                out.contig[off] = td.contig;
+                ++off;
+            }
+            prev = a;
+        }
+    }
+}
+
+// stitch the per-tile runs of the unordered buffer into tile order
+__global__ void sketch_gather_kernel(const uint64_t* __restrict__ h1_in, const uint32_t* __restrict__ pos_in,
+                                     const uint32_t* __restrict__ ctg_in, const uint32_t* __restrict__ tile_off,
+                                     const uint32_t* __restrict__ tile_cnt, const uint64_t* __restrict__ tile_dst,
+                                     uint32_t n_tiles, uint64_t* __restrict__ h1_out, uint32_t* __restrict__ pos_out,
+                                     uint32_t* __restrict__ ctg_out)
+{
+    // one warp per tile
+    uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t src = tile_off[t], n = tile_cnt[t];
+    uint64_t dst = tile_dst[t];
+    for (uint32_t i = lane; i < n; i += 32) {
+        h1_out[dst + i] = h1_in[src + i];
+        pos_out[dst + i] = pos_in[src + i];
+        ctg_out[dst + i] = ctg_in[src + i];
+    }
+}
+
+// exclusive scan of tile counts (single CTA; n_tiles is a few hundred thousand at most)
+__global__ void tile_scan_kernel(const uint32_t* __restrict__ cnt, uint64_t* __restrict__ dst, uint32_t n)
+{
+    __shared__ uint64_t s_part[1024];
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t a = threadIdx.x * per, b = min(a + per, n);
+    uint64_t sum = 0;
+    for (uint32_t i = a; i < b; ++i) sum += cnt[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (uint32_t i = 0; i < blockDim.x; ++i) { uint64_t v = s_part[i]; s_part[i] = run; run += v; }
+    }
+    __syncthreads();
+    uint64_t run = s_part[threadIdx.x];
+    for (uint32_t i = a; i < b; ++i) { dst[i] = run; run += cnt[i]; }
+}
+
+}  // namespace nts

@@ -1,0 +1,232 @@
+"""Thin object layer over the C-ABI: Context, DeviceGenome, BloomFilter, MinimizerTable.
+
+Mirrors the reference's operators for this path:
+  BloomFilter.insert_genome  <- bf->insert(record.seq)              src/ntsynt_make_common_bf.cpp:128-131
+  BloomFilter.iand           <- the contains/insert cascade          src/ntsynt_make_common_bf.cpp:136-160
+  Context.sketch             <- indexlr --long --pos [-s bf] [-r bf] bin/ntsynt_run_pipeline.smk:83-85
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import NtsError, check, lib, ptr  # noqa: F401
+
+
+def device_count():
+    n = C.c_int()
+    check(lib.nts_device_count(C.byref(n)))
+    return n.value
+
+
+class Context:
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        check(lib.nts_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib.nts_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+    def sync(self):
+        check(lib.nts_ctx_sync(self._h))
+
+    def timer_start(self):
+        check(lib.nts_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(lib.nts_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launches(self):
+        return int(lib.nts_launch_count(self._h))
+
+    def mem_info(self):
+        f, t = C.c_uint64(), C.c_uint64()
+        check(lib.nts_mem_info(self._h, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
+    # -- genome
+    def upload(self, packed):
+        return DeviceGenome(self, packed)
+
+    # -- Bloom filter
+    def bloom(self, nbytes):
+        return BloomFilter(self, nbytes)
+
+    # -- sketch (indexlr)
+    def sketch(self, genome, k, w, common=None, repeat=None, masks=None):
+        """masks: optional list (per contig) of (start, end) arrays of extra N intervals."""
+        mo = ms = me = None
+        if masks is not None:
+            off = [0]
+            starts, ends = [], []
+            for c in range(genome.n_contigs):
+                iv = masks[c] if c < len(masks) and masks[c] is not None else ((), ())
+                s = np.asarray(iv[0], dtype=np.uint64)
+                e = np.asarray(iv[1], dtype=np.uint64)
+                starts.append(s)
+                ends.append(e)
+                off.append(off[-1] + len(s))
+            mo = np.asarray(off, dtype=np.uint64)
+            ms = np.concatenate(starts) if starts else np.zeros(0, dtype=np.uint64)
+            me = np.concatenate(ends) if ends else np.zeros(0, dtype=np.uint64)
+            if ms.size == 0:
+                ms = np.zeros(1, dtype=np.uint64)
+                me = np.zeros(1, dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib.nts_sketch(self._h, genome._h, common._h if common else None, repeat._h if repeat else None,
+                             int(k), int(w), ptr(mo, C.c_uint64), ptr(ms, C.c_uint64), ptr(me, C.c_uint64),
+                             C.byref(h)))
+        return MinimizerTable(self, h, genome)
+
+    def hash_contig(self, genome, contig, k):
+        n = int(genome.lengths[contig])
+        nk = max(n - k + 1, 0)
+        h0 = np.zeros(max(nk, 1), dtype=np.uint64)
+        valid = np.zeros(max(nk, 1), dtype=np.uint8)
+        check(lib.nts_hash_contig(self._h, genome._h, int(contig), int(k), ptr(h0, C.c_uint64), ptr(valid, C.c_uint8)))
+        return h0[:nk], valid[:nk]
+
+
+class DeviceGenome:
+    def __init__(self, ctx, packed):
+        self.ctx = ctx
+        self.names = list(packed.names)
+        self.lengths = np.asarray(packed.lengths, dtype=np.uint64)
+        self.n_contigs = len(self.names)
+        h = C.c_void_p()
+        words = packed.words if packed.words.size else np.zeros(1, dtype=np.uint64)
+        ns = packed.nrun_start if packed.nrun_start.size else np.zeros(1, dtype=np.uint64)
+        nl = packed.nrun_len if packed.nrun_len.size else np.zeros(1, dtype=np.uint64)
+        check(lib.nts_genome_upload(ctx._h, self.n_contigs, ptr(self.lengths, C.c_uint64),
+                                    ptr(packed.word_off, C.c_uint64), ptr(words, C.c_uint64), int(packed.words.size),
+                                    ptr(packed.nrun_off, C.c_uint64), ptr(ns, C.c_uint64), ptr(nl, C.c_uint64),
+                                    C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def _from_handle(cls, ctx, h, names, lengths):
+        self = cls.__new__(cls)
+        self.ctx, self._h = ctx, h
+        self.names = list(names)
+        self.lengths = np.asarray(lengths, dtype=np.uint64)
+        self.n_contigs = len(self.names)
+        return self
+
+    @property
+    def total_bases(self):
+        return int(lib.nts_genome_size(self._h))
+
+    def close(self):
+        if self._h:
+            lib.nts_genome_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+class BloomFilter:
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(lib.nts_bf_create(ctx._h, int(nbytes), C.byref(h)))
+        self._h = h
+        self.nbytes = int(nbytes)
+
+    @staticmethod
+    def size_for(genome_size, fpr):
+        "approximate_bf_size, src/ntsynt_make_common_bf.cpp:28-40 (+ btllib 8-byte round-up)"
+        return int(lib.nts_bf_bytes(int(genome_size), float(fpr)))
+
+    def clear(self):
+        check(lib.nts_bf_clear(self._h))
+
+    def insert_genome(self, genome, k):
+        check(lib.nts_bf_insert_genome(self._h, genome._h, int(k)))
+
+    def insert_repeats(self, scratch, genome, k):
+        check(lib.nts_bf_insert_repeats(self._h, scratch._h, genome._h, int(k)))
+
+    def iand(self, other):
+        check(lib.nts_bf_and(self._h, other._h))
+        return self
+
+    def ior(self, other):
+        check(lib.nts_bf_or(self._h, other._h))
+        return self
+
+    def popcount(self):
+        n = C.c_uint64()
+        check(lib.nts_bf_popcount(self._h, C.byref(n)))
+        return n.value
+
+    def fpr(self):
+        "occupancy (1 hash function): what btllib's get_fpr() prints"
+        return self.popcount() / (self.nbytes * 8.0)
+
+    def to_numpy(self):
+        out = np.empty(self.nbytes, dtype=np.uint8)
+        check(lib.nts_bf_download(self._h, ptr(out, C.c_uint8)))
+        return out
+
+    def from_numpy(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        if arr.size != self.nbytes:
+            raise ValueError("size mismatch")
+        check(lib.nts_bf_upload(self._h, ptr(arr, C.c_uint8)))
+        return self
+
+    def close(self):
+        if self._h:
+            lib.nts_bf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+class MinimizerTable:
+    "device-resident (h1, pos, contig) triples in indexlr emission order"
+
+    def __init__(self, ctx, handle, genome):
+        self.ctx, self._h, self.genome = ctx, handle, genome
+
+    def __len__(self):
+        return int(lib.nts_mxs_count(self._h))
+
+    def to_numpy(self):
+        n = len(self)
+        h1 = np.empty(max(n, 1), dtype=np.uint64)
+        pos = np.empty(max(n, 1), dtype=np.uint32)
+        ctg = np.empty(max(n, 1), dtype=np.uint32)
+        check(lib.nts_mxs_download(self._h, ptr(h1, C.c_uint64), ptr(pos, C.c_uint32), ptr(ctg, C.c_uint32)))
+        return h1[:n], pos[:n], ctg[:n]
+
+    def close(self):
+        if self._h:
+            lib.nts_mxs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
