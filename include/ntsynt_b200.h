@@ -89,25 +89,6 @@ int nts_genome_download_contig(nts_genome* g, uint32_t contig, uint64_t* words_o
 int nts_genome_nruns(nts_genome* g, uint64_t* nrun_off /*[n_contigs+1]*/, uint64_t* nrun_start, uint64_t* nrun_len,
                      uint64_t cap, uint64_t* n_out);
 
-/* Synthetic genome materialised on the device from a segment table (bench.py).
- * Output base j of contig c = ancestor base (or its complement for strand -1) addressed by the
- * segment covering j, then substituted with probability sub_rate (Philox-keyed by seed,j).
- * seg_* arrays: [n_seg] sorted by (contig, dst_start); anc_contig < 0 means "random insert",
- * anc_contig == -2 means "N run".  The ancestor itself is a pure function of (anc_seed, contig,
- * position): i.i.d. bases with P(A)=P(T)=0.295, P(C)=P(G)=0.205 overlaid with repeat copies. */
-typedef struct {
-    uint32_t dst_contig;
-    int32_t anc_contig;   /* >=0 ancestor contig; -1 random insert; -2 N run */
-    uint64_t dst_start;   /* contig-local start in the new genome */
-    uint64_t anc_start;   /* ancestor coordinate of the segment's FIRST output base */
-    uint64_t len;
-    int32_t strand;       /* +1 forward, -1 reverse complement (anc_start then decreases) */
-    uint32_t pad;
-} nts_synth_seg;
-int nts_genome_synthesize(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const nts_synth_seg* segs,
-                          uint64_t n_seg, uint64_t anc_seed, uint64_t genome_seed, double sub_rate,
-                          uint32_t n_repeat_fam, double repeat_frac, nts_genome** out);
-
 /* -------------------------------------------------------------------------------- Bloom filter
  * Replaces btllib::KmerBloomFilter(bytes, 1, k) as used by src/ntsynt_make_common_bf.cpp. */
 /* a1: approximate_bf_size (cpp:28-40) + btllib's round-up to a multiple of 8 bytes */
@@ -128,15 +109,6 @@ int nts_bf_insert_repeats(nts_bf* rep, nts_bf* scratch, const nts_genome* g, uin
 int nts_bf_popcount(nts_bf* bf, uint64_t* bits_set); /* for the "Bloom filter FPR" log lines */
 int nts_bf_download(nts_bf* bf, uint8_t* bytes_out);
 int nts_bf_upload(nts_bf* bf, const uint8_t* bytes_in);
-/* Multi-GPU merge (north star: counting filters + one NCCL allreduce(sum)).  Every rank holds
- * `n_local` per-genome filters; after the call filters[0] on every rank holds the AND over all
- * genomes of all ranks.  comm is an ncclComm_t created by nts_nccl_init. */
-typedef struct nts_comm nts_comm;
-int nts_nccl_unique_id(uint8_t id_out[128]);
-int nts_nccl_init(nts_ctx* ctx, const uint8_t id[128], int rank, int world, nts_comm** out);
-void nts_nccl_destroy(nts_comm* comm);
-int nts_bf_allreduce_and(nts_comm* comm, nts_bf* const* filters, uint32_t n_local, uint32_t n_total_genomes);
-
 /* -------------------------------------------------------------------------------- sketch
  * Replaces `indexlr -k K -w W --long --pos [-s common.bf] [-r repeat.bf]`
  * (bin/ntsynt_run_pipeline.smk:83-85; subprojects/ntJoin/bin/ntjoin_utils.py:195-202).
@@ -156,24 +128,28 @@ int nts_hash_contig(nts_ctx* ctx, const nts_genome* g, uint32_t contig, uint32_t
                     uint8_t* valid_out);
 
 /* -------------------------------------------------------------------------------- graph (kernel iv)
- * Replaces ntjoin_utils.read_minimizers' duplicate removal (:182-192), filter_minimizers
- * (:152-165), build_graph's adjacency edges (:97-113,132-135) and, for edges of full weight,
- * ntjoin.find_paths (ntjoin.py:114-136).  Input: one minimizer table per assembly in the
- * caller's assembly order.  See nts_graph_* in INTEGRATION.md. */
+ * Replaces ntjoin_utils.read_minimizers' duplicate removal (subprojects/ntJoin/bin/ntjoin_utils.py:182-192),
+ * filter_minimizers (:152-165), build_graph's adjacency edges and weights (:97-113,132-135) and,
+ * for edges supported by every assembly, filter_graph_global + find_paths
+ * (subprojects/ntJoin/bin/ntjoin.py:78-87,114-136).
+ * Input: one minimizer table per assembly, in the caller's assembly order (= the reference's
+ * reverse-sorted FILES order, bin/ntsynt_synteny.py:34).  A minimizer becomes a vertex iff it occurs
+ * exactly once in every assembly.  Vertices are numbered by their rank in assembly `order_asm`'s
+ * filtered list (contig order, then position), so an edge supported by all assemblies is always
+ * (i, i+1) and maximal chains are runs of the `link` bitmap. */
 typedef struct nts_graph nts_graph;
-int nts_graph_build(nts_ctx* ctx, nts_mxs* const* tables, uint32_t n_asm, nts_graph** out);
+int nts_graph_build(nts_ctx* ctx, nts_mxs* const* tables, uint32_t n_asm, uint32_t order_asm, nts_graph** out);
 void nts_graph_destroy(nts_graph* g);
-/* number of common (deduplicated, present in all assemblies) minimizers = vertices */
 uint64_t nts_graph_vertices(const nts_graph* g);
-/* Vertex table in the order of assembly `order_asm`'s filtered list (contig, then position):
- * h1[V]; pos[n_asm*V] and contig[n_asm*V] (assembly-major); rank[n_asm*V] = index of the
- * vertex in that assembly's filtered list (lists of all contigs concatenated). */
-int nts_graph_download_vertices(nts_graph* g, uint32_t order_asm, uint64_t* h1, uint32_t* pos, uint32_t* contig,
-                                uint32_t* rank);
-/* Edge table: distinct unordered adjacencies in first-insertion order of build_graph
- * (assembly order, list order); u,v = vertex indices (order_asm numbering of the last
- * download), support = bitmask of assemblies, first_asm/first_idx = where it was first seen. */
-uint64_t nts_graph_edges(const nts_graph* g);
+/* Vertex table (any pointer may be NULL): h1[V]; pos / contig / rank are [n_asm*V], assembly-major,
+ * rank = index of the vertex in that assembly's filtered list (all contigs concatenated);
+ * link[V]: 1 iff the edge (i, i+1) has weight n_asm; degree[V]: number of distinct neighbours. */
+int nts_graph_download_vertices(nts_graph* g, uint64_t* h1, uint32_t* pos, uint32_t* contig, uint32_t* rank,
+                                uint8_t* link, uint8_t* degree);
+/* Edge table: distinct unordered adjacencies in build_graph's first-insertion order (assembly
+ * order, then list order); (u, v) in the orientation of the first insertion; support = bitmask of
+ * assemblies (weight = popcount, all assembly weights are 1: bin/ntsynt_synteny.py:32). */
+int nts_graph_edges(nts_graph* g, uint64_t* n_edges);
 int nts_graph_download_edges(nts_graph* g, uint32_t* u, uint32_t* v, uint32_t* support);
 
 #ifdef __cplusplus

@@ -74,6 +74,12 @@ _SIGS = {
     "nts_mxs_count": (C.c_uint64, [vp]),
     "nts_mxs_download": (C.c_int, [vp, u64p, u32p, u32p]),
     "nts_hash_contig": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u64p, u8p]),
+    "nts_graph_build": (C.c_int, [vp, vpp, C.c_uint32, C.c_uint32, vpp]),
+    "nts_graph_destroy": (None, [vp]),
+    "nts_graph_vertices": (C.c_uint64, [vp]),
+    "nts_graph_download_vertices": (C.c_int, [vp, u64p, u32p, u32p, u32p, u8p, u8p]),
+    "nts_graph_edges": (C.c_int, [vp, u64p]),
+    "nts_graph_download_edges": (C.c_int, [vp, u32p, u32p, u32p]),
 }
 
 

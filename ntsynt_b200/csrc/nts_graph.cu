@@ -1,0 +1,430 @@
+// nts_graph.cu -- kernel family (iv): minimizer join, adjacency edges and full-weight links.
+//
+// Replaces, for the bulk of the data, the Python/igraph path of the reference:
+//   read_minimizers' duplicate removal      subprojects/ntJoin/bin/ntjoin_utils.py:182-192
+//   filter_minimizers (G-way intersection)  subprojects/ntJoin/bin/ntjoin_utils.py:152-165
+//   build_graph's adjacency edges + weights subprojects/ntJoin/bin/ntjoin_utils.py:97-113,132-135
+//   filter_graph_global / find_paths for edges supported by ALL assemblies
+//                                           subprojects/ntJoin/bin/ntjoin.py:78-87,114-136
+// Design: one open-addressing hash table keyed by h1 holds a `seen` and a `dup` bitmask per key
+// (bit a = assembly a).  A minimizer is a vertex iff seen == all and dup == 0.  Vertices are
+// numbered by their rank in the ORIENTING assembly's filtered list, so that an edge supported by
+// every assembly is always (i, i+1) and maximal chains are runs of a `link` bitmap.
+#include <algorithm>
+#include <new>
+
+#include "nts_internal.h"
+
+namespace nts {
+
+constexpr uint64_t HT_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+// find-or-insert every minimizer of assembly `a`; remember its slot; mark seen / dup
+__global__ void join_insert_kernel(const uint64_t* __restrict__ h1, uint64_t n, uint32_t a,
+                                   unsigned long long* __restrict__ keys, uint32_t* __restrict__ seen,
+                                   uint32_t* __restrict__ dup, uint64_t mask, uint32_t* __restrict__ slot_of)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = h1[i];
+    uint64_t slot;
+    if (key == HT_EMPTY) {
+        slot = mask + 1;   // dedicated slot for the one key that collides with the empty marker
+    } else {
+        slot = mix64(key) & mask;
+        while (true) {
+            unsigned long long old = atomicCAS(&keys[slot], (unsigned long long)HT_EMPTY, (unsigned long long)key);
+            if (old == HT_EMPTY || old == key) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+    slot_of[i] = (uint32_t)slot;
+    const uint32_t bit = 1u << a;
+    uint32_t old = atomicOr(&seen[slot], bit);
+    if (old & bit) atomicOr(&dup[slot], bit);
+}
+
+__global__ void join_keep_kernel(const uint32_t* __restrict__ slot_of, uint64_t n, const uint32_t* __restrict__ seen,
+                                 const uint32_t* __restrict__ dup, uint32_t full, uint32_t* __restrict__ keep)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = slot_of[i];
+    keep[i] = (seen[s] == full && dup[s] == 0) ? 1u : 0u;
+}
+
+// ---- exclusive scan of 0/1 flags, 3 phases (block sums, scan of sums, apply)
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;   // per thread
+
+__global__ void scan_block_sums_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ block_sums)
+{
+    __shared__ uint32_t s_w[SCAN_THREADS / 32];
+    uint64_t base = ((uint64_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_ITEMS;
+    uint32_t sum = 0;
+    for (int j = 0; j < SCAN_ITEMS; ++j) if (base + j < n) sum += in[base + j];
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < SCAN_THREADS / 32; ++i) t += s_w[i];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// single CTA exclusive scan over the block sums (n_blocks <= a few thousand); also returns the total
+__global__ void scan_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t n_blocks, uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t s_part[1024];
+    const uint32_t per = (n_blocks + blockDim.x - 1) / blockDim.x;
+    const uint32_t a = threadIdx.x * per, b = min(a + per, n_blocks);
+    uint32_t sum = 0;
+    for (uint32_t i = a; i < b; ++i) sum += block_sums[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < blockDim.x; ++i) { uint32_t v = s_part[i]; s_part[i] = run; run += v; }
+        *total = run;
+    }
+    __syncthreads();
+    uint32_t run = s_part[threadIdx.x];
+    for (uint32_t i = a; i < b; ++i) { uint32_t v = block_sums[i]; block_sums[i] = run; run += v; }
+}
+
+__global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n, const uint32_t* __restrict__ block_off,
+                                  uint32_t* __restrict__ out)
+{
+    __shared__ uint32_t s_w[SCAN_THREADS / 32];
+    uint64_t base = ((uint64_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) { v[j] = (base + j < n) ? in[base + j] : 0; sum += v[j]; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) s_w[wid] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int i = 0; i < wid; ++i) woff += s_w[i];
+    uint32_t run = block_off[blockIdx.x] + woff + incl - sum;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) { if (base + j < n) out[base + j] = run; run += v[j]; }
+}
+
+// orienting assembly: vertex id = rank; publish it through the hash-table slot
+__global__ void join_number_kernel(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ rank,
+                                   const uint32_t* __restrict__ slot_of, uint64_t n, uint32_t* __restrict__ slot_vid)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    slot_vid[slot_of[i]] = rank[i];
+}
+
+// every assembly: scatter (pos, contig, rank) into vertex order and build the rank -> vertex map
+__global__ void join_scatter_kernel(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ rank,
+                                    const uint32_t* __restrict__ slot_of, const uint64_t* __restrict__ h1,
+                                    const uint32_t* __restrict__ pos, const uint32_t* __restrict__ contig, uint64_t n,
+                                    const uint32_t* __restrict__ slot_vid, uint32_t* __restrict__ v_pos,
+                                    uint32_t* __restrict__ v_ctg, uint32_t* __restrict__ v_rank,
+                                    uint32_t* __restrict__ inv, uint64_t* __restrict__ v_h1 /*nullable*/)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const uint32_t vid = slot_vid[slot_of[i]], r = rank[i];
+    v_pos[vid] = pos[i];
+    v_ctg[vid] = contig[i];
+    v_rank[vid] = r;
+    inv[r] = vid;
+    if (v_h1) v_h1[vid] = h1[i];
+}
+
+// adjacency of vertices u, v in assembly b (same contig line, neighbouring ranks)
+__device__ __forceinline__ bool adjacent_in(const uint32_t* __restrict__ v_ctg, const uint32_t* __restrict__ v_rank,
+                                            uint64_t V, uint32_t b, uint32_t u, uint32_t v)
+{
+    const uint32_t ru = v_rank[(uint64_t)b * V + u], rv = v_rank[(uint64_t)b * V + v];
+    return (ru + 1 == rv || rv + 1 == ru) && v_ctg[(uint64_t)b * V + u] == v_ctg[(uint64_t)b * V + v];
+}
+
+// link[i] = 1 iff edge (i, i+1) is supported by every assembly;  degree[v] = # distinct neighbours
+__global__ void graph_links_kernel(const uint32_t* __restrict__ v_ctg, const uint32_t* __restrict__ v_rank,
+                                   const uint32_t* __restrict__ inv, uint64_t V, uint32_t n_asm,
+                                   uint8_t* __restrict__ link, uint8_t* __restrict__ degree)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const uint32_t u = (uint32_t)i;
+    if (i + 1 < V) {
+        bool full = true;
+        for (uint32_t b = 0; b < n_asm && full; ++b) full = adjacent_in(v_ctg, v_rank, V, b, u, u + 1);
+        link[i] = full ? 1 : 0;
+    } else {
+        link[i] = 0;
+    }
+    // distinct neighbours over all assemblies (at most 2 per assembly)
+    uint32_t nb[64];
+    uint32_t cnt = 0;
+    for (uint32_t b = 0; b < n_asm; ++b) {
+        const uint32_t r = v_rank[(uint64_t)b * V + u], c = v_ctg[(uint64_t)b * V + u];
+        for (int side = 0; side < 2; ++side) {
+            if (side == 0 && r == 0) continue;
+            const uint64_t rr = side == 0 ? (uint64_t)r - 1 : (uint64_t)r + 1;
+            if (rr >= V) continue;
+            const uint32_t w = inv[(uint64_t)b * V + rr];
+            if (v_ctg[(uint64_t)b * V + w] != c) continue;
+            bool dupl = false;
+            for (uint32_t t = 0; t < cnt; ++t) dupl |= (nb[t] == w);
+            if (!dupl) nb[cnt++] = w;
+        }
+    }
+    degree[i] = (uint8_t)cnt;
+}
+
+// edge enumeration in build_graph's first-insertion order: (assembly a, rank r) is a NEW edge iff no
+// earlier assembly has the same unordered adjacency
+__global__ void graph_edge_flags_kernel(const uint32_t* __restrict__ v_ctg, const uint32_t* __restrict__ v_rank,
+                                        const uint32_t* __restrict__ inv, uint64_t V, uint32_t n_asm,
+                                        uint32_t* __restrict__ is_new /*[n_asm*V]*/)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n_asm * V) return;
+    const uint32_t a = (uint32_t)(t / V);
+    const uint64_t r = t % V;
+    uint32_t flag = 0;
+    if (r + 1 < V) {
+        const uint32_t u = inv[(uint64_t)a * V + r], v = inv[(uint64_t)a * V + r + 1];
+        if (v_ctg[(uint64_t)a * V + u] == v_ctg[(uint64_t)a * V + v]) {
+            flag = 1;
+            for (uint32_t b = 0; b < a && flag; ++b) if (adjacent_in(v_ctg, v_rank, V, b, u, v)) flag = 0;
+        }
+    }
+    is_new[t] = flag;
+}
+
+__global__ void graph_edge_emit_kernel(const uint32_t* __restrict__ v_ctg, const uint32_t* __restrict__ v_rank,
+                                       const uint32_t* __restrict__ inv, uint64_t V, uint32_t n_asm,
+                                       const uint32_t* __restrict__ is_new, const uint32_t* __restrict__ off,
+                                       uint32_t* __restrict__ e_u, uint32_t* __restrict__ e_v,
+                                       uint32_t* __restrict__ e_support)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n_asm * V || !is_new[t]) return;
+    const uint32_t a = (uint32_t)(t / V);
+    const uint64_t r = t % V;
+    const uint32_t u = inv[(uint64_t)a * V + r], v = inv[(uint64_t)a * V + r + 1];
+    uint32_t sup = 0;
+    for (uint32_t b = 0; b < n_asm; ++b) if (adjacent_in(v_ctg, v_rank, V, b, u, v)) sup |= 1u << b;
+    const uint32_t o = off[t];
+    e_u[o] = u; e_v[o] = v; e_support[o] = sup;
+}
+
+static int exclusive_scan_u32(nts_ctx* ctx, const uint32_t* in, uint64_t n, uint32_t* out, uint32_t* total_host)
+{
+    const uint64_t per_block = (uint64_t)SCAN_THREADS * SCAN_ITEMS;
+    const uint32_t n_blocks = (uint32_t)std::max<uint64_t>(1, (n + per_block - 1) / per_block);
+    DevBuf<uint32_t> sums, total;
+    if (sums.alloc(n_blocks) != cudaSuccess || total.alloc(1) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (scan)");
+    scan_block_sums_kernel<<<n_blocks, SCAN_THREADS, 0, ctx->stream>>>(in, n, sums.p);
+    scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(sums.p, n_blocks, total.p);
+    scan_apply_kernel<<<n_blocks, SCAN_THREADS, 0, ctx->stream>>>(in, n, sums.p, out);
+    ctx->launches += 3;
+    NTS_CUDA(cudaGetLastError());
+    NTS_CUDA(cudaMemcpyAsync(total_host, total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+}  // namespace nts
+
+using namespace nts;
+
+struct nts_graph {
+    nts_ctx* ctx = nullptr;
+    uint32_t n_asm = 0;
+    uint32_t order_asm = 0;
+    uint64_t V = 0;
+    DevBuf<uint64_t> v_h1;                       // [V]
+    DevBuf<uint32_t> v_pos, v_ctg, v_rank, inv;  // [n_asm * V], assembly-major
+    DevBuf<uint8_t> link, degree;                // [V]
+    // edges (built lazily)
+    bool edges_built = false;
+    uint64_t E = 0;
+    DevBuf<uint32_t> e_u, e_v, e_support;
+};
+
+extern "C" {
+
+int nts_graph_build(nts_ctx* ctx, nts_mxs* const* tables, uint32_t n_asm, uint32_t order_asm, nts_graph** out)
+{
+    if (!ctx || !tables || !out) return fail(NTS_ERR_ARG, "null argument");
+    if (n_asm < 1 || n_asm > 32) return fail(NTS_ERR_ARG, "between 1 and 32 assemblies are supported");
+    if (order_asm >= n_asm) return fail(NTS_ERR_ARG, "order_asm out of range");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    uint64_t total = 0, nmax = 0;
+    for (uint32_t a = 0; a < n_asm; ++a) {
+        if (!tables[a] || tables[a]->ctx != ctx) return fail(NTS_ERR_ARG, "bad minimizer table");
+        total += tables[a]->count;
+        nmax = std::max(nmax, tables[a]->count);
+    }
+    nts_graph* g = new (std::nothrow) nts_graph();
+    if (!g) return fail(NTS_ERR_NOMEM, "host allocation failed");
+    struct Guard { nts_graph* p; ~Guard() { delete p; } } guard{g};
+    g->ctx = ctx; g->n_asm = n_asm; g->order_asm = order_asm;
+    uint64_t cap = 1024;
+    while (cap < total * 2) cap <<= 1;
+    if (cap > 0x80000000ull) return fail(NTS_ERR_ARG, "too many minimizers for the join table");
+    DevBuf<unsigned long long> keys;
+    DevBuf<uint32_t> seen, dup, slot_vid;
+    std::vector<DevBuf<uint32_t>> slot_of(n_asm), keep(n_asm), rank(n_asm);
+    if (keys.alloc(cap + 1) != cudaSuccess || seen.alloc(cap + 1) != cudaSuccess || dup.alloc(cap + 1) != cudaSuccess ||
+        slot_vid.alloc(cap + 1) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (join table)");
+    NTS_CUDA(cudaMemsetAsync(keys.p, 0xFF, (cap + 1) * 8, ctx->stream));
+    NTS_CUDA(cudaMemsetAsync(seen.p, 0, (cap + 1) * 4, ctx->stream));
+    NTS_CUDA(cudaMemsetAsync(dup.p, 0, (cap + 1) * 4, ctx->stream));
+    for (uint32_t a = 0; a < n_asm; ++a) {
+        const uint64_t n = tables[a]->count;
+        if (slot_of[a].alloc(n) != cudaSuccess || keep[a].alloc(n) != cudaSuccess || rank[a].alloc(n) != cudaSuccess)
+            return fail(NTS_ERR_NOMEM, "device allocation failed (join)");
+        if (!n) continue;
+        join_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(tables[a]->h1.p, n, a, keys.p, seen.p, dup.p,
+                                                                                cap - 1, slot_of[a].p);
+        ctx->launches++;
+    }
+    NTS_CUDA(cudaGetLastError());
+    const uint32_t full = n_asm == 32 ? 0xFFFFFFFFu : ((1u << n_asm) - 1);
+    uint64_t V = 0;
+    for (uint32_t a = 0; a < n_asm; ++a) {
+        const uint64_t n = tables[a]->count;
+        uint32_t tot = 0;
+        if (n) {
+            join_keep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(slot_of[a].p, n, seen.p, dup.p, full, keep[a].p);
+            ctx->launches++;
+            int rc = exclusive_scan_u32(ctx, keep[a].p, n, rank[a].p, &tot);
+            if (rc) return rc;
+        }
+        if (a == 0) V = tot;
+        else if (tot != V) return fail(NTS_ERR_STATE, "internal error: assemblies disagree on the number of common minimizers");
+    }
+    g->V = V;
+    const uint64_t VA = std::max<uint64_t>(1, V * n_asm);
+    if (g->v_h1.alloc(std::max<uint64_t>(1, V)) != cudaSuccess || g->v_pos.alloc(VA) != cudaSuccess || g->v_ctg.alloc(VA) != cudaSuccess ||
+        g->v_rank.alloc(VA) != cudaSuccess || g->inv.alloc(VA) != cudaSuccess || g->link.alloc(std::max<uint64_t>(1, V)) != cudaSuccess ||
+        g->degree.alloc(std::max<uint64_t>(1, V)) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (vertex table)");
+    if (V) {
+        {
+            const uint64_t n = tables[order_asm]->count;
+            join_number_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keep[order_asm].p, rank[order_asm].p,
+                                                                                    slot_of[order_asm].p, n, slot_vid.p);
+            ctx->launches++;
+        }
+        for (uint32_t a = 0; a < n_asm; ++a) {
+            const uint64_t n = tables[a]->count;
+            join_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+                keep[a].p, rank[a].p, slot_of[a].p, tables[a]->h1.p, tables[a]->pos.p, tables[a]->contig.p, n, slot_vid.p,
+                g->v_pos.p + a * V, g->v_ctg.p + a * V, g->v_rank.p + a * V, g->inv.p + a * V,
+                a == order_asm ? g->v_h1.p : nullptr);
+            ctx->launches++;
+        }
+        graph_links_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(g->v_ctg.p, g->v_rank.p, g->inv.p, V, n_asm,
+                                                                                g->link.p, g->degree.p);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+    }
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = g; guard.p = nullptr;
+    return NTS_OK;
+}
+
+void nts_graph_destroy(nts_graph* g)
+{
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    delete g;
+}
+
+uint64_t nts_graph_vertices(const nts_graph* g) { return g ? g->V : 0; }
+
+int nts_graph_download_vertices(nts_graph* g, uint64_t* h1, uint32_t* pos, uint32_t* contig, uint32_t* rank,
+                                uint8_t* link, uint8_t* degree)
+{
+    if (!g) return fail(NTS_ERR_ARG, "null argument");
+    if (!g->V) return NTS_OK;
+    NTS_CUDA(cudaSetDevice(g->ctx->device));
+    cudaStream_t st = g->ctx->stream;
+    const uint64_t V = g->V, VA = V * g->n_asm;
+    if (h1) NTS_CUDA(cudaMemcpyAsync(h1, g->v_h1.p, V * 8, cudaMemcpyDeviceToHost, st));
+    if (pos) NTS_CUDA(cudaMemcpyAsync(pos, g->v_pos.p, VA * 4, cudaMemcpyDeviceToHost, st));
+    if (contig) NTS_CUDA(cudaMemcpyAsync(contig, g->v_ctg.p, VA * 4, cudaMemcpyDeviceToHost, st));
+    if (rank) NTS_CUDA(cudaMemcpyAsync(rank, g->v_rank.p, VA * 4, cudaMemcpyDeviceToHost, st));
+    if (link) NTS_CUDA(cudaMemcpyAsync(link, g->link.p, V, cudaMemcpyDeviceToHost, st));
+    if (degree) NTS_CUDA(cudaMemcpyAsync(degree, g->degree.p, V, cudaMemcpyDeviceToHost, st));
+    NTS_CUDA(cudaStreamSynchronize(st));
+    return NTS_OK;
+}
+
+static int build_edges(nts_graph* g)
+{
+    if (g->edges_built) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    const uint64_t V = g->V, N = V * g->n_asm;
+    g->E = 0;
+    if (N) {
+        DevBuf<uint32_t> is_new, off;
+        if (is_new.alloc(N) != cudaSuccess || off.alloc(N) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (edges)");
+        graph_edge_flags_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(g->v_ctg.p, g->v_rank.p, g->inv.p, V, g->n_asm, is_new.p);
+        ctx->launches++;
+        uint32_t tot = 0;
+        int rc = exclusive_scan_u32(ctx, is_new.p, N, off.p, &tot);
+        if (rc) return rc;
+        g->E = tot;
+        if (g->e_u.alloc(std::max<uint32_t>(1, tot)) != cudaSuccess || g->e_v.alloc(std::max<uint32_t>(1, tot)) != cudaSuccess ||
+            g->e_support.alloc(std::max<uint32_t>(1, tot)) != cudaSuccess)
+            return fail(NTS_ERR_NOMEM, "device allocation failed (edge table)");
+        graph_edge_emit_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(g->v_ctg.p, g->v_rank.p, g->inv.p, V, g->n_asm,
+                                                                                    is_new.p, off.p, g->e_u.p, g->e_v.p, g->e_support.p);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    g->edges_built = true;
+    return NTS_OK;
+}
+
+int nts_graph_edges(nts_graph* g, uint64_t* n_edges)
+{
+    if (!g || !n_edges) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(g->ctx->device));
+    int rc = build_edges(g);
+    if (rc) return rc;
+    *n_edges = g->E;
+    return NTS_OK;
+}
+
+int nts_graph_download_edges(nts_graph* g, uint32_t* u, uint32_t* v, uint32_t* support)
+{
+    if (!g) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(g->ctx->device));
+    int rc = build_edges(g);
+    if (rc) return rc;
+    if (!g->E) return NTS_OK;
+    cudaStream_t st = g->ctx->stream;
+    if (u) NTS_CUDA(cudaMemcpyAsync(u, g->e_u.p, g->E * 4, cudaMemcpyDeviceToHost, st));
+    if (v) NTS_CUDA(cudaMemcpyAsync(v, g->e_v.p, g->E * 4, cudaMemcpyDeviceToHost, st));
+    if (support) NTS_CUDA(cudaMemcpyAsync(support, g->e_support.p, g->E * 4, cudaMemcpyDeviceToHost, st));
+    NTS_CUDA(cudaStreamSynchronize(st));
+    return NTS_OK;
+}
+
+}  // extern "C"

@@ -230,3 +230,59 @@ class MinimizerTable:
             self.close()
         except Exception:  # pylint: disable=broad-except
             pass
+
+
+class MinimizerGraph:
+    """Device join of G minimizer tables (kernel iv): vertex table in the orienting assembly's
+    list order, full-weight links and vertex degrees.  See nts_graph_build in the header."""
+
+    def __init__(self, ctx, tables, order_asm):
+        self.ctx = ctx
+        self.n_asm = len(tables)
+        arr = (C.c_void_p * self.n_asm)(*[t._h for t in tables])
+        h = C.c_void_p()
+        check(lib.nts_graph_build(ctx._h, arr, self.n_asm, int(order_asm), C.byref(h)))
+        self._h = h
+        self.order_asm = order_asm
+
+    def __len__(self):
+        return int(lib.nts_graph_vertices(self._h))
+
+    def vertices(self):
+        "h1[V] u64, pos[G,V] u32, contig[G,V] u32, rank[G,V] u32, link[V] u8, degree[V] u8"
+        V, G = len(self), self.n_asm
+        n = max(V, 1)
+        h1 = np.empty(n, dtype=np.uint64)
+        pos = np.empty((G, n), dtype=np.uint32)
+        ctg = np.empty((G, n), dtype=np.uint32)
+        rank = np.empty((G, n), dtype=np.uint32)
+        link = np.empty(n, dtype=np.uint8)
+        deg = np.empty(n, dtype=np.uint8)
+        if V:
+            check(lib.nts_graph_download_vertices(self._h, ptr(h1, C.c_uint64), ptr(pos, C.c_uint32),
+                                                  ptr(ctg, C.c_uint32), ptr(rank, C.c_uint32), ptr(link, C.c_uint8),
+                                                  ptr(deg, C.c_uint8)))
+        return h1[:V], pos[:, :V], ctg[:, :V], rank[:, :V], link[:V], deg[:V]
+
+    def edges(self):
+        "(u, v, support) of the distinct adjacency edges in build_graph's first-insertion order"
+        n = C.c_uint64()
+        check(lib.nts_graph_edges(self._h, C.byref(n)))
+        E = n.value
+        u = np.empty(max(E, 1), dtype=np.uint32)
+        v = np.empty(max(E, 1), dtype=np.uint32)
+        s = np.empty(max(E, 1), dtype=np.uint32)
+        if E:
+            check(lib.nts_graph_download_edges(self._h, ptr(u, C.c_uint32), ptr(v, C.c_uint32), ptr(s, C.c_uint32)))
+        return u[:E], v[:E], s[:E]
+
+    def close(self):
+        if self._h:
+            lib.nts_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass

@@ -1,0 +1,109 @@
+"""Backends that feed ntsynt_b200.synteny.SyntenyEngine in tests.
+
+OracleBackend is TEST-ONLY: it sketches with the CPU oracle and joins with numpy so that the
+host-side graph logic can be exercised without a GPU (the driver's `-m "not gpu"` run).  The
+product never uses it: ntsynt_b200.pipeline.CudaBackend is the only backend the package ships.
+"""
+import numpy as np
+
+from oracle import sketch_oracle as so
+
+
+def numpy_join(tables, order_asm):
+    """numpy restatement of nts_graph_build (device kernel iv): dedup within each assembly, G-way
+    intersection, vertex numbering by rank in the orienting assembly's filtered list."""
+    G = len(tables)
+    filt = []
+    common = None
+    for h1, pos, ctg in tables:
+        u, cnt = np.unique(h1, return_counts=True)
+        uniq = u[cnt == 1]
+        common = uniq if common is None else np.intersect1d(common, uniq, assume_unique=True)
+    for h1, pos, ctg in tables:
+        keep = np.isin(h1, common)
+        filt.append((h1[keep], pos[keep], ctg[keep]))
+    V = len(common)
+    H = filt[order_asm][0].copy()
+    order = np.argsort(H, kind="stable")
+    Hs = H[order]
+    POS = np.zeros((G, V), dtype=np.uint32)
+    CTG = np.zeros((G, V), dtype=np.uint32)
+    RANK = np.zeros((G, V), dtype=np.uint32)
+    INV = np.zeros((G, V), dtype=np.int64)
+    for a, (h1, pos, ctg) in enumerate(filt):
+        vid = order[np.searchsorted(Hs, h1)]
+        POS[a, vid] = pos
+        CTG[a, vid] = ctg
+        RANK[a, vid] = np.arange(V)
+        INV[a] = vid
+    link = np.zeros(V, dtype=np.uint8)
+    if V > 1:
+        full = np.ones(V - 1, dtype=bool)
+        for a in range(G):
+            r0, r1 = RANK[a, :-1].astype(np.int64), RANK[a, 1:].astype(np.int64)
+            full &= (np.abs(r0 - r1) == 1) & (CTG[a, :-1] == CTG[a, 1:])
+        link[:-1] = full
+    degree = np.zeros(V, dtype=np.uint8)
+    nbsets = [set() for _ in range(V)]
+    for a in range(G):
+        vid = INV[a]
+        same = CTG[a, vid[:-1]] == CTG[a, vid[1:]]
+        for x, y in zip(vid[:-1][same], vid[1:][same]):
+            nbsets[x].add(int(y)); nbsets[y].add(int(x))
+    degree[:] = [len(s) for s in nbsets]
+    return H, POS, CTG, RANK, link, degree
+
+
+def numpy_edges(RANK, CTG):
+    "edge table in build_graph's first-insertion order: list of (u, v, support_mask)"
+    G, V = RANK.shape
+    seen = {}
+    order = []
+    for a in range(G):
+        inv = np.empty(V, dtype=np.int64)
+        inv[RANK[a]] = np.arange(V)
+        for r in range(V - 1):
+            u, v = int(inv[r]), int(inv[r + 1])
+            if CTG[a, u] != CTG[a, v]:
+                continue
+            key = (min(u, v), max(u, v))
+            if key in seen:
+                seen[key][2] |= 1 << a
+            else:
+                seen[key] = [u, v, 1 << a]
+                order.append(key)
+    return [tuple(seen[k]) for k in order]
+
+
+class OracleBackend:
+    def __init__(self, fasta_paths, tsv_names, k, fpr=0.025, common=True):
+        "fasta_paths/tsv_names in the engine's processing order (reverse-sorted TSV names)"
+        self.k = k
+        self.names = list(tsv_names)
+        self.records = [so.read_fasta(p) for p in fasta_paths]
+        self.contig_names = [[n for n, _ in recs] for recs in self.records]
+        self.contig_lengths = [[len(s) for _, s in recs] for recs in self.records]
+        self.bits = None
+        if common:
+            import os
+            genomes = [(os.path.basename(p)[:-3] if p.endswith(".gz") else os.path.basename(p), recs)
+                       for p, recs in zip(fasta_paths, self.records)]
+            self.bits = so.common_bf(genomes, k, fpr)
+        self.n_sketch = 0
+
+    def sketch(self, a, w, masks):
+        self.n_sketch += 1
+        hs, ps, cs = [], [], []
+        for c, (_, seq) in enumerate(self.records[a]):
+            if masks is not None and len(masks[c][0]):
+                buf = bytearray(seq)
+                for s, e in zip(masks[c][0], masks[c][1]):
+                    s, e = int(s), int(e)
+                    buf[s:e] = b"N" * (e - s)
+                seq = bytes(buf)
+            h1, pos = so.minimize(seq, self.k, w, self.bits)
+            hs.append(h1); ps.append(pos.astype(np.uint32)); cs.append(np.full(len(h1), c, dtype=np.uint32))
+        return np.concatenate(hs), np.concatenate(ps), np.concatenate(cs)
+
+    def join(self, tables, order_asm):
+        return numpy_join(tables, order_asm)
