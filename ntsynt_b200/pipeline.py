@@ -1,0 +1,114 @@
+"""In-process ntSynt pipeline on one GPU: FASTA -> common Bloom filter -> sketches -> graph ->
+synteny blocks.  Collapses the three processes of bin/ntsynt_run_pipeline.smk:55-103
+(ntsynt_make_common_bf, indexlr x G, ntsynt_run.py) into one, with genomes, filters and
+minimizer tables resident in HBM; intermediate files are written only on request.
+"""
+import os
+import time
+
+import numpy as np
+
+from . import device, fasta
+from .synteny import SyntenyEngine
+
+
+def tsv_name(fasta_path, k, w):
+    "the sketch file name the smk gives a genome: <basename>.k<k>.w<w>.tsv (smk:44-46,78)"
+    return f"{os.path.basename(fasta_path)}.k{k}.w{w}.tsv"
+
+
+def processing_order(names):
+    "the reference processes assemblies in reverse-sorted TSV-name order (bin/ntsynt_synteny.py:34)"
+    return sorted(range(len(names)), key=lambda i: names[i], reverse=True)
+
+
+def build_common_bf(ctx, genomes, paths, k, fpr=0.025, nbytes=None, log=None):
+    """src/ntsynt_make_common_bf.cpp:107-160 on the device.  `paths` are the strings the genomes
+    were given as (they are sorted as plain strings, cpp:107; the size comes from the first).
+    Returns the common filter (AND of per-genome bit arrays == the cascade with 1 hash fn)."""
+    order = sorted(range(len(genomes)), key=lambda i: paths[i])
+    if nbytes is None:
+        nbytes = device.BloomFilter.size_for(genomes[order[0]].total_bases, fpr)
+        if log:
+            log(f"Genome size (bp): {genomes[order[0]].total_bases}")
+    if log:
+        log(f"BF size (bytes): {nbytes}")
+    common = ctx.bloom(nbytes)
+    common.insert_genome(genomes[order[0]], k)
+    if log:
+        log(f"Bloom filter FPR: {common.fpr()}")
+    if len(order) > 1:
+        level = ctx.bloom(nbytes)
+        for n, i in enumerate(order[1:]):
+            if n:
+                level.clear()
+            level.insert_genome(genomes[i], k)
+            common.iand(level)
+            if log:
+                log(f"Bloom filter FPR: {common.fpr()}")
+        level.close()
+    return common
+
+
+class CudaBackend:
+    "SyntenyEngine backend on the CUDA library (the only backend the package ships)"
+
+    def __init__(self, ctx, genomes, names, contig_names, contig_lengths, k, common=None, repeat=None):
+        self.ctx, self.genomes = ctx, genomes
+        self.names = list(names)
+        self.contig_names = contig_names
+        self.contig_lengths = contig_lengths
+        self.k = k
+        self.common, self.repeat = common, repeat
+        self.tables = {}          # round-0 device tables, consumed by join()
+        self.timing = {"sketch_ms": 0.0, "join_ms": 0.0}
+
+    def sketch(self, a, w, masks):
+        t0 = time.perf_counter()
+        mx = self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, repeat=None, masks=masks)
+        self.timing["sketch_ms"] += (time.perf_counter() - t0) * 1e3
+        if masks is None:
+            return mx                      # round 0: stays on the device for the join
+        out = mx.to_numpy()
+        mx.close()
+        return out
+
+    def join(self, tables, order_asm):
+        t0 = time.perf_counter()
+        g = device.MinimizerGraph(self.ctx, tables, order_asm)
+        res = g.vertices()
+        g.close()
+        for t in tables:
+            t.close()
+        self.timing["join_ms"] += (time.perf_counter() - t0) * 1e3
+        return res
+
+
+def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="10000", block_size=500, fpr=0.025,
+               prefix="ntSynt", simplify=True, common=True, device_index=0, write_files=True, quiet=True,
+               packed=None, ctx=None):
+    """The whole path for `fastas` (paths; .gz accepted).  Returns (final_tsv_text, engine).
+    `packed`: optional pre-parsed fasta.PackedGenome list (same order as `fastas`)."""
+    own_ctx = ctx is None
+    ctx = ctx or device.Context(device_index)
+    if packed is None:
+        packed = [fasta.read_fasta(f) for f in fastas]
+    bases = [os.path.basename(f)[:-3] if f.endswith(".gz") else os.path.basename(f) for f in fastas]
+    names = [tsv_name(b, k, w) for b in bases]
+    order = processing_order(names)
+    genomes = [ctx.upload(p) for p in packed]
+    bf = build_common_bf(ctx, genomes, bases, k, fpr) if common else None
+    be = CudaBackend(ctx, [genomes[i] for i in order], [names[i] for i in order],
+                     [packed[i].names for i in order], [[int(x) for x in packed[i].lengths] for i in order], k,
+                     common=bf)
+    eng = SyntenyEngine(be, k, w, list(w_rounds), indel, merge, block_size, simplify=simplify, prefix=prefix,
+                        write_files=write_files, quiet=quiet)
+    out = eng.run()
+    eng.backend_timing = be.timing
+    if bf is not None:
+        bf.close()
+    for g in genomes:
+        g.close()
+    if own_ctx:
+        ctx.close()
+    return out, eng
