@@ -55,6 +55,19 @@ int nts_timer_stop(nts_ctx* ctx, float* ms_out);
 uint64_t nts_launch_count(const nts_ctx* ctx);
 /* free / total device memory in bytes */
 int nts_mem_info(nts_ctx* ctx, uint64_t* free_b, uint64_t* total_b);
+/* Per-kernel-family device timing with CUDA events on the context's stream (bench.py's roofline
+ * leg).  Families: nts_prof_name(0..nts_prof_count()-1).  units = k-mers / bytes / items the
+ * launches processed (family specific). */
+int nts_prof_enable(nts_ctx* ctx, int on);
+int nts_prof_reset(nts_ctx* ctx); /* also zeroes the transfer counters */
+int nts_prof_count(void);
+const char* nts_prof_name(int id);
+int nts_prof_get(nts_ctx* ctx, int id, double* ms, double* units, uint64_t* launches);
+/* bytes moved host->device / device->host by this library on this context */
+int nts_xfer_bytes(const nts_ctx* ctx, uint64_t* h2d, uint64_t* d2h);
+/* page-locked host memory for genome uploads */
+int nts_host_alloc(uint64_t bytes, void** out);
+void nts_host_free(void* p);
 
 /* -------------------------------------------------------------------------------- ingest
  * Replaces btllib::SeqReader as used at src/ntsynt_make_common_bf.cpp:32-36,125,143 and
@@ -88,6 +101,30 @@ int nts_genome_download_contig(nts_genome* g, uint32_t contig, uint64_t* words_o
 /* N runs of the whole genome, same layout as nts_genome_upload's arguments */
 int nts_genome_nruns(nts_genome* g, uint64_t* nrun_off /*[n_contigs+1]*/, uint64_t* nrun_start, uint64_t* nrun_len,
                      uint64_t cap, uint64_t* n_out);
+
+/* Synthetic genome materialised on the device from a segment table (bench.py workloads).
+ * Output base j of contig c is addressed by the segment covering j: a copy of an ancestor base
+ * (strand +1) or of its complement walking backwards (strand -1), substituted with probability
+ * sub_rate; a random inserted base (anc_contig == -1); or N (anc_contig == -2).  The ancestor is a
+ * pure function of (anc_seed, contig, position): i.i.d. bases with P(A)=P(T)=0.295,
+ * P(C)=P(G)=0.205 overlaid with copies of n_repeat_fam repeat families (300 bp and 6 kbp), one
+ * copy per 8 kbp slot with probability repeat_slot_prob, each copy mutated at 10 %.
+ * segs: [n_seg] sorted by (dst_contig, dst_start), tiling every contig without gaps. */
+typedef struct {
+    uint32_t dst_contig;
+    int32_t anc_contig;   /* >=0 ancestor contig; -1 random insert; -2 N run */
+    uint64_t dst_start;   /* contig-local start in the new genome */
+    uint64_t anc_start;   /* ancestor coordinate of the segment's FIRST output base */
+    uint64_t len;
+    int32_t strand;       /* +1 forward, -1 reverse complement (ancestor coordinate then decreases) */
+    uint32_t pad;
+} nts_synth_seg;
+int nts_genome_synthesize(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const nts_synth_seg* segs,
+                          uint64_t n_seg, uint64_t anc_seed, uint64_t genome_seed, double sub_rate,
+                          uint32_t n_repeat_fam, double repeat_slot_prob, nts_genome** out);
+/* host evaluation of the ancestor formula (tests) */
+int nts_synth_ancestor_base(uint64_t anc_seed, uint32_t n_repeat_fam, double repeat_slot_prob, uint32_t contig,
+                            uint64_t pos);
 
 /* -------------------------------------------------------------------------------- Bloom filter
  * Replaces btllib::KmerBloomFilter(bytes, 1, k) as used by src/ntsynt_make_common_bf.cpp. */

@@ -48,6 +48,14 @@ _SIGS = {
     "nts_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "nts_launch_count": (C.c_uint64, [vp]),
     "nts_mem_info": (C.c_int, [vp, u64p, u64p]),
+    "nts_prof_enable": (C.c_int, [vp, C.c_int]),
+    "nts_prof_reset": (C.c_int, [vp]),
+    "nts_prof_count": (C.c_int, []),
+    "nts_prof_name": (C.c_char_p, [C.c_int]),
+    "nts_prof_get": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), u64p]),
+    "nts_xfer_bytes": (C.c_int, [vp, u64p, u64p]),
+    "nts_host_alloc": (C.c_int, [C.c_uint64, vpp]),
+    "nts_host_free": (None, [vp]),
     "nts_packed_words": (C.c_uint64, [C.c_uint64]),
     "nts_pack_ascii": (C.c_int, [C.c_char_p, C.c_uint64, u64p, u64p, u64p, C.c_uint64, u64p]),
     "nts_unpack_ascii": (C.c_int, [u64p, C.c_uint64, C.c_uint64, C.c_char_p]),
@@ -57,6 +65,9 @@ _SIGS = {
     "nts_genome_contigs": (C.c_uint32, [vp]),
     "nts_genome_download_contig": (C.c_int, [vp, C.c_uint32, u64p]),
     "nts_genome_nruns": (C.c_int, [vp, u64p, u64p, u64p, C.c_uint64, u64p]),
+    "nts_genome_synthesize": (C.c_int, [vp, C.c_uint32, u64p, C.POINTER(SynthSeg), C.c_uint64, C.c_uint64, C.c_uint64,
+                                        C.c_double, C.c_uint32, C.c_double, vpp]),
+    "nts_synth_ancestor_base": (C.c_int, [C.c_uint64, C.c_uint32, C.c_double, C.c_uint32, C.c_uint64]),
     "nts_bf_bytes": (C.c_uint64, [C.c_int64, C.c_double]),
     "nts_bf_create": (C.c_int, [vp, C.c_uint64, vpp]),
     "nts_bf_destroy": (None, [vp]),

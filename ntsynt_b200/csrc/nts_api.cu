@@ -226,6 +226,67 @@ int nts_mem_info(nts_ctx* ctx, uint64_t* free_b, uint64_t* total_b)
     return NTS_OK;
 }
 
+int nts_prof_enable(nts_ctx* ctx, int on)
+{
+    if (!ctx) return fail(NTS_ERR_ARG, "null argument");
+    ctx->prof_enabled = on != 0;
+    return NTS_OK;
+}
+
+int nts_prof_reset(nts_ctx* ctx)
+{
+    if (!ctx) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto& p : ctx->prof_pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    ctx->prof_pending.clear();
+    for (int i = 0; i < PROF_COUNT; ++i) { ctx->prof_ms[i] = 0; ctx->prof_units[i] = 0; ctx->prof_launches[i] = 0; }
+    ctx->h2d_bytes = ctx->d2h_bytes = 0;
+    return NTS_OK;
+}
+
+static const char* const PROF_NAMES[PROF_COUNT] = {"fill", "bf_insert", "bf_combine", "sketch", "sketch_post", "join",
+                                                   "synth", "popcount", "bf_repeat", "edges", "nccl"};
+
+int nts_prof_count(void) { return PROF_COUNT; }
+const char* nts_prof_name(int id) { return (id >= 0 && id < PROF_COUNT) ? PROF_NAMES[id] : ""; }
+
+int nts_prof_get(nts_ctx* ctx, int id, double* ms, double* units, uint64_t* launches)
+{
+    if (!ctx || id < 0 || id >= PROF_COUNT) return fail(NTS_ERR_ARG, "bad argument");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->prof_pending.empty()) {
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (auto& p : ctx->prof_pending) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, p.e0, p.e1) == cudaSuccess) { ctx->prof_ms[p.id] += t; ctx->prof_units[p.id] += p.units; }
+            cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+        }
+        ctx->prof_pending.clear();
+    }
+    if (ms) *ms = ctx->prof_ms[id];
+    if (units) *units = ctx->prof_units[id];
+    if (launches) *launches = ctx->prof_launches[id];
+    return NTS_OK;
+}
+
+int nts_xfer_bytes(const nts_ctx* ctx, uint64_t* h2d, uint64_t* d2h)
+{
+    if (!ctx) return fail(NTS_ERR_ARG, "null argument");
+    if (h2d) *h2d = ctx->h2d_bytes;
+    if (d2h) *d2h = ctx->d2h_bytes;
+    return NTS_OK;
+}
+
+int nts_host_alloc(uint64_t bytes, void** out)
+{
+    if (!out) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return NTS_OK;
+}
+
+void nts_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 // ------------------------------------------------------------------------------------ ingest (host)
 uint64_t nts_packed_words(uint64_t n_bases) { return ((n_bases + 63) / 64) * 2; }
 
@@ -308,7 +369,7 @@ int nts_genome_upload(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_l
     if (g->packed.alloc(n_words + 2) != cudaSuccess) { delete g; return fail(NTS_ERR_NOMEM, "device allocation failed (genome)"); }
     cudaError_t e = cudaMemsetAsync(g->packed.p + n_words, 0, 16, ctx->stream);
     if (e == cudaSuccess && n_words)
-        e = cudaMemcpyAsync(g->packed.p, words, n_words * 8, cudaMemcpyHostToDevice, ctx->stream);
+        e = copy_h2d(ctx, g->packed.p, words, n_words * 8);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { delete g; return fail(NTS_ERR_CUDA, std::string("genome upload: ") + cudaGetErrorString(e)); }
     *out = g;
@@ -330,8 +391,8 @@ int nts_genome_download_contig(nts_genome* g, uint32_t contig, uint64_t* words_o
 {
     if (!g || contig >= g->n_contigs || !words_out) return fail(NTS_ERR_ARG, "bad argument");
     NTS_CUDA(cudaSetDevice(g->ctx->device));
-    NTS_CUDA(cudaMemcpyAsync(words_out, g->packed.p + g->contig_word_off[contig],
-                             nts_packed_words(g->contig_len[contig]) * 8, cudaMemcpyDeviceToHost, g->ctx->stream));
+    NTS_CUDA(copy_d2h(g->ctx, words_out, g->packed.p + g->contig_word_off[contig],
+                      nts_packed_words(g->contig_len[contig]) * 8));
     NTS_CUDA(cudaStreamSynchronize(g->ctx->stream));
     return NTS_OK;
 }
@@ -364,6 +425,7 @@ static int bf_fill(nts_bf* bf, uint32_t v)
 {
     nts_ctx* ctx = bf->ctx;
     uint64_t n16 = bf->alloc_bytes / 16;
+    ProfScope prof(ctx, PROF_FILL, (double)bf->alloc_bytes);
     fill_u128_kernel<<<grid_for(ctx, n16, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(bf->words.p), n16, v);
     ctx->launches++;
     NTS_CUDA(cudaGetLastError());
@@ -436,6 +498,7 @@ int nts_bf_insert_genome_async(nts_bf* bf, const nts_genome* g, uint32_t k)
     const uint32_t chunk = 32;
     uint64_t blocks = (v->total_valid + (uint64_t)THREADS * chunk - 1) / ((uint64_t)THREADS * chunk);
     if (blocks > 0x7FFFFFFFull) return fail(NTS_ERR_ARG, "genome too large for one launch");
+    ProfScope prof(ctx, PROF_BF_INSERT, (double)v->total_valid);
     bf_insert_kernel<THREADS><<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(device_view(g, v), tabs, bf->words.p, m, mp,
                                                                             v->total_valid, chunk);
     ctx->launches++;
@@ -459,6 +522,7 @@ static int bf_combine(nts_bf* dst, const nts_bf* src, int op, bool sync)
     nts_ctx* ctx = dst->ctx;
     NTS_CUDA(cudaSetDevice(ctx->device));
     uint64_t n16 = dst->alloc_bytes / 16;
+    ProfScope prof(ctx, PROF_BF_COMBINE, (double)dst->alloc_bytes);
     bf_combine_kernel<<<grid_for(ctx, n16 / 4 + 1, 256, 16), 256, 0, ctx->stream>>>(
         reinterpret_cast<uint4*>(dst->words.p), reinterpret_cast<const uint4*>(src->words.p), n16, op);
     ctx->launches++;
@@ -491,6 +555,7 @@ int nts_bf_insert_repeats(nts_bf* rep, nts_bf* scratch, const nts_genome* g, uin
         constexpr int THREADS = 256;
         const uint32_t chunk = 32;
         uint64_t blocks = (v->total_valid + (uint64_t)THREADS * chunk - 1) / ((uint64_t)THREADS * chunk);
+        ProfScope prof(ctx, PROF_BF_REPEAT, (double)v->total_valid);
         bf_repeat_kernel<THREADS><<<(unsigned)blocks, THREADS, 0, ctx->stream>>>(
             device_view(g, v), tabs, scratch->words.p, rep->words.p, m, mp, v->total_valid, chunk);
         ctx->launches++;
@@ -509,6 +574,7 @@ int nts_bf_popcount(nts_bf* bf, uint64_t* bits_set)
     if (acc.alloc(1) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed");
     NTS_CUDA(cudaMemsetAsync(acc.p, 0, 8, ctx->stream));
     uint64_t n16 = bf->alloc_bytes / 16;
+    ProfScope prof(ctx, PROF_POPCOUNT, (double)bf->alloc_bytes);
     bf_popcount_kernel<<<grid_for(ctx, n16, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(bf->words.p),
                                                                             n16, acc.p);
     ctx->launches++;
@@ -524,7 +590,7 @@ int nts_bf_download(nts_bf* bf, uint8_t* bytes_out)
 {
     if (!bf || !bytes_out) return fail(NTS_ERR_ARG, "null argument");
     NTS_CUDA(cudaSetDevice(bf->ctx->device));
-    NTS_CUDA(cudaMemcpyAsync(bytes_out, bf->words.p, bf->bytes, cudaMemcpyDeviceToHost, bf->ctx->stream));
+    NTS_CUDA(copy_d2h(bf->ctx, bytes_out, bf->words.p, bf->bytes));
     NTS_CUDA(cudaStreamSynchronize(bf->ctx->stream));
     return NTS_OK;
 }
@@ -533,7 +599,7 @@ int nts_bf_upload(nts_bf* bf, const uint8_t* bytes_in)
 {
     if (!bf || !bytes_in) return fail(NTS_ERR_ARG, "null argument");
     NTS_CUDA(cudaSetDevice(bf->ctx->device));
-    NTS_CUDA(cudaMemcpyAsync(bf->words.p, bytes_in, bf->bytes, cudaMemcpyHostToDevice, bf->ctx->stream));
+    NTS_CUDA(copy_h2d(bf->ctx, bf->words.p, bytes_in, bf->bytes));
     NTS_CUDA(cudaStreamSynchronize(bf->ctx->stream));
     return NTS_OK;
 }
@@ -615,7 +681,7 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     if (d_tiles.alloc(n_tiles) != cudaSuccess || d_off.alloc(n_tiles) != cudaSuccess || d_cnt.alloc(n_tiles) != cudaSuccess ||
         d_dst.alloc(n_tiles) != cudaSuccess || d_total.alloc(1) != cudaSuccess)
         return fail(NTS_ERR_NOMEM, "device allocation failed (tiles)");
-    NTS_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, ctx->stream));
+    NTS_CUDA(copy_h2d(ctx, d_tiles.p, tiles.data(), (size_t)n_tiles * sizeof(TileDesc)));
 
     uint64_t m = 0, mp = 0;
     if (common) mod_params(common, &m, &mp); else if (repeat) mod_params(repeat, &m, &mp);
@@ -642,10 +708,13 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
         SketchOut so;
         so.h1 = u_h1.p; so.pos = u_pos.p; so.contig = u_ctg.p;
         so.tile_off = d_off.p; so.tile_cnt = d_cnt.p; so.total = d_total.p; so.cap = cap;
-        sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(
-            device_view(g, v), tabs, common ? common->words.p : nullptr, repeat ? repeat->words.p : nullptr, m, mp,
-            d_tiles.p, w, T, so);
-        ctx->launches++;
+        {
+            ProfScope prof(ctx, PROF_SKETCH, (double)v->total_valid);
+            sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(
+                device_view(g, v), tabs, common ? common->words.p : nullptr, repeat ? repeat->words.p : nullptr, m, mp,
+                d_tiles.p, w, T, so);
+            ctx->launches++;
+        }
         NTS_CUDA(cudaGetLastError());
         NTS_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         NTS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -656,6 +725,7 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     mx->count = total;
     if (mx->h1.alloc(total) != cudaSuccess || mx->pos.alloc(total) != cudaSuccess || mx->contig.alloc(total) != cudaSuccess)
         return fail(NTS_ERR_NOMEM, "device allocation failed (minimizer table)");
+    ProfScope prof_post(ctx, PROF_SKETCH_POST, (double)total);
     tile_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt.p, d_dst.p, n_tiles);
     ctx->launches++;
     NTS_CUDA(cudaGetLastError());
@@ -687,9 +757,9 @@ int nts_mxs_download(nts_mxs* m, uint64_t* h1, uint32_t* pos, uint32_t* contig)
     if (m->count == 0) return NTS_OK;
     NTS_CUDA(cudaSetDevice(m->ctx->device));
     cudaStream_t st = m->ctx->stream;
-    if (h1) NTS_CUDA(cudaMemcpyAsync(h1, m->h1.p, m->count * 8, cudaMemcpyDeviceToHost, st));
-    if (pos) NTS_CUDA(cudaMemcpyAsync(pos, m->pos.p, m->count * 4, cudaMemcpyDeviceToHost, st));
-    if (contig) NTS_CUDA(cudaMemcpyAsync(contig, m->contig.p, m->count * 4, cudaMemcpyDeviceToHost, st));
+    if (h1) NTS_CUDA(copy_d2h(m->ctx, h1, m->h1.p, m->count * 8));
+    if (pos) NTS_CUDA(copy_d2h(m->ctx, pos, m->pos.p, m->count * 4));
+    if (contig) NTS_CUDA(copy_d2h(m->ctx, contig, m->contig.p, m->count * 4));
     NTS_CUDA(cudaStreamSynchronize(st));
     return NTS_OK;
 }

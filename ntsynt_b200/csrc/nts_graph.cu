@@ -280,6 +280,7 @@ int nts_graph_build(nts_ctx* ctx, nts_mxs* const* tables, uint32_t n_asm, uint32
     if (!g) return fail(NTS_ERR_NOMEM, "host allocation failed");
     struct Guard { nts_graph* p; ~Guard() { delete p; } } guard{g};
     g->ctx = ctx; g->n_asm = n_asm; g->order_asm = order_asm;
+    ProfScope prof(ctx, PROF_JOIN, (double)total);
     uint64_t cap = 1024;
     while (cap < total * 2) cap <<= 1;
     if (cap > 0x80000000ull) return fail(NTS_ERR_ARG, "too many minimizers for the join table");
@@ -364,12 +365,12 @@ int nts_graph_download_vertices(nts_graph* g, uint64_t* h1, uint32_t* pos, uint3
     NTS_CUDA(cudaSetDevice(g->ctx->device));
     cudaStream_t st = g->ctx->stream;
     const uint64_t V = g->V, VA = V * g->n_asm;
-    if (h1) NTS_CUDA(cudaMemcpyAsync(h1, g->v_h1.p, V * 8, cudaMemcpyDeviceToHost, st));
-    if (pos) NTS_CUDA(cudaMemcpyAsync(pos, g->v_pos.p, VA * 4, cudaMemcpyDeviceToHost, st));
-    if (contig) NTS_CUDA(cudaMemcpyAsync(contig, g->v_ctg.p, VA * 4, cudaMemcpyDeviceToHost, st));
-    if (rank) NTS_CUDA(cudaMemcpyAsync(rank, g->v_rank.p, VA * 4, cudaMemcpyDeviceToHost, st));
-    if (link) NTS_CUDA(cudaMemcpyAsync(link, g->link.p, V, cudaMemcpyDeviceToHost, st));
-    if (degree) NTS_CUDA(cudaMemcpyAsync(degree, g->degree.p, V, cudaMemcpyDeviceToHost, st));
+    if (h1) NTS_CUDA(copy_d2h(g->ctx, h1, g->v_h1.p, V * 8));
+    if (pos) NTS_CUDA(copy_d2h(g->ctx, pos, g->v_pos.p, VA * 4));
+    if (contig) NTS_CUDA(copy_d2h(g->ctx, contig, g->v_ctg.p, VA * 4));
+    if (rank) NTS_CUDA(copy_d2h(g->ctx, rank, g->v_rank.p, VA * 4));
+    if (link) NTS_CUDA(copy_d2h(g->ctx, link, g->link.p, V));
+    if (degree) NTS_CUDA(copy_d2h(g->ctx, degree, g->degree.p, V));
     NTS_CUDA(cudaStreamSynchronize(st));
     return NTS_OK;
 }
@@ -381,6 +382,7 @@ static int build_edges(nts_graph* g)
     const uint64_t V = g->V, N = V * g->n_asm;
     g->E = 0;
     if (N) {
+        ProfScope prof(ctx, PROF_EDGES, (double)N);
         DevBuf<uint32_t> is_new, off;
         if (is_new.alloc(N) != cudaSuccess || off.alloc(N) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (edges)");
         graph_edge_flags_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(g->v_ctg.p, g->v_rank.p, g->inv.p, V, g->n_asm, is_new.p);

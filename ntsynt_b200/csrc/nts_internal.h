@@ -45,8 +45,21 @@ struct DevBuf {
 
 }  // namespace nts
 
+namespace nts {
+// per-kernel-family device timing (CUDA events on the context's stream), off unless enabled
+enum ProfId { PROF_FILL = 0, PROF_BF_INSERT, PROF_BF_COMBINE, PROF_SKETCH, PROF_SKETCH_POST, PROF_JOIN, PROF_SYNTH,
+              PROF_POPCOUNT, PROF_BF_REPEAT, PROF_EDGES, PROF_NCCL, PROF_COUNT };
+struct ProfPending { int id; cudaEvent_t e0, e1; double units; };
+}  // namespace nts
+
 struct nts_ctx {
     int device = 0;
+    bool prof_enabled = false;
+    std::vector<nts::ProfPending> prof_pending;
+    double prof_ms[nts::PROF_COUNT] = {0};
+    double prof_units[nts::PROF_COUNT] = {0};
+    uint64_t prof_launches[nts::PROF_COUNT] = {0};
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
@@ -55,6 +68,32 @@ struct nts_ctx {
 };
 
 // valid k-mers of a genome for one (k, mask), laid out in valid-index space
+namespace nts {
+// RAII: times everything launched on ctx->stream during its lifetime under one ProfId
+struct ProfScope {
+    nts_ctx* ctx; int id; cudaEvent_t e0 = nullptr, e1 = nullptr; double units; uint64_t launches0;
+    ProfScope(nts_ctx* c, int i, double u = 0) : ctx(c), id(i), units(u), launches0(c->launches)
+    {
+        if (ctx->prof_enabled) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
+    }
+    ~ProfScope()
+    {
+        ctx->prof_launches[id] += ctx->launches - launches0;
+        if (ctx->prof_enabled) { cudaEventRecord(e1, ctx->stream); ctx->prof_pending.push_back({id, e0, e1, units}); }
+    }
+};
+inline cudaError_t copy_h2d(nts_ctx* ctx, void* dst, const void* src, size_t n)
+{
+    ctx->h2d_bytes += n;
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream);
+}
+inline cudaError_t copy_d2h(nts_ctx* ctx, void* dst, const void* src, size_t n)
+{
+    ctx->d2h_bytes += n;
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, ctx->stream);
+}
+}  // namespace nts
+
 struct nts_view {
     uint32_t k = 0;
     nts::DevBuf<uint64_t> seg_v, seg_base;

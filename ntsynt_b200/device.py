@@ -286,3 +286,110 @@ class MinimizerGraph:
             self.close()
         except Exception:  # pylint: disable=broad-except
             pass
+
+
+def _genome_nruns(self):
+    "(nrun_off[n_contigs+1], nrun_start, nrun_len) of a device genome"
+    off = np.zeros(self.n_contigs + 1, dtype=np.uint64)
+    n = C.c_uint64()
+    check(lib.nts_genome_nruns(self._h, ptr(off, C.c_uint64), None, None, 0, C.byref(n)))
+    cap = max(int(n.value), 1)
+    st = np.zeros(cap, dtype=np.uint64)
+    ln = np.zeros(cap, dtype=np.uint64)
+    check(lib.nts_genome_nruns(self._h, ptr(off, C.c_uint64), ptr(st, C.c_uint64), ptr(ln, C.c_uint64), cap,
+                               C.byref(n)))
+    return off, st[:n.value], ln[:n.value]
+
+
+def _genome_contig_words(self, contig):
+    nw = int(lib.nts_packed_words(int(self.lengths[contig])))
+    words = np.zeros(max(nw, 1), dtype=np.uint64)
+    check(lib.nts_genome_download_contig(self._h, int(contig), ptr(words, C.c_uint64)))
+    return words[:nw]
+
+
+def _genome_contig_ascii(self, contig, start=0, length=None):
+    "ASCII of (part of) a contig, N runs restored -- for host-side consumers (CPU baseline, --seq output)"
+    L = int(self.lengths[contig])
+    length = L - start if length is None else min(length, L - start)
+    words = self.contig_words(contig)
+    buf = C.create_string_buffer(max(length, 1))
+    check(lib.nts_unpack_ascii(ptr(words, C.c_uint64), int(start), int(length), buf))
+    seq = bytearray(buf.raw[:length])
+    off, st, ln = self.nruns()
+    for i in range(int(off[contig]), int(off[contig + 1])):
+        a, b = max(int(st[i]), start), min(int(st[i] + ln[i]), start + length)
+        if a < b:
+            seq[a - start:b - start] = b"N" * (b - a)
+    return bytes(seq)
+
+
+def _genome_to_packed(self):
+    "host copy (fasta.PackedGenome) of a device genome"
+    from .fasta import PackedGenome
+    parts, woff, off = [], [], 0
+    for c in range(self.n_contigs):
+        w = self.contig_words(c)
+        parts.append(w); woff.append(off); off += len(w)
+    no, ns, nl = self.nruns()
+    return PackedGenome(self.names, self.lengths, woff, np.concatenate(parts) if parts else np.zeros(0, np.uint64),
+                        no, ns, nl)
+
+
+DeviceGenome.nruns = _genome_nruns
+DeviceGenome.contig_words = _genome_contig_words
+DeviceGenome.contig_ascii = _genome_contig_ascii
+DeviceGenome.to_packed = _genome_to_packed
+
+
+# ---- profiling / transfer counters / pinned memory (bench.py)
+def _ctx_prof_enable(self, on=True):
+    check(lib.nts_prof_enable(self._h, 1 if on else 0))
+
+
+def _ctx_prof_reset(self):
+    check(lib.nts_prof_reset(self._h))
+
+
+def _ctx_prof(self):
+    "{family: (ms, units, launches)} accumulated since the last reset"
+    out = {}
+    for i in range(lib.nts_prof_count()):
+        ms, units, n = C.c_double(), C.c_double(), C.c_uint64()
+        check(lib.nts_prof_get(self._h, i, C.byref(ms), C.byref(units), C.byref(n)))
+        out[lib.nts_prof_name(i).decode()] = (ms.value, units.value, n.value)
+    return out
+
+
+def _ctx_xfer(self):
+    a, b = C.c_uint64(), C.c_uint64()
+    check(lib.nts_xfer_bytes(self._h, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+Context.prof_enable = _ctx_prof_enable
+Context.prof_reset = _ctx_prof_reset
+Context.prof = _ctx_prof
+Context.xfer_bytes = _ctx_xfer
+
+
+class PinnedU64:
+    "page-locked uint64 host array (genome words staged for H2D copies)"
+
+    def __init__(self, n):
+        p = C.c_void_p()
+        check(lib.nts_host_alloc(int(n) * 8, C.byref(p)))
+        self._p = p
+        self.array = np.ctypeslib.as_array((C.c_uint64 * max(int(n), 1)).from_address(p.value))[:n]
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib.nts_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
