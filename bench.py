@@ -1,0 +1,434 @@
+#!/usr/bin/env python3
+"""bench.py -- genome bp/s through the sketch + Bloom-filter + graph path (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+
+A step = one pass of the whole hot path over one batch of synthetic genomes: Bloom-filter zero-fill,
+per-genome insert, merge, round-0 sketch, minimizer join + graph, every refinement round (masked
+re-sketch + graph), erosion, collinear merges, final block table as TSV text.
+
+N = 1  : BASELINE.json configs[1]: 2 synthetic ~3 Gbp human-like genomes, d = 1 %, k = 24, w = 1000,
+         presets of bin/ntSynt:92-94 (block_size 1000, indel 50000, merge 100000, w_rounds 250 100).
+N > 1  : configs[4]: one 3 Gbp genome per GPU (G = N), per-GPU Bloom filters merged over NCCL (sum of
+         packed counters), then every rank sketches its genome and rank 0 runs the graph stage on the
+         gathered tables.  Weak scaling: per-GPU work is fixed.
+
+`value` times the path with the packed genomes already resident in HBM; `e2e` times the same call
+chain starting from packed genomes in PINNED HOST memory (H2D inside the timed region) and ending
+with the TSV text on the host.  Timing: CUDA events on the library's stream, bracketed by barriers,
+max over ranks.  Inputs (1.5 GB of bases, 2 x 14.8 GB of filter) are far larger than the 126 MB L2,
+so no explicit L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "genome bp/sec through sketch+BF+graph path"
+K, W = 24, 1000
+
+
+def presets(divergence):
+    "bin/ntSynt:89-99"
+    if divergence < 1:
+        return dict(indel=10000, merge="10000", w_rounds=[100, 10], block_size=500)
+    if divergence <= 10:
+        return dict(indel=50000, merge="100000", w_rounds=[250, 100], block_size=1000)
+    return dict(indel=100000, merge="1000000", w_rounds=[500, 250], block_size=10000)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- distributed plumbing
+class Dist:
+    "torch.distributed (gloo) is used only for rendezvous, barriers and max-over-ranks"
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.td = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as td
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            td.init_process_group(backend="gloo", rank=self.rank, world_size=self.world)
+            self.td, self.torch = td, torch
+
+    def barrier(self):
+        if self.td:
+            self.td.barrier()
+
+    def max(self, x):
+        if not self.td:
+            return x
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64)
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum(self, x):
+        if not self.td:
+            return x
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64)
+        self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
+        return float(t[0])
+
+    def bcast_bytes(self, b, n):
+        if not self.td:
+            return b
+        t = self.torch.zeros(n, dtype=self.torch.uint8)
+        if self.rank == 0:
+            t = self.torch.frombuffer(bytearray(b), dtype=self.torch.uint8).clone()
+        self.td.broadcast(t, 0)
+        return bytes(t.numpy().tobytes())
+
+    def gather_objects(self, obj):
+        if not self.td:
+            return [obj]
+        out = [None] * self.world
+        self.td.all_gather_object(out, obj)
+        return out
+
+    def close(self):
+        if self.td:
+            self.td.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample_records(gens, sample_mbp_per_genome):
+    "first slice of every contig of every genome, as ASCII records (host copies of device genomes)"
+    out = []
+    for g in gens:
+        per = max(int(sample_mbp_per_genome * 1e6 / g.n_contigs), 20000)
+        out.append([(g.names[c], g.contig_ascii(c, 0, per)) for c in range(g.n_contigs)])
+    return out
+
+
+def cpu_path(records_per_genome, file_names, divergence, threads):
+    """The reference's CPU path restated (oracle/): make_common_bf (OpenMP over records, atomic byte-OR;
+    src/ntsynt_make_common_bf.cpp:122-160), indexlr per genome (5 threads, 2 genomes at a time;
+    bin/ntsynt_run_pipeline.smk:79-80, bin/ntSynt:154), then the graph stage (single-threaded Python,
+    bin/ntsynt_synteny.py:33).  Returns (seconds, total bases, final TSV text)."""
+    import ctypes as C
+    import numpy as np
+    from oracle import sketch_oracle as so
+    from oracle.graph_oracle import GraphOracle
+    L = so.lib()
+    ps = presets(divergence)
+    t0 = time.perf_counter()
+    order = sorted(range(len(file_names)), key=lambda i: file_names[i])
+    n0 = sum(len(s) for _, s in records_per_genome[order[0]])
+    nbytes = so.bf_bytes(n0, 0.025)
+    m = nbytes * 8
+
+    def rec_arrays(recs):
+        seqs = (C.c_char_p * len(recs))(*[s for _, s in recs])
+        lens = (C.c_size_t * len(recs))(*[len(s) for _, s in recs])
+        return seqs, lens
+    bits = np.zeros(nbytes, dtype=np.uint8)
+    seqs, lens = rec_arrays(records_per_genome[order[0]])
+    L.orc_common_bf_level1(so._u8p(bits), m, seqs, lens, len(lens), K, threads)
+    for i in order[1:]:
+        nxt = np.zeros(nbytes, dtype=np.uint8)
+        seqs, lens = rec_arrays(records_per_genome[i])
+        L.orc_common_bf_cascade(so._u8p(bits), so._u8p(nxt), m, seqs, lens, len(lens), K, threads)
+        bits = nxt
+    # round-0 indexlr: a worker per record, 5 threads per genome, 2 genomes at a time (smk:79-80, bin/ntSynt:154)
+    tsv = [f"{fn}.k{K}.w{W}.tsv" for fn in file_names]
+    round0 = {}
+
+    def sketch_one(gi):
+        recs = records_per_genome[gi]
+        seqs, lens = rec_arrays(recs)
+        caps = [max(64, 4 * (len(s) // W) + 64) for _, s in recs]
+        h1 = [np.empty(c, dtype=np.uint64) for c in caps]
+        ps_ = [np.empty(c, dtype=np.uint64) for c in caps]
+        u64p = C.POINTER(C.c_uint64)
+        h1p = (u64p * len(recs))(*[so._u64p(a) for a in h1])
+        pp = (u64p * len(recs))(*[so._u64p(a) for a in ps_])
+        capa = (C.c_size_t * len(recs))(*caps)
+        cnt = (C.c_size_t * len(recs))()
+        L.orc_sketch_records(seqs, lens, len(recs), K, W, so._u8p(bits), m, h1p, pp, capa, cnt, min(5, threads))
+        round0[tsv[gi]] = [(recs[i][0], [(str(int(h)), int(p)) for h, p in zip(h1[i][:cnt[i]], ps_[i][:cnt[i]])])
+                           for i in range(len(recs))]
+    pending = list(range(len(file_names)))
+    while pending:
+        batch, pending = pending[:2], pending[2:]
+        ths = [threading.Thread(target=sketch_one, args=(gi,)) for gi in batch]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    go = GraphOracle(list(zip(tsv, records_per_genome)), K, W, ps["w_rounds"], ps["indel"], ps["merge"],
+                     ps["block_size"], bits)
+    try:
+        text = go.run(round0=round0)
+    except SystemExit:
+        text = ""
+    dt = time.perf_counter() - t0
+    total = sum(len(s) for recs in records_per_genome for _, s in recs)
+    return dt, total, text
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, dist):
+    import numpy as np
+    from ntsynt_b200 import device, pipeline, synth
+    from ntsynt_b200.synteny import SyntenyEngine
+    N = dist.world
+    if N != args.gpus and dist.rank == 0 and N > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {N}", file=sys.stderr)
+    ctx = device.Context(dist.local_rank)
+    G = args.genomes or (2 if N == 1 else N)
+    d = args.divergence
+    ps = presets(d)
+    wl = synth.Workload(G, int(args.genome_mbp * 1e6), d, seed=args.seed)
+    file_names = [wl.file_name(g) for g in range(G)]
+    names = [pipeline.tsv_name(f, K, W) for f in file_names]
+    order = pipeline.processing_order(names)
+    my_ids = list(range(G)) if N == 1 else [g for g in range(G) if g % N == dist.rank]
+    if N > 1:
+        raise SystemExit("multi-GPU bench requires the NCCL merge (nts_bf_allreduce_and); see DESIGN.md")
+    gens = {g: wl.materialize(ctx, g) for g in my_ids}
+    total_bp = sum(int(x.total_bases) for x in gens.values())
+    size_sorted = sorted(range(G), key=lambda i: file_names[i])
+    nbytes = device.BloomFilter.size_for(gens[size_sorted[0]].total_bases, 0.025)
+    common, level = ctx.bloom(nbytes), ctx.bloom(nbytes)
+
+    def hot_path(gen_list):
+        # src/ntsynt_make_common_bf.cpp:107-160 on resident genomes, filters re-zeroed every step
+        common.clear()
+        common.insert_genome(gen_list[size_sorted[0]], K)
+        for i in size_sorted[1:]:
+            level.clear()
+            level.insert_genome(gen_list[i], K)
+            common.iand(level)
+        be = pipeline.CudaBackend(ctx, [gen_list[i] for i in order], [names[i] for i in order], [wl.names] * G,
+                                  [[int(x) for x in gen_list[i].lengths] for i in order], K, common=common)
+        eng = SyntenyEngine(be, K, W, ps["w_rounds"], ps["indel"], ps["merge"], ps["block_size"], write_files=False,
+                            quiet=True)
+        text = eng.run()
+        return text, eng
+
+    gen_list = [gens[g] for g in range(G)]
+    # ---- warm-up (untimed)
+    for _ in range(max(args.warmup, 0)):
+        text, eng = hot_path(gen_list)
+    # ---- timed: inputs resident in HBM
+    ctx.prof_enable(True)
+    ctx.prof_reset()
+    launches0 = ctx.launches
+    clocks = ClockSampler(dist.local_rank)
+    dist.barrier(); ctx.sync()
+    ctx.timer_start()
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        text, eng = hot_path(gen_list)
+    ms = ctx.timer_stop()
+    wall = time.perf_counter() - t_wall
+    ctx.sync(); dist.barrier()
+    ms = dist.max(ms)
+    launches = ctx.launches - launches0
+    prof = ctx.prof()
+    ctx.prof_enable(False)
+    value = dist.sum(total_bp) * args.steps / (ms / 1e3)
+
+    # ---- e2e: packed genomes start in pinned host memory; result text ends on the host
+    packed_host = []
+    for g in range(G):
+        pk = gens[g].to_packed()
+        pin = device.PinnedU64(len(pk.words))
+        pin.array[:] = pk.words
+        pk.words = pin.array
+        packed_host.append((pk, pin))
+    ctx.prof_reset()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    dist.barrier(); ctx.sync()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        fresh = [ctx.upload(pk) for pk, _ in packed_host]
+        text_e2e, _ = hot_path(fresh)
+        for f in fresh:
+            f.close()
+    ms_e2e = dist.max(ctx.timer_stop())
+    h2d, d2h = ctx.xfer_bytes()
+    clk = clocks.stop()
+    e2e_value = dist.sum(total_bp) * e2e_steps / (ms_e2e / 1e3)
+    assert text_e2e == text, "e2e and resident runs disagree"
+
+    # ---- roofline of the dominant kernel family (CUDA events around every launch, same timed region)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json"), encoding="utf-8") as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    # algorithmic bytes per unit: S = 0.25 B per packed base, 32 B sector
+    alg = {"bf_insert": 64.25, "sketch": 32.25, "bf_combine": 3.0, "fill": 1.0}
+    fam = max((f for f in alg if prof[f][2]), key=lambda f: prof[f][0])
+    f_ms, f_units, f_n = prof[fam]
+    achieved = (alg[fam] * f_units / f_n) / ((f_ms / f_n) / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json"), encoding="utf-8") as fh:
+            tj = json.load(fh)
+        if tj.get("kernel") == fam and abs(tj.get("genome_mbp", 0) - args.genome_mbp) < 1:
+            traffic = tj.get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    roofline = {"kernel": fam, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[fam] * f_units / f_n, "avg_launch_ms": f_ms / f_n,
+                "kernel_ms_per_step": {f: round(prof[f][0] / args.steps, 3) for f in prof if prof[f][2]},
+                "kernel_share_of_step": round(f_ms / ms, 4)}
+
+    # ---- CPU baseline on rank 0 (bounded sample of the same workload)
+    cpu = None
+    if dist.rank == 0 and N == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        recs = cpu_sample_records(gen_list, args.cpu_sample_mbp)
+        dt, tot, _ = cpu_path(recs, file_names, d, threads)
+        cpu = {"value": tot / dt, "unit": "bp/s", "cores": threads, "kind": "port",
+               "sample": f"first {args.cpu_sample_mbp:g} Mbp of each of the {G} genomes ({tot} bp): oracle/ C+OpenMP "
+                         f"Bloom filter and sketch, pure-Python graph stage; {dt:.1f} s"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"{G} synthetic ~{args.genome_mbp:g} Mbp human-like genomes, d={d:g}, k={K} w={W}, "
+                               f"w_rounds {ps['w_rounds']}, 1xB200" if N == 1 else
+                               f"{G} synthetic {args.genome_mbp:g} Mbp genomes one-per-GPU, counting-BF NCCL-sum merge",
+                   "genomes": G, "genome_bp": total_bp // max(len(my_ids), 1), "k": K, "w": W, "fpr": 0.025,
+                   "bloom_bytes": nbytes, "l2": "inputs (bases + filters) are larger than L2; no flush needed",
+                   "blocks": text.count("\n") // G, "vertices": eng.stats.get("vertices")},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "bp/s", "h2d_bytes_per_step": h2d // e2e_steps,
+                "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "host_wall_ms_per_step": wall * 1e3 / args.steps,
+    }
+    if dist.rank == 0:
+        print(json.dumps(line))
+
+
+def run_reference(args, dist):
+    "CPU restatement of the reference path on a bounded sample of the same workload (rank 0 only)"
+    if dist.rank != 0:
+        return
+    from ntsynt_b200 import device, synth
+    N = dist.world
+    G = args.genomes or (2 if N == 1 else N)
+    d = args.divergence
+    ctx = device.Context(dist.local_rank)
+    wl = synth.Workload(G, int(args.genome_mbp * 1e6), d, seed=args.seed)
+    gens = [wl.materialize(ctx, g) for g in range(G)]
+    recs = cpu_sample_records(gens, args.cpu_sample_mbp)
+    for g in gens:
+        g.close()
+    ctx.close()
+    file_names = [wl.file_name(g) for g in range(G)]
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_path(recs, file_names, d, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, tot, _ = cpu_path(recs, file_names, d, threads)
+        t += dt
+    v = tot * args.steps / t
+    sample = (f"first {args.cpu_sample_mbp:g} Mbp of each of the {G} genomes ({tot} bp) per step; oracle/ C+OpenMP "
+              f"Bloom filter + sketch and pure-Python graph stage (btllib / python-igraph are not installable)")
+    ps = presets(d)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "bp/s", "n_gpus": N, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"{G} synthetic ~{args.genome_mbp:g} Mbp human-like genomes, d={d:g}, k={K} w={W}, "
+                               f"w_rounds {ps['w_rounds']} (bounded sample)", "genomes": G, "k": K, "w": W},
+        "cpu_baseline": {"value": v, "unit": "bp/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--genome-mbp", type=float, default=3000.0, help="size of each synthetic genome")
+    ap.add_argument("--genomes", type=int, default=0, help="number of genomes (default 2 at N=1, N otherwise)")
+    ap.add_argument("--divergence", type=float, default=1.0)
+    ap.add_argument("--seed", type=int, default=20260117)
+    ap.add_argument("--cpu-sample-mbp", type=float, default=24.0, help="per-genome sample for the CPU arm")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print("note: fewer than 3 warm-up steps; the number is not reportable", file=sys.stderr)
+    dist = Dist()
+    try:
+        if args.impl == "reference":
+            run_reference(args, dist)
+        else:
+            run_ours(args, dist)
+    finally:
+        dist.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -427,10 +427,12 @@ class GraphOracle:
         return out
 
     # ------------------------------------------------------------ driver
-    def run(self):
-        "bin/ntsynt_synteny.py:593-647"
+    def run(self, round0=None):
+        """bin/ntsynt_synteny.py:593-647.  round0: optional {tsv_name: sketch lines} made elsewhere (the
+        reference reads the round-0 sketches from the indexlr TSVs)"""
         for f in self.files:
-            self.info[f], self.lists[f] = read_minimizers(sketch_lists(self.genomes[f], self.k, self.w, self.common))
+            lines = round0[f] if round0 is not None else sketch_lists(self.genomes[f], self.k, self.w, self.common)
+            self.info[f], self.lists[f] = read_minimizers(lines)
         self.graph = build_graph(filter_minimizers(self.lists), self.weights)
         self.round0_edges = [(self.graph.vs[e.source]["name"], self.graph.vs[e.target]["name"], e["weight"])
                              for e in self.graph.es]

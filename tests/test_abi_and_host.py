@@ -1,0 +1,104 @@
+"""C-ABI surface and host-side logic that needs no GPU."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import MINI, mini_fastas
+from ntsynt_b200 import _lib, device, fasta, synth
+from oracle import sketch_oracle as so
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _lib.declared_symbols()
+    assert len(syms) >= 50
+    missing = [s for s in syms if not hasattr(_lib.lib, s)]
+    assert not missing, missing
+
+
+def test_every_declared_symbol_has_a_ctypes_signature():
+    assert sorted(_lib._SIGS) == _lib.declared_symbols()
+
+
+def test_no_cpu_fallback_without_a_device():
+    n = C.c_int()
+    rc = _lib.lib.nts_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_lib.NtsError):
+        device.Context(0)
+
+
+def test_bf_size_matches_reference_formula():
+    for n, fpr in [(29058289, 0.025), (3_000_000_000, 0.025), (123456, 0.01), (1, 0.5)]:
+        assert int(_lib.lib.nts_bf_bytes(n, fpr)) == so.bf_bytes(n, fpr)
+    assert int(_lib.lib.nts_bf_bytes(29058289, 0.025)) == 143467640
+
+
+def test_pack_unpack_roundtrip_and_n_runs():
+    seq = b"ACGTNNNNacgtRYACGT" * 7 + b"N"
+    g = fasta.pack_records([("c1", seq), ("c2", b"ACGT" * 50)])
+    assert g.total_bases == len(seq) + 200
+    text = g.contig_text(0)
+    want = seq.upper().replace(b"R", b"A").replace(b"Y", b"A").replace(b"N", b"A")
+    assert text == want
+    runs = [(int(s), int(l)) for s, l in zip(g.nrun_start[:int(g.nrun_off[1])], g.nrun_len[:int(g.nrun_off[1])])]
+    exp, i = [], 0
+    while i < len(seq):
+        if seq[i:i + 1].upper() not in (b"A", b"C", b"G", b"T"):
+            j = i
+            while j < len(seq) and seq[j:j + 1].upper() not in (b"A", b"C", b"G", b"T"):
+                j += 1
+            exp.append((i, j - i)); i = j
+        else:
+            i += 1
+    assert runs == exp
+    assert g.kmer_text(1, 3, 5) == "TACGT"
+    assert int(g.word_off[1]) % 2 == 0
+
+
+def test_fai_writer_matches_samtools_goldens(demo_dir, tmp_path):
+    for n in ["celegans-chrII-III.fa", "celegans-chrII-III.A.fa", "celegans-chrII-III.B.fa"]:
+        import gzip, shutil
+        plain = tmp_path / n
+        with gzip.open(os.path.join(demo_dir, n + ".gz"), "rb") as fi, open(plain, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+        g = fasta.read_fasta(str(plain))
+        out = tmp_path / (n + ".fai")
+        fasta.write_fai(g, str(out))
+        assert out.read_text() == open(os.path.join(demo_dir, "expected_result", n + ".fai")).read()
+
+
+def test_fai_writer_mini_fixture(tmp_path):
+    import gzip, shutil
+    plain = tmp_path / "miniA.fa"
+    with gzip.open(mini_fastas("AB")[0], "rb") as fi, open(plain, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    g = fasta.read_fasta(str(plain))
+    out = tmp_path / "miniA.fa.fai"
+    fasta.write_fai(g, str(out))
+    assert out.read_text() == open(os.path.join(MINI, "AB", "miniA.fa.fai")).read()
+
+
+def test_synth_segment_tables_tile_every_contig():
+    wl = synth.Workload(2, 3_000_000, 1.0, n_contigs=6)
+    for g in range(2):
+        lengths, segs = wl.segments(g)
+        assert segs.dtype.itemsize == C.sizeof(_lib.SynthSeg)
+        for c in range(6):
+            s = segs[segs["dst_contig"] == c]
+            assert s["dst_start"][0] == 0
+            assert (s["dst_start"][1:] == s["dst_start"][:-1] + s["len"][:-1]).all()
+            assert int(s["len"].sum()) == int(lengths[c])
+        assert (segs["strand"] == -1).any() and (segs["anc_contig"] == -1).any() and (segs["anc_contig"] == -2).any()
+    a = wl.segments(0)[1]
+    b = synth.Workload(2, 3_000_000, 1.0, n_contigs=6).segments(0)[1]
+    assert a.tobytes() == b.tobytes()          # deterministic
+
+
+def test_ancestor_formula_base_composition():
+    f = _lib.lib.nts_synth_ancestor_base
+    bases = np.array([f(1234, 0, 0.0, 0, p) for p in range(20000)])
+    frac = np.bincount(bases, minlength=4) / len(bases)
+    assert abs(frac[0] - 0.295) < 0.02 and abs(frac[1] - 0.205) < 0.02 and abs(frac[3] - 0.295) < 0.02

@@ -1,0 +1,86 @@
+"""Host-side graph logic of the product (ntsynt_b200/synteny.py) exercised without a GPU: the engine
+is fed by a TEST-ONLY backend (oracle sketches + numpy join, tests/backends.py).  The CUDA backend
+is covered by the -m gpu tests."""
+import os
+
+import numpy as np
+import pytest
+
+import synth_small
+from backends import OracleBackend, numpy_join
+from conftest import mini_expected, mini_fastas
+from ntsynt_b200.synteny import IntervalIndex, SyntenyEngine
+from oracle import sketch_oracle as so
+from oracle.graph_oracle import GraphOracle
+
+
+def run_engine(paths, k, w, w_rounds, indel, merge, z):
+    bases = [os.path.basename(p)[:-3] if p.endswith(".gz") else os.path.basename(p) for p in paths]
+    tsv = [f"{b}.k{k}.w{w}.tsv" for b in bases]
+    order = sorted(range(len(paths)), key=lambda i: tsv[i], reverse=True)
+    be = OracleBackend([paths[i] for i in order], [tsv[i] for i in order], k)
+    eng = SyntenyEngine(be, k, w, w_rounds, indel, merge, z, write_files=False, quiet=True)
+    eng.run()
+    return eng, be
+
+
+@pytest.mark.parametrize("tag", ["AB", "ABC"])
+def test_mini_against_reference_fixture(tag, mini_params):
+    p = mini_params
+    eng, _ = run_engine(mini_fastas(tag), p["k"], p["w"], p["w_rounds"], p["indel"], p["merge"], p["block_size"])
+    assert eng.outputs["final"] == mini_expected(tag, "synteny_blocks.tsv")
+    assert eng.outputs["pre_merge"] == mini_expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("k,names,gold", [
+    (24, ["celegans-chrII-III.fa", "celegans-chrII-III.A.fa"], "celegans-A-ntSynt"),
+    (20, ["celegans-chrII-III.fa", "celegans-chrII-III.A.fa", "celegans-chrII-III.B.fa"], "celegans-A-B-ntSynt")])
+def test_reference_golden_blocks(demo_dir, k, names, gold):
+    eng, _ = run_engine([os.path.join(demo_dir, n + ".gz") for n in names], k, 1000, [100, 10], 500, "3000", 500)
+    exp = os.path.join(demo_dir, "expected_result")
+    assert eng.outputs["final"] == open(os.path.join(exp, gold + ".synteny_blocks.tsv")).read()
+    assert eng.outputs["pre_merge"] == open(os.path.join(exp, gold + ".pre-collinear-merge.synteny_blocks.tsv")).read()
+
+
+@pytest.mark.parametrize("seed,G,presets", [(101, 2, "low"), (102, 3, "low"), (103, 4, "mid"), (104, 2, "mid"), (105, 5, "low")])
+def test_engine_equals_graph_oracle_on_rearranged_genomes(tmp_path, seed, G, presets):
+    "seeded genomes with inversions, translocations, duplications, N runs; d<1 and 1<=d<=10 style presets"
+    gens = synth_small.make_genomes(seed, G, contig_lens=(100000, 70000, 30000), sub=0.004 * (1 + seed % 3), n_inv=4,
+                                    n_trans=3, n_dup=3)
+    paths = []
+    for i, recs in enumerate(gens):
+        p = str(tmp_path / f"g{chr(65 + i)}.fa")
+        synth_small.write_fasta(p, recs)
+        paths.append(p)
+    k, w = 16, 40
+    w_rounds, indel, merge, z = ([20, 5], 300, "400", 200) if presets == "low" else ([25, 10], 2000, "2w", 400)
+    eng, be = run_engine(paths, k, w, w_rounds, indel, merge, z)
+    go = GraphOracle([(os.path.basename(p) + f".k{k}.w{w}.tsv", so.read_fasta(p)) for p in paths], k, w, w_rounds,
+                     indel, merge, z, be.bits)
+    go.run()
+    assert eng.outputs["final"] == go.outputs["final"]
+    assert eng.outputs["pre_merge"] == go.outputs["pre_merge"]
+    assert eng.outputs["final"].count("\n") >= G * 3
+
+
+def test_interval_index_matches_bruteforce():
+    rng = np.random.default_rng(5)
+    s = rng.integers(0, 1000, 40)
+    e = s + rng.integers(1, 60, 40)
+    ii = IntervalIndex(s, e)
+    a = rng.integers(0, 1100, 500)
+    b = a + rng.integers(1, 30, 500)
+    want = np.array([any(si < bi and ai < ei for si, ei in zip(s, e)) for ai, bi in zip(a, b)])
+    assert np.array_equal(ii.overlaps(a.astype(np.int64), b.astype(np.int64)), want)
+
+
+def test_numpy_join_semantics():
+    "dedup within an assembly, intersection across assemblies, numbering by the orienting assembly"
+    t0 = (np.array([5, 7, 7, 9, 11], dtype=np.uint64), np.arange(5, dtype=np.uint32) * 10, np.zeros(5, dtype=np.uint32))
+    t1 = (np.array([11, 9, 5, 13], dtype=np.uint64), np.arange(4, dtype=np.uint32) * 10, np.zeros(4, dtype=np.uint32))
+    H, POS, CTG, RANK, link, deg = numpy_join([t0, t1], 1)
+    assert list(H) == [11, 9, 5]            # order of assembly 1; 7 is duplicated in assembly 0, 13 is not common
+    assert list(POS[0]) == [40, 30, 0] and list(POS[1]) == [0, 10, 20]
+    assert list(RANK[0]) == [2, 1, 0]
+    assert list(link) == [1, 1, 0]

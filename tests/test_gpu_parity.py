@@ -1,0 +1,267 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the golden fixtures.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+import synth_small
+from backends import numpy_edges, numpy_join
+from conftest import MINI, mini_expected, mini_fastas, parse_sketch_tsv
+from ntsynt_b200 import _lib, device, fasta, pipeline, synth
+from oracle import sketch_oracle as so
+from oracle.graph_oracle import GraphOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _upload(ctx, records):
+    return ctx.upload(fasta.pack_records(records))
+
+
+def _tricky_records(seed=3):
+    "N runs, IUPAC codes, lower case, a contig shorter than k, one shorter than k+w-1, an all-N contig"
+    g = synth_small.make_genomes(seed, 1, contig_lens=(90000, 40000), n_nruns=6, lowercase=True)[0]
+    rng = np.random.default_rng(seed)
+    extra = bytearray(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 3000).tobytes())
+    extra[100:103] = b"RYK"
+    extra[2000:2001] = b"n"
+    return g + [("short", b"ACGTACGTAC"), ("mid", bytes(extra[:60])), ("iupac", bytes(extra)), ("allN", b"N" * 500),
+                ("empty", b"")]
+
+
+@pytest.mark.parametrize("k", [24, 20, 5, 33, 64])
+def test_nthash_kernel_matches_oracle(cuda_ctx, k):
+    recs = _tricky_records()
+    g = _upload(cuda_ctx, recs)
+    for c, (_, seq) in enumerate(recs):
+        h0, valid = cuda_ctx.hash_contig(g, c, k)
+        oh, ov = so.hash_seq(seq, k)
+        assert np.array_equal(valid, ov)
+        assert np.array_equal(h0[ov == 1], oh[ov == 1])
+
+
+def test_hash_known_answers_on_device(cuda_ctx):
+    "h1 of k-mers sampled from the reference's golden indexlr output, computed by the sketch kernel"
+    with open(os.path.join(os.path.dirname(MINI), "hash_kats.json"), encoding="utf-8") as fh:
+        kats = json.load(fh)["kats"]
+    for k in (24, 20):
+        sel = [(s, h) for s, kk, h in kats if kk == k][:400]
+        g = _upload(cuda_ctx, [(f"r{i}", s.encode()) for i, (s, _) in enumerate(sel)])
+        h1, pos, ctg = cuda_ctx.sketch(g, k, 1).to_numpy()       # w = 1: every k-mer is its own minimizer
+        assert list(ctg) == list(range(len(sel))) and not pos.any()
+        assert [int(x) for x in h1] == [int(h) for _, h in sel]
+
+
+@pytest.mark.parametrize("tag", ["AB", "ABC"])
+def test_bloom_filter_bits_match_oracle(cuda_ctx, tag, mini_params):
+    k = mini_params["k"]
+    recs = [so.read_fasta(p) for p in mini_fastas(tag)]
+    names = [os.path.basename(p)[:-3] for p in mini_fastas(tag)]
+    nbytes = device.BloomFilter.size_for(sum(len(s) for _, s in recs[0]), 0.025)
+    assert nbytes == so.bf_bytes(sum(len(s) for _, s in recs[0]), 0.025)
+    gens = [_upload(cuda_ctx, r) for r in recs]
+    per = []
+    for g, r in zip(gens, recs):
+        bf = cuda_ctx.bloom(nbytes)
+        bf.insert_genome(g, k)
+        want = so.genome_bits(r, k, nbytes)
+        assert np.array_equal(bf.to_numpy(), want)
+        assert bf.popcount() == int(np.unpackbits(want).sum())
+        per.append(bf)
+    common = pipeline.build_common_bf(cuda_ctx, gens, names, k)
+    assert np.array_equal(common.to_numpy(), so.common_bf(list(zip(names, recs)), k, 0.025, cascade=True))
+    # idempotence / commutativity of the merge
+    a = cuda_ctx.bloom(nbytes).from_numpy(per[0].to_numpy())
+    a.iand(per[1]); a.iand(per[1])
+    b = cuda_ctx.bloom(nbytes).from_numpy(per[1].to_numpy())
+    b.iand(per[0])
+    assert np.array_equal(a.to_numpy(), b.to_numpy())
+    # repeat filter (bin/ntsynt_make_repeat_bfs.py)
+    rep, scratch = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
+    for g in gens:
+        rep.insert_repeats(scratch, g, k)
+    assert np.array_equal(rep.to_numpy(), so.repeat_bf(list(zip(names, recs)), k, nbytes))
+
+
+@pytest.mark.parametrize("tag", ["AB", "ABC"])
+def test_sketch_matches_reference_consumed_fixture(cuda_ctx, tag, mini_params):
+    k, w = mini_params["k"], mini_params["w"]
+    paths = mini_fastas(tag)
+    names = [os.path.basename(p)[:-3] for p in paths]
+    packed = [fasta.read_fasta(p) for p in paths]
+    gens = [cuda_ctx.upload(p) for p in packed]
+    common = pipeline.build_common_bf(cuda_ctx, gens, names, k)
+    for n, pk, g in zip(names, packed, gens):
+        want = parse_sketch_tsv(mini_expected(tag, f"{n}.k{k}.w{w}.tsv.gz"))
+        h1, pos, ctg = cuda_ctx.sketch(g, k, w, common=common).to_numpy()
+        for c, cname in enumerate(pk.names):
+            sel = ctg == c
+            assert [int(x) for x in h1[sel]] == want[cname][0]
+            assert [int(x) for x in pos[sel]] == want[cname][1]
+
+
+@pytest.mark.parametrize("w", [1, 2, 10, 100, 999, 1000, 2500, 5000])
+def test_sketch_window_sizes_and_masks(cuda_ctx, w):
+    "ragged inputs, N runs, masks (refinement rounds), windows larger than some contigs"
+    recs = _tricky_records(seed=9)
+    k = 24
+    g = _upload(cuda_ctx, recs)
+    nbytes = so.bf_bytes(sum(len(s) for _, s in recs), 0.025)
+    bits = so.genome_bits(recs, k, nbytes)
+    bits[::3] = 0                                    # drop a third of the bytes: a sparse "common" filter
+    bf = cuda_ctx.bloom(nbytes).from_numpy(bits)
+    rng = np.random.default_rng(w)
+    masks, masked = [], []
+    for _, seq in recs:
+        L = len(seq)
+        s = np.sort(rng.integers(0, max(L, 1), 12)) if L else np.zeros(0, dtype=np.int64)
+        iv, last = [], 0
+        for a in s:
+            a = max(int(a), last)
+            b = min(a + int(rng.integers(1, 4000)), L)
+            if a < b:
+                iv.append((a, b)); last = b
+        masks.append((np.array([x for x, _ in iv], dtype=np.uint64), np.array([y for _, y in iv], dtype=np.uint64)))
+        buf = bytearray(seq)
+        for a, b in iv:
+            buf[a:b] = b"N" * (b - a)
+        masked.append(bytes(buf))
+    for use_bf in (True, False):
+        for use_mask in (False, True):
+            h1, pos, ctg = cuda_ctx.sketch(g, k, w, common=bf if use_bf else None,
+                                           masks=masks if use_mask else None).to_numpy()
+            for c, (_, seq) in enumerate(recs):
+                oh1, opos = so.minimize(masked[c] if use_mask else seq, k, w, bits if use_bf else None)
+                sel = ctg == c
+                assert np.array_equal(h1[sel], oh1), (w, use_bf, use_mask, c)
+                assert np.array_equal(pos[sel].astype(np.uint64), opos)
+
+
+def test_join_links_degrees_and_edges_match_numpy(cuda_ctx, mini_params):
+    k, w = mini_params["k"], mini_params["w"]
+    paths = mini_fastas("ABC")
+    names = [os.path.basename(p)[:-3] for p in paths]
+    gens = [cuda_ctx.upload(fasta.read_fasta(p)) for p in paths]
+    common = pipeline.build_common_bf(cuda_ctx, gens, names, k)
+    tables = [cuda_ctx.sketch(g, k, w, common=common) for g in gens]
+    host = [t.to_numpy() for t in tables]
+    for order in (0, 2):
+        mg = device.MinimizerGraph(cuda_ctx, tables, order)
+        H, POS, CTG, RANK, link, deg = mg.vertices()
+        nH, nPOS, nCTG, nRANK, nlink, ndeg = numpy_join(host, order)
+        assert np.array_equal(H, nH) and np.array_equal(POS, nPOS) and np.array_equal(CTG, nCTG)
+        assert np.array_equal(RANK, nRANK) and np.array_equal(link, nlink) and np.array_equal(deg, ndeg)
+        u, v, sup = mg.edges()
+        want = numpy_edges(nRANK.astype(np.int64), nCTG)
+        assert list(zip(u.tolist(), v.tolist(), sup.tolist())) == want
+    # the edge multiset equals the reference's round-0 graph (.mx.dot of the fixture run)
+    with gzip.open(os.path.join(MINI, "ABC", "mx_dot_edges.json.gz"), "rt") as fh:
+        dot = json.load(fh)
+    mg = device.MinimizerGraph(cuda_ctx, tables, 0)
+    H = mg.vertices()[0]
+    u, v, sup = mg.edges()
+    got = sorted([sorted((str(int(H[a])), str(int(H[b])))) + [bin(int(s)).count("1")] for a, b, s in zip(u, v, sup)])
+    assert got == dot
+
+
+@pytest.mark.parametrize("tag", ["AB", "ABC"])
+def test_pipeline_blocks_match_reference_fixture(tag, mini_params):
+    p = mini_params
+    out, eng = pipeline.run_ntsynt(mini_fastas(tag), k=p["k"], w=p["w"], w_rounds=p["w_rounds"], indel=p["indel"],
+                                   merge=p["merge"], block_size=p["block_size"], write_files=False)
+    assert out == mini_expected(tag, "synteny_blocks.tsv")
+    assert eng.outputs["pre_merge"] == mini_expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
+
+
+@pytest.mark.parametrize("k,names,gold", [
+    (24, ["celegans-chrII-III.fa", "celegans-chrII-III.A.fa"], "celegans-A-ntSynt"),
+    (20, ["celegans-chrII-III.fa", "celegans-chrII-III.A.fa", "celegans-chrII-III.B.fa"], "celegans-A-B-ntSynt")])
+def test_pipeline_reproduces_reference_goldens(demo_dir, k, names, gold):
+    "tests/ntsynt_tests.py:40-52 end to end on the GPU, whole files compared"
+    out, eng = pipeline.run_ntsynt([os.path.join(demo_dir, n + ".gz") for n in names], k=k, w=1000, w_rounds=(100, 10),
+                                   indel=500, merge="3000", block_size=500, write_files=False)
+    exp = os.path.join(demo_dir, "expected_result")
+    assert out == open(os.path.join(exp, gold + ".synteny_blocks.tsv")).read()
+    assert eng.outputs["pre_merge"] == open(os.path.join(exp, gold + ".pre-collinear-merge.synteny_blocks.tsv")).read()
+
+
+def test_golden_demo_sketches_on_device(cuda_ctx, demo_dir):
+    "tests/expected_result/*.k24.w1000.tsv from the GPU (hash, BF geometry, AND, tie-break all pinned)"
+    names = ["celegans-chrII-III.fa", "celegans-chrII-III.A.fa"]
+    packed = [fasta.read_fasta(os.path.join(demo_dir, n + ".gz")) for n in names]
+    gens = [cuda_ctx.upload(p) for p in packed]
+    common = pipeline.build_common_bf(cuda_ctx, gens, names, 24)
+    for n, pk, g in zip(names, packed, gens):
+        with open(os.path.join(demo_dir, "expected_result", f"{n}.k24.w1000.tsv"), encoding="utf-8") as fh:
+            want = parse_sketch_tsv(fh.read())
+        h1, pos, ctg = cuda_ctx.sketch(g, 24, 1000, common=common).to_numpy()
+        for c, cname in enumerate(pk.names):
+            sel = ctg == c
+            assert [int(x) for x in h1[sel]] == want[cname][0] and [int(x) for x in pos[sel]] == want[cname][1]
+
+
+@pytest.mark.parametrize("seed,G", [(201, 2), (202, 3), (203, 4)])
+def test_pipeline_equals_graph_oracle_on_rearranged_genomes(tmp_path, seed, G):
+    gens = synth_small.make_genomes(seed, G, contig_lens=(100000, 70000, 30000), sub=0.006, n_inv=4, n_trans=3, n_dup=3)
+    paths = []
+    for i, recs in enumerate(gens):
+        p = str(tmp_path / f"g{chr(65 + i)}.fa")
+        synth_small.write_fasta(p, recs)
+        paths.append(p)
+    k, w, w_rounds, indel, merge, z = 16, 40, [20, 5], 300, "400", 200
+    out, eng = pipeline.run_ntsynt(paths, k=k, w=w, w_rounds=w_rounds, indel=indel, merge=merge, block_size=z,
+                                   write_files=False)
+    genomes = [(os.path.basename(p), so.read_fasta(p)) for p in paths]
+    bits = so.common_bf(genomes, k, 0.025)
+    go = GraphOracle([(n + f".k{k}.w{w}.tsv", r) for n, r in genomes], k, w, w_rounds, indel, merge, z, bits)
+    go.run()
+    assert out == go.outputs["final"] and eng.outputs["pre_merge"] == go.outputs["pre_merge"]
+
+
+def test_synthetic_generator_matches_host_formula_and_is_deterministic(cuda_ctx):
+    wl = synth.Workload(2, 2_000_000, 1.0, n_contigs=4)
+    g0 = wl.materialize(cuda_ctx, 0)
+    again = wl.materialize(cuda_ctx, 0)
+    for c in range(4):
+        assert np.array_equal(g0.contig_words(c), again.contig_words(c))
+    lengths, segs = wl.segments(0)
+    f = _lib.lib.nts_synth_ancestor_base
+    text = g0.contig_ascii(1)
+    s1 = segs[segs["dst_contig"] == 1]
+    seg = s1[(s1["anc_contig"] >= 0) & (s1["strand"] > 0) & (s1["len"] > 2000)][0]
+    start, anc, ac = int(seg["dst_start"]), int(seg["anc_start"]), int(seg["anc_contig"])
+    want = bytes(b"ACGT"[f(wl.seed, wl.n_repeat_fam, wl.repeat_slot_prob, ac, anc + i)] for i in range(2000))
+    got = text[start:start + 2000]
+    diff = sum(a != b for a, b in zip(want, got))
+    assert diff < 40            # only the d/200 substitutions differ
+    off, st, ln = g0.nruns()
+    assert len(st) > 0 and text[int(st[int(off[1])]):int(st[int(off[1])]) + 5] == b"NNNNN"
+
+
+def test_full_size_properties(cuda_ctx):
+    "size-independent checks at 2 x 150 Mbp: sortedness, window property on samples, AND monotonicity"
+    k, w = 24, 1000
+    wl = synth.Workload(2, 150_000_000, 1.0)
+    gens = [wl.materialize(cuda_ctx, g) for g in range(2)]
+    nbytes = device.BloomFilter.size_for(gens[0].total_bases, 0.025)
+    a, b = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
+    a.insert_genome(gens[0], k); b.insert_genome(gens[1], k)
+    pa, pb = a.popcount(), b.popcount()
+    a.iand(b)
+    pc = a.popcount()
+    assert 0 < pc <= min(pa, pb)
+    h1, pos, ctg = cuda_ctx.sketch(gens[0], k, w, common=a).to_numpy()
+    key = ctg.astype(np.int64) * (1 << 32) + pos
+    assert (np.diff(key) > 0).all()                                   # sorted, distinct
+    dens = len(h1) / gens[0].total_bases
+    assert 0.5 / w < dens < 2.5 / w
+    # one contig slice checked against the oracle
+    seq = gens[0].contig_ascii(3, 0, 400000)
+    bits = a.to_numpy()
+    oh1, opos = so.minimize(seq, k, w, bits)
+    sel = (ctg == 3) & (pos < 400000 - 2 * w)
+    n = int(sel.sum())
+    assert n > 100 and np.array_equal(h1[sel], oh1[:n]) and np.array_equal(pos[sel].astype(np.uint64), opos[:n])
