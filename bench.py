@@ -239,7 +239,7 @@ def run_ours(args, dist):
     order = pipeline.processing_order(names)
     my_ids = list(range(G)) if N == 1 else [g for g in range(G) if g % N == dist.rank]
     if N > 1:
-        raise SystemExit("multi-GPU bench requires the NCCL merge (nts_bf_allreduce_and); see DESIGN.md")
+        return run_ours_multi(args, dist, ctx)
     gens = {g: wl.materialize(ctx, g) for g in my_ids}
     total_bp = sum(int(x.total_bases) for x in gens.values())
     size_sorted = sorted(range(G), key=lambda i: file_names[i])
@@ -364,6 +364,135 @@ def run_ours(args, dist):
     }
     if dist.rank == 0:
         print(json.dumps(line))
+
+
+def run_ours_multi(args, dist, ctx):
+    """N > 1: one genome per GPU (G = N, or a multiple), per-GPU filters merged by NCCL all-reduce(sum)
+    of packed counters, owners sketch, tables all-gathered, rank 0 runs the join + graph stage."""
+    import numpy as np
+    from ntsynt_b200 import device, distributed, pipeline, synth
+    from ntsynt_b200.synteny import SyntenyEngine
+    N, rank = dist.world, dist.rank
+    G = args.genomes or N
+    if G % N:
+        raise SystemExit("--genomes must be a multiple of the number of GPUs")
+    d = args.divergence
+    ps = presets(d)
+    wl = synth.Workload(G, int(args.genome_mbp * 1e6), d, seed=args.seed)
+    file_names = [wl.file_name(g) for g in range(G)]
+    names = [pipeline.tsv_name(f, K, W) for f in file_names]
+    order = pipeline.processing_order(names)
+    own = [g for g in range(G) if g % N == rank]
+    resident = list(range(G)) if rank == 0 else own          # rank 0 re-sketches the masked rounds of every genome
+    gens = {g: wl.materialize(ctx, g) for g in resident}
+    sizes = [int(wl.segments(g)[0].sum()) for g in range(G)]
+    total_bp = sum(sizes)
+    first = sorted(range(G), key=lambda i: file_names[i])[0]
+    nbytes = device.BloomFilter.size_for(sizes[first], 0.025)
+    mine, level = ctx.bloom(nbytes), (ctx.bloom(nbytes) if len(own) > 1 else None)
+    ident = distributed.Comm.new_unique_id() if rank == 0 else b""
+    comm = distributed.Comm(ctx, rank, N, dist.bcast_bytes(ident, 128))
+
+    def hot_path(gen_map):
+        mine.clear()
+        mine.insert_genome(gen_map[own[0]], K)
+        for g in own[1:]:
+            level.clear(); level.insert_genome(gen_map[g], K); mine.iand(level)
+        comm.allreduce_and(mine)                                   # the one bulk exchange
+        gathered = {}
+        for slot, g in enumerate(own):
+            t = ctx.sketch(gen_map[g], K, W, common=mine)
+            counts = dist.gather_objects(len(t))
+            owners = [slot * N + r for r in range(N)]
+            tabs = comm.allgather_tables(t, counts, [gen_map.get(x) for x in owners])
+            t.close()
+            for x, tb in zip(owners, tabs):
+                if rank == 0:
+                    gathered[x] = tb
+                else:
+                    tb.close()
+        text, eng = None, None
+        if rank == 0:
+            be = distributed.GatheredBackend(ctx, [gen_map[i] for i in order], [names[i] for i in order], [wl.names] * G,
+                                             [[int(x) for x in gen_map[i].lengths] for i in order], K, mine,
+                                             [gathered[i] for i in order])
+            eng = SyntenyEngine(be, K, W, ps["w_rounds"], ps["indel"], ps["merge"], ps["block_size"], write_files=False,
+                                quiet=True)
+            text = eng.run()
+            for tb in gathered.values():
+                tb.close()
+        dist.barrier()                                             # the step ends when the block table exists
+        return text, eng
+
+    for _ in range(max(args.warmup, 0)):
+        text, eng = hot_path(gens)
+    ctx.prof_enable(True); ctx.prof_reset()
+    launches0 = ctx.launches
+    clocks = ClockSampler(dist.local_rank)
+    dist.barrier(); ctx.sync()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        text, eng = hot_path(gens)
+    ms = ctx.timer_stop()
+    ctx.sync(); dist.barrier()
+    ms = dist.max(ms)
+    launches = dist.sum(ctx.launches - launches0)
+    prof = ctx.prof()
+    ctx.prof_enable(False)
+    value = total_bp * args.steps / (ms / 1e3)
+    # e2e: owners (and rank 0 for every genome) start from pinned host memory
+    packed_host = {}
+    for g in resident:
+        pk = gens[g].to_packed()
+        pin = device.PinnedU64(len(pk.words)); pin.array[:] = pk.words; pk.words = pin.array
+        packed_host[g] = (pk, pin)
+    ctx.prof_reset()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    dist.barrier(); ctx.sync()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        fresh = {g: ctx.upload(packed_host[g][0]) for g in resident}
+        text_e2e, _ = hot_path(fresh)
+        for f in fresh.values():
+            f.close()
+    ms_e2e = dist.max(ctx.timer_stop())
+    h2d, d2h = ctx.xfer_bytes()
+    h2d, d2h = dist.sum(h2d), dist.sum(d2h)
+    clk = clocks.stop()
+    if rank == 0:
+        assert text_e2e == text
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json"), encoding="utf-8") as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = {"bf_insert": 64.25, "sketch": 32.25, "bf_combine": 3.0, "fill": 1.0}
+    fam = max((f for f in alg if prof[f][2]), key=lambda f: prof[f][0])
+    f_ms, f_units, f_n = prof[fam]
+    achieved = (alg[fam] * f_units / f_n) / ((f_ms / f_n) / 1e3) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{G} synthetic {args.genome_mbp:g} Mbp genomes one-per-GPU, counting-BF NCCL-sum merge, "
+                                   f"d={d:g}, k={K} w={W}, w_rounds {ps['w_rounds']}, {N}xB200",
+                       "genomes": G, "genome_bp": sizes[0], "k": K, "w": W, "fpr": 0.025, "bloom_bytes": nbytes,
+                       "merge_wire_bytes_per_rank": distributed.merge_wire_bytes(nbytes, N),
+                       "l2": "inputs (bases + filters) are larger than L2; no flush needed",
+                       "blocks": text.count("\n") // G, "vertices": eng.stats.get("vertices")},
+            "clocks": clk,
+            "e2e": {"value": total_bp * e2e_steps / (ms_e2e / 1e3), "unit": "bp/s", "h2d_bytes_per_step": int(h2d // e2e_steps),
+                    "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": fam, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "rank": 0,
+                         "kernel_ms_per_step": {f: round(prof[f][0] / args.steps, 3) for f in prof if prof[f][2]}},
+            "cpu_baseline": None,
+        }))
+    comm.close()
 
 
 def run_reference(args, dist):

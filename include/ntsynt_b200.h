@@ -160,9 +160,31 @@ void nts_mxs_destroy(nts_mxs* m);
 uint64_t nts_mxs_count(const nts_mxs* m);
 /* h1 = second ntHash2 hash (what indexlr prints), pos = 0-based k-mer start, contig index */
 int nts_mxs_download(nts_mxs* m, uint64_t* h1, uint32_t* pos, uint32_t* contig);
+/* build a device table from host arrays (bin/ntsynt_run.py reads indexlr TSVs: ntjoin_utils.py:167-193) */
+int nts_mxs_upload(nts_ctx* ctx, uint64_t n, const uint64_t* h1, const uint32_t* pos, const uint32_t* contig,
+                   nts_mxs** out);
 /* test hook: canonical h0 and validity of every k-mer start of one contig (kernel i alone) */
 int nts_hash_contig(nts_ctx* ctx, const nts_genome* g, uint32_t contig, uint32_t k, uint64_t* h0_out,
                     uint8_t* valid_out);
+
+/* -------------------------------------------------------------------------------- multi-GPU
+ * The one inter-GPU exchange of the path (the reference is a single process: cpp:136-160 cascades
+ * genome after genome).  Every rank holds a filter; after nts_bf_allreduce_and each rank's filter is
+ * the AND over all ranks (OR for nts_bf_allreduce_or: contig-sharded partial filters of one genome).
+ * Implementation: bits expanded to 2/4/8-bit counters packed in uint32, ONE ncclAllReduce(sum) per
+ * 128 MB chunk (double buffered), thresholded back to bits.  NCCL is dlopen()ed on first use.
+ * The 128-byte id comes from rank 0 (nts_nccl_unique_id) over any host side channel. */
+typedef struct nts_comm nts_comm;
+int nts_nccl_unique_id(uint8_t id_out[128]);
+int nts_nccl_init(nts_ctx* ctx, const uint8_t id[128], int rank, int world, nts_comm** out);
+void nts_nccl_destroy(nts_comm* comm);
+int nts_nccl_world(const nts_comm* comm);
+int nts_nccl_rank(const nts_comm* comm);
+int nts_bf_allreduce_and(nts_comm* comm, nts_bf* bf);
+int nts_bf_allreduce_or(nts_comm* comm, nts_bf* bf);
+/* all-gather of minimizer tables (ncclAllGather over padded columns): out[r] = rank r's table, as a
+ * new nts_mxs on this rank; counts[world] must hold every rank's table size. */
+int nts_mxs_allgather(nts_comm* comm, const nts_mxs* mine, const uint64_t* counts, nts_mxs** out);
 
 /* -------------------------------------------------------------------------------- graph (kernel iv)
  * Replaces ntjoin_utils.read_minimizers' duplicate removal (subprojects/ntJoin/bin/ntjoin_utils.py:182-192),

@@ -85,6 +85,15 @@ _SIGS = {
     "nts_mxs_count": (C.c_uint64, [vp]),
     "nts_mxs_download": (C.c_int, [vp, u64p, u32p, u32p]),
     "nts_hash_contig": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u64p, u8p]),
+    "nts_mxs_upload": (C.c_int, [vp, C.c_uint64, u64p, u32p, u32p, vpp]),
+    "nts_nccl_unique_id": (C.c_int, [u8p]),
+    "nts_nccl_init": (C.c_int, [vp, u8p, C.c_int, C.c_int, vpp]),
+    "nts_nccl_destroy": (None, [vp]),
+    "nts_nccl_world": (C.c_int, [vp]),
+    "nts_nccl_rank": (C.c_int, [vp]),
+    "nts_bf_allreduce_and": (C.c_int, [vp, vp]),
+    "nts_bf_allreduce_or": (C.c_int, [vp, vp]),
+    "nts_mxs_allgather": (C.c_int, [vp, vp, u64p, vpp]),
     "nts_graph_build": (C.c_int, [vp, vpp, C.c_uint32, C.c_uint32, vpp]),
     "nts_graph_destroy": (None, [vp]),
     "nts_graph_vertices": (C.c_uint64, [vp]),

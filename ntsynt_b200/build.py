@@ -37,8 +37,11 @@ def build_lib(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *sources(), "-ldl"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or res.returncode != 0:
+    if verbose:
         sys.stderr.write(res.stdout)
+    elif res.returncode != 0:
+        sys.stderr.write("\n".join(l for l in res.stdout.splitlines() if "ptxas info" not in l and "bytes stack" not in l
+                                   and "Compile time" not in l and "registers" not in l) + "\n")
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libntsynt_b200.so")
     with open(os.path.join(HERE, "build.log"), "w", encoding="utf-8") as fh:

@@ -799,3 +799,26 @@ int nts_hash_contig(nts_ctx* ctx, const nts_genome* g, uint32_t contig, uint32_t
 }
 
 }  // extern "C"
+
+extern "C" int nts_mxs_upload(nts_ctx* ctx, uint64_t n, const uint64_t* h1, const uint32_t* pos, const uint32_t* contig,
+                              nts_mxs** out)
+{
+    if (!ctx || !out || (n && (!h1 || !pos || !contig))) return nts::fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    nts_mxs* m = new (std::nothrow) nts_mxs();
+    if (!m) return nts::fail(NTS_ERR_NOMEM, "host allocation failed");
+    m->ctx = ctx; m->count = n;
+    const uint64_t a = n ? n : 1;
+    if (m->h1.alloc(a) != cudaSuccess || m->pos.alloc(a) != cudaSuccess || m->contig.alloc(a) != cudaSuccess) {
+        delete m;
+        return nts::fail(NTS_ERR_NOMEM, "device allocation failed (minimizer table)");
+    }
+    if (n) {
+        NTS_CUDA(nts::copy_h2d(ctx, m->h1.p, h1, n * 8));
+        NTS_CUDA(nts::copy_h2d(ctx, m->pos.p, pos, n * 4));
+        NTS_CUDA(nts::copy_h2d(ctx, m->contig.p, contig, n * 4));
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = m;
+    return NTS_OK;
+}

@@ -1,0 +1,100 @@
+"""Multi-GPU plumbing: one process per GPU, genomes assigned to ranks, per-GPU Bloom
+filters merged by one NCCL all-reduce(sum) over packed counters, minimizer tables all-gathered, graph
+stage on rank 0.  The host side channel (rendezvous, the 128-byte NCCL id, table sizes, barriers) is
+whatever the launcher offers -- bench.py uses torch.distributed with the gloo backend.
+The reference has no counterpart: it is a single process (src/ntsynt_make_common_bf.cpp:136-160).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib, ptr
+from . import device
+
+
+def assign_genomes(n_genomes, world):
+    "round-robin ownership: genome g lives on rank g % world; returns [list of genome ids per rank]"
+    return [[g for g in range(n_genomes) if g % world == r] for r in range(world)]
+
+
+def owner_of(genome, world):
+    return genome % world
+
+
+def field_bits(world):
+    "counter width used by the all-reduce merge: smallest of 2/4/8 bits that can hold `world`"
+    return 2 if world <= 3 else 4 if world <= 15 else 8
+
+
+def merge_wire_bytes(filter_bytes, world):
+    "bytes each rank hands to ncclAllReduce for one filter merge"
+    return filter_bytes * field_bits(world)
+
+
+class Comm:
+    "NCCL communicator bound to a Context (nts_nccl_*)"
+
+    def __init__(self, ctx, rank, world, unique_id):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        h = C.c_void_p()
+        check(lib.nts_nccl_init(ctx._h, buf, int(rank), int(world), C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def new_unique_id():
+        buf = (C.c_uint8 * 128)()
+        check(lib.nts_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def allreduce_and(self, bf):
+        "bf := AND over all ranks' filters (replaces the cascade of cpp:136-160 across GPUs)"
+        check(lib.nts_bf_allreduce_and(self._h, bf._h))
+
+    def allreduce_or(self, bf):
+        check(lib.nts_bf_allreduce_or(self._h, bf._h))
+
+    def allgather_tables(self, table, counts, genome_for_rank):
+        "every rank's minimizer table, as MinimizerTable objects on this rank"
+        cnt = np.asarray(counts, dtype=np.uint64)
+        out = (C.c_void_p * self.world)()
+        check(lib.nts_mxs_allgather(self._h, table._h, ptr(cnt, C.c_uint64), out))
+        return [device.MinimizerTable(self.ctx, C.c_void_p(out[r]), genome_for_rank[r]) for r in range(self.world)]
+
+    def close(self):
+        if self._h:
+            lib.nts_nccl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+class GatheredBackend:
+    """SyntenyEngine backend for rank 0 of a one-genome-per-GPU run: round-0 tables were sketched on
+    their owner ranks and all-gathered; refinement sketches (tiny, <1 % unmasked) run locally on the
+    copies of the genomes rank 0 holds."""
+
+    def __init__(self, ctx, genomes, names, contig_names, contig_lengths, k, common, round0_tables):
+        self.ctx, self.genomes = ctx, genomes
+        self.names = list(names)
+        self.contig_names, self.contig_lengths = contig_names, contig_lengths
+        self.k, self.common = k, common
+        self.round0 = round0_tables
+
+    def sketch(self, a, w, masks):
+        if masks is None:
+            return self.round0[a]
+        mx = self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, masks=masks)
+        out = mx.to_numpy()
+        mx.close()
+        return out
+
+    def join(self, tables, order_asm):
+        g = device.MinimizerGraph(self.ctx, tables, order_asm)
+        res = g.vertices()
+        g.close()
+        return res
