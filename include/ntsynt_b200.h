@@ -205,6 +205,14 @@ uint64_t nts_graph_vertices(const nts_graph* g);
  * link[V]: 1 iff the edge (i, i+1) has weight n_asm; degree[V]: number of distinct neighbours. */
 int nts_graph_download_vertices(nts_graph* g, uint64_t* h1, uint32_t* pos, uint32_t* contig, uint32_t* rank,
                                 uint8_t* link, uint8_t* degree);
+/* Per-pair arrays for (i, i+1) in vertex order, consumed by the host as prefix sums over chains:
+ * inv[n_asm*V] = vertex at each rank (inverse of rank); incmask/decmask[V]: bit a set iff assembly a's
+ * position increases / decreases from vertex i to i+1 (orientation rule, bin/synteny_block.py:48-65);
+ * spread[V] = max_a |dpos| - min_a |dpos| (indel test, bin/ntsynt_synteny.py:364-368,399). */
+int nts_graph_download_links(nts_graph* g, uint32_t* inv, uint32_t* incmask, uint32_t* decmask, uint32_t* spread);
+/* vertex id of each h1 (0xFFFFFFFF if none) via the join table kept on the device
+ * (replaces `mx in mx_info` / graph.vs.find(name) lookups of the refinement rounds) */
+int nts_graph_lookup(nts_graph* g, const uint64_t* h1, uint64_t n, uint32_t* vid_out);
 /* Edge table: distinct unordered adjacencies in build_graph's first-insertion order (assembly
  * order, then list order); (u, v) in the orientation of the first insertion; support = bitmask of
  * assemblies (weight = popcount, all assembly weights are 1: bin/ntsynt_synteny.py:32). */

@@ -59,6 +59,27 @@ __global__ void join_keep_kernel(const uint32_t* __restrict__ slot_of, uint64_t 
     keep[i] = (seen[s] == full && dup[s] == 0) ? 1u : 0u;
 }
 
+__global__ void join_lookup_kernel(const uint64_t* __restrict__ h1, uint64_t n, const unsigned long long* __restrict__ keys,
+                                   const uint32_t* __restrict__ slot_vid, uint64_t mask, uint32_t* __restrict__ out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = h1[i];
+    uint32_t res = 0xFFFFFFFFu;
+    if (key == HT_EMPTY) {
+        res = slot_vid[mask + 1];
+    } else {
+        uint64_t slot = mix64(key) & mask;
+        while (true) {
+            const unsigned long long cur = keys[slot];
+            if (cur == key) { res = slot_vid[slot]; break; }
+            if (cur == HT_EMPTY) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+    out[i] = res;
+}
+
 // ---- exclusive scan of 0/1 flags, 3 phases (block sums, scan of sums, apply)
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;   // per thread
@@ -157,9 +178,11 @@ __device__ __forceinline__ bool adjacent_in(const uint32_t* __restrict__ v_ctg, 
 }
 
 // link[i] = 1 iff edge (i, i+1) is supported by every assembly;  degree[v] = # distinct neighbours
-__global__ void graph_links_kernel(const uint32_t* __restrict__ v_ctg, const uint32_t* __restrict__ v_rank,
-                                   const uint32_t* __restrict__ inv, uint64_t V, uint32_t n_asm,
-                                   uint8_t* __restrict__ link, uint8_t* __restrict__ degree)
+__global__ void graph_links_kernel(const uint32_t* __restrict__ v_pos, const uint32_t* __restrict__ v_ctg,
+                                   const uint32_t* __restrict__ v_rank, const uint32_t* __restrict__ inv, uint64_t V,
+                                   uint32_t n_asm, uint8_t* __restrict__ link, uint8_t* __restrict__ degree,
+                                   uint32_t* __restrict__ incmask, uint32_t* __restrict__ decmask,
+                                   uint32_t* __restrict__ spread)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
@@ -168,8 +191,19 @@ __global__ void graph_links_kernel(const uint32_t* __restrict__ v_ctg, const uin
         bool full = true;
         for (uint32_t b = 0; b < n_asm && full; ++b) full = adjacent_in(v_ctg, v_rank, V, b, u, u + 1);
         link[i] = full ? 1 : 0;
+        // per-assembly direction of (i -> i+1) and the spread of |delta pos| (synteny_block.py:48-65,
+        // ntsynt_synteny.py:364-368), consumed by the host as prefix sums over runs of links
+        uint32_t inc = 0, dec = 0, dmax = 0, dmin = 0xFFFFFFFFu;
+        for (uint32_t b = 0; b < n_asm; ++b) {
+            const uint32_t p0 = v_pos[(uint64_t)b * V + u], p1 = v_pos[(uint64_t)b * V + u + 1];
+            if (p1 > p0) inc |= 1u << b;
+            if (p1 < p0) dec |= 1u << b;
+            const uint32_t d = p1 > p0 ? p1 - p0 : p0 - p1;
+            dmax = max(dmax, d); dmin = min(dmin, d);
+        }
+        incmask[i] = inc; decmask[i] = dec; spread[i] = dmax - dmin;
     } else {
-        link[i] = 0;
+        link[i] = 0; incmask[i] = 0; decmask[i] = 0; spread[i] = 0;
     }
     // distinct neighbours over all assemblies (at most 2 per assembly)
     uint32_t nb[64];
@@ -256,6 +290,11 @@ struct nts_graph {
     DevBuf<uint64_t> v_h1;                       // [V]
     DevBuf<uint32_t> v_pos, v_ctg, v_rank, inv;  // [n_asm * V], assembly-major
     DevBuf<uint8_t> link, degree;                // [V]
+    DevBuf<uint32_t> incmask, decmask, spread;   // [V] per (i, i+1)
+    // the join table stays alive for nts_graph_lookup
+    DevBuf<unsigned long long> keys;
+    DevBuf<uint32_t> slot_vid, slot_ok;
+    uint64_t cap = 0;
     // edges (built lazily)
     bool edges_built = false;
     uint64_t E = 0;
@@ -284,8 +323,10 @@ int nts_graph_build(nts_ctx* ctx, nts_mxs* const* tables, uint32_t n_asm, uint32
     uint64_t cap = 1024;
     while (cap < total * 2) cap <<= 1;
     if (cap > 0x80000000ull) return fail(NTS_ERR_ARG, "too many minimizers for the join table");
-    DevBuf<unsigned long long> keys;
-    DevBuf<uint32_t> seen, dup, slot_vid;
+    DevBuf<unsigned long long>& keys = g->keys;
+    DevBuf<uint32_t>& slot_vid = g->slot_vid;
+    DevBuf<uint32_t> seen, dup;
+    g->cap = cap;
     std::vector<DevBuf<uint32_t>> slot_of(n_asm), keep(n_asm), rank(n_asm);
     if (keys.alloc(cap + 1) != cudaSuccess || seen.alloc(cap + 1) != cudaSuccess || dup.alloc(cap + 1) != cudaSuccess ||
         slot_vid.alloc(cap + 1) != cudaSuccess)
@@ -293,6 +334,7 @@ int nts_graph_build(nts_ctx* ctx, nts_mxs* const* tables, uint32_t n_asm, uint32
     NTS_CUDA(cudaMemsetAsync(keys.p, 0xFF, (cap + 1) * 8, ctx->stream));
     NTS_CUDA(cudaMemsetAsync(seen.p, 0, (cap + 1) * 4, ctx->stream));
     NTS_CUDA(cudaMemsetAsync(dup.p, 0, (cap + 1) * 4, ctx->stream));
+    NTS_CUDA(cudaMemsetAsync(slot_vid.p, 0xFF, (cap + 1) * 4, ctx->stream));   // 0xFFFFFFFF = not a vertex
     for (uint32_t a = 0; a < n_asm; ++a) {
         const uint64_t n = tables[a]->count;
         if (slot_of[a].alloc(n) != cudaSuccess || keep[a].alloc(n) != cudaSuccess || rank[a].alloc(n) != cudaSuccess)
@@ -321,7 +363,8 @@ int nts_graph_build(nts_ctx* ctx, nts_mxs* const* tables, uint32_t n_asm, uint32
     const uint64_t VA = std::max<uint64_t>(1, V * n_asm);
     if (g->v_h1.alloc(std::max<uint64_t>(1, V)) != cudaSuccess || g->v_pos.alloc(VA) != cudaSuccess || g->v_ctg.alloc(VA) != cudaSuccess ||
         g->v_rank.alloc(VA) != cudaSuccess || g->inv.alloc(VA) != cudaSuccess || g->link.alloc(std::max<uint64_t>(1, V)) != cudaSuccess ||
-        g->degree.alloc(std::max<uint64_t>(1, V)) != cudaSuccess)
+        g->degree.alloc(std::max<uint64_t>(1, V)) != cudaSuccess || g->incmask.alloc(std::max<uint64_t>(1, V)) != cudaSuccess ||
+        g->decmask.alloc(std::max<uint64_t>(1, V)) != cudaSuccess || g->spread.alloc(std::max<uint64_t>(1, V)) != cudaSuccess)
         return fail(NTS_ERR_NOMEM, "device allocation failed (vertex table)");
     if (V) {
         {
@@ -338,8 +381,9 @@ int nts_graph_build(nts_ctx* ctx, nts_mxs* const* tables, uint32_t n_asm, uint32
                 a == order_asm ? g->v_h1.p : nullptr);
             ctx->launches++;
         }
-        graph_links_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(g->v_ctg.p, g->v_rank.p, g->inv.p, V, n_asm,
-                                                                                g->link.p, g->degree.p);
+        graph_links_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(g->v_pos.p, g->v_ctg.p, g->v_rank.p, g->inv.p, V,
+                                                                                n_asm, g->link.p, g->degree.p, g->incmask.p,
+                                                                                g->decmask.p, g->spread.p);
         ctx->launches++;
         NTS_CUDA(cudaGetLastError());
     }
@@ -372,6 +416,42 @@ int nts_graph_download_vertices(nts_graph* g, uint64_t* h1, uint32_t* pos, uint3
     if (link) NTS_CUDA(copy_d2h(g->ctx, link, g->link.p, V));
     if (degree) NTS_CUDA(copy_d2h(g->ctx, degree, g->degree.p, V));
     NTS_CUDA(cudaStreamSynchronize(st));
+    return NTS_OK;
+}
+
+int nts_graph_download_links(nts_graph* g, uint32_t* inv, uint32_t* incmask, uint32_t* decmask, uint32_t* spread)
+{
+    if (!g) return fail(NTS_ERR_ARG, "null argument");
+    if (!g->V) return NTS_OK;
+    NTS_CUDA(cudaSetDevice(g->ctx->device));
+    const uint64_t V = g->V;
+    if (inv) NTS_CUDA(copy_d2h(g->ctx, inv, g->inv.p, V * g->n_asm * 4));
+    if (incmask) NTS_CUDA(copy_d2h(g->ctx, incmask, g->incmask.p, V * 4));
+    if (decmask) NTS_CUDA(copy_d2h(g->ctx, decmask, g->decmask.p, V * 4));
+    if (spread) NTS_CUDA(copy_d2h(g->ctx, spread, g->spread.p, V * 4));
+    NTS_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    return NTS_OK;
+}
+
+/* vertex id of each h1 (0xFFFFFFFF if it is not a vertex) through the join table kept on the device */
+int nts_graph_lookup(nts_graph* g, const uint64_t* h1, uint64_t n, uint32_t* vid_out)
+{
+    if (!g || (n && (!h1 || !vid_out))) return fail(NTS_ERR_ARG, "null argument");
+    if (!n) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<uint64_t> d_k;
+    DevBuf<uint32_t> d_o;
+    if (d_k.alloc(n) != cudaSuccess || d_o.alloc(n) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (lookup)");
+    NTS_CUDA(copy_h2d(ctx, d_k.p, h1, n * 8));
+    {
+        ProfScope prof(ctx, PROF_JOIN, (double)n);
+        join_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_k.p, n, g->keys.p, g->slot_vid.p, g->cap - 1, d_o.p);
+        ctx->launches++;
+    }
+    NTS_CUDA(cudaGetLastError());
+    NTS_CUDA(copy_d2h(ctx, vid_out, d_o.p, n * 4));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
     return NTS_OK;
 }
 

@@ -264,6 +264,34 @@ class MinimizerGraph:
                                                   ptr(deg, C.c_uint8)))
         return h1[:V], pos[:, :V], ctg[:, :V], rank[:, :V], link[:V], deg[:V]
 
+    def links(self):
+        "inv[G,V] u32, incmask[V], decmask[V], spread[V] u32: per-pair arrays of (i, i+1)"
+        V, G = len(self), self.n_asm
+        n = max(V, 1)
+        inv = np.empty((G, n), dtype=np.uint32)
+        inc = np.empty(n, dtype=np.uint32)
+        dec = np.empty(n, dtype=np.uint32)
+        spread = np.empty(n, dtype=np.uint32)
+        if V:
+            check(lib.nts_graph_download_links(self._h, ptr(inv, C.c_uint32), ptr(inc, C.c_uint32), ptr(dec, C.c_uint32),
+                                               ptr(spread, C.c_uint32)))
+        return inv[:, :V], inc[:V], dec[:V], spread[:V]
+
+    def lookup(self, keys):
+        "vertex id per h1 (0xFFFFFFFF if it is not a vertex), through the device join table"
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.full(max(len(keys), 1), 0xFFFFFFFF, dtype=np.uint32)
+        if len(keys):
+            check(lib.nts_graph_lookup(self._h, ptr(keys, C.c_uint64), len(keys), ptr(out, C.c_uint32)))
+        return out[:len(keys)]
+
+    def join_result(self):
+        "everything SyntenyEngine needs from the join, as a dict"
+        H, POS, CTG, RANK, link, deg = self.vertices()
+        INV, inc, dec, spread = self.links()
+        return dict(H=H, POS=POS, CTG=CTG, RANK=RANK, INV=INV, link=link, degree=deg, incmask=inc, decmask=dec,
+                    spread=spread)
+
     def edges(self):
         "(u, v, support) of the distinct adjacency edges in build_graph's first-insertion order"
         n = C.c_uint64()

@@ -94,7 +94,15 @@ class GatheredBackend:
         return out
 
     def join(self, tables, order_asm):
-        g = device.MinimizerGraph(self.ctx, tables, order_asm)
-        res = g.vertices()
-        g.close()
-        return res
+        if getattr(self, "graph", None) is not None:
+            self.graph.close()
+        self.graph = device.MinimizerGraph(self.ctx, tables, order_asm)      # kept alive for lookup()
+        return self.graph.join_result()
+
+    def lookup(self, keys):
+        return self.graph.lookup(keys)
+
+    def close(self):
+        if getattr(self, "graph", None) is not None:
+            self.graph.close()
+            self.graph = None

@@ -75,13 +75,22 @@ class CudaBackend:
 
     def join(self, tables, order_asm):
         t0 = time.perf_counter()
-        g = device.MinimizerGraph(self.ctx, tables, order_asm)
-        res = g.vertices()
-        g.close()
+        if getattr(self, "graph", None) is not None:
+            self.graph.close()
+        self.graph = device.MinimizerGraph(self.ctx, tables, order_asm)      # kept alive for lookup()
+        res = self.graph.join_result()
         for t in tables:
             t.close()
         self.timing["join_ms"] += (time.perf_counter() - t0) * 1e3
         return res
+
+    def lookup(self, keys):
+        return self.graph.lookup(keys)
+
+    def close(self):
+        if getattr(self, "graph", None) is not None:
+            self.graph.close()
+            self.graph = None
 
 
 def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="10000", block_size=500, fpr=0.025,
@@ -105,6 +114,7 @@ def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="100
                         write_files=write_files, quiet=quiet)
     out = eng.run()
     eng.backend_timing = be.timing
+    be.close()
     if bf is not None:
         bf.close()
     for g in genomes:

@@ -44,13 +44,16 @@ def _log(*a):
 
 
 class Block:
-    "one synteny block: a path of vertices with one contig and one orientation per assembly"
-    __slots__ = ("vids", "ctg", "ori", "first_pos", "last_pos", "n", "broken_reason")
+    """one synteny block: a path of vertices with one contig and one orientation per assembly.
+    The path is a list of segments (lo, hi, dir): base-vertex ids lo..hi joined by (i, i+1) links,
+    traversed upwards (dir = +1) or downwards (dir = -1); a lone vertex is (v, v, 1)."""
+    __slots__ = ("segs", "ctg", "ori", "first_id", "last_id", "first_pos", "last_pos", "n", "broken_reason")
 
-    def __init__(self, vids, ctg, ori, first_pos, last_pos, n):
-        self.vids = vids              # int64 vertex ids in path order (None after a collinear merge)
+    def __init__(self, segs, ctg, ori, first_id, last_id, first_pos, last_pos, n):
+        self.segs = segs
         self.ctg = ctg                # [G] contig index per assembly
         self.ori = ori                # [G] '+', '-'
+        self.first_id, self.last_id = first_id, last_id
         self.first_pos = first_pos    # [G] position of the first minimizer
         self.last_pos = last_pos      # [G] position of the last minimizer
         self.n = n                    # number of minimizers
@@ -61,6 +64,19 @@ class Block:
 
     def end(self, a, k):              # bin/assembly_block.py:21-23
         return max(int(self.first_pos[a]), int(self.last_pos[a])) + k
+
+
+def seg_first(seg):
+    return seg[0] if seg[2] > 0 else seg[1]
+
+
+def seg_last(seg):
+    return seg[1] if seg[2] > 0 else seg[0]
+
+
+def seg_ids(seg):
+    lo, hi, d = seg
+    return np.arange(lo, hi + 1, dtype=np.int64) if d > 0 else np.arange(hi, lo - 1, -1, dtype=np.int64)
 
 
 class IntervalIndex:
@@ -87,7 +103,9 @@ class SyntenyEngine:
          contig_names[a][c], contig_lengths[a][c]
          sketch(a, w, masks) -> (h1 u64, pos u32, ctg u32) in (contig, position) order;
                              masks = per-contig (starts, ends) extra N intervals or None
-         join(tables, order_asm) -> (H, POS, CTG, RANK, link, degree)   (device kernel iv)
+         join(tables, order_asm) -> dict with H[V], POS/CTG/RANK/INV[G,V], link/degree[V] and the per-pair
+                             arrays incmask/decmask/spread[V] of (i, i+1)            (device kernel iv)
+         lookup(h1 array)    -> vertex id per key (0xFFFFFFFF if none)               (device join table)
     """
 
     def __init__(self, backend, k, w, w_rounds, bp, collinear_merge, z, m=90, simplify=True, prefix="out",
@@ -126,25 +144,75 @@ class SyntenyEngine:
             _log(*a)
 
     # ------------------------------------------------------------------ vertex storage
-    def _init_vertices(self, H, POS, CTG, RANK):
+    def _init_vertices(self, j):
+        H = j["H"]
         V = len(H)
         self.V0 = V
         self.V = V
-        cap = V + 1024
+        cap = V + 65536 + V // 16
         self.H = np.empty(cap, dtype=np.uint64); self.H[:V] = H
-        self.POS = np.zeros((self.G, cap), dtype=np.int64); self.POS[:, :V] = POS
-        self.CTG = np.zeros((self.G, cap), dtype=np.int64); self.CTG[:, :V] = CTG
-        self.RANK = np.asarray(RANK, dtype=np.int64)                 # round-0 vertices only
-        self.INV = np.empty_like(self.RANK)
-        ar = np.arange(V, dtype=np.int64)
-        for a in range(self.G):
-            self.INV[a, self.RANK[a]] = ar
+        self.POS = np.zeros((self.G, cap), dtype=np.int64); self.POS[:, :V] = j["POS"]
+        self.CTG = np.zeros((self.G, cap), dtype=np.int32); self.CTG[:, :V] = j["CTG"]
+        self.RANK, self.INV = j["RANK"], j["INV"]                    # round-0 vertices only (uint32)
+        self._ctg0 = None                                            # copy-on-write snapshot of round-0 contigs
         self.alive = np.zeros(cap, dtype=bool); self.alive[:V] = True
         self.nbr = np.full((cap, 2), -1, dtype=np.int64)
-        # h1 -> id lookup: sorted view of the round-0 keys + dict for later additions
-        self._h_order = np.argsort(self.H[:V], kind="stable")
-        self._h_sorted = self.H[:V][self._h_order]
+        self.conn = np.zeros(max(V - 1, 0), dtype=bool)              # edge (i, i+1) present, base vertices
+        self.sparse = set()                                          # vertices that may hold a non-(i,i+1) edge
         self._h_extra = {}
+        # per-pair arrays of (i, i+1) and their prefix sums per assembly
+        self.incmask = np.array(j["incmask"], dtype=np.uint32)
+        self.decmask = np.array(j["decmask"], dtype=np.uint32)
+        self.spread = np.array(j["spread"], dtype=np.int64)
+        self._cum_dirty = True
+
+    def _cums(self):
+        "prefix sums (per assembly) of the direction bits of the pairs (i, i+1); CI[a, i] = sum over pairs < i"
+        if self._cum_dirty:
+            V = self.V0
+            self.CI = np.zeros((self.G, V + 1), dtype=np.int32)
+            self.CD = np.zeros((self.G, V + 1), dtype=np.int32)
+            for a in range(self.G):
+                np.cumsum((self.incmask >> np.uint32(a)) & np.uint32(1), out=self.CI[a, 1:])
+                np.cumsum((self.decmask >> np.uint32(a)) & np.uint32(1), out=self.CD[a, 1:])
+            self.big = np.flatnonzero(self.spread > self.bp)
+            self._cum_dirty = False
+        return self.CI, self.CD
+
+    def _refresh_pairs(self, vids):
+        """positions of base vertices were overwritten (update_list_mx_info): redo the values of their
+        (i, i+1) pairs and patch the prefix sums in place (a suffix add per changed pair)"""
+        if self._cum_dirty:
+            self._cums()
+        for v in vids:
+            for i in (v - 1, v):
+                if 0 <= i < self.V0 - 1:
+                    d = self.POS[:, i + 1] - self.POS[:, i]
+                    inc = dec = 0
+                    for a in range(self.G):
+                        inc |= (1 << a) if d[a] > 0 else 0
+                        dec |= (1 << a) if d[a] < 0 else 0
+                    old_i, old_d = int(self.incmask[i]), int(self.decmask[i])
+                    if inc != old_i or dec != old_d:
+                        for a in range(self.G):
+                            di = ((inc >> a) & 1) - ((old_i >> a) & 1)
+                            dd = ((dec >> a) & 1) - ((old_d >> a) & 1)
+                            if di:
+                                self.CI[a, i + 1:] += di
+                            if dd:
+                                self.CD[a, i + 1:] += dd
+                        self.incmask[i], self.decmask[i] = inc, dec
+                    ad = np.abs(d)
+                    sp = int(ad.max() - ad.min())
+                    if (sp > self.bp) != (self.spread[i] > self.bp):
+                        if sp > self.bp:
+                            self.big = np.insert(self.big, np.searchsorted(self.big, i), i)
+                        else:
+                            self.big = np.delete(self.big, np.searchsorted(self.big, i))
+                    self.spread[i] = sp
+
+    def _ctg_round0(self, a, v):
+        return (self.CTG if self._ctg0 is None else self._ctg0)[a, v]
 
     def _grow(self, need):
         cap = len(self.H)
@@ -153,22 +221,21 @@ class SyntenyEngine:
         new = max(cap * 2, self.V + need + 1024)
         self.H = np.concatenate([self.H, np.empty(new - cap, dtype=np.uint64)])
         self.POS = np.concatenate([self.POS, np.zeros((self.G, new - cap), dtype=np.int64)], axis=1)
-        self.CTG = np.concatenate([self.CTG, np.zeros((self.G, new - cap), dtype=np.int64)], axis=1)
+        self.CTG = np.concatenate([self.CTG, np.zeros((self.G, new - cap), dtype=np.int32)], axis=1)
         self.alive = np.concatenate([self.alive, np.zeros(new - cap, dtype=bool)])
         self.nbr = np.concatenate([self.nbr, np.full((new - cap, 2), -1, dtype=np.int64)])
 
     def _lookup(self, keys):
-        "vertex id per h1 (or -1) for a uint64 array"
-        keys = np.asarray(keys, dtype=np.uint64)
+        "vertex id per h1 (or -1) for a uint64 array: device join table, then the later additions"
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
         out = np.full(len(keys), -1, dtype=np.int64)
-        if len(self._h_sorted) and len(keys):
-            i = np.searchsorted(self._h_sorted, keys)
-            i[i >= len(self._h_sorted)] = 0
-            hit = self._h_sorted[i] == keys
-            out[hit] = self._h_order[i[hit]]
+        if len(keys) and self.V0:
+            got = np.asarray(self.be.lookup(keys)).astype(np.int64)
+            hit = got != 0xFFFFFFFF
+            out[hit] = got[hit]
         if self._h_extra:
-            for j in np.nonzero(out < 0)[0]:
-                out[j] = self._h_extra.get(int(keys[j]), -1)
+            for jx in np.nonzero(out < 0)[0]:
+                out[jx] = self._h_extra.get(int(keys[jx]), -1)
         return out
 
     # ------------------------------------------------------------------ degree-2 graph on arrays
@@ -183,34 +250,45 @@ class SyntenyEngine:
                 self.nbr[x, 1] = y
             else:
                 raise RuntimeError("internal error: vertex of degree > 2 in the weight-filtered graph")
+        if abs(u - v) == 1 and max(u, v) < self.V0:
+            self.conn[min(u, v)] = True
+        else:
+            self.sparse.add(int(u)); self.sparse.add(int(v))
 
     def _remove_edges(self, us, vs):
         us = np.asarray(us, dtype=np.int64); vs = np.asarray(vs, dtype=np.int64)
+        if not len(us):
+            return
         for x, y in ((us, vs), (vs, us)):
-            for s in (0, 1):
-                hit = self.nbr[x, s] == y
-                self.nbr[x[hit], s] = -1
+            for s_ in (0, 1):
+                hit = self.nbr[x, s_] == y
+                self.nbr[x[hit], s_] = -1
+        lo = np.minimum(us, vs)
+        base = (np.abs(us - vs) == 1) & (np.maximum(us, vs) < self.V0)
+        self.conn[lo[base]] = False
 
     def _remove_vertices(self, ids):
         ids = np.unique(np.asarray(ids, dtype=np.int64))
         if not len(ids):
             return
-        for s in (0, 1):
-            nb = self.nbr[ids, s]
+        for s_ in (0, 1):
+            nb = self.nbr[ids, s_]
             ok = nb >= 0
             self._remove_edges(ids[ok], nb[ok])
         self.alive[ids] = False
 
-    def _degree(self, ids=None):
-        n = self.nbr if ids is None else self.nbr[ids]
-        return (n >= 0).sum(axis=1)
+    def _remove_segments(self, segs):
+        "delete every vertex of the given segments"
+        ids = [seg_ids(sg) for sg in segs]
+        if ids:
+            self._remove_vertices(np.concatenate(ids))
 
     # ------------------------------------------------------------------ round-0 adjacency (implicit in ranks)
     def _adjacent(self, a, u, v):
         if u >= self.V0 or v >= self.V0:
             return False
         ru, rv = self.RANK[a, u], self.RANK[a, v]
-        return abs(int(ru) - int(rv)) == 1 and self._ctg0[a, u] == self._ctg0[a, v]
+        return abs(int(ru) - int(rv)) == 1 and self._ctg_round0(a, u) == self._ctg_round0(a, v)
 
     def _neighbors0(self, u):
         "distinct round-0 neighbours of u with their weights (number of supporting assemblies)"
@@ -220,7 +298,7 @@ class SyntenyEngine:
             for rr in (r - 1, r + 1):
                 if 0 <= rr < self.V0:
                     x = int(self.INV[a, rr])
-                    if self._ctg0[a, x] == self._ctg0[a, u]:
+                    if self._ctg_round0(a, x) == self._ctg_round0(a, u):
                         res[x] = res.get(x, 0) + 1
         return res
 
@@ -240,7 +318,7 @@ class SyntenyEngine:
             rs = int(self.RANK[a, src])
             if rs + 1 < self.V0:
                 x = int(self.INV[a, rs + 1])
-                if self._ctg0[a, x] == self._ctg0[a, src] and first_new(src, x) == a:
+                if self._ctg_round0(a, x) == self._ctg_round0(a, src) and first_new(src, x) == a:
                     sigma = (a, rs)
                     break
         return (0, sigma, tau)
@@ -283,172 +361,188 @@ class SyntenyEngine:
 
     # ------------------------------------------------------------------ paths of a max-degree-2 graph
     def _find_paths(self):
-        """ntjoin.py:114-151 on the weight-filtered graph: every component that is a simple path
-        with two distinct ends gives one path, oriented from the end with the smaller position in
-        the orienting assembly.  Returns a list of int64 id arrays."""
-        V = self.V
-        nbr = self.nbr[:V]
-        deg = (nbr >= 0).sum(axis=1)
-        ids = np.arange(V, dtype=np.int64)
-        right = (nbr[:, 0] == ids + 1) | (nbr[:, 1] == ids + 1)          # simple link i -> i+1
-        # runs of consecutive ids joined by simple links
-        start = np.ones(V, dtype=bool)
-        start[1:] = ~right[:-1]
-        run_start = np.nonzero(start)[0]
-        run_end = np.append(run_start[1:] - 1, V - 1) if V else run_start
-        run_len = run_end - run_start + 1
-        # sparse (non i,i+1) edges
-        left = np.zeros(V, dtype=bool)
-        left[1:] = right[:-1]
-        n_simple = right.astype(np.int64) + left.astype(np.int64)
-        has_sparse = deg > n_simple
+        """ntjoin.py:114-151 on the weight-filtered graph: every component that is a simple path with
+        two distinct ends gives one path, oriented from the end with the smaller position in the
+        orienting assembly.  A path is a list of segments (lo, hi, dir)."""
+        V0 = self.V0
         opos = self.POS[self.orient]
         paths = []
-        # pure runs: no sparse edge at either end
-        pure = (~has_sparse[run_start]) & (~has_sparse[run_end]) & (run_len >= 2)
-        for a, b in zip(run_start[pure], run_end[pure]):
-            pa, pb = opos[a], opos[b]
-            if pa < pb:
-                paths.append(np.arange(a, b + 1, dtype=np.int64))
-            elif pb < pa:
-                paths.append(np.arange(b, a - 1, -1, dtype=np.int64))
-        # components with sparse edges: walk run by run from every degree-1 end
-        if has_sparse.any():
-            run_of = np.cumsum(start) - 1
-            visited_runs = set()
-            sp_runs = np.unique(np.concatenate([run_of[np.nonzero(has_sparse)[0]]]))
-            ends = []
-            for rid in sp_runs:
-                for x in {int(run_start[rid]), int(run_end[rid])}:
-                    if deg[x] == 1:
-                        ends.append(x)
-            # also ends of runs reachable only through sparse edges are found by walking
-            for e0 in ends:
-                if int(run_of[e0]) in visited_runs:
+        if V0:
+            starts = np.concatenate([[0], np.flatnonzero(~self.conn) + 1])
+            ends = np.concatenate([starts[1:] - 1, [V0 - 1]])
+        else:
+            starts = ends = np.zeros(0, dtype=np.int64)
+        # vertices that really hold a sparse edge (non-consecutive neighbour, or any edge of a later vertex)
+        real_sparse = set()
+        if self.sparse:
+            sv = np.fromiter(self.sparse, dtype=np.int64, count=len(self.sparse))
+            nb = self.nbr[sv]
+            has = ((nb >= 0) & ((np.abs(nb - sv[:, None]) != 1) | (np.maximum(nb, sv[:, None]) >= V0))).any(axis=1)
+            real_sparse = set(int(x) for x in sv[has])
+            self.sparse = set(real_sparse)
+        is_sp_run = np.zeros(len(starts), dtype=bool)
+        base_sp = np.array([v for v in real_sparse if v < V0], dtype=np.int64)
+        if len(base_sp):
+            is_sp_run[np.searchsorted(starts, base_sp, side="right") - 1] = True
+        pure = np.flatnonzero((ends > starts) & ~is_sp_run)
+        pa, pb = opos[starts[pure]], opos[ends[pure]]
+        for a, b, x, y in zip(starts[pure].tolist(), ends[pure].tolist(), pa.tolist(), pb.tolist()):
+            if x < y:
+                paths.append([(a, b, 1)])
+            elif y < x:
+                paths.append([(a, b, -1)])
+        if real_sparse:
+            def run_bounds(v):
+                if v >= V0:
+                    return v, v
+                r = int(np.searchsorted(starts, v, side="right") - 1)
+                return int(starts[r]), int(ends[r])
+
+            def degree(v):
+                return int((self.nbr[v] >= 0).sum())
+            seen_runs = set()
+            cand_ends = []
+            for v in sorted(real_sparse):
+                a, b = run_bounds(v)
+                for x in {a, b}:
+                    if degree(x) == 1:
+                        cand_ends.append(x)
+            for e0 in cand_ends:
+                if run_bounds(e0)[0] in seen_runs:
                     continue
-                seq = []
-                prev, cur = -1, e0
-                ok = True
+                segs, prev, cur, ok = [], -1, e0, True
                 while True:
-                    rid = int(run_of[cur])
-                    if rid in visited_runs:
-                        ok = False       # cycle guard (cannot happen from a degree-1 start)
+                    a, b = run_bounds(cur)
+                    if a in seen_runs:
+                        ok = False
                         break
-                    visited_runs.add(rid)
-                    a, b = int(run_start[rid]), int(run_end[rid])
+                    seen_runs.add(a)
                     if cur == a:
-                        seq.append(np.arange(a, b + 1, dtype=np.int64)); last = b
+                        segs.append((a, b, 1)); last = b
                     else:
-                        seq.append(np.arange(b, a - 1, -1, dtype=np.int64)); last = a
-                    # leave the run through the sparse neighbour of `last`
-                    inside = (last - 1 if last == b and b > a else (last + 1 if last == a and b > a else -1))
+                        segs.append((a, b, -1)); last = a
+                    inside = -1
+                    if b > a:
+                        inside = last - 1 if last == b else last + 1
                     nxt = -1
-                    for s in (0, 1):
-                        y = int(nbr[last, s])
-                        if y >= 0 and y != inside and y != (prev if a == b else -2):
-                            nxt = y
-                    if a == b and nxt < 0:
-                        # singleton run: both slots may be sparse; pick the one that is not `prev`
-                        cand = [int(nbr[last, s]) for s in (0, 1) if nbr[last, s] >= 0 and nbr[last, s] != prev]
-                        nxt = cand[0] if cand else -1
+                    for y in self.nbr[last]:
+                        y = int(y)
+                        if y < 0 or y == inside:
+                            continue
+                        if a == b and y == prev:
+                            continue
+                        nxt = y
                     if nxt < 0:
                         break
                     prev, cur = last, nxt
                 if not ok:
                     continue
-                p = np.concatenate(seq)
-                if len(p) < 2:
+                first, lastv = seg_first(segs[0]), seg_last(segs[-1])
+                if first == lastv:
                     continue
-                pa, pb = opos[p[0]], opos[p[-1]]
+                pa, pb = opos[first], opos[lastv]
                 if pa < pb:
-                    paths.append(p)
+                    paths.append(segs)
                 elif pb < pa:
-                    paths.append(p[::-1].copy())
+                    paths.append([(lo, hi, -d) for lo, hi, d in reversed(segs)])
         return paths
 
-    # ------------------------------------------------------------------ blocks from paths (vectorised)
+    # ------------------------------------------------------------------ blocks from paths
     def _blocks_from_paths(self, paths):
-        """find_synteny_blocks (ntsynt_synteny.py:66-106) for every path.  Returns blocks; vertices of
-        unoriented blocks are deleted from the graph."""
-        if not paths:
-            return []
+        """find_synteny_blocks (ntsynt_synteny.py:66-106) for every path.  Orientation tallies come from
+        prefix sums of the per-pair direction masks; only junctions between segments are looked at
+        one by one.  Vertices of unoriented blocks are deleted from the graph."""
         G = self.G
-        lens = np.array([len(p) for p in paths], dtype=np.int64)
-        pv = np.concatenate(paths)
-        off = np.concatenate([[0], np.cumsum(lens)])
-        N = len(pv)
-        pid = np.repeat(np.arange(len(paths)), lens)
-        ctg = self.CTG[:, pv]                         # [G, N]
-        pos = self.POS[:, pv]
-        # contig change between consecutive path vertices (any assembly)
-        same_path = np.zeros(N, dtype=bool)
-        same_path[1:] = pid[1:] == pid[:-1]
-        chg = np.zeros(N, dtype=bool)
-        chg[1:] = (ctg[:, 1:] != ctg[:, :-1]).any(axis=0) & same_path[1:]
-        # only the LAST run of constant contigs of each path becomes a block (past_start_flag is
-        # never set, ntsynt_synteny.py:71,77): block start = last change index, else path start
-        idx = np.arange(N, dtype=np.int64)
-        last_chg = np.full(len(paths), -1, dtype=np.int64)
-        if chg.any():
-            np.maximum.at(last_chg, pid[chg], idx[chg])
-        bstart = np.where(last_chg >= 0, last_chg, off[:-1])
-        bend = off[1:]
+        CI, CD = self._cums()
         blocks, to_remove = [], []
-        # orientation tallies per assembly over consecutive pairs inside the block
-        inside = np.zeros(N, dtype=bool)             # pair (j-1, j) inside the block
-        inside[1:] = same_path[1:] & (idx[1:] > bstart[pid[1:]])
-        inc = np.zeros((G, len(paths)), dtype=np.int64)
-        dec = np.zeros((G, len(paths)), dtype=np.int64)
-        if N > 1:
-            d = pos[:, 1:] - pos[:, :-1]
-            m_in = inside[1:]
-            for a in range(G):
-                np.add.at(inc[a], pid[1:][m_in & (d[a] > 0)], 1)
-                np.add.at(dec[a], pid[1:][m_in & (d[a] < 0)], 1)
-        for p in range(len(paths)):
-            s, e = int(bstart[p]), int(bend[p])
-            n = e - s
+        for segs in paths:
+            # contig change can only happen at a junction between segments: keep the LAST run of constant
+            # contigs (past_start_flag is never set, ntsynt_synteny.py:71,77)
+            start_seg = 0
+            for jx in range(1, len(segs)):
+                u, v = seg_last(segs[jx - 1]), seg_first(segs[jx])
+                if (self.CTG[:, u] != self.CTG[:, v]).any():
+                    start_seg = jx
+            segs = segs[start_seg:]
+            n = sum(hi - lo + 1 for lo, hi, _ in segs)
+            inc = np.zeros(G, dtype=np.int64)
+            dec = np.zeros(G, dtype=np.int64)
+            for lo, hi, d in segs:
+                if hi > lo:
+                    up, down = CI[:, hi] - CI[:, lo], CD[:, hi] - CD[:, lo]
+                    if d > 0:
+                        inc += up; dec += down
+                    else:
+                        inc += down; dec += up
+            for jx in range(1, len(segs)):
+                dp = self.POS[:, seg_first(segs[jx])] - self.POS[:, seg_last(segs[jx - 1])]
+                inc += dp > 0
+                dec += dp < 0
             ori = []
             for a in range(G):
-                if n == 1 or inc[a, p] == n - 1:
+                if n == 1 or inc[a] == n - 1:
                     ori.append("+")
-                elif dec[a, p] == n - 1:
+                elif dec[a] == n - 1:
                     ori.append("-")
                 else:
-                    positive = int(inc[a, p]) / float(n - 1) * 100
+                    positive = int(inc[a]) / float(n - 1) * 100
                     negative = 100 - positive
                     ori.append("+" if positive >= self.m else ("-" if negative >= self.m else "?"))
-            vids = pv[s:e]
             if "?" in ori:
-                to_remove.append(vids)
+                to_remove.extend(segs)
                 continue
-            blocks.append(Block(vids, ctg[:, s].copy(), ori, pos[:, s].copy(), pos[:, e - 1].copy(), n))
+            f, l = seg_first(segs[0]), seg_last(segs[-1])
+            blocks.append(Block(segs, self.CTG[:, f].copy(), ori, f, l, self.POS[:, f].copy(), self.POS[:, l].copy(), n))
         if to_remove:
-            self._remove_vertices(np.concatenate(to_remove))
+            self._remove_segments(to_remove)
         return blocks
 
     def _split_indels(self, blocks):
         "check_for_indels + break_synteny_block (ntsynt_synteny.py:364-409)"
+        self._cums()
+        big = self.big
         out = []
         rm_u, rm_v = [], []
         for b in blocks:
-            if b.n < 2:
+            # break points as (segment index, id of the vertex BEFORE the break in traversal order)
+            pieces, cur = [], []
+            any_break = False
+            for jx, (lo, hi, d) in enumerate(b.segs):
+                if jx > 0:
+                    u, v = seg_last(b.segs[jx - 1]), seg_first(b.segs[jx])
+                    dd = np.abs(self.POS[:, v] - self.POS[:, u])
+                    if int(dd.max() - dd.min()) > self.bp:
+                        rm_u.append(u); rm_v.append(v)
+                        pieces.append(cur); cur = []
+                        any_break = True
+                cuts = big[np.searchsorted(big, lo):np.searchsorted(big, hi)] if hi > lo else ()
+                if len(cuts):
+                    any_break = True
+                    rm_u.extend(int(c) for c in cuts); rm_v.extend(int(c) + 1 for c in cuts)
+                    if d > 0:
+                        s0 = lo
+                        for c in cuts:
+                            cur.append((s0, int(c), 1)); pieces.append(cur); cur = []
+                            s0 = int(c) + 1
+                        cur.append((s0, hi, 1))
+                    else:
+                        s0 = hi
+                        for c in cuts[::-1]:
+                            cur.append((int(c) + 1, s0, -1)); pieces.append(cur); cur = []
+                            s0 = int(c)
+                        cur.append((lo, s0, -1))
+                else:
+                    cur.append((lo, hi, d))
+            pieces.append(cur)
+            if not any_break:
                 out.append(b)
                 continue
-            pos = self.POS[:, b.vids]
-            d = np.abs(pos[:, 1:] - pos[:, :-1])
-            spread = d.max(axis=0) - d.min(axis=0)
-            brk = np.nonzero(spread > self.bp)[0]
-            if not len(brk):
-                out.append(b)
-                continue
-            rm_u.append(b.vids[brk]); rm_v.append(b.vids[brk + 1])
-            cuts = [0] + [int(x) + 1 for x in brk] + [b.n]
-            for s, e in zip(cuts[:-1], cuts[1:]):
-                vids = b.vids[s:e]
-                out.append(Block(vids, b.ctg, list(b.ori), pos[:, s].copy(), pos[:, e - 1].copy(), e - s))
+            for segs in pieces:
+                f, l = seg_first(segs[0]), seg_last(segs[-1])
+                n = sum(hi - lo + 1 for lo, hi, _ in segs)
+                out.append(Block(segs, b.ctg, list(b.ori), f, l, self.POS[:, f].copy(), self.POS[:, l].copy(), n))
         if rm_u:
-            self._remove_edges(np.concatenate(rm_u), np.concatenate(rm_v))
+            self._remove_edges(np.array(rm_u, dtype=np.int64), np.array(rm_v, dtype=np.int64))
         return out
 
     def _filter_small(self, blocks, min_mx):
@@ -458,9 +552,9 @@ class SyntenyEngine:
             if b.n >= min_mx:
                 keep.append(b)
             else:
-                rm.append(b.vids)
+                rm.extend(b.segs)
         if rm:
-            self._remove_vertices(np.concatenate(rm))
+            self._remove_segments(rm)
         return keep
 
     # ------------------------------------------------------------------ output
@@ -529,8 +623,9 @@ class SyntenyEngine:
             else:
                 # extend: coordinates come from the first minimizer of `cur` and the last of `b`
                 cur.last_pos = b.last_pos
+                cur.last_id = b.last_id
                 cur.n += b.n
-                cur.vids = None
+                cur.segs = None
         out.append(cur)
         return out
 
@@ -582,10 +677,14 @@ class SyntenyEngine:
             h1, pos, ctg = self.be.sketch(a, new_w, masks[a])
             new.append(self._dedup(h1, pos.astype(np.int64), ctg.astype(np.int64)))
         # --- terminal / internal minimizers and block intervals (find_mx_in_blocks :205-226)
-        term_ids = np.array([x for b in blocks for x in (int(b.vids[0]), int(b.vids[-1]))], dtype=np.int64)
+        term_ids = np.array([x for b in blocks for x in (b.first_id, b.last_id)], dtype=np.int64)
         terminal_h = set(int(x) for x in self.H[term_ids]) if len(term_ids) else set()
-        internal_ids = [b.vids[1:-1] for b in blocks if b.n > 2]
-        internal_h = np.sort(self.H[np.concatenate(internal_ids)]) if internal_ids else np.zeros(0, dtype=np.uint64)
+        is_internal = np.zeros(self.V, dtype=bool)
+        for b in blocks:
+            for lo, hi, _ in b.segs:
+                is_internal[lo:hi + 1] = True
+        if len(term_ids):
+            is_internal[term_ids] = False
         intervals = [defaultdict(list) for _ in range(G)]
         for b in blocks:
             for a in range(G):
@@ -601,11 +700,10 @@ class SyntenyEngine:
             if n == 0:
                 kept.append((h1, pos, ctg, np.zeros(0, dtype=np.int64)))
                 continue
-            is_internal = np.zeros(n, dtype=bool)
-            if len(internal_h):
-                j = np.searchsorted(internal_h, h1)
-                j[j >= len(internal_h)] = 0
-                is_internal = internal_h[j] == h1
+            vid_new = self._lookup(h1)
+            internal_hit = np.zeros(n, dtype=bool)
+            known = vid_new >= 0
+            internal_hit[known] = is_internal[vid_new[known]]
             inside = np.zeros(n, dtype=bool)
             idx_by_ctg = {}
             for c in np.unique(ctg):
@@ -616,7 +714,7 @@ class SyntenyEngine:
                     idx_by_ctg[c] = ii
                     sel = np.nonzero(ctg == c)[0]
                     inside[sel] = ii.overlaps(pos[sel], pos[sel] + 1)
-            keep = ~is_internal & ~inside
+            keep = ~internal_hit & ~inside
             kh, kp, kc = h1[keep], pos[keep], ctg[keep]
             # cut between consecutive kept minimizers of one contig whose span overlaps a block interval
             cut = np.ones(len(kh), dtype=bool)
@@ -659,13 +757,22 @@ class SyntenyEngine:
                 self.alive[vid] = False
                 self.nbr[vid] = -1
                 cid[j] = vid
+            touched_base = set()
             for a in range(G):
                 kh, kp, kc, _ = lists[a]
                 j = np.searchsorted(common, kh)
                 vid = cid[j]
+                changed = (self.POS[a, vid] != kp) | (self.CTG[a, vid] != kc)
+                base_changed = vid[changed & (vid < self.V0)]
+                if len(base_changed):
+                    if self._ctg0 is None:
+                        self._ctg0 = self.CTG[:, :self.V0].copy()
+                    touched_base.update(int(x) for x in base_changed)
                 self.POS[a, vid] = kp
                 self.CTG[a, vid] = kc
                 ids_per_asm.append(vid)
+            if touched_base:
+                self._refresh_pairs(sorted(touched_base))
         else:
             ids_per_asm = [np.zeros(0, dtype=np.int64) for _ in range(G)]
         # --- build_graph in extend mode (ntjoin_utils.py:83-141)
@@ -825,10 +932,10 @@ class SyntenyEngine:
             raise SystemExit(1)
         self.log("Sketching and joining minimizers, w =", self.w)
         tables = [self.be.sketch(a, self.w, None) for a in range(G)]
-        H, POS, CTG, RANK, link, degree = self.be.join(tables, self.orient)
-        self.stats["vertices"] = int(len(H))
-        self._init_vertices(H, POS, CTG, RANK)
-        self._ctg0 = self.CTG[:, :self.V0].copy()
+        j = self.be.join(tables, self.orient)
+        link, degree = j["link"], j["degree"]
+        self.stats["vertices"] = int(len(j["H"]))
+        self._init_vertices(j)
         self._edge_birth = {}
         V = self.V0
         # --- simplification, weight filter
@@ -838,10 +945,11 @@ class SyntenyEngine:
             bumped, removed = self._simplify_round0(np.asarray(link), np.asarray(degree))
         self.stats["simplified_vertices"] = len(set(removed))
         self.log("Filtering the graph")
-        lk = np.asarray(link[:max(V - 1, 0)], dtype=bool) if V else np.zeros(0, dtype=bool)
-        ids = np.arange(max(V - 1, 0), dtype=np.int64)
-        self.nbr[ids[lk], 1] = ids[lk] + 1          # slot 1: right neighbour
-        self.nbr[ids[lk] + 1, 0] = ids[lk]          # slot 0: left neighbour
+        if V > 1:
+            self.conn[:] = np.asarray(link[:V - 1], dtype=bool)
+            ids = np.flatnonzero(self.conn)
+            self.nbr[ids, 1] = ids + 1                  # slot 1: right neighbour
+            self.nbr[ids + 1, 0] = ids                  # slot 0: left neighbour
         if removed:
             self._remove_vertices(np.array(removed, dtype=np.int64))
         for (s, t) in bumped:

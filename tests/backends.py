@@ -54,6 +54,22 @@ def numpy_join(tables, order_asm):
     return H, POS, CTG, RANK, link, degree
 
 
+def numpy_pairs(POS):
+    "per-pair (i, i+1) direction masks and |dpos| spread (graph_links_kernel restated)"
+    G, V = POS.shape
+    inc = np.zeros(V, dtype=np.uint32)
+    dec = np.zeros(V, dtype=np.uint32)
+    spread = np.zeros(V, dtype=np.uint32)
+    if V > 1:
+        d = POS[:, 1:].astype(np.int64) - POS[:, :-1].astype(np.int64)
+        for a in range(G):
+            inc[:-1] |= ((d[a] > 0).astype(np.uint32) << np.uint32(a))
+            dec[:-1] |= ((d[a] < 0).astype(np.uint32) << np.uint32(a))
+        ad = np.abs(d)
+        spread[:-1] = (ad.max(axis=0) - ad.min(axis=0)).astype(np.uint32)
+    return inc, dec, spread
+
+
 def numpy_edges(RANK, CTG):
     "edge table in build_graph's first-insertion order: list of (u, v, support_mask)"
     G, V = RANK.shape
@@ -106,4 +122,22 @@ class OracleBackend:
         return np.concatenate(hs), np.concatenate(ps), np.concatenate(cs)
 
     def join(self, tables, order_asm):
-        return numpy_join(tables, order_asm)
+        H, POS, CTG, RANK, link, degree = numpy_join(tables, order_asm)
+        G, V = RANK.shape
+        INV = np.zeros((G, V), dtype=np.uint32)
+        for a in range(G):
+            INV[a, RANK[a]] = np.arange(V, dtype=np.uint32)
+        inc, dec, spread = numpy_pairs(POS)
+        self._h_order = np.argsort(H, kind="stable")
+        self._h_sorted = H[self._h_order]
+        return dict(H=H, POS=POS, CTG=CTG, RANK=RANK, INV=INV, link=link, degree=degree, incmask=inc, decmask=dec,
+                    spread=spread)
+
+    def lookup(self, keys):
+        out = np.full(len(keys), 0xFFFFFFFF, dtype=np.uint32)
+        if len(self._h_sorted):
+            i = np.searchsorted(self._h_sorted, keys)
+            i[i >= len(self._h_sorted)] = 0
+            hit = self._h_sorted[i] == keys
+            out[hit] = self._h_order[i[hit]]
+        return out
