@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -686,6 +687,10 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     uint64_t m = 0, mp = 0;
     if (common) mod_params(common, &m, &mp); else if (repeat) mod_params(repeat, &m, &mp);
 
+    // pruning threshold: ~48 slots per window are expected below tau (uniform hashes)
+    uint64_t tau = KEY_MAX;
+    if ((common || repeat) && w > 96) tau = (uint64_t)((48.0 / (double)w) * 18446744073709551616.0);
+    if (const char* env = getenv("NTS_SKETCH_NO_PRUNE")) { if (env[0] == '1') tau = KEY_MAX; }
     const size_t smem = sketch_smem_bytes(NT, THREADS);
     NTS_CUDA(cudaFuncSetAttribute(sketch_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
@@ -712,7 +717,7 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
             ProfScope prof(ctx, PROF_SKETCH, (double)v->total_valid);
             sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(
                 device_view(g, v), tabs, common ? common->words.p : nullptr, repeat ? repeat->words.p : nullptr, m, mp,
-                d_tiles.p, w, T, so);
+                d_tiles.p, w, T, tau, so);
             ctx->launches++;
         }
         NTS_CUDA(cudaGetLastError());

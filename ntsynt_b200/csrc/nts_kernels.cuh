@@ -232,7 +232,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 2)
 sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
               const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, const TileDesc* __restrict__ tiles,
-              uint32_t w, uint32_t T, SketchOut out)
+              uint32_t w, uint32_t T, uint64_t tau, SketchOut out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t NT = T + w;
@@ -253,8 +253,28 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     const uint64_t avail = td.vend - td.vfirst + 1;               // slots 0..avail-1 map below vend
     const uint32_t n_end = (uint32_t)min((uint64_t)NT, avail);    // slots [i_lo, n_end) are real
 
-    // ---- phase A1: hash (kernel i).  thread t owns slots [t*C, t*C + C)
+    // Threshold-pruned Bloom queries: a slot whose hash is >= tau cannot be a window minimum unless every
+    // slot below tau in that window fails the filter, so pass 0 queries only the slots below tau (the others
+    // become UINT64_MAX unqueried).  A window whose minimum is still UINT64_MAX after pass 0 is unresolved;
+    // if the tile has one, the whole tile is redone with tau = UINT64_MAX (query everything).  Exact by
+    // construction: a resolved window has the same rightmost minimum under both rules.
     const uint32_t c0 = threadIdx.x * C;
+    const uint32_t hi = min(c0 + C, NT);
+    const uint32_t n_own = n_end > w ? n_end - w : 0;
+    const uint32_t per = (n_own + THREADS - 1) / THREADS;
+    const uint32_t o0 = w + threadIdx.x * per, o1 = min(o0 + per, n_end);
+    uint32_t cnt = 0;
+    // window ending at slot i covers [i-w+1, i]
+    auto win_min = [&](uint32_t i) -> uint32_t {
+        uint32_t p = s_P[i];
+        if ((i + 1) % w == 0) return p;                 // the window is exactly one block
+        uint32_t s = s_S[i + 1 - w];
+        return (s_key[p] <= s_key[s]) ? p : s;          // p lies to the right: wins ties
+    };
+    const bool filtered = (common != nullptr || repeat != nullptr);
+    for (int pass = 0; pass < 2; ++pass) {
+    const uint64_t tau_cur = (pass == 0 && filtered) ? tau : KEY_MAX;
+    // ---- phase A1: hash (kernel i).  thread t owns slots [t*C, t*C + C)
     {
         uint32_t a = max(c0, i_lo), b = min(c0 + C, n_end);
         for (uint32_t i = c0; i < min(c0 + C, NT); ++i)
@@ -265,7 +285,7 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     __syncthreads();
 
     // ---- phase A2: Bloom query (kernel iii-c), 8 independent sector loads in flight per thread
-    if (common != nullptr || repeat != nullptr) {
+    if (filtered) {
         for (uint32_t i0 = threadIdx.x; i0 < n_end; i0 += THREADS * 8) {
             uint64_t h[8];
             uint32_t cw[8], rw[8];
@@ -275,7 +295,8 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
                 h[u] = (i < n_end) ? s_key[i] : 0;
                 uint64_t idx = fast_mod(h[u], m, mprime);
                 cw[u] = 0xFFFFFFFFu; rw[u] = 0;
-                if (i < n_end && i >= i_lo) {
+                if (i < n_end && i >= i_lo && h[u] >= tau_cur) cw[u] = 0;          // pruned: not queried
+                else if (i < n_end && i >= i_lo) {
                     if (common) cw[u] = __ldg(&common[idx >> 5]) >> (idx & 31);
                     if (repeat) rw[u] = __ldg(&repeat[idx >> 5]) >> (idx & 31);
                 }
@@ -290,7 +311,6 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     }
 
     // ---- phase B: van Herk / Gil-Werman over blocks of w slots: [b*w, (b+1)*w)
-    const uint32_t hi = min(c0 + C, NT);
     // suffix arg-min S[i] over [i, end of i's block]; rightmost wins ties
     {
         KeyIdx run; run.key = KEY_MAX; run.idx = 0xFFFFFFFFu;
@@ -340,26 +360,23 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     __syncthreads();
 
     // ---- phase C: window minima, change detection, ordered compaction
-    // window ending at slot i covers [i-w+1, i]
-    auto win_min = [&](uint32_t i) -> uint32_t {
-        uint32_t p = s_P[i];
-        if ((i + 1) % w == 0) return p;                 // the window is exactly one block
-        uint32_t s = s_S[i + 1 - w];
-        return (s_key[p] <= s_key[s]) ? p : s;          // p lies to the right: wins ties
-    };
     // owned window ends: slots [w, n_end); thread t takes a contiguous share
-    const uint32_t n_own = n_end > w ? n_end - w : 0;
-    const uint32_t per = (n_own + THREADS - 1) / THREADS;
-    const uint32_t o0 = w + threadIdx.x * per, o1 = min(o0 + per, n_end);
-    uint32_t cnt = 0;
+    cnt = 0;
+    int unresolved = 0;
     if (o0 < o1) {
         uint32_t prev = (o0 == w && !td.has_prev) ? 0xFFFFFFFFu : win_min(o0 - 1);
+        // the window before the tile's first owned one decides whether that one is "new": it must be resolved too
+        if (o0 == w && td.has_prev && s_key[prev] == KEY_MAX) unresolved = 1;
         for (uint32_t i = o0; i < o1; ++i) {
             uint32_t a = win_min(i);
-            if (a != prev && s_key[a] != KEY_MAX) ++cnt;
+            if (s_key[a] == KEY_MAX) unresolved = 1;
+            else if (a != prev) ++cnt;
             prev = a;
         }
     }
+    if (tau_cur == KEY_MAX) break;                      // uniform: everything was queried
+    if (!__syncthreads_or(unresolved)) break;           // every owned window has a verified minimum
+    }   // pass
     // CTA exclusive scan of cnt
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t incl = cnt;
