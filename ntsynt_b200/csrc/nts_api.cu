@@ -12,6 +12,10 @@
 
 namespace nts {
 
+int bf_insert_partitioned(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid,
+                          bool* done);
+void part_scratch_release(nts_ctx* ctx);
+
 static thread_local std::string g_err;
 
 void set_error(const std::string& msg) { g_err = msg; }
@@ -186,6 +190,7 @@ void nts_ctx_destroy(nts_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    part_scratch_release(ctx);
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -493,6 +498,12 @@ int nts_bf_insert_genome_async(nts_bf* bf, const nts_genome* g, uint32_t k)
     rc = get_plain_view(g, k, &v);
     if (rc) return rc;
     if (v->total_valid == 0) return NTS_OK;
+    {
+        bool done = false;
+        rc = bf_insert_partitioned(ctx, bf, device_view(g, v), tabs, v->total_valid, &done);
+        if (rc) return rc;
+        if (done) return NTS_OK;
+    }
     uint64_t m, mp;
     mod_params(bf, &m, &mp);
     constexpr int THREADS = 256;

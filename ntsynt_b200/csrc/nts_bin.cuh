@@ -1,0 +1,151 @@
+// nts_bin.cuh -- (iii-a) partitioned Bloom insert.
+//
+// Random 32-byte read-modify-writes into a 14.8 GB array run at ~30 % of HBM peak and move 1.7x the
+// algorithmic bytes (profiles/README.md).  The partitioned insert makes the filter traffic streaming:
+//   pass 1 (bf_bin_kernel)   : hash a tile of k-mers, counting-sort their bit indices by filter REGION
+//                              (2^region_shift bits, sized to sit in L2) in shared memory, and append each
+//                              region's run to that region's bucket in global memory (one atomicAdd per run);
+//   pass 2 (bf_apply_kernel) : walk the buckets in region order; the RED.ORs of one region hit in L2 and
+//                              the region is written back to HBM once.
+// Items that do not fit a bucket (heavy-hitter k-mers) are applied directly -- correctness never depends
+// on the bucket capacities.
+#pragma once
+#include "nts_device.cuh"
+
+namespace nts {
+
+__device__ __forceinline__ void stage_tables_bin(HashTables* s_tabs, const HashTables* __restrict__ g_tabs, uint32_t k)
+{
+    for (uint32_t i = threadIdx.x; i < 16; i += blockDim.x) {
+        s_tabs->roll_f[i] = g_tabs->roll_f[i];
+        s_tabs->roll_r[i] = g_tabs->roll_r[i];
+    }
+    for (uint32_t i = threadIdx.x; i < k * 4; i += blockDim.x) {
+        s_tabs->init_f[i] = g_tabs->init_f[i];
+        s_tabs->init_r[i] = g_tabs->init_r[i];
+    }
+}
+
+struct BinParams {
+    uint32_t* items;               // bucket storage, bucket b at [bucket_off[b], bucket_off[b] + bucket_cap[b])
+    const uint64_t* bucket_off;    // [P]
+    const uint32_t* bucket_cap;    // [P]
+    unsigned int* cursor;          // [P] items appended so far (may run past cap: clamp when reading)
+    uint32_t n_buckets;
+    uint32_t region_shift;         // bits per region = 1 << region_shift  (<= 32)
+};
+
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const HashTables* __restrict__ g_tabs,
+                                                             uint32_t* __restrict__ bits, uint64_t m, uint64_t mprime,
+                                                             uint64_t total_valid, BinParams bp)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char smem_bin[];
+    HashTables* s_tabs = reinterpret_cast<HashTables*>(smem_bin);
+    uint32_t* s_low = reinterpret_cast<uint32_t*>(s_tabs + 1);   // [TILE] bit index inside the region, slot = j*THREADS + tid
+    uint32_t* s_br = s_low + TILE;                               // [TILE] bucket << 16 | rank inside the tile's run
+    uint32_t* s_sorted = s_br + TILE;                            // [TILE] items in region order
+    uint32_t* s_cnt = s_sorted + TILE;                           // [P] count, then exclusive offset
+    uint32_t* s_base = s_cnt + bp.n_buckets;                     // [P] position of the run inside the bucket
+    uint32_t* s_fit = s_base + bp.n_buckets;                     // [P] how many items of the run fit
+    __shared__ uint32_t s_wsum[THREADS / 32];
+    stage_tables_bin(s_tabs, g_tabs, g.k);
+    for (uint32_t b = threadIdx.x; b < bp.n_buckets; b += THREADS) s_cnt[b] = 0;
+    __syncthreads();
+    const uint64_t tile0 = (uint64_t)blockIdx.x * TILE;
+    const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, total_valid - tile0);
+    const uint64_t v0 = tile0 + (uint64_t)threadIdx.x * ITEMS;
+    const uint32_t n_mine = v0 < total_valid ? (uint32_t)min((uint64_t)ITEMS, total_valid - v0) : 0;
+    const uint32_t low_mask = bp.region_shift >= 32 ? 0xFFFFFFFFu : ((1u << bp.region_shift) - 1);
+    if (n_mine)
+        hash_run(g, s_tabs, v0, n_mine, [&](uint32_t j, uint64_t h0, uint64_t) {
+            const uint64_t idx = fast_mod(h0, m, mprime);
+            const uint32_t b = (uint32_t)(idx >> bp.region_shift);
+            const uint32_t slot = j * THREADS + threadIdx.x;
+            s_low[slot] = (uint32_t)idx & low_mask;
+            s_br[slot] = (b << 16) | atomicAdd(&s_cnt[b], 1u);
+        });
+    __syncthreads();
+    // reserve the runs (one global atomic per non-empty bucket)
+    for (uint32_t b = threadIdx.x; b < bp.n_buckets; b += THREADS) {
+        const uint32_t c = s_cnt[b];
+        uint32_t base = 0, fit = 0;
+        if (c) {
+            base = atomicAdd(&bp.cursor[b], c);
+            const uint32_t cap = bp.bucket_cap[b];
+            fit = base >= cap ? 0u : min(c, cap - base);
+        }
+        s_base[b] = base; s_fit[b] = fit;
+    }
+    __syncthreads();
+    // exclusive scan of the counts over the buckets
+    {
+        uint32_t carry = 0;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (uint32_t b0 = 0; b0 < bp.n_buckets; b0 += THREADS) {
+            const uint32_t b = b0 + threadIdx.x;
+            const uint32_t c = b < bp.n_buckets ? s_cnt[b] : 0;
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+            if (lane == 31) s_wsum[wid] = incl;
+            __syncthreads();
+            uint32_t woff = 0, total = 0;
+            for (int i = 0; i < THREADS / 32; ++i) { if (i < wid) woff += s_wsum[i]; total += s_wsum[i]; }
+            if (b < bp.n_buckets) s_cnt[b] = carry + woff + incl - c;
+            carry += total;
+            __syncthreads();
+        }
+    }
+    // place the items in region order
+    for (uint32_t j = 0; j < n_mine; ++j) {
+        const uint32_t slot = j * THREADS + threadIdx.x;
+        const uint32_t br = s_br[slot];
+        s_sorted[s_cnt[br >> 16] + (br & 0xFFFFu)] = s_low[slot];
+    }
+    __syncthreads();
+    // write every run: warp w handles buckets w, w + n_warps, ...
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t b = wid; b < bp.n_buckets; b += THREADS / 32) {
+        const uint32_t off = s_cnt[b];
+        const uint32_t c = (b + 1 < bp.n_buckets ? s_cnt[b + 1] : n_tile) - off;
+        if (!c) continue;
+        const uint32_t fit = s_fit[b];
+        uint32_t* dst = bp.items + bp.bucket_off[b] + s_base[b];
+        for (uint32_t i = lane; i < fit; i += 32) dst[i] = s_sorted[off + i];
+        const uint64_t region_bit0 = (uint64_t)b << bp.region_shift;      // overflow (heavy hitters): apply directly
+        for (uint32_t i = fit + lane; i < c; i += 32) {
+            const uint64_t idx = region_bit0 + s_sorted[off + i];
+            atomicOr(&bits[idx >> 5], 1u << (idx & 31));
+        }
+    }
+}
+
+// pass 2: CTA c applies chunk c of the concatenated buckets; chunks are in region order, so the CTAs
+// resident at any moment touch one or two regions and their RED.ORs hit in L2
+__global__ void bf_apply_kernel(const uint32_t* __restrict__ items, const uint64_t* __restrict__ bucket_off,
+                                const uint32_t* __restrict__ bucket_cap, const unsigned int* __restrict__ cursor,
+                                const uint64_t* __restrict__ chunk_first /*[P+1] first chunk id of each bucket*/,
+                                uint32_t n_buckets, uint32_t region_shift, uint32_t chunk_items,
+                                uint32_t* __restrict__ bits)
+{
+    uint32_t lo = 0, hi = n_buckets;          // bucket of this chunk: last b with chunk_first[b] <= blockIdx.x
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (chunk_first[mid] <= blockIdx.x) lo = mid; else hi = mid;
+    }
+    const uint32_t b = lo;
+    const uint32_t n = min(cursor[b], bucket_cap[b]);
+    const uint64_t start = (uint64_t)(blockIdx.x - chunk_first[b]) * chunk_items;
+    if (start >= n) return;
+    const uint32_t cnt = (uint32_t)min((uint64_t)chunk_items, n - start);
+    const uint32_t* src = items + bucket_off[b] + start;
+    uint32_t* region = bits + (((uint64_t)b << region_shift) >> 5);
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint32_t x = __ldg(&src[i]);
+        atomicOr(&region[x >> 5], 1u << (x & 31));
+    }
+}
+
+}  // namespace nts
