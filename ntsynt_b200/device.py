@@ -209,6 +209,19 @@ class MinimizerTable:
     def __init__(self, ctx, handle, genome):
         self.ctx, self._h, self.genome = ctx, handle, genome
 
+    @classmethod
+    def from_numpy(cls, ctx, h1, pos, contig, genome=None):
+        "device table from host arrays in (contig, position) order (bin/ntsynt_run.py reads indexlr TSVs)"
+        h1 = np.ascontiguousarray(h1, dtype=np.uint64)
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        contig = np.ascontiguousarray(contig, dtype=np.uint32)
+        h = C.c_void_p()
+        n = len(h1)
+        z64, z32 = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint32)
+        check(lib.nts_mxs_upload(ctx._h, n, ptr(h1 if n else z64, C.c_uint64), ptr(pos if n else z32, C.c_uint32),
+                                 ptr(contig if n else z32, C.c_uint32), C.byref(h)))
+        return cls(ctx, h, genome)
+
     def __len__(self):
         return int(lib.nts_mxs_count(self._h))
 

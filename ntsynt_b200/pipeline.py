@@ -53,17 +53,20 @@ def build_common_bf(ctx, genomes, paths, k, fpr=0.025, nbytes=None, log=None):
 class CudaBackend:
     "SyntenyEngine backend on the CUDA library (the only backend the package ships)"
 
-    def __init__(self, ctx, genomes, names, contig_names, contig_lengths, k, common=None, repeat=None):
+    def __init__(self, ctx, genomes, names, contig_names, contig_lengths, k, common=None, repeat=None, round0=None):
         self.ctx, self.genomes = ctx, genomes
         self.names = list(names)
         self.contig_names = contig_names
         self.contig_lengths = contig_lengths
         self.k = k
         self.common, self.repeat = common, repeat
-        self.tables = {}          # round-0 device tables, consumed by join()
+        self.round0 = round0      # optional pre-made round-0 tables (bin/ntsynt_run.py: sketches read from TSVs)
+        self.graph = None
         self.timing = {"sketch_ms": 0.0, "join_ms": 0.0}
 
     def sketch(self, a, w, masks):
+        if masks is None and self.round0 is not None:
+            return self.round0[a]
         t0 = time.perf_counter()
         mx = self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, repeat=None, masks=masks)
         self.timing["sketch_ms"] += (time.perf_counter() - t0) * 1e3
@@ -87,6 +90,10 @@ class CudaBackend:
     def lookup(self, keys):
         return self.graph.lookup(keys)
 
+    def write_dot(self, path, j):
+        from . import io
+        io.write_mx_dot(path, self.names, self.contig_names, j["H"], j["POS"], j["CTG"], self.graph.edges())
+
     def close(self):
         if getattr(self, "graph", None) is not None:
             self.graph.close()
@@ -95,7 +102,7 @@ class CudaBackend:
 
 def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="10000", block_size=500, fpr=0.025,
                prefix="ntSynt", simplify=True, common=True, device_index=0, write_files=True, quiet=True,
-               packed=None, ctx=None):
+               packed=None, ctx=None, intermediates=False):
     """The whole path for `fastas` (paths; .gz accepted).  Returns (final_tsv_text, engine).
     `packed`: optional pre-parsed fasta.PackedGenome list (same order as `fastas`)."""
     own_ctx = ctx is None
@@ -112,6 +119,20 @@ def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="100
                      common=bf)
     eng = SyntenyEngine(be, k, w, list(w_rounds), indel, merge, block_size, simplify=simplify, prefix=prefix,
                         write_files=write_files, quiet=quiet)
+    if intermediates:
+        # the files the smk rules leave behind (smk:44-103): .fai, <prefix>.common.bf, sketch TSVs, .mx.dot
+        from . import io
+        for b, p in zip(bases, packed):
+            if p.fai:
+                fasta.write_fai(p, b + ".fai")
+        if bf is not None:
+            io.save_bf(f"{prefix}.common.bf", bf, k)
+        for b, p, g in zip(bases, packed, genomes):
+            t = ctx.sketch(g, k, w, common=bf)
+            with open(tsv_name(b, k, w), "w", encoding="utf-8") as fh:
+                io.write_sketch_tsv(fh, p, t.to_numpy(), k)
+            t.close()
+        eng.dot_path = f"{prefix}.mx.dot"
     out = eng.run()
     eng.backend_timing = be.timing
     be.close()

@@ -935,6 +935,9 @@ class SyntenyEngine:
         j = self.be.join(tables, self.orient)
         link, degree = j["link"], j["degree"]
         self.stats["vertices"] = int(len(j["H"]))
+        if getattr(self, "dot_path", None):
+            self.log("Printing graph", self.dot_path)
+            self.be.write_dot(self.dot_path, j)
         self._init_vertices(j)
         self._edge_birth = {}
         V = self.V0

@@ -167,11 +167,13 @@ def minimize(seq: bytes, k, w, common=None, repeat=None, restart_on_gap=False):
 
 
 def sketch_tsv_lines(records, k, w, common=None, repeat=None, with_seq=True):
-    "indexlr --long --pos [--seq] output, one text line per record (SURVEY A.4)."
+    """indexlr --long --pos [--seq] output, one text line per record.  The :seq field is printed
+    upper case: btllib's SeqReader folds case by default [RECALL; unpinned -- the demo FASTAs hold no lower
+    case, and the graph stage ignores the field unless --filter Filter is used]."""
     for name, seq in records:
         h1, pos = minimize(seq, k, w, common, repeat)
         if with_seq:
-            toks = [f"{int(h)}:{int(p)}:{seq[int(p):int(p) + k].decode()}" for h, p in zip(h1, pos)]
+            toks = [f"{int(h)}:{int(p)}:{seq[int(p):int(p) + k].decode().upper()}" for h, p in zip(h1, pos)]
         else:
             toks = [f"{int(h)}:{int(p)}" for h, p in zip(h1, pos)]
         yield name + "\t" + " ".join(toks) + "\n"

@@ -1,0 +1,94 @@
+"""Drop-in executables under bin/ (SURVEY.md 8b), run as subprocesses on the GPU box with the reference's
+own command lines (bin/ntsynt_run_pipeline.smk:55-103, ntjoin_utils.py:197-198)."""
+import gzip
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+from conftest import MINI, mini_expected, mini_fastas
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bin")
+pytestmark = pytest.mark.gpu
+
+
+def run(cmd, cwd):
+    res = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:]
+    return res.stdout
+
+
+def stage(tmp_path, tag):
+    names = []
+    for p in mini_fastas(tag):
+        n = os.path.basename(p)[:-3]
+        with gzip.open(p, "rb") as fi, open(tmp_path / n, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+        names.append(n)
+    return names
+
+
+def test_smk_rule_commands_reproduce_the_fixture(tmp_path, mini_params):
+    "make_common_bf -> indexlr (both spellings) -> ntsynt_run.py, exactly as the smk rules spell them"
+    p = mini_params
+    names = stage(tmp_path, "ABC")
+    k, w = p["k"], p["w"]
+    out = run([sys.executable, os.path.join(BIN, "ntsynt_make_common_bf"), "--genome", *names, "-p", "mini.common", "--fpr",
+               str(p["fpr"]), "-k", str(k), "-t", "4"], tmp_path)
+    assert "BF size (bytes):" in out and "Final Bloom filter FPR:" in out
+    for i, n in enumerate(names):
+        tsv = f"{n}.k{k}.w{w}.tsv"
+        if i == 0:      # smk spelling, stdout redirect
+            txt = run([sys.executable, os.path.join(BIN, "indexlr"), "-k", str(k), "-w", str(w), "--long", "--seq", "--pos",
+                       "-t", "5", "-s", "mini.common.bf", n], tmp_path)
+            (tmp_path / tsv).write_text(txt)
+        else:           # ntjoin_utils.run_indexlr spelling
+            run([sys.executable, os.path.join(BIN, "indexlr"), n, "--seq", "--long", "--pos", f"-k{k}", f"-w{w}", "-t4",
+                 "-s", "mini.common.bf", "-o", tsv], tmp_path)
+        assert (tmp_path / tsv).read_text() == mini_expected("ABC", tsv + ".gz")
+    run([sys.executable, os.path.join(BIN, "ntsynt_run.py"), *[f"{n}.k{k}.w{w}.tsv" for n in names], "-k", str(k), "-w", str(w),
+         "--w-rounds", *map(str, p["w_rounds"]), "-p", "mini-ABC", "--bp", str(p["indel"]), "--collinear-merge", p["merge"],
+         "-z", str(p["block_size"]), "--common", "mini.common.bf", "--simplify-graph", "--btllib_t", "4", "--fastas", *names],
+        tmp_path)
+    assert (tmp_path / "mini-ABC.synteny_blocks.tsv").read_text() == mini_expected("ABC", "synteny_blocks.tsv")
+    assert (tmp_path / "mini-ABC.pre-collinear-merge.synteny_blocks.tsv").read_text() == \
+        mini_expected("ABC", "pre-collinear-merge.synteny_blocks.tsv")
+    for n in names:
+        assert (tmp_path / (n + ".fai")).read_text() == open(os.path.join(MINI, "ABC", n + ".fai")).read()
+    # .mx.dot: same edge multiset as the reference's round-0 graph
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import dot_edges
+    with gzip.open(os.path.join(MINI, "ABC", "mx_dot_edges.json.gz"), "rt") as fh:
+        assert dot_edges(str(tmp_path / "mini-ABC.mx.dot")) == json.load(fh)
+
+
+def test_ntsynt_cli_end_to_end(tmp_path, mini_params):
+    "bin/ntSynt with explicit parameters (tests/ntsynt_tests.py:8-23 style) + --dev intermediates"
+    p = mini_params
+    names = stage(tmp_path, "AB")
+    run([sys.executable, os.path.join(BIN, "ntSynt"), "--force", *names, f"-k{p['k']}", "-w", str(p["w"]), "-d", "0.5",
+         "--prefix", "mini-AB", "--indel", str(p["indel"]), "--merge", p["merge"], "--block_size", str(p["block_size"]),
+         "--w_rounds", *map(str, p["w_rounds"]), "--dev"], tmp_path)
+    assert (tmp_path / "mini-AB.synteny_blocks.tsv").read_text() == mini_expected("AB", "synteny_blocks.tsv")
+    tsv = f"{names[0]}.k{p['k']}.w{p['w']}.tsv"
+    assert (tmp_path / tsv).read_text() == mini_expected("AB", tsv + ".gz")
+    assert (tmp_path / "mini-AB.common.bf").exists() and (tmp_path / "mini-AB.mx.dot").exists()
+    # fastas_list spelling
+    (tmp_path / "list.tsv").write_text("\n".join(names) + "\n")
+    run([sys.executable, os.path.join(BIN, "ntSynt"), "--fastas_list", "list.tsv", f"-k{p['k']}", "-w", str(p["w"]), "-d", "0.5",
+         "--prefix", "mini-fof", "--indel", str(p["indel"]), "--merge", p["merge"], "--block_size", str(p["block_size"]),
+         "--w_rounds", *map(str, p["w_rounds"])], tmp_path)
+    assert (tmp_path / "mini-fof.synteny_blocks.tsv").read_text() == mini_expected("AB", "synteny_blocks.tsv")
+
+
+def test_cli_argument_errors(tmp_path):
+    res = subprocess.run([sys.executable, os.path.join(BIN, "ntSynt"), "a.fa", "-d", "1"], cwd=tmp_path, stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 2 and "at least two" in res.stdout
+    res = subprocess.run([sys.executable, os.path.join(BIN, "ntsynt_make_common_bf"), "--genome", "x.fa"], cwd=tmp_path,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 1
