@@ -210,6 +210,9 @@ int nts_graph_download_vertices(nts_graph* g, uint64_t* h1, uint32_t* pos, uint3
  * position increases / decreases from vertex i to i+1 (orientation rule, bin/synteny_block.py:48-65);
  * spread[V] = max_a |dpos| - min_a |dpos| (indel test, bin/ntsynt_synteny.py:364-368,399). */
 int nts_graph_download_links(nts_graph* g, uint32_t* inv, uint32_t* incmask, uint32_t* decmask, uint32_t* spread);
+/* prefix sums of the direction bits (device scans): ci, cd are [n_asm*(V+1)], assembly-major;
+ * ci[a*(V+1)+i] = number of pairs (j, j+1), j < i, whose position increases in assembly a (cd: decreases) */
+int nts_graph_download_cums(nts_graph* g, uint32_t* ci, uint32_t* cd);
 /* vertex id of each h1 (0xFFFFFFFF if none) via the join table kept on the device
  * (replaces `mx in mx_info` / graph.vs.find(name) lookups of the refinement rounds) */
 int nts_graph_lookup(nts_graph* g, const uint64_t* h1, uint64_t n, uint32_t* vid_out);

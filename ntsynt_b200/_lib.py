@@ -99,6 +99,7 @@ _SIGS = {
     "nts_graph_vertices": (C.c_uint64, [vp]),
     "nts_graph_download_vertices": (C.c_int, [vp, u64p, u32p, u32p, u32p, u8p, u8p]),
     "nts_graph_download_links": (C.c_int, [vp, u32p, u32p, u32p, u32p]),
+    "nts_graph_download_cums": (C.c_int, [vp, u32p, u32p]),
     "nts_graph_lookup": (C.c_int, [vp, u64p, C.c_uint64, u32p]),
     "nts_graph_edges": (C.c_int, [vp, u64p]),
     "nts_graph_download_edges": (C.c_int, [vp, u32p, u32p, u32p]),

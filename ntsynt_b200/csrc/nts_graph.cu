@@ -262,6 +262,12 @@ __global__ void graph_edge_emit_kernel(const uint32_t* __restrict__ v_ctg, const
     e_u[o] = u; e_v[o] = v; e_support[o] = sup;
 }
 
+__global__ void extract_bit_kernel(const uint32_t* __restrict__ mask, uint64_t n, uint32_t bit, uint32_t* __restrict__ out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (mask[i] >> bit) & 1u;
+}
+
 static int exclusive_scan_u32(nts_ctx* ctx, const uint32_t* in, uint64_t n, uint32_t* out, uint32_t* total_host)
 {
     const uint64_t per_block = (uint64_t)SCAN_THREADS * SCAN_ITEMS;
@@ -452,6 +458,33 @@ int nts_graph_lookup(nts_graph* g, const uint64_t* h1, uint64_t n, uint32_t* vid
     NTS_CUDA(cudaGetLastError());
     NTS_CUDA(copy_d2h(ctx, vid_out, d_o.p, n * 4));
     NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+/* prefix sums of the direction bits: ci/cd are [n_asm * (V+1)], assembly-major; ci[a*(V+1) + i] = number of
+ * pairs (j, j+1) with j < i whose position increases in assembly a (cd: decreases) */
+int nts_graph_download_cums(nts_graph* g, uint32_t* ci, uint32_t* cd)
+{
+    if (!g || !ci || !cd) return fail(NTS_ERR_ARG, "null argument");
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t V = g->V;
+    if (!V) return NTS_OK;
+    DevBuf<uint32_t> flags, sums;
+    if (flags.alloc(V) != cudaSuccess || sums.alloc(V) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (cums)");
+    ProfScope prof(ctx, PROF_JOIN, (double)V * g->n_asm * 2);
+    for (uint32_t a = 0; a < g->n_asm; ++a)
+        for (int which = 0; which < 2; ++which) {
+            extract_bit_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(which ? g->decmask.p : g->incmask.p, V, a, flags.p);
+            ctx->launches++;
+            uint32_t total = 0;
+            int rc = exclusive_scan_u32(ctx, flags.p, V, sums.p, &total);
+            if (rc) return rc;
+            uint32_t* dst = (which ? cd : ci) + (uint64_t)a * (V + 1);
+            NTS_CUDA(copy_d2h(ctx, dst, sums.p, V * 4));
+            NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+            dst[V] = total;
+        }
     return NTS_OK;
 }
 

@@ -298,12 +298,22 @@ class MinimizerGraph:
             check(lib.nts_graph_lookup(self._h, ptr(keys, C.c_uint64), len(keys), ptr(out, C.c_uint32)))
         return out[:len(keys)]
 
+    def cums(self):
+        "CI, CD int32 [G, V+1]: device prefix sums of the per-pair direction bits"
+        V, G = len(self), self.n_asm
+        ci = np.zeros((G, V + 1), dtype=np.uint32)
+        cd = np.zeros((G, V + 1), dtype=np.uint32)
+        if V:
+            check(lib.nts_graph_download_cums(self._h, ptr(ci, C.c_uint32), ptr(cd, C.c_uint32)))
+        return ci.view(np.int32), cd.view(np.int32)
+
     def join_result(self):
         "everything SyntenyEngine needs from the join, as a dict"
         H, POS, CTG, RANK, link, deg = self.vertices()
         INV, inc, dec, spread = self.links()
+        CI, CD = self.cums()
         return dict(H=H, POS=POS, CTG=CTG, RANK=RANK, INV=INV, link=link, degree=deg, incmask=inc, decmask=dec,
-                    spread=spread)
+                    spread=spread, CI=CI, CD=CD)
 
     def edges(self):
         "(u, v, support) of the distinct adjacency edges in build_graph's first-insertion order"

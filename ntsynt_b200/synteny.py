@@ -165,6 +165,10 @@ class SyntenyEngine:
         self.decmask = np.array(j["decmask"], dtype=np.uint32)
         self.spread = np.array(j["spread"], dtype=np.int64)
         self._cum_dirty = True
+        if "CI" in j:                                   # device prefix sums (nts_graph_download_cums)
+            self.CI, self.CD = j["CI"], j["CD"]
+            self.big = np.flatnonzero(self.spread > self.bp)
+            self._cum_dirty = False
 
     def _cums(self):
         "prefix sums (per assembly) of the direction bits of the pairs (i, i+1); CI[a, i] = sum over pairs < i"
@@ -401,12 +405,15 @@ class SyntenyEngine:
             def degree(v):
                 return int((self.nbr[v] >= 0).sum())
             seen_runs = set()
-            cand_ends = []
-            for v in sorted(real_sparse):
-                a, b = run_bounds(v)
-                for x in {a, b}:
-                    if degree(x) == 1:
-                        cand_ends.append(x)
+            sv = np.array(sorted(real_sparse), dtype=np.int64)
+            ra, rb = sv.copy(), sv.copy()
+            bm = sv < V0
+            if bm.any():
+                ri = np.searchsorted(starts, sv[bm], side="right") - 1
+                ra[bm], rb[bm] = starts[ri], ends[ri]
+            ends_all = np.unique(np.concatenate([ra, rb]))
+            deg_all = (self.nbr[ends_all] >= 0).sum(axis=1)
+            cand_ends = ends_all[deg_all == 1].tolist()
             for e0 in cand_ends:
                 if run_bounds(e0)[0] in seen_runs:
                     continue
@@ -455,7 +462,42 @@ class SyntenyEngine:
         G = self.G
         CI, CD = self._cums()
         blocks, to_remove = [], []
+        single = [p[0] for p in paths if len(p) == 1]
+        if single:
+            lo = np.array([sg[0] for sg in single], dtype=np.int64)
+            hi = np.array([sg[1] for sg in single], dtype=np.int64)
+            up_dir = np.array([sg[2] > 0 for sg in single])
+            n_all = hi - lo + 1
+            up = (CI[:, hi] - CI[:, lo]).astype(np.int64)
+            down = (CD[:, hi] - CD[:, lo]).astype(np.int64)
+            inc_all = np.where(up_dir[None, :], up, down)
+            dec_all = np.where(up_dir[None, :], down, up)
+            first = np.where(up_dir, lo, hi)
+            last = np.where(up_dir, hi, lo)
+            ctg_f, pos_f, pos_l = self.CTG[:, first], self.POS[:, first], self.POS[:, last]
+            plus = (inc_all == n_all - 1) | (n_all == 1)
+            minus = ~plus & (dec_all == n_all - 1)
+            ambiguous = ~(plus | minus)
+            for x, sg in enumerate(single):
+                n = int(n_all[x])
+                ori = []
+                for a in range(G):
+                    if plus[a, x]:
+                        ori.append("+")
+                    elif minus[a, x]:
+                        ori.append("-")
+                    else:
+                        positive = int(inc_all[a, x]) / float(n - 1) * 100
+                        negative = 100 - positive
+                        ori.append("+" if positive >= self.m else ("-" if negative >= self.m else "?"))
+                if "?" in ori:
+                    to_remove.append(sg)
+                    continue
+                blocks.append(Block([sg], ctg_f[:, x].copy(), ori, int(first[x]), int(last[x]), pos_f[:, x].copy(),
+                                    pos_l[:, x].copy(), n))
         for segs in paths:
+            if len(segs) == 1:
+                continue
             # contig change can only happen at a junction between segments: keep the LAST run of constant
             # contigs (past_start_flag is never set, ntsynt_synteny.py:71,77)
             start_seg = 0
@@ -503,7 +545,20 @@ class SyntenyEngine:
         big = self.big
         out = []
         rm_u, rm_v = [], []
-        for b in blocks:
+        # single-segment blocks without a large-spread pair inside need no work (vectorised pre-check)
+        one = [x for x, b in enumerate(blocks) if len(b.segs) == 1]
+        clean = set()
+        if one and len(big):
+            lo = np.array([blocks[x].segs[0][0] for x in one], dtype=np.int64)
+            hi = np.array([blocks[x].segs[0][1] for x in one], dtype=np.int64)
+            none = np.searchsorted(big, lo) == np.searchsorted(big, hi)
+            clean = set(x for x, ok in zip(one, none.tolist()) if ok)
+        elif one:
+            clean = set(one)
+        for bx, b in enumerate(blocks):
+            if bx in clean:
+                out.append(b)
+                continue
             # break points as (segment index, id of the vertex BEFORE the break in traversal order)
             pieces, cur = [], []
             any_break = False
