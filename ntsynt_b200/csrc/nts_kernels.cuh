@@ -265,12 +265,14 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     const uint32_t o0 = w + threadIdx.x * per, o1 = min(o0 + per, n_end);
     uint32_t cnt = 0;
     // window ending at slot i covers [i-w+1, i]
-    auto win_min = [&](uint32_t i) -> uint32_t {
+    // `whole` = the window is exactly one block, i.e. (i + 1) % w == 0 (tracked incrementally by the callers)
+    auto win_min = [&](uint32_t i, bool whole) -> uint32_t {
         uint32_t p = s_P[i];
-        if ((i + 1) % w == 0) return p;                 // the window is exactly one block
+        if (whole) return p;
         uint32_t s = s_S[i + 1 - w];
         return (s_key[p] <= s_key[s]) ? p : s;          // p lies to the right: wins ties
     };
+    const uint32_t o0_rem = (o0 < o1) ? o0 % w : 0;     // o0 % w, the only modulo of phase C
     const bool filtered = (common != nullptr || repeat != nullptr);
     for (int pass = 0; pass < 2; ++pass) {
     const uint64_t tau_cur = (pass == 0 && filtered) ? tau : KEY_MAX;
@@ -285,7 +287,45 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     __syncthreads();
 
     // ---- phase A2: Bloom query (kernel iii-c), 8 independent sector loads in flight per thread
-    if (filtered) {
+    if (filtered && tau_cur != KEY_MAX) {
+        // pruned pass: only slots below tau are looked up (a few per cent); the rest become UINT64_MAX.
+        // A thread first gathers up to 4 of its low slots, then issues their sector loads together, so the
+        // warp pays one memory latency instead of one per slot.
+        uint32_t li[4];
+        uint64_t lx[4];
+        uint32_t nl = 0;
+        auto probe = [&](uint64_t idx) -> bool {
+            bool keep = true;
+            if (common) keep = (__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u;
+            if (keep && repeat) keep = !((__ldg(&repeat[idx >> 5]) >> (idx & 31)) & 1u);
+            return keep;
+        };
+        for (uint32_t i = max(c0, i_lo); i < min(c0 + C, n_end); ++i) {
+            const uint64_t h = s_key[i];
+            if (h >= tau_cur) { s_key[i] = KEY_MAX; continue; }
+            const uint64_t idx = fast_mod(h, m, mprime);
+            if (nl < 4) {
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) if (u == nl) { li[u] = i; lx[u] = idx; }
+                ++nl;
+            } else if (!probe(idx)) {
+                s_key[i] = KEY_MAX;
+            }
+        }
+        uint32_t cwv[4], rwv[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+            cwv[u] = 0xFFFFFFFFu; rwv[u] = 0;
+            if (u < nl) {
+                if (common) cwv[u] = __ldg(&common[lx[u] >> 5]) >> (lx[u] & 31);
+                if (repeat) rwv[u] = __ldg(&repeat[lx[u] >> 5]) >> (lx[u] & 31);
+            }
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u)
+            if (u < nl && (!(cwv[u] & 1u) || (rwv[u] & 1u))) s_key[li[u]] = KEY_MAX;
+        __syncthreads();
+    } else if (filtered) {
         for (uint32_t i0 = threadIdx.x; i0 < n_end; i0 += THREADS * 8) {
             uint64_t h[8];
             uint32_t cw[8], rw[8];
@@ -295,8 +335,7 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
                 h[u] = (i < n_end) ? s_key[i] : 0;
                 uint64_t idx = fast_mod(h[u], m, mprime);
                 cw[u] = 0xFFFFFFFFu; rw[u] = 0;
-                if (i < n_end && i >= i_lo && h[u] >= tau_cur) cw[u] = 0;          // pruned: not queried
-                else if (i < n_end && i >= i_lo) {
+                if (i < n_end && i >= i_lo) {
                     if (common) cw[u] = __ldg(&common[idx >> 5]) >> (idx & 31);
                     if (repeat) rw[u] = __ldg(&repeat[idx >> 5]) >> (idx & 31);
                 }
@@ -315,9 +354,12 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     {
         KeyIdx run; run.key = KEY_MAX; run.idx = 0xFFFFFFFFu;
         uint32_t closed = 0;
+        uint32_t rem = hi % w;                       // (i + 1) % w for i = hi - 1, then counted down
         for (uint32_t i = hi; i-- > c0;) {          // local right-to-left pass
             KeyIdx cur; cur.key = s_key[i]; cur.idx = i;
-            if ((i + 1) % w == 0) { closed = 1; run = cur; }          // i is the last slot of its block
+            const bool last_of_block = rem == 0;
+            rem = rem == 0 ? w - 1 : rem - 1;
+            if (last_of_block) { closed = 1; run = cur; }             // i is the last slot of its block
             else if (run.idx == 0xFFFFFFFFu) run = cur;
             else if (cur.key < run.key) run = cur;                    // run lies to the right: wins ties
             s_S[i] = (uint16_t)run.idx;
@@ -329,8 +371,10 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
         // the carry (arg-min of what lies to the right, up to the block end) reaches the slots after the
         // last block end inside this chunk
         if (c0 < hi && (carry.flag & SEG_VALID)) {
+            uint32_t rem2 = hi % w;
             for (uint32_t i = hi; i-- > c0;) {
-                if ((i + 1) % w == 0) break;
+                if (rem2 == 0) break;
+                --rem2;
                 if (carry.key <= s_key[s_S[i]]) s_S[i] = (uint16_t)carry.idx;   // carry is to the right: wins ties
             }
         }
@@ -339,9 +383,12 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     {
         KeyIdx run; run.key = KEY_MAX; run.idx = 0xFFFFFFFFu;
         uint32_t closed = 0;
+        uint32_t rem = c0 % w;                       // i % w, counted up
         for (uint32_t i = c0; i < hi; ++i) {        // local left-to-right pass
             KeyIdx cur; cur.key = s_key[i]; cur.idx = i;
-            if (i % w == 0) { closed = 1; run = cur; }                // i is the first slot of its block
+            const bool first_of_block = rem == 0;
+            rem = rem + 1 == w ? 0 : rem + 1;
+            if (first_of_block) { closed = 1; run = cur; }            // i is the first slot of its block
             else if (run.idx == 0xFFFFFFFFu) run = cur;
             else if (cur.key <= run.key) run = cur;                   // cur lies to the right: wins ties
             s_P[i] = (uint16_t)run.idx;
@@ -351,8 +398,10 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
         if (c0 < hi) { own.idx = s_P[hi - 1]; own.key = s_key[own.idx]; own.flag = SEG_VALID | (closed ? SEG_CLOSED : 0u); }
         SegAgg carry = cta_exclusive_carry<THREADS, true>(own, s_warp);
         if (c0 < hi && (carry.flag & SEG_VALID)) {
+            uint32_t rem2 = c0 % w;
             for (uint32_t i = c0; i < hi; ++i) {
-                if (i % w == 0) break;
+                if (rem2 == 0) break;
+                rem2 = rem2 + 1 == w ? 0 : rem2 + 1;
                 if (carry.key < s_key[s_P[i]]) s_P[i] = (uint16_t)carry.idx;    // carry is to the left: loses ties
             }
         }
@@ -364,11 +413,13 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     cnt = 0;
     int unresolved = 0;
     if (o0 < o1) {
-        uint32_t prev = (o0 == w && !td.has_prev) ? 0xFFFFFFFFu : win_min(o0 - 1);
+        uint32_t prev = (o0 == w && !td.has_prev) ? 0xFFFFFFFFu : win_min(o0 - 1, o0_rem == 0);
         // the window before the tile's first owned one decides whether that one is "new": it must be resolved too
         if (o0 == w && td.has_prev && s_key[prev] == KEY_MAX) unresolved = 1;
+        uint32_t r1 = o0_rem + 1 == w ? 0 : o0_rem + 1;          // (i + 1) % w
         for (uint32_t i = o0; i < o1; ++i) {
-            uint32_t a = win_min(i);
+            uint32_t a = win_min(i, r1 == 0);
+            r1 = r1 + 1 == w ? 0 : r1 + 1;
             if (s_key[a] == KEY_MAX) unresolved = 1;
             else if (a != prev) ++cnt;
             prev = a;
@@ -408,9 +459,11 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     if (tile_base == 0xFFFFFFFFu || cnt == 0) return;   // overflow: host re-runs with a larger buffer
     uint32_t off = tile_base + (incl - cnt) + (wid ? s_misc[wid - 1] : 0);
     {
-        uint32_t prev = (o0 == w && !td.has_prev) ? 0xFFFFFFFFu : win_min(o0 - 1);
+        uint32_t prev = (o0 == w && !td.has_prev) ? 0xFFFFFFFFu : win_min(o0 - 1, o0_rem == 0);
+        uint32_t r1 = o0_rem + 1 == w ? 0 : o0_rem + 1;
         for (uint32_t i = o0; i < o1; ++i) {
-            uint32_t a = win_min(i);
+            uint32_t a = win_min(i, r1 == 0);
+            r1 = r1 + 1 == w ? 0 : r1 + 1;
             if (a != prev && s_key[a] != KEY_MAX) {
                 uint64_t b = valid_to_base(g, vbase + a);
                 out.h1[off] = ext_hash(s_key[a], 1, g.k);
