@@ -246,19 +246,27 @@ def run_ours(args, dist):
     nbytes = device.BloomFilter.size_for(gens[size_sorted[0]].total_bases, 0.025)
     common, level = ctx.bloom(nbytes), ctx.bloom(nbytes)
 
+    phase = {}
+
     def hot_path(gen_list):
         # src/ntsynt_make_common_bf.cpp:107-160 on resident genomes, filters re-zeroed every step
+        t_hp = time.perf_counter()
         common.clear()
         common.insert_genome(gen_list[size_sorted[0]], K)
         for i in size_sorted[1:]:
             level.clear()
             level.insert_genome(gen_list[i], K)
             common.iand(level)
+        phase["bf_wall_ms"] = phase.get("bf_wall_ms", 0.0) + (time.perf_counter() - t_hp) * 1e3
         be = pipeline.CudaBackend(ctx, [gen_list[i] for i in order], [names[i] for i in order], [wl.names] * G,
                                   [[int(x) for x in gen_list[i].lengths] for i in order], K, common=common)
         eng = SyntenyEngine(be, K, W, ps["w_rounds"], ps["indel"], ps["merge"], ps["block_size"], write_files=False,
                             quiet=True)
         text = eng.run()
+        be.close()
+        phase["total_wall_ms"] = phase.get("total_wall_ms", 0.0) + (time.perf_counter() - t_hp) * 1e3
+        phase["calls"] = phase.get("calls", 0) + 1
+        phase.setdefault("each_ms", []).append(round((time.perf_counter() - t_hp) * 1e3, 1))
         return text, eng
 
     gen_list = [gens[g] for g in range(G)]
@@ -361,6 +369,8 @@ def run_ours(args, dist):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "host_wall_ms_per_step": wall * 1e3 / args.steps,
+        "graph_stage_phase_ms": {k[2:]: round(v * 1e3, 1) for k, v in eng.stats.items() if k.startswith("t_")},
+        "hot_path_wall_ms": {k: (v if k == "each_ms" else round(v / max(phase.get("calls", 1), 1), 1)) for k, v in phase.items() if k != "calls"},
     }
     if dist.rank == 0:
         print(json.dumps(line))

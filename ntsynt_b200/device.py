@@ -245,6 +245,27 @@ class MinimizerTable:
             pass
 
 
+class PinnedPool:
+    """page-locked host arrays reused across calls (D2H into pageable memory runs at a few GB/s; the join
+    hands ~400 MB of vertex columns to the host every step)"""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, key, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ent = cls._bufs.get(key)
+        if ent is None or ent[1] < n:
+            if ent is not None:
+                lib.nts_host_free(ent[0])
+            p = C.c_void_p()
+            check(lib.nts_host_alloc(max(n, 1) + 64, C.byref(p)))
+            ent = (p, n + 64)
+            cls._bufs[key] = ent
+        raw = (C.c_uint8 * max(n, 1)).from_address(ent[0].value)
+        return np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 class MinimizerGraph:
     """Device join of G minimizer tables (kernel iv): vertex table in the orienting assembly's
     list order, full-weight links and vertex degrees.  See nts_graph_build in the header."""
@@ -265,12 +286,12 @@ class MinimizerGraph:
         "h1[V] u64, pos[G,V] u32, contig[G,V] u32, rank[G,V] u32, link[V] u8, degree[V] u8"
         V, G = len(self), self.n_asm
         n = max(V, 1)
-        h1 = np.empty(n, dtype=np.uint64)
-        pos = np.empty((G, n), dtype=np.uint32)
-        ctg = np.empty((G, n), dtype=np.uint32)
-        rank = np.empty((G, n), dtype=np.uint32)
-        link = np.empty(n, dtype=np.uint8)
-        deg = np.empty(n, dtype=np.uint8)
+        h1 = PinnedPool.get("h1", (n,), np.uint64)
+        pos = PinnedPool.get("pos", (G, n), np.uint32)
+        ctg = PinnedPool.get("ctg", (G, n), np.uint32)
+        rank = PinnedPool.get("rank", (G, n), np.uint32)
+        link = PinnedPool.get("link", (n,), np.uint8)
+        deg = PinnedPool.get("deg", (n,), np.uint8)
         if V:
             check(lib.nts_graph_download_vertices(self._h, ptr(h1, C.c_uint64), ptr(pos, C.c_uint32),
                                                   ptr(ctg, C.c_uint32), ptr(rank, C.c_uint32), ptr(link, C.c_uint8),
@@ -281,10 +302,10 @@ class MinimizerGraph:
         "inv[G,V] u32, incmask[V], decmask[V], spread[V] u32: per-pair arrays of (i, i+1)"
         V, G = len(self), self.n_asm
         n = max(V, 1)
-        inv = np.empty((G, n), dtype=np.uint32)
-        inc = np.empty(n, dtype=np.uint32)
-        dec = np.empty(n, dtype=np.uint32)
-        spread = np.empty(n, dtype=np.uint32)
+        inv = PinnedPool.get("inv", (G, n), np.uint32)
+        inc = PinnedPool.get("inc", (n,), np.uint32)
+        dec = PinnedPool.get("dec", (n,), np.uint32)
+        spread = PinnedPool.get("spread", (n,), np.uint32)
         if V:
             check(lib.nts_graph_download_links(self._h, ptr(inv, C.c_uint32), ptr(inc, C.c_uint32), ptr(dec, C.c_uint32),
                                                ptr(spread, C.c_uint32)))
@@ -301,8 +322,9 @@ class MinimizerGraph:
     def cums(self):
         "CI, CD int32 [G, V+1]: device prefix sums of the per-pair direction bits"
         V, G = len(self), self.n_asm
-        ci = np.zeros((G, V + 1), dtype=np.uint32)
-        cd = np.zeros((G, V + 1), dtype=np.uint32)
+        ci = PinnedPool.get("ci", (G, V + 1), np.uint32)
+        cd = PinnedPool.get("cd", (G, V + 1), np.uint32)
+        ci[:, 0] = 0; cd[:, 0] = 0
         if V:
             check(lib.nts_graph_download_cums(self._h, ptr(ci, C.c_uint32), ptr(cd, C.c_uint32)))
         return ci.view(np.int32), cd.view(np.int32)

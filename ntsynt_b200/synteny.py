@@ -143,6 +143,15 @@ class SyntenyEngine:
         if not self.quiet:
             _log(*a)
 
+    def _tick(self, name):
+        "accumulate wall time since the previous tick under stats['t_<name>'] (cheap phase timer)"
+        import time
+        now = time.perf_counter()
+        last = getattr(self, "_tick_last", None)
+        if last is not None and name:
+            self.stats["t_" + name] = self.stats.get("t_" + name, 0.0) + (now - last)
+        self._tick_last = now
+
     # ------------------------------------------------------------------ vertex storage
     def _init_vertices(self, j):
         H = j["H"]
@@ -156,14 +165,15 @@ class SyntenyEngine:
         self.RANK, self.INV = j["RANK"], j["INV"]                    # round-0 vertices only (uint32)
         self._ctg0 = None                                            # copy-on-write snapshot of round-0 contigs
         self.alive = np.zeros(cap, dtype=bool); self.alive[:V] = True
-        self.nbr = np.full((cap, 2), -1, dtype=np.int64)
+        self.nbr = np.full((cap, 2), -1, dtype=np.int32)
         self.conn = np.zeros(max(V - 1, 0), dtype=bool)              # edge (i, i+1) present, base vertices
         self.sparse = set()                                          # vertices that may hold a non-(i,i+1) edge
         self._h_extra = {}
+        self._pair_orig, self._pair_delta = {}, {}      # corrections to the device prefix sums (see _refresh_pairs)
         # per-pair arrays of (i, i+1) and their prefix sums per assembly
-        self.incmask = np.array(j["incmask"], dtype=np.uint32)
-        self.decmask = np.array(j["decmask"], dtype=np.uint32)
-        self.spread = np.array(j["spread"], dtype=np.int64)
+        self.incmask = np.asarray(j["incmask"], dtype=np.uint32)
+        self.decmask = np.asarray(j["decmask"], dtype=np.uint32)
+        self.spread = np.asarray(j["spread"], dtype=np.uint32)
         self._cum_dirty = True
         if "CI" in j:                                   # device prefix sums (nts_graph_download_cums)
             self.CI, self.CD = j["CI"], j["CD"]
@@ -185,7 +195,8 @@ class SyntenyEngine:
 
     def _refresh_pairs(self, vids):
         """positions of base vertices were overwritten (update_list_mx_info): redo the values of their
-        (i, i+1) pairs and patch the prefix sums in place (a suffix add per changed pair)"""
+        (i, i+1) pairs.  The device prefix sums stay as they are; the few changed pairs are kept as
+        corrections (pair index -> per-assembly delta) that _range_sums adds for the ranges containing them."""
         if self._cum_dirty:
             self._cums()
         for v in vids:
@@ -196,16 +207,14 @@ class SyntenyEngine:
                     for a in range(self.G):
                         inc |= (1 << a) if d[a] > 0 else 0
                         dec |= (1 << a) if d[a] < 0 else 0
-                    old_i, old_d = int(self.incmask[i]), int(self.decmask[i])
-                    if inc != old_i or dec != old_d:
-                        for a in range(self.G):
-                            di = ((inc >> a) & 1) - ((old_i >> a) & 1)
-                            dd = ((dec >> a) & 1) - ((old_d >> a) & 1)
-                            if di:
-                                self.CI[a, i + 1:] += di
-                            if dd:
-                                self.CD[a, i + 1:] += dd
-                        self.incmask[i], self.decmask[i] = inc, dec
+                    old_i, old_d = self._pair_orig.setdefault(i, (int(self.incmask[i]), int(self.decmask[i])))
+                    di = np.array([((inc >> a) & 1) - ((old_i >> a) & 1) for a in range(self.G)], dtype=np.int64)
+                    dd = np.array([((dec >> a) & 1) - ((old_d >> a) & 1) for a in range(self.G)], dtype=np.int64)
+                    if di.any() or dd.any():
+                        self._pair_delta[i] = (di, dd)
+                    else:
+                        self._pair_delta.pop(i, None)
+                    self.incmask[i], self.decmask[i] = inc, dec
                     ad = np.abs(d)
                     sp = int(ad.max() - ad.min())
                     if (sp > self.bp) != (self.spread[i] > self.bp):
@@ -213,7 +222,19 @@ class SyntenyEngine:
                             self.big = np.insert(self.big, np.searchsorted(self.big, i), i)
                         else:
                             self.big = np.delete(self.big, np.searchsorted(self.big, i))
-                    self.spread[i] = sp
+                    self.spread[i] = min(sp, 0xFFFFFFFF)
+
+    def _range_sums(self, lo, hi):
+        "per-assembly counts of increasing / decreasing pairs (i, i+1) with lo <= i < hi, for arrays lo, hi"
+        CI, CD = self._cums()
+        up = (CI[:, hi] - CI[:, lo]).astype(np.int64)
+        down = (CD[:, hi] - CD[:, lo]).astype(np.int64)
+        for i, (di, dd) in self._pair_delta.items():
+            hit = (lo <= i) & (i < hi)
+            if hit.any():
+                up[:, hit] += di[:, None]
+                down[:, hit] += dd[:, None]
+        return up, down
 
     def _ctg_round0(self, a, v):
         return (self.CTG if self._ctg0 is None else self._ctg0)[a, v]
@@ -227,7 +248,7 @@ class SyntenyEngine:
         self.POS = np.concatenate([self.POS, np.zeros((self.G, new - cap), dtype=np.int64)], axis=1)
         self.CTG = np.concatenate([self.CTG, np.zeros((self.G, new - cap), dtype=np.int32)], axis=1)
         self.alive = np.concatenate([self.alive, np.zeros(new - cap, dtype=bool)])
-        self.nbr = np.concatenate([self.nbr, np.full((new - cap, 2), -1, dtype=np.int64)])
+        self.nbr = np.concatenate([self.nbr, np.full((new - cap, 2), -1, dtype=np.int32)])
 
     def _lookup(self, keys):
         "vertex id per h1 (or -1) for a uint64 array: device join table, then the later additions"
@@ -329,38 +350,74 @@ class SyntenyEngine:
 
     # ------------------------------------------------------------------ simplification (ntsynt_synteny.py:566-590)
     def _simplify_round0(self, link, degree):
-        G = self.G
-        cand_v = np.nonzero(degree == 3)[0]
-        bumped = {}
-        removed = []
-        if len(cand_v):
-            cset = set(int(x) for x in cand_v)
-            nb_cache = {}
+        """run_graph_simplification on the round-0 graph.  Only vertices of degree 3 can take part; their
+        neighbourhoods are pulled out of the rank arrays in one vectorised step, the (few thousand) candidate
+        edges are then visited in build_graph's edge order with plain Python containers."""
+        G, V0 = self.G, self.V0
+        cand = np.flatnonzero(np.asarray(degree) == 3)
+        bumped, removed = {}, []
+        if not len(cand):
+            return bumped, removed
+        ctg0 = self.CTG if self._ctg0 is None else self._ctg0
+        left, right, ranks = [], [], []
+        for a in range(G):
+            r = self.RANK[a, cand].astype(np.int64)
+            lf = np.full(len(cand), -1, dtype=np.int64)
+            rt = np.full(len(cand), -1, dtype=np.int64)
+            ok = r > 0
+            x = self.INV[a, r[ok] - 1].astype(np.int64)
+            lf[ok] = np.where(ctg0[a, x] == ctg0[a, cand[ok]], x, -1)
+            ok = r + 1 < V0
+            x = self.INV[a, r[ok] + 1].astype(np.int64)
+            rt[ok] = np.where(ctg0[a, x] == ctg0[a, cand[ok]], x, -1)
+            left.append(lf.tolist()); right.append(rt.tolist()); ranks.append(r.tolist())
+        cl = cand.tolist()
+        pos_of = {u: i for i, u in enumerate(cl)}
+        nb = {}                                   # u -> {x: number of supporting assemblies}
+        for i, u in enumerate(cl):
+            d = {}
+            for a in range(G):
+                for x in (left[a][i], right[a][i]):
+                    if x >= 0:
+                        d[x] = d.get(x, 0) + 1
+            nb[u] = d
 
-            def nbrs(u):
-                if u not in nb_cache:
-                    nb_cache[u] = self._neighbors0(u)
-                return nb_cache[u]
+        def adjacent(a, src_i, dst):
+            return left[a][src_i] == dst or right[a][src_i] == dst
 
-            edges = set()
-            for u in cset:
-                for x in nbrs(u):
-                    if x in cset:
-                        edges.add((min(u, x), max(u, x)))
-            order = sorted(edges, key=lambda e: self._edge_key0(*e))
+        def edge_key(u, v):                       # ntjoin_utils.py:97-115, see _edge_key0
+            iu = pos_of[u]
+            a0 = next(a for a in range(G) if adjacent(a, iu, v))
+            ru, rv = ranks[a0][iu], ranks[a0][pos_of[v]]
+            src, isrc = (u, iu) if ru < rv else (v, pos_of[v])
+            tau = (a0, min(ru, rv))
+            sigma = None
+            for a in range(G):
+                x = right[a][isrc]
+                if x >= 0 and not any(adjacent(b, isrc, x) for b in range(a)):
+                    sigma = (a, ranks[a][isrc])
+                    break
+            return (0, sigma, tau)
 
-            def weight(u, x):
-                return bumped.get((min(u, x), max(u, x)), nbrs(u)[x])
+        edges = set()
+        for u in cl:
+            for x in nb[u]:
+                if x in pos_of:
+                    edges.add((u, x) if u < x else (x, u))
+        order = sorted(edges, key=lambda e: edge_key(*e))
 
-            def anchored(u):
-                return sum(1 for x in nbrs(u) if weight(u, x) == G) == 1
+        def weight(u, x):
+            return bumped.get((u, x) if u < x else (x, u), nb[u][x])
 
-            for s, t in order:
-                if anchored(s) and anchored(t):
-                    common = [x for x in nbrs(s) if x != t and x in nbrs(t)]
-                    if len(common) == 1:            # the edge itself + exactly one 2-step path
-                        removed.append(common[0])
-                        bumped[(s, t)] = G
+        def anchored(u):
+            return sum(1 for x in nb[u] if weight(u, x) == G) == 1
+
+        for s_, t_ in order:
+            if anchored(s_) and anchored(t_):
+                common = [x for x in nb[s_] if x != t_ and x in nb[t_]]
+                if len(common) == 1:            # the edge itself + exactly one 2-step path
+                    removed.append(common[0])
+                    bumped[(s_, t_)] = G
         return bumped, removed
 
     # ------------------------------------------------------------------ paths of a max-degree-2 graph
@@ -468,33 +525,38 @@ class SyntenyEngine:
             hi = np.array([sg[1] for sg in single], dtype=np.int64)
             up_dir = np.array([sg[2] > 0 for sg in single])
             n_all = hi - lo + 1
-            up = (CI[:, hi] - CI[:, lo]).astype(np.int64)
-            down = (CD[:, hi] - CD[:, lo]).astype(np.int64)
+            up, down = self._range_sums(lo, hi)
             inc_all = np.where(up_dir[None, :], up, down)
             dec_all = np.where(up_dir[None, :], down, up)
             first = np.where(up_dir, lo, hi)
             last = np.where(up_dir, hi, lo)
-            ctg_f, pos_f, pos_l = self.CTG[:, first], self.POS[:, first], self.POS[:, last]
+            ctg_f = self.CTG[:, first].T.tolist()
+            pos_f = self.POS[:, first].T.tolist()
+            pos_l = self.POS[:, last].T.tolist()
             plus = (inc_all == n_all - 1) | (n_all == 1)
             minus = ~plus & (dec_all == n_all - 1)
-            ambiguous = ~(plus | minus)
+            simple = (plus | minus).all(axis=0).tolist()
+            ori_simple = np.where(plus, "+", "-").T.tolist()
+            n_list, first_l, last_l = n_all.tolist(), first.tolist(), last.tolist()
             for x, sg in enumerate(single):
-                n = int(n_all[x])
-                ori = []
-                for a in range(G):
-                    if plus[a, x]:
-                        ori.append("+")
-                    elif minus[a, x]:
-                        ori.append("-")
-                    else:
-                        positive = int(inc_all[a, x]) / float(n - 1) * 100
-                        negative = 100 - positive
-                        ori.append("+" if positive >= self.m else ("-" if negative >= self.m else "?"))
-                if "?" in ori:
-                    to_remove.append(sg)
-                    continue
-                blocks.append(Block([sg], ctg_f[:, x].copy(), ori, int(first[x]), int(last[x]), pos_f[:, x].copy(),
-                                    pos_l[:, x].copy(), n))
+                n = n_list[x]
+                if simple[x]:
+                    ori = ori_simple[x]
+                else:
+                    ori = []
+                    for a in range(G):
+                        if plus[a, x]:
+                            ori.append("+")
+                        elif minus[a, x]:
+                            ori.append("-")
+                        else:
+                            positive = int(inc_all[a, x]) / float(n - 1) * 100
+                            negative = 100 - positive
+                            ori.append("+" if positive >= self.m else ("-" if negative >= self.m else "?"))
+                    if "?" in ori:
+                        to_remove.append(sg)
+                        continue
+                blocks.append(Block([sg], ctg_f[x], ori, first_l[x], last_l[x], pos_f[x], pos_l[x], n))
         for segs in paths:
             if len(segs) == 1:
                 continue
@@ -511,7 +573,8 @@ class SyntenyEngine:
             dec = np.zeros(G, dtype=np.int64)
             for lo, hi, d in segs:
                 if hi > lo:
-                    up, down = CI[:, hi] - CI[:, lo], CD[:, hi] - CD[:, lo]
+                    up, down = self._range_sums(np.array([lo]), np.array([hi]))
+                    up, down = up[:, 0], down[:, 0]
                     if d > 0:
                         inc += up; dec += down
                     else:
@@ -727,10 +790,13 @@ class SyntenyEngine:
         G = self.G
         # --- new minimizers from the masked assemblies (generate_additional_minimizers :532-541)
         masks = self._masks_for(blocks, prev_w)
+        self._tick("r_masks")
         new = []
         for a in range(G):
             h1, pos, ctg = self.be.sketch(a, new_w, masks[a])
             new.append(self._dedup(h1, pos.astype(np.int64), ctg.astype(np.int64)))
+        self.stats.setdefault("new_raw", []).append([int(len(x[0])) for x in new])
+        self._tick("r_sketch")
         # --- terminal / internal minimizers and block intervals (find_mx_in_blocks :205-226)
         term_ids = np.array([x for b in blocks for x in (b.first_id, b.last_id)], dtype=np.int64)
         terminal_h = set(int(x) for x in self.H[term_ids]) if len(term_ids) else set()
@@ -747,6 +813,7 @@ class SyntenyEngine:
                 if e - s < 2:
                     continue
                 intervals[a][int(b.ctg[a])].append((s + 1, e))
+        self._tick("r_blockinfo")
         # --- filter_minimizers_synteny_blocks (:256-280), vectorised per contig
         kept = []       # per assembly: (h1, pos, ctg, sublist_id)
         for a in range(G):
@@ -782,6 +849,7 @@ class SyntenyEngine:
                         ov[sel] = ii.overlaps(kp[:-1][sel], kp[1:][sel])
                 cut[1:] = ~same | ov
             kept.append((kh, kp, kc, np.cumsum(cut) - 1))
+        self._tick("r_filter")
         # --- G-way intersection (ntjoin_utils.filter_minimizers :152-165)
         common = None
         for a in range(G):
@@ -827,9 +895,11 @@ class SyntenyEngine:
                 self.CTG[a, vid] = kc
                 ids_per_asm.append(vid)
             if touched_base:
+                self.stats["base_overwrites"] = self.stats.get("base_overwrites", 0) + len(touched_base)
                 self._refresh_pairs(sorted(touched_base))
         else:
             ids_per_asm = [np.zeros(0, dtype=np.int64) for _ in range(G)]
+        self._tick("r_update")
         # --- build_graph in extend mode (ntjoin_utils.py:83-141)
         new_edges = {}          # (min,max) -> [support count, (s,t) as first inserted]
         new_order = []
@@ -878,6 +948,7 @@ class SyntenyEngine:
                 for key in bumps:
                     if key in wt:
                         wt[key] = G
+        self._tick("r_graph")
         # --- weight filter (+ flagged pairs on the last round)
         surviving = [key for key in fresh if key not in flagged_set]
         low = [key for key in surviving if wt[key] < G]
@@ -986,14 +1057,18 @@ class SyntenyEngine:
             print("Error: duplicate values found in w_rounds!", file=sys.stderr, flush=True)
             raise SystemExit(1)
         self.log("Sketching and joining minimizers, w =", self.w)
+        self._tick(None)
         tables = [self.be.sketch(a, self.w, None) for a in range(G)]
+        self._tick("sketch0")
         j = self.be.join(tables, self.orient)
+        self._tick("join")
         link, degree = j["link"], j["degree"]
         self.stats["vertices"] = int(len(j["H"]))
         if getattr(self, "dot_path", None):
             self.log("Printing graph", self.dot_path)
             self.be.write_dot(self.dot_path, j)
         self._init_vertices(j)
+        self._tick("init")
         self._edge_birth = {}
         V = self.V0
         # --- simplification, weight filter
@@ -1002,26 +1077,35 @@ class SyntenyEngine:
             self.log("Running graph simplificaton")
             bumped, removed = self._simplify_round0(np.asarray(link), np.asarray(degree))
         self.stats["simplified_vertices"] = len(set(removed))
+        self._tick("simplify0")
         self.log("Filtering the graph")
         if V > 1:
             self.conn[:] = np.asarray(link[:V - 1], dtype=bool)
-            ids = np.flatnonzero(self.conn)
-            self.nbr[ids, 1] = ids + 1                  # slot 1: right neighbour
-            self.nbr[ids + 1, 0] = ids                  # slot 0: left neighbour
+            ar = np.arange(1, V, dtype=np.int32)
+            self.nbr[:V - 1, 1] = np.where(self.conn, ar, -1)        # slot 1: right neighbour
+            self.nbr[1:V, 0] = np.where(self.conn, ar - 1, -1)       # slot 0: left neighbour
         if removed:
             self._remove_vertices(np.array(removed, dtype=np.int64))
-        for (s, t) in bumped:
-            if self.alive[s] and self.alive[t] and not self._has_edge(s, t):
-                self._add_edge(s, t)
+        if bumped:
+            be_ = np.array(list(bumped.keys()), dtype=np.int64)
+            ok = self.alive[be_[:, 0]] & self.alive[be_[:, 1]]
+            for s_, t_ in be_[ok].tolist():
+                if not self._has_edge(s_, t_):
+                    self._add_edge(s_, t_)
         # --- paths, blocks
         self.log("Finding paths")
+        self._tick("filter0")
         paths = self._find_paths()
+        self._tick("paths")
         self.stats["paths"] = len(paths)
         self.log("Finding synteny blocks")
         blocks = self._blocks_from_paths(paths)
+        self._tick("blocks")
         blocks = self._split_indels(blocks)
+        self._tick("indels")
         blocks = self._filter_small(blocks, 4)
         ordered = self._sort_blocks(blocks)
+        self._tick("filter_sort")
         if not ordered:
             print("Error - no paths found. Try adjusting the specified k/w parameters.")
             raise SystemExit(1)
@@ -1032,12 +1116,18 @@ class SyntenyEngine:
         for ri, new_w in enumerate(self.w_rounds):
             self.log("Extending synteny blocks with w =", new_w)
             last = new_w == self.w_rounds[-1]
+            self._tick("emit")
             self._refine_round(blocks, new_w, prev_w, last, ri + 1)
+            self._tick("refine")
             paths = self._find_paths()
+            self._tick("paths")
             blocks = self._blocks_from_paths(paths)
+            self._tick("blocks")
             blocks = self._split_indels(blocks)
+            self._tick("indels")
             blocks = self._filter_small(blocks, 4)
             ordered = self._sort_blocks(blocks)
+            self._tick("filter_sort")
             self._emit("pre_merge", ordered)
             if last:
                 merged = self._merge_collinear(ordered) if ordered else []
@@ -1045,5 +1135,6 @@ class SyntenyEngine:
                 merged = self._merge_collinear(merged) if merged else []
                 self._emit("final", merged, verbose=True)
             prev_w = new_w
+        self._tick("emit")
         self.log("Done extended synteny blocks")
         return self.outputs.get("final", self.outputs.get("initial"))
