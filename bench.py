@@ -402,13 +402,18 @@ def run_ours_multi(args, dist, ctx):
     mine, level = ctx.bloom(nbytes), (ctx.bloom(nbytes) if len(own) > 1 else None)
     ident = distributed.Comm.new_unique_id() if rank == 0 else b""
     comm = distributed.Comm(ctx, rank, N, dist.bcast_bytes(ident, 128))
+    peer = distributed.PeerMerge(mine, rank, N, dist.gather_objects, dist.barrier) if N <= 16 else None
+    use_p2p = args.merge == "p2p" and peer is not None
 
     def hot_path(gen_map):
         mine.clear()
         mine.insert_genome(gen_map[own[0]], K)
         for g in own[1:]:
             level.clear(); level.insert_genome(gen_map[g], K); mine.iand(level)
-        comm.allreduce_and(mine)                                   # the one bulk exchange
+        if use_p2p:
+            peer.merge("and")                                      # NVLink peer loads: reduce-scatter + all-gather
+        else:
+            comm.allreduce_and(mine)                               # the one bulk exchange (NCCL sum of counters)
         gathered = {}
         for slot, g in enumerate(own):
             t = ctx.sketch(gen_map[g], K, W, common=mine)
@@ -471,6 +476,24 @@ def run_ours_multi(args, dist, ctx):
     clk = clocks.stop()
     if rank == 0:
         assert text_e2e == text
+    # the exchange alone, both implementations (same bits: tests/test_gpu_multi.py), max over ranks
+    merge_ms = {}
+    for name in ("nccl", "p2p"):
+        if name == "p2p" and peer is None:
+            continue
+        best = None
+        for _ in range(2):
+            mine.clear(); mine.insert_genome(gens[own[0]], K)
+            ctx.sync(); dist.barrier()
+            t0 = time.perf_counter()
+            if name == "nccl":
+                comm.allreduce_and(mine)
+            else:
+                peer.merge("and")
+            ctx.sync()
+            dt = dist.max((time.perf_counter() - t0) * 1e3)
+            best = dt if best is None else min(best, dt)
+        merge_ms[name] = round(best, 2)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json"), encoding="utf-8") as fh:
@@ -490,7 +513,9 @@ def run_ours_multi(args, dist, ctx):
             "config": {"workload": f"{G} synthetic {args.genome_mbp:g} Mbp genomes one-per-GPU, counting-BF NCCL-sum merge, "
                                    f"d={d:g}, k={K} w={W}, w_rounds {ps['w_rounds']}, {N}xB200",
                        "genomes": G, "genome_bp": sizes[0], "k": K, "w": W, "fpr": 0.025, "bloom_bytes": nbytes,
+                       "merge": "p2p" if use_p2p else "nccl",
                        "merge_wire_bytes_per_rank": distributed.merge_wire_bytes(nbytes, N),
+                       "merge_alone_ms": merge_ms,
                        "l2": "inputs (bases + filters) are larger than L2; no flush needed",
                        "blocks": text.count("\n") // G, "vertices": eng.stats.get("vertices")},
             "clocks": clk,
@@ -502,6 +527,8 @@ def run_ours_multi(args, dist, ctx):
                          "kernel_ms_per_step": {f: round(prof[f][0] / args.steps, 3) for f in prof if prof[f][2]}},
             "cpu_baseline": None,
         }))
+    if peer is not None:
+        peer.close()
     comm.close()
 
 
@@ -556,6 +583,9 @@ def main():
     ap.add_argument("--cpu-sample-mbp", type=float, default=24.0, help="per-genome sample for the CPU arm")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--merge", choices=["nccl", "p2p"], default="nccl",
+                    help="multi-GPU filter merge: NCCL all-reduce(sum) of packed counters (default, the north-star form) "
+                         "or the peer-memory reduce-scatter/all-gather kernels")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: fewer than 3 warm-up steps; the number is not reportable", file=sys.stderr)

@@ -182,6 +182,17 @@ int nts_nccl_world(const nts_comm* comm);
 int nts_nccl_rank(const nts_comm* comm);
 int nts_bf_allreduce_and(nts_comm* comm, nts_bf* bf);
 int nts_bf_allreduce_or(nts_comm* comm, nts_bf* bf);
+/* Peer-memory merge (B200-native alternative, same result): every rank exports its filter with CUDA IPC
+ * (nts_bf_ipc_handle), maps the peers' filters (nts_p2p_open, handles in rank order), then
+ *   barrier; nts_p2p_reduce_scatter(op: 0 AND, 1 OR); barrier; nts_p2p_all_gather; barrier
+ * The reduce kernel reads slice `rank` of every peer's array straight from peer HBM over NVLink and
+ * combines it in registers; wire volume per rank 2*(P-1)/P * filter bytes. */
+typedef struct nts_p2p nts_p2p;
+int nts_bf_ipc_handle(nts_bf* bf, uint8_t handle_out[64]);
+int nts_p2p_open(nts_bf* mine, const uint8_t* handles, int rank, int world, nts_p2p** out);
+void nts_p2p_close(nts_p2p* p);
+int nts_p2p_reduce_scatter(nts_p2p* p, int op);
+int nts_p2p_all_gather(nts_p2p* p);
 /* all-gather of minimizer tables (ncclAllGather over padded columns): out[r] = rank r's table, as a
  * new nts_mxs on this rank; counts[world] must hold every rank's table size. */
 int nts_mxs_allgather(nts_comm* comm, const nts_mxs* mine, const uint64_t* counts, nts_mxs** out);

@@ -93,6 +93,11 @@ _SIGS = {
     "nts_nccl_rank": (C.c_int, [vp]),
     "nts_bf_allreduce_and": (C.c_int, [vp, vp]),
     "nts_bf_allreduce_or": (C.c_int, [vp, vp]),
+    "nts_bf_ipc_handle": (C.c_int, [vp, u8p]),
+    "nts_p2p_open": (C.c_int, [vp, u8p, C.c_int, C.c_int, vpp]),
+    "nts_p2p_close": (None, [vp]),
+    "nts_p2p_reduce_scatter": (C.c_int, [vp, C.c_int]),
+    "nts_p2p_all_gather": (C.c_int, [vp]),
     "nts_mxs_allgather": (C.c_int, [vp, vp, u64p, vpp]),
     "nts_graph_build": (C.c_int, [vp, vpp, C.c_uint32, C.c_uint32, vpp]),
     "nts_graph_destroy": (None, [vp]),

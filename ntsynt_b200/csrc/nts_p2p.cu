@@ -1,0 +1,163 @@
+// nts_p2p.cu -- Bloom-filter merge over NVLink peer memory (the B200-native alternative to the NCCL
+// counter merge of nts_nccl.cu).  One process per GPU: every rank exports its filter with
+// CUDA IPC, maps the peers' filters, and then
+//   reduce-scatter: rank r ANDs (or ORs) slice r of every peer's array into its own slice r with 128-bit
+//                   loads straight from peer HBM -- compute and transfer are one kernel;
+//   all-gather    : rank r copies the reduced slice s from peer s for every s != r.
+// Wire volume per rank: 2 * (P-1)/P * filter bytes (26 GB at P = 8 for a 14.8 GB filter), 4x less than
+// the 4-bit counter all-reduce.  The two phases are separated by host barriers supplied by the caller
+// (the launcher's side channel); results are bit-identical to nts_bf_allreduce_and (tests/test_gpu_multi.py).
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "nts_internal.h"
+
+namespace nts {
+
+constexpr int P2P_MAX_RANKS = 16;
+struct PeerPtrs { const uint4* p[P2P_MAX_RANKS]; };
+
+// op 0 = AND, 1 = OR
+__global__ void p2p_reduce_slice_kernel(uint4* __restrict__ mine, PeerPtrs peers, int rank, int world, uint64_t off16,
+                                        uint64_t n16, int op)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        uint4 acc = mine[off16 + i];
+        uint4 v[P2P_MAX_RANKS];
+#pragma unroll
+        for (int p = 0; p < P2P_MAX_RANKS; ++p)
+            if (p < world && p != rank) v[p] = peers.p[p][off16 + i];          // peer HBM over NVLink
+#pragma unroll
+        for (int p = 0; p < P2P_MAX_RANKS; ++p)
+            if (p < world && p != rank) {
+                if (op == 0) { acc.x &= v[p].x; acc.y &= v[p].y; acc.z &= v[p].z; acc.w &= v[p].w; }
+                else         { acc.x |= v[p].x; acc.y |= v[p].y; acc.z |= v[p].z; acc.w |= v[p].w; }
+            }
+        mine[off16 + i] = acc;
+    }
+}
+
+__global__ void p2p_gather_slice_kernel(uint4* __restrict__ mine, const uint4* __restrict__ peer, uint64_t off16, uint64_t n16)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        uint4 a = peer[off16 + i], b = peer[off16 + i + stride], c = peer[off16 + i + 2 * stride], d = peer[off16 + i + 3 * stride];
+        mine[off16 + i] = a; mine[off16 + i + stride] = b; mine[off16 + i + 2 * stride] = c; mine[off16 + i + 3 * stride] = d;
+    }
+    for (; i < n16; i += stride) mine[off16 + i] = peer[off16 + i];
+}
+
+}  // namespace nts
+
+using namespace nts;
+
+struct nts_p2p {
+    nts_ctx* ctx = nullptr;
+    nts_bf* mine = nullptr;
+    int rank = 0, world = 1;
+    void* peer[P2P_MAX_RANKS] = {nullptr};
+    uint64_t n16 = 0;
+};
+
+extern "C" {
+
+int nts_bf_ipc_handle(nts_bf* bf, uint8_t handle_out[64])
+{
+    if (!bf || !handle_out) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(bf->ctx->device));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+    NTS_CUDA(cudaIpcGetMemHandle(&h, bf->words.p));
+    memcpy(handle_out, &h, 64);
+    return NTS_OK;
+}
+
+int nts_p2p_open(nts_bf* mine, const uint8_t* handles /* world x 64 bytes, rank order */, int rank, int world, nts_p2p** out)
+{
+    if (!mine || !handles || !out || world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world) return fail(NTS_ERR_ARG, "bad argument");
+    nts_ctx* ctx = mine->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    nts_p2p* p = new (std::nothrow) nts_p2p();
+    if (!p) return fail(NTS_ERR_NOMEM, "host allocation failed");
+    p->ctx = ctx; p->mine = mine; p->rank = rank; p->world = world; p->n16 = mine->alloc_bytes / 16;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { p->peer[r] = mine->words.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&p->peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q) if (q != rank && p->peer[q]) cudaIpcCloseMemHandle(p->peer[q]);
+            delete p;
+            return fail(NTS_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer filter): ") + cudaGetErrorString(e));
+        }
+    }
+    *out = p;
+    return NTS_OK;
+}
+
+void nts_p2p_close(nts_p2p* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    for (int r = 0; r < p->world; ++r) if (r != p->rank && p->peer[r]) cudaIpcCloseMemHandle(p->peer[r]);
+    delete p;
+}
+
+static void slice_of(const nts_p2p* p, int s, uint64_t* off16, uint64_t* n16)
+{
+    const uint64_t per = (p->n16 + p->world - 1) / p->world;
+    *off16 = std::min<uint64_t>(p->n16, per * s);
+    *n16 = std::min<uint64_t>(p->n16, per * (s + 1)) - *off16;
+}
+
+/* phase 1: my slice of every peer's filter is reduced into my filter.  Call after a barrier that
+ * guarantees every rank's filter is complete; synchronous. */
+int nts_p2p_reduce_scatter(nts_p2p* p, int op)
+{
+    if (!p || (op != 0 && op != 1)) return fail(NTS_ERR_ARG, "bad argument");
+    nts_ctx* ctx = p->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    uint64_t off, n;
+    slice_of(p, p->rank, &off, &n);
+    if (n) {
+        PeerPtrs pp;
+        for (int r = 0; r < P2P_MAX_RANKS; ++r) pp.p[r] = r < p->world ? reinterpret_cast<const uint4*>(p->peer[r]) : nullptr;
+        ProfScope prof(ctx, PROF_NCCL, (double)(n * 16) * (p->world - 1));
+        p2p_reduce_slice_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(p->mine->words.p), pp, p->rank,
+                                                                           p->world, off, n, op);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+    }
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+/* phase 2: fetch every other rank's reduced slice.  Call after a barrier that guarantees every rank
+ * finished phase 1; synchronous.  A final barrier must follow before any filter is modified again. */
+int nts_p2p_all_gather(nts_p2p* p)
+{
+    if (!p) return fail(NTS_ERR_ARG, "null argument");
+    nts_ctx* ctx = p->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    {
+        ProfScope prof(ctx, PROF_NCCL, (double)p->mine->alloc_bytes);
+        for (int s = 0; s < p->world; ++s) {
+            if (s == p->rank) continue;
+            uint64_t off, n;
+            slice_of(p, s, &off, &n);
+            if (!n) continue;
+            p2p_gather_slice_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(p->mine->words.p),
+                                                                               reinterpret_cast<const uint4*>(p->peer[s]), off, n);
+            ctx->launches++;
+        }
+        NTS_CUDA(cudaGetLastError());
+    }
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+}  // extern "C"

@@ -73,6 +73,38 @@ class Comm:
             pass
 
 
+class PeerMerge:
+    """Bloom-filter merge over NVLink peer memory (nts_p2p_*): reduce-scatter + all-gather kernels that read
+    the peers' arrays directly.  `gather` / `barrier` are the launcher's host side channel:
+    gather(obj) -> list of every rank's obj in rank order; barrier() -> None."""
+
+    def __init__(self, bf, rank, world, gather, barrier):
+        self.bf, self.rank, self.world, self.barrier = bf, rank, world, barrier
+        mine = (C.c_uint8 * 64)()
+        check(lib.nts_bf_ipc_handle(bf._h, mine))
+        handles = b"".join(gather(bytes(mine)))
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        h = C.c_void_p()
+        check(lib.nts_p2p_open(bf._h, buf, int(rank), int(world), C.byref(h)))
+        self._h = h
+        barrier()
+
+    def merge(self, op="and"):
+        "filter := AND (or OR) over all ranks; every rank must call it"
+        self.bf.ctx.sync()
+        self.barrier()                       # every filter is complete
+        check(lib.nts_p2p_reduce_scatter(self._h, 0 if op == "and" else 1))
+        self.barrier()                       # every slice is reduced
+        check(lib.nts_p2p_all_gather(self._h))
+        self.barrier()                       # nobody still reads my slices
+
+    def close(self):
+        if self._h:
+            self.barrier()
+            lib.nts_p2p_close(self._h)
+            self._h = None
+
+
 class GatheredBackend:
     """SyntenyEngine backend for rank 0 of a one-genome-per-GPU run: round-0 tables were sketched on
     their owner ranks and all-gathered; refinement sketches (tiny, <1 % unmasked) run locally on the

@@ -37,6 +37,16 @@ WORKER = textwrap.dedent("""
     b = ctx.bloom(nbytes); b.insert_genome(gens[1], k)
     a.ior(b)
     assert np.array_equal(both.to_numpy(), a.to_numpy()), "NCCL counter merge != OR"
+    # peer-memory merge (CUDA IPC + NVLink loads) gives the same bits as the NCCL counter merge
+    pm_bf = ctx.bloom(nbytes)
+    pm_bf.insert_genome(gens[d.rank], k)
+    pm = distributed.PeerMerge(pm_bf, d.rank, d.world, d.gather_objects, d.barrier)
+    pm.merge("and")
+    assert np.array_equal(pm_bf.to_numpy(), ref.to_numpy()), "peer-memory merge != AND"
+    pm_bf.clear(); pm_bf.insert_genome(gens[d.rank], k)
+    pm.merge("or")
+    assert np.array_equal(pm_bf.to_numpy(), a.to_numpy()), "peer-memory merge != OR"
+    pm.close()
     t = ctx.sketch(gens[d.rank], k, 1000, common=mine)
     counts = d.gather_objects(len(t))
     tabs = comm.allgather_tables(t, counts, gens)
