@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "nts_internal.h"
@@ -17,6 +18,81 @@ int bf_insert_partitioned(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const 
 void part_scratch_release(nts_ctx* ctx);
 
 static thread_local std::string g_err;
+
+// ---- caching device allocator (see nts_internal.h)
+namespace {
+struct PoolState {
+    std::mutex mu;
+    std::map<int, std::multimap<size_t, void*>> free_blocks;   // device -> size -> block
+    std::map<void*, std::pair<int, size_t>> live;              // block -> (device, size)
+};
+PoolState& pool() { static PoolState* s = new PoolState(); return *s; }
+size_t pool_round(size_t b)
+{
+    if (b < 4096) return 4096;
+    if (b < (1u << 20)) { size_t r = 4096; while (r < b) r <<= 1; return r; }
+    const size_t g = 2u << 20;                                  // 2 MB granules
+    return (b + g - 1) / g * g;
+}
+}  // namespace
+
+cudaError_t pool_alloc(void** out, size_t bytes)
+{
+    const size_t want = pool_round(bytes);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    PoolState& ps = pool();
+    {
+        std::lock_guard<std::mutex> lk(ps.mu);
+        auto& fl = ps.free_blocks[dev];
+        auto it = fl.lower_bound(want);
+        if (it != fl.end() && it->first <= want + want / 4 + (1u << 20)) {     // close enough in size: reuse
+            *out = it->second;
+            ps.live[*out] = {dev, it->first};
+            fl.erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim(dev);                                          // out of memory: drop the cache and retry once
+        e = cudaMalloc(out, want);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(ps.mu);
+        ps.live[*out] = {dev, want};
+    }
+    return e;
+}
+
+void pool_free(void* p)
+{
+    if (!p) return;
+    PoolState& ps = pool();
+    std::lock_guard<std::mutex> lk(ps.mu);
+    auto it = ps.live.find(p);
+    if (it == ps.live.end()) { cudaFree(p); return; }
+    ps.free_blocks[it->second.first].emplace(it->second.second, p);
+    ps.live.erase(it);
+}
+
+void pool_trim(int device)
+{
+    PoolState& ps = pool();
+    std::vector<void*> blocks;
+    {
+        std::lock_guard<std::mutex> lk(ps.mu);
+        auto& fl = ps.free_blocks[device];
+        for (auto& kv : fl) blocks.push_back(kv.second);
+        fl.clear();
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    for (void* b : blocks) cudaFree(b);
+    if (cur != device) cudaSetDevice(cur);
+}
 
 void set_error(const std::string& msg) { g_err = msg; }
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -190,7 +266,9 @@ void nts_ctx_destroy(nts_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
     part_scratch_release(ctx);
+    pool_trim(ctx->device);
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

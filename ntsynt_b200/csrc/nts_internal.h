@@ -22,6 +22,14 @@ int fail(int code, const std::string& msg);
             return ::nts::fail(NTS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));        \
     } while (0)
 
+// Caching device allocator: freed blocks are kept per device and reused.  cudaMalloc / cudaFree are
+// synchronising and become much slower once peer access is enabled (NCCL, CUDA IPC), and the hot path
+// allocates scratch buffers every step.  Blocks are whole cudaMalloc allocations (never sub-allocated), so a
+// pooled pointer can still be exported with cudaIpcGetMemHandle.
+cudaError_t pool_alloc(void** p, size_t bytes);
+void pool_free(void* p);
+void pool_trim(int device);   // give every cached block of a device back to the driver
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -32,12 +40,12 @@ struct DevBuf {
     DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; return *this; }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) pool_free(p); p = nullptr; n = 0; }
     cudaError_t alloc(size_t count)
     {
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+        cudaError_t e = pool_alloc(reinterpret_cast<void**>(&p), count * sizeof(T));
         if (e == cudaSuccess) n = count; else p = nullptr;
         return e;
     }

@@ -169,6 +169,7 @@ class SyntenyEngine:
         self.conn = np.zeros(max(V - 1, 0), dtype=bool)              # edge (i, i+1) present, base vertices
         self.sparse = set()                                          # vertices that may hold a non-(i,i+1) edge
         self._h_extra = {}
+        self._pair_cache = None
         self._pair_orig, self._pair_delta = {}, {}      # corrections to the device prefix sums (see _refresh_pairs)
         # per-pair arrays of (i, i+1) and their prefix sums per assembly
         self.incmask = np.asarray(j["incmask"], dtype=np.uint32)
@@ -214,6 +215,7 @@ class SyntenyEngine:
                         self._pair_delta[i] = (di, dd)
                     else:
                         self._pair_delta.pop(i, None)
+                    self._pair_cache = None
                     self.incmask[i], self.decmask[i] = inc, dec
                     ad = np.abs(d)
                     sp = int(ad.max() - ad.min())
@@ -227,13 +229,22 @@ class SyntenyEngine:
     def _range_sums(self, lo, hi):
         "per-assembly counts of increasing / decreasing pairs (i, i+1) with lo <= i < hi, for arrays lo, hi"
         CI, CD = self._cums()
+        lo = np.minimum(lo, self.V0)          # vertices added after round 0 only form single-vertex segments
+        hi = np.minimum(hi, self.V0)
         up = (CI[:, hi] - CI[:, lo]).astype(np.int64)
         down = (CD[:, hi] - CD[:, lo]).astype(np.int64)
-        for i, (di, dd) in self._pair_delta.items():
-            hit = (lo <= i) & (i < hi)
-            if hit.any():
-                up[:, hit] += di[:, None]
-                down[:, hit] += dd[:, None]
+        if self._pair_delta:
+            if self._pair_cache is None or self._pair_cache[0] != len(self._pair_delta):
+                keys = np.array(sorted(self._pair_delta), dtype=np.int64)
+                di = np.array([self._pair_delta[int(k)][0] for k in keys], dtype=np.int64).T      # [G, n]
+                dd = np.array([self._pair_delta[int(k)][1] for k in keys], dtype=np.int64).T
+                z = np.zeros((self.G, 1), dtype=np.int64)
+                self._pair_cache = (len(self._pair_delta), keys, np.concatenate([z, np.cumsum(di, axis=1)], axis=1),
+                                    np.concatenate([z, np.cumsum(dd, axis=1)], axis=1))
+            _, keys, pdi, pdd = self._pair_cache
+            a0, a1 = np.searchsorted(keys, lo), np.searchsorted(keys, hi)
+            up += pdi[:, a1] - pdi[:, a0]
+            down += pdd[:, a1] - pdd[:, a0]
         return up, down
 
     def _ctg_round0(self, a, v):
@@ -513,152 +524,150 @@ class SyntenyEngine:
 
     # ------------------------------------------------------------------ blocks from paths
     def _blocks_from_paths(self, paths):
-        """find_synteny_blocks (ntsynt_synteny.py:66-106) for every path.  Orientation tallies come from
-        prefix sums of the per-pair direction masks; only junctions between segments are looked at
-        one by one.  Vertices of unoriented blocks are deleted from the graph."""
+        """find_synteny_blocks (ntsynt_synteny.py:66-106) for every path, vectorised over the flattened
+        segments and junctions of all paths.  Orientation tallies come from prefix sums of the per-pair
+        direction masks (segments) plus the few junction steps.  Vertices of unoriented blocks are deleted."""
+        if not paths:
+            return []
         G = self.G
-        CI, CD = self._cums()
-        blocks, to_remove = [], []
-        single = [p[0] for p in paths if len(p) == 1]
-        if single:
-            lo = np.array([sg[0] for sg in single], dtype=np.int64)
-            hi = np.array([sg[1] for sg in single], dtype=np.int64)
-            up_dir = np.array([sg[2] > 0 for sg in single])
-            n_all = hi - lo + 1
-            up, down = self._range_sums(lo, hi)
-            inc_all = np.where(up_dir[None, :], up, down)
-            dec_all = np.where(up_dir[None, :], down, up)
-            first = np.where(up_dir, lo, hi)
-            last = np.where(up_dir, hi, lo)
-            ctg_f = self.CTG[:, first].T.tolist()
-            pos_f = self.POS[:, first].T.tolist()
-            pos_l = self.POS[:, last].T.tolist()
-            plus = (inc_all == n_all - 1) | (n_all == 1)
-            minus = ~plus & (dec_all == n_all - 1)
-            simple = (plus | minus).all(axis=0).tolist()
-            ori_simple = np.where(plus, "+", "-").T.tolist()
-            n_list, first_l, last_l = n_all.tolist(), first.tolist(), last.tolist()
-            for x, sg in enumerate(single):
-                n = n_list[x]
-                if simple[x]:
-                    ori = ori_simple[x]
-                else:
-                    ori = []
-                    for a in range(G):
-                        if plus[a, x]:
-                            ori.append("+")
-                        elif minus[a, x]:
-                            ori.append("-")
-                        else:
-                            positive = int(inc_all[a, x]) / float(n - 1) * 100
-                            negative = 100 - positive
-                            ori.append("+" if positive >= self.m else ("-" if negative >= self.m else "?"))
-                    if "?" in ori:
-                        to_remove.append(sg)
-                        continue
-                blocks.append(Block([sg], ctg_f[x], ori, first_l[x], last_l[x], pos_f[x], pos_l[x], n))
-        for segs in paths:
-            if len(segs) == 1:
-                continue
-            # contig change can only happen at a junction between segments: keep the LAST run of constant
-            # contigs (past_start_flag is never set, ntsynt_synteny.py:71,77)
-            start_seg = 0
-            for jx in range(1, len(segs)):
-                u, v = seg_last(segs[jx - 1]), seg_first(segs[jx])
-                if (self.CTG[:, u] != self.CTG[:, v]).any():
-                    start_seg = jx
-            segs = segs[start_seg:]
-            n = sum(hi - lo + 1 for lo, hi, _ in segs)
-            inc = np.zeros(G, dtype=np.int64)
-            dec = np.zeros(G, dtype=np.int64)
-            for lo, hi, d in segs:
-                if hi > lo:
-                    up, down = self._range_sums(np.array([lo]), np.array([hi]))
-                    up, down = up[:, 0], down[:, 0]
-                    if d > 0:
-                        inc += up; dec += down
-                    else:
-                        inc += down; dec += up
-            for jx in range(1, len(segs)):
-                dp = self.POS[:, seg_first(segs[jx])] - self.POS[:, seg_last(segs[jx - 1])]
-                inc += dp > 0
-                dec += dp < 0
-            ori = []
+        nseg = np.array([len(p) for p in paths], dtype=np.int64)
+        flat = [sg for p in paths for sg in p]
+        lo = np.array([sg[0] for sg in flat], dtype=np.int64)
+        hi = np.array([sg[1] for sg in flat], dtype=np.int64)
+        up_dir = np.array([sg[2] > 0 for sg in flat])
+        pid = np.repeat(np.arange(len(paths)), nseg)
+        seg0 = np.concatenate([[0], np.cumsum(nseg)])                 # first segment index of each path
+        first = np.where(up_dir, lo, hi)
+        last = np.where(up_dir, hi, lo)
+        # junctions: between segment j-1 and j of the same path
+        jn = np.flatnonzero(pid[1:] == pid[:-1]) + 1                  # index of the segment AFTER the junction
+        start_seg = seg0[:-1].copy()
+        jinc = jdec = None
+        if len(jn):
+            u, v = last[jn - 1], first[jn]
+            chg = (self.CTG[:, u] != self.CTG[:, v]).any(axis=0)
+            # only the LAST run of constant contigs of a path becomes a block (past_start_flag is never set,
+            # ntsynt_synteny.py:71,77): the block starts at the last junction with a contig change
+            if chg.any():
+                np.maximum.at(start_seg, pid[jn[chg]], jn[chg])
+            dp = self.POS[:, v] - self.POS[:, u]
+            jkeep = jn > start_seg[pid[jn]]                           # junctions inside the block
+            jinc = np.zeros((G, len(paths)), dtype=np.int64)
+            jdec = np.zeros((G, len(paths)), dtype=np.int64)
             for a in range(G):
-                if n == 1 or inc[a] == n - 1:
-                    ori.append("+")
-                elif dec[a] == n - 1:
-                    ori.append("-")
-                else:
-                    positive = int(inc[a]) / float(n - 1) * 100
-                    negative = 100 - positive
-                    ori.append("+" if positive >= self.m else ("-" if negative >= self.m else "?"))
-            if "?" in ori:
-                to_remove.extend(segs)
-                continue
-            f, l = seg_first(segs[0]), seg_last(segs[-1])
-            blocks.append(Block(segs, self.CTG[:, f].copy(), ori, f, l, self.POS[:, f].copy(), self.POS[:, l].copy(), n))
+                jinc[a] = np.bincount(pid[jn[jkeep]], weights=(dp[a, jkeep] > 0), minlength=len(paths))
+                jdec[a] = np.bincount(pid[jn[jkeep]], weights=(dp[a, jkeep] < 0), minlength=len(paths))
+        keep_seg = np.arange(len(flat)) >= start_seg[pid]
+        up, down = self._range_sums(lo, hi)
+        sinc = np.where(up_dir[None, :], up, down) * keep_seg[None, :]
+        sdec = np.where(up_dir[None, :], down, up) * keep_seg[None, :]
+        inc = np.zeros((G, len(paths)), dtype=np.int64)
+        dec = np.zeros((G, len(paths)), dtype=np.int64)
+        for a in range(G):
+            inc[a] = np.bincount(pid, weights=sinc[a], minlength=len(paths))
+            dec[a] = np.bincount(pid, weights=sdec[a], minlength=len(paths))
+        if jinc is not None:
+            inc += jinc; dec += jdec
+        n_all = np.bincount(pid, weights=(hi - lo + 1) * keep_seg, minlength=len(paths)).astype(np.int64)
+        f_id = first[start_seg]
+        l_id = last[seg0[1:] - 1]
+        plus = (inc == n_all - 1) | (n_all == 1)
+        minus = ~plus & (dec == n_all - 1)
+        simple = (plus | minus).all(axis=0).tolist()
+        ori_simple = np.where(plus, "+", "-").T.tolist()
+        ctg_f = self.CTG[:, f_id].T.tolist()
+        pos_f = self.POS[:, f_id].T.tolist()
+        pos_l = self.POS[:, l_id].T.tolist()
+        n_list, f_list, l_list = n_all.tolist(), f_id.tolist(), l_id.tolist()
+        s_list, e_list = (start_seg - seg0[:-1]).tolist(), nseg.tolist()
+        blocks, to_remove = [], []
+        for x, segs in enumerate(paths):
+            if s_list[x]:
+                segs = segs[s_list[x]:]
+            n = n_list[x]
+            if simple[x]:
+                ori = ori_simple[x]
+            else:
+                ori = []
+                for a in range(G):
+                    if plus[a, x]:
+                        ori.append("+")
+                    elif minus[a, x]:
+                        ori.append("-")
+                    else:
+                        positive = int(inc[a, x]) / float(n - 1) * 100
+                        negative = 100 - positive
+                        ori.append("+" if positive >= self.m else ("-" if negative >= self.m else "?"))
+                if "?" in ori:
+                    to_remove.extend(segs)
+                    continue
+            blocks.append(Block(segs, ctg_f[x], ori, f_list[x], l_list[x], pos_f[x], pos_l[x], n))
         if to_remove:
             self._remove_segments(to_remove)
         return blocks
 
     def _split_indels(self, blocks):
         "check_for_indels + break_synteny_block (ntsynt_synteny.py:364-409)"
+        if not blocks:
+            return blocks
         self._cums()
         big = self.big
+        # vectorised detection: blocks with no large-spread pair inside a segment and no large-spread junction
+        nseg = np.array([len(b.segs) for b in blocks], dtype=np.int64)
+        flat = [sg for b in blocks for sg in b.segs]
+        lo = np.array([sg[0] for sg in flat], dtype=np.int64)
+        hi = np.array([sg[1] for sg in flat], dtype=np.int64)
+        bid = np.repeat(np.arange(len(blocks)), nseg)
+        dirty = np.zeros(len(blocks), dtype=bool)
+        if len(big):
+            inside = np.searchsorted(big, lo) != np.searchsorted(big, hi)
+            dirty[bid[inside]] = True
+        jn = np.flatnonzero(bid[1:] == bid[:-1]) + 1
+        if len(jn):
+            up_dir = np.array([sg[2] > 0 for sg in flat])
+            first = np.where(up_dir, lo, hi)
+            last = np.where(up_dir, hi, lo)
+            dd = np.abs(self.POS[:, first[jn]] - self.POS[:, last[jn - 1]])
+            wide = (dd.max(axis=0) - dd.min(axis=0)) > self.bp
+            dirty[bid[jn[wide]]] = True
+        if not dirty.any():
+            return blocks
         out = []
         rm_u, rm_v = [], []
-        # single-segment blocks without a large-spread pair inside need no work (vectorised pre-check)
-        one = [x for x, b in enumerate(blocks) if len(b.segs) == 1]
-        clean = set()
-        if one and len(big):
-            lo = np.array([blocks[x].segs[0][0] for x in one], dtype=np.int64)
-            hi = np.array([blocks[x].segs[0][1] for x in one], dtype=np.int64)
-            none = np.searchsorted(big, lo) == np.searchsorted(big, hi)
-            clean = set(x for x, ok in zip(one, none.tolist()) if ok)
-        elif one:
-            clean = set(one)
         for bx, b in enumerate(blocks):
-            if bx in clean:
+            if not dirty[bx]:
                 out.append(b)
                 continue
-            # break points as (segment index, id of the vertex BEFORE the break in traversal order)
             pieces, cur = [], []
-            any_break = False
-            for jx, (lo, hi, d) in enumerate(b.segs):
+            for jx, (slo, shi, d) in enumerate(b.segs):
                 if jx > 0:
                     u, v = seg_last(b.segs[jx - 1]), seg_first(b.segs[jx])
                     dd = np.abs(self.POS[:, v] - self.POS[:, u])
                     if int(dd.max() - dd.min()) > self.bp:
                         rm_u.append(u); rm_v.append(v)
                         pieces.append(cur); cur = []
-                        any_break = True
-                cuts = big[np.searchsorted(big, lo):np.searchsorted(big, hi)] if hi > lo else ()
+                cuts = big[np.searchsorted(big, slo):np.searchsorted(big, shi)] if shi > slo else ()
                 if len(cuts):
-                    any_break = True
                     rm_u.extend(int(c) for c in cuts); rm_v.extend(int(c) + 1 for c in cuts)
                     if d > 0:
-                        s0 = lo
+                        s0 = slo
                         for c in cuts:
                             cur.append((s0, int(c), 1)); pieces.append(cur); cur = []
                             s0 = int(c) + 1
-                        cur.append((s0, hi, 1))
+                        cur.append((s0, shi, 1))
                     else:
-                        s0 = hi
+                        s0 = shi
                         for c in cuts[::-1]:
                             cur.append((int(c) + 1, s0, -1)); pieces.append(cur); cur = []
                             s0 = int(c)
-                        cur.append((lo, s0, -1))
+                        cur.append((slo, s0, -1))
                 else:
-                    cur.append((lo, hi, d))
+                    cur.append((slo, shi, d))
             pieces.append(cur)
-            if not any_break:
-                out.append(b)
-                continue
             for segs in pieces:
                 f, l = seg_first(segs[0]), seg_last(segs[-1])
-                n = sum(hi - lo + 1 for lo, hi, _ in segs)
-                out.append(Block(segs, b.ctg, list(b.ori), f, l, self.POS[:, f].copy(), self.POS[:, l].copy(), n))
+                n = sum(h_ - l_ + 1 for l_, h_, _ in segs)
+                out.append(Block(segs, b.ctg, list(b.ori), f, l, self.POS[:, f].tolist(), self.POS[:, l].tolist(), n))
         if rm_u:
             self._remove_edges(np.array(rm_u, dtype=np.int64), np.array(rm_v, dtype=np.int64))
         return out
