@@ -53,6 +53,8 @@ int nts_timer_start(nts_ctx* ctx);
 int nts_timer_stop(nts_ctx* ctx, float* ms_out);
 /* number of kernel launches issued by this library on this context since creation */
 uint64_t nts_launch_count(const nts_ctx* ctx);
+/* statistics: dense sub-tiles the sparse sketch kernel handed to the dense selector (unresolved windows) since creation */
+uint64_t nts_sketch_escalated(const nts_ctx* ctx);
 /* free / total device memory in bytes */
 int nts_mem_info(nts_ctx* ctx, uint64_t* free_b, uint64_t* total_b);
 /* Per-kernel-family device timing with CUDA events on the context's stream (bench.py's roofline

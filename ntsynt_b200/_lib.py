@@ -47,6 +47,7 @@ _SIGS = {
     "nts_timer_start": (C.c_int, [vp]),
     "nts_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "nts_launch_count": (C.c_uint64, [vp]),
+    "nts_sketch_escalated": (C.c_uint64, [vp]),
     "nts_mem_info": (C.c_int, [vp, u64p, u64p]),
     "nts_prof_enable": (C.c_int, [vp, C.c_int]),
     "nts_prof_reset": (C.c_int, [vp]),

@@ -104,8 +104,9 @@ static void make_hash_tables(uint32_t k, HashTables* t)
     std::memset(t, 0, sizeof(*t));
     for (unsigned in = 0; in < 4; ++in)
         for (unsigned out = 0; out < 4; ++out) {
-            t->roll_f[in * 4 + out] = seed_of(in) ^ srol_n(seed_of(out), k);
-            t->roll_r[in * 4 + out] = seed_of(3 - out) ^ srol_n(seed_of(3 - in), k);
+            const uint64_t rf = seed_of(in) ^ srol_n(seed_of(out), k);
+            const uint64_t rr = seed_of(3 - out) ^ srol_n(seed_of(3 - in), k);
+            t->roll[in * 4 + out] = make_uint4((uint32_t)rf, (uint32_t)(rf >> 32), (uint32_t)rr, (uint32_t)(rr >> 32));
         }
     for (unsigned i = 0; i < k; ++i)
         for (unsigned c = 0; c < 4; ++c) {
@@ -300,6 +301,7 @@ int nts_timer_stop(nts_ctx* ctx, float* ms_out)
 }
 
 uint64_t nts_launch_count(const nts_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t nts_sketch_escalated(const nts_ctx* ctx) { return ctx ? ctx->sketch_escalated : 0; }
 
 int nts_mem_info(nts_ctx* ctx, uint64_t* free_b, uint64_t* total_b)
 {
@@ -712,14 +714,32 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     if (w < 1) return fail(NTS_ERR_ARG, "w must be >= 1");
     NTS_CUDA(cudaSetDevice(ctx->device));
     constexpr int THREADS = 512;
-    // slots per tile: as many as fit two CTAs per SM; wide windows fall back to one CTA per SM
+    // dense tiles: as many slots as fit two CTAs per SM; wide windows fall back to one CTA per SM
     int max_optin = 0;
     NTS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     uint32_t NT = 8960;
     if (w > 4096) NT = 18432;
     if (2ull * w > NT || sketch_smem_bytes(NT, THREADS) > (size_t)max_optin)
         return fail(NTS_ERR_ARG, "w too large for the shared-memory window selector (max 9216)");
-    const uint32_t T = NT - w;
+    uint32_t T = NT - w;
+    // sparse tiles (sketch_sparse_kernel): R dense tiles each, sized so that a thread stages ~3 candidates
+    constexpr int SCAP = 16, CCAP = 3072;
+    bool sparse = w >= 128;
+    if (const char* env = getenv("NTS_SKETCH_DENSE")) { if (env[0] == '1') sparse = false; }
+    uint32_t R = 1, NT_s = 0, C_s = 0, tau_hi = 0;
+    if (sparse) {
+        const double density = 48.0 / (double)w;                  // ~48 candidates per window
+        uint32_t c_target = (uint32_t)(3.1 / density);
+        c_target = std::max<uint32_t>(4, std::min<uint32_t>(c_target, 120));
+        const uint32_t nt_target = std::max<uint32_t>(THREADS * c_target, 2 * w);
+        const uint32_t ts_target = nt_target - w;
+        R = (ts_target + T - 1) / T;
+        T = std::max<uint32_t>(ts_target / R, 1);                 // dense sub-tile size; R * T window ends per sparse tile
+        NT_s = R * T + w;
+        C_s = (NT_s + THREADS - 1) / THREADS;
+        tau_hi = (uint32_t)std::min(density * 4294967296.0, 4294967295.0);
+        if (C_s > 255 || NT_s > 65535) sparse = false, T = NT - w, R = 1;
+    }
 
     const HashTables* tabs = nullptr;
     int rc = get_tables(ctx, k, &tabs);
@@ -736,20 +756,25 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     }
     struct ViewGuard { nts_view* p; ~ViewGuard() { delete p; } } guard{owned};
 
-    // tiles
+    // tiles: one per R * T window ends of a contig; each stands for up to R output slots (dense sub-tiles)
     std::vector<TileDesc> tiles;
+    uint32_t n_slots = 0;
     for (uint32_t c = 0; c < g->n_contigs; ++c) {
         const uint64_t v0 = v->contig_v[c], v1 = v->contig_v[c + 1];
         const uint64_t nv = v1 - v0;
         if (nv < w) continue;
         const uint64_t n_win = nv - w + 1;
-        for (uint64_t t = 0; t * T < n_win; ++t) {
+        const uint64_t TS = (uint64_t)R * T;
+        for (uint64_t t = 0; t * TS < n_win; ++t) {
             TileDesc td;
-            td.vfirst = v0 + t * T;
+            td.vfirst = v0 + t * TS;
             td.vend = v1;
             td.cbase = g->contig_word_off[c] * 32;
             td.contig = c;
             td.has_prev = t > 0;
+            td.out_slot = n_slots;
+            td.n_sub = (uint32_t)((std::min<uint64_t>(TS, n_win - t * TS) + T - 1) / T);
+            n_slots += td.n_sub;
             tiles.push_back(td);
         }
     }
@@ -764,24 +789,28 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
         return NTS_OK;
     }
     const uint32_t n_tiles = (uint32_t)tiles.size();
-    DevBuf<TileDesc> d_tiles;
+    DevBuf<TileDesc> d_tiles, d_esc;
     DevBuf<uint32_t> d_off, d_cnt;
     DevBuf<uint64_t> d_dst;
-    DevBuf<unsigned long long> d_total;
-    if (d_tiles.alloc(n_tiles) != cudaSuccess || d_off.alloc(n_tiles) != cudaSuccess || d_cnt.alloc(n_tiles) != cudaSuccess ||
-        d_dst.alloc(n_tiles) != cudaSuccess || d_total.alloc(1) != cudaSuccess)
+    DevBuf<unsigned long long> d_total;      // [0] minimizers so far, [1] (low word) escalated dense tiles
+    if (d_tiles.alloc(n_tiles) != cudaSuccess || d_off.alloc(n_slots) != cudaSuccess || d_cnt.alloc(n_slots) != cudaSuccess ||
+        d_dst.alloc(n_slots) != cudaSuccess || d_total.alloc(2) != cudaSuccess || (sparse && d_esc.alloc(n_slots) != cudaSuccess))
         return fail(NTS_ERR_NOMEM, "device allocation failed (tiles)");
     NTS_CUDA(copy_h2d(ctx, d_tiles.p, tiles.data(), (size_t)n_tiles * sizeof(TileDesc)));
 
     uint64_t m = 0, mp = 0;
     if (common) mod_params(common, &m, &mp); else if (repeat) mod_params(repeat, &m, &mp);
 
-    // pruning threshold: ~48 slots per window are expected below tau (uniform hashes)
+    // dense kernel's own pruning threshold: ~48 slots per window are expected below tau (uniform hashes)
     uint64_t tau = KEY_MAX;
     if ((common || repeat) && w > 96) tau = (uint64_t)((48.0 / (double)w) * 18446744073709551616.0);
     if (const char* env = getenv("NTS_SKETCH_NO_PRUNE")) { if (env[0] == '1') tau = KEY_MAX; }
     const size_t smem = sketch_smem_bytes(NT, THREADS);
     NTS_CUDA(cudaFuncSetAttribute(sketch_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem_s = sizeof(HashTables) + (size_t)SCAP * THREADS * 9 + (size_t)CCAP * 10;
+    if (sparse)
+        NTS_CUDA(cudaFuncSetAttribute(sketch_sparse_kernel<THREADS, SCAP, CCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_s));
 
     // expected density of minimizers is 2/(w+1) per window; start with 2.5x that
     uint64_t n_win_total = 0;
@@ -789,7 +818,7 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
         uint64_t nv = v->contig_v[c + 1] - v->contig_v[c];
         if (nv >= w) n_win_total += nv - w + 1;
     }
-    uint64_t cap = (uint64_t)(5.0 * (double)n_win_total / (double)(w + 1)) + 4096 + n_tiles;
+    uint64_t cap = (uint64_t)(5.0 * (double)n_win_total / (double)(w + 1)) + 4096 + n_slots;
     cap = std::min<uint64_t>(cap, n_win_total);
     DevBuf<uint64_t> u_h1;
     DevBuf<uint32_t> u_pos, u_ctg;
@@ -798,16 +827,34 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
         if (cap > 0xFFFFFFF0ull) return fail(NTS_ERR_OVERFLOW, "more than 2^32 minimizers in one sketch");
         if (u_h1.alloc(cap) != cudaSuccess || u_pos.alloc(cap) != cudaSuccess || u_ctg.alloc(cap) != cudaSuccess)
             return fail(NTS_ERR_NOMEM, "device allocation failed (minimizer buffer)");
-        NTS_CUDA(cudaMemsetAsync(d_total.p, 0, 8, ctx->stream));
+        NTS_CUDA(cudaMemsetAsync(d_total.p, 0, 16, ctx->stream));
         SketchOut so;
         so.h1 = u_h1.p; so.pos = u_pos.p; so.contig = u_ctg.p;
         so.tile_off = d_off.p; so.tile_cnt = d_cnt.p; so.total = d_total.p; so.cap = cap;
         {
             ProfScope prof(ctx, PROF_SKETCH, (double)v->total_valid);
-            sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(
-                device_view(g, v), tabs, common ? common->words.p : nullptr, repeat ? repeat->words.p : nullptr, m, mp,
-                d_tiles.p, w, T, tau, so);
-            ctx->launches++;
+            const GenomeView gv = device_view(g, v);
+            const uint32_t* cw = common ? common->words.p : nullptr;
+            const uint32_t* rw = repeat ? repeat->words.p : nullptr;
+            if (sparse) {
+                unsigned int* esc_count = reinterpret_cast<unsigned int*>(d_total.p + 1);
+                sketch_sparse_kernel<THREADS, SCAP, CCAP><<<n_tiles, THREADS, smem_s, ctx->stream>>>(
+                    gv, tabs, cw, rw, m, mp, d_tiles.p, w, NT_s, C_s, T, tau_hi, so, d_esc.p, esc_count);
+                ctx->launches++;
+                NTS_CUDA(cudaGetLastError());
+                unsigned int n_esc = 0;
+                NTS_CUDA(cudaMemcpyAsync(&n_esc, esc_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+                ctx->sketch_escalated += n_esc;
+                if (n_esc) {       // tiles with an unresolved window: the dense selector, every slot queried
+                    sketch_kernel<THREADS><<<n_esc, THREADS, smem, ctx->stream>>>(gv, tabs, cw, rw, m, mp, d_esc.p, w, T,
+                                                                                 KEY_MAX, so);
+                    ctx->launches++;
+                }
+            } else {
+                sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(gv, tabs, cw, rw, m, mp, d_tiles.p, w, T, tau, so);
+                ctx->launches++;
+            }
         }
         NTS_CUDA(cudaGetLastError());
         NTS_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -820,13 +867,13 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     if (mx->h1.alloc(total) != cudaSuccess || mx->pos.alloc(total) != cudaSuccess || mx->contig.alloc(total) != cudaSuccess)
         return fail(NTS_ERR_NOMEM, "device allocation failed (minimizer table)");
     ProfScope prof_post(ctx, PROF_SKETCH_POST, (double)total);
-    tile_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt.p, d_dst.p, n_tiles);
+    tile_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt.p, d_dst.p, n_slots);
     ctx->launches++;
     NTS_CUDA(cudaGetLastError());
     {
-        uint64_t threads_needed = (uint64_t)n_tiles * 32;
+        uint64_t threads_needed = (uint64_t)n_slots * 32;
         unsigned blocks = (unsigned)((threads_needed + 255) / 256);
-        sketch_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(u_h1.p, u_pos.p, u_ctg.p, d_off.p, d_cnt.p, d_dst.p, n_tiles,
+        sketch_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(u_h1.p, u_pos.p, u_ctg.p, d_off.p, d_cnt.p, d_dst.p, n_slots,
                                                              mx->h1.p, mx->pos.p, mx->contig.p);
         ctx->launches++;
         NTS_CUDA(cudaGetLastError());

@@ -17,8 +17,7 @@ namespace nts {
 __device__ __forceinline__ void stage_tables_bin(HashTables* s_tabs, const HashTables* __restrict__ g_tabs, uint32_t k)
 {
     for (uint32_t i = threadIdx.x; i < 16; i += blockDim.x) {
-        s_tabs->roll_f[i] = g_tabs->roll_f[i];
-        s_tabs->roll_r[i] = g_tabs->roll_r[i];
+        s_tabs->roll[i] = g_tabs->roll[i];
     }
     for (uint32_t i = threadIdx.x; i < k * 4; i += blockDim.x) {
         s_tabs->init_f[i] = g_tabs->init_f[i];

@@ -49,8 +49,9 @@ __host__ __device__ __forceinline__ uint64_t ext_hash(uint64_t h0, unsigned i, u
 // Hash constants for one k, built on the host (nts_api.cu: make_hash_tables) and staged into
 // shared memory by every kernel that hashes.
 struct HashTables {
-    uint64_t roll_f[16];          // [in*4+out] = seed[in] ^ srol^k(seed[out])
-    uint64_t roll_r[16];          // [in*4+out] = seed[3-out] ^ srol^k(seed[3-in])
+    // [in*4+out] = { f.lo, f.hi, r.lo, r.hi }: f = seed[in] ^ srol^k(seed[out]), r = seed[3-out] ^ srol^k(seed[3-in]);
+    // one 16-byte entry per (in,out) pair so that a roll step costs a single LDS.128
+    uint4 roll[16];
     uint64_t init_f[MAX_K * 4];   // [i*4+c] = srol^(k-1-i)(seed[c])
     uint64_t init_r[MAX_K * 4];   // [i*4+c] = srol^i(seed[3-c])
 };
@@ -91,21 +92,44 @@ __device__ __forceinline__ unsigned base_at(const uint64_t* __restrict__ packed,
     return (unsigned)((__ldg(&packed[b >> 5]) >> ((b & 31) * 2)) & 3ull);
 }
 
+// split rotates on a 64-bit value held as two 32-bit registers (the SM's datapath is 32 bits wide)
+__device__ __forceinline__ void srol32(uint32_t& lo, uint32_t& hi)
+{
+    const uint32_t f = __funnelshift_l(lo, hi, 1);       // (hi << 1) | (lo >> 31)
+    const uint32_t nlo = (lo << 1) | (hi & 1u);           // bit 32 -> bit 0
+    hi = (f & ~2u) | ((hi >> 30) & 2u);                   // bit 63 -> bit 33
+    lo = nlo;
+}
+
+__device__ __forceinline__ void sror32(uint32_t& lo, uint32_t& hi)
+{
+    const uint32_t nlo = __funnelshift_r(lo, hi, 1);      // (lo >> 1) | (hi << 31)
+    hi = ((hi >> 1) & ~1u) | (lo & 1u) | ((hi & 2u) << 30);   // bit 0 -> bit 32, bit 33 -> bit 63
+    lo = nlo;
+}
+
 // Rolling ntHash2 over a run of consecutive valid indices [v, v + count).  For every k-mer calls
 // f(j, h0, base) with j = 0..count-1 (run-local index) and base = global base index of the k-mer.
 // Re-seeds itself at island boundaries.  `tabs` must point to shared memory.
+//
+// Inner loop: the leaving and the entering base streams are read as unaligned 32-bit groups (16 bases
+// each, one funnel shift per group), merged into two words whose nibbles are the (in,out) table indices
+// of the even / odd steps, and 16 roll steps are unrolled with static shifts: per k-mer one LDS.128,
+// two 5-instruction split rotates, four XORs and a 64-bit add.
 template <typename F>
 __device__ __forceinline__ void hash_run(const GenomeView& g, const HashTables* tabs, uint64_t v, uint32_t count, F&& f)
 {
     if (count == 0) return;
     const uint32_t k = g.k;
+    const uint32_t* __restrict__ p32 = reinterpret_cast<const uint32_t*>(g.packed);
+    const char* roll = reinterpret_cast<const char*>(tabs->roll);
     uint32_t s = find_island(g, v);
     uint32_t j = 0;
     while (j < count) {
         const uint64_t sv0 = __ldg(&g.seg_v[s]);
         const uint64_t sv1 = __ldg(&g.seg_v[s + 1]);
-        uint64_t b = __ldg(&g.seg_base[s]) + (v + j - sv0);   // base index of current k-mer
-        uint32_t n_here = (uint32_t)min((uint64_t)(count - j), sv1 - (v + j));
+        const uint64_t b = __ldg(&g.seg_base[s]) + (v + j - sv0);   // base index of the piece's first k-mer
+        const uint32_t n_here = (uint32_t)min((uint64_t)(count - j), sv1 - (v + j));
         // seed: XOR of per-position tables over the k bases of the first k-mer
         uint64_t fwd = 0, rev = 0;
         {
@@ -121,22 +145,48 @@ __device__ __forceinline__ void hash_run(const GenomeView& g, const HashTables* 
             }
         }
         f(j, fwd + rev, b);
-        // cursors: `out` = base leaving (b), `in` = base entering (b + k)
-        uint64_t wo = b >> 5, wn = (b + k) >> 5;
-        uint32_t so = (uint32_t)(b & 31) * 2, sn = (uint32_t)((b + k) & 31) * 2;
-        uint64_t word_o = __ldg(&g.packed[wo]);
-        uint64_t word_n = (n_here > 1) ? __ldg(&g.packed[wn]) : 0;
-        for (uint32_t t = 1; t < n_here; ++t) {
-            unsigned cout = (unsigned)(word_o >> so) & 3u;
-            unsigned cin = (unsigned)(word_n >> sn) & 3u;
-            unsigned idx = cin * 4 + cout;
-            fwd = srol(fwd) ^ tabs->roll_f[idx];
-            rev = sror(rev ^ tabs->roll_r[idx]);
-            ++b;
-            f(j + t, fwd + rev, b);
-            so += 2; sn += 2;
-            if (so == 64) { so = 0; word_o = __ldg(&g.packed[++wo]); }
-            if (sn == 64) { sn = 0; if (t + 1 < n_here) word_n = __ldg(&g.packed[++wn]); }
+        if (n_here > 1) {
+            uint32_t flo = (uint32_t)fwd, fhi = (uint32_t)(fwd >> 32), rlo = (uint32_t)rev, rhi = (uint32_t)(rev >> 32);
+            // step t (1-based) drops base b + t - 1 and takes in base b + t - 1 + k
+            const uint64_t ob = b * 2, ib = (b + k) * 2;
+            uint32_t ow = (uint32_t)(ob >> 5), iw = (uint32_t)(ib >> 5);
+            const uint32_t os = (uint32_t)ob & 31u, is = (uint32_t)ib & 31u;
+            uint32_t o_lo = __ldg(p32 + ow), i_lo = __ldg(p32 + iw);
+            auto step = [&](uint32_t nib) {
+                const uint4 e = *reinterpret_cast<const uint4*>(roll + nib);     // nib = table index * 16
+                srol32(flo, fhi);
+                flo ^= e.x; fhi ^= e.y;
+                rlo ^= e.z; rhi ^= e.w;
+                sror32(rlo, rhi);
+                uint32_t hl, hh;                                                  // h0 = fwd + rev
+                asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(hl), "=r"(hh) : "r"(flo), "r"(fhi), "r"(rlo), "r"(rhi));
+                return ((uint64_t)hh << 32) | hl;
+            };
+            for (uint32_t t = 1; t < n_here; t += 16) {
+                const uint32_t o_hi = __ldg(p32 + ow + 1), i_hi = __ldg(p32 + iw + 1);
+                const uint32_t O = __funnelshift_r(o_lo, o_hi, os), I = __funnelshift_r(i_lo, i_hi, is);
+                o_lo = o_hi; i_lo = i_hi; ++ow; ++iw;
+                const uint32_t E = ((I << 2) & 0xCCCCCCCCu) | (O & 0x33333333u);     // nibble q: step 2q
+                const uint32_t D = (I & 0xCCCCCCCCu) | ((O >> 2) & 0x33333333u);     // nibble q: step 2q + 1
+                const uint32_t left = n_here - t;
+                if (left >= 16) {
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t src = (u & 1) ? D : E;
+                        const int q = u >> 1;
+                        const uint32_t nib = (q == 0 ? (src << 4) : (src >> (4 * q - 4))) & 0xF0u;
+                        const uint64_t h = step(nib);
+                        f(j + t + u, h, b + t + u);
+                    }
+                } else {
+                    for (uint32_t u = 0; u < left; ++u) {
+                        const uint32_t src = (u & 1) ? D : E;
+                        const uint32_t nib = ((src >> (4 * (u >> 1))) & 15u) << 4;
+                        const uint64_t h = step(nib);
+                        f(j + t + u, h, b + t + u);
+                    }
+                }
+            }
         }
         j += n_here;
         ++s;

@@ -71,6 +71,7 @@ struct nts_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
+    uint64_t sketch_escalated = 0;   // dense sub-tiles the sparse sketch kernel handed to the dense one (statistics)
     int sm_count = 148;
     std::map<uint32_t, nts::HashTables*> tables;   // per k, device resident
 };

@@ -62,8 +62,7 @@ __device__ __forceinline__ void stage_tables(HashTables* s_tabs, const HashTable
 {
     // roll tables (32 words) + the first k rows of the init tables
     for (uint32_t i = threadIdx.x; i < 16; i += blockDim.x) {
-        s_tabs->roll_f[i] = g_tabs->roll_f[i];
-        s_tabs->roll_r[i] = g_tabs->roll_r[i];
+        s_tabs->roll[i] = g_tabs->roll[i];
     }
     for (uint32_t i = threadIdx.x; i < k * 4; i += blockDim.x) {
         s_tabs->init_f[i] = g_tabs->init_f[i];
@@ -141,6 +140,8 @@ struct TileDesc {
     uint64_t cbase;      // global base index of the contig's first base
     uint32_t contig;
     uint32_t has_prev;   // 0 for the first tile of a contig (slot 0 is a dummy)
+    uint32_t out_slot;   // where the tile's run is recorded in tile_off / tile_cnt (tile order of the output)
+    uint32_t n_sub;      // sparse tiles: number of dense tiles (and output slots) the tile stands for
 };
 
 struct SketchOut {
@@ -237,11 +238,11 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t NT = T + w;
     const uint32_t C = (NT + THREADS - 1) / THREADS;   // slots per thread (contiguous)
-    uint64_t* s_key = reinterpret_cast<uint64_t*>(smem_raw);
+    HashTables* s_tabs = reinterpret_cast<HashTables*>(smem_raw);          // first: its uint4 rows need 16-byte alignment
+    uint64_t* s_key = reinterpret_cast<uint64_t*>(s_tabs + 1);
     uint16_t* s_P = reinterpret_cast<uint16_t*>(s_key + NT);
     uint16_t* s_S = s_P + ((NT + 3) & ~3u);
-    HashTables* s_tabs = reinterpret_cast<HashTables*>(s_S + ((NT + 3) & ~3u));
-    SegAgg* s_warp = reinterpret_cast<SegAgg*>(s_tabs + 1);
+    SegAgg* s_warp = reinterpret_cast<SegAgg*>(s_S + ((NT + 3) & ~3u));
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_warp + THREADS / 32);   // [THREADS/32 + 2]
 
     const TileDesc td = tiles[blockIdx.x];
@@ -450,8 +451,8 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
             // one allocation per tile in the unordered buffer
             unsigned long long base = atomicAdd(out.total, (unsigned long long)v);
             s_misc[THREADS / 32] = (base + v <= out.cap) ? (uint32_t)base : 0xFFFFFFFFu;
-            out.tile_off[blockIdx.x] = (uint32_t)base;
-            out.tile_cnt[blockIdx.x] = v;
+            out.tile_off[td.out_slot] = (uint32_t)base;
+            out.tile_cnt[td.out_slot] = v;
         }
     }
     __syncthreads();
@@ -473,6 +474,201 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
             }
             prev = a;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------ (ii) sketch, sparse form
+// The same selection as sketch_kernel, for tiles several times larger, without keeping every key in shared
+// memory.  Only slots whose hash is below tau = tau_hi * 2^32 ("candidates", a few per cent) can be the minimum
+// of a window that holds at least one candidate passing the filter, so:
+//   A  hash every slot (kernel i); a thread stages its few candidates (key, slot) in its own column;
+//   B  ordered compaction of the columns into one slot-sorted candidate list; Bloom query (iii-c) of the
+//      candidates only, all of a thread's sector loads in flight together; failures become UINT64_MAX;
+//   C  a candidate c at slot p is the rightmost minimum of some window iff no survivor with a smaller key lies
+//      in (p - w, p) closer than ... precisely: with L = nearest survivor to the left with key < key_c and
+//      e = max(p, L + w) the end of the first window that can elect c, c is elected iff no survivor with
+//      key <= key_c lies in (p, e].  It is this tile's to emit iff w <= e < n_end (window ends are
+//      partitioned between tiles).  Both scans touch a handful of neighbours.
+//   D  ordered compaction of the elected candidates into the unordered output buffer.
+// Exactness needs every window of the tile (and the one before its first) to hold a survivor: gaps between
+// consecutive survivors are checked, and a tile with an unresolved window (or a staging overflow) hands its
+// `n_sub` dense sub-tiles to sketch_kernel through the escalation list instead of emitting anything.
+template <int THREADS, int SCAP, int CCAP>
+__global__ void __launch_bounds__(THREADS, 2)
+sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
+                     const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, const TileDesc* __restrict__ tiles,
+                     uint32_t w, uint32_t NT, uint32_t C, uint32_t T_dense, uint32_t tau_hi, SketchOut out,
+                     TileDesc* __restrict__ esc, unsigned int* __restrict__ esc_count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HashTables* s_tabs = reinterpret_cast<HashTables*>(smem_raw);
+    uint64_t* s_skey = reinterpret_cast<uint64_t*>(s_tabs + 1);            // [SCAP][THREADS] staged keys, column per thread
+    uint64_t* c_key = s_skey + (size_t)SCAP * THREADS;                     // [CCAP] candidate keys in slot order
+    uint16_t* c_slot = reinterpret_cast<uint16_t*>(c_key + CCAP);          // [CCAP]
+    uint8_t* s_sj = reinterpret_cast<uint8_t*>(c_slot + CCAP);             // [SCAP][THREADS] staged slot offsets
+    __shared__ uint32_t s_wsum[THREADS / 32];
+    __shared__ uint32_t s_bcast[2];
+
+    const TileDesc td = tiles[blockIdx.x];
+    stage_tables(s_tabs, g_tabs, g.k);
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t vbase = td.vfirst - 1;
+    const uint32_t i_lo = td.has_prev ? 0u : 1u;
+    const uint64_t avail = td.vend - td.vfirst + 1;
+    const uint32_t n_end = (uint32_t)min((uint64_t)NT, avail);
+
+    // CTA-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = sum
+    auto cta_scan = [&](uint32_t val, uint32_t* total) -> uint32_t {
+        uint32_t incl = val;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        __syncthreads();                       // s_wsum may still be read from the previous scan
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        uint32_t woff = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; ++i) { const uint32_t x = s_wsum[i]; if (i < wid) woff += x; tot += x; }
+        *total = tot;
+        return woff + incl - val;
+    };
+
+    // ---- phase A: hash, stage the candidates
+    const uint32_t c0 = tid * C;
+    uint32_t n_st = 0;
+    {
+        const uint32_t a = max(c0, i_lo), b = min(c0 + C, n_end);
+        if (a < b) {
+            const uint32_t j0 = a - c0;
+            hash_run(g, s_tabs, vbase + a, b - a, [&](uint32_t j, uint64_t h0, uint64_t) {
+                if ((uint32_t)(h0 >> 32) < tau_hi) {
+                    if (n_st < SCAP) {
+                        s_skey[n_st * THREADS + tid] = h0;
+                        s_sj[n_st * THREADS + tid] = (uint8_t)(j0 + j);
+                    }
+                    ++n_st;
+                }
+            });
+        }
+    }
+    int bad = n_st > SCAP;                     // staging overflow: escalate
+    const uint32_t n_mine = min(n_st, (uint32_t)SCAP);
+    uint32_t ncand = 0;
+    const uint32_t off = cta_scan(n_mine, &ncand);
+    if (ncand > CCAP) { bad = 1; ncand = 0; }
+    else
+        for (uint32_t i = 0; i < n_mine; ++i) {
+            c_key[off + i] = s_skey[i * THREADS + tid];
+            c_slot[off + i] = (uint16_t)(c0 + s_sj[i * THREADS + tid]);
+        }
+    __syncthreads();
+
+    // ---- phase B: Bloom query of the candidates (kernel iii-c)
+    if ((common != nullptr || repeat != nullptr) && ncand) {
+        constexpr int PER = (CCAP + THREADS - 1) / THREADS;
+        uint32_t cw[PER], rw[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const uint32_t i = tid + u * THREADS;
+            cw[u] = 0xFFFFFFFFu; rw[u] = 0;
+            if (i < ncand) {
+                const uint64_t idx = fast_mod(c_key[i], m, mprime);
+                if (common) cw[u] = __ldg(&common[idx >> 5]) >> (idx & 31);
+                if (repeat) rw[u] = __ldg(&repeat[idx >> 5]) >> (idx & 31);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const uint32_t i = tid + u * THREADS;
+            if (i < ncand && (!(cw[u] & 1u) || (rw[u] & 1u))) c_key[i] = KEY_MAX;
+        }
+        __syncthreads();
+    }
+
+    // ---- phase C: which candidates are elected, and is every window resolved
+    const uint32_t q = (ncand + THREADS - 1) / THREADS;      // candidates per thread (contiguous share)
+    const uint32_t i0 = min((uint32_t)tid * q, ncand), i1 = min(i0 + q, ncand);
+    uint32_t emit_mask = 0, n_emit = 0;
+    const int e_lo = td.has_prev ? (int)w - 1 : (int)w;      // end of the first window that must be resolved
+    for (uint32_t i = i0; i < i1; ++i) {
+        const uint64_t key = c_key[i];
+        if (key == KEY_MAX) continue;
+        const int p = c_slot[i];
+        // previous survivor: the gap must not leave a window without one
+        {
+            int j = (int)i - 1;
+            while (j >= 0 && c_key[j] == KEY_MAX) --j;
+            const int prev_p = j >= 0 ? (int)c_slot[j] : e_lo - (int)w;
+            if (p - prev_p > (int)w) bad = 1;
+        }
+        // nearest strictly smaller survivor on the left, within reach of a window
+        int e = p;
+        for (int j = (int)i - 1; j >= 0; --j) {
+            const int pj = c_slot[j];
+            if (p - pj >= (int)w) break;
+            if (c_key[j] < key) { e = pj + (int)w; break; }
+        }
+        if (e < (int)w) {
+            if (td.has_prev) continue;             // elected by a window of the previous tile
+            e = (int)w;                            // the contig's first window
+        }
+        if (e >= (int)n_end) continue;             // the next tile's (or no window at all)
+        bool ok = true;
+        for (uint32_t j = i + 1; j < ncand; ++j) {
+            if ((int)c_slot[j] > e) break;
+            if (c_key[j] <= key) { ok = false; break; }
+        }
+        if (ok) { emit_mask |= 1u << (i - i0); ++n_emit; }
+    }
+    if (tid == 0 && !bad) {                        // the last window needs a survivor too
+        int j = (int)ncand - 1;
+        while (j >= 0 && c_key[j] == KEY_MAX) --j;
+        const int last_p = j >= 0 ? (int)c_slot[j] : e_lo - (int)w;
+        if ((int)n_end - last_p > (int)w) bad = 1;
+    }
+    if (q > 32) bad = 1;                           // cannot happen (CCAP / THREADS <= 32); keeps emit_mask honest
+    if (__syncthreads_or(bad)) {
+        // hand the tile's dense sub-tiles to sketch_kernel
+        if (tid == 0) s_bcast[0] = atomicAdd(esc_count, td.n_sub);
+        __syncthreads();
+        const uint32_t base = s_bcast[0];
+        if ((uint32_t)tid < td.n_sub) {
+            TileDesc d;
+            d.vfirst = td.vfirst + (uint64_t)tid * T_dense;
+            d.vend = td.vend; d.cbase = td.cbase; d.contig = td.contig;
+            d.has_prev = (td.has_prev || tid > 0) ? 1u : 0u;
+            d.out_slot = td.out_slot + tid; d.n_sub = 1;
+            esc[base + tid] = d;
+            out.tile_off[td.out_slot + tid] = 0;
+            out.tile_cnt[td.out_slot + tid] = 0;
+        }
+        return;
+    }
+
+    // ---- phase D: ordered compaction of the elected candidates
+    uint32_t total = 0;
+    const uint32_t eoff = cta_scan(n_emit, &total);
+    if (tid == 0) {
+        unsigned long long base = atomicAdd(out.total, (unsigned long long)total);
+        s_bcast[1] = (base + total <= out.cap) ? (uint32_t)base : 0xFFFFFFFFu;
+        out.tile_off[td.out_slot] = (uint32_t)base;
+        out.tile_cnt[td.out_slot] = total;
+    }
+    if (tid >= 1 && (uint32_t)tid < td.n_sub) { out.tile_off[td.out_slot + tid] = 0; out.tile_cnt[td.out_slot + tid] = 0; }
+    __syncthreads();
+    const uint32_t tile_base = s_bcast[1];
+    if (tile_base == 0xFFFFFFFFu || n_emit == 0) return;    // overflow: host re-runs with a larger buffer
+    uint32_t o = tile_base + eoff;
+    for (uint32_t i = i0; i < i1; ++i) {
+        if (!((emit_mask >> (i - i0)) & 1u)) continue;
+        const uint64_t b = valid_to_base(g, vbase + c_slot[i]);
+        out.h1[o] = ext_hash(c_key[i], 1, g.k);
+        out.pos[o] = (uint32_t)(b - td.cbase);
+        out.contig[o] = td.contig;
+        ++o;
     }
 }
 

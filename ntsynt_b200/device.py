@@ -51,6 +51,11 @@ class Context:
     def launches(self):
         return int(lib.nts_launch_count(self._h))
 
+    @property
+    def sketch_escalated(self):
+        "dense sub-tiles the sparse sketch kernel handed to the dense selector so far (statistics)"
+        return int(lib.nts_sketch_escalated(self._h))
+
     def mem_info(self):
         f, t = C.c_uint64(), C.c_uint64()
         check(lib.nts_mem_info(self._h, C.byref(f), C.byref(t)))

@@ -265,3 +265,37 @@ def test_full_size_properties(cuda_ctx):
     sel = (ctg == 3) & (pos < 400000 - 2 * w)
     n = int(sel.sum())
     assert n > 100 and np.array_equal(h1[sel], oh1[:n]) and np.array_equal(pos[sel].astype(np.uint64), opos[:n])
+
+
+@pytest.mark.parametrize("w", [128, 500, 1000, 4000])
+def test_sparse_and_dense_sketch_kernels_agree(cuda_ctx, w):
+    """sketch_sparse_kernel (candidates below a hash threshold + nearest-smaller scans, escalating unresolved
+    tiles) against sketch_kernel (van Herk over every slot) on 2 x 40 Mbp; also a thinned filter that leaves
+    windows without any survivor, which must take the escalation path"""
+    k = 24
+    wl = synth.Workload(2, 40_000_000, 1.0)
+    gens = [wl.materialize(cuda_ctx, g) for g in range(2)]
+    nbytes = device.BloomFilter.size_for(gens[0].total_bases, 0.025)
+    a, b = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
+    a.insert_genome(gens[0], k); b.insert_genome(gens[1], k)
+    a.iand(b)
+    thin = a.to_numpy().copy()
+    thin[len(thin) // 16:] = 0                       # 15/16 of the hash space never passes: many windows without a survivor
+    thin_bf = cuda_ctx.bloom(nbytes).from_numpy(thin)
+    for bf, must_escalate in ((a, False), (thin_bf, True), (None, False)):
+        e0 = cuda_ctx.sketch_escalated
+        sparse = [x.copy() for x in cuda_ctx.sketch(gens[1], k, w, common=bf).to_numpy()]
+        esc = cuda_ctx.sketch_escalated - e0
+        os.environ["NTS_SKETCH_DENSE"] = "1"
+        try:
+            dense = cuda_ctx.sketch(gens[1], k, w, common=bf).to_numpy()
+        finally:
+            del os.environ["NTS_SKETCH_DENSE"]
+        assert len(sparse[0]) > 0
+        for x, y in zip(sparse, dense):
+            assert np.array_equal(x, y)
+        if must_escalate:
+            assert esc > 0
+        elif bf is a and w >= 500:
+            n_tiles_dense = gens[1].total_bases / (8960 - w)
+            assert esc < 0.02 * n_tiles_dense        # the sparse kernel did the work
