@@ -51,6 +51,7 @@ int bf_insert_partitioned(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const 
         const uint64_t bits_b = std::min<uint64_t>(1ull << shift, m - ((uint64_t)b << shift));
         const double expect = (double)total_valid * (double)bits_b / (double)m;
         uint64_t c = (uint64_t)(expect * 1.02 + 6.0 * std::sqrt(expect) + 4096.0);
+        c = (c + 3) & ~3ull;                               // 16-byte aligned buckets (bf_apply_kernel loads uint4)
         if (c > 0xFFFFFFF0ull) return NTS_OK;
         cap[b] = (uint32_t)c;
         off[b + 1] = off[b] + c;

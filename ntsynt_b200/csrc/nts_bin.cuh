@@ -122,11 +122,13 @@ __global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const 
 }
 
 // pass 2: CTA c applies chunk c of the concatenated buckets; chunks are in region order, so the CTAs
-// resident at any moment touch one or two regions and their RED.ORs hit in L2
-__global__ void bf_apply_kernel(const uint32_t* __restrict__ items, const uint64_t* __restrict__ bucket_off,
+// resident at any moment touch one or two regions and their RED.ORs hit in L2.  A chunk is 4096 items =
+// 256 threads x 4 independent 128-bit loads, all in flight before the first RED is issued (bucket offsets
+// are multiples of 4 items, so the loads are aligned).
+__global__ void __launch_bounds__(256) bf_apply_kernel(const uint32_t* __restrict__ items, const uint64_t* __restrict__ bucket_off,
                                 const uint32_t* __restrict__ bucket_cap, const unsigned int* __restrict__ cursor,
                                 const uint64_t* __restrict__ chunk_first /*[P+1] first chunk id of each bucket*/,
-                                uint32_t n_buckets, uint32_t region_shift, uint32_t chunk_items,
+                                uint32_t n_buckets, uint32_t region_shift, uint32_t chunk_items /* = 4096 */,
                                 uint32_t* __restrict__ bits)
 {
     uint32_t lo = 0, hi = n_buckets;          // bucket of this chunk: last b with chunk_first[b] <= blockIdx.x
@@ -141,7 +143,26 @@ __global__ void bf_apply_kernel(const uint32_t* __restrict__ items, const uint64
     const uint32_t cnt = (uint32_t)min((uint64_t)chunk_items, n - start);
     const uint32_t* src = items + bucket_off[b] + start;
     uint32_t* region = bits + (((uint64_t)b << region_shift) >> 5);
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);
+    const uint32_t n4 = cnt >> 2;
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t i = threadIdx.x + u * 256;
+        if (i < n4) v[u] = __ldg(src4 + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t i = threadIdx.x + u * 256;
+        if (i < n4) {
+            atomicOr(&region[v[u].x >> 5], 1u << (v[u].x & 31));
+            atomicOr(&region[v[u].y >> 5], 1u << (v[u].y & 31));
+            atomicOr(&region[v[u].z >> 5], 1u << (v[u].z & 31));
+            atomicOr(&region[v[u].w >> 5], 1u << (v[u].w & 31));
+        }
+    }
+    const uint32_t i = (n4 << 2) + threadIdx.x;           // up to 3 leftover items
+    if (i < cnt) {
         const uint32_t x = __ldg(&src[i]);
         atomicOr(&region[x >> 5], 1u << (x & 31));
     }

@@ -484,11 +484,9 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
 //   A  hash every slot (kernel i); a thread stages its few candidates (key, slot) in its own column;
 //   B  ordered compaction of the columns into one slot-sorted candidate list; Bloom query (iii-c) of the
 //      candidates only, all of a thread's sector loads in flight together; failures become UINT64_MAX;
-//   C  a candidate c at slot p is the rightmost minimum of some window iff no survivor with a smaller key lies
-//      in (p - w, p) closer than ... precisely: with L = nearest survivor to the left with key < key_c and
-//      e = max(p, L + w) the end of the first window that can elect c, c is elected iff no survivor with
-//      key <= key_c lies in (p, e].  It is this tile's to emit iff w <= e < n_end (window ends are
-//      partitioned between tiles).  Both scans touch a handful of neighbours.
+//   C  every thread slides over a contiguous share of the window ends, jumping between the only events that
+//      can change the minimum (a candidate enters; the current minimum leaves -> rescan of ~tau*w survivors),
+//      and marks a candidate the first time it becomes a window's rightmost minimum;
 //   D  ordered compaction of the elected candidates into the unordered output buffer.
 // Exactness needs every window of the tile (and the one before its first) to hold a survivor: gaps between
 // consecutive survivors are checked, and a tile with an unresolved window (or a staging overflow) hands its
@@ -588,48 +586,25 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
         __syncthreads();
     }
 
-    // ---- phase C: which candidates are elected, and is every window resolved
+    // ---- phase C1: is every window resolved?  (gaps between consecutive survivors, first and last window)
     const uint32_t q = (ncand + THREADS - 1) / THREADS;      // candidates per thread (contiguous share)
     const uint32_t i0 = min((uint32_t)tid * q, ncand), i1 = min(i0 + q, ncand);
-    uint32_t emit_mask = 0, n_emit = 0;
     const int e_lo = td.has_prev ? (int)w - 1 : (int)w;      // end of the first window that must be resolved
+    uint8_t* c_flag = s_sj;                                  // [CCAP] elected marks (the staging columns are dead)
     for (uint32_t i = i0; i < i1; ++i) {
-        const uint64_t key = c_key[i];
-        if (key == KEY_MAX) continue;
-        const int p = c_slot[i];
-        // previous survivor: the gap must not leave a window without one
-        {
-            int j = (int)i - 1;
-            while (j >= 0 && c_key[j] == KEY_MAX) --j;
-            const int prev_p = j >= 0 ? (int)c_slot[j] : e_lo - (int)w;
-            if (p - prev_p > (int)w) bad = 1;
-        }
-        // nearest strictly smaller survivor on the left, within reach of a window
-        int e = p;
-        for (int j = (int)i - 1; j >= 0; --j) {
-            const int pj = c_slot[j];
-            if (p - pj >= (int)w) break;
-            if (c_key[j] < key) { e = pj + (int)w; break; }
-        }
-        if (e < (int)w) {
-            if (td.has_prev) continue;             // elected by a window of the previous tile
-            e = (int)w;                            // the contig's first window
-        }
-        if (e >= (int)n_end) continue;             // the next tile's (or no window at all)
-        bool ok = true;
-        for (uint32_t j = i + 1; j < ncand; ++j) {
-            if ((int)c_slot[j] > e) break;
-            if (c_key[j] <= key) { ok = false; break; }
-        }
-        if (ok) { emit_mask |= 1u << (i - i0); ++n_emit; }
+        c_flag[i] = 0;
+        if (c_key[i] == KEY_MAX) continue;
+        int j = (int)i - 1;
+        while (j >= 0 && c_key[j] == KEY_MAX) --j;
+        const int prev_p = j >= 0 ? (int)c_slot[j] : e_lo - (int)w;
+        if ((int)c_slot[i] - prev_p > (int)w) bad = 1;
     }
-    if (tid == 0 && !bad) {                        // the last window needs a survivor too
+    if (tid == 0 && !bad) {
         int j = (int)ncand - 1;
         while (j >= 0 && c_key[j] == KEY_MAX) --j;
         const int last_p = j >= 0 ? (int)c_slot[j] : e_lo - (int)w;
         if ((int)n_end - last_p > (int)w) bad = 1;
     }
-    if (q > 32) bad = 1;                           // cannot happen (CCAP / THREADS <= 32); keeps emit_mask honest
     if (__syncthreads_or(bad)) {
         // hand the tile's dense sub-tiles to sketch_kernel
         if (tid == 0) s_bcast[0] = atomicAdd(esc_count, td.n_sub);
@@ -648,7 +623,63 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
         return;
     }
 
+    // ---- phase C2: every thread slides over its share of the window ends.  The window minimum can only change
+    // when a candidate enters (its slot becomes the window end) or when the current minimum leaves, so the
+    // thread jumps from event to event; a candidate is marked the first time it becomes the minimum.
+    {
+        const uint32_t n_own = n_end > w ? n_end - w : 0;
+        const uint32_t per = (n_own + THREADS - 1) / THREADS;
+        const uint32_t e0 = w + tid * per, e1 = min(e0 + per, n_end);
+        // first candidate index with slot >= x
+        auto lower = [&](uint32_t x) -> uint32_t {
+            uint32_t lo = 0, hi = ncand;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (c_slot[mid] < x) lo = mid + 1; else hi = mid; }
+            return lo;
+        };
+        // rightmost minimum among the survivors with slot in [a, b]; `from` = lower(a); -1 if none; *past = first index beyond b
+        auto scan = [&](uint32_t from, uint32_t b, uint32_t* past) -> int {
+            int best = -1;
+            uint64_t bk = KEY_MAX;
+            uint32_t i = from;
+            for (; i < ncand && c_slot[i] <= b; ++i) {
+                const uint64_t kx = c_key[i];
+                if (kx != KEY_MAX && kx <= bk) { bk = kx; best = (int)i; }
+            }
+            *past = i;
+            return best;
+        };
+        if (e0 < e1) {
+            int cur;
+            uint32_t nxt;                                    // next candidate (by index) that has not entered yet
+            if (e0 > w || td.has_prev) {
+                cur = scan(lower(e0 - w), e0 - 1, &nxt);     // the window before the first owned one: already emitted
+            } else {
+                cur = scan(lower(1), e0, &nxt);              // the contig's first window
+                if (cur >= 0) c_flag[cur] = 1;
+            }
+            for (;;) {
+                const uint32_t e_in = nxt < ncand ? (uint32_t)c_slot[nxt] : 0xFFFFFFFFu;
+                const uint32_t e_out = cur >= 0 ? (uint32_t)c_slot[cur] + w : 0xFFFFFFFFu;
+                const uint32_t e = min(e_in, e_out);
+                if (e >= e1) break;
+                int neu;
+                if (e_out <= e_in) {
+                    neu = scan(lower(e + 1 - w), e, &nxt);   // the minimum left: look at the whole window again
+                } else {
+                    const uint64_t kx = c_key[nxt];
+                    neu = (kx != KEY_MAX && (cur < 0 || kx <= c_key[cur])) ? (int)nxt : cur;
+                    ++nxt;
+                }
+                if (neu != cur && neu >= 0) c_flag[neu] = 1;
+                cur = neu;
+            }
+        }
+    }
+    __syncthreads();
+
     // ---- phase D: ordered compaction of the elected candidates
+    uint32_t n_emit = 0;
+    for (uint32_t i = i0; i < i1; ++i) n_emit += c_flag[i];
     uint32_t total = 0;
     const uint32_t eoff = cta_scan(n_emit, &total);
     if (tid == 0) {
@@ -663,7 +694,7 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
     if (tile_base == 0xFFFFFFFFu || n_emit == 0) return;    // overflow: host re-runs with a larger buffer
     uint32_t o = tile_base + eoff;
     for (uint32_t i = i0; i < i1; ++i) {
-        if (!((emit_mask >> (i - i0)) & 1u)) continue;
+        if (!c_flag[i]) continue;
         const uint64_t b = valid_to_base(g, vbase + c_slot[i]);
         out.h1[o] = ext_hash(c_key[i], 1, g.k);
         out.pos[o] = (uint32_t)(b - td.cbase);
