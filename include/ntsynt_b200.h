@@ -226,6 +226,17 @@ int nts_graph_download_links(nts_graph* g, uint32_t* inv, uint32_t* incmask, uin
 /* prefix sums of the direction bits (device scans): ci, cd are [n_asm*(V+1)], assembly-major;
  * ci[a*(V+1)+i] = number of pairs (j, j+1), j < i, whose position increases in assembly a (cd: decreases) */
 int nts_graph_download_cums(nts_graph* g, uint32_t* ci, uint32_t* cd);
+/* Host-ready columns for the graph stage, with room to grow: `cap` >= V is the row pitch (in elements) of
+ * pos64 / ctg32 and the length of h1 / nbr / conn; only the first V entries of each row are written.
+ * pos64 = positions widened to int64; nbr[v] = (left, right) neighbour of v in the weight-filtered graph
+ * (subprojects/ntJoin/bin/ntjoin.py:78-87) or -1; conn[i] = 1 iff edge (i, i+1) has full weight. */
+int nts_graph_download_host_arrays(nts_graph* g, uint64_t cap, uint64_t* h1, long long* pos64, int32_t* ctg32, int32_t* nbr,
+                                   uint8_t* conn);
+/* Sparse views of the vertex table, each sorted ascending: breaks = i < V-1 without a full-weight edge (i, i+1);
+ * deg3 = vertices with exactly 3 distinct neighbours (candidates of run_graph_simplification,
+ * bin/ntsynt_synteny.py:566-590); big = i whose pair (i, i+1) spreads by more than bp (check_for_indels,
+ * bin/ntsynt_synteny.py:364-409).  Pass NULL pointers to get the counts first. */
+int nts_graph_sparse_lists(nts_graph* g, uint32_t bp, uint32_t* breaks, uint32_t* deg3, uint32_t* big, uint64_t counts[3]);
 /* vertex id of each h1 (0xFFFFFFFF if none) via the join table kept on the device
  * (replaces `mx in mx_info` / graph.vs.find(name) lookups of the refinement rounds) */
 int nts_graph_lookup(nts_graph* g, const uint64_t* h1, uint64_t n, uint32_t* vid_out);

@@ -106,6 +106,9 @@ _SIGS = {
     "nts_graph_download_vertices": (C.c_int, [vp, u64p, u32p, u32p, u32p, u8p, u8p]),
     "nts_graph_download_links": (C.c_int, [vp, u32p, u32p, u32p, u32p]),
     "nts_graph_download_cums": (C.c_int, [vp, u32p, u32p]),
+    "nts_graph_download_host_arrays": (C.c_int, [vp, C.c_uint64, u64p, C.POINTER(C.c_longlong), C.POINTER(C.c_int32),
+                                                 C.POINTER(C.c_int32), u8p]),
+    "nts_graph_sparse_lists": (C.c_int, [vp, C.c_uint32, u32p, u32p, u32p, u64p]),
     "nts_graph_lookup": (C.c_int, [vp, u64p, C.c_uint64, u32p]),
     "nts_graph_edges": (C.c_int, [vp, u64p]),
     "nts_graph_download_edges": (C.c_int, [vp, u32p, u32p, u32p]),

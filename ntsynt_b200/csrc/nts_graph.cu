@@ -284,6 +284,34 @@ static int exclusive_scan_u32(nts_ctx* ctx, const uint32_t* in, uint64_t n, uint
     return NTS_OK;
 }
 
+// host-ready columns for the graph stage (ntsynt_b200/synteny.py): positions widened to int64, the
+// weight-filtered graph as nbr[v] = (left, right) neighbour ids or -1
+__global__ void graph_export_kernel(const uint32_t* __restrict__ v_pos, const uint8_t* __restrict__ link, uint64_t V,
+                                    uint32_t n_asm, long long* __restrict__ pos64, int2* __restrict__ nbr)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    for (uint32_t b = 0; b < n_asm; ++b) pos64[(uint64_t)b * V + i] = (long long)v_pos[(uint64_t)b * V + i];
+    const int left = (i > 0 && link[i - 1]) ? (int)(i - 1) : -1;
+    const int right = link[i] ? (int)(i + 1) : -1;
+    nbr[i] = make_int2(left, right);
+}
+
+// the three sparse views the host walks: pairs (i, i+1) without a full-weight link, vertices of degree 3
+// (graph simplification candidates), pairs whose position deltas spread by more than `bp` (indel splits).
+// Unordered appends (the lists are short); the host sorts them.
+__global__ void graph_sparse_lists_kernel(const uint8_t* __restrict__ link, const uint8_t* __restrict__ degree,
+                                          const uint32_t* __restrict__ spread, uint64_t V, uint32_t bp,
+                                          uint32_t* __restrict__ breaks, uint32_t* __restrict__ deg3,
+                                          uint32_t* __restrict__ big, unsigned int* __restrict__ counts, uint32_t cap)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    if (i + 1 < V && !link[i]) { const unsigned int k = atomicAdd(&counts[0], 1u); if (k < cap) breaks[k] = (uint32_t)i; }
+    if (degree[i] == 3) { const unsigned int k = atomicAdd(&counts[1], 1u); if (k < cap) deg3[k] = (uint32_t)i; }
+    if (i + 1 < V && spread[i] > bp) { const unsigned int k = atomicAdd(&counts[2], 1u); if (k < cap) big[k] = (uint32_t)i; }
+}
+
 }  // namespace nts
 
 using namespace nts;
@@ -301,6 +329,11 @@ struct nts_graph {
     DevBuf<unsigned long long> keys;
     DevBuf<uint32_t> slot_vid, slot_ok;
     uint64_t cap = 0;
+    // sparse lists (built lazily, per bp)
+    bool lists_built = false;
+    uint32_t lists_bp = 0;
+    uint64_t n_lists[3] = {0, 0, 0};
+    DevBuf<uint32_t> l_breaks, l_deg3, l_big;
     // edges (built lazily)
     bool edges_built = false;
     uint64_t E = 0;
@@ -485,6 +518,92 @@ int nts_graph_download_cums(nts_graph* g, uint32_t* ci, uint32_t* cd)
             NTS_CUDA(cudaStreamSynchronize(ctx->stream));
             dst[V] = total;
         }
+    return NTS_OK;
+}
+
+
+/* Host-ready columns with room to grow: `cap` >= V is the row pitch (in elements) of pos64 / ctg32 and the
+ * length of h1 / nbr; only the first V entries of each row are written.
+ *   h1[cap] u64, pos64[n_asm x cap] i64, ctg32[n_asm x cap] i32, nbr[cap x 2] i32 (left, right neighbour in
+ *   the weight-filtered graph or -1), conn[cap] u8 (conn[i] = 1 iff edge (i, i+1) has full weight). */
+int nts_graph_download_host_arrays(nts_graph* g, uint64_t cap, uint64_t* h1, long long* pos64, int32_t* ctg32, int32_t* nbr,
+                                   uint8_t* conn)
+{
+    if (!g || !h1 || !pos64 || !ctg32 || !nbr || !conn) return fail(NTS_ERR_ARG, "null argument");
+    const uint64_t V = g->V;
+    if (cap < V) return fail(NTS_ERR_ARG, "cap is smaller than the number of vertices");
+    if (!V) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<long long> d_pos;
+    DevBuf<int2> d_nbr;
+    if (d_pos.alloc(V * g->n_asm) != cudaSuccess || d_nbr.alloc(V) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (export)");
+    {
+        ProfScope prof(ctx, PROF_JOIN, (double)V);
+        graph_export_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(g->v_pos.p, g->link.p, V, g->n_asm, d_pos.p, d_nbr.p);
+        ctx->launches++;
+    }
+    NTS_CUDA(cudaGetLastError());
+    NTS_CUDA(copy_d2h(ctx, h1, g->v_h1.p, V * 8));
+    NTS_CUDA(cudaMemcpy2DAsync(pos64, cap * 8, d_pos.p, V * 8, V * 8, g->n_asm, cudaMemcpyDeviceToHost, ctx->stream));
+    NTS_CUDA(cudaMemcpy2DAsync(ctg32, cap * 4, g->v_ctg.p, V * 4, V * 4, g->n_asm, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->d2h_bytes += V * g->n_asm * 12;
+    NTS_CUDA(copy_d2h(ctx, nbr, d_nbr.p, V * 8));
+    NTS_CUDA(copy_d2h(ctx, conn, g->link.p, V));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+/* Sparse views of the vertex table (each list is returned sorted ascending):
+ *   breaks: i with no full-weight edge (i, i+1), i < V - 1;  deg3: vertices with exactly 3 distinct neighbours;
+ *   big: i whose pair (i, i+1) has max|dpos| - min|dpos| > bp.
+ * Call with the three pointers NULL to get the counts, then with buffers of at least those sizes. */
+int nts_graph_sparse_lists(nts_graph* g, uint32_t bp, uint32_t* breaks, uint32_t* deg3, uint32_t* big, uint64_t counts[3])
+{
+    if (!g || !counts) return fail(NTS_ERR_ARG, "null argument");
+    const uint64_t V = g->V;
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    if (!g->lists_built || g->lists_bp != bp) {
+        g->n_lists[0] = g->n_lists[1] = g->n_lists[2] = 0;
+        if (V) {
+            uint32_t cap = (uint32_t)std::min<uint64_t>(V, 1u << 20);
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                DevBuf<unsigned int> d_counts;
+                if (g->l_breaks.alloc(cap) != cudaSuccess || g->l_deg3.alloc(cap) != cudaSuccess || g->l_big.alloc(cap) != cudaSuccess ||
+                    d_counts.alloc(3) != cudaSuccess)
+                    return fail(NTS_ERR_NOMEM, "device allocation failed (sparse lists)");
+                NTS_CUDA(cudaMemsetAsync(d_counts.p, 0, 12, ctx->stream));
+                {
+                    ProfScope prof(ctx, PROF_JOIN, (double)V);
+                    graph_sparse_lists_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(
+                        g->link.p, g->degree.p, g->spread.p, V, bp, g->l_breaks.p, g->l_deg3.p, g->l_big.p, d_counts.p, cap);
+                    ctx->launches++;
+                }
+                NTS_CUDA(cudaGetLastError());
+                unsigned int h[3] = {0, 0, 0};
+                NTS_CUDA(cudaMemcpyAsync(h, d_counts.p, 12, cudaMemcpyDeviceToHost, ctx->stream));
+                NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+                const unsigned int mx = std::max(h[0], std::max(h[1], h[2]));
+                for (int i = 0; i < 3; ++i) g->n_lists[i] = h[i];
+                if (mx <= cap) break;
+                if (attempt == 1) return fail(NTS_ERR_STATE, "internal error: sparse lists overflow after retry");
+                cap = mx;
+            }
+        }
+        g->lists_built = true; g->lists_bp = bp;
+    }
+    for (int i = 0; i < 3; ++i) counts[i] = g->n_lists[i];
+    uint32_t* dst[3] = {breaks, deg3, big};
+    uint32_t* src[3] = {g->l_breaks.p, g->l_deg3.p, g->l_big.p};
+    bool any = false;
+    for (int i = 0; i < 3; ++i)
+        if (dst[i] && g->n_lists[i]) { NTS_CUDA(copy_d2h(ctx, dst[i], src[i], g->n_lists[i] * 4)); any = true; }
+    if (any) {
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < 3; ++i)
+            if (dst[i] && g->n_lists[i]) std::sort(dst[i], dst[i] + g->n_lists[i]);
+    }
     return NTS_OK;
 }
 

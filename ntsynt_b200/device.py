@@ -334,13 +334,67 @@ class MinimizerGraph:
             check(lib.nts_graph_download_cums(self._h, ptr(ci, C.c_uint32), ptr(cd, C.c_uint32)))
         return ci.view(np.int32), cd.view(np.int32)
 
-    def join_result(self):
-        "everything SyntenyEngine needs from the join, as a dict"
-        H, POS, CTG, RANK, link, deg = self.vertices()
-        INV, inc, dec, spread = self.links()
+    def host_arrays(self, cap):
+        """H[cap] u64, POS[G,cap] i64, CTG[G,cap] i32, nbr[cap,2] i32, conn[cap] u8: the graph stage's working
+        columns in their final dtypes, written by the device into pinned buffers with room for later vertices"""
+        V, G = len(self), self.n_asm
+        cap = max(int(cap), V, 1)
+        H = PinnedPool.get("H", (cap,), np.uint64)
+        POS = PinnedPool.get("POS64", (G, cap), np.int64)
+        CTG = PinnedPool.get("CTG32", (G, cap), np.int32)
+        nbr = PinnedPool.get("nbr", (cap, 2), np.int32)
+        conn = PinnedPool.get("conn", (cap,), np.uint8)
+        if V:
+            check(lib.nts_graph_download_host_arrays(self._h, cap, ptr(H, C.c_uint64), ptr(POS, C.c_longlong),
+                                                     ptr(CTG, C.c_int32), ptr(nbr, C.c_int32), ptr(conn, C.c_uint8)))
+        return H, POS, CTG, nbr, conn
+
+    def sparse_lists(self, bp):
+        "(breaks, deg3, big) sorted int64 arrays -- see nts_graph_sparse_lists in the header"
+        cnt = (C.c_uint64 * 3)()
+        bp = min(int(bp), 0xFFFFFFFF)
+        check(lib.nts_graph_sparse_lists(self._h, bp, None, None, None, cnt))
+        arrs = [np.empty(max(int(c), 1), dtype=np.uint32) for c in cnt]
+        check(lib.nts_graph_sparse_lists(self._h, bp, ptr(arrs[0], C.c_uint32), ptr(arrs[1], C.c_uint32),
+                                         ptr(arrs[2], C.c_uint32), cnt))
+        return tuple(a[:int(c)].astype(np.int64) for a, c in zip(arrs, cnt))
+
+    def rank_inv(self):
+        "RANK[G,V], INV[G,V] u32 (round-0 neighbourhoods of the simplification candidates)"
+        V, G = len(self), self.n_asm
+        n = max(V, 1)
+        rank = PinnedPool.get("rank", (G, n), np.uint32)
+        inv = PinnedPool.get("inv", (G, n), np.uint32)
+        if V:
+            check(lib.nts_graph_download_vertices(self._h, None, None, None, ptr(rank, C.c_uint32), None, None))
+            check(lib.nts_graph_download_links(self._h, ptr(inv, C.c_uint32), None, None, None))
+        return rank[:, :V], inv[:, :V]
+
+    def pair_masks(self):
+        "incmask, decmask, spread [V] u32 of the pairs (i, i+1) (fetched only when a refinement round overwrites positions)"
+        V = len(self)
+        n = max(V, 1)
+        inc = PinnedPool.get("inc", (n,), np.uint32)
+        dec = PinnedPool.get("dec", (n,), np.uint32)
+        spread = PinnedPool.get("spread", (n,), np.uint32)
+        if V:
+            check(lib.nts_graph_download_links(self._h, None, ptr(inc, C.c_uint32), ptr(dec, C.c_uint32), ptr(spread, C.c_uint32)))
+        return inc[:V], dec[:V], spread[:V]
+
+    def join_result(self, full=False):
+        """everything SyntenyEngine needs from the join, as a dict.  Default: lean form -- the O(V) columns arrive
+        host-ready through `host(cap)`, the sparse views through `sparse(bp)`, the pair masks lazily; full=True
+        also returns the raw columns (tests, .mx.dot writer)."""
+        V = len(self)
+        RANK, INV = self.rank_inv()
         CI, CD = self.cums()
-        return dict(H=H, POS=POS, CTG=CTG, RANK=RANK, INV=INV, link=link, degree=deg, incmask=inc, decmask=dec,
-                    spread=spread, CI=CI, CD=CD)
+        res = dict(V=V, RANK=RANK, INV=INV, CI=CI, CD=CD, host=self.host_arrays, sparse=self.sparse_lists,
+                   pair_masks=self.pair_masks)
+        if full:
+            H, POS, CTG, _, link, deg = self.vertices()
+            _, inc, dec, spread = self.links()
+            res.update(H=H, POS=POS, CTG=CTG, link=link, degree=deg, incmask=inc, decmask=dec, spread=spread)
+        return res
 
     def edges(self):
         "(u, v, support) of the distinct adjacency edges in build_graph's first-insertion order"

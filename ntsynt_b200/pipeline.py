@@ -92,7 +92,8 @@ class CudaBackend:
 
     def write_dot(self, path, j):
         from . import io
-        io.write_mx_dot(path, self.names, self.contig_names, j["H"], j["POS"], j["CTG"], self.graph.edges())
+        H, POS, CTG = self.graph.vertices()[:3]
+        io.write_mx_dot(path, self.names, self.contig_names, H, POS, CTG, self.graph.edges())
 
     def close(self):
         if getattr(self, "graph", None) is not None:

@@ -154,6 +154,30 @@ class SyntenyEngine:
 
     # ------------------------------------------------------------------ vertex storage
     def _init_vertices(self, j):
+        self._prebuilt = "host" in j
+        self._pair_masks = j.get("pair_masks")
+        self._h_extra = {}
+        self._pair_cache = None
+        self._pair_orig, self._pair_delta = {}, {}      # corrections to the device prefix sums (see _refresh_pairs)
+        self._br_touched = set()                        # pairs (i, i+1) whose `conn` changed since _breaks was made
+        self.sparse = set()                             # vertices that may hold a non-(i,i+1) edge
+        self._ctg0 = None                               # copy-on-write snapshot of round-0 contigs
+        if self._prebuilt:
+            # lean form (device backend): the O(V) columns arrive in their final dtype and layout, written by the
+            # device into pinned buffers with room for the vertices later rounds add
+            V = int(j["V"])
+            self.V0 = self.V = V
+            cap = V + 65536 + V // 16
+            self.H, self.POS, self.CTG, self.nbr, conn = j["host"](cap)
+            self.conn = conn[:max(V - 1, 0)].view(bool)
+            self.alive = np.zeros(cap, dtype=bool); self.alive[:V] = True
+            self.RANK, self.INV = j["RANK"], j["INV"]
+            self.incmask = self.decmask = self.spread = None             # fetched on demand (_refresh_pairs)
+            self.CI, self.CD = j["CI"], j["CD"]
+            breaks, deg3, big = j["sparse"](self.bp)
+            self._breaks, self._deg3, self.big = breaks, deg3, big
+            self._cum_dirty = False
+            return
         H = j["H"]
         V = len(H)
         self.V0 = V
@@ -163,14 +187,10 @@ class SyntenyEngine:
         self.POS = np.zeros((self.G, cap), dtype=np.int64); self.POS[:, :V] = j["POS"]
         self.CTG = np.zeros((self.G, cap), dtype=np.int32); self.CTG[:, :V] = j["CTG"]
         self.RANK, self.INV = j["RANK"], j["INV"]                    # round-0 vertices only (uint32)
-        self._ctg0 = None                                            # copy-on-write snapshot of round-0 contigs
         self.alive = np.zeros(cap, dtype=bool); self.alive[:V] = True
         self.nbr = np.full((cap, 2), -1, dtype=np.int32)
         self.conn = np.zeros(max(V - 1, 0), dtype=bool)              # edge (i, i+1) present, base vertices
-        self.sparse = set()                                          # vertices that may hold a non-(i,i+1) edge
-        self._h_extra = {}
-        self._pair_cache = None
-        self._pair_orig, self._pair_delta = {}, {}      # corrections to the device prefix sums (see _refresh_pairs)
+        self._breaks = self._deg3 = None
         # per-pair arrays of (i, i+1) and their prefix sums per assembly
         self.incmask = np.asarray(j["incmask"], dtype=np.uint32)
         self.decmask = np.asarray(j["decmask"], dtype=np.uint32)
@@ -200,6 +220,9 @@ class SyntenyEngine:
         corrections (pair index -> per-assembly delta) that _range_sums adds for the ranges containing them."""
         if self._cum_dirty:
             self._cums()
+        if self.incmask is None:
+            inc, dec, spread = self._pair_masks()
+            self.incmask, self.decmask, self.spread = np.array(inc), np.array(dec), np.array(spread)
         for v in vids:
             for i in (v - 1, v):
                 if 0 <= i < self.V0 - 1:
@@ -288,6 +311,7 @@ class SyntenyEngine:
                 raise RuntimeError("internal error: vertex of degree > 2 in the weight-filtered graph")
         if abs(u - v) == 1 and max(u, v) < self.V0:
             self.conn[min(u, v)] = True
+            self._br_touched.add(int(min(u, v)))
         else:
             self.sparse.add(int(u)); self.sparse.add(int(v))
 
@@ -302,6 +326,7 @@ class SyntenyEngine:
         lo = np.minimum(us, vs)
         base = (np.abs(us - vs) == 1) & (np.maximum(us, vs) < self.V0)
         self.conn[lo[base]] = False
+        self._br_touched.update(lo[base].tolist())
 
     def _remove_vertices(self, ids):
         ids = np.unique(np.asarray(ids, dtype=np.int64))
@@ -365,7 +390,7 @@ class SyntenyEngine:
         neighbourhoods are pulled out of the rank arrays in one vectorised step, the (few thousand) candidate
         edges are then visited in build_graph's edge order with plain Python containers."""
         G, V0 = self.G, self.V0
-        cand = np.flatnonzero(np.asarray(degree) == 3)
+        cand = self._deg3 if self._deg3 is not None else np.flatnonzero(np.asarray(degree) == 3)
         bumped, removed = {}, []
         if not len(cand):
             return bumped, removed
@@ -440,7 +465,15 @@ class SyntenyEngine:
         opos = self.POS[self.orient]
         paths = []
         if V0:
-            starts = np.concatenate([[0], np.flatnonzero(~self.conn) + 1])
+            if self._breaks is None:
+                self._breaks = np.flatnonzero(~self.conn)
+            elif self._br_touched:
+                # pairs whose link changed since the list was made: their truth is conn[i]
+                t = np.fromiter(self._br_touched, dtype=np.int64, count=len(self._br_touched))
+                keep = self._breaks[~np.isin(self._breaks, t)]
+                self._breaks = np.union1d(keep, t[~self.conn[t]])
+            self._br_touched = set()
+            starts = np.concatenate([[0], self._breaks + 1])
             ends = np.concatenate([starts[1:] - 1, [V0 - 1]])
         else:
             starts = ends = np.zeros(0, dtype=np.int64)
@@ -1071,8 +1104,8 @@ class SyntenyEngine:
         self._tick("sketch0")
         j = self.be.join(tables, self.orient)
         self._tick("join")
-        link, degree = j["link"], j["degree"]
-        self.stats["vertices"] = int(len(j["H"]))
+        link, degree = j.get("link"), j.get("degree")
+        self.stats["vertices"] = int(j["V"]) if "V" in j else int(len(j["H"]))
         if getattr(self, "dot_path", None):
             self.log("Printing graph", self.dot_path)
             self.be.write_dot(self.dot_path, j)
@@ -1084,11 +1117,11 @@ class SyntenyEngine:
         bumped, removed = ({}, [])
         if self.simplify:
             self.log("Running graph simplificaton")
-            bumped, removed = self._simplify_round0(np.asarray(link), np.asarray(degree))
+            bumped, removed = self._simplify_round0(link, degree)
         self.stats["simplified_vertices"] = len(set(removed))
         self._tick("simplify0")
         self.log("Filtering the graph")
-        if V > 1:
+        if V > 1 and not self._prebuilt:
             self.conn[:] = np.asarray(link[:V - 1], dtype=bool)
             ar = np.arange(1, V, dtype=np.int32)
             self.nbr[:V - 1, 1] = np.where(self.conn, ar, -1)        # slot 1: right neighbour

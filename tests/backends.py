@@ -92,9 +92,12 @@ def numpy_edges(RANK, CTG):
 
 
 class OracleBackend:
-    def __init__(self, fasta_paths, tsv_names, k, fpr=0.025, common=True):
-        "fasta_paths/tsv_names in the engine's processing order (reverse-sorted TSV names)"
+    def __init__(self, fasta_paths, tsv_names, k, fpr=0.025, common=True, lean=False):
+        """fasta_paths/tsv_names in the engine's processing order (reverse-sorted TSV names).
+        lean=True hands the join to the engine in the form the CUDA backend uses (host-ready columns,
+        sparse lists, lazily fetched pair masks; ntsynt_b200.device.MinimizerGraph.join_result)."""
         self.k = k
+        self.lean = lean
         self.names = list(tsv_names)
         self.records = [so.read_fasta(p) for p in fasta_paths]
         self.contig_names = [[n for n, _ in recs] for recs in self.records]
@@ -130,6 +133,32 @@ class OracleBackend:
         inc, dec, spread = numpy_pairs(POS)
         self._h_order = np.argsort(H, kind="stable")
         self._h_sorted = H[self._h_order]
+        if self.lean:
+            CI = np.zeros((G, V + 1), dtype=np.int32)
+            CD = np.zeros((G, V + 1), dtype=np.int32)
+            for a in range(G):
+                np.cumsum((inc >> np.uint32(a)) & np.uint32(1), out=CI[a, 1:])
+                np.cumsum((dec >> np.uint32(a)) & np.uint32(1), out=CD[a, 1:])
+
+            def host(cap):
+                rng = np.random.default_rng(V)                       # rows beyond V hold garbage on the device path too
+                Hc = rng.integers(0, 1 << 62, cap).astype(np.uint64); Hc[:V] = H
+                P = rng.integers(0, 1 << 30, (G, cap)).astype(np.int64); P[:, :V] = POS
+                Cc = rng.integers(0, 50, (G, cap)).astype(np.int32); Cc[:, :V] = CTG
+                nbr = rng.integers(-1, 100, (cap, 2)).astype(np.int32)
+                conn = rng.integers(0, 2, cap).astype(np.uint8); conn[:V] = link
+                ar = np.arange(V, dtype=np.int32)
+                nbr[:V, 1] = np.where(link.astype(bool), ar + 1, -1)
+                nbr[:V, 0] = -1
+                if V > 1:
+                    nbr[1:V, 0] = np.where(link[:-1].astype(bool), ar[:-1], -1)
+                return Hc, P, Cc, nbr, conn
+
+            def sparse(bp):
+                return (np.flatnonzero(link[:max(V - 1, 0)] == 0).astype(np.int64), np.flatnonzero(degree == 3).astype(np.int64),
+                        np.flatnonzero(spread[:max(V - 1, 0)] > bp).astype(np.int64))
+            return dict(V=V, RANK=RANK, INV=INV, CI=CI, CD=CD, host=host, sparse=sparse,
+                        pair_masks=lambda: (inc, dec, spread))
         return dict(H=H, POS=POS, CTG=CTG, RANK=RANK, INV=INV, link=link, degree=degree, incmask=inc, decmask=dec,
                     spread=spread)
 

@@ -14,20 +14,21 @@ from oracle import sketch_oracle as so
 from oracle.graph_oracle import GraphOracle
 
 
-def run_engine(paths, k, w, w_rounds, indel, merge, z):
+def run_engine(paths, k, w, w_rounds, indel, merge, z, lean=False):
     bases = [os.path.basename(p)[:-3] if p.endswith(".gz") else os.path.basename(p) for p in paths]
     tsv = [f"{b}.k{k}.w{w}.tsv" for b in bases]
     order = sorted(range(len(paths)), key=lambda i: tsv[i], reverse=True)
-    be = OracleBackend([paths[i] for i in order], [tsv[i] for i in order], k)
+    be = OracleBackend([paths[i] for i in order], [tsv[i] for i in order], k, lean=lean)
     eng = SyntenyEngine(be, k, w, w_rounds, indel, merge, z, write_files=False, quiet=True)
     eng.run()
     return eng, be
 
 
+@pytest.mark.parametrize("lean", [False, True])
 @pytest.mark.parametrize("tag", ["AB", "ABC"])
-def test_mini_against_reference_fixture(tag, mini_params):
+def test_mini_against_reference_fixture(tag, mini_params, lean):
     p = mini_params
-    eng, _ = run_engine(mini_fastas(tag), p["k"], p["w"], p["w_rounds"], p["indel"], p["merge"], p["block_size"])
+    eng, _ = run_engine(mini_fastas(tag), p["k"], p["w"], p["w_rounds"], p["indel"], p["merge"], p["block_size"], lean)
     assert eng.outputs["final"] == mini_expected(tag, "synteny_blocks.tsv")
     assert eng.outputs["pre_merge"] == mini_expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
 
@@ -55,7 +56,7 @@ def test_engine_equals_graph_oracle_on_rearranged_genomes(tmp_path, seed, G, pre
         paths.append(p)
     k, w = 16, 40
     w_rounds, indel, merge, z = ([20, 5], 300, "400", 200) if presets == "low" else ([25, 10], 2000, "2w", 400)
-    eng, be = run_engine(paths, k, w, w_rounds, indel, merge, z)
+    eng, be = run_engine(paths, k, w, w_rounds, indel, merge, z, lean=bool(seed % 2))
     go = GraphOracle([(os.path.basename(p) + f".k{k}.w{w}.tsv", so.read_fasta(p)) for p in paths], k, w, w_rounds,
                      indel, merge, z, be.bits)
     go.run()
