@@ -172,7 +172,7 @@ class SyntenyEngine:
             self.conn = conn[:max(V - 1, 0)].view(bool)
             self.alive = np.zeros(cap, dtype=bool); self.alive[:V] = True
             self.RANK, self.INV = j["RANK"], j["INV"]
-            self.incmask = self.decmask = self.spread = None             # fetched on demand (_refresh_pairs)
+            self.incmask = self.decmask = self.spread = None             # never needed: see _refresh_pairs
             self.CI, self.CD = j["CI"], j["CD"]
             breaks, deg3, big = j["sparse"](self.bp)
             self._breaks, self._deg3, self.big = breaks, deg3, big
@@ -214,40 +214,47 @@ class SyntenyEngine:
             self._cum_dirty = False
         return self.CI, self.CD
 
-    def _refresh_pairs(self, vids):
-        """positions of base vertices were overwritten (update_list_mx_info): redo the values of their
-        (i, i+1) pairs.  The device prefix sums stay as they are; the few changed pairs are kept as
-        corrections (pair index -> per-assembly delta) that _range_sums adds for the ranges containing them."""
+    def _pair_values(self, idx):
+        "direction masks and |dpos| spread of the pairs (i, i+1), i in idx, from the current positions (graph_links_kernel)"
+        d = self.POS[:, idx + 1] - self.POS[:, idx]                    # [G, n]
+        bits = (np.int64(1) << np.arange(self.G, dtype=np.int64))[:, None]
+        inc = ((d > 0) * bits).sum(axis=0)
+        dec = ((d < 0) * bits).sum(axis=0)
+        ad = np.abs(d)
+        return inc, dec, ad.max(axis=0) - ad.min(axis=0)
+
+    def _pairs_around(self, vids):
+        "indices of the pairs (v-1, v) and (v, v+1) of base vertices vids"
+        v = np.asarray(vids, dtype=np.int64)
+        p = np.unique(np.concatenate([v - 1, v]))
+        return p[(p >= 0) & (p < self.V0 - 1)]
+
+    def _refresh_pairs(self, pairs, old):
+        """positions of base vertices were overwritten (update_list_mx_info): redo the values of the pairs around
+        them.  `old` = _pair_values(pairs) taken BEFORE the overwrite.  The device prefix sums stay as they are; the
+        few changed pairs are kept as corrections (pair index -> per-assembly delta against the ORIGINAL value)
+        that _range_sums adds for the ranges containing them."""
         if self._cum_dirty:
             self._cums()
-        if self.incmask is None:
-            inc, dec, spread = self._pair_masks()
-            self.incmask, self.decmask, self.spread = np.array(inc), np.array(dec), np.array(spread)
-        for v in vids:
-            for i in (v - 1, v):
-                if 0 <= i < self.V0 - 1:
-                    d = self.POS[:, i + 1] - self.POS[:, i]
-                    inc = dec = 0
-                    for a in range(self.G):
-                        inc |= (1 << a) if d[a] > 0 else 0
-                        dec |= (1 << a) if d[a] < 0 else 0
-                    old_i, old_d = self._pair_orig.setdefault(i, (int(self.incmask[i]), int(self.decmask[i])))
-                    di = np.array([((inc >> a) & 1) - ((old_i >> a) & 1) for a in range(self.G)], dtype=np.int64)
-                    dd = np.array([((dec >> a) & 1) - ((old_d >> a) & 1) for a in range(self.G)], dtype=np.int64)
-                    if di.any() or dd.any():
-                        self._pair_delta[i] = (di, dd)
-                    else:
-                        self._pair_delta.pop(i, None)
-                    self._pair_cache = None
-                    self.incmask[i], self.decmask[i] = inc, dec
-                    ad = np.abs(d)
-                    sp = int(ad.max() - ad.min())
-                    if (sp > self.bp) != (self.spread[i] > self.bp):
-                        if sp > self.bp:
-                            self.big = np.insert(self.big, np.searchsorted(self.big, i), i)
-                        else:
-                            self.big = np.delete(self.big, np.searchsorted(self.big, i))
-                    self.spread[i] = min(sp, 0xFFFFFFFF)
+        if not len(pairs):
+            return
+        new = self._pair_values(pairs)
+        G = self.G
+        for i, oi, od, osp, ni, nd, nsp in zip(pairs.tolist(), old[0].tolist(), old[1].tolist(), old[2].tolist(),
+                                               new[0].tolist(), new[1].tolist(), new[2].tolist()):
+            orig_i, orig_d = self._pair_orig.setdefault(i, (oi, od))
+            di = np.array([((ni >> a) & 1) - ((orig_i >> a) & 1) for a in range(G)], dtype=np.int64)
+            dd = np.array([((nd >> a) & 1) - ((orig_d >> a) & 1) for a in range(G)], dtype=np.int64)
+            if di.any() or dd.any():
+                self._pair_delta[i] = (di, dd)
+            else:
+                self._pair_delta.pop(i, None)
+            self._pair_cache = None
+            if (nsp > self.bp) != (osp > self.bp):
+                if nsp > self.bp:
+                    self.big = np.insert(self.big, np.searchsorted(self.big, i), i)
+                else:
+                    self.big = np.delete(self.big, np.searchsorted(self.big, i))
 
     def _range_sums(self, lo, hi):
         "per-assembly counts of increasing / decreasing pairs (i, i+1) with lo <= i < hi, for arrays lo, hi"
@@ -314,6 +321,30 @@ class SyntenyEngine:
             self._br_touched.add(int(min(u, v)))
         else:
             self.sparse.add(int(u)); self.sparse.add(int(v))
+
+    def _add_edges(self, us, vs):
+        "vectorised _add_edge for a batch of edges (a vertex may take two of them)"
+        us = np.asarray(us, dtype=np.int64); vs = np.asarray(vs, dtype=np.int64)
+        if not len(us):
+            return
+        X = np.concatenate([us, vs]); Y = np.concatenate([vs, us])
+        order = np.argsort(X, kind="stable")
+        X, Y = X[order], Y[order]
+        first = np.ones(len(X), dtype=bool); first[1:] = X[1:] != X[:-1]
+        start = np.maximum.accumulate(np.where(first, np.arange(len(X)), 0))
+        r = np.arange(len(X)) - start                                  # 0, 1, .. within the vertex's group
+        free0 = self.nbr[X, 0] < 0
+        free1 = self.nbr[X, 1] < 0
+        slot = np.where((r == 0) & free0, 0, 1)
+        ok = np.where(slot == 0, free0, free1) & (r < 2) & ~((r == 1) & ~free0)
+        if not ok.all():
+            raise RuntimeError("internal error: vertex of degree > 2 in the weight-filtered graph")
+        self.nbr[X, slot] = Y.astype(np.int32)
+        lo, hi = np.minimum(us, vs), np.maximum(us, vs)
+        base = ((hi - lo) == 1) & (hi < self.V0)
+        self.conn[lo[base]] = True
+        self._br_touched.update(lo[base].tolist())
+        self.sparse.update(us[~base].tolist()); self.sparse.update(vs[~base].tolist())
 
     def _remove_edges(self, us, vs):
         us = np.asarray(us, dtype=np.int64); vs = np.asarray(vs, dtype=np.int64)
@@ -497,14 +528,6 @@ class SyntenyEngine:
             elif y < x:
                 paths.append([(a, b, -1)])
         if real_sparse:
-            def run_bounds(v):
-                if v >= V0:
-                    return v, v
-                r = int(np.searchsorted(starts, v, side="right") - 1)
-                return int(starts[r]), int(ends[r])
-
-            def degree(v):
-                return int((self.nbr[v] >= 0).sum())
             seen_runs = set()
             sv = np.array(sorted(real_sparse), dtype=np.int64)
             ra, rb = sv.copy(), sv.copy()
@@ -513,6 +536,19 @@ class SyntenyEngine:
                 ri = np.searchsorted(starts, sv[bm], side="right") - 1
                 ra[bm], rb[bm] = starts[ri], ends[ri]
             ends_all = np.unique(np.concatenate([ra, rb]))
+            # run of every vertex the walk can stand on: the sparse vertices and the ends of their runs
+            bounds = dict(zip(sv.tolist(), zip(ra.tolist(), rb.tolist())))
+            bounds.update(zip(ra.tolist(), zip(ra.tolist(), rb.tolist())))
+            bounds.update(zip(rb.tolist(), zip(ra.tolist(), rb.tolist())))
+
+            def run_bounds(v):
+                got = bounds.get(v)
+                if got is not None:
+                    return got
+                if v >= V0:
+                    return v, v
+                r = int(np.searchsorted(starts, v, side="right") - 1)
+                return int(starts[r]), int(ends[r])
             deg_all = (self.nbr[ends_all] >= 0).sum(axis=1)
             cand_ends = ends_all[deg_all == 1].tolist()
             for e0 in cand_ends:
@@ -533,8 +569,7 @@ class SyntenyEngine:
                     if b > a:
                         inside = last - 1 if last == b else last + 1
                     nxt = -1
-                    for y in self.nbr[last]:
-                        y = int(y)
+                    for y in self.nbr[last].tolist():
                         if y < 0 or y == inside:
                             continue
                         if a == b and y == prev:
@@ -914,78 +949,100 @@ class SyntenyEngine:
             cid = self._lookup(common)
             missing = np.nonzero(cid < 0)[0]
             self._grow(len(missing))
-            for j in missing:
-                vid = self.V
-                self.V += 1
-                self.H[vid] = common[j]
-                self._h_extra[int(common[j])] = vid
-                self.alive[vid] = False
-                self.nbr[vid] = -1
-                cid[j] = vid
-            touched_base = set()
+            if len(missing):
+                nv = np.arange(self.V, self.V + len(missing), dtype=np.int64)
+                self.V += len(missing)
+                self.H[nv] = common[missing]
+                self._h_extra.update(zip(common[missing].tolist(), nv.tolist()))
+                self.alive[nv] = False
+                self.nbr[nv] = -1
+                cid[missing] = nv
+            # pass 1: which base vertices get a new position / contig (assembly a only writes row a)
+            touched = []
             for a in range(G):
                 kh, kp, kc, _ = lists[a]
-                j = np.searchsorted(common, kh)
-                vid = cid[j]
+                vid = cid[np.searchsorted(common, kh)]
                 changed = (self.POS[a, vid] != kp) | (self.CTG[a, vid] != kc)
-                base_changed = vid[changed & (vid < self.V0)]
-                if len(base_changed):
-                    if self._ctg0 is None:
-                        self._ctg0 = self.CTG[:, :self.V0].copy()
-                    touched_base.update(int(x) for x in base_changed)
-                self.POS[a, vid] = kp
-                self.CTG[a, vid] = kc
+                touched.append(vid[changed & (vid < self.V0)])
                 ids_per_asm.append(vid)
-            if touched_base:
+            touched_base = np.unique(np.concatenate(touched)) if touched else np.zeros(0, dtype=np.int64)
+            pairs = old = None
+            if len(touched_base):
+                if self._ctg0 is None:
+                    self._ctg0 = self.CTG[:, :self.V0].copy()
                 self.stats["base_overwrites"] = self.stats.get("base_overwrites", 0) + len(touched_base)
-                self._refresh_pairs(sorted(touched_base))
+                pairs = self._pairs_around(touched_base)
+                old = self._pair_values(pairs)
+            # pass 2: overwrite
+            for a in range(G):
+                _, kp, kc, _ = lists[a]
+                self.POS[a, ids_per_asm[a]] = kp
+                self.CTG[a, ids_per_asm[a]] = kc
+            if pairs is not None:
+                self._refresh_pairs(pairs, old)
         else:
             ids_per_asm = [np.zeros(0, dtype=np.int64) for _ in range(G)]
         self._tick("r_update")
-        # --- build_graph in extend mode (ntjoin_utils.py:83-141)
-        new_edges = {}          # (min,max) -> [support count, (s,t) as first inserted]
-        new_order = []
+        # --- build_graph in extend mode (ntjoin_utils.py:83-141): consecutive pairs of every sub-list, in
+        #     (assembly, position) order; an edge's id order is its first appearance, its weight the number of
+        #     assemblies (pairs) that support it
+        S, T = [], []
         for a in range(G):
             vid, sub = ids_per_asm[a], lists[a][3]
-            for i in range(len(vid) - 1):
-                if sub[i] != sub[i + 1]:
-                    continue
-                s, t = int(vid[i]), int(vid[i + 1])
-                key = (s, t) if s < t else (t, s)
-                if key in new_edges:
-                    new_edges[key][0] += 1
-                else:
-                    new_edges[key] = [1, (s, t)]
-                    new_order.append(key)
-            for x in vid:
-                x = int(x)
-                if int(self.H[x]) not in terminal_h and not self.alive[x]:
-                    self.alive[x] = True        # add_vertices: new (or previously deleted) vertex
-                    self.nbr[x] = -1
+            if len(vid) > 1:
+                m_ = sub[:-1] == sub[1:]
+                S.append(vid[:-1][m_]); T.append(vid[1:][m_])
+        S = np.concatenate(S) if S else np.zeros(0, dtype=np.int64)
+        T = np.concatenate(T) if T else np.zeros(0, dtype=np.int64)
+        lo_, hi_ = np.minimum(S, T), np.maximum(S, T)
+        _, first_ix, cnt_ = np.unique((lo_ << np.int64(32)) | hi_, return_index=True, return_counts=True)
+        eo = np.argsort(first_ix, kind="stable")
+        first_ix, cnt_ = first_ix[eo], cnt_[eo]
+        eu, ev = lo_[first_ix], hi_[first_ix]                           # distinct new pairs in insertion order
+        # add_vertices: new (or previously deleted) vertices, except the blocks' terminal minimizers
+        allv = np.unique(np.concatenate(ids_per_asm)) if ids_per_asm else np.zeros(0, dtype=np.int64)
+        if len(allv):
+            term_arr = np.unique(self.H[term_ids]) if len(term_ids) else np.zeros(0, dtype=np.uint64)
+            revive = allv[~self.alive[allv] & ~np.isin(self.H[allv], term_arr)]
+            self.alive[revive] = True
+            self.nbr[revive] = -1
         # edges already in the graph are skipped (either orientation)
-        fresh = [key for key in new_order if not self._has_edge(*key)]
-        for key in fresh:
-            for x in key:
-                if not self.alive[x]:
-                    raise RuntimeError("internal error: edge to a vertex that is not in the graph")
-        inc_new = defaultdict(list)
-        for seq, key in enumerate(fresh):
-            inc_new[key[0]].append(key); inc_new[key[1]].append(key)
-            self._edge_birth[key] = (round_no, seq)
-        wt = {key: new_edges[key][0] for key in fresh}
+        if len(eu):
+            has = (self.nbr[eu, 0] == ev) | (self.nbr[eu, 1] == ev)
+            eu, ev, cnt_ = eu[~has], ev[~has], cnt_[~has]
+            if not (self.alive[eu].all() and self.alive[ev].all()):
+                raise RuntimeError("internal error: edge to a vertex that is not in the graph")
+        fresh = list(zip(eu.tolist(), ev.tolist()))
+        wt = dict(zip(fresh, cnt_.tolist()))
+        self._edge_birth.update(zip(fresh, ((round_no, seq) for seq in range(len(fresh)))))
 
         def old_nbrs(x):
             return [int(y) for y in self.nbr[x] if y >= 0]
 
-        # incident-weight guard (check_added_edges_incident_weights :70-80)
-        def incident_weight(x):
-            return G * len(old_nbrs(x)) + sum(wt[e] for e in inc_new[x])
-        flagged = [key for key in fresh if incident_weight(key[0]) > 2 * G or incident_weight(key[1]) > 2 * G]
+        # incident-weight guard (check_added_edges_incident_weights :70-80), per touched vertex
+        flagged, cand_v, inc_new = [], [], defaultdict(list)
+        if len(eu):
+            ends = np.concatenate([eu, ev])
+            tv, inv_ = np.unique(ends, return_inverse=True)
+            new_w = np.bincount(inv_, weights=np.concatenate([cnt_, cnt_]), minlength=len(tv))
+            new_deg = np.bincount(inv_, minlength=len(tv))
+            old_deg = (self.nbr[tv] >= 0).sum(axis=1)
+            heavy = (G * old_deg + new_w) > 2 * G
+            fl = heavy[inv_[:len(eu)]] | heavy[inv_[len(eu):]]
+            flagged = [fresh[i] for i in np.flatnonzero(fl).tolist()]
+            # simplification candidates: touched vertices with exactly three neighbours in the extended graph
+            cand_mask = (old_deg + new_deg) == 3
+            cand_v = tv[cand_mask].tolist()
+            if cand_v:
+                at_cand = cand_mask[inv_[:len(eu)]] | cand_mask[inv_[len(eu):]]
+                for i in np.flatnonzero(at_cand).tolist():
+                    key = fresh[i]
+                    inc_new[key[0]].append(key); inc_new[key[1]].append(key)
         flagged_set = set(flagged)
         # --- simplification runs on the graph WITH the flagged edges; its weight bumps survive only
         #     when nothing was flagged (same object), its vertex deletions never do
         if self.simplify:
-            bumps = self._simplify_extended(fresh, wt, inc_new, old_nbrs)
+            bumps = self._simplify_extended(fresh, wt, inc_new, old_nbrs, cand_v)
             if not flagged:
                 for key in bumps:
                     if key in wt:
@@ -994,17 +1051,18 @@ class SyntenyEngine:
         # --- weight filter (+ flagged pairs on the last round)
         surviving = [key for key in fresh if key not in flagged_set]
         low = [key for key in surviving if wt[key] < G]
-        for key in surviving:
-            if wt[key] >= G:
-                self._add_edge(*key)
+        full = [key for key in surviving if wt[key] >= G]
+        if full:
+            fa = np.array(full, dtype=np.int64)
+            self._add_edges(fa[:, 0], fa[:, 1])
         if last_round and low:
             self._erode(low)
         return None
 
-    def _simplify_extended(self, fresh, wt, inc_new, old_nbrs):
-        "run_graph_simplification on the extended graph; returns the edges whose weight it sets to G"
+    def _simplify_extended(self, fresh, wt, inc_new, old_nbrs, cand_v):
+        """run_graph_simplification on the extended graph; returns the edges whose weight it sets to G.
+        cand_v: the touched vertices with exactly three neighbours; inc_new: the new edges at those vertices."""
         G = self.G
-        touched = set(inc_new.keys())
 
         def nbrs(x):
             res = {y: G for y in old_nbrs(x)}
@@ -1013,7 +1071,7 @@ class SyntenyEngine:
                 res[y] = wt[e]
             return res
 
-        cand_v = {x for x in touched if len(nbrs(x)) == 3}
+        cand_v = set(cand_v)
         if not cand_v:
             return []
         bumped = {}
