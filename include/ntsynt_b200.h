@@ -142,6 +142,11 @@ int nts_bf_insert_genome(nts_bf* bf, const nts_genome* g, uint32_t k);
 /* a3: the cascade of cpp:136-160 with one hash function == dst &= src (kernel iii-b) */
 int nts_bf_and(nts_bf* dst, const nts_bf* src);
 int nts_bf_or(nts_bf* dst, const nts_bf* src);
+/* The whole of src/ntsynt_make_common_bf.cpp:107-160 in one call: zero both filters, then
+ * common = AND over i of bits(genomes[i]) (genomes in the caller's sorted-path order; `level` is scratch of the same
+ * size, may be NULL when n == 1).  Large inputs are pipelined over two CUDA streams: the binning pass of genome i+1
+ * overlaps the apply pass of genome i.  Result is bit-identical to nts_bf_insert_genome + nts_bf_and. */
+int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k);
 /* repeat filter, bin/ntsynt_make_repeat_bfs.py:56-69: rep |= k-mers seen >= 2x in g (kernel iii-d).
  * `scratch` is a per-genome filter of the same size that the call clears and uses. */
 int nts_bf_insert_repeats(nts_bf* rep, nts_bf* scratch, const nts_genome* g, uint32_t k);

@@ -77,6 +77,7 @@ _SIGS = {
     "nts_bf_insert_genome": (C.c_int, [vp, vp, C.c_uint32]),
     "nts_bf_and": (C.c_int, [vp, vp]),
     "nts_bf_or": (C.c_int, [vp, vp]),
+    "nts_bf_build_common": (C.c_int, [vp, vp, vpp, C.c_uint32, C.c_uint32]),
     "nts_bf_insert_repeats": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "nts_bf_popcount": (C.c_int, [vp, u64p]),
     "nts_bf_download": (C.c_int, [vp, u8p]),

@@ -16,6 +16,9 @@ namespace nts {
 int bf_insert_partitioned(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid,
                           bool* done);
 void part_scratch_release(nts_ctx* ctx);
+int part_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t total_valid, bool* ok);
+int part_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid);
+int part_apply(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf);
 
 static thread_local std::string g_err;
 
@@ -273,6 +276,7 @@ void nts_ctx_destroy(nts_ctx* ctx)
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -332,7 +336,7 @@ int nts_prof_reset(nts_ctx* ctx)
 }
 
 static const char* const PROF_NAMES[PROF_COUNT] = {"fill", "bf_insert", "bf_combine", "sketch", "sketch_post", "join",
-                                                   "synth", "popcount", "bf_repeat", "edges", "nccl"};
+                                                   "synth", "popcount", "bf_repeat", "edges", "nccl", "bf_build", "bf_bin", "bf_apply"};
 
 int nts_prof_count(void) { return PROF_COUNT; }
 const char* nts_prof_name(int id) { return (id >= 0 && id < PROF_COUNT) ? PROF_NAMES[id] : ""; }
@@ -626,6 +630,118 @@ static int bf_combine(nts_bf* dst, const nts_bf* src, int op, bool sync)
 int nts_bf_and(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 0, true); }
 int nts_bf_or(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 1, true); }
 int nts_bf_and_async(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 0, false); }
+
+/* src/ntsynt_make_common_bf.cpp:107-160 in one call: common = AND over the genomes of bits(genome), genomes in the
+ * caller's (sorted-path) order.  Large inputs are pipelined over two streams: the binning pass of genome i+1 (bound by
+ * shared-memory atomics in the SMs) runs while the apply pass of genome i (bound by the L2 atomic units) is in flight. */
+int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k)
+{
+    if (!common || !genomes || n < 1 || (n > 1 && !level)) return fail(NTS_ERR_ARG, "null argument");
+    nts_ctx* ctx = common->ctx;
+    if (n > 1 && (level->ctx != ctx || level->bytes != common->bytes)) return fail(NTS_ERR_ARG, "common and level filters differ");
+    for (uint32_t i = 0; i < n; ++i)
+        if (!genomes[i] || genomes[i]->ctx != ctx) return fail(NTS_ERR_ARG, "bad genome");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    const HashTables* tabs = nullptr;
+    int rc = get_tables(ctx, k, &tabs);
+    if (rc) return rc;
+    std::vector<const nts_view*> views(n);
+    uint64_t max_valid = 0, sum_valid = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        rc = get_plain_view(genomes[i], k, &views[i]);
+        if (rc) return rc;
+        max_valid = std::max(max_valid, views[i]->total_valid);
+        sum_valid += views[i]->total_valid;
+    }
+    // pipelined path: one bucket plan (sized for the largest genome) shared by both scratch slots
+    bool pipe = n >= 2;
+    if (const char* env = getenv("NTS_BF_PIPELINE")) { if (env[0] == '0') pipe = false; }
+    for (uint32_t i = 0; i < n && pipe; ++i) pipe = views[i]->total_valid > 0;
+    for (int slot = 0; slot < 2 && pipe; ++slot) {
+        bool ok = false;
+        rc = part_prepare(ctx, slot, common->bytes * 8, max_valid, &ok);
+        if (rc) return rc;
+        pipe = ok;
+    }
+    DevBuf<uint32_t> level2;                           // n >= 3: the level filters alternate so that binning never waits for an AND
+    if (pipe && n >= 3 && level2.alloc(common->alloc_bytes / 4) != cudaSuccess) pipe = false;
+    if (!pipe) {
+        rc = bf_fill(common, 0);
+        if (rc) return rc;
+        rc = nts_bf_insert_genome_async(common, genomes[0], k);
+        if (rc) return rc;
+        for (uint32_t i = 1; i < n; ++i) {
+            if ((rc = bf_fill(level, 0)) || (rc = nts_bf_insert_genome_async(level, genomes[i], k)) || (rc = bf_combine(common, level, 0, false)))
+                return rc;
+        }
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+        return NTS_OK;
+    }
+    if (!ctx->stream2) NTS_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    cudaStream_t A = ctx->stream, B = ctx->stream2;
+    auto target = [&](uint32_t i) -> uint32_t* { return i == 0 ? common->words.p : (((i - 1) & 1) ? level2.p : level->words.p); };
+    struct Ev { std::vector<cudaEvent_t> v; ~Ev() { for (auto e : v) cudaEventDestroy(e); }
+                cudaEvent_t make() { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); v.push_back(e); return e; } } evs;
+    std::vector<cudaEvent_t> BN(n), AP(n), FR(n, nullptr);
+    const uint64_t n16 = common->alloc_bytes / 16;
+    auto fill = [&](uint32_t* p) {
+        fill_u128_kernel<<<grid_for(ctx, n16, 256, 16), 256, 0, A>>>(reinterpret_cast<uint4*>(p), n16, 0u);
+        ctx->launches++;
+    };
+    // a filter object for the bin / apply launches of genome i (they only use words.p and bytes)
+    nts_bf tgt; tgt.ctx = ctx; tgt.bytes = common->bytes; tgt.alloc_bytes = common->alloc_bytes;
+    auto with_target = [&](uint32_t i, auto&& fn) -> int {
+        uint32_t* keep_p = tgt.words.p; size_t keep_n = tgt.words.n;
+        tgt.words.p = target(i); tgt.words.n = common->words.n;
+        int r = fn(&tgt);
+        tgt.words.p = keep_p; tgt.words.n = keep_n;     // never owns the memory
+        return r;
+    };
+    {
+        ProfScope prof(ctx, PROF_BF_BUILD, (double)sum_valid, true);
+        fill(common->words.p);
+        fill(level->words.p);
+        if (n >= 3) fill(level2.p);
+        cudaEvent_t f0 = evs.make();
+        NTS_CUDA(cudaEventRecord(f0, A));
+        NTS_CUDA(cudaStreamWaitEvent(B, f0, 0));
+        rc = with_target(0, [&](nts_bf* t) { return part_bin(ctx, 0, B, t, device_view(genomes[0], views[0]), tabs, views[0]->total_valid); });
+        if (rc) return rc;
+        BN[0] = evs.make();
+        NTS_CUDA(cudaEventRecord(BN[0], B));
+        for (uint32_t i = 0; i < n; ++i) {
+            if (i + 1 < n) {                            // bin of the next genome: its slot must be free, its target zeroed
+                if (i >= 1) NTS_CUDA(cudaStreamWaitEvent(B, AP[i - 1], 0));
+                if (FR[i + 1]) NTS_CUDA(cudaStreamWaitEvent(B, FR[i + 1], 0));
+                rc = with_target(i + 1, [&](nts_bf* t) {
+                    return part_bin(ctx, (int)((i + 1) & 1), B, t, device_view(genomes[i + 1], views[i + 1]), tabs, views[i + 1]->total_valid);
+                });
+                if (rc) return rc;
+                BN[i + 1] = evs.make();
+                NTS_CUDA(cudaEventRecord(BN[i + 1], B));
+            }
+            NTS_CUDA(cudaStreamWaitEvent(A, BN[i], 0));
+            rc = with_target(i, [&](nts_bf* t) { return part_apply(ctx, (int)(i & 1), A, t); });
+            if (rc) return rc;
+            AP[i] = evs.make();
+            NTS_CUDA(cudaEventRecord(AP[i], A));
+            if (i >= 1) {
+                bf_combine_kernel<<<grid_for(ctx, n16 / 4 + 1, 256, 16), 256, 0, A>>>(
+                    reinterpret_cast<uint4*>(common->words.p), reinterpret_cast<const uint4*>(target(i)), n16, 0);
+                ctx->launches++;
+                if (i + 2 < n) {                        // the same level filter takes genome i + 2
+                    fill(target(i));
+                    FR[i + 2] = evs.make();
+                    NTS_CUDA(cudaEventRecord(FR[i + 2], A));
+                }
+            }
+        }
+        NTS_CUDA(cudaGetLastError());
+    }
+    NTS_CUDA(cudaStreamSynchronize(A));
+    NTS_CUDA(cudaStreamSynchronize(B));
+    return NTS_OK;
+}
 
 int nts_bf_insert_repeats(nts_bf* rep, nts_bf* scratch, const nts_genome* g, uint32_t k)
 {

@@ -56,7 +56,7 @@ struct DevBuf {
 namespace nts {
 // per-kernel-family device timing (CUDA events on the context's stream), off unless enabled
 enum ProfId { PROF_FILL = 0, PROF_BF_INSERT, PROF_BF_COMBINE, PROF_SKETCH, PROF_SKETCH_POST, PROF_JOIN, PROF_SYNTH,
-              PROF_POPCOUNT, PROF_BF_REPEAT, PROF_EDGES, PROF_NCCL, PROF_COUNT };
+              PROF_POPCOUNT, PROF_BF_REPEAT, PROF_EDGES, PROF_NCCL, PROF_BF_BUILD, PROF_BF_BIN, PROF_BF_APPLY, PROF_COUNT };
 struct ProfPending { int id; cudaEvent_t e0, e1; double units; };
 }  // namespace nts
 
@@ -69,6 +69,7 @@ struct nts_ctx {
     uint64_t prof_launches[nts::PROF_COUNT] = {0};
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // side stream of the pipelined Bloom-filter build (created on first use)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     uint64_t sketch_escalated = 0;   // dense sub-tiles the sparse sketch kernel handed to the dense one (statistics)
@@ -81,14 +82,17 @@ namespace nts {
 // RAII: times everything launched on ctx->stream during its lifetime under one ProfId
 struct ProfScope {
     nts_ctx* ctx; int id; cudaEvent_t e0 = nullptr, e1 = nullptr; double units; uint64_t launches0;
-    ProfScope(nts_ctx* c, int i, double u = 0) : ctx(c), id(i), units(u), launches0(c->launches)
+    bool as_one = false;      // count the scope as one unit of work (a pipelined multi-kernel call) instead of its launches
+    cudaStream_t st;          // the stream the timed launches go to
+    ProfScope(nts_ctx* c, int i, double u = 0, bool one = false, cudaStream_t s = nullptr)
+        : ctx(c), id(i), units(u), launches0(c->launches), as_one(one), st(s ? s : c->stream)
     {
-        if (ctx->prof_enabled) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
+        if (ctx->prof_enabled) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     }
     ~ProfScope()
     {
-        ctx->prof_launches[id] += ctx->launches - launches0;
-        if (ctx->prof_enabled) { cudaEventRecord(e1, ctx->stream); ctx->prof_pending.push_back({id, e0, e1, units}); }
+        ctx->prof_launches[id] += as_one ? 1 : ctx->launches - launches0;
+        if (ctx->prof_enabled) { cudaEventRecord(e1, st); ctx->prof_pending.push_back({id, e0, e1, units}); }
     }
 };
 inline cudaError_t copy_h2d(nts_ctx* ctx, void* dst, const void* src, size_t n)

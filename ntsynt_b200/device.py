@@ -164,6 +164,13 @@ class BloomFilter:
     def insert_genome(self, genome, k):
         check(lib.nts_bf_insert_genome(self._h, genome._h, int(k)))
 
+    def build_common(self, level, genomes, k):
+        """self = AND over the genomes of their k-mer bit arrays (src/ntsynt_make_common_bf.cpp:107-160); `level` is a
+        scratch filter of the same size (None for one genome); both are zeroed inside"""
+        arr = (C.c_void_p * len(genomes))(*[g._h for g in genomes])
+        check(lib.nts_bf_build_common(self._h, level._h if level is not None else None, arr, len(genomes), int(k)))
+        return self
+
     def insert_repeats(self, scratch, genome, k):
         check(lib.nts_bf_insert_repeats(self._h, scratch._h, genome._h, int(k)))
 

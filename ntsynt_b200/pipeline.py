@@ -34,6 +34,13 @@ def build_common_bf(ctx, genomes, paths, k, fpr=0.025, nbytes=None, log=None):
     if log:
         log(f"BF size (bytes): {nbytes}")
     common = ctx.bloom(nbytes)
+    if not log:
+        # one call: per-genome binning and apply passes pipelined on two streams (nts_bf_build_common)
+        level = ctx.bloom(nbytes) if len(order) > 1 else None
+        common.build_common(level, [genomes[i] for i in order], k)
+        if level is not None:
+            level.close()
+        return common
     common.insert_genome(genomes[order[0]], k)
     if log:
         log(f"Bloom filter FPR: {common.fpr()}")

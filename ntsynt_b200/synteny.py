@@ -473,17 +473,15 @@ class SyntenyEngine:
                     edges.add((u, x) if u < x else (x, u))
         order = sorted(edges, key=lambda e: edge_key(*e))
 
-        def weight(u, x):
-            return bumped.get((u, x) if u < x else (x, u), nb[u][x])
-
-        def anchored(u):
-            return sum(1 for x in nb[u] if weight(u, x) == G) == 1
-
+        # number of full-weight edges at each candidate; a bump (visible to later iterations) adds one at both ends
+        fullc = {u: sum(1 for c_ in d.values() if c_ == G) for u, d in nb.items()}
         for s_, t_ in order:
-            if anchored(s_) and anchored(t_):
+            if fullc[s_] == 1 and fullc[t_] == 1:   # node_partially_anchored on both ends
                 common = [x for x in nb[s_] if x != t_ and x in nb[t_]]
                 if len(common) == 1:            # the edge itself + exactly one 2-step path
                     removed.append(common[0])
+                    if (s_, t_) not in bumped and nb[s_][t_] != G:
+                        fullc[s_] += 1; fullc[t_] += 1
                     bumped[(s_, t_)] = G
         return bumped, removed
 
@@ -549,8 +547,10 @@ class SyntenyEngine:
                     return v, v
                 r = int(np.searchsorted(starts, v, side="right") - 1)
                 return int(starts[r]), int(ends[r])
-            deg_all = (self.nbr[ends_all] >= 0).sum(axis=1)
-            cand_ends = ends_all[deg_all == 1].tolist()
+            nb_all = self.nbr[ends_all]
+            cand_ends = ends_all[(nb_all >= 0).sum(axis=1) == 1].tolist()
+            keys_arr = np.unique(np.concatenate([sv, ends_all]))
+            nbr_of = dict(zip(keys_arr.tolist(), self.nbr[keys_arr].tolist()))
             for e0 in cand_ends:
                 if run_bounds(e0)[0] in seen_runs:
                     continue
@@ -569,7 +569,7 @@ class SyntenyEngine:
                     if b > a:
                         inside = last - 1 if last == b else last + 1
                     nxt = -1
-                    for y in self.nbr[last].tolist():
+                    for y in (nbr_of.get(last) or self.nbr[last].tolist()):
                         if y < 0 or y == inside:
                             continue
                         if a == b and y == prev:
@@ -1064,11 +1064,16 @@ class SyntenyEngine:
         cand_v: the touched vertices with exactly three neighbours; inc_new: the new edges at those vertices."""
         G = self.G
 
+        memo = {}
+
         def nbrs(x):
-            res = {y: G for y in old_nbrs(x)}
-            for e in inc_new.get(x, ()):
-                y = e[1] if e[0] == x else e[0]
-                res[y] = wt[e]
+            res = memo.get(x)
+            if res is None:
+                res = {y: G for y in old_nbrs(x)}
+                for e in inc_new.get(x, ()):
+                    y = e[1] if e[0] == x else e[0]
+                    res[y] = wt[e]
+                memo[x] = res
             return res
 
         cand_v = set(cand_v)

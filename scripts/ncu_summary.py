@@ -2,7 +2,8 @@
 "summarise an .ncu-rep (raw page key metrics + top stall lines of the source page) as markdown"
 import csv, io, subprocess, sys
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+sel = ["--kernel-name", "regex:" + sys.argv[2], "--launch-count", "1"] if len(sys.argv) > 2 else []   # one kernel of the report
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", *sel], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
@@ -19,7 +20,7 @@ for r in rows[2:]:
     for w in want:
         if w in idx:
             print(f"| {w} | {r[idx[w]]} | {units[idx[w]]} |")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *sel], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
 if hi:
@@ -28,6 +29,8 @@ if hi:
     def num(x):
         try: return int(x)
         except ValueError: return 0
+    end = hi[1] if len(hi) > 1 else len(rows)                 # first launch of the selection only
+    rows = rows[:end]
     data = [(num(r[i_s]), r[i_src].strip(), num(r[i_ex])) for r in rows[hi[0] + 1:] if len(r) > i_ex and r[0].startswith("0x")]
     tot = sum(d[0] for d in data) or 1
     stall_cols = [(j, c) for j, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
