@@ -654,8 +654,10 @@ int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* 
         sum_valid += views[i]->total_valid;
     }
     // pipelined path: one bucket plan (sized for the largest genome) shared by both scratch slots
-    bool pipe = n >= 2;
-    if (const char* env = getenv("NTS_BF_PIPELINE")) { if (env[0] == '0') pipe = false; }
+    // Off unless NTS_BF_PIPELINE=1: measured on B200 the overlap buys nothing (both passes are bound by the SMs'
+    // LSU atomic issue rate -- profiles/README.md), and serial passes give clean per-kernel timings.
+    bool pipe = false;
+    if (const char* env = getenv("NTS_BF_PIPELINE")) pipe = n >= 2 && env[0] == '1';
     for (uint32_t i = 0; i < n && pipe; ++i) pipe = views[i]->total_valid > 0;
     for (int slot = 0; slot < 2 && pipe; ++slot) {
         bool ok = false;

@@ -68,7 +68,7 @@ int part_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t total_valid, bool*
         off[b + 1] = off[b] + c;
         chunk_first[b + 1] = chunk_first[b] + (c + CHUNK_ITEMS - 1) / CHUNK_ITEMS;
     }
-    if (chunk_first[P] > 0x7FFFFFF0ull) return NTS_OK;
+    if (chunk_first[P] > 0x7FFFFFF0ull || off[P] > 0xFFFFFFF0ull) return NTS_OK;   // 32-bit item indices in bf_bin_kernel
     PartScratch*& sc = g_scratch[{ctx, slot}];
     if (!sc) sc = new PartScratch();
     if (sc->items.n < off[P] && sc->items.alloc(off[P]) != cudaSuccess) { scratch_drop(ctx, slot); return NTS_OK; }   // no memory: direct path
@@ -96,7 +96,7 @@ int part_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const GenomeVi
     BinParams bp;
     bp.items = sc->items.p; bp.bucket_off = sc->bucket_off.p; bp.bucket_cap = sc->bucket_cap.p; bp.cursor = sc->cursor.p;
     bp.n_buckets = sc->P; bp.region_shift = sc->shift;
-    const size_t smem = sizeof(HashTables) + (size_t)BIN_TILE * 12 + (size_t)sc->P * 12;
+    const size_t smem = sizeof(HashTables) + (size_t)BIN_TILE * 12 + (size_t)sc->P * 12 + 4;
     NTS_CUDA(cudaFuncSetAttribute(bf_bin_kernel<BIN_THREADS, BIN_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t mprime = 0xFFFFFFFFFFFFFFFFull / m;
     const unsigned blocks = (unsigned)((total_valid + BIN_TILE - 1) / BIN_TILE);

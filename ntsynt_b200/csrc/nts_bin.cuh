@@ -45,12 +45,13 @@ __global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const 
     uint32_t* s_low = reinterpret_cast<uint32_t*>(s_tabs + 1);   // [TILE] bit index inside the region, slot = j*THREADS + tid
     uint32_t* s_br = s_low + TILE;                               // [TILE] bucket << 16 | rank inside the tile's run
     uint32_t* s_sorted = s_br + TILE;                            // [TILE] items in region order
-    uint32_t* s_cnt = s_sorted + TILE;                           // [P] count, then exclusive offset
-    uint32_t* s_base = s_cnt + bp.n_buckets;                     // [P] position of the run inside the bucket
-    uint32_t* s_fit = s_base + bp.n_buckets;                     // [P] how many items of the run fit
+    uint32_t* s_cnt = s_sorted + TILE;                           // [P + 1] count, then exclusive offset (+ sentinel n_tile)
+    uint32_t* s_dst = s_cnt + bp.n_buckets + 1;                  // [P] global item index of the run's first element
+    uint32_t* s_fit = s_dst + bp.n_buckets;                      // [P] how many items of the run fit the bucket
+    __shared__ uint16_t s_wb[TILE / 32];                         // bucket of the item at sorted position 32 * w
     __shared__ uint32_t s_wsum[THREADS / 32];
     stage_tables_bin(s_tabs, g_tabs, g.k);
-    for (uint32_t b = threadIdx.x; b < bp.n_buckets; b += THREADS) s_cnt[b] = 0;
+    for (uint32_t b = threadIdx.x; b <= bp.n_buckets; b += THREADS) s_cnt[b] = 0;
     __syncthreads();
     const uint64_t tile0 = (uint64_t)blockIdx.x * TILE;
     const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, total_valid - tile0);
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const 
             const uint32_t cap = bp.bucket_cap[b];
             fit = base >= cap ? 0u : min(c, cap - base);
         }
-        s_base[b] = base; s_fit[b] = fit;
+        s_dst[b] = (uint32_t)bp.bucket_off[b] + base;             // the item buffer holds fewer than 2^32 items (host-checked)
+        s_fit[b] = fit;
     }
     __syncthreads();
     // exclusive scan of the counts over the buckets
@@ -96,26 +98,29 @@ __global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const 
             carry += total;
             __syncthreads();
         }
+        if (threadIdx.x == 0) s_cnt[bp.n_buckets] = n_tile;        // sentinel: end of the last run
     }
-    // place the items in region order
+    __syncthreads();
+    // place the items in region order; remember the bucket at every 32nd position
     for (uint32_t j = 0; j < n_mine; ++j) {
         const uint32_t slot = j * THREADS + threadIdx.x;
         const uint32_t br = s_br[slot];
-        s_sorted[s_cnt[br >> 16] + (br & 0xFFFFu)] = s_low[slot];
+        const uint32_t pos = s_cnt[br >> 16] + (br & 0xFFFFu);
+        s_sorted[pos] = s_low[slot];
+        if ((pos & 31u) == 0) s_wb[pos >> 5] = (uint16_t)(br >> 16);
     }
     __syncthreads();
-    // write every run: warp w handles buckets w, w + n_warps, ...
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint32_t b = wid; b < bp.n_buckets; b += THREADS / 32) {
-        const uint32_t off = s_cnt[b];
-        const uint32_t c = (b + 1 < bp.n_buckets ? s_cnt[b + 1] : n_tile) - off;
-        if (!c) continue;
-        const uint32_t fit = s_fit[b];
-        uint32_t* dst = bp.items + bp.bucket_off[b] + s_base[b];
-        for (uint32_t i = lane; i < fit; i += 32) dst[i] = s_sorted[off + i];
-        const uint64_t region_bit0 = (uint64_t)b << bp.region_shift;      // overflow (heavy hitters): apply directly
-        for (uint32_t i = fit + lane; i < c; i += 32) {
-            const uint64_t idx = region_bit0 + s_sorted[off + i];
+    // write out, one thread per item: consecutive threads hold consecutive sorted positions, i.e. a warp writes
+    // the tails / heads of two or three bucket runs as contiguous segments
+    for (uint32_t i = threadIdx.x; i < n_tile; i += THREADS) {
+        uint32_t b = s_wb[i >> 5];
+        while (s_cnt[b + 1] <= i) ++b;                             // skips the (few) run ends inside the 32-group
+        const uint32_t r = i - s_cnt[b];
+        const uint32_t x = s_sorted[i];
+        if (r < s_fit[b]) {
+            bp.items[(uint64_t)s_dst[b] + r] = x;
+        } else {                                                   // overflow (heavy hitters): apply directly
+            const uint64_t idx = ((uint64_t)b << bp.region_shift) + x;
             atomicOr(&bits[idx >> 5], 1u << (idx & 31));
         }
     }

@@ -315,6 +315,7 @@ def test_pipelined_common_filter_equals_sequential_inserts(cuda_ctx, G):
         lvl.clear(); lvl.insert_genome(g, k); want.iand(lvl)
     bits = want.to_numpy()
     os.environ["NTS_BF_PARTITION"] = "1"             # small filters would otherwise take the direct path
+    os.environ["NTS_BF_PIPELINE"] = "1"              # two-stream schedule (off by default: no gain measured)
     try:
         got = cuda_ctx.bloom(nbytes)
         got.from_numpy(np.full(nbytes, 0xFF, dtype=np.uint8))      # must be cleared inside
@@ -322,8 +323,12 @@ def test_pipelined_common_filter_equals_sequential_inserts(cuda_ctx, G):
         assert np.array_equal(got.to_numpy(), bits)
         got.build_common(lvl, gens, k)                             # and be repeatable
         assert np.array_equal(got.to_numpy(), bits)
+        del os.environ["NTS_BF_PIPELINE"]
+        got.build_common(lvl, gens, k)                             # serial schedule of the same call
+        assert np.array_equal(got.to_numpy(), bits)
     finally:
         del os.environ["NTS_BF_PARTITION"]
+        os.environ.pop("NTS_BF_PIPELINE", None)
     one = cuda_ctx.bloom(nbytes)
     one.build_common(None, gens[:1], k)
     solo = cuda_ctx.bloom(nbytes); solo.insert_genome(gens[0], k)
