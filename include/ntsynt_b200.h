@@ -251,6 +251,23 @@ int nts_graph_lookup(nts_graph* g, const uint64_t* h1, uint64_t n, uint32_t* vid
 int nts_graph_edges(nts_graph* g, uint64_t* n_edges);
 int nts_graph_download_edges(nts_graph* g, uint32_t* u, uint32_t* v, uint32_t* support);
 
+/* ---- native host-side pieces of the graph stage (no device work; operate on the caller's host arrays) ------------
+ * nts_host_walk_paths: find_paths (subprojects/ntJoin/bin/ntjoin.py:114-151) over the components of the
+ * weight-filtered graph that contain an edge other than (i, i+1).  nbr = [n_vertices x 2] neighbours or -1;
+ * (starts, ends) = the n_runs maximal (i, i+1) chains over base vertices [0, V0), ascending; sv = the n_sv vertices
+ * holding such an edge, ascending; opos = position of every vertex in the orienting assembly.  Paths come back as
+ * segments (lo, hi, dir = +1 / -1) with path p owning segments [path_off[p], path_off[p+1]); seg_cap >= 2 * n_sv + 2. */
+int nts_host_walk_paths(const int32_t* nbr, int64_t V0, const int64_t* starts, const int64_t* ends, int64_t n_runs,
+                        const int64_t* sv, int64_t n_sv, const int64_t* opos, int64_t* seg_lo, int64_t* seg_hi,
+                        int8_t* seg_dir, int64_t* path_off, int64_t seg_cap, int64_t* n_paths, int64_t* n_segs);
+/* nts_host_simplify: run_graph_simplification on the round-0 graph (bin/ntsynt_synteny.py:548-590), candidate edges
+ * visited in build_graph's edge-id order (subprojects/ntJoin/bin/ntjoin_utils.py:97-115).  cand = the n_cand vertices
+ * with exactly three distinct neighbours, ascending; rank / inv = [G x V]; ctg = [G x ctg_stride].  For every edge
+ * that fires: bump_s < bump_t (the edge that becomes full weight) and removed (the triangle's third vertex). */
+int nts_host_simplify(const int64_t* cand, int64_t n_cand, const uint32_t* rank, const uint32_t* inv, const int32_t* ctg,
+                      int64_t ctg_stride, int64_t V, uint32_t G, int64_t* bump_s, int64_t* bump_t, int64_t* removed,
+                      int64_t out_cap, int64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,7 @@ lib = _load()
 
 u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
 vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
+i64p = C.POINTER(C.c_int64)
 
 _SIGS = {
     "nts_version": (C.c_char_p, []),
@@ -110,6 +111,10 @@ _SIGS = {
     "nts_graph_download_host_arrays": (C.c_int, [vp, C.c_uint64, u64p, C.POINTER(C.c_longlong), C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_int32), u8p]),
     "nts_graph_sparse_lists": (C.c_int, [vp, C.c_uint32, u32p, u32p, u32p, u64p]),
+    "nts_host_walk_paths": (C.c_int, [C.POINTER(C.c_int32), C.c_int64, i64p, i64p, C.c_int64, i64p, C.c_int64, i64p, i64p, i64p,
+                                      C.POINTER(C.c_int8), i64p, C.c_int64, i64p, i64p]),
+    "nts_host_simplify": (C.c_int, [i64p, C.c_int64, u32p, u32p, C.POINTER(C.c_int32), C.c_int64, C.c_int64, C.c_uint32,
+                                    i64p, i64p, i64p, C.c_int64, i64p]),
     "nts_graph_lookup": (C.c_int, [vp, u64p, C.c_uint64, u32p]),
     "nts_graph_edges": (C.c_int, [vp, u64p]),
     "nts_graph_download_edges": (C.c_int, [vp, u32p, u32p, u32p]),

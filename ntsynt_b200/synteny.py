@@ -138,6 +138,7 @@ class SyntenyEngine:
         self.labels = [(mt.group(1) if (mt := re.search(FA_TSV_RE, nm)) else nm) for nm in self.names]
         self.outputs = {}
         self.stats = {}
+        self.native = True       # irregular walks in C++ (csrc/nts_hostgraph.cu); False = the Python statements of the same rules
 
     def log(self, *a):
         if not self.quiet:
@@ -426,6 +427,23 @@ class SyntenyEngine:
         if not len(cand):
             return bumped, removed
         ctg0 = self.CTG if self._ctg0 is None else self._ctg0
+        if self.native:
+            # same visiting order and rules, in C++ (csrc/nts_hostgraph.cu: nts_host_simplify)
+            import ctypes as C
+            from ._lib import check, lib, ptr
+            cand64 = np.ascontiguousarray(cand, dtype=np.int64)
+            rank = np.ascontiguousarray(self.RANK, dtype=np.uint32)
+            inv = np.ascontiguousarray(self.INV, dtype=np.uint32)
+            if not (ctg0.dtype == np.int32 and ctg0.strides[1] == 4):
+                ctg0 = np.ascontiguousarray(ctg0, dtype=np.int32)
+            cap = 4 * len(cand64) + 4
+            bs, bt, rm = (np.empty(cap, dtype=np.int64) for _ in range(3))
+            n_out = C.c_int64()
+            check(lib.nts_host_simplify(ptr(cand64, C.c_int64), len(cand64), ptr(rank, C.c_uint32), ptr(inv, C.c_uint32),
+                                        ctg0.ctypes.data_as(C.POINTER(C.c_int32)), ctg0.strides[0] // 4, V0, G,
+                                        ptr(bs, C.c_int64), ptr(bt, C.c_int64), ptr(rm, C.c_int64), cap, C.byref(n_out)))
+            n = n_out.value
+            return dict(zip(zip(bs[:n].tolist(), bt[:n].tolist()), [G] * n)), rm[:n].tolist()
         left, right, ranks = [], [], []
         for a in range(G):
             r = self.RANK[a, cand].astype(np.int64)
@@ -525,7 +543,28 @@ class SyntenyEngine:
                 paths.append([(a, b, 1)])
             elif y < x:
                 paths.append([(a, b, -1)])
-        if real_sparse:
+        if real_sparse and self.native:
+            # the walk over runs joined by sparse edges, in C++ (csrc/nts_hostgraph.cu: nts_host_walk_paths)
+            import ctypes as C
+            from ._lib import check, lib, ptr
+            sv = np.array(sorted(real_sparse), dtype=np.int64)
+            starts64 = np.ascontiguousarray(starts, dtype=np.int64)
+            ends64 = np.ascontiguousarray(ends, dtype=np.int64)
+            opos64 = np.ascontiguousarray(opos, dtype=np.int64)
+            nbr32 = self.nbr if self.nbr.flags.c_contiguous else np.ascontiguousarray(self.nbr)
+            cap = 2 * len(sv) + 2
+            slo, shi, poff = (np.empty(cap + 1, dtype=np.int64) for _ in range(3))
+            sdir = np.empty(cap + 1, dtype=np.int8)
+            n_p, n_s = C.c_int64(), C.c_int64()
+            check(lib.nts_host_walk_paths(nbr32.ctypes.data_as(C.POINTER(C.c_int32)), V0, ptr(starts64, C.c_int64),
+                                          ptr(ends64, C.c_int64), len(starts64), ptr(sv, C.c_int64), len(sv),
+                                          ptr(opos64, C.c_int64), ptr(slo, C.c_int64), ptr(shi, C.c_int64),
+                                          sdir.ctypes.data_as(C.POINTER(C.c_int8)), ptr(poff, C.c_int64), cap,
+                                          C.byref(n_p), C.byref(n_s)))
+            segs_all = list(zip(slo[:n_s.value].tolist(), shi[:n_s.value].tolist(), sdir[:n_s.value].tolist()))
+            off = poff[:n_p.value + 1].tolist()
+            paths.extend(segs_all[off[i]:off[i + 1]] for i in range(n_p.value))
+        elif real_sparse:
             seen_runs = set()
             sv = np.array(sorted(real_sparse), dtype=np.int64)
             ra, rb = sv.copy(), sv.copy()

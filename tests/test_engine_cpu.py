@@ -14,12 +14,13 @@ from oracle import sketch_oracle as so
 from oracle.graph_oracle import GraphOracle
 
 
-def run_engine(paths, k, w, w_rounds, indel, merge, z, lean=False):
+def run_engine(paths, k, w, w_rounds, indel, merge, z, lean=False, native=True):
     bases = [os.path.basename(p)[:-3] if p.endswith(".gz") else os.path.basename(p) for p in paths]
     tsv = [f"{b}.k{k}.w{w}.tsv" for b in bases]
     order = sorted(range(len(paths)), key=lambda i: tsv[i], reverse=True)
     be = OracleBackend([paths[i] for i in order], [tsv[i] for i in order], k, lean=lean)
     eng = SyntenyEngine(be, k, w, w_rounds, indel, merge, z, write_files=False, quiet=True)
+    eng.native = native      # C++ walks (csrc/nts_hostgraph.cu) or their Python statements
     eng.run()
     return eng, be
 
@@ -63,6 +64,10 @@ def test_engine_equals_graph_oracle_on_rearranged_genomes(tmp_path, seed, G, pre
     assert eng.outputs["final"] == go.outputs["final"]
     assert eng.outputs["pre_merge"] == go.outputs["pre_merge"]
     assert eng.outputs["final"].count("\n") >= G * 3
+    # the Python statements of the two native walks give the same blocks and the same intermediate counts
+    eng_py, _ = run_engine(paths, k, w, w_rounds, indel, merge, z, lean=bool(seed % 2), native=False)
+    assert eng_py.outputs == eng.outputs
+    assert eng_py.stats["simplified_vertices"] == eng.stats["simplified_vertices"] and eng_py.stats["paths"] == eng.stats["paths"]
 
 
 def test_interval_index_matches_bruteforce():
