@@ -300,7 +300,7 @@ def run_ours(args, dist):
     dist.barrier(); ctx.sync()
     ctx.timer_start()
     for _ in range(e2e_steps):
-        fresh = [ctx.upload(pk) for pk, _ in packed_host]
+        fresh = [ctx.upload(pk, async_copy=True) for pk, _ in packed_host]     # H2D of genome i+1 overlaps insert i
         text_e2e, _ = hot_path(fresh)
         for f in fresh:
             f.close()

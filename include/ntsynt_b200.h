@@ -94,6 +94,13 @@ int nts_unpack_ascii(const uint64_t* words, uint64_t start, uint64_t n, char* ou
 int nts_genome_upload(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const uint64_t* contig_word_off,
                       const uint64_t* words, uint64_t n_words, const uint64_t* nrun_off, const uint64_t* nrun_start,
                       const uint64_t* nrun_len, nts_genome** out);
+/* Same, but the host->device copy is queued on the context's copy stream and the call returns at once; every entry
+ * point that reads the genome orders itself after the copy.  `words` must stay valid (and should be page-locked,
+ * nts_host_alloc) until the first such call has completed.  Lets the upload of genome i+1 overlap the Bloom insert
+ * of genome i (the reference re-reads every FASTA per stage instead: src/ntsynt_make_common_bf.cpp:125,143). */
+int nts_genome_upload_async(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const uint64_t* contig_word_off,
+                      const uint64_t* words, uint64_t n_words, const uint64_t* nrun_off, const uint64_t* nrun_start,
+                      const uint64_t* nrun_len, nts_genome** out);
 void nts_genome_destroy(nts_genome* g);
 /* total bases, Ns included (the `n` of approximate_bf_size, cpp:34-36) */
 uint64_t nts_genome_size(const nts_genome* g);

@@ -62,6 +62,7 @@ _SIGS = {
     "nts_pack_ascii": (C.c_int, [C.c_char_p, C.c_uint64, u64p, u64p, u64p, C.c_uint64, u64p]),
     "nts_unpack_ascii": (C.c_int, [u64p, C.c_uint64, C.c_uint64, C.c_char_p]),
     "nts_genome_upload": (C.c_int, [vp, C.c_uint32, u64p, u64p, u64p, C.c_uint64, u64p, u64p, u64p, vpp]),
+    "nts_genome_upload_async": (C.c_int, [vp, C.c_uint32, u64p, u64p, u64p, C.c_uint64, u64p, u64p, u64p, vpp]),
     "nts_genome_destroy": (None, [vp]),
     "nts_genome_size": (C.c_uint64, [vp]),
     "nts_genome_contigs": (C.c_uint32, [vp]),

@@ -191,8 +191,20 @@ static int build_view(const nts_genome* g, uint32_t k, const uint64_t* mask_off,
     return NTS_OK;
 }
 
+// order ctx->stream after an asynchronous upload of the genome (once; later work on the stream is ordered by it)
+static int wait_ready(const nts_genome* g)
+{
+    nts_genome* gm = const_cast<nts_genome*>(g);
+    if (gm->ready && !gm->ready_waited) {
+        NTS_CUDA(cudaStreamWaitEvent(gm->ctx->stream, gm->ready, 0));
+        gm->ready_waited = true;
+    }
+    return NTS_OK;
+}
+
 static int get_plain_view(const nts_genome* g, uint32_t k, const nts_view** out)
 {
+    { int rc = wait_ready(g); if (rc) return rc; }
     nts_genome* gm = const_cast<nts_genome*>(g);
     auto it = gm->views.find(k);
     if (it == gm->views.end()) {
@@ -277,6 +289,7 @@ void nts_ctx_destroy(nts_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -430,9 +443,9 @@ int nts_unpack_ascii(const uint64_t* words, uint64_t start, uint64_t n, char* ou
     return NTS_OK;
 }
 
-int nts_genome_upload(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const uint64_t* contig_word_off,
-                      const uint64_t* words, uint64_t n_words, const uint64_t* nrun_off, const uint64_t* nrun_start,
-                      const uint64_t* nrun_len, nts_genome** out)
+static int genome_upload_impl(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const uint64_t* contig_word_off,
+                              const uint64_t* words, uint64_t n_words, const uint64_t* nrun_off, const uint64_t* nrun_start,
+                              const uint64_t* nrun_len, bool async_copy, nts_genome** out)
 {
     if (!ctx || !out || !contig_len || !contig_word_off || !nrun_off) return fail(NTS_ERR_ARG, "null argument");
     if (n_words && !words) return fail(NTS_ERR_ARG, "words is null");
@@ -457,19 +470,49 @@ int nts_genome_upload(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_l
     if (nr) { g->nrun_start.assign(nrun_start, nrun_start + nr); g->nrun_len.assign(nrun_len, nrun_len + nr); }
     // two guard words so that cursor pre-loads one word past the last base stay in bounds
     if (g->packed.alloc(n_words + 2) != cudaSuccess) { delete g; return fail(NTS_ERR_NOMEM, "device allocation failed (genome)"); }
-    cudaError_t e = cudaMemsetAsync(g->packed.p + n_words, 0, 16, ctx->stream);
-    if (e == cudaSuccess && n_words)
-        e = copy_h2d(ctx, g->packed.p, words, n_words * 8);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { delete g; return fail(NTS_ERR_CUDA, std::string("genome upload: ") + cudaGetErrorString(e)); }
+    cudaError_t e = cudaSuccess;
+    if (async_copy) {
+        // copy on the context's H2D stream; consumers order themselves after `ready` (wait_ready)
+        if (!ctx->stream_copy) e = cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMemsetAsync(g->packed.p + n_words, 0, 16, ctx->stream_copy);
+        if (e == cudaSuccess && n_words) {
+            ctx->h2d_bytes += n_words * 8;
+            e = cudaMemcpyAsync(g->packed.p, words, n_words * 8, cudaMemcpyHostToDevice, ctx->stream_copy);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(g->ready, ctx->stream_copy);
+        g->ready_waited = false;
+    } else {
+        e = cudaMemsetAsync(g->packed.p + n_words, 0, 16, ctx->stream);
+        if (e == cudaSuccess && n_words)
+            e = copy_h2d(ctx, g->packed.p, words, n_words * 8);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e != cudaSuccess) { if (g->ready) cudaEventDestroy(g->ready); delete g; return fail(NTS_ERR_CUDA, std::string("genome upload: ") + cudaGetErrorString(e)); }
     *out = g;
     return NTS_OK;
 }
+
+int nts_genome_upload(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const uint64_t* contig_word_off,
+                      const uint64_t* words, uint64_t n_words, const uint64_t* nrun_off, const uint64_t* nrun_start,
+                      const uint64_t* nrun_len, nts_genome** out)
+{
+    return genome_upload_impl(ctx, n_contigs, contig_len, contig_word_off, words, n_words, nrun_off, nrun_start, nrun_len, false, out);
+}
+
+int nts_genome_upload_async(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, const uint64_t* contig_word_off,
+                            const uint64_t* words, uint64_t n_words, const uint64_t* nrun_off, const uint64_t* nrun_start,
+                            const uint64_t* nrun_len, nts_genome** out)
+{
+    return genome_upload_impl(ctx, n_contigs, contig_len, contig_word_off, words, n_words, nrun_off, nrun_start, nrun_len, true, out);
+}
+
 
 void nts_genome_destroy(nts_genome* g)
 {
     if (!g) return;
     cudaSetDevice(g->ctx->device);
+    if (g->ready) { cudaEventSynchronize(g->ready); cudaEventDestroy(g->ready); }   // the copy must not outlive the buffer
     for (auto& kv : g->views) delete kv.second;
     delete g;
 }
@@ -481,6 +524,7 @@ int nts_genome_download_contig(nts_genome* g, uint32_t contig, uint64_t* words_o
 {
     if (!g || contig >= g->n_contigs || !words_out) return fail(NTS_ERR_ARG, "bad argument");
     NTS_CUDA(cudaSetDevice(g->ctx->device));
+    { int rc = wait_ready(g); if (rc) return rc; }
     NTS_CUDA(copy_d2h(g->ctx, words_out, g->packed.p + g->contig_word_off[contig],
                       nts_packed_words(g->contig_len[contig]) * 8));
     NTS_CUDA(cudaStreamSynchronize(g->ctx->stream));
@@ -645,19 +689,19 @@ int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* 
     const HashTables* tabs = nullptr;
     int rc = get_tables(ctx, k, &tabs);
     if (rc) return rc;
-    std::vector<const nts_view*> views(n);
-    uint64_t max_valid = 0, sum_valid = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        rc = get_plain_view(genomes[i], k, &views[i]);
-        if (rc) return rc;
-        max_valid = std::max(max_valid, views[i]->total_valid);
-        sum_valid += views[i]->total_valid;
-    }
     // pipelined path: one bucket plan (sized for the largest genome) shared by both scratch slots
     // Off unless NTS_BF_PIPELINE=1: measured on B200 the overlap buys nothing (both passes are bound by the SMs'
     // LSU atomic issue rate -- profiles/README.md), and serial passes give clean per-kernel timings.
     bool pipe = false;
     if (const char* env = getenv("NTS_BF_PIPELINE")) pipe = n >= 2 && env[0] == '1';
+    std::vector<const nts_view*> views(n);
+    uint64_t max_valid = 0, sum_valid = 0;
+    for (uint32_t i = 0; i < n && pipe; ++i) {          // (the serial path takes each view when it gets to the genome, so
+        rc = get_plain_view(genomes[i], k, &views[i]);  //  that an asynchronous upload of genome i+1 overlaps insert i)
+        if (rc) return rc;
+        max_valid = std::max(max_valid, views[i]->total_valid);
+        sum_valid += views[i]->total_valid;
+    }
     for (uint32_t i = 0; i < n && pipe; ++i) pipe = views[i]->total_valid > 0;
     for (int slot = 0; slot < 2 && pipe; ++slot) {
         bool ok = false;
@@ -873,6 +917,7 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
         if (rc) return rc;
     }
     struct ViewGuard { nts_view* p; ~ViewGuard() { delete p; } } guard{owned};
+    if ((rc = wait_ready(g))) return rc;
 
     // tiles: one per R * T window ends of a contig; each stands for up to R output slots (dense sub-tiles)
     std::vector<TileDesc> tiles;

@@ -70,6 +70,7 @@ struct nts_ctx {
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // side stream of the pipelined Bloom-filter build (created on first use)
+    cudaStream_t stream_copy = nullptr;   // H2D stream of nts_genome_upload_async (created on first use)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     uint64_t sketch_escalated = 0;   // dense sub-tiles the sparse sketch kernel handed to the dense one (statistics)
@@ -125,6 +126,8 @@ struct nts_genome {
     nts::DevBuf<uint64_t> packed;
     std::vector<uint64_t> nrun_off, nrun_start, nrun_len;   // host copy (tiny)
     std::map<uint32_t, nts_view*> views;     // unmasked views per k
+    cudaEvent_t ready = nullptr;             // async upload: recorded after the H2D copy on ctx->stream_copy
+    bool ready_waited = true;                // ctx->stream already ordered after `ready`
 };
 
 struct nts_bf {

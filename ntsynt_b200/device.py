@@ -62,8 +62,10 @@ class Context:
         return f.value, t.value
 
     # -- genome
-    def upload(self, packed):
-        return DeviceGenome(self, packed)
+    def upload(self, packed, async_copy=False):
+        """async_copy: queue the H2D copy on the context's copy stream and return at once (the packed words should be
+        page-locked and are kept alive by the returned object); consumers order themselves after the copy"""
+        return DeviceGenome(self, packed, async_copy)
 
     # -- Bloom filter
     def bloom(self, nbytes):
@@ -105,8 +107,9 @@ class Context:
 
 
 class DeviceGenome:
-    def __init__(self, ctx, packed):
+    def __init__(self, ctx, packed, async_copy=False):
         self.ctx = ctx
+        self._keep = packed.words if async_copy else None      # the copy may still be reading it
         self.names = list(packed.names)
         self.lengths = np.asarray(packed.lengths, dtype=np.uint64)
         self.n_contigs = len(self.names)
@@ -114,7 +117,7 @@ class DeviceGenome:
         words = packed.words if packed.words.size else np.zeros(1, dtype=np.uint64)
         ns = packed.nrun_start if packed.nrun_start.size else np.zeros(1, dtype=np.uint64)
         nl = packed.nrun_len if packed.nrun_len.size else np.zeros(1, dtype=np.uint64)
-        check(lib.nts_genome_upload(ctx._h, self.n_contigs, ptr(self.lengths, C.c_uint64),
+        check((lib.nts_genome_upload_async if async_copy else lib.nts_genome_upload)(ctx._h, self.n_contigs, ptr(self.lengths, C.c_uint64),
                                     ptr(packed.word_off, C.c_uint64), ptr(words, C.c_uint64), int(packed.words.size),
                                     ptr(packed.nrun_off, C.c_uint64), ptr(ns, C.c_uint64), ptr(nl, C.c_uint64),
                                     C.byref(h)))

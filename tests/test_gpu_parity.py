@@ -333,3 +333,24 @@ def test_pipelined_common_filter_equals_sequential_inserts(cuda_ctx, G):
     one.build_common(None, gens[:1], k)
     solo = cuda_ctx.bloom(nbytes); solo.insert_genome(gens[0], k)
     assert np.array_equal(one.to_numpy(), solo.to_numpy())
+
+
+def test_async_upload_gives_the_same_filter_and_sketch(cuda_ctx):
+    "nts_genome_upload_async: consumers order themselves after the copy (page-locked source)"
+    k, w = 24, 200
+    recs = _tricky_records(seed=21)
+    packed = fasta.pack_records(recs) if hasattr(fasta, "pack_records") else None
+    if packed is None:
+        pytest.skip("no in-memory packer")
+    pin = device.PinnedU64(len(packed.words))
+    pin.array[:] = packed.words
+    sync_g = cuda_ctx.upload(packed)
+    packed.words = pin.array
+    async_g = cuda_ctx.upload(packed, async_copy=True)
+    nbytes = so.bf_bytes(sum(len(s) for _, s in recs), 0.025)
+    a, b = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
+    b.build_common(None, [async_g], k)              # first consumer of the async genome
+    a.insert_genome(sync_g, k)
+    assert np.array_equal(a.to_numpy(), b.to_numpy())
+    for x, y in zip(cuda_ctx.sketch(sync_g, k, w, common=a).to_numpy(), cuda_ctx.sketch(async_g, k, w, common=b).to_numpy()):
+        assert np.array_equal(x, y)
