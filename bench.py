@@ -10,9 +10,11 @@ re-sketch + graph), erosion, collinear merges, final block table as TSV text.
 
 N = 1  : BASELINE.json configs[1]: 2 synthetic ~3 Gbp human-like genomes, d = 1 %, k = 24, w = 1000,
          presets of bin/ntSynt:92-94 (block_size 1000, indel 50000, merge 100000, w_rounds 250 100).
-N > 1  : configs[4]: one 3 Gbp genome per GPU (G = N), per-GPU Bloom filters merged over NCCL (sum of
-         packed counters), then every rank sketches its genome and rank 0 runs the graph stage on the
-         gathered tables.  Weak scaling: per-GPU work is fixed.
+N > 1  : configs[4]: one 3 Gbp genome per GPU (G = N), per-GPU Bloom filters merged over NVLink -- by default with
+         the peer-memory reduce-scatter / all-gather kernels (csrc/nts_p2p.cu), or with --merge nccl by one NCCL
+         all-reduce(sum) over packed counters (the north-star form; bit-identical, ~4x the wire volume; both are
+         timed alone in config.merge_alone_ms) -- then every rank sketches its genome and rank 0 runs the
+         graph stage on the gathered tables.  Weak scaling: per-GPU work is fixed.
 
 `value` times the path with the packed genomes already resident in HBM; `e2e` times the same call
 chain starting from packed genomes in PINNED HOST memory (H2D inside the timed region) and ending
@@ -408,6 +410,8 @@ def run_ours_multi(args, dist, ctx):
     ident = distributed.Comm.new_unique_id() if rank == 0 else b""
     comm = distributed.Comm(ctx, rank, N, dist.bcast_bytes(ident, 128))
     peer = distributed.PeerMerge(mine, rank, N, dist.gather_objects, dist.barrier) if N <= 16 else None
+    if peer is not None and not peer.ok:           # no peer access on some rank: the NCCL form is the fallback
+        peer = None
     use_p2p = args.merge == "p2p" and peer is not None
 
     def hot_path(gen_map):
@@ -515,7 +519,8 @@ def run_ours_multi(args, dist, ctx):
             "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{G} synthetic {args.genome_mbp:g} Mbp genomes one-per-GPU, counting-BF NCCL-sum merge, "
+            "config": {"workload": f"{G} synthetic {args.genome_mbp:g} Mbp genomes one-per-GPU, Bloom filters merged over NVLink "
+                                   f"({'peer-memory AND kernels' if use_p2p else 'counting-BF NCCL-sum'}), "
                                    f"d={d:g}, k={K} w={W}, w_rounds {ps['w_rounds']}, {N}xB200",
                        "genomes": G, "genome_bp": sizes[0], "k": K, "w": W, "fpr": 0.025, "bloom_bytes": nbytes,
                        "merge": "p2p" if use_p2p else "nccl",
@@ -588,9 +593,10 @@ def main():
     ap.add_argument("--cpu-sample-mbp", type=float, default=24.0, help="per-genome sample for the CPU arm")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--merge", choices=["nccl", "p2p"], default="nccl",
-                    help="multi-GPU filter merge: NCCL all-reduce(sum) of packed counters (default, the north-star form) "
-                         "or the peer-memory reduce-scatter/all-gather kernels")
+    ap.add_argument("--merge", choices=["nccl", "p2p"], default="p2p",
+                    help="multi-GPU filter merge: peer-memory reduce-scatter/all-gather kernels over NVLink (default; "
+                         "bit-identical and ~4x less wire volume) or NCCL all-reduce(sum) of packed counters (the "
+                         "north-star form; also timed alone in config.merge_alone_ms)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: fewer than 3 warm-up steps; the number is not reportable", file=sys.stderr)

@@ -85,8 +85,13 @@ class PeerMerge:
         handles = b"".join(gather(bytes(mine)))
         buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
         h = C.c_void_p()
-        check(lib.nts_p2p_open(bf._h, buf, int(rank), int(world), C.byref(h)))
-        self._h = h
+        rc = lib.nts_p2p_open(bf._h, buf, int(rank), int(world), C.byref(h))
+        # every rank must agree: one rank without peer access would leave the others waiting in merge()
+        self.ok = all(gather(rc == 0))
+        self._h = h if rc == 0 else None
+        if not self.ok and self._h:
+            lib.nts_p2p_close(self._h)
+            self._h = None
         barrier()
 
     def merge(self, op="and"):
