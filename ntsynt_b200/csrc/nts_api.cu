@@ -890,7 +890,9 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     if (const char* env = getenv("NTS_SKETCH_DENSE")) { if (env[0] == '1') sparse = false; }
     uint32_t R = 1, NT_s = 0, C_s = 0, tau_hi = 0;
     if (sparse) {
-        const double density = 32.0 / (double)w;                  // ~32 candidates per window
+        double lambda = 24.0;                                     // candidates expected per window
+        if (const char* env = getenv("NTS_SKETCH_LAMBDA")) { double x = atof(env); if (x >= 4.0 && x <= 256.0) lambda = x; }
+        const double density = lambda / (double)w;
         uint32_t c_target = (uint32_t)(3.1 / density);
         c_target = std::max<uint32_t>(4, std::min<uint32_t>(c_target, 120));
         const uint32_t nt_target = std::max<uint32_t>(THREADS * c_target, 2 * w);

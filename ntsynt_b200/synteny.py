@@ -162,7 +162,7 @@ class SyntenyEngine:
         self._pair_orig, self._pair_delta = {}, {}      # corrections to the device prefix sums (see _refresh_pairs)
         self._br_touched = set()                        # pairs (i, i+1) whose `conn` changed since _breaks was made
         self.sparse = set()                             # vertices that may hold a non-(i,i+1) edge
-        self._ctg0 = None                               # copy-on-write snapshot of round-0 contigs
+        self._ctg0 = {}                                 # (assembly, base vertex) -> round-0 contig, for the few overwritten entries
         if self._prebuilt:
             # lean form (device backend): the O(V) columns arrive in their final dtype and layout, written by the
             # device into pinned buffers with room for the vertices later rounds add
@@ -279,7 +279,8 @@ class SyntenyEngine:
         return up, down
 
     def _ctg_round0(self, a, v):
-        return (self.CTG if self._ctg0 is None else self._ctg0)[a, v]
+        got = self._ctg0.get((a, int(v))) if self._ctg0 else None
+        return self.CTG[a, v] if got is None else got
 
     def _grow(self, need):
         cap = len(self.H)
@@ -426,7 +427,7 @@ class SyntenyEngine:
         bumped, removed = {}, []
         if not len(cand):
             return bumped, removed
-        ctg0 = self.CTG if self._ctg0 is None else self._ctg0
+        ctg0 = self.CTG                                 # round 0: nothing has been overwritten yet
         if self.native:
             # same visiting order and rules, in C++ (csrc/nts_hostgraph.cu: nts_host_simplify)
             import ctypes as C
@@ -1002,13 +1003,14 @@ class SyntenyEngine:
                 kh, kp, kc, _ = lists[a]
                 vid = cid[np.searchsorted(common, kh)]
                 changed = (self.POS[a, vid] != kp) | (self.CTG[a, vid] != kc)
-                touched.append(vid[changed & (vid < self.V0)])
+                tb = vid[changed & (vid < self.V0)]
+                for v_, c_ in zip(tb.tolist(), self.CTG[a, tb].tolist()):      # keep the round-0 contig of what gets overwritten
+                    self._ctg0.setdefault((a, v_), c_)
+                touched.append(tb)
                 ids_per_asm.append(vid)
             touched_base = np.unique(np.concatenate(touched)) if touched else np.zeros(0, dtype=np.int64)
             pairs = old = None
             if len(touched_base):
-                if self._ctg0 is None:
-                    self._ctg0 = self.CTG[:, :self.V0].copy()
                 self.stats["base_overwrites"] = self.stats.get("base_overwrites", 0) + len(touched_base)
                 pairs = self._pairs_around(touched_base)
                 old = self._pair_values(pairs)
@@ -1232,10 +1234,9 @@ class SyntenyEngine:
             self._remove_vertices(np.array(removed, dtype=np.int64))
         if bumped:
             be_ = np.array(list(bumped.keys()), dtype=np.int64)
-            ok = self.alive[be_[:, 0]] & self.alive[be_[:, 1]]
-            for s_, t_ in be_[ok].tolist():
-                if not self._has_edge(s_, t_):
-                    self._add_edge(s_, t_)
+            be_ = be_[self.alive[be_[:, 0]] & self.alive[be_[:, 1]]]
+            has = (self.nbr[be_[:, 0], 0] == be_[:, 1]) | (self.nbr[be_[:, 0], 1] == be_[:, 1])
+            self._add_edges(be_[~has, 0], be_[~has, 1])
         # --- paths, blocks
         self.log("Finding paths")
         self._tick("filter0")
