@@ -11,6 +11,7 @@ import synth_small
 from backends import numpy_edges, numpy_join
 from conftest import MINI, mini_expected, mini_fastas, parse_sketch_tsv
 from ntsynt_b200 import _lib, device, fasta, pipeline, synth
+from ntsynt_b200.synteny import SyntenyEngine
 from oracle import sketch_oracle as so
 from oracle.graph_oracle import GraphOracle
 
@@ -354,3 +355,44 @@ def test_async_upload_gives_the_same_filter_and_sketch(cuda_ctx):
     assert np.array_equal(a.to_numpy(), b.to_numpy())
     for x, y in zip(cuda_ctx.sketch(sync_g, k, w, common=a).to_numpy(), cuda_ctx.sketch(async_g, k, w, common=b).to_numpy()):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("G,mbp,d", [(2, 16, 1.0), (3, 12, 1.3), (5, 8, 12.0)])
+def test_baseline_configs_at_reduced_size_equal_the_oracle(cuda_ctx, G, mbp, d):
+    """BASELINE.json configs 2 / 3 / 4 (2 genomes d=1; 3 genomes d=1.3; 5 genomes d=12 with w_rounds 500 250) on the
+    bench's own synthetic generator at a size the CPU oracle finishes in seconds: k=24, w=1000, presets of
+    bin/ntSynt:89-99.  Filter bits, round-0 sketches and both block files must equal the oracle's."""
+    import bench
+    k, w = 24, 1000
+    ps = bench.presets(d)
+    wl = synth.Workload(G, int(mbp * 1e6), d)
+    gens = [wl.materialize(cuda_ctx, g) for g in range(G)]
+    files = [wl.file_name(g) for g in range(G)]
+    names = [pipeline.tsv_name(f, k, w) for f in files]
+    order = pipeline.processing_order(names)
+    recs = [[(wl.names[c], g.contig_ascii(c)) for c in range(g.n_contigs)] for g in gens]
+    bits = so.common_bf(list(zip(files, recs)), k, 0.025)
+    common = pipeline.build_common_bf(cuda_ctx, gens, files, k)
+    assert np.array_equal(common.to_numpy(), bits)
+    for g, rc in zip(gens[:2], recs[:2]):
+        h1, pos, ctg = cuda_ctx.sketch(g, k, w, common=common).to_numpy()
+        for c in (0, len(rc) - 1):
+            oh1, opos = so.minimize(rc[c][1], k, w, bits)
+            assert np.array_equal(h1[ctg == c], oh1) and np.array_equal(pos[ctg == c].astype(np.uint64), opos)
+    be = pipeline.CudaBackend(cuda_ctx, [gens[i] for i in order], [names[i] for i in order], [wl.names] * G,
+                              [[int(x) for x in gens[i].lengths] for i in order], k, common=common)
+    eng = SyntenyEngine(be, k, w, ps["w_rounds"], ps["indel"], ps["merge"], ps["block_size"], write_files=False, quiet=True)
+    go = GraphOracle(list(zip(names, recs)), k, w, ps["w_rounds"], ps["indel"], ps["merge"], ps["block_size"], bits)
+    got = want = None
+    try:
+        got = eng.run()
+    except SystemExit:
+        got = "no paths"
+    try:
+        want = go.run()
+    except SystemExit:
+        want = "no paths"
+    be.close()
+    assert got == want
+    if got != "no paths":
+        assert eng.outputs["pre_merge"] == go.outputs["pre_merge"]
