@@ -475,7 +475,7 @@ def run_ours_multi(args, dist, ctx):
     dist.barrier(); ctx.sync()
     ctx.timer_start()
     for _ in range(e2e_steps):
-        fresh = {g: ctx.upload(packed_host[g][0]) for g in resident}
+        fresh = {g: ctx.upload(packed_host[g][0], async_copy=True) for g in own + [x for x in resident if x not in own]}
         text_e2e, _ = hot_path(fresh)
         for f in fresh.values():
             f.close()
