@@ -884,27 +884,6 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     if (2ull * w > NT || sketch_smem_bytes(NT, THREADS) > (size_t)max_optin)
         return fail(NTS_ERR_ARG, "w too large for the shared-memory window selector (max 9216)");
     uint32_t T = NT - w;
-    // sparse tiles (sketch_sparse_kernel): R dense tiles each, sized so that a thread stages ~3 candidates
-    constexpr int SCAP = 16, CCAP = 3072;
-    bool sparse = w >= 128;
-    if (const char* env = getenv("NTS_SKETCH_DENSE")) { if (env[0] == '1') sparse = false; }
-    uint32_t R = 1, NT_s = 0, C_s = 0, tau_hi = 0;
-    if (sparse) {
-        double lambda = 24.0;                                     // candidates expected per window
-        if (const char* env = getenv("NTS_SKETCH_LAMBDA")) { double x = atof(env); if (x >= 4.0 && x <= 256.0) lambda = x; }
-        const double density = lambda / (double)w;
-        uint32_t c_target = (uint32_t)(3.1 / density);
-        c_target = std::max<uint32_t>(4, std::min<uint32_t>(c_target, 120));
-        const uint32_t nt_target = std::max<uint32_t>(THREADS * c_target, 2 * w);
-        const uint32_t ts_target = nt_target - w;
-        R = (ts_target + T - 1) / T;
-        T = std::max<uint32_t>(ts_target / R, 1);                 // dense sub-tile size; R * T window ends per sparse tile
-        NT_s = R * T + w;
-        C_s = (NT_s + THREADS - 1) / THREADS;
-        tau_hi = (uint32_t)std::min(density * 4294967296.0, 4294967295.0);
-        if (C_s > 255 || NT_s > 65535) sparse = false, T = NT - w, R = 1;
-    }
-
     const HashTables* tabs = nullptr;
     int rc = get_tables(ctx, k, &tabs);
     if (rc) return rc;
@@ -920,6 +899,52 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     }
     struct ViewGuard { nts_view* p; ~ViewGuard() { delete p; } } guard{owned};
     if ((rc = wait_ready(g))) return rc;
+
+    uint64_t m = 0, mp = 0;
+    if (common) mod_params(common, &m, &mp); else if (repeat) mod_params(repeat, &m, &mp);
+    // how often does a k-mer of this view pass the filter?  (sampled; only steers the candidate density)
+    double pass = 1.0;
+    if ((common || repeat) && w >= 128 && v->total_valid > (1u << 20)) {
+        DevBuf<unsigned int> d_cnt2;
+        if (d_cnt2.alloc(2) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (sample)");
+        NTS_CUDA(cudaMemsetAsync(d_cnt2.p, 0, 8, ctx->stream));
+        const uint64_t n_samp = 16384, stride = std::max<uint64_t>(1, v->total_valid / n_samp);
+        {
+            ProfScope prof(ctx, PROF_SKETCH, 0.0);
+            sketch_sample_kernel<<<(unsigned)((n_samp + 255) / 256), 256, 0, ctx->stream>>>(
+                device_view(g, v), tabs, common ? common->words.p : nullptr, repeat ? repeat->words.p : nullptr, m, mp,
+                v->total_valid, stride, d_cnt2.p);
+            ctx->launches++;
+        }
+        NTS_CUDA(cudaGetLastError());
+        unsigned int hc[2] = {0, 0};
+        NTS_CUDA(cudaMemcpyAsync(hc, d_cnt2.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (hc[1]) pass = std::max(1e-4, (double)hc[0] / (double)hc[1]);
+    }
+    // ~19 SURVIVING candidates per window keep unresolved windows rare (e^-19); below a 10 % pass rate the
+    // candidate list would be as long as the window, and the dense selector (every slot queried) is the better tool
+    double lambda = std::max(24.0, 19.0 / pass);
+    if (const char* env = getenv("NTS_SKETCH_LAMBDA")) { double x = atof(env); if (x >= 4.0 && x <= 256.0) lambda = x; }
+    // sparse tiles (sketch_sparse_kernel): R dense tiles each, sized so that a thread stages ~3 candidates
+    constexpr int SCAP = 16, CCAP = 3072;
+    bool sparse = w >= 128 && lambda <= 192.0 && lambda / (double)w <= 0.25;
+    if (const char* env = getenv("NTS_SKETCH_DENSE")) { if (env[0] == '1') sparse = false; }
+    uint32_t R = 1, NT_s = 0, C_s = 0, tau_hi = 0;
+    if (sparse) {
+        const double density = lambda / (double)w;
+        uint32_t c_target = (uint32_t)(3.1 / density);
+        c_target = std::max<uint32_t>(4, std::min<uint32_t>(c_target, 120));
+        const uint32_t nt_target = std::max<uint32_t>(THREADS * c_target, 2 * w);
+        const uint32_t ts_target = nt_target - w;
+        R = (ts_target + T - 1) / T;
+        T = std::max<uint32_t>(ts_target / R, 1);                 // dense sub-tile size; R * T window ends per sparse tile
+        NT_s = R * T + w;
+        C_s = (NT_s + THREADS - 1) / THREADS;
+        tau_hi = (uint32_t)std::min(density * 4294967296.0, 4294967295.0);
+        if (C_s > 255 || NT_s > 65535) sparse = false, T = NT - w, R = 1;
+    }
+
 
     // tiles: one per R * T window ends of a contig; each stands for up to R output slots (dense sub-tiles)
     std::vector<TileDesc> tiles;
@@ -963,12 +988,9 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
         return fail(NTS_ERR_NOMEM, "device allocation failed (tiles)");
     NTS_CUDA(copy_h2d(ctx, d_tiles.p, tiles.data(), (size_t)n_tiles * sizeof(TileDesc)));
 
-    uint64_t m = 0, mp = 0;
-    if (common) mod_params(common, &m, &mp); else if (repeat) mod_params(repeat, &m, &mp);
-
     // dense kernel's own pruning threshold: ~48 slots per window are expected below tau (uniform hashes)
     uint64_t tau = KEY_MAX;
-    if ((common || repeat) && w > 96) tau = (uint64_t)((48.0 / (double)w) * 18446744073709551616.0);
+    if ((common || repeat) && w > 96 && pass >= 0.1) tau = (uint64_t)((48.0 / (double)w) * 18446744073709551616.0);
     if (const char* env = getenv("NTS_SKETCH_NO_PRUNE")) { if (env[0] == '1') tau = KEY_MAX; }
     const size_t smem = sketch_smem_bytes(NT, THREADS);
     NTS_CUDA(cudaFuncSetAttribute(sketch_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -477,6 +477,28 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
     }
 }
 
+// ------------------------------------------------------------------------------ filter pass rate (sampled)
+// A few thousand evenly spaced k-mers of the view are hashed and looked up: the fraction that passes the filter
+// decides how many candidates per window the sparse sketch kernel needs (its exactness never depends on it).
+__global__ void sketch_sample_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
+                                     const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t total_valid,
+                                     uint64_t stride, unsigned int* __restrict__ counts /* [0] passed, [1] sampled */)
+{
+    __shared__ HashTables s_tabs;
+    stage_tables(&s_tabs, g_tabs, g.k);
+    __syncthreads();
+    const uint64_t v = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * stride;
+    if (v >= total_valid) return;
+    hash_run(g, &s_tabs, v, 1, [&](uint32_t, uint64_t h0, uint64_t) {
+        const uint64_t idx = fast_mod(h0, m, mprime);
+        bool keep = true;
+        if (common) keep = (__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u;
+        if (keep && repeat) keep = !((__ldg(&repeat[idx >> 5]) >> (idx & 31)) & 1u);
+        atomicAdd(&counts[1], 1u);
+        if (keep) atomicAdd(&counts[0], 1u);
+    });
+}
+
 // ------------------------------------------------------------------------------ (ii) sketch, sparse form
 // The same selection as sketch_kernel, for tiles several times larger, without keeping every key in shared
 // memory.  Only slots whose hash is below tau = tau_hi * 2^32 ("candidates", a few per cent) can be the minimum

@@ -158,6 +158,7 @@ class SyntenyEngine:
         self._prebuilt = "host" in j
         self._pair_masks = j.get("pair_masks")
         self._h_extra = {}
+        self._h_extra_cache = None
         self._pair_cache = None
         self._pair_orig, self._pair_delta = {}, {}      # corrections to the device prefix sums (see _refresh_pairs)
         self._br_touched = set()                        # pairs (i, i+1) whose `conn` changed since _breaks was made
@@ -302,8 +303,18 @@ class SyntenyEngine:
             hit = got != 0xFFFFFFFF
             out[hit] = got[hit]
         if self._h_extra:
-            for jx in np.nonzero(out < 0)[0]:
-                out[jx] = self._h_extra.get(int(keys[jx]), -1)
+            if self._h_extra_cache is None or self._h_extra_cache[0] != len(self._h_extra):
+                ek = np.fromiter(self._h_extra.keys(), dtype=np.uint64, count=len(self._h_extra))
+                ev = np.fromiter(self._h_extra.values(), dtype=np.int64, count=len(self._h_extra))
+                o = np.argsort(ek)
+                self._h_extra_cache = (len(self._h_extra), ek[o], ev[o])
+            _, ek, ev = self._h_extra_cache
+            miss = np.flatnonzero(out < 0)
+            if len(miss):
+                j = np.searchsorted(ek, keys[miss])
+                j[j >= len(ek)] = 0
+                hit = ek[j] == keys[miss]
+                out[miss[hit]] = ev[j[hit]]
         return out
 
     # ------------------------------------------------------------------ degree-2 graph on arrays
@@ -812,13 +823,31 @@ class SyntenyEngine:
             rows.append(row + "\n")
         return "".join(rows)
 
+    def _block_coords(self, blocks):
+        "start[nb, G], end[nb, G] of the blocks (bin/assembly_block.py:17-23), ctg[nb, G]"
+        if not blocks:
+            z = np.zeros((0, self.G), dtype=np.int64)
+            return z, z, z
+        fp = np.array([b.first_pos for b in blocks], dtype=np.int64)
+        lp = np.array([b.last_pos for b in blocks], dtype=np.int64)
+        ctg = np.array([b.ctg for b in blocks], dtype=np.int64)
+        return np.minimum(fp, lp), np.maximum(fp, lp) + self.k, ctg
+
     def _emit(self, key, blocks, verbose=False):
-        text, num = [], 0
-        for b in blocks:
-            if not self._long_enough(b):
-                continue
-            text.append(self._block_rows(b, num, verbose))
-            num += 1
+        st, en, ctg = self._block_coords(blocks)
+        keep = np.flatnonzero(((en - st) >= self.z).all(axis=1)) if len(blocks) else []
+        text = []
+        if len(keep):
+            order = self.name_order
+            st_l, en_l, ctg_l = st[keep][:, order].tolist(), en[keep][:, order].tolist(), ctg[keep][:, order].tolist()
+            labels = [self.labels[a] for a in order]
+            cnames = [self.be.contig_names[a] for a in order]
+            for num, bi in enumerate(keep.tolist()):
+                b = blocks[bi]
+                tail = f"\t{b.n}\t{b.broken_reason}\n" if verbose else f"\t{b.n}\n"
+                s_, e_, c_ = st_l[num], en_l[num], ctg_l[num]
+                for j, a in enumerate(order):
+                    text.append(f"{num}\t{labels[j]}\t{cnames[j][c_[j]]}\t{s_[j]}\t{e_[j]}\t{b.ori[a]}{tail}")
         text = "".join(text)
         self.outputs[key] = text
         if self.write_files:
@@ -869,28 +898,32 @@ class SyntenyEngine:
         "get_synteny_bed_lists + mask_assemblies_with_synteny_extents (ntsynt_synteny.py:117-157)"
         thr = max(2 * prev_w, prev_w + self.k + 1)
         shrink = prev_w + self.k
+        st, en, ctg = self._block_coords(blocks)
         masks = []
         for a in range(self.G):
-            per = defaultdict(list)
-            for b in blocks:
-                s, e = b.start(a), b.end(a, self.k)
-                if e - s > thr:
-                    c = int(b.ctg[a])
-                    s2 = max(s + shrink, 0)
-                    e2 = min(e - shrink, int(self.be.contig_lengths[a][c]))
-                    if s2 < e2:      # an interval the negative slop empties is dropped (unpinned)
-                        per[c].append((s2, e2))
-            lst = []
-            for c in range(len(self.be.contig_names[a])):
-                iv = sorted(per.get(c, []))
-                # union (bedtools maskfasta semantics): merge overlapping intervals
-                ms, me = [], []
-                for s, e in iv:
-                    if ms and s <= me[-1]:
-                        me[-1] = max(me[-1], e)
-                    else:
-                        ms.append(s); me.append(e)
-                lst.append((np.array(ms, dtype=np.uint64), np.array(me, dtype=np.uint64)))
+            lens = np.asarray(self.be.contig_lengths[a], dtype=np.int64)
+            s, e, c = st[:, a], en[:, a], ctg[:, a]
+            big = (e - s) > thr
+            s2 = np.maximum(s[big] + shrink, 0)
+            c2 = c[big]
+            e2 = np.minimum(e[big] - shrink, lens[c2]) if len(c2) else s2
+            ok = s2 < e2             # an interval the negative slop empties is dropped (unpinned)
+            s2, e2, c2 = s2[ok], e2[ok], c2[ok]
+            o = np.lexsort((e2, s2, c2))
+            s2, e2, c2 = s2[o], e2[o], c2[o]
+            # union per contig (bedtools maskfasta semantics): an interval starts a new run unless it begins at or
+            # before the furthest end seen so far in its contig
+            lst = [(np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64)) for _ in self.be.contig_names[a]]
+            if len(s2):
+                cb = np.flatnonzero(np.r_[True, c2[1:] != c2[:-1]])           # first interval of each contig
+                ce = np.r_[cb[1:], len(c2)]
+                for i0, i1 in zip(cb.tolist(), ce.tolist()):
+                    ss, ee = s2[i0:i1], e2[i0:i1]
+                    run_max = np.maximum.accumulate(ee)
+                    new_run = np.r_[True, ss[1:] > run_max[:-1]]
+                    heads = np.flatnonzero(new_run)
+                    ends_ = run_max[np.r_[heads[1:] - 1, len(ss) - 1]]
+                    lst[int(c2[i0])] = (ss[heads].astype(np.uint64), ends_.astype(np.uint64))
             masks.append(lst)
         return masks
 
@@ -917,19 +950,31 @@ class SyntenyEngine:
         # --- terminal / internal minimizers and block intervals (find_mx_in_blocks :205-226)
         term_ids = np.array([x for b in blocks for x in (b.first_id, b.last_id)], dtype=np.int64)
         terminal_h = set(int(x) for x in self.H[term_ids]) if len(term_ids) else set()
+        seg_lo = np.array([sg[0] for b in blocks for sg in b.segs], dtype=np.int64)
+        seg_hi = np.array([sg[1] for b in blocks for sg in b.segs], dtype=np.int64)
         is_internal = np.zeros(self.V, dtype=bool)
-        for b in blocks:
-            for lo, hi, _ in b.segs:
-                is_internal[lo:hi + 1] = True
+        long_ = np.flatnonzero(seg_hi - seg_lo > 64)
+        for lo, hi in zip(seg_lo[long_].tolist(), seg_hi[long_].tolist()):          # the few long runs: slice fills
+            is_internal[lo:hi + 1] = True
+        short_ = np.flatnonzero(seg_hi - seg_lo <= 64)                                 # the many short ones: one scatter
+        if len(short_):
+            n_ = seg_hi[short_] - seg_lo[short_] + 1
+            off_ = np.repeat(np.cumsum(n_) - n_, n_)
+            is_internal[np.repeat(seg_lo[short_], n_) + (np.arange(int(n_.sum())) - off_)] = True
         if len(term_ids):
             is_internal[term_ids] = False
-        intervals = [defaultdict(list) for _ in range(G)]
-        for b in blocks:
-            for a in range(G):
-                s, e = b.start(a), max(int(b.first_pos[a]), int(b.last_pos[a]))
-                if e - s < 2:
-                    continue
-                intervals[a][int(b.ctg[a])].append((s + 1, e))
+        # open intervals (start, last minimizer) of the blocks per (assembly, contig), as (starts, ends) arrays
+        bst, ben, bctg = self._block_coords(blocks)
+        intervals = []
+        for a in range(G):
+            s_, e_, c_ = bst[:, a], ben[:, a] - self.k, bctg[:, a]
+            ok = (e_ - s_) >= 2
+            s_, e_, c_ = s_[ok] + 1, e_[ok], c_[ok]
+            o = np.argsort(c_, kind="stable")
+            s_, e_, c_ = s_[o], e_[o], c_[o]
+            cb = np.flatnonzero(np.r_[True, c_[1:] != c_[:-1]]) if len(c_) else np.zeros(0, dtype=np.int64)
+            ce = np.r_[cb[1:], len(c_)] if len(c_) else cb
+            intervals.append({int(c_[i0]): (s_[i0:i1], e_[i0:i1]) for i0, i1 in zip(cb.tolist(), ce.tolist())})
         self._tick("r_blockinfo")
         # --- filter_minimizers_synteny_blocks (:256-280), vectorised per contig
         kept = []       # per assembly: (h1, pos, ctg, sublist_id)
@@ -948,7 +993,7 @@ class SyntenyEngine:
             for c in np.unique(ctg):
                 c = int(c)
                 if c in intervals[a]:
-                    st, en = zip(*intervals[a][c])
+                    st, en = intervals[a][c]
                     ii = IntervalIndex(st, en)
                     idx_by_ctg[c] = ii
                     sel = np.nonzero(ctg == c)[0]
@@ -1122,12 +1167,13 @@ class SyntenyEngine:
             return []
         bumped = {}
 
-        def weight(u, x):
-            key = (u, x) if u < x else (x, u)
-            return bumped.get(key, nbrs(u)[x])
+        fullc = {}          # number of full-weight edges at a candidate; a bump adds one at both ends
 
         def anchored(u):
-            return sum(1 for x in nbrs(u) if weight(u, x) == G) == 1
+            c = fullc.get(u)
+            if c is None:
+                c = fullc[u] = sum(1 for w_ in nbrs(u).values() if w_ == G)
+            return c == 1
 
         # candidate edges in edge-id order: old edges first (their relative order only matters among
         # themselves), then the new edges in insertion order
@@ -1148,6 +1194,8 @@ class SyntenyEngine:
             if anchored(s) and anchored(t):
                 common = [x for x in nbrs(s) if x != t and x in nbrs(t)]
                 if len(common) == 1:
+                    if (s, t) not in bumped and nbrs(s)[t] != G:
+                        fullc[s] += 1; fullc[t] += 1
                     bumped[(s, t)] = G
                     out.append((s, t))
         return out

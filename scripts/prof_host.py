@@ -13,7 +13,7 @@ from ntsynt_b200 import device, pipeline, synth  # noqa: E402
 from ntsynt_b200.synteny import SyntenyEngine  # noqa: E402
 
 mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 3000.0
-K, W, G, d = 24, 1000, 2, 1.0
+K, W, G, d = 24, 1000, (int(sys.argv[2]) if len(sys.argv) > 2 else 2), 1.0
 ps = bench.presets(d)
 ctx = device.Context(0)
 wl = synth.Workload(G, int(mbp * 1e6), d, seed=20260117)

@@ -283,9 +283,14 @@ def test_sparse_and_dense_sketch_kernels_agree(cuda_ctx, w):
     thin = a.to_numpy().copy()
     thin[len(thin) // 16:] = 0                       # 15/16 of the hash space never passes: many windows without a survivor
     thin_bf = cuda_ctx.bloom(nbytes).from_numpy(thin)
-    for bf, must_escalate in ((a, False), (thin_bf, True), (None, False)):
+    for bf, must_escalate in ((a, False), (thin_bf, True), (thin_bf, False), (None, False)):
         e0 = cuda_ctx.sketch_escalated
-        sparse = [x.copy() for x in cuda_ctx.sketch(gens[1], k, w, common=bf).to_numpy()]
+        if must_escalate:                            # pin the candidate density: the sampled pass rate would raise it
+            os.environ["NTS_SKETCH_LAMBDA"] = "24"   # (or choose the dense kernel outright)
+        try:
+            sparse = [x.copy() for x in cuda_ctx.sketch(gens[1], k, w, common=bf).to_numpy()]
+        finally:
+            os.environ.pop("NTS_SKETCH_LAMBDA", None)
         esc = cuda_ctx.sketch_escalated - e0
         os.environ["NTS_SKETCH_DENSE"] = "1"
         try:
