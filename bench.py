@@ -299,13 +299,19 @@ def run_ours(args, dist):
         packed_host.append((pk, pin))
     ctx.prof_reset()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def e2e_step():
+        fresh = [ctx.upload(pk, async_copy=True) for pk, _ in packed_host]     # H2D of genome i+1 overlaps insert i
+        out, _ = hot_path(fresh)
+        for f in fresh:
+            f.close()
+        return out
+    e2e_step()                                   # untimed: first-use costs of this leg (copy stream, device blocks)
+    ctx.prof_reset()                             # (also zeroes the transfer counters)
     dist.barrier(); ctx.sync()
     ctx.timer_start()
     for _ in range(e2e_steps):
-        fresh = [ctx.upload(pk, async_copy=True) for pk, _ in packed_host]     # H2D of genome i+1 overlaps insert i
-        text_e2e, _ = hot_path(fresh)
-        for f in fresh:
-            f.close()
+        text_e2e = e2e_step()
     ms_e2e = dist.max(ctx.timer_stop())
     h2d, d2h = ctx.xfer_bytes()
     clk = clocks.stop()

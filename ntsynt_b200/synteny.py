@@ -865,31 +865,44 @@ class SyntenyEngine:
 
     def _merge_collinear(self, blocks):
         out = []
+        G, k = self.G, self.k
+        st, en, _ = self._block_coords(blocks)
+        st_l, en_l = st.tolist(), en.tolist()
         cur = blocks[0]
-        for b in blocks[1:]:
-            same_ori = all(cur.ori[a] == b.ori[a] for a in range(self.G))
-            same_ctg = all(int(cur.ctg[a]) == int(b.ctg[a]) for a in range(self.G))
-            diffs = [self._gap(cur, b, a) for a in range(self.G)]
-            spread = max(diffs) - min(diffs)
-            if (not same_ori) or (not same_ctg) or spread > self.bp - self.k or max(diffs) >= self.collinear_merge:
+        cur_st, cur_en = st_l[0], en_l[0]
+        cur_ori, cur_ctg = list(cur.ori), [int(x) for x in cur.ctg]
+        for i in range(1, len(blocks)):
+            b = blocks[i]
+            b_ori, b_ctg = list(b.ori), [int(x) for x in b.ctg]
+            same_ori = cur_ori == b_ori
+            same_ctg = cur_ctg == b_ctg
+            bs, be_ = st_l[i], en_l[i]
+            # get_difference_between_blocks: distance from the end of the first block to the start of the second,
+            # measured the other way round where both are on the minus strand
+            diffs = [(cur_st[a] - be_[a]) if (cur_ori[a] == "-" and b_ori[a] == "-") else (bs[a] - cur_en[a]) for a in range(G)]
+            mx, mn = max(diffs), min(diffs)
+            spread = mx - mn
+            if (not same_ori) or (not same_ctg) or spread > self.bp - k or mx >= self.collinear_merge:
                 if not same_ctg:
                     b.broken_reason = "id_change"
                 elif not same_ori:
                     b.broken_reason = "ori_change"
-                elif any(x < 0 for x in diffs):
+                elif mn < 0:
                     b.broken_reason = "inconsistent_order"
-                elif spread > self.bp - self.k:
+                elif spread > self.bp - k:
                     b.broken_reason = "indel"
-                elif max(diffs) >= self.collinear_merge:
+                elif mx >= self.collinear_merge:
                     b.broken_reason = "merge"
                 out.append(cur)
-                cur = b
+                cur, cur_st, cur_en, cur_ori, cur_ctg = b, bs, be_, b_ori, b_ctg
             else:
                 # extend: coordinates come from the first minimizer of `cur` and the last of `b`
                 cur.last_pos = b.last_pos
                 cur.last_id = b.last_id
                 cur.n += b.n
                 cur.segs = None
+                cur_st = [min(int(f), int(l)) for f, l in zip(cur.first_pos, cur.last_pos)]
+                cur_en = [max(int(f), int(l)) + k for f, l in zip(cur.first_pos, cur.last_pos)]
         out.append(cur)
         return out
 
@@ -1302,7 +1315,8 @@ class SyntenyEngine:
         if not ordered:
             print("Error - no paths found. Try adjusting the specified k/w parameters.")
             raise SystemExit(1)
-        self._emit("initial", ordered)
+        if self.write_files or not self.w_rounds:      # with refinement rounds the final table replaces this one
+            self._emit("initial", ordered)
         self.log("Done initial synteny blocks")
         # --- refinement rounds (refine_block_coordinates :476-530)
         prev_w = self.w
@@ -1321,7 +1335,8 @@ class SyntenyEngine:
             blocks = self._filter_small(blocks, 4)
             ordered = self._sort_blocks(blocks)
             self._tick("filter_sort")
-            self._emit("pre_merge", ordered)
+            if last or self.write_files:               # every round overwrites the same table: only the last one stays
+                self._emit("pre_merge", ordered)
             if last:
                 merged = self._merge_collinear(ordered) if ordered else []
                 merged = [b for b in merged if self._long_enough(b)]
