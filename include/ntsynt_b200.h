@@ -275,6 +275,24 @@ int nts_host_simplify(const int64_t* cand, int64_t n_cand, const uint32_t* rank,
                       int64_t ctg_stride, int64_t V, uint32_t G, int64_t* bump_s, int64_t* bump_t, int64_t* removed,
                       int64_t out_cap, int64_t* n_out);
 
+/* ---- native FASTA ingest (host code; replaces btllib::SeqReader, src/ntsynt_make_common_bf.cpp:32-36,125,143, and
+ * `samtools faidx`, bin/ntsynt_run_pipeline.smk:48-53) --------------------------------------------------------------
+ * nts_fasta_scan: records of a FASTA held in memory.  Per record: name = first whitespace-delimited token of the
+ * header (name_off / name_len into buf), n_bases, [seq_off, seq_end) = file span of its sequence lines, linebases /
+ * linewidth of its first non-empty sequence line (the .fai columns), uniform = 1 iff every sequence line but the last
+ * has that width.  *n_records may exceed cap: call again with larger arrays. */
+int nts_fasta_scan(const char* buf, uint64_t n, uint64_t cap, uint64_t* name_off, uint32_t* name_len, uint64_t* n_bases,
+                   uint64_t* seq_off, uint64_t* seq_end, uint32_t* linebases, uint32_t* linewidth, uint8_t* uniform,
+                   uint64_t* n_records);
+/* nts_fasta_pack: 2-bit pack every record with n_threads threads (0 = hardware concurrency; records in parallel, long
+ * uniform records split at 4 Mbp).  word_off[r] = even offset of record r in words_out (zero-initialised, sum of
+ * nts_packed_words(n_bases[r]) words); N runs in record coordinates, record r owning [nrun_off[r], nrun_off[r+1]).
+ * If *n_nruns > nrun_cap only the count is valid: call again with larger arrays. */
+int nts_fasta_pack(const char* buf, uint64_t n_records, const uint64_t* n_bases, const uint64_t* seq_off, const uint64_t* seq_end,
+                   const uint32_t* linebases, const uint32_t* linewidth, const uint8_t* uniform, const uint64_t* word_off,
+                   uint64_t* words_out, uint64_t* nrun_off, uint64_t* nrun_start, uint64_t* nrun_len, uint64_t nrun_cap,
+                   uint64_t* n_nruns, uint32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,8 +107,58 @@ def pack_records(records, path=None):
                         np.concatenate(nrl) if nrl else np.zeros(0, dtype=np.uint64), fai, path)
 
 
-def read_fasta(path):
+def read_fasta_python(path):
+    "line-by-line reader + per-record packing (the statement of the format the native reader is tested against)"
     return pack_records(iter_fasta(path), path=path)
+
+
+def parse_fasta_bytes(data, path=None, threads=0):
+    """FASTA text (bytes) -> PackedGenome with the native reader: one memchr scan for the records, then the records
+    (and the 4 Mbp pieces of long uniform-width records) packed by `threads` threads (0 = all cores)"""
+    n = len(data)
+    cap = 4096
+    while True:
+        name_off, n_bases, seq_off, seq_end = (np.zeros(cap, dtype=np.uint64) for _ in range(4))
+        name_len, lb, lw = (np.zeros(cap, dtype=np.uint32) for _ in range(3))
+        uni = np.zeros(cap, dtype=np.uint8)
+        nrec = C.c_uint64()
+        check(lib.nts_fasta_scan(data, n, cap, ptr(name_off, C.c_uint64), ptr(name_len, C.c_uint32), ptr(n_bases, C.c_uint64),
+                                 ptr(seq_off, C.c_uint64), ptr(seq_end, C.c_uint64), ptr(lb, C.c_uint32), ptr(lw, C.c_uint32),
+                                 ptr(uni, C.c_uint8), C.byref(nrec)))
+        if nrec.value <= cap:
+            break
+        cap = int(nrec.value)
+    R = int(nrec.value)
+    n_bases, seq_off, seq_end, lb, lw, uni = n_bases[:R], seq_off[:R], seq_end[:R], lb[:R], lw[:R], uni[:R]
+    names = [data[int(o):int(o) + int(l)].decode() for o, l in zip(name_off[:R], name_len[:R])]
+    nw = ((n_bases + np.uint64(63)) // np.uint64(64)) * np.uint64(2)
+    word_off = np.zeros(R + 1, dtype=np.uint64)
+    np.cumsum(nw, out=word_off[1:])
+    words = np.zeros(int(word_off[R]), dtype=np.uint64)
+    nrun_off = np.zeros(R + 1, dtype=np.uint64)
+    rcap = 65536
+    z64 = np.zeros(1, dtype=np.uint64)
+    while True:
+        rs, rl = np.zeros(rcap, dtype=np.uint64), np.zeros(rcap, dtype=np.uint64)
+        nruns = C.c_uint64()
+        check(lib.nts_fasta_pack(data, R, ptr(n_bases if R else z64, C.c_uint64), ptr(seq_off if R else z64, C.c_uint64),
+                                 ptr(seq_end if R else z64, C.c_uint64), ptr(lb if R else np.zeros(1, np.uint32), C.c_uint32),
+                                 ptr(lw if R else np.zeros(1, np.uint32), C.c_uint32), ptr(uni if R else np.zeros(1, np.uint8), C.c_uint8),
+                                 ptr(word_off, C.c_uint64), ptr(words if words.size else z64, C.c_uint64), ptr(nrun_off, C.c_uint64),
+                                 ptr(rs, C.c_uint64), ptr(rl, C.c_uint64), rcap, C.byref(nruns), int(threads)))
+        if nruns.value <= rcap:
+            break
+        rcap = int(nruns.value)
+    fai = [(nm, int(nb), int(so_), int(a), int(b)) for nm, nb, so_, a, b in zip(names, n_bases, seq_off, lb, lw)]
+    return PackedGenome(names, n_bases, word_off[:R], words, nrun_off, rs[:nruns.value], rl[:nruns.value], fai, path)
+
+
+def read_fasta(path, threads=0):
+    "FASTA file (.gz accepted) -> PackedGenome through the native reader (csrc/nts_fasta.cu)"
+    op = gzip.open if str(path).endswith(".gz") else open
+    with op(path, "rb") as fh:
+        data = fh.read()
+    return parse_fasta_bytes(data, path=path, threads=threads)
 
 
 def write_fai(packed, out_path):
