@@ -456,7 +456,7 @@ def run_ours_multi(args, dist, ctx):
         for g in own[1:]:
             level.clear(); level.insert_genome(gen_map[g], K); mine.iand(level)
         if use_p2p:
-            peer.merge("and")                                      # NVLink peer loads: reduce-scatter + all-gather
+            peer.merge("and", comm=comm)                           # NVLink peer loads: reduce-scatter + all-gather
         else:
             comm.allreduce_and(mine)                               # the one bulk exchange (NCCL sum of counters)
         gathered = {}
@@ -534,7 +534,7 @@ def run_ours_multi(args, dist, ctx):
             if name == "nccl":
                 comm.allreduce_and(mine)
             else:
-                peer.merge("and")
+                peer.merge("and", comm=comm)
             ctx.sync()
             dt = dist.max((time.perf_counter() - t0) * 1e3)
             best = dt if best is None else min(best, dt)

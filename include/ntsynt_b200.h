@@ -192,6 +192,8 @@ typedef struct nts_comm nts_comm;
 int nts_nccl_unique_id(uint8_t id_out[128]);
 int nts_nccl_init(nts_ctx* ctx, const uint8_t id[128], int rank, int world, nts_comm** out);
 void nts_nccl_destroy(nts_comm* comm);
+/* stream-ordered barrier (a one-word all-reduce on the context's stream; no host synchronisation) */
+int nts_nccl_barrier(nts_comm* c);
 int nts_nccl_world(const nts_comm* comm);
 int nts_nccl_rank(const nts_comm* comm);
 int nts_bf_allreduce_and(nts_comm* comm, nts_bf* bf);

@@ -93,6 +93,7 @@ _SIGS = {
     "nts_nccl_unique_id": (C.c_int, [u8p]),
     "nts_nccl_init": (C.c_int, [vp, u8p, C.c_int, C.c_int, vpp]),
     "nts_nccl_destroy": (None, [vp]),
+    "nts_nccl_barrier": (C.c_int, [vp]),
     "nts_nccl_world": (C.c_int, [vp]),
     "nts_nccl_rank": (C.c_int, [vp]),
     "nts_bf_allreduce_and": (C.c_int, [vp, vp]),

@@ -107,6 +107,7 @@ struct nts_comm {
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
     DevBuf<uint32_t> stage[2];
+    DevBuf<uint32_t> bar;         // one word for nts_nccl_barrier
     uint64_t chunk_words = 0;     // input words per chunk
 };
 
@@ -156,6 +157,23 @@ void nts_nccl_destroy(nts_comm* c)
         if (c->done[i]) cudaEventDestroy(c->done[i]);
     }
     delete c;
+}
+
+/* Stream-ordered barrier: a one-word all-reduce on the context's stream.  Work queued after it on any rank starts
+ * only when every rank's stream has reached its own call -- the inter-GPU ordering the peer-memory merge kernels need
+ * (nts_p2p_*), without a host round trip. */
+int nts_nccl_barrier(nts_comm* c)
+{
+    if (!c) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(c->ctx->device));
+    if (!c->bar.p) {
+        if (c->bar.alloc(1) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (barrier word)");
+        NTS_CUDA(cudaMemsetAsync(c->bar.p, 0, 4, c->ctx->stream));
+    }
+    ProfScope prof(c->ctx, PROF_NCCL, 0.0);
+    NTS_NCCL(g_nccl.AllReduce(c->bar.p, c->bar.p, 1, ncclUint32, ncclSum, c->comm, c->ctx->stream));
+    c->ctx->launches++;
+    return NTS_OK;
 }
 
 int nts_nccl_world(const nts_comm* c) { return c ? c->world : 0; }

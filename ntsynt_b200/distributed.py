@@ -54,6 +54,10 @@ class Comm:
     def allreduce_or(self, bf):
         check(lib.nts_bf_allreduce_or(self._h, bf._h))
 
+    def barrier(self):
+        "stream-ordered barrier across the ranks (one-word all-reduce on the context's stream; the host does not wait)"
+        check(lib.nts_nccl_barrier(self._h))
+
     def allgather_tables(self, table, counts, genome_for_rank):
         "every rank's minimizer table, as MinimizerTable objects on this rank"
         cnt = np.asarray(counts, dtype=np.uint64)
@@ -94,14 +98,18 @@ class PeerMerge:
             self._h = None
         barrier()
 
-    def merge(self, op="and"):
-        "filter := AND (or OR) over all ranks; every rank must call it"
-        self.bf.ctx.sync()
-        self.barrier()                       # every filter is complete
+    def merge(self, op="and", comm=None):
+        """filter := AND (or OR) over all ranks; every rank must call it.  The three inter-GPU orderings (every filter
+        complete / every slice reduced / nobody still reads my slices) are stream-ordered NCCL barriers when a Comm is
+        given, host barriers of the launcher's side channel otherwise."""
+        if comm is None:
+            self.bf.ctx.sync()
+        sync = comm.barrier if comm is not None else self.barrier
+        sync()                               # every filter is complete
         check(lib.nts_p2p_reduce_scatter(self._h, 0 if op == "and" else 1))
-        self.barrier()                       # every slice is reduced
+        sync()                               # every slice is reduced
         check(lib.nts_p2p_all_gather(self._h))
-        self.barrier()                       # nobody still reads my slices
+        sync()                               # nobody still reads my slices
 
     def close(self):
         if self._h:
