@@ -420,6 +420,8 @@ def run_ours(args, dist):
 
 
 def run_ours_multi(args, dist, ctx):
+    # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+    os.environ["NCCL_DEBUG"] = os.environ.get("NTS_NCCL_DEBUG", "WARN")
     """N > 1: one genome per GPU (G = N, or a multiple), per-GPU filters merged by NCCL all-reduce(sum)
     of packed counters, owners sketch, tables all-gathered, rank 0 runs the join + graph stage."""
     import numpy as np
