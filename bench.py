@@ -420,8 +420,9 @@ def run_ours(args, dist):
 
 
 def run_ours_multi(args, dist, ctx):
-    # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-    os.environ["NCCL_DEBUG"] = os.environ.get("NTS_NCCL_DEBUG", "WARN")
+    # NCCL prints its version banner to stdout from NCCL_DEBUG=VERSION upwards (WARN included): keep stdout to the
+    # one JSON line unless asked otherwise
+    os.environ["NCCL_DEBUG"] = os.environ.get("NTS_NCCL_DEBUG", "NONE")
     """N > 1: one genome per GPU (G = N, or a multiple), per-GPU filters merged by NCCL all-reduce(sum)
     of packed counters, owners sketch, tables all-gathered, rank 0 runs the join + graph stage."""
     import numpy as np
