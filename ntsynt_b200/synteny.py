@@ -537,15 +537,16 @@ class SyntenyEngine:
         else:
             starts = ends = np.zeros(0, dtype=np.int64)
         # vertices that really hold a sparse edge (non-consecutive neighbour, or any edge of a later vertex)
-        real_sparse = set()
+        rs = np.zeros(0, dtype=np.int64)                   # the real sparse vertices, ascending
         if self.sparse:
             sv = np.fromiter(self.sparse, dtype=np.int64, count=len(self.sparse))
             nb = self.nbr[sv]
             has = ((nb >= 0) & ((np.abs(nb - sv[:, None]) != 1) | (np.maximum(nb, sv[:, None]) >= V0))).any(axis=1)
-            real_sparse = set(int(x) for x in sv[has])
-            self.sparse = set(real_sparse)
+            rs = np.sort(sv[has])
+            self.sparse = set(rs.tolist())
+        real_sparse = len(rs) > 0
         is_sp_run = np.zeros(len(starts), dtype=bool)
-        base_sp = np.array([v for v in real_sparse if v < V0], dtype=np.int64)
+        base_sp = rs[rs < V0]
         if len(base_sp):
             is_sp_run[np.searchsorted(starts, base_sp, side="right") - 1] = True
         pure = np.flatnonzero((ends > starts) & ~is_sp_run)
@@ -559,7 +560,7 @@ class SyntenyEngine:
             # the walk over runs joined by sparse edges, in C++ (csrc/nts_hostgraph.cu: nts_host_walk_paths)
             import ctypes as C
             from ._lib import check, lib, ptr
-            sv = np.array(sorted(real_sparse), dtype=np.int64)
+            sv = rs
             starts64 = np.ascontiguousarray(starts, dtype=np.int64)
             ends64 = np.ascontiguousarray(ends, dtype=np.int64)
             opos64 = np.ascontiguousarray(opos, dtype=np.int64)
@@ -578,7 +579,7 @@ class SyntenyEngine:
             paths.extend(segs_all[off[i]:off[i + 1]] for i in range(n_p.value))
         elif real_sparse:
             seen_runs = set()
-            sv = np.array(sorted(real_sparse), dtype=np.int64)
+            sv = rs
             ra, rb = sv.copy(), sv.copy()
             bm = sv < V0
             if bm.any():
