@@ -318,23 +318,6 @@ class SyntenyEngine:
         return out
 
     # ------------------------------------------------------------------ degree-2 graph on arrays
-    def _has_edge(self, u, v):
-        return self.nbr[u, 0] == v or self.nbr[u, 1] == v
-
-    def _add_edge(self, u, v):
-        for x, y in ((u, v), (v, u)):
-            if self.nbr[x, 0] < 0:
-                self.nbr[x, 0] = y
-            elif self.nbr[x, 1] < 0:
-                self.nbr[x, 1] = y
-            else:
-                raise RuntimeError("internal error: vertex of degree > 2 in the weight-filtered graph")
-        if abs(u - v) == 1 and max(u, v) < self.V0:
-            self.conn[min(u, v)] = True
-            self._br_touched.add(int(min(u, v)))
-        else:
-            self.sparse.add(int(u)); self.sparse.add(int(v))
-
     def _add_edges(self, us, vs):
         "vectorised _add_edge for a batch of edges (a vertex may take two of them)"
         us = np.asarray(us, dtype=np.int64); vs = np.asarray(vs, dtype=np.int64)
@@ -394,18 +377,6 @@ class SyntenyEngine:
             return False
         ru, rv = self.RANK[a, u], self.RANK[a, v]
         return abs(int(ru) - int(rv)) == 1 and self._ctg_round0(a, u) == self._ctg_round0(a, v)
-
-    def _neighbors0(self, u):
-        "distinct round-0 neighbours of u with their weights (number of supporting assemblies)"
-        res = {}
-        for a in range(self.G):
-            r = int(self.RANK[a, u])
-            for rr in (r - 1, r + 1):
-                if 0 <= rr < self.V0:
-                    x = int(self.INV[a, rr])
-                    if self._ctg_round0(a, x) == self._ctg_round0(a, u):
-                        res[x] = res.get(x, 0) + 1
-        return res
 
     def _edge_key0(self, u, v):
         "position of edge {u,v} in build_graph's formatted_edges order for round 0 (ntjoin_utils.py:97-115)"
@@ -814,16 +785,6 @@ class SyntenyEngine:
     def _long_enough(self, b):
         return all(b.end(a, self.k) - b.start(a) >= self.z for a in range(self.G))
 
-    def _block_rows(self, b, num, verbose=False):
-        rows = []
-        for a in self.name_order:
-            row = (f"{num}\t{self.labels[a]}\t{self.be.contig_names[a][int(b.ctg[a])]}\t{b.start(a)}"
-                   f"\t{b.end(a, self.k)}\t{b.ori[a]}\t{b.n}")
-            if verbose:
-                row = f"{row.strip()}\t{b.broken_reason}"
-            rows.append(row + "\n")
-        return "".join(rows)
-
     def _block_coords(self, blocks):
         "start[nb, G], end[nb, G] of the blocks (bin/assembly_block.py:17-23), ctg[nb, G]"
         if not blocks:
@@ -859,11 +820,6 @@ class SyntenyEngine:
         return text
 
     # ------------------------------------------------------------------ merge (ntsynt_synteny.py:428-472)
-    def _gap(self, b1, b2, a):
-        if b1.ori[a] == "-" and b2.ori[a] == "-":
-            return b1.start(a) - b2.end(a, self.k)
-        return b2.start(a) - b1.end(a, self.k)
-
     def _merge_collinear(self, blocks):
         out = []
         G, k = self.G, self.k
