@@ -46,6 +46,12 @@ WORKER = textwrap.dedent("""
     pm_bf.clear(); pm_bf.insert_genome(gens[d.rank], k)
     pm.merge("or")
     assert np.array_equal(pm_bf.to_numpy(), a.to_numpy()), "peer-memory merge != OR"
+    # the same merge ordered by stream barriers (one-word NCCL all-reduces) instead of host barriers,
+    # back to back without any host synchronisation in between
+    for _ in range(3):
+        pm_bf.clear(); pm_bf.insert_genome(gens[d.rank], k)
+        pm.merge("and", comm=comm)
+    assert np.array_equal(pm_bf.to_numpy(), ref.to_numpy()), "peer-memory merge (stream barriers) != AND"
     pm.close()
     t = ctx.sketch(gens[d.rank], k, 1000, common=mine)
     counts = d.gather_objects(len(t))
