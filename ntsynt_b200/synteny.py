@@ -933,20 +933,23 @@ class SyntenyEngine:
             is_internal[np.repeat(seg_lo[short_], n_) + (np.arange(int(n_.sum())) - off_)] = True
         if len(term_ids):
             is_internal[term_ids] = False
-        # open intervals (start, last minimizer) of the blocks per (assembly, contig), as (starts, ends) arrays
+        # open intervals (start, last minimizer) of the blocks per assembly, on one axis: coordinate = contig << 40 | pos
+        # (intervals of different contigs cannot meet there, so one index answers the queries of every contig)
+        SH = np.int64(40)
         bst, ben, bctg = self._block_coords(blocks)
         intervals = []
         for a in range(G):
             s_, e_, c_ = bst[:, a], ben[:, a] - self.k, bctg[:, a]
             ok = (e_ - s_) >= 2
-            s_, e_, c_ = s_[ok] + 1, e_[ok], c_[ok]
-            o = np.argsort(c_, kind="stable")
-            s_, e_, c_ = s_[o], e_[o], c_[o]
-            cb = np.flatnonzero(np.r_[True, c_[1:] != c_[:-1]]) if len(c_) else np.zeros(0, dtype=np.int64)
-            ce = np.r_[cb[1:], len(c_)] if len(c_) else cb
-            intervals.append({int(c_[i0]): (s_[i0:i1], e_[i0:i1]) for i0, i1 in zip(cb.tolist(), ce.tolist())})
+            base_ = c_[ok] << SH
+            intervals.append(IntervalIndex(base_ + s_[ok] + 1, base_ + e_[ok]) if ok.any() else None)
         self._tick("r_blockinfo")
-        # --- filter_minimizers_synteny_blocks (:256-280), vectorised per contig
+        # --- filter_minimizers_synteny_blocks (:256-280), vectorised over all contigs of an assembly
+        # all new minimizers of all assemblies through ONE device lookup
+        sizes = [len(x[0]) for x in new]
+        all_h1 = np.concatenate([x[0] for x in new]) if sum(sizes) else np.zeros(0, dtype=np.uint64)
+        all_vid = self._lookup(all_h1) if len(all_h1) else np.zeros(0, dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
         kept = []       # per assembly: (h1, pos, ctg, sublist_id)
         for a in range(G):
             h1, pos, ctg = new[a]
@@ -954,39 +957,35 @@ class SyntenyEngine:
             if n == 0:
                 kept.append((h1, pos, ctg, np.zeros(0, dtype=np.int64)))
                 continue
-            vid_new = self._lookup(h1)
+            vid_new = all_vid[offs[a]:offs[a + 1]]
             internal_hit = np.zeros(n, dtype=bool)
             known = vid_new >= 0
             internal_hit[known] = is_internal[vid_new[known]]
-            inside = np.zeros(n, dtype=bool)
-            idx_by_ctg = {}
-            for c in np.unique(ctg):
-                c = int(c)
-                if c in intervals[a]:
-                    st, en = intervals[a][c]
-                    ii = IntervalIndex(st, en)
-                    idx_by_ctg[c] = ii
-                    sel = np.nonzero(ctg == c)[0]
-                    inside[sel] = ii.overlaps(pos[sel], pos[sel] + 1)
+            ii = intervals[a]
+            key = (ctg.astype(np.int64) << SH) + pos
+            inside = ii.overlaps(key, key + 1) if ii is not None else np.zeros(n, dtype=bool)
             keep = ~internal_hit & ~inside
-            kh, kp, kc = h1[keep], pos[keep], ctg[keep]
+            kh, kp, kc, kk = h1[keep], pos[keep], ctg[keep], key[keep]
             # cut between consecutive kept minimizers of one contig whose span overlaps a block interval
             cut = np.ones(len(kh), dtype=bool)
             if len(kh) > 1:
                 same = kc[1:] == kc[:-1]
                 ov = np.zeros(len(kh) - 1, dtype=bool)
-                for c, ii in idx_by_ctg.items():
-                    sel = np.nonzero(same & (kc[1:] == c))[0]
-                    if len(sel):
-                        ov[sel] = ii.overlaps(kp[:-1][sel], kp[1:][sel])
+                if ii is not None:
+                    sel = np.flatnonzero(same)
+                    ov[sel] = ii.overlaps(kk[:-1][sel], kk[1:][sel])
                 cut[1:] = ~same | ov
             kept.append((kh, kp, kc, np.cumsum(cut) - 1))
         self._tick("r_filter")
         # --- G-way intersection (ntjoin_utils.filter_minimizers :152-165)
-        common = None
-        for a in range(G):
-            hs = np.unique(kept[a][0])
-            common = hs if common is None else np.intersect1d(common, hs, assume_unique=True)
+        # every assembly's keys are distinct by now (read_minimizers dropped the repeated ones), so a key is common
+        # to all G lists iff it occurs G times in their concatenation: one sort instead of G sorts + G-1 merges
+        allk = np.concatenate([x[0] for x in kept])
+        if len(allk):
+            uk, cnt_k = np.unique(allk, return_counts=True)
+            common = uk[cnt_k == G]
+        else:
+            common = allk
         lists = []
         for a in range(G):
             kh, kp, kc, sub = kept[a]
