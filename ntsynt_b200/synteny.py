@@ -1124,16 +1124,18 @@ class SyntenyEngine:
         def nbrs(x):
             res = memo.get(x)
             if res is None:
-                res = {y: G for y in old_nbrs(x)}
+                row = rows.get(x)
+                res = {y: G for y in (row if row is not None else old_nbrs(x)) if y >= 0}
                 for e in inc_new.get(x, ()):
                     y = e[1] if e[0] == x else e[0]
                     res[y] = wt[e]
                 memo[x] = res
             return res
 
-        cand_v = set(cand_v)
         if not cand_v:
             return []
+        rows = dict(zip(cand_v, self.nbr[np.asarray(cand_v, dtype=np.int64)].tolist()))    # old neighbours, one gather
+        cand_v = set(cand_v)
         bumped = {}
 
         fullc = {}          # number of full-weight edges at a candidate; a bump adds one at both ends
@@ -1185,14 +1187,15 @@ class SyntenyEngine:
         def overlap(s, t):
             return bool((np.abs(self.POS[:, s] - self.POS[:, t]) < self.k).any())
 
-        deg = lambda x: int((self.nbr[x] >= 0).sum())   # noqa: E731
-        for (u, v) in low:
+        # the graph is not modified inside the loop (removals are applied at the end), so the degree test of every
+        # flagged pair can be taken up front
+        la = np.array(low, dtype=np.int64).reshape(-1, 2)
+        both1 = ((self.nbr[la[:, 0]] >= 0).sum(axis=1) == 1) & ((self.nbr[la[:, 1]] >= 0).sum(axis=1) == 1)
+        for (u, v) in la[both1].tolist():
             # igraph reports (source, target) = (min id, max id); the reference then orders by NAME string
             s, t = (u, v)
             if name(s) > name(t):
                 s, t = t, s
-            if deg(s) != 1 or deg(t) != 1:
-                continue
             erode_target = True
             cs, ct = s, t
             visited = {cs, ct}
