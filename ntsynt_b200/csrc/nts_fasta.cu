@@ -41,18 +41,54 @@ uint64_t pack_piece(const char* p, const char* e, uint64_t b0, uint64_t* words, 
     uint64_t b = b0, word = 0;
     bool in_run = false;
     uint64_t run_start = 0;
-    for (; p < e; ++p) {
-        uint8_t c = L.v[(unsigned char)*p];
-        if (c == 5) continue;
-        if (c == 4) {
-            if (!in_run) { in_run = true; run_start = b; }
-            c = 0;
-        } else if (in_run) {
-            runs.push_back({run_start, b - run_start});
-            in_run = false;
+    constexpr uint64_t ONES = 0x0101010101010101ull, LOW7 = 0x7F7F7F7F7F7F7F7Full, HIGH = 0x8080808080808080ull;
+    // 0x80 in every byte of v that is zero (exact per byte: no carries cross byte boundaries)
+    auto zero_bytes = [&](uint64_t v) { return ~(((v & LOW7) + LOW7) | v) & HIGH; };
+    while (p < e) {
+        uint64_t nslow = 1;
+        // fast path: 8 bytes that are all ACGT / acgt (no line end, nothing ambiguous)
+        if (e - p >= 8) {
+            uint64_t x;
+            memcpy(&x, p, 8);
+            const uint64_t up = x & 0xDFDFDFDFDFDFDFDFull;                       // fold to upper case
+            const uint64_t ok = zero_bytes(up ^ (ONES * 'A')) | zero_bytes(up ^ (ONES * 'C')) |
+                                zero_bytes(up ^ (ONES * 'G')) | zero_bytes(up ^ (ONES * 'T'));
+            if (ok == HIGH) {
+                if (in_run) { runs.push_back({run_start, b - run_start}); in_run = false; }
+                // A 0x41 C 0x43 G 0x47 T 0x54: ((c >> 1) ^ (c >> 2)) & 3 = 0, 1, 2, 3
+                const uint64_t c2 = ((x >> 1) ^ (x >> 2)) & 0x0303030303030303ull;
+                // gather the four 2-bit codes of each 32-bit half into one byte: bit 8i -> bit 24 + 2i
+                constexpr uint32_t M = (1u << 24) | (1u << 18) | (1u << 12) | (1u << 6);
+                const uint32_t lo = ((uint32_t)c2 * M) >> 24, hi = ((uint32_t)(c2 >> 32) * M) >> 24;
+                const uint64_t code = lo | (hi << 8);
+                const unsigned sh = (unsigned)(b & 31) * 2;
+                word |= code << sh;
+                const uint64_t nb = b + 8;
+                if ((nb >> 5) != (b >> 5)) { words[b >> 5] = word; word = sh > 48 ? code >> (64 - sh) : 0; }   // spill into the next word
+                p += 8; b = nb;
+                continue;
+            }
+            nslow = (uint64_t)(__builtin_ctzll(~ok & HIGH) >> 3) + 1;            // the valid prefix + the byte that is not a base
         }
-        word |= (uint64_t)c << ((b & 31) * 2);
-        if ((++b & 31) == 0) { words[(b >> 5) - 1] = word; word = 0; }
+        // slow path: those bytes one by one, then on through whatever else is not a base (line ends, N runs)
+        for (;;) {
+            uint8_t c = L.v[(unsigned char)*p];
+            ++p;
+            if (c != 5) {
+                if (c == 4) {
+                    if (!in_run) { in_run = true; run_start = b; }
+                    c = 0;
+                } else if (in_run) {
+                    runs.push_back({run_start, b - run_start});
+                    in_run = false;
+                }
+                word |= (uint64_t)c << ((b & 31) * 2);
+                if ((++b & 31) == 0) { words[(b >> 5) - 1] = word; word = 0; }
+            }
+            if (p >= e) break;
+            if (nslow > 1) { --nslow; continue; }
+            if (L.v[(unsigned char)*p] < 4) break;
+        }
     }
     if (b & 31) words[b >> 5] = word;
     if (in_run) runs.push_back({run_start, b - run_start});
