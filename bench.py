@@ -553,6 +553,14 @@ def run_ours_multi(args, dist, ctx):
     fam = max((f for f in alg if prof[f][2]), key=lambda f: prof[f][0])
     f_ms, f_units, f_n = prof[fam]
     achieved = (alg[fam] * f_units / f_n) / ((f_ms / f_n) / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json"), encoding="utf-8") as fh:
+            tj = json.load(fh).get(fam, {})
+        if abs(tj.get("genome_mbp", 0) - args.genome_mbp) < 1:
+            traffic = tj.get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
@@ -572,7 +580,7 @@ def run_ours_multi(args, dist, ctx):
                     "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"kernel": fam, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "rank": 0,
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "rank": 0,
                          "kernel_ms_per_step": {f: round(prof[f][0] / args.steps, 3) for f in prof if prof[f][2]}},
             "cpu_baseline": None,
         }))
