@@ -102,3 +102,43 @@ def test_ancestor_formula_base_composition():
     bases = np.array([f(1234, 0, 0.0, 0, p) for p in range(20000)])
     frac = np.bincount(bases, minlength=4) / len(bases)
     assert abs(frac[0] - 0.295) < 0.02 and abs(frac[1] - 0.205) < 0.02 and abs(frac[3] - 0.295) < 0.02
+
+
+def test_native_graph_walks_on_tiny_inputs():
+    "nts_host_walk_paths / nts_host_simplify: empty inputs, one three-run path through two sparse edges, one bubble"
+    import ctypes as C
+    from ntsynt_b200._lib import check, lib, ptr
+    i64 = np.int64
+    # runs [0..2] [3..5] [6..8]; sparse edges 2-6 and 8-3: path 0..2, 6..8, 3..5
+    nbr = np.array([[-1, 1], [0, 2], [1, 6], [8, 4], [3, 5], [4, -1], [2, 7], [6, 8], [7, 3]], dtype=np.int32)
+    starts, ends = np.array([0, 3, 6], dtype=i64), np.array([2, 5, 8], dtype=i64)
+    sv = np.array([2, 3, 6, 8], dtype=i64)
+    opos = np.arange(100, 109, dtype=i64)
+    lo, hi, off = (np.zeros(16, dtype=i64) for _ in range(3))
+    dr = np.zeros(16, dtype=np.int8)
+    n_p, n_s = C.c_int64(), C.c_int64()
+    check(lib.nts_host_walk_paths(nbr.ctypes.data_as(C.POINTER(C.c_int32)), 9, ptr(starts, C.c_int64), ptr(ends, C.c_int64), 3,
+                                  ptr(sv, C.c_int64), 4, ptr(opos, C.c_int64), ptr(lo, C.c_int64), ptr(hi, C.c_int64),
+                                  dr.ctypes.data_as(C.POINTER(C.c_int8)), ptr(off, C.c_int64), 16, C.byref(n_p), C.byref(n_s)))
+    assert (n_p.value, n_s.value) == (1, 3)
+    assert list(zip(lo[:3].tolist(), hi[:3].tolist(), dr[:3].tolist())) == [(0, 2, 1), (6, 8, 1), (3, 5, 1)]
+    check(lib.nts_host_walk_paths(nbr.ctypes.data_as(C.POINTER(C.c_int32)), 9, ptr(starts, C.c_int64), ptr(ends, C.c_int64), 3,
+                                  ptr(sv, C.c_int64), 0, ptr(opos, C.c_int64), ptr(lo, C.c_int64), ptr(hi, C.c_int64),
+                                  dr.ctypes.data_as(C.POINTER(C.c_int8)), ptr(off, C.c_int64), 16, C.byref(n_p), C.byref(n_s)))
+    assert (n_p.value, n_s.value) == (0, 0)
+    # bubble: assembly 0 lists 0 1 2 3, assembly 1 lists 0 1 3 (vertex 2 missing there is impossible after the join, so
+    # use ranks that put 2 elsewhere): a0 = [0,1,2,3,4], a1 = [0,1,3,4,2] -> 1 and 3 have three neighbours
+    rank = np.array([[0, 1, 2, 3, 4], [0, 1, 4, 2, 3]], dtype=np.uint32)
+    inv = np.array([[0, 1, 2, 3, 4], [0, 1, 3, 4, 2]], dtype=np.uint32)
+    ctg = np.zeros((2, 5), dtype=np.int32)
+    cand = np.array([1, 3], dtype=i64)
+    bs, bt, rm = (np.zeros(16, dtype=i64) for _ in range(3))
+    n_out = C.c_int64()
+    check(lib.nts_host_simplify(ptr(cand, C.c_int64), 2, ptr(rank, C.c_uint32), ptr(inv, C.c_uint32),
+                                ctg.ctypes.data_as(C.POINTER(C.c_int32)), 5, 5, 2, ptr(bs, C.c_int64), ptr(bt, C.c_int64),
+                                ptr(rm, C.c_int64), 16, C.byref(n_out)))
+    assert n_out.value == 1 and (bs[0], bt[0], rm[0]) == (1, 3, 2)      # edge 1-3 closes the triangle over vertex 2
+    check(lib.nts_host_simplify(ptr(cand, C.c_int64), 0, ptr(rank, C.c_uint32), ptr(inv, C.c_uint32),
+                                ctg.ctypes.data_as(C.POINTER(C.c_int32)), 5, 5, 2, ptr(bs, C.c_int64), ptr(bt, C.c_int64),
+                                ptr(rm, C.c_int64), 16, C.byref(n_out)))
+    assert n_out.value == 0
