@@ -55,6 +55,10 @@ int nts_timer_stop(nts_ctx* ctx, float* ms_out);
 uint64_t nts_launch_count(const nts_ctx* ctx);
 /* statistics: dense sub-tiles the sparse sketch kernel handed to the dense selector (unresolved windows) since creation */
 uint64_t nts_sketch_escalated(const nts_ctx* ctx);
+/* statistics: Bloom inserts that took the partitioned path (csrc/nts_part.cuh), and the items those inserts applied
+ * through their overflow lists (heavy-hitter k-mers), since creation */
+uint64_t nts_part_inserts(const nts_ctx* ctx);
+uint64_t nts_part_overflow_items(const nts_ctx* ctx);
 /* free / total device memory in bytes */
 int nts_mem_info(nts_ctx* ctx, uint64_t* free_b, uint64_t* total_b);
 /* Per-kernel-family device timing with CUDA events on the context's stream (bench.py's roofline
@@ -146,13 +150,17 @@ int nts_bf_clear(nts_bf* bf);
 /* a2: bf->insert(record.seq) for every record (cpp:128-131): sets bit ntHash2_h0(kmer) mod m
  * for every all-ACGT k-mer (kernels i + iii-a). */
 int nts_bf_insert_genome(nts_bf* bf, const nts_genome* g, uint32_t k);
+/* bf = bits(g): nts_bf_clear + nts_bf_insert_genome without the zero-fill pass (the first level of cpp:122-131) */
+int nts_bf_set_genome(nts_bf* bf, const nts_genome* g, uint32_t k);
 /* a3: the cascade of cpp:136-160 with one hash function == dst &= src (kernel iii-b) */
 int nts_bf_and(nts_bf* dst, const nts_bf* src);
 int nts_bf_or(nts_bf* dst, const nts_bf* src);
-/* The whole of src/ntsynt_make_common_bf.cpp:107-160 in one call: zero both filters, then
+/* The whole of src/ntsynt_make_common_bf.cpp:107-160 in one call:
  * common = AND over i of bits(genomes[i]) (genomes in the caller's sorted-path order; `level` is scratch of the same
- * size, may be NULL when n == 1).  Large inputs are pipelined over two CUDA streams: the binning pass of genome i+1
- * overlaps the apply pass of genome i.  Result is bit-identical to nts_bf_insert_genome + nts_bf_and. */
+ * size, may be NULL when n == 1; neither needs to be zeroed).  Genome 0 is written as a whole filter, every further
+ * genome as next = current & bits(genome) into the other filter (the cascade level of cpp:136-160), so there is no
+ * zero-fill and no separate AND pass; the two filters may swap their device storage.  Result is bit-identical to
+ * nts_bf_insert_genome + nts_bf_and. */
 int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k);
 /* repeat filter, bin/ntsynt_make_repeat_bfs.py:56-69: rep |= k-mers seen >= 2x in g (kernel iii-d).
  * `scratch` is a per-genome filter of the same size that the call clears and uses. */

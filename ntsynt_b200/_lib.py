@@ -49,6 +49,8 @@ _SIGS = {
     "nts_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "nts_launch_count": (C.c_uint64, [vp]),
     "nts_sketch_escalated": (C.c_uint64, [vp]),
+    "nts_part_inserts": (C.c_uint64, [vp]),
+    "nts_part_overflow_items": (C.c_uint64, [vp]),
     "nts_mem_info": (C.c_int, [vp, u64p, u64p]),
     "nts_prof_enable": (C.c_int, [vp, C.c_int]),
     "nts_prof_reset": (C.c_int, [vp]),
@@ -77,6 +79,7 @@ _SIGS = {
     "nts_bf_size_bytes": (C.c_uint64, [vp]),
     "nts_bf_clear": (C.c_int, [vp]),
     "nts_bf_insert_genome": (C.c_int, [vp, vp, C.c_uint32]),
+    "nts_bf_set_genome": (C.c_int, [vp, vp, C.c_uint32]),
     "nts_bf_and": (C.c_int, [vp, vp]),
     "nts_bf_or": (C.c_int, [vp, vp]),
     "nts_bf_build_common": (C.c_int, [vp, vp, vpp, C.c_uint32, C.c_uint32]),

@@ -13,12 +13,11 @@
 
 namespace nts {
 
-int bf_insert_partitioned(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid,
-                          bool* done);
 void part_scratch_release(nts_ctx* ctx);
-int part_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t total_valid, bool* ok);
-int part_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid);
-int part_apply(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf);
+int part_insert(nts_ctx* ctx, cudaStream_t st, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, uint64_t m,
+                const uint32_t* prev, uint32_t* out, uint64_t alloc_bytes, int mode, bool* done);
+void part_check(nts_ctx* ctx, bool* overflowed, uint64_t* ovf_items);
+enum { APPLY_SET = 0, APPLY_AND = 1, APPLY_OR = 2 };      // nts_part.cuh
 
 static thread_local std::string g_err;
 
@@ -298,6 +297,10 @@ int nts_ctx_sync(nts_ctx* ctx)
 {
     NTS_CUDA(cudaSetDevice(ctx->device));
     NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    bool over = false;
+    part_check(ctx, &over, nullptr);      // an asynchronous partitioned insert whose overflow list ran out
+    if (over) return fail(NTS_ERR_OVERFLOW, "partitioned Bloom insert: overflow list exhausted; the filter is incomplete "
+                                            "(use nts_bf_insert_genome, or set NTS_BF_PARTITION=0)");
     return NTS_OK;
 }
 
@@ -349,7 +352,8 @@ int nts_prof_reset(nts_ctx* ctx)
 }
 
 static const char* const PROF_NAMES[PROF_COUNT] = {"fill", "bf_insert", "bf_combine", "sketch", "sketch_post", "join",
-                                                   "synth", "popcount", "bf_repeat", "edges", "nccl", "bf_build", "bf_bin", "bf_apply"};
+                                                   "synth", "popcount", "bf_repeat", "edges", "nccl", "bf_build", "bf_part1", "bf_part2",
+                                                   "bf_apply", "graph"};
 
 int nts_prof_count(void) { return PROF_COUNT; }
 const char* nts_prof_name(int id) { return (id >= 0 && id < PROF_COUNT) ? PROF_NAMES[id] : ""; }
@@ -613,25 +617,11 @@ static int mod_params(const nts_bf* bf, uint64_t* m, uint64_t* mprime)
     return NTS_OK;
 }
 
-int nts_bf_insert_genome_async(nts_bf* bf, const nts_genome* g, uint32_t k)
+static int bf_combine(nts_bf* dst, const nts_bf* src, int op, bool sync);
+
+// direct insert: one RED.OR per k-mer (small filters; the fallback of the partitioned path)
+static int bf_insert_direct(nts_ctx* ctx, nts_bf* bf, const nts_genome* g, const nts_view* v, const HashTables* tabs)
 {
-    if (!bf || !g) return fail(NTS_ERR_ARG, "null argument");
-    if (bf->ctx != g->ctx) return fail(NTS_ERR_ARG, "filter and genome live on different contexts");
-    nts_ctx* ctx = bf->ctx;
-    NTS_CUDA(cudaSetDevice(ctx->device));
-    const HashTables* tabs = nullptr;
-    int rc = get_tables(ctx, k, &tabs);
-    if (rc) return rc;
-    const nts_view* v = nullptr;
-    rc = get_plain_view(g, k, &v);
-    if (rc) return rc;
-    if (v->total_valid == 0) return NTS_OK;
-    {
-        bool done = false;
-        rc = bf_insert_partitioned(ctx, bf, device_view(g, v), tabs, v->total_valid, &done);
-        if (rc) return rc;
-        if (done) return NTS_OK;
-    }
     uint64_t m, mp;
     mod_params(bf, &m, &mp);
     constexpr int THREADS = 256;
@@ -646,12 +636,85 @@ int nts_bf_insert_genome_async(nts_bf* bf, const nts_genome* g, uint32_t k)
     return NTS_OK;
 }
 
+// bits(genome) into a filter.  mode APPLY_OR: bf |= bits (the reference's bf->insert(seq), src/ntsynt_make_common_bf.cpp:130);
+// APPLY_SET: bf = bits (no zero-fill needed); APPLY_AND: bf = prev & bits with prev a different filter of the same size
+// (one level of the cascade, cpp:136-160).  Large filters take the partitioned path (nts_part.cuh); *partitioned says so.
+static int bf_insert_mode(nts_bf* bf, const nts_bf* prev, const nts_genome* g, uint32_t k, int mode, bool* partitioned)
+{
+    nts_ctx* ctx = bf->ctx;
+    if (partitioned) *partitioned = false;
+    const HashTables* tabs = nullptr;
+    int rc = get_tables(ctx, k, &tabs);
+    if (rc) return rc;
+    const nts_view* v = nullptr;
+    rc = get_plain_view(g, k, &v);
+    if (rc) return rc;
+    const uint64_t n16 = bf->alloc_bytes / 16;
+    bool done = false;
+    if (v->total_valid) {
+        rc = part_insert(ctx, ctx->stream, device_view(g, v), tabs, v->total_valid, bf->bytes * 8,
+                         mode == APPLY_AND ? prev->words.p : bf->words.p, bf->words.p, bf->alloc_bytes, mode, &done);
+        if (rc) return rc;
+    }
+    if (done) { if (partitioned) *partitioned = true; return NTS_OK; }
+    // direct path: zero-fill (SET / AND), RED.OR per k-mer, separate AND pass
+    if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
+    if (v->total_valid && (rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
+    if (mode == APPLY_AND) {
+        ProfScope prof(ctx, PROF_BF_COMBINE, (double)bf->alloc_bytes);
+        bf_combine_kernel<<<grid_for(ctx, n16 / 4 + 1, 256, 16), 256, 0, ctx->stream>>>(
+            reinterpret_cast<uint4*>(bf->words.p), reinterpret_cast<const uint4*>(prev->words.p), n16, 0);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+    }
+    return NTS_OK;
+}
+
+// synchronise and make sure the last partitioned insert did not exhaust its overflow list; if it did, redo it directly
+static int bf_finish_insert(nts_bf* bf, const nts_bf* prev, const nts_genome* g, uint32_t k, int mode)
+{
+    nts_ctx* ctx = bf->ctx;
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    bool over = false;
+    part_check(ctx, &over, nullptr);
+    if (!over) return NTS_OK;
+    // pathological input (one k-mer making up a large part of the genome): OR is idempotent, SET / AND start over
+    const HashTables* tabs = nullptr;
+    int rc = get_tables(ctx, k, &tabs);
+    if (rc) return rc;
+    const nts_view* v = nullptr;
+    if ((rc = get_plain_view(g, k, &v))) return rc;
+    if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
+    if ((rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
+    if (mode == APPLY_AND && (rc = bf_combine(bf, prev, 0, false))) return rc;
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+int nts_bf_insert_genome_async(nts_bf* bf, const nts_genome* g, uint32_t k)
+{
+    if (!bf || !g) return fail(NTS_ERR_ARG, "null argument");
+    if (bf->ctx != g->ctx) return fail(NTS_ERR_ARG, "filter and genome live on different contexts");
+    NTS_CUDA(cudaSetDevice(bf->ctx->device));
+    return bf_insert_mode(bf, nullptr, g, k, APPLY_OR, nullptr);
+}
+
 int nts_bf_insert_genome(nts_bf* bf, const nts_genome* g, uint32_t k)
 {
     int rc = nts_bf_insert_genome_async(bf, g, k);
     if (rc) return rc;
-    NTS_CUDA(cudaStreamSynchronize(bf->ctx->stream));
-    return NTS_OK;
+    return bf_finish_insert(bf, nullptr, g, k, APPLY_OR);
+}
+
+/* bf = bits(genome): like nts_bf_clear + nts_bf_insert_genome without the zero-fill pass */
+int nts_bf_set_genome(nts_bf* bf, const nts_genome* g, uint32_t k)
+{
+    if (!bf || !g) return fail(NTS_ERR_ARG, "null argument");
+    if (bf->ctx != g->ctx) return fail(NTS_ERR_ARG, "filter and genome live on different contexts");
+    NTS_CUDA(cudaSetDevice(bf->ctx->device));
+    int rc = bf_insert_mode(bf, nullptr, g, k, APPLY_SET, nullptr);
+    if (rc) return rc;
+    return bf_finish_insert(bf, nullptr, g, k, APPLY_SET);
 }
 
 static int bf_combine(nts_bf* dst, const nts_bf* src, int op, bool sync)
@@ -676,8 +739,9 @@ int nts_bf_or(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 1, t
 int nts_bf_and_async(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 0, false); }
 
 /* src/ntsynt_make_common_bf.cpp:107-160 in one call: common = AND over the genomes of bits(genome), genomes in the
- * caller's (sorted-path) order.  Large inputs are pipelined over two streams: the binning pass of genome i+1 (bound by
- * shared-memory atomics in the SMs) runs while the apply pass of genome i (bound by the L2 atomic units) is in flight. */
+ * caller's (sorted-path) order.  Genome 0 is SET into one filter; every further genome is applied as
+ * next = current & bits(genome) into the other filter (the cascade level), and the two swap -- no zero-fill and no
+ * separate AND pass.  On return `common` holds the result and `level` is scratch. */
 int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k)
 {
     if (!common || !genomes || n < 1 || (n > 1 && !level)) return fail(NTS_ERR_ARG, "null argument");
@@ -686,108 +750,23 @@ int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* 
     for (uint32_t i = 0; i < n; ++i)
         if (!genomes[i] || genomes[i]->ctx != ctx) return fail(NTS_ERR_ARG, "bad genome");
     NTS_CUDA(cudaSetDevice(ctx->device));
-    const HashTables* tabs = nullptr;
-    int rc = get_tables(ctx, k, &tabs);
-    if (rc) return rc;
-    // pipelined path: one bucket plan (sized for the largest genome) shared by both scratch slots
-    // Off unless NTS_BF_PIPELINE=1: measured on B200 the overlap buys nothing (both passes are bound by the SMs'
-    // LSU atomic issue rate -- profiles/README.md), and serial passes give clean per-kernel timings.
-    bool pipe = false;
-    if (const char* env = getenv("NTS_BF_PIPELINE")) pipe = n >= 2 && env[0] == '1';
-    std::vector<const nts_view*> views(n);
-    uint64_t max_valid = 0, sum_valid = 0;
-    for (uint32_t i = 0; i < n && pipe; ++i) {          // (the serial path takes each view when it gets to the genome, so
-        rc = get_plain_view(genomes[i], k, &views[i]);  //  that an asynchronous upload of genome i+1 overlaps insert i)
-        if (rc) return rc;
-        max_valid = std::max(max_valid, views[i]->total_valid);
-        sum_valid += views[i]->total_valid;
+    ProfScope prof(ctx, PROF_BF_BUILD, 0.0, true);
+    nts_bf* cur = common;
+    nts_bf* other = level;
+    int rc = bf_insert_mode(cur, nullptr, genomes[0], k, APPLY_SET, nullptr);
+    if (rc || (rc = bf_finish_insert(cur, nullptr, genomes[0], k, APPLY_SET))) return rc;
+    for (uint32_t i = 1; i < n; ++i) {
+        if ((rc = bf_insert_mode(other, cur, genomes[i], k, APPLY_AND, nullptr)) ||
+            (rc = bf_finish_insert(other, cur, genomes[i], k, APPLY_AND)))
+            return rc;
+        std::swap(cur, other);
     }
-    for (uint32_t i = 0; i < n && pipe; ++i) pipe = views[i]->total_valid > 0;
-    for (int slot = 0; slot < 2 && pipe; ++slot) {
-        bool ok = false;
-        rc = part_prepare(ctx, slot, common->bytes * 8, max_valid, &ok);
-        if (rc) return rc;
-        pipe = ok;
-    }
-    DevBuf<uint32_t> level2;                           // n >= 3: the level filters alternate so that binning never waits for an AND
-    if (pipe && n >= 3 && level2.alloc(common->alloc_bytes / 4) != cudaSuccess) pipe = false;
-    if (!pipe) {
-        rc = bf_fill(common, 0);
-        if (rc) return rc;
-        rc = nts_bf_insert_genome_async(common, genomes[0], k);
-        if (rc) return rc;
-        for (uint32_t i = 1; i < n; ++i) {
-            if ((rc = bf_fill(level, 0)) || (rc = nts_bf_insert_genome_async(level, genomes[i], k)) || (rc = bf_combine(common, level, 0, false)))
-                return rc;
-        }
-        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
-        return NTS_OK;
-    }
-    if (!ctx->stream2) NTS_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-    cudaStream_t A = ctx->stream, B = ctx->stream2;
-    auto target = [&](uint32_t i) -> uint32_t* { return i == 0 ? common->words.p : (((i - 1) & 1) ? level2.p : level->words.p); };
-    struct Ev { std::vector<cudaEvent_t> v; ~Ev() { for (auto e : v) cudaEventDestroy(e); }
-                cudaEvent_t make() { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); v.push_back(e); return e; } } evs;
-    std::vector<cudaEvent_t> BN(n), AP(n), FR(n, nullptr);
-    const uint64_t n16 = common->alloc_bytes / 16;
-    auto fill = [&](uint32_t* p) {
-        fill_u128_kernel<<<grid_for(ctx, n16, 256, 16), 256, 0, A>>>(reinterpret_cast<uint4*>(p), n16, 0u);
-        ctx->launches++;
-    };
-    // a filter object for the bin / apply launches of genome i (they only use words.p and bytes)
-    nts_bf tgt; tgt.ctx = ctx; tgt.bytes = common->bytes; tgt.alloc_bytes = common->alloc_bytes;
-    auto with_target = [&](uint32_t i, auto&& fn) -> int {
-        uint32_t* keep_p = tgt.words.p; size_t keep_n = tgt.words.n;
-        tgt.words.p = target(i); tgt.words.n = common->words.n;
-        int r = fn(&tgt);
-        tgt.words.p = keep_p; tgt.words.n = keep_n;     // never owns the memory
-        return r;
-    };
-    {
-        ProfScope prof(ctx, PROF_BF_BUILD, (double)sum_valid, true);
-        fill(common->words.p);
-        fill(level->words.p);
-        if (n >= 3) fill(level2.p);
-        cudaEvent_t f0 = evs.make();
-        NTS_CUDA(cudaEventRecord(f0, A));
-        NTS_CUDA(cudaStreamWaitEvent(B, f0, 0));
-        rc = with_target(0, [&](nts_bf* t) { return part_bin(ctx, 0, B, t, device_view(genomes[0], views[0]), tabs, views[0]->total_valid); });
-        if (rc) return rc;
-        BN[0] = evs.make();
-        NTS_CUDA(cudaEventRecord(BN[0], B));
-        for (uint32_t i = 0; i < n; ++i) {
-            if (i + 1 < n) {                            // bin of the next genome: its slot must be free, its target zeroed
-                if (i >= 1) NTS_CUDA(cudaStreamWaitEvent(B, AP[i - 1], 0));
-                if (FR[i + 1]) NTS_CUDA(cudaStreamWaitEvent(B, FR[i + 1], 0));
-                rc = with_target(i + 1, [&](nts_bf* t) {
-                    return part_bin(ctx, (int)((i + 1) & 1), B, t, device_view(genomes[i + 1], views[i + 1]), tabs, views[i + 1]->total_valid);
-                });
-                if (rc) return rc;
-                BN[i + 1] = evs.make();
-                NTS_CUDA(cudaEventRecord(BN[i + 1], B));
-            }
-            NTS_CUDA(cudaStreamWaitEvent(A, BN[i], 0));
-            rc = with_target(i, [&](nts_bf* t) { return part_apply(ctx, (int)(i & 1), A, t); });
-            if (rc) return rc;
-            AP[i] = evs.make();
-            NTS_CUDA(cudaEventRecord(AP[i], A));
-            if (i >= 1) {
-                bf_combine_kernel<<<grid_for(ctx, n16 / 4 + 1, 256, 16), 256, 0, A>>>(
-                    reinterpret_cast<uint4*>(common->words.p), reinterpret_cast<const uint4*>(target(i)), n16, 0);
-                ctx->launches++;
-                if (i + 2 < n) {                        // the same level filter takes genome i + 2
-                    fill(target(i));
-                    FR[i + 2] = evs.make();
-                    NTS_CUDA(cudaEventRecord(FR[i + 2], A));
-                }
-            }
-        }
-        NTS_CUDA(cudaGetLastError());
-    }
-    NTS_CUDA(cudaStreamSynchronize(A));
-    NTS_CUDA(cudaStreamSynchronize(B));
+    if (cur != common) std::swap(common->words, level->words);     // same size, same context: hand the result over
     return NTS_OK;
 }
+
+uint64_t nts_part_inserts(const nts_ctx* ctx) { return ctx ? ctx->part_inserts : 0; }
+uint64_t nts_part_overflow_items(const nts_ctx* ctx) { return ctx ? ctx->part_overflow_items : 0; }
 
 int nts_bf_insert_repeats(nts_bf* rep, nts_bf* scratch, const nts_genome* g, uint32_t k)
 {

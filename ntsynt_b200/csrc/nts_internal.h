@@ -56,7 +56,8 @@ struct DevBuf {
 namespace nts {
 // per-kernel-family device timing (CUDA events on the context's stream), off unless enabled
 enum ProfId { PROF_FILL = 0, PROF_BF_INSERT, PROF_BF_COMBINE, PROF_SKETCH, PROF_SKETCH_POST, PROF_JOIN, PROF_SYNTH,
-              PROF_POPCOUNT, PROF_BF_REPEAT, PROF_EDGES, PROF_NCCL, PROF_BF_BUILD, PROF_BF_BIN, PROF_BF_APPLY, PROF_COUNT };
+              PROF_POPCOUNT, PROF_BF_REPEAT, PROF_EDGES, PROF_NCCL, PROF_BF_BUILD, PROF_BF_PART1, PROF_BF_PART2, PROF_BF_APPLY,
+              PROF_GRAPH, PROF_COUNT };
 struct ProfPending { int id; cudaEvent_t e0, e1; double units; };
 }  // namespace nts
 
@@ -74,6 +75,8 @@ struct nts_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
     uint64_t sketch_escalated = 0;   // dense sub-tiles the sparse sketch kernel handed to the dense one (statistics)
+    uint64_t part_inserts = 0;       // Bloom inserts that took the partitioned path (statistics / tests)
+    uint64_t part_overflow_items = 0;   // items those inserts applied through the overflow list
     int sm_count = 148;
     std::map<uint32_t, nts::HashTables*> tables;   // per k, device resident
 };

@@ -56,6 +56,16 @@ class Context:
         "dense sub-tiles the sparse sketch kernel handed to the dense selector so far (statistics)"
         return int(lib.nts_sketch_escalated(self._h))
 
+    @property
+    def part_inserts(self):
+        "Bloom inserts that took the partitioned path so far (statistics)"
+        return int(lib.nts_part_inserts(self._h))
+
+    @property
+    def part_overflow_items(self):
+        "items those inserts applied through their overflow lists (heavy-hitter k-mers)"
+        return int(lib.nts_part_overflow_items(self._h))
+
     def mem_info(self):
         f, t = C.c_uint64(), C.c_uint64()
         check(lib.nts_mem_info(self._h, C.byref(f), C.byref(t)))
@@ -166,6 +176,10 @@ class BloomFilter:
 
     def insert_genome(self, genome, k):
         check(lib.nts_bf_insert_genome(self._h, genome._h, int(k)))
+
+    def set_genome(self, genome, k):
+        "self = bits(genome): clear + insert_genome without the zero-fill pass"
+        check(lib.nts_bf_set_genome(self._h, genome._h, int(k)))
 
     def build_common(self, level, genomes, k):
         """self = AND over the genomes of their k-mer bit arrays (src/ntsynt_make_common_bf.cpp:107-160); `level` is a

@@ -35,7 +35,7 @@ def build_common_bf(ctx, genomes, paths, k, fpr=0.025, nbytes=None, log=None):
         log(f"BF size (bytes): {nbytes}")
     common = ctx.bloom(nbytes)
     if not log:
-        # one call: per-genome binning and apply passes pipelined on two streams (nts_bf_build_common)
+        # one call: genome 0 written as a whole filter, every further genome ANDed in by the apply pass (nts_bf_build_common)
         level = ctx.bloom(nbytes) if len(order) > 1 else None
         common.build_common(level, [genomes[i] for i in order], k)
         if level is not None:
@@ -121,7 +121,9 @@ def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="100
     names = [tsv_name(b, k, w) for b in bases]
     order = processing_order(names)
     genomes = [ctx.upload(p) for p in packed]
-    bf = build_common_bf(ctx, genomes, bases, k, fpr) if common else None
+    # the filter is sized from the lexicographically first PATH STRING as given (src/ntsynt_make_common_bf.cpp:107,116),
+    # not from the first basename
+    bf = build_common_bf(ctx, genomes, [str(f) for f in fastas], k, fpr) if common else None
     be = CudaBackend(ctx, [genomes[i] for i in order], [names[i] for i in order],
                      [packed[i].names for i in order], [[int(x) for x in packed[i].lengths] for i in order], k,
                      common=bf)

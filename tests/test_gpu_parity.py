@@ -307,40 +307,6 @@ def test_sparse_and_dense_sketch_kernels_agree(cuda_ctx, w):
             assert esc < 0.02 * n_tiles_dense        # the sparse kernel did the work
 
 
-@pytest.mark.parametrize("G", [2, 3, 4])
-def test_pipelined_common_filter_equals_sequential_inserts(cuda_ctx, G):
-    "nts_bf_build_common (two streams, alternating scratch slots and level filters) == insert + AND one by one"
-    k = 24
-    wl = synth.Workload(G, 6_000_000, 1.0)
-    gens = [wl.materialize(cuda_ctx, g) for g in range(G)]
-    nbytes = device.BloomFilter.size_for(gens[0].total_bases, 0.025)
-    want = cuda_ctx.bloom(nbytes)
-    lvl = cuda_ctx.bloom(nbytes)
-    want.insert_genome(gens[0], k)
-    for g in gens[1:]:
-        lvl.clear(); lvl.insert_genome(g, k); want.iand(lvl)
-    bits = want.to_numpy()
-    os.environ["NTS_BF_PARTITION"] = "1"             # small filters would otherwise take the direct path
-    os.environ["NTS_BF_PIPELINE"] = "1"              # two-stream schedule (off by default: no gain measured)
-    try:
-        got = cuda_ctx.bloom(nbytes)
-        got.from_numpy(np.full(nbytes, 0xFF, dtype=np.uint8))      # must be cleared inside
-        got.build_common(lvl, gens, k)
-        assert np.array_equal(got.to_numpy(), bits)
-        got.build_common(lvl, gens, k)                             # and be repeatable
-        assert np.array_equal(got.to_numpy(), bits)
-        del os.environ["NTS_BF_PIPELINE"]
-        got.build_common(lvl, gens, k)                             # serial schedule of the same call
-        assert np.array_equal(got.to_numpy(), bits)
-    finally:
-        del os.environ["NTS_BF_PARTITION"]
-        os.environ.pop("NTS_BF_PIPELINE", None)
-    one = cuda_ctx.bloom(nbytes)
-    one.build_common(None, gens[:1], k)
-    solo = cuda_ctx.bloom(nbytes); solo.insert_genome(gens[0], k)
-    assert np.array_equal(one.to_numpy(), solo.to_numpy())
-
-
 def test_async_upload_gives_the_same_filter_and_sketch(cuda_ctx):
     "nts_genome_upload_async: consumers order themselves after the copy (page-locked source)"
     k, w = 24, 200
