@@ -17,6 +17,7 @@ void part_scratch_release(nts_ctx* ctx);
 int part_insert(nts_ctx* ctx, cudaStream_t st, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, uint64_t m,
                 const uint32_t* prev, uint32_t* out, uint64_t alloc_bytes, int mode, bool* done);
 void part_check(nts_ctx* ctx, bool* overflowed, uint64_t* ovf_items);
+int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done);
 enum { APPLY_SET = 0, APPLY_AND = 1, APPLY_OR = 2 };      // nts_part.cuh
 
 static thread_local std::string g_err;
@@ -657,9 +658,14 @@ static int bf_insert_mode(nts_bf* bf, const nts_bf* prev, const nts_genome* g, u
         if (rc) return rc;
     }
     if (done) { if (partitioned) *partitioned = true; return NTS_OK; }
-    // direct path: zero-fill (SET / AND), RED.OR per k-mer, separate AND pass
+    // zero-fill (SET / AND), then OR the genome in -- large filters with the binning + apply pair (nts_bin.cuh), small
+    // ones with one RED.OR per k-mer -- then a separate AND pass
     if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
-    if (v->total_valid && (rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
+    if (v->total_valid) {
+        if ((rc = pair_insert(ctx, bf, device_view(g, v), tabs, v->total_valid, &done))) return rc;
+        if (done && partitioned) *partitioned = true;
+        if (!done && (rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
+    }
     if (mode == APPLY_AND) {
         ProfScope prof(ctx, PROF_BF_COMBINE, (double)bf->alloc_bytes);
         bf_combine_kernel<<<grid_for(ctx, n16 / 4 + 1, 256, 16), 256, 0, ctx->stream>>>(
@@ -739,9 +745,9 @@ int nts_bf_or(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 1, t
 int nts_bf_and_async(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 0, false); }
 
 /* src/ntsynt_make_common_bf.cpp:107-160 in one call: common = AND over the genomes of bits(genome), genomes in the
- * caller's (sorted-path) order.  Genome 0 is SET into one filter; every further genome is applied as
- * next = current & bits(genome) into the other filter (the cascade level), and the two swap -- no zero-fill and no
- * separate AND pass.  On return `common` holds the result and `level` is scratch. */
+ * caller's (sorted-path) order.  Genome 0 goes into one filter; every further genome is built as
+ * next = current & bits(genome) in the other filter (the cascade level), and the two swap.  On return `common` holds
+ * the result and `level` is scratch. */
 int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k)
 {
     if (!common || !genomes || n < 1 || (n > 1 && !level)) return fail(NTS_ERR_ARG, "null argument");

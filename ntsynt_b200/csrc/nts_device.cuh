@@ -169,9 +169,11 @@ __device__ __forceinline__ void hash_run(const GenomeView& g, const HashTables* 
                 const uint32_t E = ((I << 2) & 0xCCCCCCCCu) | (O & 0x33333333u);     // nibble q: step 2q
                 const uint32_t D = (I & 0xCCCCCCCCu) | ((O >> 2) & 0x33333333u);     // nibble q: step 2q + 1
                 const uint32_t left = n_here - t;
-                if (left >= 16) {
+                if (left >= 15) {
+                    // (15: a run of 16 k-mers = the seed + 15 steps, the shape of the Bloom insert's tiles)
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
+                        if (u == 15 && left == 15) break;
                         const uint32_t src = (u & 1) ? D : E;
                         const int q = u >> 1;
                         const uint32_t nib = (q == 0 ? (src << 4) : (src >> (4 * q - 4))) & 0xF0u;

@@ -10,7 +10,7 @@
 //                             (no atomics), stage it in bucket order in shared memory, append every bucket's run
 //                             to its global bucket (one global atomicAdd per (tile, non-empty bucket));
 //   pass 2  bf_part2_kernel : the same partition step over the items of one level-1 bucket, by final region b2;
-//   pass 3  bf_apply_kernel : a CTA owns one final region of R bits at a time: byte flags in shared memory are set
+//   pass 3  bf_apply3_kernel: a CTA owns one final region of R bits at a time: byte flags in shared memory are set
 //                             with plain stores, packed 128 flags -> 128 bits, and written with coalesced 128-bit
 //                             stores as SET (out = bits), AND (out = prev & bits; the cascade of
 //                             src/ntsynt_make_common_bf.cpp:136-160 without a separate level filter pass) or
@@ -319,7 +319,7 @@ __device__ __forceinline__ uint32_t pack16(uint4 f)
 __device__ __forceinline__ uint32_t swz(uint32_t x) { return x ^ ((x >> 3) & 0x70u); }
 
 template <int MAXT, int MAXI>
-__global__ void __launch_bounds__(MAXT) bf_apply_kernel(PartParams pp, const uint4* prev, uint4* out,
+__global__ void __launch_bounds__(MAXT) bf_apply3_kernel(PartParams pp, const uint4* prev, uint4* out,
                                                         uint64_t n16 /* uint4 words of the filter */, int mode)
 {
     extern __shared__ __align__(16) unsigned char s_flags[];

@@ -93,7 +93,37 @@ def mini():
     shutil.rmtree(tmp)
 
 
+def presets():
+    """tests/golden/presets/: the d >= 1 presets of bin/ntSynt:89-99 (G = 3 with -d 1.3, G = 5 with -d 12) on seeded
+    genomes; block files written by the reference's own bin/ntsynt_run.py under oracle/shims"""
+    import preset_cases as pc
+    os.makedirs(pc.PRESET_DIR, exist_ok=True)
+    meta = {}
+    for tag, case in pc.CASES.items():
+        gens = pc.genomes(tag)
+        tmp = tempfile.mkdtemp(prefix="mkpre_")
+        for n, recs in zip(pc.names(tag), gens):
+            synth_small.write_fasta(os.path.join(tmp, n), recs)
+        p = case["params"]
+        res = ref_harness.run_reference([os.path.join(tmp, n) for n in pc.names(tag)], os.path.join(tmp, "wd"), tag,
+                                        k=p["k"], w=p["w"], w_rounds=p["w_rounds"], indel=p["indel"], merge=p["merge"],
+                                        block_size=p["block_size"])
+        assert res["returncode"] == 0, res["log"][-2000:]
+        out = os.path.join(pc.PRESET_DIR, tag)
+        os.makedirs(out, exist_ok=True)
+        shutil.copyfile(res["blocks"], os.path.join(out, "synteny_blocks.tsv"))
+        shutil.copyfile(res["pre_merge"], os.path.join(out, "pre-collinear-merge.synteny_blocks.tsv"))
+        meta[tag] = {**{k: v for k, v in case.items() if k != "lens"}, "lens": list(case["lens"]),
+                     "genomes_sha1": pc.digest(gens),
+                     "made_by": "tests/golden/make_golden.py presets(): reference bin/ntsynt_run.py under oracle/shims"}
+        shutil.rmtree(tmp)
+    with open(os.path.join(pc.PRESET_DIR, "params.json"), "w", encoding="utf-8") as fh:
+        json.dump(meta, fh, indent=1)
+
+
 if __name__ == "__main__":
     print("hash KATs:", hash_kats())
     mini()
     print("mini fixtures written to", MINI)
+    presets()
+    print("preset fixtures written")

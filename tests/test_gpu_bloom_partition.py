@@ -1,9 +1,13 @@
-"""Bit-exact parity of the partitioned Bloom insert (csrc/nts_part.cuh: bf_part1_kernel, bf_part2_kernel,
-bf_apply_kernel, bf_overflow_kernel) -- the path every real genome takes and bench.py times -- against the direct
-RED.OR kernel and the C oracle (oracle/ntsynt_oracle.c, which follows src/ntsynt_make_common_bf.cpp:122-160).
+"""Bit-exact parity of the partitioned Bloom inserts against the direct RED.OR kernel and the C oracle
+(oracle/ntsynt_oracle.c, which follows src/ntsynt_make_common_bf.cpp:122-160):
 
-The plan knobs (NTS_BF_P1MAX, NTS_BF_P2, NTS_BF_CAP_SCALE, NTS_BF_OVF_CAP) only change bucket counts and
-capacities; every setting must give the same bits."""
+  * the production pair bf_bin_kernel + bf_apply_kernel (csrc/nts_bin.cuh) -- the path every real genome takes and
+    bench.py times -- at many buckets, with a short last region, and with bucket capacities shrunk so that the
+    overflow-to-direct-atomics branch fires (knobs NTS_BF_REGION_SHIFT, NTS_BF_CAP_SCALE);
+  * the atomics-free three-pass variant (csrc/nts_part.cuh, NTS_BF_IMPL=3; knobs NTS_BF_P1MAX, NTS_BF_P2,
+    NTS_BF_CAP_SCALE, NTS_BF_OVF_CAP).
+
+The knobs only change bucket counts and capacities; every setting must give the same bits."""
 import os
 from contextlib import contextmanager
 
@@ -65,9 +69,9 @@ PLANS = [dict(NTS_BF_P1MAX=1024, NTS_BF_P2=1024),             # R = 256 bits
 
 @pytest.mark.parametrize("plan", PLANS)
 @pytest.mark.parametrize("match", [0, 1])
-def test_partitioned_insert_modes_equal_direct_kernel(cuda_ctx, small, plan, match):
+def test_three_pass_insert_modes_equal_direct_kernel(cuda_ctx, small, plan, match):
     gens, nbytes, per = small
-    with env(NTS_BF_PARTITION=1, NTS_BF_MATCH=match, **plan):
+    with env(NTS_BF_PARTITION=1, NTS_BF_IMPL=3, NTS_BF_MATCH=match, **plan):
         n0 = cuda_ctx.part_inserts
         bf = cuda_ctx.bloom(nbytes)
         bf.from_numpy(np.full(nbytes, 0xFF, dtype=np.uint8))
@@ -90,23 +94,23 @@ def test_partitioned_insert_modes_equal_direct_kernel(cuda_ctx, small, plan, mat
 
 
 @pytest.mark.parametrize("scale", [0.9, 0.5, 0.05])
-def test_bucket_overflow_goes_through_the_overflow_list(cuda_ctx, small, scale):
+def test_three_pass_bucket_overflow_goes_through_the_overflow_list(cuda_ctx, small, scale):
     "capacities below the expected load: the surplus of every bucket is applied from the overflow list"
     gens, nbytes, per = small
-    with env(NTS_BF_PARTITION=1, NTS_BF_P1MAX=64, NTS_BF_P2=64, NTS_BF_CAP_SCALE=scale, NTS_BF_OVF_CAP=50_000_000):
+    with env(NTS_BF_PARTITION=1, NTS_BF_IMPL=3, NTS_BF_P1MAX=64, NTS_BF_P2=64, NTS_BF_CAP_SCALE=scale, NTS_BF_OVF_CAP=50_000_000):
         o0 = cuda_ctx.part_overflow_items
         bf, lvl = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
         bf.build_common(lvl, gens, K)
         assert np.array_equal(bf.to_numpy(), per[0] & per[1] & per[2])
         bf.insert_genome(gens[1], K)
-        assert np.array_equal(bf.to_numpy(), (per[0] & per[2]) | per[1])
+        assert np.array_equal(bf.to_numpy(), per[1])                  # (a & b & c) | b == b
         assert cuda_ctx.part_overflow_items - o0 > (0.05 if scale > 0.6 else 0.4) * gens[0].total_bases
         bf.close(); lvl.close()
 
 
-def test_exhausted_overflow_list_falls_back_to_the_direct_kernel(cuda_ctx, small):
+def test_three_pass_exhausted_overflow_list_falls_back_to_the_direct_kernel(cuda_ctx, small):
     gens, nbytes, per = small
-    with env(NTS_BF_PARTITION=1, NTS_BF_P1MAX=64, NTS_BF_P2=64, NTS_BF_CAP_SCALE=0.5, NTS_BF_OVF_CAP=1000):
+    with env(NTS_BF_PARTITION=1, NTS_BF_IMPL=3, NTS_BF_P1MAX=64, NTS_BF_P2=64, NTS_BF_CAP_SCALE=0.5, NTS_BF_OVF_CAP=1000):
         bf, lvl = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
         bf.build_common(lvl, gens, K)
         assert np.array_equal(bf.to_numpy(), per[0] & per[1] & per[2])
@@ -117,7 +121,8 @@ def test_exhausted_overflow_list_falls_back_to_the_direct_kernel(cuda_ctx, small
         bf.close(); lvl.close()
 
 
-def test_heavy_hitter_kmers(cuda_ctx):
+@pytest.mark.parametrize("impl", [2, 3])
+def test_heavy_hitter_kmers(cuda_ctx, impl):
     "one k-mer repeated 2 M times (poly-A) plus a tandem repeat: far more copies than any bucket holds"
     rng = np.random.default_rng(5)
     rnd = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 3_000_000).tobytes()
@@ -125,18 +130,48 @@ def test_heavy_hitter_kmers(cuda_ctx):
     g = cuda_ctx.upload(fasta.pack_records(recs))
     nbytes = device.BloomFilter.size_for(g.total_bases, 0.025)
     want = so.genome_bits(recs, K, nbytes)
-    with env(NTS_BF_PARTITION=1, NTS_BF_P1MAX=128, NTS_BF_P2=128):
+    with env(NTS_BF_PARTITION=1, NTS_BF_IMPL=impl, NTS_BF_P1MAX=128, NTS_BF_P2=128, NTS_BF_REGION_SHIFT=18):
         bf = cuda_ctx.bloom(nbytes)
-        o0 = cuda_ctx.part_overflow_items
+        o0, n0 = cuda_ctx.part_overflow_items, cuda_ctx.part_inserts
         bf.set_genome(g, K)
         assert np.array_equal(bf.to_numpy(), want)
-        assert cuda_ctx.part_overflow_items - o0 > 1_500_000
+        assert cuda_ctx.part_inserts - n0 == 1
+        if impl == 3:
+            assert cuda_ctx.part_overflow_items - o0 > 1_500_000
         bf.close()
 
 
+# ---------------------------------------------------------------------------------------- the production pair
+@pytest.mark.parametrize("shift", [14, 18, 21, 23, 27])
+@pytest.mark.parametrize("scale", [1.0, 0.6, 0.05])
+def test_pair_many_buckets_short_last_region_and_overflow_branch(cuda_ctx, small, shift, scale):
+    """bf_bin_kernel + bf_apply_kernel with 2^shift-bit regions (m = 2.4e8 bits: 1024 buckets at shift 18 -- 14 asks
+    for more than the 1024 the kernel supports and is widened --, 29 with a short last region at 23, 2 at 27) and
+    with capacities below the load (items past a bucket's capacity are applied with direct atomics)"""
+    gens, nbytes, per = small
+    with env(NTS_BF_PARTITION=1, NTS_BF_REGION_SHIFT=shift, NTS_BF_CAP_SCALE=scale):
+        n0 = cuda_ctx.part_inserts
+        bf, lvl = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
+        bf.from_numpy(np.full(nbytes, 0xFF, dtype=np.uint8))
+        bf.set_genome(gens[0], K)
+        assert np.array_equal(bf.to_numpy(), per[0])
+        bf.insert_genome(gens[1], K)
+        assert np.array_equal(bf.to_numpy(), per[0] | per[1])
+        lvl.from_numpy(np.full(nbytes, 0x55, dtype=np.uint8))
+        for n in (1, 2, 3):
+            bf.build_common(lvl if n > 1 else None, gens[:n], K)
+            want = per[0].copy()
+            for x in per[1:n]:
+                want &= x
+            assert np.array_equal(bf.to_numpy(), want), n
+        assert cuda_ctx.part_inserts - n0 == 2 + 6
+        bf.close(); lvl.close()
+
+
 def test_default_plan_at_150_mbp_equals_direct_kernel_and_oracle(cuda_ctx):
-    """the plan a real genome gets (1024 x 1024 buckets, no knobs) at a filter of 5.9e9 bits: SET and AND against
-    the direct kernel on the device, and genome 0 against the C oracle on the host"""
+    """what a real genome gets (no knobs) at a filter of 5.9e9 bits (> 2^32: 23 regions of 32 MB): the pair's SET and
+    AND against the direct kernel on the device, genome 0 against the C oracle on the host; then the same with 706
+    regions and shrunk capacities, and with the three-pass variant"""
     wl = synth.Workload(2, 150_000_000, 1.0)
     gens = [wl.materialize(cuda_ctx, g) for g in range(2)]
     nbytes = device.BloomFilter.size_for(gens[0].total_bases, 0.025)
@@ -157,5 +192,10 @@ def test_default_plan_at_150_mbp_equals_direct_kernel_and_oracle(cuda_ctx):
     # C oracle (OpenMP over records; a few seconds)
     recs = _records(gens[0])
     assert np.array_equal(a, so.genome_bits(recs, K, nbytes))
+    want = d0.to_numpy()
+    for knobs in (dict(NTS_BF_REGION_SHIFT=23), dict(NTS_BF_REGION_SHIFT=23, NTS_BF_CAP_SCALE=0.7), dict(NTS_BF_IMPL=3)):
+        with env(**knobs):
+            common.build_common(lvl, gens, K)
+        assert np.array_equal(common.to_numpy(), want), knobs
     for x in (common, lvl, first, d0, d1):
         x.close()

@@ -367,3 +367,18 @@ def test_baseline_configs_at_reduced_size_equal_the_oracle(cuda_ctx, G, mbp, d):
     assert got == want
     if got != "no paths":
         assert eng.outputs["pre_merge"] == go.outputs["pre_merge"]
+
+
+@pytest.mark.parametrize("tag", ["d1.3_G3", "d12_G5"])
+def test_presets_cuda_path_equals_reference_made_fixture(cuda_ctx, tag):
+    """the d >= 1 presets of bin/ntSynt:89-99 (w_rounds 250 100 / 500 250, --indel 50000 / 100000) with 3 and 5
+    genomes: the CUDA path against block files written by the reference's own bin/ntsynt_run.py
+    (tests/golden/make_golden.py presets(); tests/preset_cases.py regenerates the seeded genomes)"""
+    import preset_cases as pc
+    p = pc.CASES[tag]["params"]
+    names = pc.names(tag)
+    packed = [fasta.pack_records(r) for r in pc.checked_genomes(tag)]
+    out, eng = pipeline.run_ntsynt(names, k=p["k"], w=p["w"], w_rounds=p["w_rounds"], indel=p["indel"], merge=p["merge"],
+                                   block_size=p["block_size"], write_files=False, ctx=cuda_ctx, packed=packed)
+    assert out == pc.expected(tag)
+    assert eng.outputs["pre_merge"] == pc.expected(tag, "pre-collinear-merge.synteny_blocks.tsv")

@@ -41,3 +41,44 @@ def test_reference_golden_blocks(demo_dir, k, names, gold):
     exp = os.path.join(demo_dir, "expected_result")
     assert go.outputs["final"] == open(os.path.join(exp, gold + ".synteny_blocks.tsv")).read()
     assert go.outputs["pre_merge"] == open(os.path.join(exp, gold + ".pre-collinear-merge.synteny_blocks.tsv")).read()
+
+
+# ---- the d >= 1 presets of bin/ntSynt:89-99 (BASELINE configs 2-5), G = 3 and G = 5
+import preset_cases as pc  # noqa: E402
+
+
+def _oracle_on_case(tag):
+    p = pc.CASES[tag]["params"]
+    genomes = list(zip(pc.names(tag), pc.checked_genomes(tag)))
+    bits = so.common_bf(genomes, p["k"], 0.025)
+    go = GraphOracle([(f"{n}.k{p['k']}.w{p['w']}.tsv", r) for n, r in genomes], p["k"], p["w"], p["w_rounds"], p["indel"],
+                     p["merge"], p["block_size"], bits)
+    go.run()
+    return go
+
+
+@pytest.mark.parametrize("tag", sorted(pc.CASES))
+def test_presets_graph_oracle_equals_reference_made_fixture(tag):
+    "oracle/graph_oracle.py against block files written by the reference's own bin/ntsynt_run.py (make_golden.presets)"
+    go = _oracle_on_case(tag)
+    assert go.outputs["final"] == pc.expected(tag)
+    assert go.outputs["pre_merge"] == pc.expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
+
+
+@pytest.mark.parametrize("tag", sorted(pc.CASES))
+def test_presets_fixture_is_what_the_reference_writes(tag, tmp_path):
+    """build container only: run the reference's own bin/ntsynt_run.py (oracle/ref_harness.py, shimmed third-party
+    modules) on the seeded genomes and compare with the committed fixture -- the fixture is reference-made, not
+    restatement-made"""
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("needs /root/reference (build container)")
+    import synth_small
+    p = pc.CASES[tag]["params"]
+    for n, recs in zip(pc.names(tag), pc.checked_genomes(tag)):
+        synth_small.write_fasta(str(tmp_path / n), recs)
+    res = ref_harness.run_reference([str(tmp_path / n) for n in pc.names(tag)], str(tmp_path / "wd"), tag, k=p["k"], w=p["w"],
+                                    w_rounds=p["w_rounds"], indel=p["indel"], merge=p["merge"], block_size=p["block_size"])
+    assert res["returncode"] == 0, res["log"][-2000:]
+    assert open(res["blocks"], encoding="utf-8").read() == pc.expected(tag)
+    assert open(res["pre_merge"], encoding="utf-8").read() == pc.expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
