@@ -267,6 +267,36 @@ int nts_graph_lookup(nts_graph* g, const uint64_t* h1, uint64_t n, uint32_t* vid
  * assemblies (weight = popcount, all assembly weights are 1: bin/ntsynt_synteny.py:32). */
 int nts_graph_edges(nts_graph* g, uint64_t* n_edges);
 int nts_graph_download_edges(nts_graph* g, uint32_t* u, uint32_t* v, uint32_t* support);
+/* ---- lean form of the graph stage: the O(V) columns stay on the device, the host asks for what it walks ---------
+ * nts_graph_gather: columns at the n vertex ids idx (what: 0 h1 -> u64[n]; 1 pos -> i64[n_asm x n]; 2 contig ->
+ * i32[n_asm x n]; 3 rank -> u32[n_asm x n]; 4 inv = vertex at rank idx -> u32[n_asm x n]); ids outside [0, V) give 0. */
+int nts_graph_gather(nts_graph* g, int what, const int64_t* idx, uint64_t n, void* out);
+/* up / down [n_asm x n] i64: pairs (j, j+1), lo[i] <= j < hi[i] (clamped to V), whose position increases / decreases
+ * in each assembly -- the orientation tallies of bin/synteny_block.py:48-65 from device prefix sums */
+int nts_graph_range_sums(nts_graph* g, const int64_t* lo, const int64_t* hi, uint64_t n, long long* up, long long* down);
+/* left / right / rank [n x n_asm] i64 of the vertices cand: neighbour on the same contig line in every assembly's
+ * filtered list or -1 (the neighbourhoods run_graph_simplification inspects, bin/ntsynt_synteny.py:548-590) */
+int nts_graph_neigh(nts_graph* g, const int64_t* cand, uint64_t n, long long* left, long long* right, long long* rk);
+/* nbr[cap x 2] i32 and conn[cap] u8 of the weight-filtered graph alone (see nts_graph_download_host_arrays) */
+int nts_graph_download_links_nbr(nts_graph* g, uint64_t cap, int32_t* nbr, uint8_t* conn);
+/* Chain extraction on the device (find_paths, subprojects/ntJoin/bin/ntjoin.py:114-136, for the (i, i+1) part of the
+ * graph): ascending (starts, ends) of the maximal runs of >= 2 base vertices joined by full-weight edges.  Call with
+ * NULL outputs for the count, then with arrays of that length.  nts_graph_set_links pushes the host's edits of pairs
+ * (i, i+1) (val 1 = edge present) back to the device's link bitmap first. */
+int nts_graph_set_links(nts_graph* g, const int64_t* idx, const uint8_t* val, uint64_t n);
+int nts_graph_runs(nts_graph* g, int64_t* starts, int64_t* ends, uint64_t* n_runs);
+/* number of pairs (i, i+1) whose |dpos| spread exceeds bp */
+int nts_graph_big_count(nts_graph* g, uint32_t bp, uint64_t* n_big);
+/* Kernel (iv-c), collinear-path extraction on the device, for the n_runs runs [starts[i], ends[i]] of base vertices
+ * joined by (i, i+1) full-weight edges whose vertices still hold their round-0 positions: find_paths
+ * (subprojects/ntJoin/bin/ntjoin.py:89-136), find_synteny_blocks + orientation (bin/ntsynt_synteny.py:66-106,
+ * bin/synteny_block.py:48-65; m_pct = -m), check_for_indels (bin/ntsynt_synteny.py:364-409; bp = --bp) and
+ * filter_synteny_blocks (:411-426; min_mx = 4).  Outputs, unordered, each with room for cap >= n_runs +
+ * nts_graph_big_count + 1 entries: surviving blocks (b_lo..b_hi traversed in direction b_dir, bit a of b_plus = '+'
+ * in assembly a), deleted vertex intervals (r_lo..r_hi), cut pairs (c, c+1); counts[3] = how many of each. */
+int nts_graph_runs_to_blocks(nts_graph* g, const int64_t* starts, const int64_t* ends, uint64_t n_runs, uint32_t bp,
+                             double m_pct, uint32_t min_mx, uint32_t* b_lo, uint32_t* b_hi, uint32_t* b_plus, int8_t* b_dir,
+                             uint32_t* r_lo, uint32_t* r_hi, uint32_t* cuts, uint64_t counts[3], uint64_t cap);
 
 /* ---- native host-side pieces of the graph stage (no device work; operate on the caller's host arrays) ------------
  * nts_host_walk_paths: find_paths (subprojects/ntJoin/bin/ntjoin.py:114-151) over the components of the
@@ -277,6 +307,12 @@ int nts_graph_download_edges(nts_graph* g, uint32_t* u, uint32_t* v, uint32_t* s
 int nts_host_walk_paths(const int32_t* nbr, int64_t V0, const int64_t* starts, const int64_t* ends, int64_t n_runs,
                         const int64_t* sv, int64_t n_sv, const int64_t* opos, int64_t* seg_lo, int64_t* seg_hi,
                         int8_t* seg_dir, int64_t* path_off, int64_t seg_cap, int64_t* n_paths, int64_t* n_segs);
+/* the same with the orienting positions given only where a path can end: opos_ids (ascending) = the sparse vertices
+ * and both ends of the runs that hold them, opos_vals their positions (the lean form keeps positions on the device) */
+int nts_host_walk_paths_sparse(const int32_t* nbr, int64_t V0, const int64_t* starts, const int64_t* ends, int64_t n_runs,
+                               const int64_t* sv, int64_t n_sv, const int64_t* opos_ids, const int64_t* opos_vals, int64_t n_opos,
+                               int64_t* seg_lo, int64_t* seg_hi, int8_t* seg_dir, int64_t* path_off, int64_t seg_cap,
+                               int64_t* n_paths, int64_t* n_segs);
 /* nts_host_simplify: run_graph_simplification on the round-0 graph (bin/ntsynt_synteny.py:548-590), candidate edges
  * visited in build_graph's edge-id order (subprojects/ntJoin/bin/ntjoin_utils.py:97-115).  cand = the n_cand vertices
  * with exactly three distinct neighbours, ascending; rank / inv = [G x V]; ctg = [G x ctg_stride].  For every edge
@@ -284,6 +320,9 @@ int nts_host_walk_paths(const int32_t* nbr, int64_t V0, const int64_t* starts, c
 int nts_host_simplify(const int64_t* cand, int64_t n_cand, const uint32_t* rank, const uint32_t* inv, const int32_t* ctg,
                       int64_t ctg_stride, int64_t V, uint32_t G, int64_t* bump_s, int64_t* bump_t, int64_t* removed,
                       int64_t out_cap, int64_t* n_out);
+/* the same from neighbourhoods extracted on the device (nts_graph_neigh): left / right / rk are [n_cand x G] */
+int nts_host_simplify_neigh(const int64_t* cand, int64_t n_cand, const int64_t* left, const int64_t* right, const int64_t* rk,
+                            uint32_t G, int64_t* bump_s, int64_t* bump_t, int64_t* removed, int64_t out_cap, int64_t* n_out);
 
 /* ---- native FASTA ingest (host code; replaces btllib::SeqReader, src/ntsynt_make_common_bf.cpp:32-36,125,143, and
  * `samtools faidx`, bin/ntsynt_run_pipeline.smk:48-53) --------------------------------------------------------------

@@ -118,6 +118,8 @@ _SIGS = {
     "nts_graph_sparse_lists": (C.c_int, [vp, C.c_uint32, u32p, u32p, u32p, u64p]),
     "nts_host_walk_paths": (C.c_int, [C.POINTER(C.c_int32), C.c_int64, i64p, i64p, C.c_int64, i64p, C.c_int64, i64p, i64p, i64p,
                                       C.POINTER(C.c_int8), i64p, C.c_int64, i64p, i64p]),
+    "nts_host_walk_paths_sparse": (C.c_int, [C.POINTER(C.c_int32), C.c_int64, i64p, i64p, C.c_int64, i64p, C.c_int64, i64p, i64p,
+                                             C.c_int64, i64p, i64p, C.POINTER(C.c_int8), i64p, C.c_int64, i64p, i64p]),
     "nts_host_simplify": (C.c_int, [i64p, C.c_int64, u32p, u32p, C.POINTER(C.c_int32), C.c_int64, C.c_int64, C.c_uint32,
                                     i64p, i64p, i64p, C.c_int64, i64p]),
     "nts_fasta_scan": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, u64p, u32p, u64p, u64p, u64p, u32p, u32p, u8p, u64p]),
@@ -126,6 +128,16 @@ _SIGS = {
     "nts_graph_lookup": (C.c_int, [vp, u64p, C.c_uint64, u32p]),
     "nts_graph_edges": (C.c_int, [vp, u64p]),
     "nts_graph_download_edges": (C.c_int, [vp, u32p, u32p, u32p]),
+    "nts_graph_gather": (C.c_int, [vp, C.c_int, i64p, C.c_uint64, vp]),
+    "nts_graph_range_sums": (C.c_int, [vp, i64p, i64p, C.c_uint64, i64p, i64p]),
+    "nts_graph_neigh": (C.c_int, [vp, i64p, C.c_uint64, i64p, i64p, i64p]),
+    "nts_graph_download_links_nbr": (C.c_int, [vp, C.c_uint64, C.POINTER(C.c_int32), u8p]),
+    "nts_graph_set_links": (C.c_int, [vp, i64p, u8p, C.c_uint64]),
+    "nts_graph_runs": (C.c_int, [vp, i64p, i64p, u64p]),
+    "nts_graph_big_count": (C.c_int, [vp, C.c_uint32, u64p]),
+    "nts_graph_runs_to_blocks": (C.c_int, [vp, i64p, i64p, C.c_uint64, C.c_uint32, C.c_double, C.c_uint32, u32p, u32p, u32p,
+                                           C.POINTER(C.c_int8), u32p, u32p, u32p, u64p, C.c_uint64]),
+    "nts_host_simplify_neigh": (C.c_int, [i64p, C.c_int64, i64p, i64p, i64p, C.c_uint32, i64p, i64p, i64p, C.c_int64, i64p]),
 }
 
 

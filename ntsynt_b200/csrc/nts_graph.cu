@@ -268,7 +268,8 @@ __global__ void extract_bit_kernel(const uint32_t* __restrict__ mask, uint64_t n
     if (i < n) out[i] = (mask[i] >> bit) & 1u;
 }
 
-static int exclusive_scan_u32(nts_ctx* ctx, const uint32_t* in, uint64_t n, uint32_t* out, uint32_t* total_host)
+static int exclusive_scan_u32(nts_ctx* ctx, const uint32_t* in, uint64_t n, uint32_t* out, uint32_t* total_host,
+                              uint32_t* total_dev = nullptr)
 {
     const uint64_t per_block = (uint64_t)SCAN_THREADS * SCAN_ITEMS;
     const uint32_t n_blocks = (uint32_t)std::max<uint64_t>(1, (n + per_block - 1) / per_block);
@@ -279,6 +280,7 @@ static int exclusive_scan_u32(nts_ctx* ctx, const uint32_t* in, uint64_t n, uint
     scan_apply_kernel<<<n_blocks, SCAN_THREADS, 0, ctx->stream>>>(in, n, sums.p, out);
     ctx->launches += 3;
     NTS_CUDA(cudaGetLastError());
+    if (total_dev) NTS_CUDA(cudaMemcpyAsync(total_dev, total.p, 4, cudaMemcpyDeviceToDevice, ctx->stream));
     NTS_CUDA(cudaMemcpyAsync(total_host, total.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     NTS_CUDA(cudaStreamSynchronize(ctx->stream));
     return NTS_OK;
@@ -312,6 +314,164 @@ __global__ void graph_sparse_lists_kernel(const uint8_t* __restrict__ link, cons
     if (i + 1 < V && spread[i] > bp) { const unsigned int k = atomicAdd(&counts[2], 1u); if (k < cap) big[k] = (uint32_t)i; }
 }
 
+
+// ---- device-side lookups for the graph stage: the host walks a few thousand places; the O(V) columns stay here
+// out[a * n + i] = (T) src[a * V + idx[i]]   (assembly-major columns; idx >= V gives `fill`)
+template <typename S, typename T>
+__global__ void gather_rows_kernel(const S* __restrict__ src, uint64_t V, uint32_t n_rows, const int64_t* __restrict__ idx,
+                                   uint64_t n, T fill, T* __restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * n_rows) return;
+    const uint32_t a = (uint32_t)(t / n);
+    const int64_t v = idx[t % n];
+    out[t] = (v >= 0 && (uint64_t)v < V) ? (T)src[(uint64_t)a * V + v] : fill;
+}
+
+// up[a * n + i] = number of pairs (j, j+1), lo[i] <= j < hi[i], whose position increases in assembly a (down: decreases)
+__global__ void range_sums_kernel(const uint32_t* __restrict__ cum_inc, const uint32_t* __restrict__ cum_dec, uint64_t V,
+                                  uint32_t n_asm, const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, uint64_t n,
+                                  long long* __restrict__ up, long long* __restrict__ down)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * n_asm) return;
+    const uint32_t a = (uint32_t)(t / n);
+    const uint64_t i = t % n;
+    const uint64_t l = (uint64_t)min((long long)lo[i], (long long)V), h = (uint64_t)min((long long)hi[i], (long long)V);
+    const uint32_t* ci = cum_inc + (uint64_t)a * (V + 1);
+    const uint32_t* cd = cum_dec + (uint64_t)a * (V + 1);
+    up[t] = (long long)ci[h] - (long long)ci[l];
+    down[t] = (long long)cd[h] - (long long)cd[l];
+}
+
+// neighbourhood of simplification candidates: left / right neighbour (same contig line) and rank in every assembly
+__global__ void cand_neigh_kernel(const uint32_t* __restrict__ v_ctg, const uint32_t* __restrict__ v_rank,
+                                  const uint32_t* __restrict__ inv, uint64_t V, uint32_t n_asm, const int64_t* __restrict__ cand,
+                                  uint64_t n, long long* __restrict__ left, long long* __restrict__ right, long long* __restrict__ rk)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * n_asm) return;
+    const uint64_t i = t / n_asm;
+    const uint32_t a = (uint32_t)(t % n_asm);
+    const uint64_t u = (uint64_t)cand[i];
+    const uint64_t r = v_rank[(uint64_t)a * V + u];
+    const uint32_t c = v_ctg[(uint64_t)a * V + u];
+    long long lf = -1, rt = -1;
+    if (r > 0) { const uint32_t x = inv[(uint64_t)a * V + r - 1]; if (v_ctg[(uint64_t)a * V + x] == c) lf = x; }
+    if (r + 1 < V) { const uint32_t x = inv[(uint64_t)a * V + r + 1]; if (v_ctg[(uint64_t)a * V + x] == c) rt = x; }
+    left[t] = lf; right[t] = rt; rk[t] = (long long)r;            // [i * n_asm + a]
+}
+
+__global__ void flag_big_kernel(const uint32_t* __restrict__ spread, uint64_t V, uint32_t bp, uint32_t* __restrict__ flag)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V) flag[i] = (i + 1 < V && spread[i] > bp) ? 1u : 0u;
+}
+
+__global__ void compact_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ off, uint64_t V, uint32_t* __restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V && flag[i]) out[off[i]] = (uint32_t)i;
+}
+
+// runs of consecutive base vertices joined by full-weight (i, i+1) edges, two or more vertices long: vertex i starts
+// one iff link[i-1] == 0 and link[i] == 1, ends one iff link[i-1] == 1 and link[i] == 0
+__global__ void run_flags_kernel(const uint8_t* __restrict__ link, uint64_t V, uint32_t* __restrict__ is_start,
+                                 uint32_t* __restrict__ is_end)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const bool prev = i > 0 && link[i - 1], cur = i + 1 < V && link[i];
+    is_start[i] = (!prev && cur) ? 1u : 0u;
+    is_end[i] = (prev && !cur) ? 1u : 0u;
+}
+
+__global__ void set_links_kernel(uint8_t* __restrict__ link, uint64_t V, const int64_t* __restrict__ idx,
+                                 const uint8_t* __restrict__ val, uint64_t n)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && idx[t] >= 0 && (uint64_t)idx[t] < V) link[idx[t]] = val[t];
+}
+
+// first index of the sorted list with value >= x
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t x)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid] < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// (iv-c) collinear-path extraction for the runs that are plain chains of (i, i+1) edges -- all but a few of them.
+// One thread per run [s, e] (e > s) of consecutive base vertices joined by full-weight edges:
+//   find_paths          the run is a path from the end with the smaller position in the orienting assembly
+//                       (subprojects/ntJoin/bin/ntjoin.py:89-102,114-136); equal positions: no path
+//   find_synteny_blocks one block (the contig cannot change along full-weight edges); per assembly '+' if every step
+//                       increases, '-' if every step decreases, else by the >= m percent rule, else the block is
+//                       dropped and its vertices deleted (bin/ntsynt_synteny.py:66-106, bin/synteny_block.py:48-65)
+//   check_for_indels    cut at every pair whose |dpos| spread exceeds --bp (bin/ntsynt_synteny.py:364-409)
+//   filter_synteny_blocks pieces with fewer than min_mx minimizers are deleted (:411-426)
+// Output (unordered appends): surviving blocks (lo, hi, dir, plus-mask), deleted vertex intervals, cut pairs.
+struct RunOut {
+    uint32_t* b_lo; uint32_t* b_hi; uint32_t* b_plus; int8_t* b_dir;     // [cap]
+    uint32_t* r_lo; uint32_t* r_hi;                                       // [cap] deleted intervals
+    uint32_t* cuts;                                                       // [cap] pairs (c, c+1) cut as indels
+    unsigned int* counts;                                                 // [3] blocks, deleted intervals, cuts
+    uint32_t cap;
+};
+
+__global__ void runs_to_blocks_kernel(const uint32_t* __restrict__ v_pos, const uint32_t* __restrict__ cum_inc,
+                                      const uint32_t* __restrict__ cum_dec, uint64_t V, uint32_t n_asm, uint32_t orient,
+                                      const uint32_t* __restrict__ big, uint32_t n_big, const int64_t* __restrict__ starts,
+                                      const int64_t* __restrict__ ends, uint64_t n_runs, double m_pct, uint32_t min_mx, RunOut o)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_runs) return;
+    const uint32_t s = (uint32_t)starts[t], e = (uint32_t)ends[t];
+    if (e <= s) return;
+    const uint32_t x = v_pos[(uint64_t)orient * V + s], y = v_pos[(uint64_t)orient * V + e];
+    if (x == y) return;                                       // no path: the vertices stay as they are
+    const int dir = x < y ? 1 : -1;
+    const uint32_t n = e - s + 1;
+    uint32_t plus = 0;
+    bool unoriented = false;
+    for (uint32_t a = 0; a < n_asm; ++a) {
+        const uint32_t* ci = cum_inc + (uint64_t)a * (V + 1);
+        const uint32_t* cd = cum_dec + (uint64_t)a * (V + 1);
+        const uint32_t up = ci[e] - ci[s], down = cd[e] - cd[s];
+        const uint32_t inc = dir > 0 ? up : down, dec = dir > 0 ? down : up;
+        if (inc == n - 1) plus |= 1u << a;
+        else if (dec == n - 1) { }
+        else {
+            const double positive = __dmul_rn(__ddiv_rn((double)inc, (double)(n - 1)), 100.0);
+            const double negative = __dsub_rn(100.0, positive);
+            if (positive >= m_pct) plus |= 1u << a;
+            else if (negative >= m_pct) { }
+            else unoriented = true;
+        }
+    }
+    auto drop = [&](uint32_t lo, uint32_t hi) {
+        const unsigned int k = atomicAdd(&o.counts[1], 1u);
+        if (k < o.cap) { o.r_lo[k] = lo; o.r_hi[k] = hi; }
+    };
+    if (unoriented) { drop(s, e); return; }
+    // pieces between the large-spread pairs c in [s, e)
+    uint32_t ib = lower_bound_u32(big, n_big, s);
+    uint32_t lo = s;
+    for (;;) {
+        const bool cut = ib < n_big && big[ib] < e;
+        const uint32_t hi = cut ? big[ib] : e;
+        if (cut) { const unsigned int k = atomicAdd(&o.counts[2], 1u); if (k < o.cap) o.cuts[k] = hi; }
+        if (hi - lo + 1 >= min_mx) {
+            const unsigned int k = atomicAdd(&o.counts[0], 1u);
+            if (k < o.cap) { o.b_lo[k] = lo; o.b_hi[k] = hi; o.b_plus[k] = plus; o.b_dir[k] = (int8_t)dir; }
+        } else {
+            drop(lo, hi);
+        }
+        if (!cut) break;
+        lo = hi + 1; ++ib;
+    }
+}
+
 }  // namespace nts
 
 using namespace nts;
@@ -334,6 +494,16 @@ struct nts_graph {
     uint32_t lists_bp = 0;
     uint64_t n_lists[3] = {0, 0, 0};
     DevBuf<uint32_t> l_breaks, l_deg3, l_big;
+    // prefix sums of the direction bits, [n_asm x (V + 1)] (built lazily, kept on the device)
+    bool cums_built = false;
+    DevBuf<uint32_t> cum_inc, cum_dec;
+    // pairs with a large |dpos| spread, ascending (built lazily, per bp, kept on the device)
+    bool big_built = false;
+    uint32_t big_bp = 0, n_big = 0;
+    DevBuf<uint32_t> d_big;
+    // runs of the last nts_graph_runs call
+    uint64_t n_runs = 0;
+    DevBuf<uint32_t> run_s, run_e;
     // edges (built lazily)
     bool edges_built = false;
     uint64_t E = 0;
@@ -604,6 +774,304 @@ int nts_graph_sparse_lists(nts_graph* g, uint32_t bp, uint32_t* breaks, uint32_t
         for (int i = 0; i < 3; ++i)
             if (dst[i] && g->n_lists[i]) std::sort(dst[i], dst[i] + g->n_lists[i]);
     }
+    return NTS_OK;
+}
+
+
+static int build_cums(nts_graph* g)
+{
+    if (g->cums_built) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    const uint64_t V = g->V;
+    const uint64_t n = (uint64_t)g->n_asm * (V + 1);
+    if (g->cum_inc.alloc(n) != cudaSuccess || g->cum_dec.alloc(n) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (cums)");
+    if (V) {
+        DevBuf<uint32_t> flags;
+        if (flags.alloc(V) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (cums)");
+        ProfScope prof(ctx, PROF_GRAPH, (double)V * g->n_asm * 2);
+        for (uint32_t a = 0; a < g->n_asm; ++a)
+            for (int which = 0; which < 2; ++which) {
+                extract_bit_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(which ? g->decmask.p : g->incmask.p, V, a, flags.p);
+                ctx->launches++;
+                uint32_t* dst = (which ? g->cum_dec.p : g->cum_inc.p) + (uint64_t)a * (V + 1);
+                uint32_t total = 0;
+                int rc = exclusive_scan_u32(ctx, flags.p, V, dst, &total, dst + V);
+                if (rc) return rc;
+            }
+    } else {
+        NTS_CUDA(cudaMemsetAsync(g->cum_inc.p, 0, n * 4, ctx->stream));
+        NTS_CUDA(cudaMemsetAsync(g->cum_dec.p, 0, n * 4, ctx->stream));
+    }
+    g->cums_built = true;
+    return NTS_OK;
+}
+
+static int build_big(nts_graph* g, uint32_t bp)
+{
+    if (g->big_built && g->big_bp == bp) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    const uint64_t V = g->V;
+    g->n_big = 0;
+    if (V) {
+        DevBuf<uint32_t> flag, off;
+        if (flag.alloc(V) != cudaSuccess || off.alloc(V) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (big)");
+        ProfScope prof(ctx, PROF_GRAPH, (double)V);
+        flag_big_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(g->spread.p, V, bp, flag.p);
+        ctx->launches++;
+        uint32_t tot = 0;
+        int rc = exclusive_scan_u32(ctx, flag.p, V, off.p, &tot);
+        if (rc) return rc;
+        if (g->d_big.alloc(std::max<uint32_t>(1, tot)) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (big)");
+        compact_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(flag.p, off.p, V, g->d_big.p);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+        g->n_big = tot;
+    } else if (g->d_big.alloc(1) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (big)");
+    g->big_built = true; g->big_bp = bp;
+    return NTS_OK;
+}
+
+/* Columns of the vertex table at the given vertex ids (what: 0 h1 -> u64[n]; 1 pos -> i64[n_asm x n]; 2 contig ->
+ * i32[n_asm x n]; 3 rank -> u32[n_asm x n]; 4 inv (vertex at rank idx) -> u32[n_asm x n]).  Ids outside [0, V) give 0. */
+int nts_graph_gather(nts_graph* g, int what, const int64_t* idx, uint64_t n, void* out)
+{
+    if (!g || (n && (!idx || !out)) || what < 0 || what > 4) return fail(NTS_ERR_ARG, "bad argument");
+    if (!n) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t V = g->V;
+    const uint32_t rows = what == 0 ? 1 : g->n_asm;
+    const size_t esz = what == 0 || what == 1 ? 8 : 4;
+    DevBuf<int64_t> d_idx;
+    DevBuf<uint8_t> d_out;
+    if (d_idx.alloc(n) != cudaSuccess || d_out.alloc(n * rows * esz) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (gather)");
+    NTS_CUDA(copy_h2d(ctx, d_idx.p, idx, n * 8));
+    const unsigned blocks = (unsigned)((n * rows + 255) / 256);
+    {
+        ProfScope prof(ctx, PROF_GRAPH, (double)n * rows);
+        if (what == 0) gather_rows_kernel<uint64_t, uint64_t><<<blocks, 256, 0, ctx->stream>>>(g->v_h1.p, V, 1, d_idx.p, n, 0ull, reinterpret_cast<uint64_t*>(d_out.p));
+        else if (what == 1) gather_rows_kernel<uint32_t, long long><<<blocks, 256, 0, ctx->stream>>>(g->v_pos.p, V, rows, d_idx.p, n, 0ll, reinterpret_cast<long long*>(d_out.p));
+        else if (what == 2) gather_rows_kernel<uint32_t, int32_t><<<blocks, 256, 0, ctx->stream>>>(g->v_ctg.p, V, rows, d_idx.p, n, 0, reinterpret_cast<int32_t*>(d_out.p));
+        else if (what == 3) gather_rows_kernel<uint32_t, uint32_t><<<blocks, 256, 0, ctx->stream>>>(g->v_rank.p, V, rows, d_idx.p, n, 0u, reinterpret_cast<uint32_t*>(d_out.p));
+        else gather_rows_kernel<uint32_t, uint32_t><<<blocks, 256, 0, ctx->stream>>>(g->inv.p, V, rows, d_idx.p, n, 0u, reinterpret_cast<uint32_t*>(d_out.p));
+        ctx->launches++;
+    }
+    NTS_CUDA(cudaGetLastError());
+    NTS_CUDA(copy_d2h(ctx, out, d_out.p, n * rows * esz));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+/* up / down [n_asm x n] (i64): pairs (j, j+1) with lo[i] <= j < hi[i] whose position increases / decreases in each
+ * assembly (lo, hi are clamped to V).  The prefix sums behind it are built once and stay on the device. */
+int nts_graph_range_sums(nts_graph* g, const int64_t* lo, const int64_t* hi, uint64_t n, long long* up, long long* down)
+{
+    if (!g || (n && (!lo || !hi || !up || !down))) return fail(NTS_ERR_ARG, "null argument");
+    if (!n) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    int rc = build_cums(g);
+    if (rc) return rc;
+    DevBuf<int64_t> d_lo, d_hi;
+    DevBuf<long long> d_up, d_down;
+    const uint64_t nn = n * g->n_asm;
+    if (d_lo.alloc(n) != cudaSuccess || d_hi.alloc(n) != cudaSuccess || d_up.alloc(nn) != cudaSuccess || d_down.alloc(nn) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (range sums)");
+    NTS_CUDA(copy_h2d(ctx, d_lo.p, lo, n * 8));
+    NTS_CUDA(copy_h2d(ctx, d_hi.p, hi, n * 8));
+    {
+        ProfScope prof(ctx, PROF_GRAPH, (double)nn);
+        range_sums_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, ctx->stream>>>(g->cum_inc.p, g->cum_dec.p, g->V, g->n_asm, d_lo.p, d_hi.p, n, d_up.p, d_down.p);
+        ctx->launches++;
+    }
+    NTS_CUDA(cudaGetLastError());
+    NTS_CUDA(copy_d2h(ctx, up, d_up.p, nn * 8));
+    NTS_CUDA(copy_d2h(ctx, down, d_down.p, nn * 8));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+/* left / right / rank [n x n_asm] (i64) of the simplification candidates: neighbour on the same contig line in every
+ * assembly's filtered list, or -1 (what nts_host_simplify_neigh consumes) */
+int nts_graph_neigh(nts_graph* g, const int64_t* cand, uint64_t n, long long* left, long long* right, long long* rk)
+{
+    if (!g || (n && (!cand || !left || !right || !rk))) return fail(NTS_ERR_ARG, "null argument");
+    if (!n) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t nn = n * g->n_asm;
+    DevBuf<int64_t> d_c;
+    DevBuf<long long> d_l, d_r, d_k;
+    if (d_c.alloc(n) != cudaSuccess || d_l.alloc(nn) != cudaSuccess || d_r.alloc(nn) != cudaSuccess || d_k.alloc(nn) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (neighbourhoods)");
+    NTS_CUDA(copy_h2d(ctx, d_c.p, cand, n * 8));
+    {
+        ProfScope prof(ctx, PROF_GRAPH, (double)nn);
+        cand_neigh_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, ctx->stream>>>(g->v_ctg.p, g->v_rank.p, g->inv.p, g->V, g->n_asm, d_c.p, n, d_l.p, d_r.p, d_k.p);
+        ctx->launches++;
+    }
+    NTS_CUDA(cudaGetLastError());
+    NTS_CUDA(copy_d2h(ctx, left, d_l.p, nn * 8));
+    NTS_CUDA(copy_d2h(ctx, right, d_r.p, nn * 8));
+    NTS_CUDA(copy_d2h(ctx, rk, d_k.p, nn * 8));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+/* (iv-c) on the device: paths, blocks, indel splits and the min_mx filter for runs [starts[i], ends[i]] of base
+ * vertices joined by (i, i+1) full-weight edges (see runs_to_blocks_kernel).  The caller passes only runs whose
+ * vertices still hold their round-0 positions.  Outputs are unordered; counts[3] = blocks, deleted intervals, cuts.
+ * Call with the output pointers NULL to run the kernel and get the counts, then again to fetch (same arguments). */
+int nts_graph_runs_to_blocks(nts_graph* g, const int64_t* starts, const int64_t* ends, uint64_t n_runs, uint32_t bp,
+                             double m_pct, uint32_t min_mx, uint32_t* b_lo, uint32_t* b_hi, uint32_t* b_plus, int8_t* b_dir,
+                             uint32_t* r_lo, uint32_t* r_hi, uint32_t* cuts, uint64_t counts[3], uint64_t cap)
+{
+    if (!g || !counts || (n_runs && (!starts || !ends))) return fail(NTS_ERR_ARG, "null argument");
+    counts[0] = counts[1] = counts[2] = 0;
+    if (!n_runs) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    int rc = build_cums(g);
+    if (rc || (rc = build_big(g, bp))) return rc;
+    // every run gives at most (cuts inside + 1) pieces; cuts <= n_big
+    const uint64_t need = n_runs + g->n_big + 1;
+    if (cap < need) return fail(NTS_ERR_ARG, "output capacity must be at least n_runs + nts_graph_big_count + 1");
+    DevBuf<int64_t> d_s, d_e;
+    DevBuf<uint32_t> d_u32;
+    DevBuf<int8_t> d_dir;
+    DevBuf<unsigned int> d_cnt;
+    if (d_s.alloc(n_runs) != cudaSuccess || d_e.alloc(n_runs) != cudaSuccess || d_u32.alloc(need * 6) != cudaSuccess ||
+        d_dir.alloc(need) != cudaSuccess || d_cnt.alloc(3) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (runs)");
+    NTS_CUDA(copy_h2d(ctx, d_s.p, starts, n_runs * 8));
+    NTS_CUDA(copy_h2d(ctx, d_e.p, ends, n_runs * 8));
+    NTS_CUDA(cudaMemsetAsync(d_cnt.p, 0, 12, ctx->stream));
+    RunOut o;
+    o.b_lo = d_u32.p; o.b_hi = d_u32.p + need; o.b_plus = d_u32.p + 2 * need; o.r_lo = d_u32.p + 3 * need;
+    o.r_hi = d_u32.p + 4 * need; o.cuts = d_u32.p + 5 * need; o.b_dir = d_dir.p; o.counts = d_cnt.p; o.cap = (uint32_t)need;
+    {
+        ProfScope prof(ctx, PROF_GRAPH, (double)n_runs);
+        runs_to_blocks_kernel<<<(unsigned)((n_runs + 127) / 128), 128, 0, ctx->stream>>>(
+            g->v_pos.p, g->cum_inc.p, g->cum_dec.p, g->V, g->n_asm, g->order_asm, g->d_big.p, g->n_big, d_s.p, d_e.p, n_runs,
+            m_pct, min_mx, o);
+        ctx->launches++;
+    }
+    NTS_CUDA(cudaGetLastError());
+    unsigned int h[3] = {0, 0, 0};
+    NTS_CUDA(cudaMemcpyAsync(h, d_cnt.p, 12, cudaMemcpyDeviceToHost, ctx->stream));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) counts[i] = h[i];
+    if (h[0] > need || h[1] > need || h[2] > need) return fail(NTS_ERR_STATE, "internal error: run output overflow");
+    if (h[0]) {
+        NTS_CUDA(copy_d2h(ctx, b_lo, o.b_lo, h[0] * 4)); NTS_CUDA(copy_d2h(ctx, b_hi, o.b_hi, h[0] * 4));
+        NTS_CUDA(copy_d2h(ctx, b_plus, o.b_plus, h[0] * 4)); NTS_CUDA(copy_d2h(ctx, b_dir, o.b_dir, h[0]));
+    }
+    if (h[1]) { NTS_CUDA(copy_d2h(ctx, r_lo, o.r_lo, h[1] * 4)); NTS_CUDA(copy_d2h(ctx, r_hi, o.r_hi, h[1] * 4)); }
+    if (h[2]) NTS_CUDA(copy_d2h(ctx, cuts, o.cuts, h[2] * 4));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+
+/* The host edits the weight-filtered graph (simplification, indel cuts, deleted blocks, refinement splices); the pairs
+ * (i, i+1) it changed are pushed back so that the device's link bitmap stays the truth for nts_graph_runs. */
+int nts_graph_set_links(nts_graph* g, const int64_t* idx, const uint8_t* val, uint64_t n)
+{
+    if (!g || (n && (!idx || !val))) return fail(NTS_ERR_ARG, "null argument");
+    if (!n || !g->V) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<int64_t> d_i;
+    DevBuf<uint8_t> d_v;
+    if (d_i.alloc(n) != cudaSuccess || d_v.alloc(n) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (links)");
+    NTS_CUDA(copy_h2d(ctx, d_i.p, idx, n * 8));
+    NTS_CUDA(copy_h2d(ctx, d_v.p, val, n));
+    set_links_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(g->link.p, g->V, d_i.p, d_v.p, n);
+    ctx->launches++;
+    NTS_CUDA(cudaGetLastError());
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));      // the host buffers may go away
+    return NTS_OK;
+}
+
+/* Chain extraction (kernel iv-c, find_paths of subprojects/ntJoin/bin/ntjoin.py:114-136 for the (i, i+1) part of the
+ * graph): the maximal runs of two or more base vertices joined by full-weight edges, as ascending (starts, ends).
+ * Call with NULL outputs for the count, then with arrays of that length. */
+int nts_graph_runs(nts_graph* g, int64_t* starts, int64_t* ends, uint64_t* n_runs)
+{
+    if (!g || !n_runs) return fail(NTS_ERR_ARG, "null argument");
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t V = g->V;
+    if (!starts || !ends) {
+        g->n_runs = 0;
+        if (V) {
+            DevBuf<uint32_t> fs, fe, os, oe;
+            if (fs.alloc(V) != cudaSuccess || fe.alloc(V) != cudaSuccess || os.alloc(V) != cudaSuccess || oe.alloc(V) != cudaSuccess)
+                return fail(NTS_ERR_NOMEM, "device allocation failed (runs)");
+            ProfScope prof(ctx, PROF_GRAPH, (double)V);
+            run_flags_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(g->link.p, V, fs.p, fe.p);
+            ctx->launches++;
+            uint32_t ns = 0, ne = 0;
+            int rc = exclusive_scan_u32(ctx, fs.p, V, os.p, &ns);
+            if (rc || (rc = exclusive_scan_u32(ctx, fe.p, V, oe.p, &ne))) return rc;
+            if (ns != ne) return fail(NTS_ERR_STATE, "internal error: run starts and ends disagree");
+            if (g->run_s.alloc(std::max<uint32_t>(1, ns)) != cudaSuccess || g->run_e.alloc(std::max<uint32_t>(1, ns)) != cudaSuccess)
+                return fail(NTS_ERR_NOMEM, "device allocation failed (runs)");
+            compact_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(fs.p, os.p, V, g->run_s.p);
+            compact_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(fe.p, oe.p, V, g->run_e.p);
+            ctx->launches += 2;
+            NTS_CUDA(cudaGetLastError());
+            NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+            g->n_runs = ns;
+        }
+        *n_runs = g->n_runs;
+        return NTS_OK;
+    }
+    *n_runs = g->n_runs;
+    if (g->n_runs) {
+        std::vector<uint32_t> hs(g->n_runs), he(g->n_runs);
+        NTS_CUDA(copy_d2h(ctx, hs.data(), g->run_s.p, g->n_runs * 4));
+        NTS_CUDA(copy_d2h(ctx, he.data(), g->run_e.p, g->n_runs * 4));
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (uint64_t i = 0; i < g->n_runs; ++i) { starts[i] = hs[i]; ends[i] = he[i]; }
+    }
+    return NTS_OK;
+}
+
+/* number of pairs whose |dpos| spread exceeds bp (sizes the outputs of nts_graph_runs_to_blocks) */
+int nts_graph_big_count(nts_graph* g, uint32_t bp, uint64_t* n_big)
+{
+    if (!g || !n_big) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(g->ctx->device));
+    int rc = build_big(g, bp);
+    if (rc) return rc;
+    *n_big = g->n_big;
+    return NTS_OK;
+}
+
+/* conn[cap] u8 (conn[i] = 1 iff edge (i, i+1) has full weight) and nbr[cap x 2] i32 alone: the lean form of
+ * nts_graph_download_host_arrays (positions, contigs and hashes stay on the device: nts_graph_gather) */
+int nts_graph_download_links_nbr(nts_graph* g, uint64_t cap, int32_t* nbr, uint8_t* conn)
+{
+    if (!g || !nbr || !conn) return fail(NTS_ERR_ARG, "null argument");
+    const uint64_t V = g->V;
+    if (cap < V) return fail(NTS_ERR_ARG, "cap is smaller than the number of vertices");
+    if (!V) return NTS_OK;
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<long long> d_pos;
+    DevBuf<int2> d_nbr;
+    if (d_pos.alloc(1) != cudaSuccess || d_nbr.alloc(V) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (export)");
+    {
+        ProfScope prof(ctx, PROF_GRAPH, (double)V);
+        graph_export_kernel<<<(unsigned)((V + 255) / 256), 256, 0, ctx->stream>>>(g->v_pos.p, g->link.p, V, 0, d_pos.p, d_nbr.p);
+        ctx->launches++;
+    }
+    NTS_CUDA(cudaGetLastError());
+    NTS_CUDA(copy_d2h(ctx, nbr, d_nbr.p, V * 8));
+    NTS_CUDA(copy_d2h(ctx, conn, g->link.p, V));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
     return NTS_OK;
 }
 

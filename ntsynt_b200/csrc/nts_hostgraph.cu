@@ -9,6 +9,7 @@
 //                         (bin/ntsynt_synteny.py:548-590; SyntenyEngine._simplify_round0)
 // Both reproduce the reference's visiting ORDER, which decides bit-exactness.
 #include <algorithm>
+#include <climits>
 #include <cstdint>
 #include <unordered_set>
 #include <vector>
@@ -35,16 +36,24 @@ extern "C" {
  * position of every vertex in the orienting assembly.  A component that is a simple path with two distinct ends
  * becomes one path, listed from the end with the smaller position, as segments (lo, hi, dir) over runs.
  * Output: seg_lo/seg_hi/seg_dir [<= 2*n_sv + 2], path_off [<= n_paths + 1]; returns through n_paths / n_segs. */
-int nts_host_walk_paths(const int32_t* nbr, int64_t V0, const int64_t* starts, const int64_t* ends, int64_t n_runs,
-                        const int64_t* sv, int64_t n_sv, const int64_t* opos, int64_t* seg_lo, int64_t* seg_hi,
-                        int8_t* seg_dir, int64_t* path_off, int64_t seg_cap, int64_t* n_paths, int64_t* n_segs)
+static int walk_paths_core(const int32_t* nbr, int64_t V0, const int64_t* starts, const int64_t* ends, int64_t n_runs,
+                           const int64_t* sv, int64_t n_sv, const int64_t* opos, const int64_t* opos_ids, int64_t n_opos,
+                           int64_t* seg_lo, int64_t* seg_hi, int8_t* seg_dir, int64_t* path_off, int64_t seg_cap,
+                           int64_t* n_paths, int64_t* n_segs)
 {
     if (!nbr || !sv || !opos || !seg_lo || !seg_hi || !seg_dir || !path_off || !n_paths || !n_segs)
         return fail(NTS_ERR_ARG, "null argument");
+    // position in the orienting assembly: dense (indexed by vertex id) or sparse (sorted ids + values)
+    auto opos_at = [&](int64_t v) -> int64_t {
+        if (!opos_ids) return opos[v];
+        const int64_t* p = std::lower_bound(opos_ids, opos_ids + n_opos, v);
+        return (p != opos_ids + n_opos && *p == v) ? opos[p - opos_ids] : INT64_MIN;
+    };
     const Runs runs{starts, ends, n_runs, V0};
     auto bounds = [&](int64_t v, int64_t* a, int64_t* b) {
         if (v >= V0) { *a = *b = v; return; }
         const int64_t r = runs.find(v);
+        if (r < 0 || ends[r] < v) { *a = *b = v; return; }      // (the run list may leave out single-vertex runs)
         *a = starts[r]; *b = ends[r];
     };
     // ends of the runs that hold a sparse vertex, ascending and distinct
@@ -94,7 +103,8 @@ int nts_host_walk_paths(const int32_t* nbr, int64_t V0, const int64_t* starts, c
         const int64_t first = dir.front() > 0 ? lo.front() : hi.front();
         const int64_t lastv = dir.back() > 0 ? hi.back() : lo.back();
         if (first == lastv) continue;
-        const int64_t pa = opos[first], pb = opos[lastv];
+        const int64_t pa = opos_at(first), pb = opos_at(lastv);
+        if (pa == INT64_MIN || pb == INT64_MIN) return fail(NTS_ERR_ARG, "position of a path end was not supplied");
         if (pa == pb) continue;
         const size_t n = lo.size();
         if (ns + (int64_t)n > seg_cap) return fail(NTS_ERR_OVERFLOW, "segment buffer too small");
@@ -109,31 +119,36 @@ int nts_host_walk_paths(const int32_t* nbr, int64_t V0, const int64_t* starts, c
     return NTS_OK;
 }
 
+int nts_host_walk_paths(const int32_t* nbr, int64_t V0, const int64_t* starts, const int64_t* ends, int64_t n_runs,
+                        const int64_t* sv, int64_t n_sv, const int64_t* opos, int64_t* seg_lo, int64_t* seg_hi,
+                        int8_t* seg_dir, int64_t* path_off, int64_t seg_cap, int64_t* n_paths, int64_t* n_segs)
+{
+    return walk_paths_core(nbr, V0, starts, ends, n_runs, sv, n_sv, opos, nullptr, 0, seg_lo, seg_hi, seg_dir, path_off, seg_cap,
+                           n_paths, n_segs);
+}
+
+/* the same with the orienting positions given only where a path can end: opos_ids (ascending) = the sparse vertices and
+ * the ends of the runs that hold them, opos_vals their positions */
+int nts_host_walk_paths_sparse(const int32_t* nbr, int64_t V0, const int64_t* starts, const int64_t* ends, int64_t n_runs,
+                               const int64_t* sv, int64_t n_sv, const int64_t* opos_ids, const int64_t* opos_vals, int64_t n_opos,
+                               int64_t* seg_lo, int64_t* seg_hi, int8_t* seg_dir, int64_t* path_off, int64_t seg_cap,
+                               int64_t* n_paths, int64_t* n_segs)
+{
+    if (!opos_ids) return fail(NTS_ERR_ARG, "null argument");
+    return walk_paths_core(nbr, V0, starts, ends, n_runs, sv, n_sv, opos_vals, opos_ids, n_opos, seg_lo, seg_hi, seg_dir, path_off,
+                           seg_cap, n_paths, n_segs);
+}
+
 /* run_graph_simplification on the round-0 graph (bin/ntsynt_synteny.py:566-590).  cand = the vertices with exactly
  * three distinct neighbours, ascending; rank / inv = [G x V] rank of every vertex in every assembly's filtered list
  * and its inverse; ctg = [G x ctg_stride] contig of every vertex.  Candidate edges (both ends candidates) are
  * visited in build_graph's edge-id order (ntjoin_utils.py:97-115); an edge whose two ends each have exactly one
  * incident full-weight edge and which closes exactly one triangle removes the triangle's third vertex and becomes
  * full weight itself (visible to the later edges).  Output (same length, <= n_cand * 4): bump_s < bump_t, removed. */
-int nts_host_simplify(const int64_t* cand, int64_t n_cand, const uint32_t* rank, const uint32_t* inv, const int32_t* ctg,
-                      int64_t ctg_stride, int64_t V, uint32_t G, int64_t* bump_s, int64_t* bump_t, int64_t* removed,
-                      int64_t out_cap, int64_t* n_out)
+static int simplify_core(const int64_t* cand, int64_t n_cand, const int64_t* left, const int64_t* right, const int64_t* rk,
+                         uint32_t G, int64_t* bump_s, int64_t* bump_t, int64_t* removed, int64_t out_cap, int64_t* n_out)
 {
-    if (!cand || !rank || !inv || !ctg || !bump_s || !bump_t || !removed || !n_out) return fail(NTS_ERR_ARG, "null argument");
-    if (G < 1 || G > 32) return fail(NTS_ERR_ARG, "between 1 and 32 assemblies are supported");
     const size_t n = (size_t)n_cand;
-    // neighbourhoods: left / right neighbour of every candidate in every assembly (or -1)
-    std::vector<int64_t> left(n * G), right(n * G), rk(n * G);
-    for (size_t i = 0; i < n; ++i) {
-        const int64_t u = cand[i];
-        for (uint32_t a = 0; a < G; ++a) {
-            const int64_t r = rank[(size_t)a * V + u];
-            int64_t lf = -1, rt = -1;
-            if (r > 0) { const int64_t x = inv[(size_t)a * V + r - 1]; if (ctg[a * ctg_stride + x] == ctg[a * ctg_stride + u]) lf = x; }
-            if (r + 1 < V) { const int64_t x = inv[(size_t)a * V + r + 1]; if (ctg[a * ctg_stride + x] == ctg[a * ctg_stride + u]) rt = x; }
-            left[i * G + a] = lf; right[i * G + a] = rt; rk[i * G + a] = r;
-        }
-    }
     auto pos_of = [&](int64_t v) -> int64_t {
         const int64_t* p = std::lower_bound(cand, cand + n_cand, v);
         return (p != cand + n_cand && *p == v) ? (int64_t)(p - cand) : -1;
@@ -209,6 +224,38 @@ int nts_host_simplify(const int64_t* cand, int64_t n_cand, const uint32_t* rank,
     }
     *n_out = no;
     return NTS_OK;
+}
+
+int nts_host_simplify(const int64_t* cand, int64_t n_cand, const uint32_t* rank, const uint32_t* inv, const int32_t* ctg,
+                      int64_t ctg_stride, int64_t V, uint32_t G, int64_t* bump_s, int64_t* bump_t, int64_t* removed,
+                      int64_t out_cap, int64_t* n_out)
+{
+    if (!cand || !rank || !inv || !ctg || !bump_s || !bump_t || !removed || !n_out) return fail(NTS_ERR_ARG, "null argument");
+    if (G < 1 || G > 32) return fail(NTS_ERR_ARG, "between 1 and 32 assemblies are supported");
+    const size_t n = (size_t)n_cand;
+    // neighbourhoods: left / right neighbour of every candidate in every assembly (or -1)
+    std::vector<int64_t> left(n * G), right(n * G), rk(n * G);
+    for (size_t i = 0; i < n; ++i) {
+        const int64_t u = cand[i];
+        for (uint32_t a = 0; a < G; ++a) {
+            const int64_t r = rank[(size_t)a * V + u];
+            int64_t lf = -1, rt = -1;
+            if (r > 0) { const int64_t x = inv[(size_t)a * V + r - 1]; if (ctg[a * ctg_stride + x] == ctg[a * ctg_stride + u]) lf = x; }
+            if (r + 1 < V) { const int64_t x = inv[(size_t)a * V + r + 1]; if (ctg[a * ctg_stride + x] == ctg[a * ctg_stride + u]) rt = x; }
+            left[i * G + a] = lf; right[i * G + a] = rt; rk[i * G + a] = r;
+        }
+    }
+    return simplify_core(cand, n_cand, left.data(), right.data(), rk.data(), G, bump_s, bump_t, removed, out_cap, n_out);
+}
+
+/* the same with the candidates' neighbourhoods already extracted on the device (nts_graph_neigh): left / right / rk are
+ * [n_cand x G] */
+int nts_host_simplify_neigh(const int64_t* cand, int64_t n_cand, const int64_t* left, const int64_t* right, const int64_t* rk,
+                            uint32_t G, int64_t* bump_s, int64_t* bump_t, int64_t* removed, int64_t out_cap, int64_t* n_out)
+{
+    if (!cand || !left || !right || !rk || !bump_s || !bump_t || !removed || !n_out) return fail(NTS_ERR_ARG, "null argument");
+    if (G < 1 || G > 32) return fail(NTS_ERR_ARG, "between 1 and 32 assemblies are supported");
+    return simplify_core(cand, n_cand, left, right, rk, G, bump_s, bump_t, removed, out_cap, n_out);
 }
 
 }  // extern "C"

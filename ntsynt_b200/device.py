@@ -6,6 +6,7 @@ Mirrors the reference's operators for this path:
   Context.sketch             <- indexlr --long --pos [-s bf] [-r bf] bin/ntsynt_run_pipeline.smk:83-85
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -373,14 +374,19 @@ class MinimizerGraph:
                                                      ptr(CTG, C.c_int32), ptr(nbr, C.c_int32), ptr(conn, C.c_uint8)))
         return H, POS, CTG, nbr, conn
 
-    def sparse_lists(self, bp):
-        "(breaks, deg3, big) sorted int64 arrays -- see nts_graph_sparse_lists in the header"
+    def sparse_lists(self, bp, breaks=True):
+        """(breaks, deg3, big) sorted int64 arrays -- see nts_graph_sparse_lists in the header; breaks=False leaves the
+        (long) list of pairs without a link on the device (the lean form gets its runs from nts_graph_runs)"""
         cnt = (C.c_uint64 * 3)()
         bp = min(int(bp), 0xFFFFFFFF)
         check(lib.nts_graph_sparse_lists(self._h, bp, None, None, None, cnt))
+        if not breaks:
+            cnt[0] = 0
         arrs = [np.empty(max(int(c), 1), dtype=np.uint32) for c in cnt]
-        check(lib.nts_graph_sparse_lists(self._h, bp, ptr(arrs[0], C.c_uint32), ptr(arrs[1], C.c_uint32),
+        check(lib.nts_graph_sparse_lists(self._h, bp, ptr(arrs[0], C.c_uint32) if breaks else None, ptr(arrs[1], C.c_uint32),
                                          ptr(arrs[2], C.c_uint32), cnt))
+        if not breaks:
+            cnt[0] = 0
         return tuple(a[:int(c)].astype(np.int64) for a, c in zip(arrs, cnt))
 
     def rank_inv(self):
@@ -405,11 +411,106 @@ class MinimizerGraph:
             check(lib.nts_graph_download_links(self._h, None, ptr(inc, C.c_uint32), ptr(dec, C.c_uint32), ptr(spread, C.c_uint32)))
         return inc[:V], dec[:V], spread[:V]
 
-    def join_result(self, full=False):
-        """everything SyntenyEngine needs from the join, as a dict.  Default: lean form -- the O(V) columns arrive
-        host-ready through `host(cap)`, the sparse views through `sparse(bp)`, the pair masks lazily; full=True
-        also returns the raw columns (tests, .mx.dot writer)."""
+
+    # ---- lean form: the O(V) columns stay on the device, the host asks for what it walks
+    _GATHER = {"h1": (0, np.uint64, False), "pos": (1, np.int64, True), "ctg": (2, np.int32, True),
+               "rank": (3, np.uint32, True), "inv": (4, np.uint32, True)}
+
+    def gather(self, what, ids):
+        "column `what` at vertex ids: h1 -> u64[n]; pos / ctg / rank / inv -> [G, n]"
+        code, dt, per_asm = self._GATHER[what]
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        n = len(ids)
+        out = np.zeros((self.n_asm, n) if per_asm else (n,), dtype=dt)
+        if n:
+            check(lib.nts_graph_gather(self._h, code, ptr(ids, C.c_int64), n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def range_sums(self, lo, hi):
+        "up, down i64 [G, n]: increasing / decreasing pairs (j, j+1), lo <= j < hi, per assembly (device prefix sums)"
+        lo = np.ascontiguousarray(lo, dtype=np.int64)
+        hi = np.ascontiguousarray(hi, dtype=np.int64)
+        n = len(lo)
+        up = np.zeros((self.n_asm, n), dtype=np.int64)
+        down = np.zeros((self.n_asm, n), dtype=np.int64)
+        if n:
+            check(lib.nts_graph_range_sums(self._h, ptr(lo, C.c_int64), ptr(hi, C.c_int64), n, ptr(up, C.c_int64),
+                                           ptr(down, C.c_int64)))
+        return up, down
+
+    def neigh(self, cand):
+        "left, right, rank i64 [n, G] of the candidates (neighbour on the same contig line per assembly, or -1)"
+        cand = np.ascontiguousarray(cand, dtype=np.int64)
+        n = len(cand)
+        out = [np.zeros((n, self.n_asm), dtype=np.int64) for _ in range(3)]
+        if n:
+            check(lib.nts_graph_neigh(self._h, ptr(cand, C.c_int64), n, *[ptr(x, C.c_int64) for x in out]))
+        return tuple(out)
+
+    def links_nbr(self, cap):
+        "nbr[cap, 2] i32, conn[cap] u8 of the weight-filtered graph (pinned, room for later vertices)"
         V = len(self)
+        cap = max(int(cap), V, 1)
+        nbr = PinnedPool.get("nbr", (cap, 2), np.int32)
+        conn = PinnedPool.get("conn", (cap,), np.uint8)
+        if V:
+            check(lib.nts_graph_download_links_nbr(self._h, cap, ptr(nbr, C.c_int32), ptr(conn, C.c_uint8)))
+        return nbr, conn
+
+    def set_links(self, idx, val):
+        "push the host's edits of pairs (i, i+1) back to the device link bitmap"
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        val = np.ascontiguousarray(val, dtype=np.uint8)
+        if len(idx):
+            check(lib.nts_graph_set_links(self._h, ptr(idx, C.c_int64), ptr(val, C.c_uint8), len(idx)))
+
+    def runs(self):
+        "(starts, ends) i64, ascending: maximal runs of >= 2 base vertices joined by full-weight edges (device)"
+        n = C.c_uint64()
+        check(lib.nts_graph_runs(self._h, None, None, C.byref(n)))
+        st = np.zeros(max(n.value, 1), dtype=np.int64)
+        en = np.zeros(max(n.value, 1), dtype=np.int64)
+        if n.value:
+            check(lib.nts_graph_runs(self._h, ptr(st, C.c_int64), ptr(en, C.c_int64), C.byref(n)))
+        return st[:n.value], en[:n.value]
+
+    def runs_to_blocks(self, starts, ends, bp, m_pct, min_mx):
+        """paths, blocks, indel cuts and the >= min_mx filter for plain (i, i+1) runs on the device (kernel iv-c);
+        dict of b_lo, b_hi, b_plus, b_dir (surviving blocks), r_lo, r_hi (deleted intervals), cuts"""
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        ends = np.ascontiguousarray(ends, dtype=np.int64)
+        n = len(starts)
+        z32 = np.zeros(0, dtype=np.uint32)
+        if not n:
+            return dict(b_lo=z32, b_hi=z32, b_plus=z32, b_dir=np.zeros(0, dtype=np.int8), r_lo=z32, r_hi=z32, cuts=z32)
+        bp = min(int(bp), 0xFFFFFFFF)
+        nb = C.c_uint64()
+        check(lib.nts_graph_big_count(self._h, bp, C.byref(nb)))
+        cap = n + nb.value + 1
+        a = [np.zeros(cap, dtype=np.uint32) for _ in range(6)]
+        d = np.zeros(cap, dtype=np.int8)
+        cnt = (C.c_uint64 * 3)()
+        check(lib.nts_graph_runs_to_blocks(self._h, ptr(starts, C.c_int64), ptr(ends, C.c_int64), n, bp, float(m_pct),
+                                           int(min_mx), ptr(a[0], C.c_uint32), ptr(a[1], C.c_uint32), ptr(a[2], C.c_uint32),
+                                           d.ctypes.data_as(C.POINTER(C.c_int8)), ptr(a[3], C.c_uint32), ptr(a[4], C.c_uint32),
+                                           ptr(a[5], C.c_uint32), cnt, cap))
+        nb_, nr, nc = (int(x) for x in cnt)
+        return dict(b_lo=a[0][:nb_], b_hi=a[1][:nb_], b_plus=a[2][:nb_], b_dir=d[:nb_], r_lo=a[3][:nr], r_hi=a[4][:nr],
+                    cuts=a[5][:nc])
+
+    def join_result(self, full=False, lean=None):
+        """everything SyntenyEngine needs from the join, as a dict.  Default: device-resident form -- positions,
+        contigs, hashes, ranks and the direction prefix sums stay in HBM and are read through gather / range_sums /
+        neigh / runs / runs_to_blocks; only the weight-filtered graph (links_nbr) and three sparse lists come to the
+        host.  lean="host" gives the round-1 form (host-ready O(V) columns); full=True also returns the raw columns
+        (tests, .mx.dot writer)."""
+        V = len(self)
+        if lean is None:
+            lean = os.environ.get("NTS_GRAPH_FORM", "device")
+        if lean != "host" and not full:
+            return dict(V=V, gather=self.gather, range_sums=self.range_sums, neigh=self.neigh, links_nbr=self.links_nbr,
+                        set_links=self.set_links, runs=self.runs, runs_to_blocks=self.runs_to_blocks,
+                        sparse=lambda bp: self.sparse_lists(bp, breaks=False))
         RANK, INV = self.rank_inv()
         CI, CD = self.cums()
         res = dict(V=V, RANK=RANK, INV=INV, CI=CI, CD=CD, host=self.host_arrays, sparse=self.sparse_lists,

@@ -96,6 +96,134 @@ class IntervalIndex:
         return res
 
 
+class _LazyRow:
+    "one assembly's row of a LazyMatrix (read-only view)"
+
+    def __init__(self, mat, a):
+        self.mat, self.a = mat, a
+
+    def __getitem__(self, idx):
+        return self.mat[self.a, idx]
+
+
+class LazyMatrix:
+    """A [G, V] column of the device vertex table (positions or contigs), read where the host looks through
+    `fetch(ids) -> [G, n]` (nts_graph_gather).  What later rounds write lives on the host: vertices added after
+    round 0 in dense rows indexed by id - V0, the few round-0 entries that update_list_mx_info overwrites in a
+    per-assembly dict (a byte mask over the ids says where to look).  Supports the index forms the engine uses:
+    M[:, ids], M[a, ids], M[a] (a row view), M[a, ids] = vals; ids may be an int (that axis is then dropped)."""
+
+    def __init__(self, fetch, G, V0, dtype):
+        self.fetch, self.G, self.V0, self.dtype = fetch, G, V0, np.dtype(dtype)
+        self.over = [dict() for _ in range(G)]          # overwritten round-0 entries
+        self.ov_mask = np.zeros(max(V0, 1), dtype=bool)
+        self.extra = np.zeros((G, 1024), dtype=self.dtype)   # vertices >= V0
+        self._memo = {}                         # small read cache for single-vertex queries (erosion walks)
+
+    def touched_base(self):
+        "sorted ids < V0 whose entry differs (or may differ) from the device's in some assembly"
+        keys = set()
+        for d in self.over:
+            keys.update(d)
+        return np.array(sorted(keys), dtype=np.int64)
+
+    def _get(self, rows, ids):
+        ids = np.asarray(ids, dtype=np.int64)
+        out = np.empty((self.G, len(ids)), dtype=self.dtype)
+        base = ids < self.V0
+        if base.all():
+            bi = ids
+            if len(ids):
+                out[:] = self.fetch(ids)
+        else:
+            bi = ids[base]
+            if len(bi):
+                out[:, base] = self.fetch(bi)
+            x = ids[~base] - self.V0
+            self._reserve(int(x.max()) + 1)
+            out[:, ~base] = self.extra[:, x]                # (zero until written, like the dense form's spare rows)
+        if len(bi) and any(self.over):
+            hit = np.flatnonzero(self.ov_mask[bi])
+            if len(hit):
+                at = np.flatnonzero(base)[hit] if len(bi) != len(ids) else hit
+                for a in rows:
+                    d = self.over[a]
+                    if d:
+                        for i, v in zip(at.tolist(), bi[hit].tolist()):
+                            got = d.get(v)
+                            if got is not None:
+                                out[a, i] = got
+        return out
+
+    def _reserve(self, need):
+        if need > self.extra.shape[1]:
+            grown = np.zeros((self.G, max(need, 2 * self.extra.shape[1])), dtype=self.dtype)
+            grown[:, :self.extra.shape[1]] = self.extra
+            self.extra = grown
+
+    def prefetch(self, ids):
+        "cache the columns of `ids` for later single-vertex reads"
+        ids = np.unique(np.asarray(ids, dtype=np.int64))
+        ids = ids[ids >= 0]
+        if len(ids):
+            cols = self._get(range(self.G), ids)
+            self._memo.update(zip(ids.tolist(), cols.T))
+
+    def __getitem__(self, key):
+        if not isinstance(key, tuple):
+            return _LazyRow(self, int(key))
+        r, ids = key
+        scalar = np.ndim(ids) == 0
+        if scalar:
+            got = self._memo.get(int(ids))
+            col = got if got is not None else self._get(range(self.G), [int(ids)])[:, 0]
+            return col.copy() if isinstance(r, slice) else col[int(r)]
+        if isinstance(r, slice):
+            return self._get(range(self.G), ids)
+        return self._get([int(r)], ids)[int(r)]
+
+    def __setitem__(self, key, vals):
+        a, ids = key
+        a = int(a)
+        ids = np.atleast_1d(np.asarray(ids, dtype=np.int64))
+        vals = np.broadcast_to(np.asarray(vals, dtype=self.dtype), ids.shape)
+        new = ids >= self.V0
+        if new.any():
+            x = ids[new] - self.V0
+            self._reserve(int(x.max()) + 1)
+            self.extra[a, x] = vals[new]
+        if not new.all():
+            b = ids[~new]
+            self.over[a].update(zip(b.tolist(), vals[~new].tolist()))
+            self.ov_mask[b] = True
+        if self._memo:
+            for v in ids.tolist():
+                self._memo.pop(v, None)
+
+
+class LazyVector:
+    "the h1 column, same idea: device gather for round-0 vertices, host dict for the vertices added later"
+
+    def __init__(self, fetch, V0):
+        self.fetch, self.V0 = fetch, V0
+        self.extra = {}
+
+    def __getitem__(self, ids):
+        scalar = np.ndim(ids) == 0
+        idx = np.atleast_1d(np.asarray(ids, dtype=np.int64))
+        out = np.zeros(len(idx), dtype=np.uint64)
+        base = idx < self.V0
+        if base.any():
+            out[base] = self.fetch(idx[base])
+        for i in np.flatnonzero(~base).tolist():
+            out[i] = self.extra[int(idx[i])]
+        return out[0] if scalar else out
+
+    def __setitem__(self, ids, vals):
+        self.extra.update(zip(np.atleast_1d(np.asarray(ids, dtype=np.int64)).tolist(),
+                              np.atleast_1d(np.asarray(vals, dtype=np.uint64)).tolist()))
+
+
 class SyntenyEngine:
     """backend must provide:
          names[a]            TSV-style assembly names, ALREADY in the reference's processing order
@@ -155,15 +283,35 @@ class SyntenyEngine:
 
     # ------------------------------------------------------------------ vertex storage
     def _init_vertices(self, j):
-        self._prebuilt = "host" in j
+        self._prebuilt = "host" in j or "gather" in j
         self._pair_masks = j.get("pair_masks")
         self._h_extra = {}
         self._h_extra_cache = None
         self._pair_cache = None
         self._pair_orig, self._pair_delta = {}, {}      # corrections to the device prefix sums (see _refresh_pairs)
-        self._br_touched = set()                        # pairs (i, i+1) whose `conn` changed since _breaks was made
+        self._br_touched = []                           # arrays of pairs (i, i+1) whose `conn` changed since the runs were last made
         self.sparse = set()                             # vertices that may hold a non-(i,i+1) edge
         self._ctg0 = {}                                 # (assembly, base vertex) -> round-0 contig, for the few overwritten entries
+        self._dev = j if "gather" in j else None        # device-resident form: columns are read through gathers
+        if self._dev is not None:
+            # the O(V) columns stay on the device (nts_graph_gather / _range_sums / _neigh / _runs_to_blocks); the host
+            # holds the weight-filtered graph (nbr, conn), the three sparse lists and what later rounds write
+            V = int(j["V"])
+            self.V0 = self.V = V
+            cap = V + 65536 + V // 16
+            G = self.G
+            self.H = LazyVector(lambda ids: j["gather"]("h1", ids), V)
+            self.POS = LazyMatrix(lambda ids: j["gather"]("pos", ids), G, V, np.int64)
+            self.CTG = LazyMatrix(lambda ids: j["gather"]("ctg", ids), G, V, np.int32)
+            self.nbr, conn = j["links_nbr"](cap)
+            self.conn = conn[:max(V - 1, 0)].view(bool)
+            self.alive = np.zeros(cap, dtype=bool); self.alive[:V] = True
+            self.RANK = self.INV = self.CI = self.CD = None
+            self.incmask = self.decmask = self.spread = None
+            breaks, deg3, big = j["sparse"](self.bp)
+            self._breaks, self._deg3, self.big = breaks, deg3, big
+            self._cum_dirty = False
+            return
         if self._prebuilt:
             # lean form (device backend): the O(V) columns arrive in their final dtype and layout, written by the
             # device into pinned buffers with room for the vertices later rounds add
@@ -260,11 +408,14 @@ class SyntenyEngine:
 
     def _range_sums(self, lo, hi):
         "per-assembly counts of increasing / decreasing pairs (i, i+1) with lo <= i < hi, for arrays lo, hi"
-        CI, CD = self._cums()
         lo = np.minimum(lo, self.V0)          # vertices added after round 0 only form single-vertex segments
         hi = np.minimum(hi, self.V0)
-        up = (CI[:, hi] - CI[:, lo]).astype(np.int64)
-        down = (CD[:, hi] - CD[:, lo]).astype(np.int64)
+        if self._dev is not None:
+            up, down = self._dev["range_sums"](lo, hi)
+        else:
+            CI, CD = self._cums()
+            up = (CI[:, hi] - CI[:, lo]).astype(np.int64)
+            down = (CD[:, hi] - CD[:, lo]).astype(np.int64)
         if self._pair_delta:
             if self._pair_cache is None or self._pair_cache[0] != len(self._pair_delta):
                 keys = np.array(sorted(self._pair_delta), dtype=np.int64)
@@ -284,13 +435,14 @@ class SyntenyEngine:
         return self.CTG[a, v] if got is None else got
 
     def _grow(self, need):
-        cap = len(self.H)
+        cap = len(self.alive)
         if self.V + need <= cap:
             return
         new = max(cap * 2, self.V + need + 1024)
-        self.H = np.concatenate([self.H, np.empty(new - cap, dtype=np.uint64)])
-        self.POS = np.concatenate([self.POS, np.zeros((self.G, new - cap), dtype=np.int64)], axis=1)
-        self.CTG = np.concatenate([self.CTG, np.zeros((self.G, new - cap), dtype=np.int32)], axis=1)
+        if self._dev is None:
+            self.H = np.concatenate([self.H, np.empty(new - cap, dtype=np.uint64)])
+            self.POS = np.concatenate([self.POS, np.zeros((self.G, new - cap), dtype=np.int64)], axis=1)
+            self.CTG = np.concatenate([self.CTG, np.zeros((self.G, new - cap), dtype=np.int32)], axis=1)
         self.alive = np.concatenate([self.alive, np.zeros(new - cap, dtype=bool)])
         self.nbr = np.concatenate([self.nbr, np.full((new - cap, 2), -1, dtype=np.int32)])
 
@@ -339,7 +491,7 @@ class SyntenyEngine:
         lo, hi = np.minimum(us, vs), np.maximum(us, vs)
         base = ((hi - lo) == 1) & (hi < self.V0)
         self.conn[lo[base]] = True
-        self._br_touched.update(lo[base].tolist())
+        self._br_touched.append(lo[base])
         self.sparse.update(us[~base].tolist()); self.sparse.update(vs[~base].tolist())
 
     def _remove_edges(self, us, vs):
@@ -353,7 +505,7 @@ class SyntenyEngine:
         lo = np.minimum(us, vs)
         base = (np.abs(us - vs) == 1) & (np.maximum(us, vs) < self.V0)
         self.conn[lo[base]] = False
-        self._br_touched.update(lo[base].tolist())
+        self._br_touched.append(lo[base])
 
     def _remove_vertices(self, ids):
         ids = np.unique(np.asarray(ids, dtype=np.int64))
@@ -372,10 +524,20 @@ class SyntenyEngine:
             self._remove_vertices(np.concatenate(ids))
 
     # ------------------------------------------------------------------ round-0 adjacency (implicit in ranks)
+    def _rank_of(self, a, u):
+        if self._dev is not None:
+            return int(self._dev["gather"]("rank", np.array([u], dtype=np.int64))[a, 0])
+        return int(self.RANK[a, u])
+
+    def _at_rank(self, a, r):
+        if self._dev is not None:
+            return int(self._dev["gather"]("inv", np.array([r], dtype=np.int64))[a, 0])
+        return int(self.INV[a, r])
+
     def _adjacent(self, a, u, v):
         if u >= self.V0 or v >= self.V0:
             return False
-        ru, rv = self.RANK[a, u], self.RANK[a, v]
+        ru, rv = self._rank_of(a, u), self._rank_of(a, v)
         return abs(int(ru) - int(rv)) == 1 and self._ctg_round0(a, u) == self._ctg_round0(a, v)
 
     def _edge_key0(self, u, v):
@@ -386,14 +548,14 @@ class SyntenyEngine:
                     return a
             return None
         a0 = first_new(u, v)
-        r = min(int(self.RANK[a0, u]), int(self.RANK[a0, v]))
-        src = u if int(self.RANK[a0, u]) < int(self.RANK[a0, v]) else v
+        r = min(self._rank_of(a0, u), self._rank_of(a0, v))
+        src = u if self._rank_of(a0, u) < self._rank_of(a0, v) else v
         tau = (a0, r)
         sigma = None
         for a in range(self.G):                      # first time src is the left element of a NEW pair
-            rs = int(self.RANK[a, src])
+            rs = self._rank_of(a, src)
             if rs + 1 < self.V0:
-                x = int(self.INV[a, rs + 1])
+                x = self._at_rank(a, rs + 1)
                 if self._ctg_round0(a, x) == self._ctg_round0(a, src) and first_new(src, x) == a:
                     sigma = (a, rs)
                     break
@@ -410,6 +572,21 @@ class SyntenyEngine:
         if not len(cand):
             return bumped, removed
         ctg0 = self.CTG                                 # round 0: nothing has been overwritten yet
+        if self._dev is not None:
+            # neighbourhoods of the candidates come from the device (nts_graph_neigh); same visiting order and rules in
+            # C++ (csrc/nts_hostgraph.cu: nts_host_simplify_neigh)
+            import ctypes as C
+            from ._lib import check, lib, ptr
+            cand64 = np.ascontiguousarray(cand, dtype=np.int64)
+            left, right, rk = self._dev["neigh"](cand64)
+            cap = 4 * len(cand64) + 4
+            bs, bt, rm = (np.empty(cap, dtype=np.int64) for _ in range(3))
+            n_out = C.c_int64()
+            check(lib.nts_host_simplify_neigh(ptr(cand64, C.c_int64), len(cand64), ptr(left, C.c_int64), ptr(right, C.c_int64),
+                                              ptr(rk, C.c_int64), G, ptr(bs, C.c_int64), ptr(bt, C.c_int64),
+                                              ptr(rm, C.c_int64), cap, C.byref(n_out)))
+            n = n_out.value
+            return dict(zip(zip(bs[:n].tolist(), bt[:n].tolist()), [G] * n)), rm[:n].tolist()
         if self.native:
             # same visiting order and rules, in C++ (csrc/nts_hostgraph.cu: nts_host_simplify)
             import ctypes as C
@@ -487,26 +664,46 @@ class SyntenyEngine:
         return bumped, removed
 
     # ------------------------------------------------------------------ paths of a max-degree-2 graph
-    def _find_paths(self):
+    def _find_paths(self, device_pure=False):
         """ntjoin.py:114-151 on the weight-filtered graph: every component that is a simple path with
         two distinct ends gives one path, oriented from the end with the smaller position in the
-        orienting assembly.  A path is a list of segments (lo, hi, dir)."""
+        orienting assembly.  A path is a list of segments (lo, hi, dir).
+        device_pure (device-resident form): the plain (i, i+1) runs whose vertices still hold their round-0
+        positions are not turned into paths here; they are returned as a second value (starts, ends) for
+        nts_graph_runs_to_blocks."""
         V0 = self.V0
         opos = self.POS[self.orient]
         paths = []
-        if V0:
+        dev = self._dev is not None
+        if V0 and dev:
+            # chain extraction on the device: push the pairs the host edited, get the runs of >= 2 vertices back
+            if self._br_touched:
+                t = np.unique(np.concatenate(self._br_touched))
+                if len(t):
+                    self._dev["set_links"](t, self.conn[t].astype(np.uint8))
+            self._br_touched = []
+            starts, ends = self._dev["runs"]()
+            self._tick("p_runs")
+        elif V0:
             if self._breaks is None:
                 self._breaks = np.flatnonzero(~self.conn)
             elif self._br_touched:
                 # pairs whose link changed since the list was made: their truth is conn[i]
-                t = np.fromiter(self._br_touched, dtype=np.int64, count=len(self._br_touched))
+                t = np.unique(np.concatenate(self._br_touched))
                 keep = self._breaks[~np.isin(self._breaks, t)]
                 self._breaks = np.union1d(keep, t[~self.conn[t]])
-            self._br_touched = set()
+            self._br_touched = []
             starts = np.concatenate([[0], self._breaks + 1])
             ends = np.concatenate([starts[1:] - 1, [V0 - 1]])
         else:
             starts = ends = np.zeros(0, dtype=np.int64)
+
+        def run_of(v):
+            "index of the listed run holding base vertices v, or -1 (single-vertex runs are not listed on the device path)"
+            r = np.searchsorted(starts, v, side="right") - 1
+            ok = r >= 0
+            ok[ok] = ends[r[ok]] >= v[ok]
+            return np.where(ok, r, -1)
         # vertices that really hold a sparse edge (non-consecutive neighbour, or any edge of a later vertex)
         rs = np.zeros(0, dtype=np.int64)                   # the real sparse vertices, ascending
         if self.sparse:
@@ -518,33 +715,66 @@ class SyntenyEngine:
         real_sparse = len(rs) > 0
         is_sp_run = np.zeros(len(starts), dtype=bool)
         base_sp = rs[rs < V0]
-        if len(base_sp):
-            is_sp_run[np.searchsorted(starts, base_sp, side="right") - 1] = True
-        pure = np.flatnonzero((ends > starts) & ~is_sp_run)
-        pa, pb = opos[starts[pure]], opos[ends[pure]]
-        for a, b, x, y in zip(starts[pure].tolist(), ends[pure].tolist(), pa.tolist(), pb.tolist()):
-            if x < y:
-                paths.append([(a, b, 1)])
-            elif y < x:
-                paths.append([(a, b, -1)])
-        if real_sparse and self.native:
+        if len(base_sp) and len(starts):
+            r = run_of(base_sp)
+            is_sp_run[r[r >= 0]] = True
+        plain = (ends > starts) & ~is_sp_run
+        dev_runs = None
+        if device_pure:
+            # runs holding a vertex whose position / contig was overwritten after round 0 stay on the host
+            touched = np.union1d(self.POS.touched_base(), self.CTG.touched_base())
+            stale = np.zeros(len(starts), dtype=bool)
+            if len(touched) and len(starts):
+                r = run_of(touched)
+                stale[r[r >= 0]] = True
+            dv = np.flatnonzero(plain & ~stale)
+            dev_runs = (starts[dv], ends[dv])
+            plain &= stale
+        pure = np.flatnonzero(plain)
+        if len(pure):
+            pa, pb = opos[starts[pure]], opos[ends[pure]]
+            for a, b, x, y in zip(starts[pure].tolist(), ends[pure].tolist(), pa.tolist(), pb.tolist()):
+                if x < y:
+                    paths.append([(a, b, 1)])
+                elif y < x:
+                    paths.append([(a, b, -1)])
+        if dev:
+            self._tick("p_pure")
+        if real_sparse and (self.native or dev):
             # the walk over runs joined by sparse edges, in C++ (csrc/nts_hostgraph.cu: nts_host_walk_paths)
             import ctypes as C
             from ._lib import check, lib, ptr
             sv = rs
             starts64 = np.ascontiguousarray(starts, dtype=np.int64)
             ends64 = np.ascontiguousarray(ends, dtype=np.int64)
-            opos64 = np.ascontiguousarray(opos, dtype=np.int64)
             nbr32 = self.nbr if self.nbr.flags.c_contiguous else np.ascontiguousarray(self.nbr)
             cap = 2 * len(sv) + 2
             slo, shi, poff = (np.empty(cap + 1, dtype=np.int64) for _ in range(3))
             sdir = np.empty(cap + 1, dtype=np.int8)
             n_p, n_s = C.c_int64(), C.c_int64()
-            check(lib.nts_host_walk_paths(nbr32.ctypes.data_as(C.POINTER(C.c_int32)), V0, ptr(starts64, C.c_int64),
-                                          ptr(ends64, C.c_int64), len(starts64), ptr(sv, C.c_int64), len(sv),
-                                          ptr(opos64, C.c_int64), ptr(slo, C.c_int64), ptr(shi, C.c_int64),
-                                          sdir.ctypes.data_as(C.POINTER(C.c_int8)), ptr(poff, C.c_int64), cap,
-                                          C.byref(n_p), C.byref(n_s)))
+            if dev:
+                # positions only where a path can end: the sparse vertices and both ends of the runs that hold them
+                ra, rb = sv.copy(), sv.copy()
+                bm = sv < V0
+                if bm.any() and len(starts):
+                    r = run_of(sv[bm])
+                    hit = r >= 0
+                    ia = np.flatnonzero(bm)[hit]
+                    ra[ia], rb[ia] = starts[r[hit]], ends[r[hit]]
+                oid = np.unique(np.concatenate([sv, ra, rb]))
+                oval = np.ascontiguousarray(opos[oid], dtype=np.int64)
+                check(lib.nts_host_walk_paths_sparse(nbr32.ctypes.data_as(C.POINTER(C.c_int32)), V0, ptr(starts64, C.c_int64),
+                                                     ptr(ends64, C.c_int64), len(starts64), ptr(sv, C.c_int64), len(sv),
+                                                     ptr(oid, C.c_int64), ptr(oval, C.c_int64), len(oid), ptr(slo, C.c_int64),
+                                                     ptr(shi, C.c_int64), sdir.ctypes.data_as(C.POINTER(C.c_int8)),
+                                                     ptr(poff, C.c_int64), cap, C.byref(n_p), C.byref(n_s)))
+            else:
+                opos64 = np.ascontiguousarray(opos, dtype=np.int64)
+                check(lib.nts_host_walk_paths(nbr32.ctypes.data_as(C.POINTER(C.c_int32)), V0, ptr(starts64, C.c_int64),
+                                              ptr(ends64, C.c_int64), len(starts64), ptr(sv, C.c_int64), len(sv),
+                                              ptr(opos64, C.c_int64), ptr(slo, C.c_int64), ptr(shi, C.c_int64),
+                                              sdir.ctypes.data_as(C.POINTER(C.c_int8)), ptr(poff, C.c_int64), cap,
+                                              C.byref(n_p), C.byref(n_s)))
             segs_all = list(zip(slo[:n_s.value].tolist(), shi[:n_s.value].tolist(), sdir[:n_s.value].tolist()))
             off = poff[:n_p.value + 1].tolist()
             paths.extend(segs_all[off[i]:off[i + 1]] for i in range(n_p.value))
@@ -611,7 +841,7 @@ class SyntenyEngine:
                     paths.append(segs)
                 elif pb < pa:
                     paths.append([(lo, hi, -d) for lo, hi, d in reversed(segs)])
-        return paths
+        return (paths, dev_runs) if device_pure else paths
 
     # ------------------------------------------------------------------ blocks from paths
     def _blocks_from_paths(self, paths):
@@ -774,6 +1004,58 @@ class SyntenyEngine:
         if rm:
             self._remove_segments(rm)
         return keep
+
+    # ------------------------------------------------------------------ paths -> blocks (one round)
+    def _extract_blocks(self):
+        """find_paths -> find_synteny_blocks -> check_for_indels -> filter_synteny_blocks(4) for the current graph.
+        Device-resident form: the plain (i, i+1) runs go through nts_graph_runs_to_blocks (kernel iv-c) and come back
+        as a compact block table; only the components with a non-(i, i+1) edge, and the runs holding a vertex whose
+        position was overwritten after round 0, are walked on the host."""
+        if self._dev is None:
+            paths = self._find_paths()
+            self._tick("paths")
+            self.stats["paths"] = len(paths)
+            blocks = self._blocks_from_paths(paths)
+            self._tick("blocks")
+            blocks = self._split_indels(blocks)
+            self._tick("indels")
+            return self._filter_small(blocks, 4)
+        paths, (ds, de) = self._find_paths(device_pure=True)
+        self._tick("p_walk")
+        res = self._dev["runs_to_blocks"](ds, de, self.bp, float(self.m), 4)
+        self._tick("b_dev")
+        blocks = self._blocks_from_paths(paths)
+        self._tick("b_host_blocks")
+        blocks = self._split_indels(blocks)
+        self._tick("b_host_indels")
+        blocks = self._filter_small(blocks, 4)
+        self._tick("b_host_small")
+        lo, hi = res["b_lo"].astype(np.int64), res["b_hi"].astype(np.int64)
+        self.stats["paths"] = len(paths) + len(lo) + len(res["r_lo"])
+        if len(lo):
+            o = np.argsort(lo)
+            lo, hi, up = lo[o], hi[o], res["b_dir"][o] > 0
+            plus = res["b_plus"][o]
+            f_id, l_id = np.where(up, lo, hi), np.where(up, hi, lo)
+            both = np.concatenate([f_id, l_id])
+            pos = self.POS[:, both]
+            ctg_f = self.CTG[:, f_id].T.tolist()
+            pos_f, pos_l = pos[:, :len(lo)].T.tolist(), pos[:, len(lo):].T.tolist()
+            ori = [["+" if (p >> a) & 1 else "-" for a in range(self.G)] for p in plus.tolist()]
+            for i, (l_, h_, u_, f_, e_) in enumerate(zip(lo.tolist(), hi.tolist(), up.tolist(), f_id.tolist(), l_id.tolist())):
+                blocks.append(Block([(l_, h_, 1 if u_ else -1)], ctg_f[i], ori[i], f_, e_, pos_f[i], pos_l[i], h_ - l_ + 1))
+        self._tick("b_make")
+        # what the kernel deleted: unoriented / short pieces, and the edges cut as indels
+        if len(res["r_lo"]):
+            rl, rh = res["r_lo"].astype(np.int64), res["r_hi"].astype(np.int64)
+            n = rh - rl + 1
+            self._remove_vertices(np.repeat(rl, n) + (np.arange(int(n.sum())) - np.repeat(np.cumsum(n) - n, n)))
+        if len(res["cuts"]):
+            c = res["cuts"].astype(np.int64)
+            self._remove_edges(c, c + 1)
+        self.stats["dev_runs"] = self.stats.get("dev_runs", []) + [[int(len(ds)), int(len(lo)), int(len(res["r_lo"])), int(len(res["cuts"])), len(paths)]]
+        self._tick("b_apply")
+        return blocks
 
     # ------------------------------------------------------------------ output
     def _sort_blocks(self, blocks):
@@ -1012,16 +1294,19 @@ class SyntenyEngine:
                 self.nbr[nv] = -1
                 cid[missing] = nv
             # pass 1: which base vertices get a new position / contig (assembly a only writes row a)
-            touched = []
+            touched, changed_per_asm = [], []
             for a in range(G):
                 kh, kp, kc, _ = lists[a]
                 vid = cid[np.searchsorted(common, kh)]
-                changed = (self.POS[a, vid] != kp) | (self.CTG[a, vid] != kc)
-                tb = vid[changed & (vid < self.V0)]
-                for v_, c_ in zip(tb.tolist(), self.CTG[a, tb].tolist()):      # keep the round-0 contig of what gets overwritten
+                cur_c = self.CTG[a, vid]
+                changed = (self.POS[a, vid] != kp) | (cur_c != kc)
+                sel = changed & (vid < self.V0)
+                tb = vid[sel]
+                for v_, c_ in zip(tb.tolist(), cur_c[sel].tolist()):           # keep the round-0 contig of what gets overwritten
                     self._ctg0.setdefault((a, v_), c_)
                 touched.append(tb)
                 ids_per_asm.append(vid)
+                changed_per_asm.append(changed | (vid >= self.V0))
             touched_base = np.unique(np.concatenate(touched)) if touched else np.zeros(0, dtype=np.int64)
             pairs = old = None
             if len(touched_base):
@@ -1031,8 +1316,9 @@ class SyntenyEngine:
             # pass 2: overwrite
             for a in range(G):
                 _, kp, kc, _ = lists[a]
-                self.POS[a, ids_per_asm[a]] = kp
-                self.CTG[a, ids_per_asm[a]] = kc
+                ch = changed_per_asm[a]                   # (the other entries already hold these values)
+                self.POS[a, ids_per_asm[a][ch]] = kp[ch]
+                self.CTG[a, ids_per_asm[a][ch]] = kc[ch]
             if pairs is not None:
                 self._refresh_pairs(pairs, old)
         else:
@@ -1191,10 +1477,19 @@ class SyntenyEngine:
         # flagged pair can be taken up front
         la = np.array(low, dtype=np.int64).reshape(-1, 2)
         both1 = ((self.nbr[la[:, 0]] >= 0).sum(axis=1) == 1) & ((self.nbr[la[:, 1]] >= 0).sum(axis=1) == 1)
-        for (u, v) in la[both1].tolist():
+        sel = la[both1]
+        hv = self.H[sel.ravel()].reshape(-1, 2) if len(sel) else np.zeros((0, 2), dtype=np.uint64)
+        if self._dev is not None and len(sel):
+            # positions around the flagged pairs in one gather (the walk below reads them one vertex at a time)
+            ring = sel.ravel()
+            for _ in range(3):
+                nb = self.nbr[ring].ravel()
+                ring = np.unique(np.concatenate([ring, nb[nb >= 0]]))
+            self.POS.prefetch(ring)
+        for (u, v), (hu, hv_) in zip(sel.tolist(), hv.tolist()):
             # igraph reports (source, target) = (min id, max id); the reference then orders by NAME string
             s, t = (u, v)
-            if name(s) > name(t):
+            if str(int(hu)) > str(int(hv_)):
                 s, t = t, s
             erode_target = True
             cs, ct = s, t
@@ -1260,15 +1555,8 @@ class SyntenyEngine:
         # --- paths, blocks
         self.log("Finding paths")
         self._tick("filter0")
-        paths = self._find_paths()
-        self._tick("paths")
-        self.stats["paths"] = len(paths)
         self.log("Finding synteny blocks")
-        blocks = self._blocks_from_paths(paths)
-        self._tick("blocks")
-        blocks = self._split_indels(blocks)
-        self._tick("indels")
-        blocks = self._filter_small(blocks, 4)
+        blocks = self._extract_blocks()
         ordered = self._sort_blocks(blocks)
         self._tick("filter_sort")
         if not ordered:
@@ -1285,13 +1573,7 @@ class SyntenyEngine:
             self._tick("emit")
             self._refine_round(blocks, new_w, prev_w, last, ri + 1)
             self._tick("refine")
-            paths = self._find_paths()
-            self._tick("paths")
-            blocks = self._blocks_from_paths(paths)
-            self._tick("blocks")
-            blocks = self._split_indels(blocks)
-            self._tick("indels")
-            blocks = self._filter_small(blocks, 4)
+            blocks = self._extract_blocks()
             ordered = self._sort_blocks(blocks)
             self._tick("filter_sort")
             if last or self.write_files:               # every round overwrites the same table: only the last one stays

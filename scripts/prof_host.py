@@ -35,6 +35,37 @@ def step():
 
 for _ in range(2):
     step()
+
+# where do the numpy calls of the graph stage spend their time?  (caller line, calls, total ms, largest operand)
+import collections
+import time
+import numpy as _np
+_acc = collections.defaultdict(lambda: [0, 0.0, 0])
+
+
+def _wrap(name):
+    orig = getattr(_np, name)
+
+    def f(*a, **k):
+        t0 = time.perf_counter()
+        r = orig(*a, **k)
+        fr = sys._getframe(1)
+        e = _acc[(name, os.path.basename(fr.f_code.co_filename), fr.f_lineno)]
+        e[0] += 1; e[1] += time.perf_counter() - t0
+        e[2] = max(e[2], max((getattr(x, "size", 0) for x in a), default=0))
+        return r
+    setattr(_np, name, f)
+    return orig
+
+
+_origs = {n: _wrap(n) for n in ("searchsorted", "unique", "union1d", "concatenate", "flatnonzero", "isin", "argsort", "fromiter",
+                                "zeros", "repeat", "cumsum", "bincount", "array", "sort", "where")}
+eng = step()
+for n, o in _origs.items():
+    setattr(_np, n, o)
+for key, (cnt, tot, size) in sorted(_acc.items(), key=lambda kv: -kv[1][1])[:40]:
+    print(f"{key[0]:14s} {key[1]}:{key[2]:<5d} calls {cnt:5d}  {tot * 1e3:8.2f} ms  max operand {size}")
+print({k: (round(v * 1e3, 1) if k.startswith("t_") else v) for k, v in eng.stats.items()})
 pr = cProfile.Profile()
 pr.enable()
 eng = step()

@@ -133,6 +133,8 @@ class OracleBackend:
         inc, dec, spread = numpy_pairs(POS)
         self._h_order = np.argsort(H, kind="stable")
         self._h_sorted = H[self._h_order]
+        if self.lean == "dev":
+            return self._device_form(H, POS, CTG, RANK, INV, link, degree, inc, dec, spread, order_asm)
         if self.lean:
             CI = np.zeros((G, V + 1), dtype=np.int32)
             CD = np.zeros((G, V + 1), dtype=np.int32)
@@ -161,6 +163,126 @@ class OracleBackend:
                         pair_masks=lambda: (inc, dec, spread))
         return dict(H=H, POS=POS, CTG=CTG, RANK=RANK, INV=INV, link=link, degree=degree, incmask=inc, decmask=dec,
                     spread=spread)
+
+    def _device_form(self, H, POS, CTG, RANK, INV, link, degree, inc, dec, spread, order_asm):
+        """numpy restatement of the device-resident join result (ntsynt_b200.device.MinimizerGraph.join_result):
+        gather / range_sums / neigh / links_nbr / set_links / runs / runs_to_blocks -- the kernels of csrc/nts_graph.cu
+        restated for the CPU tests of the host logic"""
+        G, V = RANK.shape
+        CI = np.zeros((G, V + 1), dtype=np.int64)
+        CD = np.zeros((G, V + 1), dtype=np.int64)
+        for a in range(G):
+            np.cumsum((inc >> np.uint32(a)) & np.uint32(1), out=CI[a, 1:])
+            np.cumsum((dec >> np.uint32(a)) & np.uint32(1), out=CD[a, 1:])
+        dlink = link.astype(np.uint8).copy()
+        cols = {"h1": H, "pos": POS.astype(np.int64), "ctg": CTG.astype(np.int32), "rank": RANK, "inv": INV}
+        self.calls = {}
+
+        def count(name):
+            self.calls[name] = self.calls.get(name, 0) + 1
+
+        def gather(what, ids):
+            count("gather")
+            ids = np.asarray(ids, dtype=np.int64)
+            assert ((ids >= 0) & (ids < V)).all()
+            c = cols[what]
+            return c[ids].copy() if c.ndim == 1 else c[:, ids].copy()
+
+        def range_sums(lo, hi):
+            count("range_sums")
+            lo, hi = np.minimum(lo, V), np.minimum(hi, V)
+            return CI[:, hi] - CI[:, lo], CD[:, hi] - CD[:, lo]
+
+        def neigh(cand):
+            count("neigh")
+            n = len(cand)
+            left, right, rk = (np.full((n, G), -1, dtype=np.int64) for _ in range(3))
+            for a in range(G):
+                r = RANK[a, cand].astype(np.int64)
+                rk[:, a] = r
+                ok = r > 0
+                x = INV[a, r[ok] - 1].astype(np.int64)
+                left[ok, a] = np.where(CTG[a, x] == CTG[a, cand[ok]], x, -1)
+                ok = r + 1 < V
+                x = INV[a, r[ok] + 1].astype(np.int64)
+                right[ok, a] = np.where(CTG[a, x] == CTG[a, cand[ok]], x, -1)
+            return left, right, rk
+
+        def links_nbr(cap):
+            rng = np.random.default_rng(V)
+            nbr = rng.integers(-1, 100, (cap, 2)).astype(np.int32)
+            conn = rng.integers(0, 2, cap).astype(np.uint8); conn[:V] = link
+            ar = np.arange(V, dtype=np.int32)
+            nbr[:V, 1] = np.where(link.astype(bool), ar + 1, -1)
+            nbr[:V, 0] = -1
+            if V > 1:
+                nbr[1:V, 0] = np.where(link[:-1].astype(bool), ar[:-1], -1)
+            return nbr, conn
+
+        def set_links(idx, val):
+            count("set_links")
+            dlink[np.asarray(idx, dtype=np.int64)] = val
+
+        def runs():
+            count("runs")
+            l = dlink[:max(V - 1, 0)].astype(bool)
+            prev = np.r_[False, l]            # link[i-1]
+            cur = np.r_[l, False]             # link[i]
+            return np.flatnonzero(~prev & cur)[:V].astype(np.int64), np.flatnonzero(prev & ~cur).astype(np.int64)
+
+        def sparse(bp):
+            return (np.zeros(0, dtype=np.int64), np.flatnonzero(degree == 3).astype(np.int64),
+                    np.flatnonzero(spread[:max(V - 1, 0)] > bp).astype(np.int64))
+
+        def runs_to_blocks(starts, ends, bp, m_pct, min_mx):
+            count("runs_to_blocks")
+            big = np.flatnonzero(spread[:max(V - 1, 0)] > bp)
+            out = dict(b_lo=[], b_hi=[], b_plus=[], b_dir=[], r_lo=[], r_hi=[], cuts=[])
+            for s_, e_ in zip(starts.tolist(), ends.tolist()):
+                assert e_ > s_ and dlink[s_:e_].all()
+                x, y = int(POS[order_asm, s_]), int(POS[order_asm, e_])
+                if x == y:
+                    continue
+                d = 1 if x < y else -1
+                n = e_ - s_ + 1
+                plus, bad = 0, False
+                for a in range(G):
+                    up, down = int(CI[a, e_] - CI[a, s_]), int(CD[a, e_] - CD[a, s_])
+                    i_, d_ = (up, down) if d > 0 else (down, up)
+                    if i_ == n - 1:
+                        plus |= 1 << a
+                    elif d_ == n - 1:
+                        pass
+                    else:
+                        positive = i_ / float(n - 1) * 100
+                        if positive >= m_pct:
+                            plus |= 1 << a
+                        elif 100 - positive >= m_pct:
+                            pass
+                        else:
+                            bad = True
+                if bad:
+                    out["r_lo"].append(s_); out["r_hi"].append(e_)
+                    continue
+                cuts = big[(big >= s_) & (big < e_)].tolist()
+                lo = s_
+                for hi in cuts + [e_]:
+                    if hi - lo + 1 >= min_mx:
+                        out["b_lo"].append(lo); out["b_hi"].append(hi); out["b_plus"].append(plus); out["b_dir"].append(d)
+                    else:
+                        out["r_lo"].append(lo); out["r_hi"].append(hi)
+                    lo = hi + 1
+                out["cuts"].extend(cuts)
+            rng = np.random.default_rng(len(starts))           # the device appends in no particular order
+            pb, pr = rng.permutation(len(out["b_lo"])), rng.permutation(len(out["r_lo"]))
+            res = {k: np.asarray(v, dtype=np.int8 if k == "b_dir" else np.uint32) for k, v in out.items()}
+            for k in ("b_lo", "b_hi", "b_plus", "b_dir"):
+                res[k] = res[k][pb]
+            for k in ("r_lo", "r_hi"):
+                res[k] = res[k][pr]
+            return res
+        return dict(V=V, gather=gather, range_sums=range_sums, neigh=neigh, links_nbr=links_nbr, set_links=set_links, runs=runs,
+                    runs_to_blocks=runs_to_blocks, sparse=sparse)
 
     def lookup(self, keys):
         out = np.full(len(keys), 0xFFFFFFFF, dtype=np.uint32)

@@ -25,7 +25,7 @@ def run_engine(paths, k, w, w_rounds, indel, merge, z, lean=False, native=True):
     return eng, be
 
 
-@pytest.mark.parametrize("lean", [False, True])
+@pytest.mark.parametrize("lean", [False, True, "dev"])
 @pytest.mark.parametrize("tag", ["AB", "ABC"])
 def test_mini_against_reference_fixture(tag, mini_params, lean):
     p = mini_params
@@ -57,7 +57,8 @@ def test_engine_equals_graph_oracle_on_rearranged_genomes(tmp_path, seed, G, pre
         paths.append(p)
     k, w = 16, 40
     w_rounds, indel, merge, z = ([20, 5], 300, "400", 200) if presets == "low" else ([25, 10], 2000, "2w", 400)
-    eng, be = run_engine(paths, k, w, w_rounds, indel, merge, z, lean=bool(seed % 2))
+    lean = ["dev", True, False][seed % 3]
+    eng, be = run_engine(paths, k, w, w_rounds, indel, merge, z, lean=lean)
     go = GraphOracle([(os.path.basename(p) + f".k{k}.w{w}.tsv", so.read_fasta(p)) for p in paths], k, w, w_rounds,
                      indel, merge, z, be.bits)
     go.run()
@@ -65,9 +66,14 @@ def test_engine_equals_graph_oracle_on_rearranged_genomes(tmp_path, seed, G, pre
     assert eng.outputs["pre_merge"] == go.outputs["pre_merge"]
     assert eng.outputs["final"].count("\n") >= G * 3
     # the Python statements of the two native walks give the same blocks and the same intermediate counts
-    eng_py, _ = run_engine(paths, k, w, w_rounds, indel, merge, z, lean=bool(seed % 2), native=False)
+    eng_py, _ = run_engine(paths, k, w, w_rounds, indel, merge, z, lean=lean, native=False)
     assert eng_py.outputs == eng.outputs
     assert eng_py.stats["simplified_vertices"] == eng.stats["simplified_vertices"] and eng_py.stats["paths"] == eng.stats["paths"]
+    # and the device-resident form gives what the dense forms give
+    if lean != "dev":
+        eng_dev, be_dev = run_engine(paths, k, w, w_rounds, indel, merge, z, lean="dev")
+        assert eng_dev.outputs == eng.outputs
+        assert be_dev.calls.get("runs_to_blocks", 0) == 1 + len(w_rounds)
 
 
 def test_interval_index_matches_bruteforce():
