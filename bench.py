@@ -10,11 +10,15 @@ re-sketch + graph), erosion, collinear merges, final block table as TSV text.
 
 N = 1  : BASELINE.json configs[1]: 2 synthetic ~3 Gbp human-like genomes, d = 1 %, k = 24, w = 1000,
          presets of bin/ntSynt:92-94 (block_size 1000, indel 50000, merge 100000, w_rounds 250 100).
-N > 1  : configs[4]: one 3 Gbp genome per GPU (G = N), per-GPU Bloom filters merged over NVLink -- by default with
-         the peer-memory reduce-scatter / all-gather kernels (csrc/nts_p2p.cu), or with --merge nccl by one NCCL
-         all-reduce(sum) over packed counters (the north-star form; bit-identical, ~4x the wire volume; both are
-         timed alone in config.merge_alone_ms) -- then every rank sketches its genome and rank 0 runs the
+N > 1  : configs[4] (default, G = N or a multiple): one 3 Gbp genome per GPU, per-GPU Bloom filters merged over NVLink
+         -- by default with the peer-memory reduce-scatter / all-gather kernels (csrc/nts_p2p.cu), or with --merge nccl
+         by one NCCL all-reduce(sum) over packed counters (the north-star form; bit-identical, ~4x the wire volume;
+         both are timed alone in config.merge_alone_ms) -- then every rank sketches its genome and rank 0 runs the
          graph stage on the gathered tables.  Weak scaling: per-GPU work is fixed.
+         configs[2] / configs[3] (--genomes 3 --divergence 1.3, --genomes 5 --divergence 12; any G that is not a
+         multiple of N, or --shard contig): CONTIG-sharded ownership -- every rank inserts its contigs of every genome,
+         common = AND over genomes of (OR over ranks) in one peer-memory kernel, every rank sketches its contigs, the
+         tables are put back in contig order on rank 0.  Strong scaling: the job is fixed.
 
 `value` times the path with the packed genomes already resident in HBM; `e2e` times the same call
 chain starting from packed genomes in PINNED HOST memory (H2D inside the timed region) and ending
@@ -147,6 +151,19 @@ class Dist:
             self.td.destroy_process_group()
 
 
+def nccl_env():
+    """NCCL's log goes to stderr (stdout carries the one JSON line): the communicator banner (ranks, NVLS, transports)
+    stays visible to whoever reads the run's stderr"""
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+def sha1_text(text):
+    import hashlib
+    return hashlib.sha1((text or "").encode()).hexdigest()
+
+
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_sample_records(gens, sample_mbp_per_genome):
     "first slice of every contig of every genome, as ASCII records (host copies of device genomes)"
@@ -269,7 +286,8 @@ def run_ours(args, dist):
     order = pipeline.processing_order(names)
     my_ids = list(range(G)) if N == 1 else [g for g in range(G) if g % N == dist.rank]
     if N > 1:
-        return run_ours_multi(args, dist, ctx)
+        shard = args.shard or ("genome" if G % N == 0 else "contig")
+        return run_ours_sharded(args, dist, ctx) if shard == "contig" else run_ours_multi(args, dist, ctx)
     gens = {g: wl.materialize(ctx, g) for g in my_ids}
     total_bp = sum(int(x.total_bases) for x in gens.values())
     size_sorted = sorted(range(G), key=lambda i: file_names[i])
@@ -405,7 +423,7 @@ def run_ours(args, dist):
                                f"{G} synthetic {args.genome_mbp:g} Mbp genomes one-per-GPU, counting-BF NCCL-sum merge",
                    "genomes": G, "genome_bp": total_bp // max(len(my_ids), 1), "k": K, "w": W, "fpr": 0.025,
                    "bloom_bytes": nbytes, "l2": "inputs (bases + filters) are larger than L2; no flush needed",
-                   "blocks": text.count("\n") // G, "vertices": eng.stats.get("vertices")},
+                   "blocks": text.count("\n") // G, "blocks_sha1": sha1_text(text), "vertices": eng.stats.get("vertices")},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "bp/s", "h2d_bytes_per_step": h2d // e2e_steps,
                 "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
@@ -422,9 +440,7 @@ def run_ours(args, dist):
 
 
 def run_ours_multi(args, dist, ctx):
-    # NCCL prints its version banner to stdout from NCCL_DEBUG=VERSION upwards (WARN included): keep stdout to the
-    # one JSON line unless asked otherwise
-    os.environ["NCCL_DEBUG"] = os.environ.get("NTS_NCCL_DEBUG", "NONE")
+    nccl_env()
     """N > 1: one genome per GPU (G = N, or a multiple), per-GPU filters merged by NCCL all-reduce(sum)
     of packed counters, owners sketch, tables all-gathered, rank 0 runs the join + graph stage."""
     import numpy as np
@@ -433,7 +449,7 @@ def run_ours_multi(args, dist, ctx):
     N, rank = dist.world, dist.rank
     G = args.genomes or N
     if G % N:
-        raise SystemExit("--genomes must be a multiple of the number of GPUs")
+        raise SystemExit("one-genome-per-GPU sharding needs --genomes to be a multiple of the number of GPUs (use --shard contig)")
     d = args.divergence
     ps = presets(d)
     wl = synth.Workload(G, int(args.genome_mbp * 1e6), d, seed=args.seed)
@@ -575,7 +591,7 @@ def run_ours_multi(args, dist, ctx):
                        "merge_wire_bytes_per_rank": distributed.merge_wire_bytes(nbytes, N),
                        "merge_alone_ms": merge_ms,
                        "l2": "inputs (bases + filters) are larger than L2; no flush needed",
-                       "blocks": text.count("\n") // G, "vertices": eng.stats.get("vertices")},
+                       "blocks": text.count("\n") // G, "blocks_sha1": sha1_text(text), "vertices": eng.stats.get("vertices")},
             "clocks": clk,
             "e2e": {"value": total_bp * e2e_steps / (ms_e2e / 1e3), "unit": "bp/s", "h2d_bytes_per_step": int(h2d // e2e_steps),
                     "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
@@ -590,6 +606,164 @@ def run_ours_multi(args, dist, ctx):
         peer.close()
     comm.close()
 
+
+
+def run_ours_sharded(args, dist, ctx):
+    """N > 1, contig-sharded ownership (BASELINE configs 3 and 4): every rank holds its contigs of every
+    genome; per genome it builds the bits of those contigs; common = AND over genomes of (OR over ranks) with the
+    peer-memory kernel (or, --merge nccl, one NCCL counter all-reduce per genome and a local AND); every rank sketches
+    its contigs; the tables are all-gathered and put back in contig order; rank 0 runs the join + graph stage (it also
+    keeps whole genomes for the masked refinement sketches, < 1 % of the bases)."""
+    nccl_env()
+    import numpy as np
+    from ntsynt_b200 import device, distributed, pipeline, synth
+    from ntsynt_b200.synteny import SyntenyEngine
+    N, rank = dist.world, dist.rank
+    G = args.genomes or 3
+    d = args.divergence
+    ps = presets(d)
+    wl = synth.Workload(G, int(args.genome_mbp * 1e6), d, seed=args.seed)
+    file_names = [wl.file_name(g) for g in range(G)]
+    names = [pipeline.tsv_name(f, K, W) for f in file_names]
+    order = pipeline.processing_order(names)
+    n_contigs = len(wl.names)
+    own_of = distributed.assign_contigs(wl.anc_lengths, N)
+    owner_of_contig = [next(r for r in range(N) if c in own_of[r]) for c in range(n_contigs)]
+    mine_c = own_of[rank]
+    shards = [wl.materialize(ctx, g, contigs=mine_c) for g in range(G)]
+    whole = [wl.materialize(ctx, g) for g in range(G)] if rank == 0 else None
+    sizes = [int(wl.segments(g)[0].sum()) for g in range(G)]
+    total_bp = sum(sizes)
+    first = sorted(range(G), key=lambda i: file_names[i])[0]
+    nbytes = device.BloomFilter.size_for(sizes[first], 0.025)
+    parts = [ctx.bloom(nbytes) for _ in range(G)]
+    common = ctx.bloom(nbytes)
+    ident = distributed.Comm.new_unique_id() if rank == 0 else b""
+    comm = distributed.Comm(ctx, rank, N, dist.bcast_bytes(ident, 128))
+    peer = distributed.ShardedMerge(parts, common, rank, N, dist.gather_objects, dist.barrier) if N <= 16 and G <= 8 else None
+    if peer is not None and not peer.ok:
+        peer = None
+    use_p2p = args.merge == "p2p" and peer is not None
+    phase = {}
+
+    def tick(name, t0):
+        phase[name] = phase.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+
+    def hot_path(shard_list, whole_list):
+        t0 = time.perf_counter()
+        for g in range(G):
+            parts[g].set_genome(shard_list[g], K)                  # bits of my contigs of genome g
+        ctx.sync(); tick("insert", t0); t0 = time.perf_counter()
+        if use_p2p:
+            peer.merge(comm=comm)                                  # AND_g OR_r over NVLink peer memory, then all-gather
+        else:
+            for g in range(G):                                     # north-star form: counter all-reduce per genome
+                comm.allreduce_or(parts[g])
+            common.build_from_and(parts)
+        ctx.sync(); tick("merge", t0); t0 = time.perf_counter()
+        tables = []
+        for g in range(G):
+            t = ctx.sketch(shard_list[g], K, W, common=common)
+            tables.append(distributed.gather_sharded_table(comm, t, n_contigs, owner_of_contig, dist.gather_objects))
+            t.close()
+        tick("sketch_gather", t0); t0 = time.perf_counter()
+        text, eng = None, None
+        if rank == 0:
+            be = distributed.GatheredBackend(ctx, [whole_list[i] for i in order], [names[i] for i in order], [wl.names] * G,
+                                             [[int(x) for x in whole_list[i].lengths] for i in order], K, common,
+                                             [tables[i] for i in order])
+            eng = SyntenyEngine(be, K, W, ps["w_rounds"], ps["indel"], ps["merge"], ps["block_size"], write_files=False,
+                                quiet=True)
+            text = eng.run()
+            be.close()
+        for t in tables:
+            t.close()
+        dist.barrier()
+        tick("graph", t0)
+        return text, eng
+
+    for _ in range(max(args.warmup, 0)):
+        text, eng = hot_path(shards, whole)
+    ctx.prof_enable(True); ctx.prof_reset()
+    phase.clear()
+    launches0 = ctx.launches
+    clocks = ClockSampler(dist.local_rank)
+    dist.barrier(); ctx.sync()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        text, eng = hot_path(shards, whole)
+    ms = ctx.timer_stop()
+    ctx.sync(); dist.barrier()
+    ms = dist.max(ms)
+    launches = dist.sum(ctx.launches - launches0)
+    prof = ctx.prof()
+    ctx.prof_enable(False)
+    phase_ms = {k: round(v / args.steps, 2) for k, v in phase.items()}
+    value = total_bp * args.steps / (ms / 1e3)
+    # e2e: shards (and rank 0's whole genomes) start in pinned host memory
+    def pin(gen):
+        pk = gen.to_packed()
+        pb = device.PinnedU64(len(pk.words)); pb.array[:] = pk.words; pk.words = pb.array
+        return pk, pb
+    pinned_sh = [pin(x) for x in shards]
+    pinned_wh = [pin(x) for x in whole] if rank == 0 else None
+    ctx.prof_reset()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    dist.barrier(); ctx.sync()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        fs = [ctx.upload(pk, async_copy=True) for pk, _ in pinned_sh]
+        fw = [ctx.upload(pk, async_copy=True) for pk, _ in pinned_wh] if rank == 0 else None
+        text_e2e, _ = hot_path(fs, fw)
+        for f in fs + (fw or []):
+            f.close()
+    ms_e2e = dist.max(ctx.timer_stop())
+    h2d, d2h = ctx.xfer_bytes()
+    h2d, d2h = dist.sum(h2d), dist.sum(d2h)
+    clk = clocks.stop()
+    if rank == 0:
+        assert text_e2e == text
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json"), encoding="utf-8") as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    pair = prof.get("bf_part1", (0, 0, 0))
+    f_ms = pair[0] + prof.get("bf_apply", (0, 0, 0))[0]
+    achieved = (64.25 * pair[1] / max(pair[2], 1)) / ((f_ms / max(pair[2], 1)) / 1e3) / 1e9 if pair[2] else 0.0
+    wire = nbytes * (N - 1) / N * (G + 1)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{G} synthetic ~{args.genome_mbp:g} Mbp genomes, contigs sharded over {N}xB200, d={d:g}, "
+                                   f"k={K} w={W}, w_rounds {ps['w_rounds']}; common = AND_g OR_rank over NVLink "
+                                   f"({'peer-memory kernel' if use_p2p else 'NCCL counter all-reduce per genome'})",
+                       "genomes": G, "genome_bp": sizes[0], "k": K, "w": W, "fpr": 0.025, "bloom_bytes": nbytes,
+                       "shard": "contig", "contigs_per_rank": [len(x) for x in own_of],
+                       "bases_per_rank_of_genome0": [int(sum(int(wl.segments(0)[0][c]) for c in x)) for x in own_of],
+                       "merge": "p2p" if use_p2p else "nccl", "merge_wire_bytes_per_rank": int(wire),
+                       "phase_ms_rank0": phase_ms,
+                       "l2": "inputs (bases + filters) are larger than L2; no flush needed",
+                       "blocks": text.count("\n") // G, "blocks_sha1": sha1_text(text), "vertices": eng.stats.get("vertices"),
+                       "refinement_new_minimizers": eng.stats.get("new_raw"), "unmasked_fraction": eng.stats.get("unmasked")},
+            "clocks": clk,
+            "e2e": {"value": total_bp * e2e_steps / (ms_e2e / 1e3), "unit": "bp/s", "h2d_bytes_per_step": int(h2d // e2e_steps),
+                    "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "bf_bin_kernel + bf_apply_kernel (one Bloom insert of this rank's contigs)", "bound": "hbm",
+                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": None, "rank": 0,
+                         "kernel_ms_per_step": {f: round(prof[f][0] / args.steps, 3) for f in prof if prof[f][2]}},
+            "cpu_baseline": None,
+            "graph_stage_phase_ms": {k[2:]: round(v * 1e3, 1) for k, v in eng.stats.items() if k.startswith("t_")},
+        }))
+    if peer is not None:
+        peer.close()
+    comm.close()
 
 def run_reference(args, dist):
     "CPU restatement of the reference path on a bounded sample of the same workload (rank 0 only)"
@@ -643,6 +817,9 @@ def main():
                     help="per-genome sample for the CPU arm (192 Mbp x 2 genomes is ~12 s of CPU work on 16 cores)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard", choices=["genome", "contig"], default=None,
+                    help="multi-GPU ownership: one genome per GPU (default when --genomes is a multiple of --gpus) or the "
+                         "contigs of every genome spread over the GPUs (default otherwise: BASELINE configs 3 and 4)")
     ap.add_argument("--merge", choices=["nccl", "p2p"], default="p2p",
                     help="multi-GPU filter merge: peer-memory reduce-scatter/all-gather kernels over NVLink (default; "
                          "bit-identical and ~4x less wire volume) or NCCL all-reduce(sum) of packed counters (the "

@@ -217,6 +217,12 @@ int nts_p2p_open(nts_bf* mine, const uint8_t* handles, int rank, int world, nts_
 void nts_p2p_close(nts_p2p* p);
 int nts_p2p_reduce_scatter(nts_p2p* p, int op);
 int nts_p2p_all_gather(nts_p2p* p);
+/* Contig-sharded ownership (G < number of GPUs): every rank holds, per genome, the bits of its own
+ * contigs.  sets[g] maps genome g's partial filters of all ranks, `out` maps the common filter:
+ *   barrier; nts_p2p_reduce_and_of_or(sets, G, out); barrier; nts_p2p_all_gather(out); barrier
+ * computes common = AND over genomes of (OR over ranks) -- src/ntsynt_make_common_bf.cpp:136-160 and the cross-GPU
+ * merge in one kernel that reads peer HBM; up to 8 genomes. */
+int nts_p2p_reduce_and_of_or(nts_p2p* const* sets, uint32_t n_sets, nts_p2p* out);
 /* all-gather of minimizer tables (ncclAllGather over padded columns): out[r] = rank r's table, as a
  * new nts_mxs on this rank; counts[world] must hold every rank's table size. */
 int nts_mxs_allgather(nts_comm* comm, const nts_mxs* mine, const uint64_t* counts, nts_mxs** out);
@@ -267,6 +273,11 @@ int nts_graph_lookup(nts_graph* g, const uint64_t* h1, uint64_t n, uint32_t* vid
  * assemblies (weight = popcount, all assembly weights are 1: bin/ntsynt_synteny.py:32). */
 int nts_graph_edges(nts_graph* g, uint64_t* n_edges);
 int nts_graph_download_edges(nts_graph* g, uint32_t* u, uint32_t* v, uint32_t* support);
+/* row range [off[c], off[c+1]) of every contig of a table (off has n_contigs + 1 entries); a new table made of row
+ * ranges of other tables in the given order -- used to put the tables of a contig-sharded sketch back in contig order */
+int nts_mxs_contig_offsets(nts_mxs* m, uint32_t n_contigs, uint64_t* off);
+int nts_mxs_concat(nts_ctx* ctx, nts_mxs* const* parts, const uint64_t* src_off, const uint64_t* cnt, uint64_t n_parts,
+                   nts_mxs** out);
 /* ---- lean form of the graph stage: the O(V) columns stay on the device, the host asks for what it walks ---------
  * nts_graph_gather: columns at the n vertex ids idx (what: 0 h1 -> u64[n]; 1 pos -> i64[n_asm x n]; 2 contig ->
  * i32[n_asm x n]; 3 rank -> u32[n_asm x n]; 4 inv = vertex at rank idx -> u32[n_asm x n]); ids outside [0, V) give 0. */

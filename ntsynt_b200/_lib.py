@@ -106,6 +106,9 @@ _SIGS = {
     "nts_p2p_close": (None, [vp]),
     "nts_p2p_reduce_scatter": (C.c_int, [vp, C.c_int]),
     "nts_p2p_all_gather": (C.c_int, [vp]),
+    "nts_p2p_reduce_and_of_or": (C.c_int, [vpp, C.c_uint32, vp]),
+    "nts_mxs_contig_offsets": (C.c_int, [vp, C.c_uint32, u64p]),
+    "nts_mxs_concat": (C.c_int, [vp, vpp, u64p, u64p, C.c_uint64, vpp]),
     "nts_mxs_allgather": (C.c_int, [vp, vp, u64p, vpp]),
     "nts_graph_build": (C.c_int, [vp, vpp, C.c_uint32, C.c_uint32, vpp]),
     "nts_graph_destroy": (None, [vp]),

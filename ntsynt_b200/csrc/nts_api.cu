@@ -1135,3 +1135,66 @@ extern "C" int nts_mxs_upload(nts_ctx* ctx, uint64_t n, const uint64_t* h1, cons
     *out = m;
     return NTS_OK;
 }
+
+namespace nts {
+// first row of every contig in a table sorted by (contig, position): off[c] = lower_bound(contig[], c)
+__global__ void mxs_contig_offsets_kernel(const uint32_t* __restrict__ contig, uint64_t n, uint32_t n_contigs, uint64_t* __restrict__ off)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_contigs) return;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (contig[mid] < c) lo = mid + 1; else hi = mid; }
+    off[c] = lo;
+}
+}  // namespace nts
+
+/* off[n_contigs + 1]: row range [off[c], off[c+1]) of every contig of a table in (contig, position) order */
+extern "C" int nts_mxs_contig_offsets(nts_mxs* m, uint32_t n_contigs, uint64_t* off)
+{
+    if (!m || !off) return nts::fail(NTS_ERR_ARG, "null argument");
+    nts_ctx* ctx = m->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    if (!m->count) { for (uint32_t c = 0; c <= n_contigs; ++c) off[c] = 0; return NTS_OK; }
+    nts::DevBuf<uint64_t> d;
+    if (d.alloc(n_contigs + 1) != cudaSuccess) return nts::fail(NTS_ERR_NOMEM, "device allocation failed");
+    nts::mxs_contig_offsets_kernel<<<(n_contigs + 1 + 127) / 128, 128, 0, ctx->stream>>>(m->contig.p, m->count, n_contigs, d.p);
+    ctx->launches++;
+    NTS_CUDA(cudaGetLastError());
+    NTS_CUDA(nts::copy_d2h(ctx, off, d.p, (size_t)(n_contigs + 1) * 8));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+/* A new table made of row ranges [src_off[i], src_off[i] + cnt[i]) of parts[i], in the given order (contig-sharded
+ * runs: every contig of a genome was sketched on the rank that owns it; the pieces are put back in contig order). */
+extern "C" int nts_mxs_concat(nts_ctx* ctx, nts_mxs* const* parts, const uint64_t* src_off, const uint64_t* cnt, uint64_t n_parts,
+                              nts_mxs** out)
+{
+    if (!ctx || !out || (n_parts && (!parts || !src_off || !cnt))) return nts::fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n_parts; ++i) {
+        if (!parts[i] || parts[i]->ctx != ctx || src_off[i] + cnt[i] > parts[i]->count) return nts::fail(NTS_ERR_ARG, "bad part");
+        total += cnt[i];
+    }
+    nts_mxs* m = new (std::nothrow) nts_mxs();
+    if (!m) return nts::fail(NTS_ERR_NOMEM, "host allocation failed");
+    m->ctx = ctx; m->count = total;
+    const uint64_t a = total ? total : 1;
+    if (m->h1.alloc(a) != cudaSuccess || m->pos.alloc(a) != cudaSuccess || m->contig.alloc(a) != cudaSuccess) {
+        delete m;
+        return nts::fail(NTS_ERR_NOMEM, "device allocation failed (minimizer table)");
+    }
+    uint64_t at = 0;
+    for (uint64_t i = 0; i < n_parts; ++i) {
+        if (!cnt[i]) continue;
+        cudaError_t e = cudaMemcpyAsync(m->h1.p + at, parts[i]->h1.p + src_off[i], cnt[i] * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(m->pos.p + at, parts[i]->pos.p + src_off[i], cnt[i] * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(m->contig.p + at, parts[i]->contig.p + src_off[i], cnt[i] * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) { delete m; return nts::fail(NTS_ERR_CUDA, cudaGetErrorString(e)); }
+        at += cnt[i];
+    }
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = m;
+    return NTS_OK;
+}

@@ -51,6 +51,33 @@ __global__ void p2p_gather_slice_kernel(uint4* __restrict__ mine, const uint4* _
     for (; i < n16; i += stride) mine[off16 + i] = peer[off16 + i];
 }
 
+// Contig-sharded ownership: every rank holds, per genome g, the bits of ITS contigs of g.
+// common = AND over genomes of (OR over ranks of those partial filters): rank r produces slice r of `out` reading
+// slice r of every (genome, rank) partial array straight from peer HBM -- the cascade of
+// src/ntsynt_make_common_bf.cpp:136-160 and the cross-GPU merge in one kernel.
+constexpr int P2P_MAX_SETS = 8;
+struct MultiPtrs { const uint4* p[P2P_MAX_SETS][P2P_MAX_RANKS]; };
+
+__global__ void p2p_and_of_or_kernel(uint4* __restrict__ out, MultiPtrs mp, int n_sets, int world, uint64_t off16, uint64_t n16)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        uint4 acc = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        for (int g = 0; g < n_sets; ++g) {
+            uint4 v[P2P_MAX_RANKS];
+#pragma unroll
+            for (int p = 0; p < P2P_MAX_RANKS; ++p)
+                if (p < world) v[p] = mp.p[g][p][off16 + i];                    // all of a genome's loads in flight together
+            uint4 t = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int p = 0; p < P2P_MAX_RANKS; ++p)
+                if (p < world) { t.x |= v[p].x; t.y |= v[p].y; t.z |= v[p].z; t.w |= v[p].w; }
+            acc.x &= t.x; acc.y &= t.y; acc.z &= t.z; acc.w &= t.w;
+        }
+        out[off16 + i] = acc;
+    }
+}
+
 }  // namespace nts
 
 using namespace nts;
@@ -129,6 +156,34 @@ int nts_p2p_reduce_scatter(nts_p2p* p, int op)
         ProfScope prof(ctx, PROF_NCCL, (double)(n * 16) * (p->world - 1));
         p2p_reduce_slice_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(p->mine->words.p), pp, p->rank,
                                                                            p->world, off, n, op);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+    }
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+/* Contig-sharded merge, phase 1: slice `rank` of out->mine = AND over the n_sets genomes of (OR over ranks of slice
+ * `rank` of sets[g]'s filters).  sets[g] maps genome g's partial filter of every rank, `out` maps the common filter
+ * (its phase 2 is nts_p2p_all_gather(out)).  Call after a barrier that guarantees every partial filter is complete. */
+int nts_p2p_reduce_and_of_or(nts_p2p* const* sets, uint32_t n_sets, nts_p2p* out)
+{
+    if (!sets || !out || n_sets < 1 || n_sets > (uint32_t)P2P_MAX_SETS) return fail(NTS_ERR_ARG, "between 1 and 8 genome filter sets are supported");
+    nts_ctx* ctx = out->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    MultiPtrs mp;
+    memset(&mp, 0, sizeof(mp));
+    for (uint32_t g = 0; g < n_sets; ++g) {
+        if (!sets[g] || sets[g]->ctx != ctx || sets[g]->world != out->world || sets[g]->rank != out->rank || sets[g]->n16 != out->n16)
+            return fail(NTS_ERR_ARG, "filter sets disagree with the output set");
+        for (int r = 0; r < out->world; ++r) mp.p[g][r] = reinterpret_cast<const uint4*>(sets[g]->peer[r]);
+    }
+    uint64_t off, n;
+    slice_of(out, out->rank, &off, &n);
+    if (n) {
+        ProfScope prof(ctx, PROF_NCCL, (double)(n * 16) * (out->world - 1) * n_sets);
+        p2p_and_of_or_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(out->mine->words.p), mp, (int)n_sets,
+                                                                        out->world, off, n);
         ctx->launches++;
         NTS_CUDA(cudaGetLastError());
     }

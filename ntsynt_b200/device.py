@@ -189,6 +189,14 @@ class BloomFilter:
         check(lib.nts_bf_build_common(self._h, level._h if level is not None else None, arr, len(genomes), int(k)))
         return self
 
+    def build_from_and(self, filters):
+        "self = AND of the given filters (same size)"
+        self.clear()
+        self.ior(filters[0])
+        for f in filters[1:]:
+            self.iand(f)
+        return self
+
     def insert_repeats(self, scratch, genome, k):
         check(lib.nts_bf_insert_repeats(self._h, scratch._h, genome._h, int(k)))
 
@@ -254,6 +262,24 @@ class MinimizerTable:
 
     def __len__(self):
         return int(lib.nts_mxs_count(self._h))
+
+    def contig_offsets(self, n_contigs):
+        "off[n_contigs + 1]: rows [off[c], off[c+1]) belong to contig c"
+        off = np.zeros(n_contigs + 1, dtype=np.uint64)
+        check(lib.nts_mxs_contig_offsets(self._h, int(n_contigs), ptr(off, C.c_uint64)))
+        return off
+
+    @classmethod
+    def concat(cls, ctx, parts, src_off, cnt, genome=None):
+        "new table = rows [src_off[i], src_off[i] + cnt[i]) of parts[i], in order"
+        arr = (C.c_void_p * max(len(parts), 1))(*[t._h for t in parts])
+        so = np.ascontiguousarray(src_off, dtype=np.uint64)
+        cn = np.ascontiguousarray(cnt, dtype=np.uint64)
+        h = C.c_void_p()
+        z = np.zeros(1, dtype=np.uint64)
+        check(lib.nts_mxs_concat(ctx._h, arr, ptr(so if len(so) else z, C.c_uint64), ptr(cn if len(cn) else z, C.c_uint64),
+                                 len(parts), C.byref(h)))
+        return cls(ctx, h, genome)
 
     def to_numpy(self):
         n = len(self)

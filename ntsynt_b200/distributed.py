@@ -21,6 +21,19 @@ def owner_of(genome, world):
     return genome % world
 
 
+def assign_contigs(lengths, world):
+    """contig-sharded ownership (for fewer genomes than GPUs): longest-first greedy packing of the
+    contigs into `world` bins; returns [sorted contig ids per rank].  A k-mer lies inside one contig, so Bloom inserts
+    need no halo; a minimizer window never crosses a contig, so neither does the sketch."""
+    load = [0] * world
+    bins = [[] for _ in range(world)]
+    for c in sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i)):
+        r = min(range(world), key=lambda i: (load[i], i))
+        bins[r].append(c)
+        load[r] += int(lengths[c])
+    return [sorted(b) for b in bins]
+
+
 def field_bits(world):
     "counter width used by the all-reduce merge: smallest of 2/4/8 bits that can hold `world`"
     return 2 if world <= 3 else 4 if world <= 15 else 8
@@ -116,6 +129,66 @@ class PeerMerge:
             self.barrier()
             lib.nts_p2p_close(self._h)
             self._h = None
+
+
+class ShardedMerge:
+    """common = AND over genomes of (OR over ranks of the per-rank partial filters) over NVLink peer memory
+    (nts_p2p_reduce_and_of_or + nts_p2p_all_gather): the merge of a contig-sharded run.  `parts[g]` is this rank's
+    filter of its contigs of genome g, `common` receives the result on every rank."""
+
+    def __init__(self, parts, common, rank, world, gather, barrier):
+        self.parts, self.common, self.rank, self.world, self.barrier = parts, common, rank, world, barrier
+        self._sets, self._out = [], None
+        ok = True
+        for bf in list(parts) + [common]:
+            mine = (C.c_uint8 * 64)()
+            check(lib.nts_bf_ipc_handle(bf._h, mine))
+            handles = b"".join(gather(bytes(mine)))
+            buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+            h = C.c_void_p()
+            rc = lib.nts_p2p_open(bf._h, buf, int(rank), int(world), C.byref(h))
+            ok = ok and rc == 0
+            self._sets.append(h if rc == 0 else None)
+        self.ok = all(gather(ok))
+        if self.ok:
+            self._out = self._sets.pop()
+        else:
+            self.close()
+        barrier()
+
+    def merge(self, comm=None):
+        if comm is None:
+            self.common.ctx.sync()
+        sync = comm.barrier if comm is not None else self.barrier
+        sync()                               # every partial filter is complete
+        arr = (C.c_void_p * len(self._sets))(*self._sets)
+        check(lib.nts_p2p_reduce_and_of_or(arr, len(self._sets), self._out))
+        sync()                               # every slice of the common filter is reduced
+        check(lib.nts_p2p_all_gather(self._out))
+        sync()                               # nobody still reads my slice / my partial filters
+
+    def close(self):
+        for h in self._sets + [self._out]:
+            if h:
+                lib.nts_p2p_close(h)
+        self._sets, self._out = [], None
+
+
+def gather_sharded_table(comm, table, n_contigs, owner_of_contig, gather_objects, genome=None):
+    """every rank sketched its own contigs of one genome (empty records elsewhere, global contig numbering): all-gather
+    the tables and put the contigs back in order.  Returns the whole genome's table on this rank."""
+    off = table.contig_offsets(n_contigs)
+    info = gather_objects((len(table), off.tolist()))
+    tabs = comm.allgather_tables(table, [n for n, _ in info], [None] * comm.world)
+    parts, src, cnt = [], [], []
+    for c in range(n_contigs):
+        r = owner_of_contig[c]
+        o = info[r][1]
+        parts.append(tabs[r]); src.append(o[c]); cnt.append(o[c + 1] - o[c])
+    out = device.MinimizerTable.concat(comm.ctx, parts, src, cnt, genome)
+    for t in tabs:
+        t.close()
+    return out
 
 
 class GatheredBackend:

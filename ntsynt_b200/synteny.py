@@ -1192,6 +1192,9 @@ class SyntenyEngine:
         G = self.G
         # --- new minimizers from the masked assemblies (generate_additional_minimizers :532-541)
         masks = self._masks_for(blocks, prev_w)
+        # u_r of SURVEY 8d: the fraction of every assembly the masked round still has to sketch
+        self.stats.setdefault("unmasked", []).append(
+            [round(1.0 - sum(int((e - s).sum()) for s, e in masks[a]) / max(sum(self.be.contig_lengths[a]), 1), 6) for a in range(G)])
         self._tick("r_masks")
         new = []
         for a in range(G):

@@ -222,6 +222,14 @@ def genome_segments(anc_seed, genome_index, anc_lengths, anc_nruns, divergence_p
     return np.array(lengths, dtype=np.uint64), np.concatenate(rows)
 
 
+def _empty_packed(names):
+    from .fasta import PackedGenome
+    n = len(names)
+    z = np.zeros(0, dtype=np.uint64)
+    return PackedGenome(list(names), np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64), z, np.zeros(n + 1, dtype=np.uint64),
+                        z, z)
+
+
 class Workload:
     "G synthetic genomes derived from one ancestor"
 
@@ -244,9 +252,17 @@ class Workload:
                                             self.n_trans)
         return self._segs[g]
 
-    def materialize(self, ctx, g):
-        "genome g resident in HBM (device.DeviceGenome)"
+    def materialize(self, ctx, g, contigs=None):
+        """genome g resident in HBM (device.DeviceGenome).  contigs: only these contig indices are generated, the others
+        are kept as empty records so that contig numbering stays global (contig-sharded multi-GPU runs)"""
         lengths, segs = self.segments(g)
+        if contigs is not None:
+            own = np.zeros(len(lengths), dtype=bool)
+            own[np.asarray(list(contigs), dtype=np.int64)] = True
+            lengths = np.where(own, lengths, 0).astype(np.uint64)
+            segs = np.ascontiguousarray(segs[own[segs["dst_contig"]]])
+            if not len(segs):                       # a rank that owns nothing of this genome still needs a valid object
+                return device.DeviceGenome(ctx, _empty_packed(self.names))
         h = C.c_void_p()
         check(lib.nts_genome_synthesize(ctx._h, len(lengths), lengths.ctypes.data_as(C.POINTER(C.c_uint64)),
                                         segs.ctypes.data_as(C.POINTER(SynthSeg)), len(segs), self.seed,

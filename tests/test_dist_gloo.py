@@ -63,3 +63,15 @@ def test_gloo_world2(tmp_path):
                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]
     assert res.stdout.count("ok") >= 2
+
+
+def test_assign_contigs_covers_everything_and_balances():
+    "contig-sharded ownership (SURVEY 8e P2): every contig has exactly one owner; human-like sizes balance within ~15 %"
+    from ntsynt_b200 import distributed, synth
+    lens = synth.ancestor_layout(3_000_000_000)
+    for world in (1, 2, 3, 4, 8):
+        own = distributed.assign_contigs(lens, world)
+        assert sorted(c for b in own for c in b) == list(range(len(lens)))
+        load = [sum(int(lens[c]) for c in b) for b in own]
+        assert max(load) <= 1.15 * sum(load) / world
+    assert distributed.assign_contigs([5, 1, 1], 8)[0] == [0]          # more ranks than contigs: some own nothing

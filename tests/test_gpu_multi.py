@@ -75,3 +75,91 @@ def test_nccl_merge_and_allgather(tmp_path):
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:]
     assert res.stdout.count("ok") >= 2
+
+
+SHARD_WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    sys.path.insert(0, {root!r})
+    import bench
+    from ntsynt_b200 import device, distributed, pipeline, synth
+    d = bench.Dist()
+    ctx = device.Context(d.local_rank)
+    G, k, w = 3, 24, 1000
+    wl = synth.Workload(G, 20_000_000, 1.3, n_contigs=6)
+    whole = [wl.materialize(ctx, g) for g in range(G)]
+    nbytes = device.BloomFilter.size_for(whole[0].total_bases, 0.025)
+    ref = pipeline.build_common_bf(ctx, whole, [wl.file_name(g) for g in range(G)], k, nbytes=nbytes)
+    own = distributed.assign_contigs(wl.anc_lengths, d.world)
+    assert sorted(c for b in own for c in b) == list(range(6))
+    owner = [next(r for r in range(d.world) if c in own[r]) for c in range(6)]
+    shards = [wl.materialize(ctx, g, contigs=own[d.rank]) for g in range(G)]
+    for g in range(G):                      # a shard holds exactly its contigs, bit for bit, and nothing else
+        for c in range(6):
+            if c in own[d.rank]:
+                assert np.array_equal(shards[g].contig_words(c), whole[g].contig_words(c))
+            else:
+                assert int(shards[g].lengths[c]) == 0
+    parts = [ctx.bloom(nbytes) for _ in range(G)]
+    common = ctx.bloom(nbytes)
+    common.from_numpy(np.full(nbytes, 0x5A, dtype=np.uint8))
+    ident = distributed.Comm.new_unique_id() if d.rank == 0 else b""
+    comm = distributed.Comm(ctx, d.rank, d.world, d.bcast_bytes(ident, 128))
+    sm = distributed.ShardedMerge(parts, common, d.rank, d.world, d.gather_objects, d.barrier)
+    assert sm.ok
+    for rep in range(2):
+        for g in range(G):
+            parts[g].set_genome(shards[g], k)
+        sm.merge(comm=comm if rep else None)
+        assert np.array_equal(common.to_numpy(), ref.to_numpy()), "AND_g OR_rank over peer memory != single-GPU filter"
+    sm.close()
+    # the north-star form: one counter all-reduce per genome, AND locally
+    for g in range(G):
+        parts[g].set_genome(shards[g], k)
+        comm.allreduce_or(parts[g])
+    nccl = ctx.bloom(nbytes).build_from_and(parts)
+    assert np.array_equal(nccl.to_numpy(), ref.to_numpy()), "NCCL OR per genome + AND != single-GPU filter"
+    for g in range(G):
+        t = ctx.sketch(shards[g], k, w, common=common)
+        full = distributed.gather_sharded_table(comm, t, 6, owner, d.gather_objects)
+        want = ctx.sketch(whole[g], k, w, common=ref).to_numpy()
+        assert all(np.array_equal(x, y) for x, y in zip(want, full.to_numpy())), "contig-sharded sketch differs"
+    comm.close(); d.barrier(); d.close()
+    print("rank", d.rank, "ok")
+""")
+
+
+def _torchrun(script, port, n=2, timeout=900):
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                           "--master-addr", "127.0.0.1", "--master-port", str(port), *script],
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+
+
+def test_contig_sharded_merge_and_sketch(tmp_path):
+    "SURVEY 8e P2: contigs of every genome spread over the ranks; AND over genomes of OR over ranks; sketch by owner"
+    if device.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(SHARD_WORKER.format(root=ROOT))
+    res = _torchrun([str(script)], 29571)
+    assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
+    assert res.stdout.count("ok") >= 2
+
+
+@pytest.mark.parametrize("flags", [["--genomes", "3", "--divergence", "1.3"], ["--genomes", "2", "--divergence", "1"]])
+def test_bench_block_table_is_the_same_on_one_and_two_gpus(flags):
+    "bench.py prints a sha1 of the final block table: contig-sharded (G = 3) and one-genome-per-GPU (G = 2) runs == 1 GPU"
+    if device.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import json
+    common = [os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu", "--genome-mbp", "40", *flags]
+    one = subprocess.run([sys.executable, *common, "--gpus", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         timeout=900)
+    assert one.returncode == 0, one.stderr[-3000:]
+    two = _torchrun([*common, "--gpus", "2"], 29573)
+    assert two.returncode == 0, two.stderr[-3000:]
+    a = json.loads(one.stdout.strip().splitlines()[-1])
+    b = json.loads(two.stdout.strip().splitlines()[-1])
+    assert a["config"]["blocks"] > 0
+    assert a["config"]["blocks_sha1"] == b["config"]["blocks_sha1"]
+    assert a["config"]["vertices"] == b["config"]["vertices"]
