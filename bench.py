@@ -165,13 +165,17 @@ def sha1_text(text):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_sample_records(gens, sample_mbp_per_genome):
-    "first slice of every contig of every genome, as ASCII records (host copies of device genomes)"
-    out = []
-    for g in gens:
-        per = max(int(sample_mbp_per_genome * 1e6 / g.n_contigs), 20000)
-        out.append([(g.names[c], g.contig_ascii(c, 0, per)) for c in range(g.n_contigs)])
-    return out
+def cpu_sample_records(layout, G, sample_mbp_per_genome):
+    """first slice of every contig of every genome, as ASCII records, written by the oracle's own statement of the
+    workload generator (oracle/synth_oracle.c) -- the CPU arm never touches the CUDA library"""
+    from oracle import sketch_oracle as so
+    per = max(int(sample_mbp_per_genome * 1e6 / len(layout.names)), 20000)
+    return [so.synth_records(layout, g, per_contig=per) for g in range(G)]
+
+
+def cpu_sample_mbp(args, G):
+    "per-genome CPU sample: --cpu-sample-mbp for 2 genomes, scaled so that the whole sample (and its run time) stays the same"
+    return args.cpu_sample_mbp * 2.0 / max(G, 2)
 
 
 def cpu_path(records_per_genome, file_names, divergence, threads):
@@ -240,12 +244,12 @@ def cpu_path(records_per_genome, file_names, divergence, threads):
     return dt, total, text
 
 
-def ingest_probe(gen, sample_mbp):
+def ingest_probe(layout, sample_mbp):
     """FASTA ingest, reported separately from the path: the first slice of every contig of one genome as
     60-column FASTA text in memory -> ntsynt_b200.fasta.parse_fasta_bytes (native scan + multi-threaded 2-bit pack)"""
     import numpy as np
     from ntsynt_b200 import fasta
-    recs = cpu_sample_records([gen], sample_mbp)[0]
+    recs = cpu_sample_records(layout, 1, sample_mbp)[0]
     parts = []
     for name, seq in recs:
         n = len(seq) - len(seq) % 60
@@ -408,12 +412,13 @@ def run_ours(args, dist):
     cpu = None
     if dist.rank == 0 and N == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        recs = cpu_sample_records(gen_list, args.cpu_sample_mbp)
+        smbp = cpu_sample_mbp(args, G)
+        recs = cpu_sample_records(wl, G, smbp)
         dt, tot, _ = cpu_path(recs, file_names, d, threads)
         cpu = {"value": tot / dt, "unit": "bp/s", "cores": threads, "kind": "port",
-               "sample": f"first {args.cpu_sample_mbp:g} Mbp of each of the {G} genomes ({tot} bp): oracle/ C+OpenMP "
+               "sample": f"first {smbp:g} Mbp of each of the {G} genomes ({tot} bp): oracle/ C+OpenMP "
                          f"Bloom filter and sketch, pure-Python graph stage; {dt:.1f} s"}
-    ingest = ingest_probe(gen_list[0], 120.0) if (dist.rank == 0 and N == 1 and not args.no_cpu) else None
+    ingest = ingest_probe(wl, 120.0) if (dist.rank == 0 and N == 1 and not args.no_cpu) else None
     line = {
         "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -766,38 +771,40 @@ def run_ours_sharded(args, dist, ctx):
     comm.close()
 
 def run_reference(args, dist):
-    "CPU restatement of the reference path on a bounded sample of the same workload (rank 0 only)"
+    """CPU restatement of the reference path on a bounded sample of the same workload (rank 0 only).  Nothing of the
+    product is imported here: the sample comes from oracle/synth_oracle.c over ntsynt_b200/synth_layout.py (pure numpy),
+    the path from oracle/ntsynt_oracle.c and oracle/graph_oracle.py."""
     if dist.rank != 0:
         return
-    from ntsynt_b200 import device, synth
+    from ntsynt_b200 import synth_layout
     N = dist.world
     G = args.genomes or (2 if N == 1 else N)
     d = args.divergence
-    ctx = device.Context(dist.local_rank)
-    wl = synth.Workload(G, int(args.genome_mbp * 1e6), d, seed=args.seed)
-    gens = [wl.materialize(ctx, g) for g in range(G)]
-    recs = cpu_sample_records(gens, args.cpu_sample_mbp)
-    for g in gens:
-        g.close()
-    ctx.close()
-    file_names = [wl.file_name(g) for g in range(G)]
+    lay = synth_layout.Layout(G, int(args.genome_mbp * 1e6), d, seed=args.seed)
+    smbp = cpu_sample_mbp(args, G)
+    recs = cpu_sample_records(lay, G, smbp)
+    file_names = [lay.file_name(g) for g in range(G)]
     threads = os.cpu_count() or 1
     for _ in range(args.warmup):
         cpu_path(recs, file_names, d, threads)
     t = 0.0
     for _ in range(args.steps):
-        dt, tot, _ = cpu_path(recs, file_names, d, threads)
+        dt, tot, text = cpu_path(recs, file_names, d, threads)
         t += dt
     v = tot * args.steps / t
-    sample = (f"first {args.cpu_sample_mbp:g} Mbp of each of the {G} genomes ({tot} bp) per step; oracle/ C+OpenMP "
-              f"Bloom filter + sketch and pure-Python graph stage (btllib / python-igraph are not installable)")
+    sample = (f"first {smbp:g} Mbp of each of the {G} genomes ({tot} bp) per step -- a bp/s extrapolation, not a same-size "
+              f"run (the filter is sized for the sample); oracle/ C+OpenMP Bloom filter + sketch with the reference's "
+              f"threading structure and pure-Python graph stage (btllib / python-igraph are not installable); the "
+              f"per-k-mer substr of indexlr --seq is not charged to this arm")
     ps = presets(d)
+    assert "ntsynt_b200._lib" not in sys.modules, "the reference arm must not load the CUDA library"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "bp/s", "n_gpus": N, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": f"{G} synthetic ~{args.genome_mbp:g} Mbp human-like genomes, d={d:g}, k={K} w={W}, "
-                               f"w_rounds {ps['w_rounds']} (bounded sample)", "genomes": G, "k": K, "w": W},
+                               f"w_rounds {ps['w_rounds']} (bounded sample)", "genomes": G, "k": K, "w": W,
+                   "sample_bp": tot, "blocks_sha1_of_sample": sha1_text(text)},
         "cpu_baseline": {"value": v, "unit": "bp/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -814,7 +821,8 @@ def main():
     ap.add_argument("--divergence", type=float, default=1.0)
     ap.add_argument("--seed", type=int, default=20260117)
     ap.add_argument("--cpu-sample-mbp", type=float, default=192.0,
-                    help="per-genome sample for the CPU arm (192 Mbp x 2 genomes is ~12 s of CPU work on 16 cores)")
+                    help="per-genome sample for the CPU arm at 2 genomes (192 Mbp x 2 is ~12 s of CPU work on 16 cores); "
+                         "with G genomes each gets 2/G of it, so the arm costs the same at every N")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--shard", choices=["genome", "contig"], default=None,

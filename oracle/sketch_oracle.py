@@ -18,8 +18,8 @@ _LIB = None
 def build(force=False):
     "Compile libntsynt_oracle.so with the committed Makefile (gcc, no reference sources involved)."
     so = os.path.join(_HERE, "libntsynt_oracle.so")
-    src = os.path.join(_HERE, "ntsynt_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("ntsynt_oracle.c", "synth_oracle.c", "Makefile")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", _HERE, "clean", "all"], stdout=subprocess.DEVNULL)
     return so
 
@@ -50,6 +50,8 @@ def lib():
         L.orc_sketch_records.argtypes = [C.POINTER(cp), C.POINTER(sz), C.c_int, C.c_uint, C.c_uint, u8p, u64,
                                          C.POINTER(u64p), C.POINTER(u64p), C.POINTER(sz), C.POINTER(sz), C.c_int]
         L.orc_max_threads.restype = C.c_int
+        L.orc_synth_contig.restype = None
+        L.orc_synth_contig.argtypes = [C.c_void_p, sz, C.c_uint32, u64, u64, u64, C.c_double, C.c_uint32, C.c_double, C.c_char_p]
         _LIB = L
     return _LIB
 
@@ -183,3 +185,21 @@ def write_sketch_tsv(path, records, k, w, common=None, repeat=None):
     with open(path, "w", encoding="utf-8") as out:
         for line in sketch_tsv_lines(records, k, w, common, repeat):
             out.write(line)
+
+
+def synth_records(layout, g, per_contig=None):
+    """ASCII records of synthetic genome g (SURVEY 8d workload; oracle/synth_oracle.c), from a workload layout object
+    with .names, .seed, .d, .n_repeat_fam, .repeat_slot_prob and .segments(g) (ntsynt_b200.synth_layout based).
+    per_contig: only the first that many bases of every contig."""
+    lengths, segs = layout.segments(g)
+    out = []
+    for c, name in enumerate(layout.names):
+        sel = np.ascontiguousarray(segs[segs["dst_contig"] == c])
+        n = int(lengths[c]) if per_contig is None else min(int(per_contig), int(lengths[c]))
+        buf = C.create_string_buffer(max(n, 1))
+        if n:
+            lib().orc_synth_contig(sel.ctypes.data_as(C.c_void_p), len(sel), c, n, int(layout.seed),
+                                   int(layout.seed) * 1000003 + g + 1, float(layout.d) / 200.0, int(layout.n_repeat_fam),
+                                   float(layout.repeat_slot_prob), buf)
+        out.append((name, buf.raw[:n]))
+    return out

@@ -142,3 +142,18 @@ def test_native_graph_walks_on_tiny_inputs():
                                 ctg.ctypes.data_as(C.POINTER(C.c_int32)), 5, 5, 2, ptr(bs, C.c_int64), ptr(bt, C.c_int64),
                                 ptr(rm, C.c_int64), 16, C.byref(n_out)))
     assert n_out.value == 0
+
+
+def test_reference_arm_runs_without_the_cuda_library():
+    "bench.py --impl reference: oracle-made sample + oracle path; the product library is never loaded (bench.py asserts it)"
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--genome-mbp", "60", "--cpu-sample-mbp", "6"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0

@@ -382,3 +382,18 @@ def test_presets_cuda_path_equals_reference_made_fixture(cuda_ctx, tag):
                                    block_size=p["block_size"], write_files=False, ctx=cuda_ctx, packed=packed)
     assert out == pc.expected(tag)
     assert eng.outputs["pre_merge"] == pc.expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
+
+
+def test_oracle_generator_equals_device_genome(cuda_ctx):
+    "the CPU arm's sample (oracle/synth_oracle.c) is the same workload the GPU arm materialises: base for base, Ns included"
+    from ntsynt_b200 import synth_layout
+    wl = synth.Workload(2, 3_000_000, 1.3, n_contigs=5)
+    lay = synth_layout.Layout(2, 3_000_000, 1.3, n_contigs=5)
+    for g in range(2):
+        dev = wl.materialize(cuda_ctx, g)
+        recs = so.synth_records(lay, g)
+        assert [n for n, _ in recs] == dev.names
+        for c, (_, seq) in enumerate(recs):
+            assert seq == dev.contig_ascii(c), (g, c)
+        part = so.synth_records(lay, g, per_contig=12345)
+        assert all(p[1] == r[1][:12345] for p, r in zip(part, recs))
