@@ -296,6 +296,22 @@ int nts_graph_download_links_nbr(nts_graph* g, uint64_t cap, int32_t* nbr, uint8
  * (i, i+1) (val 1 = edge present) back to the device's link bitmap first. */
 int nts_graph_set_links(nts_graph* g, const int64_t* idx, const uint8_t* val, uint64_t n);
 int nts_graph_runs(nts_graph* g, int64_t* starts, int64_t* ends, uint64_t* n_runs);
+/* One refinement round's minimizer filtering on the device, for the new (masked, smaller-w) tables of all assemblies:
+ *   read_minimizers' duplicate removal (subprojects/ntJoin/bin/ntjoin_utils.py:182-192), find_mx_in_blocks +
+ *   filter_minimizers_synteny_blocks (bin/ntsynt_synteny.py:205-280: drop the blocks' internal minimizers and the ones
+ *   inside a block interval, start a new sub-list where the span from the previous kept minimizer overlaps a block)
+ *   and filter_minimizers (ntjoin_utils.py:152-165: keep the keys that survive in every assembly).
+ * Host inputs (small): the blocks' vertex segments (seg_lo / seg_hi ascending, disjoint), their terminal vertices
+ * (ascending), the vertices added after round 0 (x_key ascending with x_vid), and per assembly a the block intervals
+ * iv_start[iv_off[a] .. iv_off[a+1]) ascending with iv_maxend their running maximum end (coordinate = contig << 40 | pos).
+ * Outputs: n_raw[a] = entries of assembly a after duplicate removal; the surviving (h1, pos, ctg, sub-list id) of
+ * assembly a at [out_off[a], out_off[a+1]) of the out_* arrays (out_cap entries in all; if out_off[n_asm] > out_cap only
+ * out_off is valid -- call again with larger arrays). */
+int nts_graph_refine_filter(nts_graph* g, nts_mxs* const* tables, const uint32_t* seg_lo, const uint32_t* seg_hi, uint32_t n_seg,
+                            const uint32_t* term, uint32_t n_term, const uint64_t* x_key, const uint32_t* x_vid, uint32_t n_x,
+                            const long long* iv_start, const long long* iv_maxend, const uint64_t* iv_off, uint64_t* n_raw,
+                            uint64_t* out_off, uint64_t* out_h1, uint32_t* out_pos, uint32_t* out_ctg, uint32_t* out_sub,
+                            uint64_t out_cap);
 /* number of pairs (i, i+1) whose |dpos| spread exceeds bp */
 int nts_graph_big_count(nts_graph* g, uint32_t bp, uint64_t* n_big);
 /* Kernel (iv-c), collinear-path extraction on the device, for the n_runs runs [starts[i], ends[i]] of base vertices

@@ -137,6 +137,8 @@ _SIGS = {
     "nts_graph_download_links_nbr": (C.c_int, [vp, C.c_uint64, C.POINTER(C.c_int32), u8p]),
     "nts_graph_set_links": (C.c_int, [vp, i64p, u8p, C.c_uint64]),
     "nts_graph_runs": (C.c_int, [vp, i64p, i64p, u64p]),
+    "nts_graph_refine_filter": (C.c_int, [vp, vpp, u32p, u32p, C.c_uint32, u32p, C.c_uint32, u64p, u32p, C.c_uint32, i64p, i64p, u64p,
+                                          u64p, u64p, u64p, u32p, u32p, u32p, C.c_uint64]),
     "nts_graph_big_count": (C.c_int, [vp, C.c_uint32, u64p]),
     "nts_graph_runs_to_blocks": (C.c_int, [vp, i64p, i64p, C.c_uint64, C.c_uint32, C.c_double, C.c_uint32, u32p, u32p, u32p,
                                            C.POINTER(C.c_int8), u32p, u32p, u32p, u64p, C.c_uint64]),

@@ -393,6 +393,123 @@ __global__ void set_links_kernel(uint8_t* __restrict__ link, uint64_t V, const i
     if (t < n && idx[t] >= 0 && (uint64_t)idx[t] < V) link[idx[t]] = val[t];
 }
 
+// ---- refinement rounds on the device (bin/ntsynt_synteny.py:205-280 + ntjoin_utils.py:152-193 for the new minimizers)
+// One hash table keyed by h1 over the new tables of all assemblies: seen / dup masks give read_minimizers' duplicate
+// removal, a `kept` mask gives the G-way intersection after the block filter.
+struct RefineCtx {
+    const uint32_t* seg_lo; const uint32_t* seg_hi; uint32_t n_seg;       // block segments, ascending, disjoint
+    const uint32_t* term; uint32_t n_term;                                 // terminal vertices, ascending
+    const uint64_t* x_key; const uint32_t* x_vid; uint32_t n_x;            // vertices added after round 0, by key
+    const unsigned long long* g_keys; const uint32_t* g_slot_vid; uint64_t g_mask;   // the join table of the graph
+};
+
+__device__ __forceinline__ uint32_t refine_vid(const RefineCtx& c, uint64_t key)
+{
+    uint32_t res = 0xFFFFFFFFu;
+    if (key == HT_EMPTY) res = c.g_slot_vid[c.g_mask + 1];
+    else {
+        uint64_t slot = mix64(key) & c.g_mask;
+        for (;;) {
+            const unsigned long long cur = c.g_keys[slot];
+            if (cur == key) { res = c.g_slot_vid[slot]; break; }
+            if (cur == HT_EMPTY) break;
+            slot = (slot + 1) & c.g_mask;
+        }
+    }
+    if (res == 0xFFFFFFFFu && c.n_x) {
+        uint32_t lo = 0, hi = c.n_x;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (c.x_key[mid] < key) lo = mid + 1; else hi = mid; }
+        if (lo < c.n_x && c.x_key[lo] == key) res = c.x_vid[lo];
+    }
+    return res;
+}
+
+// exists an interval [s, e) with s < b and a < e  (starts ascending, maxend = running maximum of the ends)
+__device__ __forceinline__ bool interval_hit(const long long* __restrict__ starts, const long long* __restrict__ maxend, uint32_t n,
+                                             long long a, long long b)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (starts[mid] < b) lo = mid + 1; else hi = mid; }
+    return lo > 0 && maxend[lo - 1] > a;
+}
+
+// pass 2: keep[i] = not duplicated in its file, not an internal vertex of a block, not inside a block interval
+__global__ void refine_keep_kernel(const uint64_t* __restrict__ h1, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ ctg,
+                                   const uint32_t* __restrict__ slot_of, uint64_t n, uint32_t a, const uint32_t* __restrict__ dup,
+                                   uint32_t* __restrict__ kept_mask, RefineCtx c, const long long* __restrict__ iv_start,
+                                   const long long* __restrict__ iv_maxend, uint32_t n_iv, uint32_t* __restrict__ keep,
+                                   unsigned int* __restrict__ n_raw)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = 0;
+    if (!(dup[slot_of[i]] & (1u << a))) {
+        atomicAdd(n_raw, 1u);
+        const uint32_t vid = refine_vid(c, h1[i]);
+        bool internal = false;
+        if (vid != 0xFFFFFFFFu && c.n_seg) {
+            uint32_t lo = 0, hi = c.n_seg;                       // last segment with seg_lo <= vid
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (c.seg_lo[mid] <= vid) lo = mid + 1; else hi = mid; }
+            if (lo > 0 && c.seg_hi[lo - 1] >= vid) {
+                internal = true;
+                uint32_t tl = 0, th = c.n_term;
+                while (tl < th) { const uint32_t mid = (tl + th) >> 1; if (c.term[mid] < vid) tl = mid + 1; else th = mid; }
+                if (tl < c.n_term && c.term[tl] == vid) internal = false;
+            }
+        }
+        const long long key = ((long long)ctg[i] << 40) + (long long)pos[i];
+        const bool inside = n_iv && interval_hit(iv_start, iv_maxend, n_iv, key, key + 1);
+        k = (!internal && !inside) ? 1u : 0u;
+        if (k) atomicOr(&kept_mask[slot_of[i]], 1u << a);
+    }
+    keep[i] = k;
+}
+
+// compact the kept entries (order preserved)
+__global__ void refine_compact_kernel(const uint64_t* __restrict__ h1, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ ctg,
+                                      const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ keep,
+                                      const uint32_t* __restrict__ off, uint64_t n, uint64_t* __restrict__ o_h1,
+                                      uint32_t* __restrict__ o_pos, uint32_t* __restrict__ o_ctg, uint32_t* __restrict__ o_slot)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const uint32_t o = off[i];
+    o_h1[o] = h1[i]; o_pos[o] = pos[i]; o_ctg[o] = ctg[i]; o_slot[o] = slot_of[i];
+}
+
+// over the kept list: cut[i] = a new sub-list starts at i (first entry, contig change, or the span from the previous
+// kept minimizer overlaps a block interval); fin[i] = the key is kept in every assembly
+__global__ void refine_cut_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ ctg, const uint32_t* __restrict__ slot,
+                                  uint64_t n, const uint32_t* __restrict__ kept_mask, uint32_t full,
+                                  const long long* __restrict__ iv_start, const long long* __restrict__ iv_maxend, uint32_t n_iv,
+                                  uint32_t* __restrict__ cut, uint32_t* __restrict__ fin)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = 1;
+    if (i > 0 && ctg[i] == ctg[i - 1]) {
+        const long long a = ((long long)ctg[i - 1] << 40) + (long long)pos[i - 1];
+        const long long b = ((long long)ctg[i] << 40) + (long long)pos[i];
+        c = (n_iv && interval_hit(iv_start, iv_maxend, n_iv, a, b)) ? 1u : 0u;
+    }
+    cut[i] = c;
+    fin[i] = kept_mask[slot[i]] == full ? 1u : 0u;
+}
+
+// final compaction: (h1, pos, ctg, sub = inclusive prefix of cut - 1) of the kept entries whose key is common
+__global__ void refine_emit_kernel(const uint64_t* __restrict__ h1, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ ctg,
+                                   const uint32_t* __restrict__ cut, const uint32_t* __restrict__ cut_excl,
+                                   const uint32_t* __restrict__ fin, const uint32_t* __restrict__ fin_off, uint64_t n,
+                                   uint64_t* __restrict__ o_h1, uint32_t* __restrict__ o_pos, uint32_t* __restrict__ o_ctg,
+                                   uint32_t* __restrict__ o_sub)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !fin[i]) return;
+    const uint32_t o = fin_off[i];
+    o_h1[o] = h1[i]; o_pos[o] = pos[i]; o_ctg[o] = ctg[i];
+    o_sub[o] = cut_excl[i] + cut[i] - 1;
+}
+
 // first index of the sorted list with value >= x
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t x)
 {
@@ -1036,6 +1153,144 @@ int nts_graph_runs(nts_graph* g, int64_t* starts, int64_t* ends, uint64_t* n_run
         NTS_CUDA(cudaStreamSynchronize(ctx->stream));
         for (uint64_t i = 0; i < g->n_runs; ++i) { starts[i] = hs[i]; ends[i] = he[i]; }
     }
+    return NTS_OK;
+}
+
+
+/* One refinement round's minimizer filtering on the device, for the new tables of all assemblies at once:
+ *   read_minimizers        drop every h1 seen more than once in its file      (ntjoin_utils.py:182-192)
+ *   filter_minimizers_synteny_blocks  drop the internal minimizers of the blocks and the ones inside a block interval,
+ *                          start a new sub-list where the span from the previous kept minimizer overlaps a block
+ *                                                                              (bin/ntsynt_synteny.py:205-280)
+ *   filter_minimizers      keep the keys that survive in every assembly       (ntjoin_utils.py:152-165)
+ * Inputs (host, small): the blocks' segments (seg_lo/seg_hi, ascending, disjoint) and terminal vertices (ascending);
+ * the vertices added after round 0 (x_key ascending, x_vid); per assembly a the block intervals
+ * iv_start[iv_off[a] .. iv_off[a+1]) ascending with iv_maxend their running maximum end (coordinates contig << 40 | pos).
+ * Outputs per assembly: n_raw[a] (entries after duplicate removal), and the surviving (h1, pos, ctg, sub-list id),
+ * assembly a at out_off[a] .. out_off[a+1) of the out_* arrays (capacity out_cap entries in total; if the total
+ * exceeds it only out_off is valid).  n_common = number of distinct surviving keys. */
+int nts_graph_refine_filter(nts_graph* g, nts_mxs* const* tables, const uint32_t* seg_lo, const uint32_t* seg_hi, uint32_t n_seg,
+                            const uint32_t* term, uint32_t n_term, const uint64_t* x_key, const uint32_t* x_vid, uint32_t n_x,
+                            const long long* iv_start, const long long* iv_maxend, const uint64_t* iv_off, uint64_t* n_raw,
+                            uint64_t* out_off, uint64_t* out_h1, uint32_t* out_pos, uint32_t* out_ctg, uint32_t* out_sub,
+                            uint64_t out_cap)
+{
+    if (!g || !tables || !iv_off || !n_raw || !out_off) return fail(NTS_ERR_ARG, "null argument");
+    nts_ctx* ctx = g->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t G = g->n_asm;
+    uint64_t total = 0;
+    for (uint32_t a = 0; a < G; ++a) {
+        if (!tables[a] || tables[a]->ctx != ctx) return fail(NTS_ERR_ARG, "bad minimizer table");
+        total += tables[a]->count;
+    }
+    out_off[0] = 0;
+    for (uint32_t a = 0; a < G; ++a) { n_raw[a] = 0; out_off[a + 1] = 0; }
+    if (!total) return NTS_OK;
+    ProfScope prof(ctx, PROF_GRAPH, (double)total);
+    uint64_t cap = 1024;
+    while (cap < total * 2) cap <<= 1;
+    DevBuf<unsigned long long> keys;
+    DevBuf<uint32_t> seen, dup, kept;
+    if (keys.alloc(cap + 1) != cudaSuccess || seen.alloc(cap + 1) != cudaSuccess || dup.alloc(cap + 1) != cudaSuccess ||
+        kept.alloc(cap + 1) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (refine table)");
+    NTS_CUDA(cudaMemsetAsync(keys.p, 0xFF, (cap + 1) * 8, ctx->stream));
+    NTS_CUDA(cudaMemsetAsync(seen.p, 0, (cap + 1) * 4, ctx->stream));
+    NTS_CUDA(cudaMemsetAsync(dup.p, 0, (cap + 1) * 4, ctx->stream));
+    NTS_CUDA(cudaMemsetAsync(kept.p, 0, (cap + 1) * 4, ctx->stream));
+    // small host inputs
+    DevBuf<uint32_t> d_seg_lo, d_seg_hi, d_term, d_xvid;
+    DevBuf<uint64_t> d_xkey;
+    DevBuf<long long> d_ivs, d_ive;
+    const uint64_t n_iv_all = iv_off[G];
+    if (d_seg_lo.alloc(n_seg) != cudaSuccess || d_seg_hi.alloc(n_seg) != cudaSuccess || d_term.alloc(n_term) != cudaSuccess ||
+        d_xkey.alloc(n_x) != cudaSuccess || d_xvid.alloc(n_x) != cudaSuccess || d_ivs.alloc(n_iv_all) != cudaSuccess ||
+        d_ive.alloc(n_iv_all) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (refine inputs)");
+    if (n_seg) { NTS_CUDA(copy_h2d(ctx, d_seg_lo.p, seg_lo, n_seg * 4)); NTS_CUDA(copy_h2d(ctx, d_seg_hi.p, seg_hi, n_seg * 4)); }
+    if (n_term) NTS_CUDA(copy_h2d(ctx, d_term.p, term, n_term * 4));
+    if (n_x) { NTS_CUDA(copy_h2d(ctx, d_xkey.p, x_key, n_x * 8)); NTS_CUDA(copy_h2d(ctx, d_xvid.p, x_vid, n_x * 4)); }
+    if (n_iv_all) { NTS_CUDA(copy_h2d(ctx, d_ivs.p, iv_start, n_iv_all * 8)); NTS_CUDA(copy_h2d(ctx, d_ive.p, iv_maxend, n_iv_all * 8)); }
+    RefineCtx rc;
+    rc.seg_lo = d_seg_lo.p; rc.seg_hi = d_seg_hi.p; rc.n_seg = n_seg; rc.term = d_term.p; rc.n_term = n_term;
+    rc.x_key = d_xkey.p; rc.x_vid = d_xvid.p; rc.n_x = n_x; rc.g_keys = g->keys.p; rc.g_slot_vid = g->slot_vid.p; rc.g_mask = g->cap - 1;
+    std::vector<DevBuf<uint32_t>> slot_of(G), keep(G), off(G);
+    DevBuf<unsigned int> d_raw;
+    if (d_raw.alloc(G) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed");
+    NTS_CUDA(cudaMemsetAsync(d_raw.p, 0, G * 4, ctx->stream));
+    for (uint32_t a = 0; a < G; ++a) {
+        const uint64_t n = tables[a]->count;
+        if (slot_of[a].alloc(n) != cudaSuccess || keep[a].alloc(n) != cudaSuccess || off[a].alloc(n) != cudaSuccess)
+            return fail(NTS_ERR_NOMEM, "device allocation failed (refine)");
+        if (!n) continue;
+        join_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(tables[a]->h1.p, n, a, keys.p, seen.p, dup.p, cap - 1, slot_of[a].p);
+        ctx->launches++;
+    }
+    for (uint32_t a = 0; a < G; ++a) {
+        const uint64_t n = tables[a]->count;
+        if (!n) continue;
+        const uint32_t n_iv = (uint32_t)(iv_off[a + 1] - iv_off[a]);
+        refine_keep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            tables[a]->h1.p, tables[a]->pos.p, tables[a]->contig.p, slot_of[a].p, n, a, dup.p, kept.p, rc, d_ivs.p + iv_off[a],
+            d_ive.p + iv_off[a], n_iv, keep[a].p, d_raw.p + a);
+        ctx->launches++;
+    }
+    NTS_CUDA(cudaGetLastError());
+    const uint32_t full = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1);
+    // per assembly: compact the kept entries, cut into sub-lists, keep the common keys
+    struct Part { DevBuf<uint64_t> h1; DevBuf<uint32_t> pos, ctg, sub; uint32_t n = 0; };
+    std::vector<Part> parts(G);
+    for (uint32_t a = 0; a < G; ++a) {
+        const uint64_t n = tables[a]->count;
+        if (!n) continue;
+        uint32_t n_keep = 0;
+        int rcode = exclusive_scan_u32(ctx, keep[a].p, n, off[a].p, &n_keep);
+        if (rcode) return rcode;
+        if (!n_keep) continue;
+        DevBuf<uint64_t> k_h1;
+        DevBuf<uint32_t> k_pos, k_ctg, k_slot, cut, fin, cut_x, fin_x;
+        if (k_h1.alloc(n_keep) != cudaSuccess || k_pos.alloc(n_keep) != cudaSuccess || k_ctg.alloc(n_keep) != cudaSuccess ||
+            k_slot.alloc(n_keep) != cudaSuccess || cut.alloc(n_keep) != cudaSuccess || fin.alloc(n_keep) != cudaSuccess ||
+            cut_x.alloc(n_keep) != cudaSuccess || fin_x.alloc(n_keep) != cudaSuccess)
+            return fail(NTS_ERR_NOMEM, "device allocation failed (refine kept)");
+        refine_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            tables[a]->h1.p, tables[a]->pos.p, tables[a]->contig.p, slot_of[a].p, keep[a].p, off[a].p, n, k_h1.p, k_pos.p, k_ctg.p, k_slot.p);
+        const uint32_t n_iv = (uint32_t)(iv_off[a + 1] - iv_off[a]);
+        refine_cut_kernel<<<(unsigned)((n_keep + 255) / 256), 256, 0, ctx->stream>>>(k_pos.p, k_ctg.p, k_slot.p, n_keep, kept.p, full,
+                                                                                    d_ivs.p + iv_off[a], d_ive.p + iv_off[a], n_iv, cut.p, fin.p);
+        ctx->launches += 2;
+        uint32_t n_cut = 0, n_fin = 0;
+        if ((rcode = exclusive_scan_u32(ctx, cut.p, n_keep, cut_x.p, &n_cut)) || (rcode = exclusive_scan_u32(ctx, fin.p, n_keep, fin_x.p, &n_fin)))
+            return rcode;
+        Part& pt = parts[a];
+        pt.n = n_fin;
+        if (!n_fin) continue;
+        if (pt.h1.alloc(n_fin) != cudaSuccess || pt.pos.alloc(n_fin) != cudaSuccess || pt.ctg.alloc(n_fin) != cudaSuccess || pt.sub.alloc(n_fin) != cudaSuccess)
+            return fail(NTS_ERR_NOMEM, "device allocation failed (refine out)");
+        refine_emit_kernel<<<(unsigned)((n_keep + 255) / 256), 256, 0, ctx->stream>>>(k_h1.p, k_pos.p, k_ctg.p, cut.p, cut_x.p, fin.p, fin_x.p,
+                                                                                     n_keep, pt.h1.p, pt.pos.p, pt.ctg.p, pt.sub.p);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));            // the kept buffers go out of scope
+    }
+    std::vector<unsigned int> h_raw(G, 0);
+    NTS_CUDA(cudaMemcpyAsync(h_raw.data(), d_raw.p, G * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t at = 0;
+    for (uint32_t a = 0; a < G; ++a) { n_raw[a] = h_raw[a]; out_off[a] = at; at += parts[a].n; }
+    out_off[G] = at;
+    if (at > out_cap || !at) return NTS_OK;
+    if (!out_h1 || !out_pos || !out_ctg || !out_sub) return fail(NTS_ERR_ARG, "null output");
+    for (uint32_t a = 0; a < G; ++a) {
+        const Part& pt = parts[a];
+        if (!pt.n) continue;
+        NTS_CUDA(copy_d2h(ctx, out_h1 + out_off[a], pt.h1.p, (size_t)pt.n * 8));
+        NTS_CUDA(copy_d2h(ctx, out_pos + out_off[a], pt.pos.p, (size_t)pt.n * 4));
+        NTS_CUDA(copy_d2h(ctx, out_ctg + out_off[a], pt.ctg.p, (size_t)pt.n * 4));
+        NTS_CUDA(copy_d2h(ctx, out_sub + out_off[a], pt.sub.p, (size_t)pt.n * 4));
+    }
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
     return NTS_OK;
 }
 

@@ -524,6 +524,40 @@ class MinimizerGraph:
         return dict(b_lo=a[0][:nb_], b_hi=a[1][:nb_], b_plus=a[2][:nb_], b_dir=d[:nb_], r_lo=a[3][:nr], r_hi=a[4][:nr],
                     cuts=a[5][:nc])
 
+    def refine_filter(self, tables, seg_lo, seg_hi, term, x_key, x_vid, iv_start, iv_maxend, iv_off):
+        """one refinement round's minimizer filtering on the device (nts_graph_refine_filter); returns
+        (n_raw[G], [(h1 u64, pos i64, ctg i64, sub i64) per assembly])"""
+        G = self.n_asm
+        arr = (C.c_void_p * G)(*[t._h for t in tables])
+        u32 = lambda x: np.ascontiguousarray(x, dtype=np.uint32)          # noqa: E731
+        seg_lo, seg_hi, term, x_vid = u32(seg_lo), u32(seg_hi), u32(term), u32(x_vid)
+        x_key = np.ascontiguousarray(x_key, dtype=np.uint64)
+        iv_start = np.ascontiguousarray(iv_start, dtype=np.int64)
+        iv_maxend = np.ascontiguousarray(iv_maxend, dtype=np.int64)
+        iv_off = np.ascontiguousarray(iv_off, dtype=np.uint64)
+        n_raw = np.zeros(G, dtype=np.uint64)
+        off = np.zeros(G + 1, dtype=np.uint64)
+        z32, z64, zi = np.zeros(1, dtype=np.uint32), np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.int64)
+        cap = 1 << 16
+        while True:
+            o_h1 = np.zeros(cap, dtype=np.uint64)
+            o_pos, o_ctg, o_sub = (np.zeros(cap, dtype=np.uint32) for _ in range(3))
+            check(lib.nts_graph_refine_filter(
+                self._h, arr, ptr(seg_lo if len(seg_lo) else z32, C.c_uint32), ptr(seg_hi if len(seg_hi) else z32, C.c_uint32),
+                len(seg_lo), ptr(term if len(term) else z32, C.c_uint32), len(term), ptr(x_key if len(x_key) else z64, C.c_uint64),
+                ptr(x_vid if len(x_vid) else z32, C.c_uint32), len(x_key), ptr(iv_start if len(iv_start) else zi, C.c_int64),
+                ptr(iv_maxend if len(iv_maxend) else zi, C.c_int64), ptr(iv_off, C.c_uint64), ptr(n_raw, C.c_uint64),
+                ptr(off, C.c_uint64), ptr(o_h1, C.c_uint64), ptr(o_pos, C.c_uint32), ptr(o_ctg, C.c_uint32), ptr(o_sub, C.c_uint32),
+                cap))
+            if int(off[G]) <= cap:
+                break
+            cap = int(off[G])
+        out = []
+        for a in range(G):
+            i0, i1 = int(off[a]), int(off[a + 1])
+            out.append((o_h1[i0:i1].copy(), o_pos[i0:i1].astype(np.int64), o_ctg[i0:i1].astype(np.int64), o_sub[i0:i1].astype(np.int64)))
+        return [int(x) for x in n_raw], out
+
     def join_result(self, full=False, lean=None):
         """everything SyntenyEngine needs from the join, as a dict.  Default: device-resident form -- positions,
         contigs, hashes, ranks and the direction prefix sums stay in HBM and are read through gather / range_sums /
@@ -536,6 +570,7 @@ class MinimizerGraph:
         if lean != "host" and not full:
             return dict(V=V, gather=self.gather, range_sums=self.range_sums, neigh=self.neigh, links_nbr=self.links_nbr,
                         set_links=self.set_links, runs=self.runs, runs_to_blocks=self.runs_to_blocks,
+                        refine_filter=self.refine_filter,
                         sparse=lambda bp: self.sparse_lists(bp, breaks=False))
         RANK, INV = self.rank_inv()
         CI, CD = self.cums()

@@ -211,6 +211,9 @@ class GatheredBackend:
         mx.close()
         return out
 
+    def sketch_table(self, a, w, masks):
+        return self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, masks=masks)
+
     def join(self, tables, order_asm):
         if getattr(self, "graph", None) is not None:
             self.graph.close()

@@ -83,6 +83,13 @@ class CudaBackend:
         mx.close()
         return out
 
+    def sketch_table(self, a, w, masks):
+        "a masked refinement sketch that stays on the device (consumed by MinimizerGraph.refine_filter)"
+        t0 = time.perf_counter()
+        mx = self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, repeat=None, masks=masks)
+        self.timing["sketch_ms"] += (time.perf_counter() - t0) * 1e3
+        return mx
+
     def join(self, tables, order_asm):
         t0 = time.perf_counter()
         if getattr(self, "graph", None) is not None:

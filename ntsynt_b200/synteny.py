@@ -953,6 +953,13 @@ class SyntenyEngine:
             dirty[bid[jn[wide]]] = True
         if not dirty.any():
             return blocks
+        if self._dev is not None:
+            # the loop below reads positions one vertex at a time: fetch the segment ends of the dirty blocks at once
+            ends_ = [x for bx in np.flatnonzero(dirty).tolist() for sg in blocks[bx].segs for x in (sg[0], sg[1])]
+            cuts_ = [big[np.searchsorted(big, sg[0]):np.searchsorted(big, sg[1])] for bx in np.flatnonzero(dirty).tolist()
+                     for sg in blocks[bx].segs if sg[1] > sg[0]]
+            cuts_ = np.concatenate(cuts_) if cuts_ else np.zeros(0, dtype=np.int64)
+            self.POS.prefetch(np.concatenate([np.asarray(ends_, dtype=np.int64), cuts_, cuts_ + 1]))
         out = []
         rm_u, rm_v = [], []
         for bx, b in enumerate(blocks):
@@ -1196,91 +1203,123 @@ class SyntenyEngine:
         self.stats.setdefault("unmasked", []).append(
             [round(1.0 - sum(int((e - s).sum()) for s, e in masks[a]) / max(sum(self.be.contig_lengths[a]), 1), 6) for a in range(G)])
         self._tick("r_masks")
-        new = []
-        for a in range(G):
-            h1, pos, ctg = self.be.sketch(a, new_w, masks[a])
-            new.append(self._dedup(h1, pos.astype(np.int64), ctg.astype(np.int64)))
-        self.stats.setdefault("new_raw", []).append([int(len(x[0])) for x in new])
-        self._tick("r_sketch")
-        # --- terminal / internal minimizers and block intervals (find_mx_in_blocks :205-226)
+        use_dev = self._dev is not None and "refine_filter" in self._dev and hasattr(self.be, "sketch_table")
         term_ids = np.array([x for b in blocks for x in (b.first_id, b.last_id)], dtype=np.int64)
-        terminal_h = set(int(x) for x in self.H[term_ids]) if len(term_ids) else set()
-        seg_lo = np.array([sg[0] for b in blocks for sg in b.segs], dtype=np.int64)
-        seg_hi = np.array([sg[1] for b in blocks for sg in b.segs], dtype=np.int64)
-        is_internal = np.zeros(self.V, dtype=bool)
-        long_ = np.flatnonzero(seg_hi - seg_lo > 64)
-        for lo, hi in zip(seg_lo[long_].tolist(), seg_hi[long_].tolist()):          # the few long runs: slice fills
-            is_internal[lo:hi + 1] = True
-        short_ = np.flatnonzero(seg_hi - seg_lo <= 64)                                 # the many short ones: one scatter
-        if len(short_):
-            n_ = seg_hi[short_] - seg_lo[short_] + 1
-            off_ = np.repeat(np.cumsum(n_) - n_, n_)
-            is_internal[np.repeat(seg_lo[short_], n_) + (np.arange(int(n_.sum())) - off_)] = True
-        if len(term_ids):
-            is_internal[term_ids] = False
-        # open intervals (start, last minimizer) of the blocks per assembly, on one axis: coordinate = contig << 40 | pos
-        # (intervals of different contigs cannot meet there, so one index answers the queries of every contig)
-        SH = np.int64(40)
-        bst, ben, bctg = self._block_coords(blocks)
-        intervals = []
-        for a in range(G):
-            s_, e_, c_ = bst[:, a], ben[:, a] - self.k, bctg[:, a]
-            ok = (e_ - s_) >= 2
-            base_ = c_[ok] << SH
-            intervals.append(IntervalIndex(base_ + s_[ok] + 1, base_ + e_[ok]) if ok.any() else None)
-        self._tick("r_blockinfo")
-        # --- filter_minimizers_synteny_blocks (:256-280), vectorised over all contigs of an assembly
-        # all new minimizers of all assemblies through ONE device lookup
-        sizes = [len(x[0]) for x in new]
-        all_h1 = np.concatenate([x[0] for x in new]) if sum(sizes) else np.zeros(0, dtype=np.uint64)
-        all_vid = self._lookup(all_h1) if len(all_h1) else np.zeros(0, dtype=np.int64)
-        offs = np.concatenate([[0], np.cumsum(sizes)])
-        kept = []       # per assembly: (h1, pos, ctg, sublist_id)
-        for a in range(G):
-            h1, pos, ctg = new[a]
-            n = len(h1)
-            if n == 0:
-                kept.append((h1, pos, ctg, np.zeros(0, dtype=np.int64)))
-                continue
-            vid_new = all_vid[offs[a]:offs[a + 1]]
-            internal_hit = np.zeros(n, dtype=bool)
-            known = vid_new >= 0
-            internal_hit[known] = is_internal[vid_new[known]]
-            ii = intervals[a]
-            key = (ctg.astype(np.int64) << SH) + pos
-            inside = ii.overlaps(key, key + 1) if ii is not None else np.zeros(n, dtype=bool)
-            keep = ~internal_hit & ~inside
-            kh, kp, kc, kk = h1[keep], pos[keep], ctg[keep], key[keep]
-            # cut between consecutive kept minimizers of one contig whose span overlaps a block interval
-            cut = np.ones(len(kh), dtype=bool)
-            if len(kh) > 1:
-                same = kc[1:] == kc[:-1]
-                ov = np.zeros(len(kh) - 1, dtype=bool)
-                if ii is not None:
-                    sel = np.flatnonzero(same)
-                    ov[sel] = ii.overlaps(kk[:-1][sel], kk[1:][sel])
-                cut[1:] = ~same | ov
-            kept.append((kh, kp, kc, np.cumsum(cut) - 1))
-        self._tick("r_filter")
-        # --- G-way intersection (ntjoin_utils.filter_minimizers :152-165)
-        # every assembly's keys are distinct by now (read_minimizers dropped the repeated ones), so a key is common
-        # to all G lists iff it occurs G times in their concatenation: one sort instead of G sorts + G-1 merges
-        allk = np.concatenate([x[0] for x in kept])
-        if len(allk):
-            uk, cnt_k = np.unique(allk, return_counts=True)
-            common = uk[cnt_k == G]
+        if use_dev:
+            # the new tables never leave the device: duplicate removal, the block filter and the G-way intersection are
+            # kernels (nts_graph_refine_filter); the host gets the few survivors
+            tables = [self.be.sketch_table(a, new_w, masks[a]) for a in range(G)]
+            self._tick("r_sketch")
+            seg_lo = np.array([sg[0] for b in blocks for sg in b.segs], dtype=np.int64)
+            seg_hi = np.array([sg[1] for b in blocks for sg in b.segs], dtype=np.int64)
+            o = np.argsort(seg_lo)
+            SH = np.int64(40)
+            bst, ben, bctg = self._block_coords(blocks)
+            ivs, ive, ivo = [], [], [0]
+            for a in range(G):
+                s_, e_, c_ = bst[:, a], ben[:, a] - self.k, bctg[:, a]
+                ok = (e_ - s_) >= 2
+                base_ = c_[ok] << SH
+                ii = IntervalIndex(base_ + s_[ok] + 1, base_ + e_[ok])
+                ivs.append(ii.starts); ive.append(ii.maxend); ivo.append(ivo[-1] + len(ii.starts))
+            xk = np.fromiter(self._h_extra.keys(), dtype=np.uint64, count=len(self._h_extra))
+            xv = np.fromiter(self._h_extra.values(), dtype=np.int64, count=len(self._h_extra))
+            xo = np.argsort(xk)
+            self._tick("r_blockinfo")
+            n_raw, lists = self._dev["refine_filter"](tables, seg_lo[o], seg_hi[o], np.unique(term_ids), xk[xo], xv[xo],
+                                                      np.concatenate(ivs) if ivs else np.zeros(0, dtype=np.int64),
+                                                      np.concatenate(ive) if ive else np.zeros(0, dtype=np.int64), ivo)
+            for t in tables:
+                t.close()
+            self.stats.setdefault("new_raw", []).append(n_raw)
+            common = np.sort(lists[0][0]) if len(lists[0][0]) else np.zeros(0, dtype=np.uint64)
+            self._tick("r_filter")
         else:
-            common = allk
-        lists = []
-        for a in range(G):
-            kh, kp, kc, sub = kept[a]
-            if len(kh) and len(common):
-                j = np.searchsorted(common, kh)
-                j[j >= len(common)] = 0
-                ok = common[j] == kh
+            new = []
+            for a in range(G):
+                h1, pos, ctg = self.be.sketch(a, new_w, masks[a])
+                new.append(self._dedup(h1, pos.astype(np.int64), ctg.astype(np.int64)))
+            self.stats.setdefault("new_raw", []).append([int(len(x[0])) for x in new])
+            self._tick("r_sketch")
+            # --- terminal / internal minimizers and block intervals (find_mx_in_blocks :205-226)
+            term_ids = np.array([x for b in blocks for x in (b.first_id, b.last_id)], dtype=np.int64)
+            terminal_h = set(int(x) for x in self.H[term_ids]) if len(term_ids) else set()
+            seg_lo = np.array([sg[0] for b in blocks for sg in b.segs], dtype=np.int64)
+            seg_hi = np.array([sg[1] for b in blocks for sg in b.segs], dtype=np.int64)
+            is_internal = np.zeros(self.V, dtype=bool)
+            long_ = np.flatnonzero(seg_hi - seg_lo > 64)
+            for lo, hi in zip(seg_lo[long_].tolist(), seg_hi[long_].tolist()):          # the few long runs: slice fills
+                is_internal[lo:hi + 1] = True
+            short_ = np.flatnonzero(seg_hi - seg_lo <= 64)                                 # the many short ones: one scatter
+            if len(short_):
+                n_ = seg_hi[short_] - seg_lo[short_] + 1
+                off_ = np.repeat(np.cumsum(n_) - n_, n_)
+                is_internal[np.repeat(seg_lo[short_], n_) + (np.arange(int(n_.sum())) - off_)] = True
+            if len(term_ids):
+                is_internal[term_ids] = False
+            # open intervals (start, last minimizer) of the blocks per assembly, on one axis: coordinate = contig << 40 | pos
+            # (intervals of different contigs cannot meet there, so one index answers the queries of every contig)
+            SH = np.int64(40)
+            bst, ben, bctg = self._block_coords(blocks)
+            intervals = []
+            for a in range(G):
+                s_, e_, c_ = bst[:, a], ben[:, a] - self.k, bctg[:, a]
+                ok = (e_ - s_) >= 2
+                base_ = c_[ok] << SH
+                intervals.append(IntervalIndex(base_ + s_[ok] + 1, base_ + e_[ok]) if ok.any() else None)
+            self._tick("r_blockinfo")
+            # --- filter_minimizers_synteny_blocks (:256-280), vectorised over all contigs of an assembly
+            # all new minimizers of all assemblies through ONE device lookup
+            sizes = [len(x[0]) for x in new]
+            all_h1 = np.concatenate([x[0] for x in new]) if sum(sizes) else np.zeros(0, dtype=np.uint64)
+            all_vid = self._lookup(all_h1) if len(all_h1) else np.zeros(0, dtype=np.int64)
+            offs = np.concatenate([[0], np.cumsum(sizes)])
+            kept = []       # per assembly: (h1, pos, ctg, sublist_id)
+            for a in range(G):
+                h1, pos, ctg = new[a]
+                n = len(h1)
+                if n == 0:
+                    kept.append((h1, pos, ctg, np.zeros(0, dtype=np.int64)))
+                    continue
+                vid_new = all_vid[offs[a]:offs[a + 1]]
+                internal_hit = np.zeros(n, dtype=bool)
+                known = vid_new >= 0
+                internal_hit[known] = is_internal[vid_new[known]]
+                ii = intervals[a]
+                key = (ctg.astype(np.int64) << SH) + pos
+                inside = ii.overlaps(key, key + 1) if ii is not None else np.zeros(n, dtype=bool)
+                keep = ~internal_hit & ~inside
+                kh, kp, kc, kk = h1[keep], pos[keep], ctg[keep], key[keep]
+                # cut between consecutive kept minimizers of one contig whose span overlaps a block interval
+                cut = np.ones(len(kh), dtype=bool)
+                if len(kh) > 1:
+                    same = kc[1:] == kc[:-1]
+                    ov = np.zeros(len(kh) - 1, dtype=bool)
+                    if ii is not None:
+                        sel = np.flatnonzero(same)
+                        ov[sel] = ii.overlaps(kk[:-1][sel], kk[1:][sel])
+                    cut[1:] = ~same | ov
+                kept.append((kh, kp, kc, np.cumsum(cut) - 1))
+            self._tick("r_filter")
+            # --- G-way intersection (ntjoin_utils.filter_minimizers :152-165)
+            # every assembly's keys are distinct by now (read_minimizers dropped the repeated ones), so a key is common
+            # to all G lists iff it occurs G times in their concatenation: one sort instead of G sorts + G-1 merges
+            allk = np.concatenate([x[0] for x in kept])
+            if len(allk):
+                uk, cnt_k = np.unique(allk, return_counts=True)
+                common = uk[cnt_k == G]
             else:
-                ok = np.zeros(len(kh), dtype=bool)
-            lists.append((kh[ok], kp[ok], kc[ok], sub[ok]))
+                common = allk
+            lists = []
+            for a in range(G):
+                kh, kp, kc, sub = kept[a]
+                if len(kh) and len(common):
+                    j = np.searchsorted(common, kh)
+                    j[j >= len(common)] = 0
+                    ok = common[j] == kh
+                else:
+                    ok = np.zeros(len(kh), dtype=bool)
+                lists.append((kh[ok], kp[ok], kc[ok], sub[ok]))
         self.stats.setdefault("new_common", []).append(int(len(common)))
         # --- update_list_mx_info (:282-290) + vertex ids for every surviving minimizer
         ids_per_asm = []

@@ -91,6 +91,14 @@ def numpy_edges(RANK, CTG):
     return [tuple(seen[k]) for k in order]
 
 
+class _HostTable(tuple):
+    def __new__(cls, t):
+        return super().__new__(cls, t)
+
+    def close(self):
+        pass
+
+
 class OracleBackend:
     def __init__(self, fasta_paths, tsv_names, k, fpr=0.025, common=True, lean=False):
         """fasta_paths/tsv_names in the engine's processing order (reverse-sorted TSV names).
@@ -281,8 +289,59 @@ class OracleBackend:
             for k in ("r_lo", "r_hi"):
                 res[k] = res[k][pr]
             return res
+        def refine_filter(tables, seg_lo, seg_hi, term, x_key, x_vid, iv_start, iv_maxend, iv_off):
+            "nts_graph_refine_filter restated with numpy (dedup, block filter, sub-lists, G-way intersection)"
+            count("refine_filter")
+            assert (np.diff(seg_lo) > 0).all() and (np.diff(term) > 0).all() and (np.diff(x_key.astype(np.float64)) >= 0).all()
+
+            def hit(st, mx, a, b):
+                n = np.searchsorted(st, b, side="left")
+                res = np.zeros(len(a), dtype=bool)
+                ok = n > 0
+                res[ok] = mx[n[ok] - 1] > a[ok]
+                return res
+            kept, n_raw = [], []
+            for a, (h1, pos, ctg) in enumerate(tables):
+                _, inv_, cnt = np.unique(h1, return_inverse=True, return_counts=True)
+                uniq = cnt[inv_] == 1 if len(h1) else np.zeros(0, dtype=bool)
+                h1, pos, ctg = h1[uniq], pos[uniq].astype(np.int64), ctg[uniq].astype(np.int64)
+                n_raw.append(len(h1))
+                vid = self.lookup(h1).astype(np.int64)
+                vid[vid == 0xFFFFFFFF] = -1
+                if len(x_key):
+                    j = np.searchsorted(x_key, h1)
+                    j[j >= len(x_key)] = 0
+                    m = (vid < 0) & (x_key[j] == h1)
+                    vid[m] = x_vid[j[m]]
+                internal = np.zeros(len(h1), dtype=bool)
+                if len(seg_lo):
+                    k = np.searchsorted(seg_lo, vid, side="right") - 1
+                    ok = (vid >= 0) & (k >= 0)
+                    internal[ok] = seg_hi[k[ok]] >= vid[ok]
+                    internal &= ~np.isin(vid, term)
+                st, mx = iv_start[int(iv_off[a]):int(iv_off[a + 1])], iv_maxend[int(iv_off[a]):int(iv_off[a + 1])]
+                key = (ctg << np.int64(40)) + pos
+                keep = ~internal & ~hit(st, mx, key, key + 1)
+                kh, kp, kc, kk = h1[keep], pos[keep], ctg[keep], key[keep]
+                cut = np.ones(len(kh), dtype=bool)
+                if len(kh) > 1:
+                    same = kc[1:] == kc[:-1]
+                    cut[1:] = ~same | (same & hit(st, mx, kk[:-1], kk[1:]))
+                kept.append((kh, kp, kc, np.cumsum(cut) - 1))
+            allk = np.concatenate([x[0] for x in kept])
+            uk, ck = np.unique(allk, return_counts=True) if len(allk) else (allk, allk)
+            common = uk[ck == G] if len(allk) else allk
+            out = []
+            for kh, kp, kc, sub in kept:
+                ok = np.isin(kh, common)
+                out.append((kh[ok], kp[ok], kc[ok], sub[ok]))
+            return n_raw, out
         return dict(V=V, gather=gather, range_sums=range_sums, neigh=neigh, links_nbr=links_nbr, set_links=set_links, runs=runs,
-                    runs_to_blocks=runs_to_blocks, sparse=sparse)
+                    runs_to_blocks=runs_to_blocks, sparse=sparse, refine_filter=refine_filter)
+
+    def sketch_table(self, a, w, masks):
+        "what stays on the device in the CUDA backend: here simply the host table"
+        return _HostTable(self.sketch(a, w, masks))
 
     def lookup(self, keys):
         out = np.full(len(keys), 0xFFFFFFFF, dtype=np.uint32)

@@ -74,6 +74,8 @@ def test_engine_equals_graph_oracle_on_rearranged_genomes(tmp_path, seed, G, pre
         eng_dev, be_dev = run_engine(paths, k, w, w_rounds, indel, merge, z, lean="dev")
         assert eng_dev.outputs == eng.outputs
         assert be_dev.calls.get("runs_to_blocks", 0) == 1 + len(w_rounds)
+        assert be_dev.calls.get("refine_filter", 0) == len(w_rounds)
+        assert eng_dev.stats["new_raw"] == eng.stats["new_raw"] and eng_dev.stats["new_common"] == eng.stats["new_common"]
 
 
 def test_interval_index_matches_bruteforce():
