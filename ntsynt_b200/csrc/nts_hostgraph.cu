@@ -139,6 +139,168 @@ int nts_host_walk_paths_sparse(const int32_t* nbr, int64_t V0, const int64_t* st
                            seg_cap, n_paths, n_segs);
 }
 
+/* find_synteny_blocks + check_for_indels + filter_synteny_blocks for paths given as segments (bin/ntsynt_synteny.py:
+ * 66-106, 364-426; bin/synteny_block.py:48-65) -- the host-walked paths of a round in one call.
+ *   path p owns segments [path_off[p], path_off[p+1]) = runs lo..hi of consecutive ids traversed in direction dir;
+ *   up / down [G x n_seg]: pairs (j, j+1), lo <= j < hi, whose position increases / decreases in each assembly;
+ *   (ids ascending, pos / ctg [G x n_ids]): positions and contigs of every vertex the call looks at -- both ends of
+ *   every segment and c, c + 1 for every large-spread pair c inside a segment;  big: those pairs, ascending.
+ * A path's block = its segments from the last junction with a contig change on (the reference never flags the earlier
+ * part); per assembly '+' / '-' if every step increases / decreases, else by the m_pct rule, else the block's segments
+ * are deleted.  The block is then cut at every junction / inner pair whose |dpos| spread exceeds bp (that edge is
+ * removed), and pieces with fewer than min_mx minimizers are deleted.
+ * Outputs: blocks (b_off into the out segment arrays o_lo/o_hi/o_dir, b_n, b_first, b_last, b_ori / b_ctg / b_fpos /
+ * b_lpos [n_blocks x G]); deleted segments (r_lo, r_hi); removed edges (e_u, e_v).  cap bounds every output array
+ * (n_seg + number of large-spread pairs inside segments + 1 is enough).  counts[4] = blocks, out segments, deleted
+ * segments, removed edges. */
+int nts_host_paths_to_blocks(int64_t n_paths, const int64_t* path_off, const int64_t* seg_lo, const int64_t* seg_hi,
+                             const int8_t* seg_dir, uint32_t G, const int64_t* up, const int64_t* down, const int64_t* ids,
+                             int64_t n_ids, const int64_t* pos, const int32_t* ctg, const int64_t* big, int64_t n_big, int64_t bp,
+                             double m_pct, int64_t min_mx, int64_t cap, int64_t* b_off, int64_t* b_n, int64_t* b_first,
+                             int64_t* b_last, int8_t* b_ori, int32_t* b_ctg, int64_t* b_fpos, int64_t* b_lpos, int64_t* o_lo,
+                             int64_t* o_hi, int8_t* o_dir, int64_t* r_lo, int64_t* r_hi, int64_t* e_u, int64_t* e_v,
+                             int64_t counts[4])
+{
+    if (!path_off || !counts || (n_paths && (!seg_lo || !seg_hi || !seg_dir || !up || !down || !ids || !pos || !ctg)))
+        return fail(NTS_ERR_ARG, "null argument");
+    if (G < 1 || G > 32) return fail(NTS_ERR_ARG, "between 1 and 32 assemblies are supported");
+    const int64_t n_seg = n_paths ? path_off[n_paths] : 0;
+    int64_t nb = 0, no = 0, nr = 0, ne = 0;
+    bool missing = false;
+    auto at = [&](int64_t v) -> int64_t {
+        const int64_t* p = std::lower_bound(ids, ids + n_ids, v);
+        if (p == ids + n_ids || *p != v) { missing = true; return 0; }
+        return (int64_t)(p - ids);
+    };
+    auto first_of = [&](int64_t j) { return seg_dir[j] > 0 ? seg_lo[j] : seg_hi[j]; };
+    auto last_of = [&](int64_t j) { return seg_dir[j] > 0 ? seg_hi[j] : seg_lo[j]; };
+    auto spread_gt = [&](int64_t u, int64_t v) {          // max |dpos| - min |dpos| over the assemblies > bp
+        const int64_t iu = at(u), iv = at(v);
+        int64_t mx = 0, mn = INT64_MAX;
+        for (uint32_t a = 0; a < G; ++a) {
+            int64_t d = pos[a * n_ids + iv] - pos[a * n_ids + iu];
+            if (d < 0) d = -d;
+            mx = std::max(mx, d); mn = std::min(mn, d);
+        }
+        return mx - mn > bp;
+    };
+    std::vector<int64_t> inc(G), dec(G);
+    std::vector<int8_t> ori(G);
+    struct Seg { int64_t lo, hi; int8_t d; };
+    std::vector<Seg> cur;
+    std::vector<std::vector<Seg>> pieces;
+    for (int64_t p = 0; p < n_paths; ++p) {
+        const int64_t s0 = path_off[p], s1 = path_off[p + 1];
+        if (s1 <= s0) continue;
+        // the block starts after the last junction where some assembly changes contig
+        int64_t start = s0;
+        for (int64_t j = s0 + 1; j < s1; ++j) {
+            const int64_t iu = at(last_of(j - 1)), iv = at(first_of(j));
+            bool chg = false;
+            for (uint32_t a = 0; a < G && !chg; ++a) chg = ctg[a * n_ids + iu] != ctg[a * n_ids + iv];
+            if (chg) start = j;
+        }
+        int64_t n = 0;
+        std::fill(inc.begin(), inc.end(), 0); std::fill(dec.begin(), dec.end(), 0);
+        for (int64_t j = start; j < s1; ++j) {
+            n += seg_hi[j] - seg_lo[j] + 1;
+            for (uint32_t a = 0; a < G; ++a) {
+                const int64_t u_ = up[a * n_seg + j], d_ = down[a * n_seg + j];
+                inc[a] += seg_dir[j] > 0 ? u_ : d_;
+                dec[a] += seg_dir[j] > 0 ? d_ : u_;
+            }
+            if (j > start) {
+                const int64_t iu = at(last_of(j - 1)), iv = at(first_of(j));
+                for (uint32_t a = 0; a < G; ++a) {
+                    const int64_t d = pos[a * n_ids + iv] - pos[a * n_ids + iu];
+                    if (d > 0) ++inc[a]; else if (d < 0) ++dec[a];
+                }
+            }
+        }
+        bool unoriented = false;
+        for (uint32_t a = 0; a < G; ++a) {
+            if (inc[a] == n - 1 || n == 1) ori[a] = '+';
+            else if (dec[a] == n - 1) ori[a] = '-';
+            else {
+                const double positive = (double)inc[a] / (double)(n - 1) * 100;
+                const double negative = 100 - positive;
+                ori[a] = positive >= m_pct ? '+' : (negative >= m_pct ? '-' : '?');
+                if (ori[a] == '?') unoriented = true;
+            }
+        }
+        if (unoriented) {
+            for (int64_t j = start; j < s1; ++j) {
+                if (nr >= cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
+                r_lo[nr] = seg_lo[j]; r_hi[nr] = seg_hi[j]; ++nr;
+            }
+            continue;
+        }
+        const int64_t i_f = at(first_of(start));
+        // indel cuts
+        pieces.clear(); cur.clear();
+        for (int64_t j = start; j < s1; ++j) {
+            const int64_t slo = seg_lo[j], shi = seg_hi[j];
+            const int8_t d = seg_dir[j];
+            if (j > start) {
+                const int64_t u = last_of(j - 1), v = first_of(j);
+                if (spread_gt(u, v)) {
+                    if (ne >= cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
+                    e_u[ne] = u; e_v[ne] = v; ++ne;
+                    pieces.push_back(cur); cur.clear();
+                }
+            }
+            const int64_t* c0 = shi > slo ? std::lower_bound(big, big + n_big, slo) : big;
+            const int64_t* c1 = shi > slo ? std::lower_bound(big, big + n_big, shi) : big;
+            if (c1 > c0) {
+                for (const int64_t* c = c0; c < c1; ++c) {
+                    if (ne >= cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
+                    e_u[ne] = *c; e_v[ne] = *c + 1; ++ne;
+                }
+                if (d > 0) {
+                    int64_t a0 = slo;
+                    for (const int64_t* c = c0; c < c1; ++c) { cur.push_back({a0, *c, 1}); pieces.push_back(cur); cur.clear(); a0 = *c + 1; }
+                    cur.push_back({a0, shi, 1});
+                } else {
+                    int64_t a0 = shi;
+                    for (const int64_t* c = c1; c-- > c0;) { cur.push_back({*c + 1, a0, -1}); pieces.push_back(cur); cur.clear(); a0 = *c; }
+                    cur.push_back({slo, a0, -1});
+                }
+            } else {
+                cur.push_back({slo, shi, d});
+            }
+        }
+        pieces.push_back(cur);
+        for (const auto& pc : pieces) {
+            int64_t pn = 0;
+            for (const Seg& sg : pc) pn += sg.hi - sg.lo + 1;
+            if (pn < min_mx) {
+                for (const Seg& sg : pc) {
+                    if (nr >= cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
+                    r_lo[nr] = sg.lo; r_hi[nr] = sg.hi; ++nr;
+                }
+                continue;
+            }
+            if (nb >= cap || no + (int64_t)pc.size() > cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
+            const int64_t f = pc.front().d > 0 ? pc.front().lo : pc.front().hi;
+            const int64_t l = pc.back().d > 0 ? pc.back().hi : pc.back().lo;
+            const int64_t jf = at(f), jl = at(l);
+            b_off[nb] = no; b_n[nb] = pn; b_first[nb] = f; b_last[nb] = l;
+            for (uint32_t a = 0; a < G; ++a) {
+                b_ori[nb * G + a] = ori[a];
+                b_ctg[nb * G + a] = ctg[a * n_ids + i_f];             // the contigs of the path's block, also for its pieces
+                b_fpos[nb * G + a] = pos[a * n_ids + jf];
+                b_lpos[nb * G + a] = pos[a * n_ids + jl];
+            }
+            for (const Seg& sg : pc) { o_lo[no] = sg.lo; o_hi[no] = sg.hi; o_dir[no] = sg.d; ++no; }
+            ++nb;
+        }
+    }
+    if (missing) return fail(NTS_ERR_ARG, "paths_to_blocks: a vertex the walk needs is not in the position table");
+    b_off[nb] = no;
+    counts[0] = nb; counts[1] = no; counts[2] = nr; counts[3] = ne;
+    return NTS_OK;
+}
+
 /* run_graph_simplification on the round-0 graph (bin/ntsynt_synteny.py:566-590).  cand = the vertices with exactly
  * three distinct neighbours, ascending; rank / inv = [G x V] rank of every vertex in every assembly's filtered list
  * and its inverse; ctg = [G x ctg_stride] contig of every vertex.  Candidate edges (both ends candidates) are

@@ -664,13 +664,14 @@ class SyntenyEngine:
         return bumped, removed
 
     # ------------------------------------------------------------------ paths of a max-degree-2 graph
-    def _find_paths(self, device_pure=False):
+    def _find_paths(self, device_pure=False, as_arrays=False):
         """ntjoin.py:114-151 on the weight-filtered graph: every component that is a simple path with
         two distinct ends gives one path, oriented from the end with the smaller position in the
         orienting assembly.  A path is a list of segments (lo, hi, dir).
         device_pure (device-resident form): the plain (i, i+1) runs whose vertices still hold their round-0
         positions are not turned into paths here; they are returned as a second value (starts, ends) for
-        nts_graph_runs_to_blocks."""
+        nts_graph_runs_to_blocks.
+        as_arrays: the paths come back as (path_off, seg_lo, seg_hi, seg_dir) arrays instead of lists of tuples."""
         V0 = self.V0
         opos = self.POS[self.orient]
         paths = []
@@ -731,13 +732,22 @@ class SyntenyEngine:
             dev_runs = (starts[dv], ends[dv])
             plain &= stale
         pure = np.flatnonzero(plain)
+        arr_lo = arr_hi = np.zeros(0, dtype=np.int64)
+        arr_dir = np.zeros(0, dtype=np.int8)
+        arr_off = np.zeros(1, dtype=np.int64)
         if len(pure):
             pa, pb = opos[starts[pure]], opos[ends[pure]]
-            for a, b, x, y in zip(starts[pure].tolist(), ends[pure].tolist(), pa.tolist(), pb.tolist()):
-                if x < y:
-                    paths.append([(a, b, 1)])
-                elif y < x:
-                    paths.append([(a, b, -1)])
+            if as_arrays:
+                ok = pa != pb
+                arr_lo, arr_hi = starts[pure][ok].astype(np.int64), ends[pure][ok].astype(np.int64)
+                arr_dir = np.where(pa[ok] < pb[ok], 1, -1).astype(np.int8)
+                arr_off = np.arange(len(arr_lo) + 1, dtype=np.int64)
+            else:
+                for a, b, x, y in zip(starts[pure].tolist(), ends[pure].tolist(), pa.tolist(), pb.tolist()):
+                    if x < y:
+                        paths.append([(a, b, 1)])
+                    elif y < x:
+                        paths.append([(a, b, -1)])
         if dev:
             self._tick("p_pure")
         if real_sparse and (self.native or dev):
@@ -775,9 +785,15 @@ class SyntenyEngine:
                                               ptr(opos64, C.c_int64), ptr(slo, C.c_int64), ptr(shi, C.c_int64),
                                               sdir.ctypes.data_as(C.POINTER(C.c_int8)), ptr(poff, C.c_int64), cap,
                                               C.byref(n_p), C.byref(n_s)))
-            segs_all = list(zip(slo[:n_s.value].tolist(), shi[:n_s.value].tolist(), sdir[:n_s.value].tolist()))
-            off = poff[:n_p.value + 1].tolist()
-            paths.extend(segs_all[off[i]:off[i + 1]] for i in range(n_p.value))
+            if as_arrays:
+                ns, np_ = n_s.value, n_p.value
+                arr_off = np.concatenate([arr_off, arr_off[-1] + poff[1:np_ + 1]])
+                arr_lo = np.concatenate([arr_lo, slo[:ns]]); arr_hi = np.concatenate([arr_hi, shi[:ns]])
+                arr_dir = np.concatenate([arr_dir, sdir[:ns]])
+            else:
+                segs_all = list(zip(slo[:n_s.value].tolist(), shi[:n_s.value].tolist(), sdir[:n_s.value].tolist()))
+                off = poff[:n_p.value + 1].tolist()
+                paths.extend(segs_all[off[i]:off[i + 1]] for i in range(n_p.value))
         elif real_sparse:
             seen_runs = set()
             sv = rs
@@ -841,6 +857,8 @@ class SyntenyEngine:
                     paths.append(segs)
                 elif pb < pa:
                     paths.append([(lo, hi, -d) for lo, hi, d in reversed(segs)])
+        if as_arrays:
+            paths = (arr_off, arr_lo, arr_hi, arr_dir)
         return (paths, dev_runs) if device_pure else paths
 
     # ------------------------------------------------------------------ blocks from paths
@@ -1012,6 +1030,61 @@ class SyntenyEngine:
             self._remove_segments(rm)
         return keep
 
+    def _host_blocks_native(self, path_off, lo, hi, sdir):
+        """_blocks_from_paths + _split_indels + _filter_small(4) for paths given as segment arrays, in C++
+        (csrc/nts_hostgraph.cu: nts_host_paths_to_blocks); the graph edits it asks for are applied here"""
+        import ctypes as C
+        from ._lib import check, lib, ptr
+        G, n_paths, n_seg = self.G, len(path_off) - 1, len(lo)
+        if not n_paths:
+            return []
+        if self._dev is None:
+            self._cums()
+        up, down = self._range_sums(lo, hi)
+        up, down = np.ascontiguousarray(up, dtype=np.int64), np.ascontiguousarray(down, dtype=np.int64)
+        big = np.ascontiguousarray(self.big, dtype=np.int64)
+        i0 = np.searchsorted(big, lo)
+        cnt = np.maximum(np.searchsorted(big, hi) - i0, 0)
+        tot = int(cnt.sum())
+        cuts = big[np.repeat(i0, cnt) + (np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt))] if tot else big[:0]
+        ids = np.unique(np.concatenate([lo, hi, cuts, cuts + 1]))
+        pos = np.ascontiguousarray(self.POS[:, ids], dtype=np.int64)
+        ctg = np.ascontiguousarray(self.CTG[:, ids], dtype=np.int32)
+        cap = n_seg + tot + 2
+        i64 = lambda n: np.empty(n, dtype=np.int64)          # noqa: E731
+        b_off, b_n, b_first, b_last = i64(cap + 1), i64(cap), i64(cap), i64(cap)
+        b_ori, b_ctg = np.empty((cap, G), dtype=np.int8), np.empty((cap, G), dtype=np.int32)
+        b_fpos, b_lpos = np.empty((cap, G), dtype=np.int64), np.empty((cap, G), dtype=np.int64)
+        o_lo, o_hi, o_dir = i64(cap), i64(cap), np.empty(cap, dtype=np.int8)
+        r_lo, r_hi, e_u, e_v = i64(cap), i64(cap), i64(cap), i64(cap)
+        counts = (C.c_int64 * 4)()
+        p8 = lambda x: x.ctypes.data_as(C.POINTER(C.c_int8))      # noqa: E731
+        path_off = np.ascontiguousarray(path_off, dtype=np.int64)
+        lo, hi = np.ascontiguousarray(lo, dtype=np.int64), np.ascontiguousarray(hi, dtype=np.int64)
+        sdir = np.ascontiguousarray(sdir, dtype=np.int8)
+        check(lib.nts_host_paths_to_blocks(n_paths, ptr(path_off, C.c_int64), ptr(lo, C.c_int64), ptr(hi, C.c_int64), p8(sdir), G,
+                                           ptr(up, C.c_int64), ptr(down, C.c_int64), ptr(ids, C.c_int64), len(ids),
+                                           ptr(pos, C.c_int64), ctg.ctypes.data_as(C.POINTER(C.c_int32)), ptr(big, C.c_int64),
+                                           len(big), int(self.bp), float(self.m), 4, cap, ptr(b_off, C.c_int64), ptr(b_n, C.c_int64),
+                                           ptr(b_first, C.c_int64), ptr(b_last, C.c_int64), p8(b_ori),
+                                           b_ctg.ctypes.data_as(C.POINTER(C.c_int32)), ptr(b_fpos, C.c_int64), ptr(b_lpos, C.c_int64),
+                                           ptr(o_lo, C.c_int64), ptr(o_hi, C.c_int64), p8(o_dir), ptr(r_lo, C.c_int64),
+                                           ptr(r_hi, C.c_int64), ptr(e_u, C.c_int64), ptr(e_v, C.c_int64), counts))
+        nb, no, nr, ne = (int(x) for x in counts)
+        segs = list(zip(o_lo[:no].tolist(), o_hi[:no].tolist(), o_dir[:no].tolist()))
+        off = b_off[:nb + 1].tolist()
+        ori = [[chr(c) for c in row] for row in b_ori[:nb].tolist()]
+        ctg_l, fp, lp = b_ctg[:nb].tolist(), b_fpos[:nb].tolist(), b_lpos[:nb].tolist()
+        blocks = [Block(segs[off[i]:off[i + 1]], ctg_l[i], ori[i], f, l, fp[i], lp[i], n)
+                  for i, (f, l, n) in enumerate(zip(b_first[:nb].tolist(), b_last[:nb].tolist(), b_n[:nb].tolist()))]
+        if ne:
+            self._remove_edges(e_u[:ne].copy(), e_v[:ne].copy())
+        if nr:
+            rl, rh = r_lo[:nr], r_hi[:nr]
+            n = rh - rl + 1
+            self._remove_vertices(np.repeat(rl, n) + (np.arange(int(n.sum())) - np.repeat(np.cumsum(n) - n, n)))
+        return blocks
+
     # ------------------------------------------------------------------ paths -> blocks (one round)
     def _extract_blocks(self):
         """find_paths -> find_synteny_blocks -> check_for_indels -> filter_synteny_blocks(4) for the current graph.
@@ -1019,6 +1092,13 @@ class SyntenyEngine:
         as a compact block table; only the components with a non-(i, i+1) edge, and the runs holding a vertex whose
         position was overwritten after round 0, are walked on the host."""
         if self._dev is None:
+            if self.native:
+                poff, lo, hi, sdir = self._find_paths(as_arrays=True)
+                self._tick("paths")
+                self.stats["paths"] = len(poff) - 1
+                blocks = self._host_blocks_native(poff, lo, hi, sdir)
+                self._tick("blocks")
+                return blocks
             paths = self._find_paths()
             self._tick("paths")
             self.stats["paths"] = len(paths)
@@ -1027,18 +1107,21 @@ class SyntenyEngine:
             blocks = self._split_indels(blocks)
             self._tick("indels")
             return self._filter_small(blocks, 4)
-        paths, (ds, de) = self._find_paths(device_pure=True)
+        paths, (ds, de) = self._find_paths(device_pure=True, as_arrays=self.native)
         self._tick("p_walk")
         res = self._dev["runs_to_blocks"](ds, de, self.bp, float(self.m), 4)
         self._tick("b_dev")
-        blocks = self._blocks_from_paths(paths)
-        self._tick("b_host_blocks")
-        blocks = self._split_indels(blocks)
-        self._tick("b_host_indels")
-        blocks = self._filter_small(blocks, 4)
-        self._tick("b_host_small")
+        if self.native:
+            blocks = self._host_blocks_native(*paths)
+            n_host = len(paths[0]) - 1
+        else:
+            blocks = self._blocks_from_paths(paths)
+            blocks = self._split_indels(blocks)
+            blocks = self._filter_small(blocks, 4)
+            n_host = len(paths)
+        self._tick("b_host")
         lo, hi = res["b_lo"].astype(np.int64), res["b_hi"].astype(np.int64)
-        self.stats["paths"] = len(paths) + len(lo) + len(res["r_lo"])
+        self.stats["paths"] = n_host + len(lo) + len(res["r_lo"])
         if len(lo):
             o = np.argsort(lo)
             lo, hi, up = lo[o], hi[o], res["b_dir"][o] > 0
@@ -1060,7 +1143,7 @@ class SyntenyEngine:
         if len(res["cuts"]):
             c = res["cuts"].astype(np.int64)
             self._remove_edges(c, c + 1)
-        self.stats["dev_runs"] = self.stats.get("dev_runs", []) + [[int(len(ds)), int(len(lo)), int(len(res["r_lo"])), int(len(res["cuts"])), len(paths)]]
+        self.stats["dev_runs"] = self.stats.get("dev_runs", []) + [[int(len(ds)), int(len(lo)), int(len(res["r_lo"])), int(len(res["cuts"])), n_host]]
         self._tick("b_apply")
         return blocks
 
