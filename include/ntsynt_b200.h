@@ -344,12 +344,11 @@ int nts_host_walk_paths_sparse(const int32_t* nbr, int64_t V0, const int64_t* st
  * 364-426; bin/synteny_block.py:48-65) for the host-walked paths of a round, given as segments with their range sums and
  * a small table of the positions / contigs of the vertices involved; see csrc/nts_hostgraph.cu for the argument list. */
 int nts_host_paths_to_blocks(int64_t n_paths, const int64_t* path_off, const int64_t* seg_lo, const int64_t* seg_hi,
-                             const int8_t* seg_dir, uint32_t G, const int64_t* up, const int64_t* down, const int64_t* ids,
-                             int64_t n_ids, const int64_t* pos, const int32_t* ctg, const int64_t* big, int64_t n_big, int64_t bp,
-                             double m_pct, int64_t min_mx, int64_t cap, int64_t* b_off, int64_t* b_n, int64_t* b_first,
-                             int64_t* b_last, int8_t* b_ori, int32_t* b_ctg, int64_t* b_fpos, int64_t* b_lpos, int64_t* o_lo,
-                             int64_t* o_hi, int8_t* o_dir, int64_t* r_lo, int64_t* r_hi, int64_t* e_u, int64_t* e_v,
-                             int64_t counts[4]);
+                             const int8_t* seg_dir, uint32_t G, const int64_t* up, const int64_t* down, const int64_t* cuts,
+                             const int64_t* cut_off, const int64_t* pos, const int32_t* ctg, int64_t bp, double m_pct,
+                             int64_t min_mx, int64_t cap, int64_t* b_off, int64_t* b_n, int64_t* b_first, int64_t* b_last,
+                             int8_t* b_ori, int32_t* b_ctg, int64_t* b_fpos, int64_t* b_lpos, int64_t* o_lo, int64_t* o_hi,
+                             int8_t* o_dir, int64_t* r_lo, int64_t* r_hi, int64_t* e_u, int64_t* e_v, int64_t counts[4]);
 /* nts_host_simplify: run_graph_simplification on the round-0 graph (bin/ntsynt_synteny.py:548-590), candidate edges
  * visited in build_graph's edge-id order (subprojects/ntJoin/bin/ntjoin_utils.py:97-115).  cand = the n_cand vertices
  * with exactly three distinct neighbours, ascending; rank / inv = [G x V]; ctg = [G x ctg_stride].  For every edge

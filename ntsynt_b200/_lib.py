@@ -123,8 +123,8 @@ _SIGS = {
                                       C.POINTER(C.c_int8), i64p, C.c_int64, i64p, i64p]),
     "nts_host_walk_paths_sparse": (C.c_int, [C.POINTER(C.c_int32), C.c_int64, i64p, i64p, C.c_int64, i64p, C.c_int64, i64p, i64p,
                                              C.c_int64, i64p, i64p, C.POINTER(C.c_int8), i64p, C.c_int64, i64p, i64p]),
-    "nts_host_paths_to_blocks": (C.c_int, [C.c_int64, i64p, i64p, i64p, C.POINTER(C.c_int8), C.c_uint32, i64p, i64p, i64p, C.c_int64,
-                                           i64p, C.POINTER(C.c_int32), i64p, C.c_int64, C.c_int64, C.c_double, C.c_int64, C.c_int64,
+    "nts_host_paths_to_blocks": (C.c_int, [C.c_int64, i64p, i64p, i64p, C.POINTER(C.c_int8), C.c_uint32, i64p, i64p, i64p, i64p,
+                                           i64p, C.POINTER(C.c_int32), C.c_int64, C.c_double, C.c_int64, C.c_int64,
                                            i64p, i64p, i64p, i64p, C.POINTER(C.c_int8), C.POINTER(C.c_int32), i64p, i64p, i64p, i64p,
                                            C.POINTER(C.c_int8), i64p, i64p, i64p, i64p, i64p]),
     "nts_host_simplify": (C.c_int, [i64p, C.c_int64, u32p, u32p, C.POINTER(C.c_int32), C.c_int64, C.c_int64, C.c_uint32,

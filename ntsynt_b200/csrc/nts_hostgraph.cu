@@ -143,61 +143,49 @@ int nts_host_walk_paths_sparse(const int32_t* nbr, int64_t V0, const int64_t* st
  * 66-106, 364-426; bin/synteny_block.py:48-65) -- the host-walked paths of a round in one call.
  *   path p owns segments [path_off[p], path_off[p+1]) = runs lo..hi of consecutive ids traversed in direction dir;
  *   up / down [G x n_seg]: pairs (j, j+1), lo <= j < hi, whose position increases / decreases in each assembly;
- *   (ids ascending, pos / ctg [G x n_ids]): positions and contigs of every vertex the call looks at -- both ends of
- *   every segment and c, c + 1 for every large-spread pair c inside a segment;  big: those pairs, ascending.
+ *   segment j's large-spread pairs are cuts[cut_off[j] .. cut_off[j+1]) (ascending pair indices c, lo <= c < hi);
+ *   pos / ctg [G x n_col]: positions and contigs of the vertices the call looks at, by column:
+ *       j -> seg_lo[j];  n_seg + j -> seg_hi[j];  2 n_seg + k -> cuts[k];  2 n_seg + n_cut + k -> cuts[k] + 1.
  * A path's block = its segments from the last junction with a contig change on (the reference never flags the earlier
  * part); per assembly '+' / '-' if every step increases / decreases, else by the m_pct rule, else the block's segments
  * are deleted.  The block is then cut at every junction / inner pair whose |dpos| spread exceeds bp (that edge is
  * removed), and pieces with fewer than min_mx minimizers are deleted.
  * Outputs: blocks (b_off into the out segment arrays o_lo/o_hi/o_dir, b_n, b_first, b_last, b_ori / b_ctg / b_fpos /
  * b_lpos [n_blocks x G]); deleted segments (r_lo, r_hi); removed edges (e_u, e_v).  cap bounds every output array
- * (n_seg + number of large-spread pairs inside segments + 1 is enough).  counts[4] = blocks, out segments, deleted
- * segments, removed edges. */
+ * (n_seg + n_cut + 1 is enough).  counts[4] = blocks, out segments, deleted segments, removed edges. */
 int nts_host_paths_to_blocks(int64_t n_paths, const int64_t* path_off, const int64_t* seg_lo, const int64_t* seg_hi,
-                             const int8_t* seg_dir, uint32_t G, const int64_t* up, const int64_t* down, const int64_t* ids,
-                             int64_t n_ids, const int64_t* pos, const int32_t* ctg, const int64_t* big, int64_t n_big, int64_t bp,
-                             double m_pct, int64_t min_mx, int64_t cap, int64_t* b_off, int64_t* b_n, int64_t* b_first,
-                             int64_t* b_last, int8_t* b_ori, int32_t* b_ctg, int64_t* b_fpos, int64_t* b_lpos, int64_t* o_lo,
-                             int64_t* o_hi, int8_t* o_dir, int64_t* r_lo, int64_t* r_hi, int64_t* e_u, int64_t* e_v,
-                             int64_t counts[4])
+                             const int8_t* seg_dir, uint32_t G, const int64_t* up, const int64_t* down, const int64_t* cuts,
+                             const int64_t* cut_off, const int64_t* pos, const int32_t* ctg, int64_t bp, double m_pct,
+                             int64_t min_mx, int64_t cap, int64_t* b_off, int64_t* b_n, int64_t* b_first, int64_t* b_last,
+                             int8_t* b_ori, int32_t* b_ctg, int64_t* b_fpos, int64_t* b_lpos, int64_t* o_lo, int64_t* o_hi,
+                             int8_t* o_dir, int64_t* r_lo, int64_t* r_hi, int64_t* e_u, int64_t* e_v, int64_t counts[4])
 {
-    if (!path_off || !counts || (n_paths && (!seg_lo || !seg_hi || !seg_dir || !up || !down || !ids || !pos || !ctg)))
+    if (!path_off || !counts || (n_paths && (!seg_lo || !seg_hi || !seg_dir || !up || !down || !cut_off || !pos || !ctg)))
         return fail(NTS_ERR_ARG, "null argument");
     if (G < 1 || G > 32) return fail(NTS_ERR_ARG, "between 1 and 32 assemblies are supported");
     const int64_t n_seg = n_paths ? path_off[n_paths] : 0;
+    const int64_t n_cut = n_seg ? cut_off[n_seg] : 0;
+    const int64_t n_col = 2 * n_seg + 2 * n_cut;
     int64_t nb = 0, no = 0, nr = 0, ne = 0;
-    bool missing = false;
-    auto at = [&](int64_t v) -> int64_t {
-        const int64_t* p = std::lower_bound(ids, ids + n_ids, v);
-        if (p == ids + n_ids || *p != v) { missing = true; return 0; }
-        return (int64_t)(p - ids);
-    };
+    auto col_first = [&](int64_t j) { return seg_dir[j] > 0 ? j : n_seg + j; };
+    auto col_last = [&](int64_t j) { return seg_dir[j] > 0 ? n_seg + j : j; };
     auto first_of = [&](int64_t j) { return seg_dir[j] > 0 ? seg_lo[j] : seg_hi[j]; };
     auto last_of = [&](int64_t j) { return seg_dir[j] > 0 ? seg_hi[j] : seg_lo[j]; };
-    auto spread_gt = [&](int64_t u, int64_t v) {          // max |dpos| - min |dpos| over the assemblies > bp
-        const int64_t iu = at(u), iv = at(v);
-        int64_t mx = 0, mn = INT64_MAX;
-        for (uint32_t a = 0; a < G; ++a) {
-            int64_t d = pos[a * n_ids + iv] - pos[a * n_ids + iu];
-            if (d < 0) d = -d;
-            mx = std::max(mx, d); mn = std::min(mn, d);
-        }
-        return mx - mn > bp;
-    };
     std::vector<int64_t> inc(G), dec(G);
     std::vector<int8_t> ori(G);
-    struct Seg { int64_t lo, hi; int8_t d; };
+    struct Seg { int64_t lo, hi; int8_t d; int64_t c_lo, c_hi; };      // c_*: columns of the positions of lo / hi
     std::vector<Seg> cur;
-    std::vector<std::vector<Seg>> pieces;
+    std::vector<int64_t> piece_end;                                     // pieces = consecutive ranges of `all`
+    std::vector<Seg> all;
     for (int64_t p = 0; p < n_paths; ++p) {
         const int64_t s0 = path_off[p], s1 = path_off[p + 1];
         if (s1 <= s0) continue;
         // the block starts after the last junction where some assembly changes contig
         int64_t start = s0;
         for (int64_t j = s0 + 1; j < s1; ++j) {
-            const int64_t iu = at(last_of(j - 1)), iv = at(first_of(j));
+            const int64_t cu = col_last(j - 1), cv = col_first(j);
             bool chg = false;
-            for (uint32_t a = 0; a < G && !chg; ++a) chg = ctg[a * n_ids + iu] != ctg[a * n_ids + iv];
+            for (uint32_t a = 0; a < G && !chg; ++a) chg = ctg[a * n_col + cu] != ctg[a * n_col + cv];
             if (chg) start = j;
         }
         int64_t n = 0;
@@ -210,9 +198,9 @@ int nts_host_paths_to_blocks(int64_t n_paths, const int64_t* path_off, const int
                 dec[a] += seg_dir[j] > 0 ? d_ : u_;
             }
             if (j > start) {
-                const int64_t iu = at(last_of(j - 1)), iv = at(first_of(j));
+                const int64_t cu = col_last(j - 1), cv = col_first(j);
                 for (uint32_t a = 0; a < G; ++a) {
-                    const int64_t d = pos[a * n_ids + iv] - pos[a * n_ids + iu];
+                    const int64_t d = pos[a * n_col + cv] - pos[a * n_col + cu];
                     if (d > 0) ++inc[a]; else if (d < 0) ++dec[a];
                 }
             }
@@ -235,67 +223,80 @@ int nts_host_paths_to_blocks(int64_t n_paths, const int64_t* path_off, const int
             }
             continue;
         }
-        const int64_t i_f = at(first_of(start));
-        // indel cuts
-        pieces.clear(); cur.clear();
+        const int64_t c_first = col_first(start);
+        // indel cuts: junctions and inner pairs whose |dpos| spread exceeds bp
+        all.clear(); piece_end.clear();
         for (int64_t j = start; j < s1; ++j) {
             const int64_t slo = seg_lo[j], shi = seg_hi[j];
             const int8_t d = seg_dir[j];
             if (j > start) {
-                const int64_t u = last_of(j - 1), v = first_of(j);
-                if (spread_gt(u, v)) {
+                const int64_t cu = col_last(j - 1), cv = col_first(j);
+                int64_t mx = 0, mn = INT64_MAX;
+                for (uint32_t a = 0; a < G; ++a) {
+                    int64_t dd = pos[a * n_col + cv] - pos[a * n_col + cu];
+                    if (dd < 0) dd = -dd;
+                    mx = std::max(mx, dd); mn = std::min(mn, dd);
+                }
+                if (mx - mn > bp) {
                     if (ne >= cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
-                    e_u[ne] = u; e_v[ne] = v; ++ne;
-                    pieces.push_back(cur); cur.clear();
+                    e_u[ne] = last_of(j - 1); e_v[ne] = first_of(j); ++ne;
+                    piece_end.push_back((int64_t)all.size());
                 }
             }
-            const int64_t* c0 = shi > slo ? std::lower_bound(big, big + n_big, slo) : big;
-            const int64_t* c1 = shi > slo ? std::lower_bound(big, big + n_big, shi) : big;
-            if (c1 > c0) {
-                for (const int64_t* c = c0; c < c1; ++c) {
+            const int64_t k0 = cut_off[j], k1 = cut_off[j + 1];
+            if (k1 > k0) {
+                for (int64_t k = k0; k < k1; ++k) {
                     if (ne >= cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
-                    e_u[ne] = *c; e_v[ne] = *c + 1; ++ne;
+                    e_u[ne] = cuts[k]; e_v[ne] = cuts[k] + 1; ++ne;
                 }
                 if (d > 0) {
-                    int64_t a0 = slo;
-                    for (const int64_t* c = c0; c < c1; ++c) { cur.push_back({a0, *c, 1}); pieces.push_back(cur); cur.clear(); a0 = *c + 1; }
-                    cur.push_back({a0, shi, 1});
+                    int64_t a0 = slo, ca = j;
+                    for (int64_t k = k0; k < k1; ++k) {
+                        all.push_back({a0, cuts[k], 1, ca, 2 * n_seg + k}); piece_end.push_back((int64_t)all.size());
+                        a0 = cuts[k] + 1; ca = 2 * n_seg + n_cut + k;
+                    }
+                    all.push_back({a0, shi, 1, ca, n_seg + j});
                 } else {
-                    int64_t a0 = shi;
-                    for (const int64_t* c = c1; c-- > c0;) { cur.push_back({*c + 1, a0, -1}); pieces.push_back(cur); cur.clear(); a0 = *c; }
-                    cur.push_back({slo, a0, -1});
+                    int64_t a0 = shi, ca = n_seg + j;
+                    for (int64_t k = k1; k-- > k0;) {
+                        all.push_back({cuts[k] + 1, a0, -1, 2 * n_seg + n_cut + k, ca}); piece_end.push_back((int64_t)all.size());
+                        a0 = cuts[k]; ca = 2 * n_seg + k;
+                    }
+                    all.push_back({slo, a0, -1, j, ca});
                 }
             } else {
-                cur.push_back({slo, shi, d});
+                all.push_back({slo, shi, d, j, n_seg + j});
             }
         }
-        pieces.push_back(cur);
-        for (const auto& pc : pieces) {
+        piece_end.push_back((int64_t)all.size());
+        int64_t q0 = 0;
+        for (int64_t q1 : piece_end) {
             int64_t pn = 0;
-            for (const Seg& sg : pc) pn += sg.hi - sg.lo + 1;
+            for (int64_t i = q0; i < q1; ++i) pn += all[i].hi - all[i].lo + 1;
             if (pn < min_mx) {
-                for (const Seg& sg : pc) {
+                for (int64_t i = q0; i < q1; ++i) {
                     if (nr >= cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
-                    r_lo[nr] = sg.lo; r_hi[nr] = sg.hi; ++nr;
+                    r_lo[nr] = all[i].lo; r_hi[nr] = all[i].hi; ++nr;
                 }
-                continue;
+            } else if (q1 > q0) {
+                if (nb >= cap || no + (q1 - q0) > cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
+                const Seg& sf = all[q0];
+                const Seg& sl = all[q1 - 1];
+                const int64_t f = sf.d > 0 ? sf.lo : sf.hi, cf = sf.d > 0 ? sf.c_lo : sf.c_hi;
+                const int64_t l = sl.d > 0 ? sl.hi : sl.lo, cl = sl.d > 0 ? sl.c_hi : sl.c_lo;
+                b_off[nb] = no; b_n[nb] = pn; b_first[nb] = f; b_last[nb] = l;
+                for (uint32_t a = 0; a < G; ++a) {
+                    b_ori[nb * G + a] = ori[a];
+                    b_ctg[nb * G + a] = ctg[a * n_col + c_first];            // the contigs of the path's block, also for its pieces
+                    b_fpos[nb * G + a] = pos[a * n_col + cf];
+                    b_lpos[nb * G + a] = pos[a * n_col + cl];
+                }
+                for (int64_t i = q0; i < q1; ++i) { o_lo[no] = all[i].lo; o_hi[no] = all[i].hi; o_dir[no] = all[i].d; ++no; }
+                ++nb;
             }
-            if (nb >= cap || no + (int64_t)pc.size() > cap) return fail(NTS_ERR_OVERFLOW, "paths_to_blocks: output capacity too small");
-            const int64_t f = pc.front().d > 0 ? pc.front().lo : pc.front().hi;
-            const int64_t l = pc.back().d > 0 ? pc.back().hi : pc.back().lo;
-            const int64_t jf = at(f), jl = at(l);
-            b_off[nb] = no; b_n[nb] = pn; b_first[nb] = f; b_last[nb] = l;
-            for (uint32_t a = 0; a < G; ++a) {
-                b_ori[nb * G + a] = ori[a];
-                b_ctg[nb * G + a] = ctg[a * n_ids + i_f];             // the contigs of the path's block, also for its pieces
-                b_fpos[nb * G + a] = pos[a * n_ids + jf];
-                b_lpos[nb * G + a] = pos[a * n_ids + jl];
-            }
-            for (const Seg& sg : pc) { o_lo[no] = sg.lo; o_hi[no] = sg.hi; o_dir[no] = sg.d; ++no; }
-            ++nb;
+            q0 = q1;
         }
     }
-    if (missing) return fail(NTS_ERR_ARG, "paths_to_blocks: a vertex the walk needs is not in the position table");
     b_off[nb] = no;
     counts[0] = nb; counts[1] = no; counts[2] = nr; counts[3] = ne;
     return NTS_OK;

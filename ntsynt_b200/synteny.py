@@ -293,6 +293,7 @@ class SyntenyEngine:
         self.sparse = set()                             # vertices that may hold a non-(i,i+1) edge
         self._ctg0 = {}                                 # (assembly, base vertex) -> round-0 contig, for the few overwritten entries
         self._dev = j if "gather" in j else None        # device-resident form: columns are read through gathers
+        self._rk_cache, self._inv_cache = {}, {}
         if self._dev is not None:
             # the O(V) columns stay on the device (nts_graph_gather / _range_sums / _neigh / _runs_to_blocks); the host
             # holds the weight-filtered graph (nbr, conn), the three sparse lists and what later rounds write
@@ -526,13 +527,42 @@ class SyntenyEngine:
     # ------------------------------------------------------------------ round-0 adjacency (implicit in ranks)
     def _rank_of(self, a, u):
         if self._dev is not None:
-            return int(self._dev["gather"]("rank", np.array([u], dtype=np.int64))[a, 0])
+            got = self._rk_cache.get((a, u))
+            if got is None:
+                got = int(self._dev["gather"]("rank", np.array([u], dtype=np.int64))[a, 0])
+            return got
         return int(self.RANK[a, u])
 
     def _at_rank(self, a, r):
         if self._dev is not None:
-            return int(self._dev["gather"]("inv", np.array([r], dtype=np.int64))[a, 0])
+            got = self._inv_cache.get((a, r))
+            if got is None:
+                got = int(self._dev["gather"]("inv", np.array([r], dtype=np.int64))[a, 0])
+            return got
         return int(self.INV[a, r])
+
+    def _prefetch_edge_keys(self, edges):
+        """device-resident form: _edge_key0 of these round-0 edges reads ranks, rank neighbours and contigs one value at
+        a time; fetch them in four gathers"""
+        if self._dev is None or not edges:
+            return
+        G, V0 = self.G, self.V0
+        ends = np.unique(np.array([x for e in edges for x in e if x < V0], dtype=np.int64))
+        if not len(ends):
+            return
+        rk = self._dev["gather"]("rank", ends)                            # [G, n]
+        for a in range(G):
+            self._rk_cache.update(zip(((a, v) for v in ends.tolist()), rk[a].tolist()))
+        nxt = np.unique(rk.astype(np.int64) + 1)
+        nxt = nxt[nxt < V0]
+        iv = self._dev["gather"]("inv", nxt)                              # vertex at rank r + 1, per assembly
+        for a in range(G):
+            self._inv_cache.update(zip(((a, r) for r in nxt.tolist()), iv[a].tolist()))
+        xs = np.unique(iv.astype(np.int64))
+        rx = self._dev["gather"]("rank", xs)
+        for a in range(G):
+            self._rk_cache.update(zip(((a, v) for v in xs.tolist()), rx[a].tolist()))
+        self.CTG.prefetch(np.concatenate([ends, xs]))
 
     def _adjacent(self, a, u, v):
         if u >= self.V0 or v >= self.V0:
@@ -1046,10 +1076,13 @@ class SyntenyEngine:
         i0 = np.searchsorted(big, lo)
         cnt = np.maximum(np.searchsorted(big, hi) - i0, 0)
         tot = int(cnt.sum())
-        cuts = big[np.repeat(i0, cnt) + (np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt))] if tot else big[:0]
-        ids = np.unique(np.concatenate([lo, hi, cuts, cuts + 1]))
-        pos = np.ascontiguousarray(self.POS[:, ids], dtype=np.int64)
-        ctg = np.ascontiguousarray(self.CTG[:, ids], dtype=np.int32)
+        cut_off = np.zeros(n_seg + 1, dtype=np.int64)
+        np.cumsum(cnt, out=cut_off[1:])
+        cuts = np.ascontiguousarray(big[np.repeat(i0, cnt) + (np.arange(tot) - np.repeat(cut_off[:-1], cnt))]) if tot else big[:0]
+        # columns of the position table: segment starts, segment ends, cut pairs c, c + 1
+        cols = np.concatenate([lo, hi, cuts, cuts + 1])
+        pos = np.ascontiguousarray(self.POS[:, cols], dtype=np.int64)
+        ctg = np.ascontiguousarray(self.CTG[:, cols], dtype=np.int32)
         cap = n_seg + tot + 2
         i64 = lambda n: np.empty(n, dtype=np.int64)          # noqa: E731
         b_off, b_n, b_first, b_last = i64(cap + 1), i64(cap), i64(cap), i64(cap)
@@ -1062,21 +1095,25 @@ class SyntenyEngine:
         path_off = np.ascontiguousarray(path_off, dtype=np.int64)
         lo, hi = np.ascontiguousarray(lo, dtype=np.int64), np.ascontiguousarray(hi, dtype=np.int64)
         sdir = np.ascontiguousarray(sdir, dtype=np.int8)
+        self._tick("bh_prep")
         check(lib.nts_host_paths_to_blocks(n_paths, ptr(path_off, C.c_int64), ptr(lo, C.c_int64), ptr(hi, C.c_int64), p8(sdir), G,
-                                           ptr(up, C.c_int64), ptr(down, C.c_int64), ptr(ids, C.c_int64), len(ids),
-                                           ptr(pos, C.c_int64), ctg.ctypes.data_as(C.POINTER(C.c_int32)), ptr(big, C.c_int64),
-                                           len(big), int(self.bp), float(self.m), 4, cap, ptr(b_off, C.c_int64), ptr(b_n, C.c_int64),
+                                           ptr(up, C.c_int64), ptr(down, C.c_int64), ptr(cuts if tot else np.zeros(1, np.int64), C.c_int64),
+                                           ptr(cut_off, C.c_int64), ptr(pos, C.c_int64), ctg.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           int(self.bp), float(self.m), 4, cap, ptr(b_off, C.c_int64), ptr(b_n, C.c_int64),
                                            ptr(b_first, C.c_int64), ptr(b_last, C.c_int64), p8(b_ori),
                                            b_ctg.ctypes.data_as(C.POINTER(C.c_int32)), ptr(b_fpos, C.c_int64), ptr(b_lpos, C.c_int64),
                                            ptr(o_lo, C.c_int64), ptr(o_hi, C.c_int64), p8(o_dir), ptr(r_lo, C.c_int64),
                                            ptr(r_hi, C.c_int64), ptr(e_u, C.c_int64), ptr(e_v, C.c_int64), counts))
         nb, no, nr, ne = (int(x) for x in counts)
+        self._tick("bh_c")
         segs = list(zip(o_lo[:no].tolist(), o_hi[:no].tolist(), o_dir[:no].tolist()))
         off = b_off[:nb + 1].tolist()
         ori = [[chr(c) for c in row] for row in b_ori[:nb].tolist()]
         ctg_l, fp, lp = b_ctg[:nb].tolist(), b_fpos[:nb].tolist(), b_lpos[:nb].tolist()
         blocks = [Block(segs[off[i]:off[i + 1]], ctg_l[i], ori[i], f, l, fp[i], lp[i], n)
                   for i, (f, l, n) in enumerate(zip(b_first[:nb].tolist(), b_last[:nb].tolist(), b_n[:nb].tolist()))]
+        self._tick("bh_wrap")
+        self.stats.setdefault("host_blocks", []).append([n_paths, n_seg, nb, no, nr, ne])
         if ne:
             self._remove_edges(e_u[:ne].copy(), e_v[:ne].copy())
         if nr:
@@ -1420,11 +1457,13 @@ class SyntenyEngine:
                 cid[missing] = nv
             # pass 1: which base vertices get a new position / contig (assembly a only writes row a)
             touched, changed_per_asm = [], []
+            cur_P, cur_C = self.POS[:, cid], self.CTG[:, cid]                     # one gather each, in `common` order
             for a in range(G):
                 kh, kp, kc, _ = lists[a]
-                vid = cid[np.searchsorted(common, kh)]
-                cur_c = self.CTG[a, vid]
-                changed = (self.POS[a, vid] != kp) | (cur_c != kc)
+                j_ = np.searchsorted(common, kh)
+                vid = cid[j_]
+                cur_c = cur_C[a, j_]
+                changed = (cur_P[a, j_] != kp) | (cur_c != kc)
                 sel = changed & (vid < self.V0)
                 tb = vid[sel]
                 for v_, c_ in zip(tb.tolist(), cur_c[sel].tolist()):           # keep the round-0 contig of what gets overwritten
@@ -1569,7 +1608,9 @@ class SyntenyEngine:
                         new_c.append(key)
                     else:
                         old_c.append(key)
-        old_c = sorted(set(old_c), key=self._old_edge_key)
+        old_c = set(old_c)
+        self._prefetch_edge_keys([e for e in old_c if e not in self._edge_birth])
+        old_c = sorted(old_c, key=self._old_edge_key)
         new_c = sorted(set(new_c), key=lambda e: fresh_pos[e])
         out = []
         for s, t in old_c + new_c:
