@@ -17,7 +17,8 @@ void part_scratch_release(nts_ctx* ctx);
 int part_insert(nts_ctx* ctx, cudaStream_t st, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, uint64_t m,
                 const uint32_t* prev, uint32_t* out, uint64_t alloc_bytes, int mode, bool* done);
 void part_check(nts_ctx* ctx, bool* overflowed, uint64_t* ovf_items);
-int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done);
+int pair_insert(nts_ctx* ctx, nts_bf* bf, nts_bf* and_dst, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done,
+                bool* anded);
 enum { APPLY_SET = 0, APPLY_AND = 1, APPLY_OR = 2 };      // nts_part.cuh
 
 static thread_local std::string g_err;
@@ -638,12 +639,12 @@ static int bf_insert_direct(nts_ctx* ctx, nts_bf* bf, const nts_genome* g, const
 }
 
 // bits(genome) into a filter.  mode APPLY_OR: bf |= bits (the reference's bf->insert(seq), src/ntsynt_make_common_bf.cpp:130);
-// APPLY_SET: bf = bits (no zero-fill needed); APPLY_AND: bf = prev & bits with prev a different filter of the same size
-// (one level of the cascade, cpp:136-160).  Large filters take the partitioned path (nts_part.cuh); *partitioned says so.
-static int bf_insert_mode(nts_bf* bf, const nts_bf* prev, const nts_genome* g, uint32_t k, int mode, bool* partitioned)
+// APPLY_SET: bf = bits; APPLY_AND: dst = dst & bits with bf as the scratch level filter of the same size (one level of the
+// cascade, cpp:136-160; `dst` is updated in place -- its device storage may be swapped with the scratch filter's).
+// Large filters take a partitioned path (nts_bin.cuh, or nts_part.cuh with NTS_BF_IMPL=3).
+static int bf_insert_mode(nts_bf* bf, nts_bf* dst, const nts_genome* g, uint32_t k, int mode)
 {
     nts_ctx* ctx = bf->ctx;
-    if (partitioned) *partitioned = false;
     const HashTables* tabs = nullptr;
     int rc = get_tables(ctx, k, &tabs);
     if (rc) return rc;
@@ -654,22 +655,25 @@ static int bf_insert_mode(nts_bf* bf, const nts_bf* prev, const nts_genome* g, u
     bool done = false;
     if (v->total_valid) {
         rc = part_insert(ctx, ctx->stream, device_view(g, v), tabs, v->total_valid, bf->bytes * 8,
-                         mode == APPLY_AND ? prev->words.p : bf->words.p, bf->words.p, bf->alloc_bytes, mode, &done);
+                         mode == APPLY_AND ? dst->words.p : bf->words.p, bf->words.p, bf->alloc_bytes, mode, &done);
         if (rc) return rc;
     }
-    if (done) { if (partitioned) *partitioned = true; return NTS_OK; }
+    if (done) {
+        if (mode == APPLY_AND) std::swap(dst->words, bf->words);      // the three-pass apply wrote dst & bits into the scratch
+        return NTS_OK;
+    }
     // zero-fill (SET / AND), then OR the genome in -- large filters with the binning + apply pair (nts_bin.cuh), small
-    // ones with one RED.OR per k-mer -- then a separate AND pass
+    // ones with one RED.OR per k-mer; the AND is fused into the pair's apply pass or runs as a separate kernel
     if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
+    bool anded = false;
     if (v->total_valid) {
-        if ((rc = pair_insert(ctx, bf, device_view(g, v), tabs, v->total_valid, &done))) return rc;
-        if (done && partitioned) *partitioned = true;
+        if ((rc = pair_insert(ctx, bf, mode == APPLY_AND ? dst : nullptr, device_view(g, v), tabs, v->total_valid, &done, &anded))) return rc;
         if (!done && (rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
     }
-    if (mode == APPLY_AND) {
+    if (mode == APPLY_AND && !anded) {
         ProfScope prof(ctx, PROF_BF_COMBINE, (double)bf->alloc_bytes);
         bf_combine_kernel<<<grid_for(ctx, n16 / 4 + 1, 256, 16), 256, 0, ctx->stream>>>(
-            reinterpret_cast<uint4*>(bf->words.p), reinterpret_cast<const uint4*>(prev->words.p), n16, 0);
+            reinterpret_cast<uint4*>(dst->words.p), reinterpret_cast<const uint4*>(bf->words.p), n16, 0);
         ctx->launches++;
         NTS_CUDA(cudaGetLastError());
     }
@@ -677,22 +681,28 @@ static int bf_insert_mode(nts_bf* bf, const nts_bf* prev, const nts_genome* g, u
 }
 
 // synchronise and make sure the last partitioned insert did not exhaust its overflow list; if it did, redo it directly
-static int bf_finish_insert(nts_bf* bf, const nts_bf* prev, const nts_genome* g, uint32_t k, int mode)
+// (only the three-pass variant has such a list).  AND: `keep` is a copy of dst taken before the insert.
+static int bf_finish_insert(nts_bf* bf, nts_bf* dst, const nts_genome* g, uint32_t k, int mode)
 {
     nts_ctx* ctx = bf->ctx;
     NTS_CUDA(cudaStreamSynchronize(ctx->stream));
     bool over = false;
     part_check(ctx, &over, nullptr);
     if (!over) return NTS_OK;
-    // pathological input (one k-mer making up a large part of the genome): OR is idempotent, SET / AND start over
+    // pathological input (one k-mer making up a large part of the genome): OR is idempotent, SET starts over; AND: the
+    // swap left the previous dst in `bf` untouched, so the level is rebuilt in `dst` and ANDed into `bf`, then swapped back
     const HashTables* tabs = nullptr;
     int rc = get_tables(ctx, k, &tabs);
     if (rc) return rc;
     const nts_view* v = nullptr;
     if ((rc = get_plain_view(g, k, &v))) return rc;
-    if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
-    if ((rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
-    if (mode == APPLY_AND && (rc = bf_combine(bf, prev, 0, false))) return rc;
+    if (mode == APPLY_AND) {
+        if ((rc = bf_fill(dst, 0)) || (rc = bf_insert_direct(ctx, dst, g, v, tabs)) || (rc = bf_combine(bf, dst, 0, false))) return rc;
+        std::swap(dst->words, bf->words);
+    } else {
+        if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
+        if ((rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
+    }
     NTS_CUDA(cudaStreamSynchronize(ctx->stream));
     return NTS_OK;
 }
@@ -702,7 +712,7 @@ int nts_bf_insert_genome_async(nts_bf* bf, const nts_genome* g, uint32_t k)
     if (!bf || !g) return fail(NTS_ERR_ARG, "null argument");
     if (bf->ctx != g->ctx) return fail(NTS_ERR_ARG, "filter and genome live on different contexts");
     NTS_CUDA(cudaSetDevice(bf->ctx->device));
-    return bf_insert_mode(bf, nullptr, g, k, APPLY_OR, nullptr);
+    return bf_insert_mode(bf, nullptr, g, k, APPLY_OR);
 }
 
 int nts_bf_insert_genome(nts_bf* bf, const nts_genome* g, uint32_t k)
@@ -718,7 +728,7 @@ int nts_bf_set_genome(nts_bf* bf, const nts_genome* g, uint32_t k)
     if (!bf || !g) return fail(NTS_ERR_ARG, "null argument");
     if (bf->ctx != g->ctx) return fail(NTS_ERR_ARG, "filter and genome live on different contexts");
     NTS_CUDA(cudaSetDevice(bf->ctx->device));
-    int rc = bf_insert_mode(bf, nullptr, g, k, APPLY_SET, nullptr);
+    int rc = bf_insert_mode(bf, nullptr, g, k, APPLY_SET);
     if (rc) return rc;
     return bf_finish_insert(bf, nullptr, g, k, APPLY_SET);
 }
@@ -745,9 +755,9 @@ int nts_bf_or(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 1, t
 int nts_bf_and_async(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, src, 0, false); }
 
 /* src/ntsynt_make_common_bf.cpp:107-160 in one call: common = AND over the genomes of bits(genome), genomes in the
- * caller's (sorted-path) order.  Genome 0 goes into one filter; every further genome is built as
- * next = current & bits(genome) in the other filter (the cascade level), and the two swap.  On return `common` holds
- * the result and `level` is scratch. */
+ * caller's (sorted-path) order.  Genome 0 goes into `common`; every further genome is built in `level` (the cascade
+ * level) and ANDed into `common` region by region inside the apply pass.  On return `common` holds the result and
+ * `level` is scratch. */
 int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k)
 {
     if (!common || !genomes || n < 1 || (n > 1 && !level)) return fail(NTS_ERR_ARG, "null argument");
@@ -757,17 +767,11 @@ int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* 
         if (!genomes[i] || genomes[i]->ctx != ctx) return fail(NTS_ERR_ARG, "bad genome");
     NTS_CUDA(cudaSetDevice(ctx->device));
     ProfScope prof(ctx, PROF_BF_BUILD, 0.0, true);
-    nts_bf* cur = common;
-    nts_bf* other = level;
-    int rc = bf_insert_mode(cur, nullptr, genomes[0], k, APPLY_SET, nullptr);
-    if (rc || (rc = bf_finish_insert(cur, nullptr, genomes[0], k, APPLY_SET))) return rc;
-    for (uint32_t i = 1; i < n; ++i) {
-        if ((rc = bf_insert_mode(other, cur, genomes[i], k, APPLY_AND, nullptr)) ||
-            (rc = bf_finish_insert(other, cur, genomes[i], k, APPLY_AND)))
+    int rc = bf_insert_mode(common, nullptr, genomes[0], k, APPLY_SET);
+    if (rc || (rc = bf_finish_insert(common, nullptr, genomes[0], k, APPLY_SET))) return rc;
+    for (uint32_t i = 1; i < n; ++i)
+        if ((rc = bf_insert_mode(level, common, genomes[i], k, APPLY_AND)) || (rc = bf_finish_insert(level, common, genomes[i], k, APPLY_AND)))
             return rc;
-        std::swap(cur, other);
-    }
-    if (cur != common) std::swap(common->words, level->words);     // same size, same context: hand the result over
     return NTS_OK;
 }
 
