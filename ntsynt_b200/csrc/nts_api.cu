@@ -17,8 +17,7 @@ void part_scratch_release(nts_ctx* ctx);
 int part_insert(nts_ctx* ctx, cudaStream_t st, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, uint64_t m,
                 const uint32_t* prev, uint32_t* out, uint64_t alloc_bytes, int mode, bool* done);
 void part_check(nts_ctx* ctx, bool* overflowed, uint64_t* ovf_items);
-int pair_insert(nts_ctx* ctx, nts_bf* bf, nts_bf* and_dst, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done,
-                bool* anded);
+int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done);
 enum { APPLY_SET = 0, APPLY_AND = 1, APPLY_OR = 2 };      // nts_part.cuh
 
 static thread_local std::string g_err;
@@ -663,14 +662,13 @@ static int bf_insert_mode(nts_bf* bf, nts_bf* dst, const nts_genome* g, uint32_t
         return NTS_OK;
     }
     // zero-fill (SET / AND), then OR the genome in -- large filters with the binning + apply pair (nts_bin.cuh), small
-    // ones with one RED.OR per k-mer; the AND is fused into the pair's apply pass or runs as a separate kernel
+    // ones with one RED.OR per k-mer; then the AND pass
     if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
-    bool anded = false;
     if (v->total_valid) {
-        if ((rc = pair_insert(ctx, bf, mode == APPLY_AND ? dst : nullptr, device_view(g, v), tabs, v->total_valid, &done, &anded))) return rc;
+        if ((rc = pair_insert(ctx, bf, device_view(g, v), tabs, v->total_valid, &done))) return rc;
         if (!done && (rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
     }
-    if (mode == APPLY_AND && !anded) {
+    if (mode == APPLY_AND) {
         ProfScope prof(ctx, PROF_BF_COMBINE, (double)bf->alloc_bytes);
         bf_combine_kernel<<<grid_for(ctx, n16 / 4 + 1, 256, 16), 256, 0, ctx->stream>>>(
             reinterpret_cast<uint4*>(dst->words.p), reinterpret_cast<const uint4*>(bf->words.p), n16, 0);
@@ -756,8 +754,7 @@ int nts_bf_and_async(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, sr
 
 /* src/ntsynt_make_common_bf.cpp:107-160 in one call: common = AND over the genomes of bits(genome), genomes in the
  * caller's (sorted-path) order.  Genome 0 goes into `common`; every further genome is built in `level` (the cascade
- * level) and ANDed into `common` region by region inside the apply pass.  On return `common` holds the result and
- * `level` is scratch. */
+ * level) and ANDed into `common`.  On return `common` holds the result and `level` is scratch. */
 int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k)
 {
     if (!common || !genomes || n < 1 || (n > 1 && !level)) return fail(NTS_ERR_ARG, "null argument");

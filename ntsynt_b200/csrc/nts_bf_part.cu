@@ -52,11 +52,6 @@ struct PairScratch {
     DevBuf<uint64_t> bucket_off, chunk_first;
     DevBuf<uint32_t> bucket_cap;
     DevBuf<unsigned int> cursor;
-    // fused apply (bf_apply_fused_kernel): grid layout with / without and-CTAs, chunks per region, progress counters
-    DevBuf<uint64_t> cta_first_set, cta_first_and;
-    DevBuf<uint32_t> n_chunks_r;
-    DevBuf<unsigned int> progress;         // [2 * 1024] zero_done, chunks_done
-    uint64_t grid_set = 0, grid_and = 0;
     // plan of the current use
     uint32_t P = 0, shift = 0;
     uint64_t n_chunks = 0, n_items = 0;
@@ -65,7 +60,6 @@ struct PairScratch {
 static std::map<std::pair<nts_ctx*, int>, PairScratch*> g_pair_scratch;
 static constexpr int BIN_THREADS = 512, BIN_ITEMS = 16, BIN_TILE = BIN_THREADS * BIN_ITEMS;
 static constexpr uint32_t CHUNK_ITEMS = 4096;
-static constexpr uint32_t FUSED_STAGE_CTAS = 16, FUSED_AND_CTAS = 16;
 
 static void pair_scratch_release(nts_ctx* ctx)
 {
@@ -119,24 +113,9 @@ static int pair_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t total_valid
     if (sc->items.n < off[P] && sc->items.alloc(off[P]) != cudaSuccess) { scratch_drop(ctx, slot); return NTS_OK; }   // no memory: direct path
     if (sc->bucket_off.n < 1025) {
         if (sc->bucket_off.alloc(1025) != cudaSuccess || sc->chunk_first.alloc(1025) != cudaSuccess ||
-            sc->bucket_cap.alloc(1024) != cudaSuccess || sc->cursor.alloc(1024) != cudaSuccess ||
-            sc->cta_first_set.alloc(1025) != cudaSuccess || sc->cta_first_and.alloc(1025) != cudaSuccess ||
-            sc->n_chunks_r.alloc(1024) != cudaSuccess || sc->progress.alloc(2048) != cudaSuccess)
+            sc->bucket_cap.alloc(1024) != cudaSuccess || sc->cursor.alloc(1024) != cudaSuccess)
             return fail(NTS_ERR_NOMEM, "device allocation failed (partition tables)");
     }
-    // grid layout of the fused apply: per region [stage CTAs][item chunks][and-CTAs]
-    std::vector<uint64_t> first_set(P + 1, 0), first_and(P + 1, 0);
-    std::vector<uint32_t> nch(P);
-    for (uint32_t b = 0; b < P; ++b) {
-        nch[b] = (uint32_t)(chunk_first[b + 1] - chunk_first[b]);
-        first_set[b + 1] = first_set[b] + FUSED_STAGE_CTAS + nch[b];
-        first_and[b + 1] = first_and[b] + FUSED_STAGE_CTAS + nch[b] + FUSED_AND_CTAS;
-    }
-    if (first_and[P] > 0x7FFFFFF0ull) return NTS_OK;
-    sc->grid_set = first_set[P]; sc->grid_and = first_and[P];
-    NTS_CUDA(cudaMemcpyAsync(sc->cta_first_set.p, first_set.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    NTS_CUDA(cudaMemcpyAsync(sc->cta_first_and.p, first_and.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    NTS_CUDA(cudaMemcpyAsync(sc->n_chunks_r.p, nch.data(), P * 4, cudaMemcpyHostToDevice, ctx->stream));
     NTS_CUDA(cudaMemcpyAsync(sc->bucket_off.p, off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     NTS_CUDA(cudaMemcpyAsync(sc->chunk_first.p, chunk_first.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     NTS_CUDA(cudaMemcpyAsync(sc->bucket_cap.p, cap.data(), P * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -179,45 +158,16 @@ static int pair_apply(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf)
     return NTS_OK;
 }
 
-// pass 2, fused form (see bf_apply_fused_kernel): REDs into bf through L2-staged regions; and_dst != null: and_dst &= bf
-// region by region while each is still in L2
-static int pair_apply_fused(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, nts_bf* and_dst)
-{
-    PairScratch* sc = g_pair_scratch[{ctx, slot}];
-    NTS_CUDA(cudaMemsetAsync(sc->progress.p, 0, 2048 * 4, st));
-    ApplyPlan ap;
-    ap.cta_first = and_dst ? sc->cta_first_and.p : sc->cta_first_set.p;
-    ap.n_chunks = sc->n_chunks_r.p;
-    ap.zero_done = sc->progress.p; ap.chunks_done = sc->progress.p + 1024;
-    ap.n_zero = FUSED_STAGE_CTAS; ap.n_and = and_dst ? FUSED_AND_CTAS : 0;
-    ProfScope prof(ctx, PROF_BF_APPLY, (double)sc->n_items, false, st);
-    bf_apply_fused_kernel<<<(unsigned)(and_dst ? sc->grid_and : sc->grid_set), 256, 0, st>>>(
-        sc->items.p, sc->bucket_off.p, sc->bucket_cap.p, sc->cursor.p, ap, sc->P, sc->shift, CHUNK_ITEMS, bf->words.p,
-        and_dst ? and_dst->words.p : nullptr, bf->alloc_bytes / 4);
-    ctx->launches++;
-    NTS_CUDA(cudaGetLastError());
-    return NTS_OK;
-}
-
-// OR bits(genome) into bf with the pair; and_dst != null: then and_dst &= bf, fused into the apply pass.
-// *done = false (nothing launched) when the pair does not apply.  NTS_BF_FUSED=0 selects the unfused apply kernel.
-int pair_insert(nts_ctx* ctx, nts_bf* bf, nts_bf* and_dst, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done,
-                bool* anded)
+// OR bits(genome) into bf with the pair; *done = false (nothing launched) when the pair does not apply
+int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done)
 {
     *done = false;
-    if (anded) *anded = false;
     bool ok = false;
     int rc = pair_prepare(ctx, 0, bf->bytes * 8, total_valid, &ok);
     if (rc || !ok) return rc;
-    const char* ef = getenv("NTS_BF_FUSED");
-    const bool fused = !(ef && ef[0] == '0');
     {
         ProfScope prof(ctx, PROF_BF_INSERT, (double)total_valid);
-        if ((rc = pair_bin(ctx, 0, ctx->stream, bf, gv, tabs, total_valid))) return rc;
-        if (fused) {
-            if ((rc = pair_apply_fused(ctx, 0, ctx->stream, bf, and_dst))) return rc;
-            if (anded) *anded = and_dst != nullptr;
-        } else if ((rc = pair_apply(ctx, 0, ctx->stream, bf))) return rc;
+        if ((rc = pair_bin(ctx, 0, ctx->stream, bf, gv, tabs, total_valid)) || (rc = pair_apply(ctx, 0, ctx->stream, bf))) return rc;
     }
     ctx->part_inserts++;
     *done = true;

@@ -173,121 +173,5 @@ __global__ void __launch_bounds__(256) bf_apply_kernel(const uint32_t* __restric
     }
 }
 
-// pass 2, fused form: the grid is laid out region by region as
-//     [Z stage CTAs][the region's item chunks][A and-CTAs (AND mode only)]
-// and CTAs are dispatched in blockIdx order, so a CTA only ever waits for CTAs that are already resident:
-//   stage CTAs  bring the region into L2 with coalesced line prefetches (one streaming DRAM read instead of a
-//               32-byte fill behind every first RED to a sector) and count themselves in zero_done[r];
-//   chunk CTAs  wait for zero_done[r] == Z, then issue their RED.ORs -- all of them L2 hits -- and count themselves
-//               in chunks_done[r];
-//   and-CTAs    wait for chunks_done[r] == number of chunks, then dst[region] &= bits[region] (the cascade level of
-//               src/ntsynt_make_common_bf.cpp:136-160) while the region is still in L2.
-// Against the unfused form this turns the sector-granular DRAM read-modify-write of the whole filter into streaming
-// traffic and removes the separate AND pass over both filters.
-struct ApplyPlan {
-    const uint64_t* cta_first;     // [P + 1] first CTA of every region
-    const uint32_t* n_chunks;      // [P] item chunks of every region
-    unsigned int* zero_done;       // [P]
-    unsigned int* chunks_done;     // [P]
-    uint32_t n_zero, n_and;        // CTAs per region that zero / AND
-};
-
-__device__ __forceinline__ void wait_count(const unsigned int* p, unsigned int want)
-{
-    if (threadIdx.x == 0) {
-        unsigned int v;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); if (v < want) __nanosleep(64); } while (v < want);
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void signal_count(unsigned int* p)
-{
-    __threadfence();               // this thread's stores / REDs are performed before the count moves
-    __syncthreads();
-    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p) : "memory");
-}
-
-__global__ void __launch_bounds__(256) bf_apply_fused_kernel(const uint32_t* __restrict__ items, const uint64_t* __restrict__ bucket_off,
-                                const uint32_t* __restrict__ bucket_cap, const unsigned int* __restrict__ cursor, ApplyPlan ap,
-                                uint32_t n_buckets, uint32_t region_shift, uint32_t chunk_items /* = 4096 */,
-                                uint32_t* bits, uint32_t* and_dst /* null: SET */, uint64_t n_words /* of the filter */)
-{
-    uint32_t lo = 0, hi = n_buckets;          // region of this CTA: last b with cta_first[b] <= blockIdx.x
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (ap.cta_first[mid] <= blockIdx.x) lo = mid; else hi = mid;
-    }
-    const uint32_t b = lo;
-    const uint32_t local = (uint32_t)(blockIdx.x - ap.cta_first[b]);
-    const uint64_t w0 = ((uint64_t)b << region_shift) >> 5;                       // first word of the region
-    const uint64_t w1 = min(n_words, (((uint64_t)b + 1) << region_shift) >> 5);    // (the last region may be short)
-    const uint64_t q0 = w0 >> 2, q1 = (w1 + 3) >> 2;                               // in uint4 (the filter is padded to 16 bytes)
-    const uint32_t nch = ap.n_chunks[b];
-    if (local < ap.n_zero) {
-        const uint64_t per = (q1 - q0 + ap.n_zero - 1) / ap.n_zero;
-        const uint64_t a = q0 + per * local, e = min(q1, a + per);
-        const uint4* p = reinterpret_cast<const uint4*>(bits);
-        // one prefetch per 128-byte line (8 uint4)
-        for (uint64_t i = (a & ~7ull) + (uint64_t)threadIdx.x * 8; i < e; i += 256 * 8)
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(p + i));
-        signal_count(&ap.zero_done[b]);
-        return;
-    }
-    if (local < ap.n_zero + nch) {
-        const uint32_t c = local - ap.n_zero;
-        const uint32_t n = min(cursor[b], bucket_cap[b]);
-        const uint64_t start = (uint64_t)c * chunk_items;
-        uint4 v[4];
-        uint32_t cnt = 0, n4 = 0;
-        const uint32_t* src = items + bucket_off[b] + start;
-        if (start < n) {
-            cnt = (uint32_t)min((uint64_t)chunk_items, n - start);
-            n4 = cnt >> 2;
-            const uint4* src4 = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t i = threadIdx.x + u * 256;
-                if (i < n4) v[u] = __ldg(src4 + i);                                  // in flight while we wait for the zeros
-            }
-        }
-        wait_count(&ap.zero_done[b], ap.n_zero);
-        if (cnt) {
-            uint32_t* region = bits + w0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t i = threadIdx.x + u * 256;
-                if (i < n4) {
-                    atomicOr(&region[v[u].x >> 5], 1u << (v[u].x & 31));
-                    atomicOr(&region[v[u].y >> 5], 1u << (v[u].y & 31));
-                    atomicOr(&region[v[u].z >> 5], 1u << (v[u].z & 31));
-                    atomicOr(&region[v[u].w >> 5], 1u << (v[u].w & 31));
-                }
-            }
-            const uint32_t i = (n4 << 2) + threadIdx.x;
-            if (i < cnt) {
-                const uint32_t x = __ldg(&src[i]);
-                atomicOr(&region[x >> 5], 1u << (x & 31));
-            }
-        }
-        signal_count(&ap.chunks_done[b]);
-        return;
-    }
-    // and-CTA
-    const uint32_t k = local - ap.n_zero - nch;
-    wait_count(&ap.chunks_done[b], nch);
-    const uint64_t per = (q1 - q0 + ap.n_and - 1) / ap.n_and;
-    const uint64_t a = q0 + per * k, e = min(q1, a + per);
-    const uint4* src = reinterpret_cast<const uint4*>(bits);
-    uint4* dst = reinterpret_cast<uint4*>(and_dst);
-    for (uint64_t i = a + threadIdx.x; i < e; i += 256 * 4) {
-        uint4 x[4], y[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if (i + u * 256 < e) { x[u] = __ldcg(src + i + u * 256); y[u] = dst[i + u * 256]; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (i + u * 256 < e) dst[i + u * 256] = make_uint4(x[u].x & y[u].x, x[u].y & y[u].y, x[u].z & y[u].z, x[u].w & y[u].w);
-    }
-}
 
 }  // namespace nts

@@ -142,17 +142,14 @@ def test_heavy_hitter_kmers(cuda_ctx, impl):
 
 
 # ---------------------------------------------------------------------------------------- the production pair
-@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("shift", [14, 18, 21, 23, 27])
 @pytest.mark.parametrize("scale", [1.0, 0.6, 0.05])
-def test_pair_many_buckets_short_last_region_and_overflow_branch(cuda_ctx, small, shift, scale, fused):
+def test_pair_many_buckets_short_last_region_and_overflow_branch(cuda_ctx, small, shift, scale):
     """bf_bin_kernel + bf_apply_kernel with 2^shift-bit regions (m = 2.4e8 bits: 1024 buckets at shift 18 -- 14 asks
     for more than the 1024 the kernel supports and is widened --, 29 with a short last region at 23, 2 at 27) and
-    with capacities below the load (items past a bucket's capacity are applied with direct atomics); fused = the
-    apply pass stages every region in L2 and ANDs it into the running filter (bf_apply_fused_kernel), 0 = the plain
-    apply kernel + a separate AND pass"""
+    with capacities below the load (items past a bucket's capacity are applied with direct atomics)"""
     gens, nbytes, per = small
-    with env(NTS_BF_PARTITION=1, NTS_BF_REGION_SHIFT=shift, NTS_BF_CAP_SCALE=scale, NTS_BF_FUSED=fused):
+    with env(NTS_BF_PARTITION=1, NTS_BF_REGION_SHIFT=shift, NTS_BF_CAP_SCALE=scale):
         n0 = cuda_ctx.part_inserts
         bf, lvl = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
         bf.from_numpy(np.full(nbytes, 0xFF, dtype=np.uint8))
@@ -196,8 +193,7 @@ def test_default_plan_at_150_mbp_equals_direct_kernel_and_oracle(cuda_ctx):
     recs = _records(gens[0])
     assert np.array_equal(a, so.genome_bits(recs, K, nbytes))
     want = d0.to_numpy()
-    for knobs in (dict(NTS_BF_REGION_SHIFT=23), dict(NTS_BF_REGION_SHIFT=23, NTS_BF_CAP_SCALE=0.7), dict(NTS_BF_FUSED=0),
-                  dict(NTS_BF_IMPL=3)):
+    for knobs in (dict(NTS_BF_REGION_SHIFT=23), dict(NTS_BF_REGION_SHIFT=23, NTS_BF_CAP_SCALE=0.7), dict(NTS_BF_IMPL=3)):
         with env(**knobs):
             common.build_common(lvl, gens, K)
         assert np.array_equal(common.to_numpy(), want), knobs
