@@ -273,6 +273,9 @@ int nts_graph_lookup(nts_graph* g, const uint64_t* h1, uint64_t n, uint32_t* vid
  * assemblies (weight = popcount, all assembly weights are 1: bin/ntsynt_synteny.py:32). */
 int nts_graph_edges(nts_graph* g, uint64_t* n_edges);
 int nts_graph_download_edges(nts_graph* g, uint32_t* u, uint32_t* v, uint32_t* support);
+/* --filter Filter of the graph stage (bin/ntsynt_synteny.py:601-609; read_minimizers(tsv, repeat_bf),
+ * subprojects/ntJoin/bin/ntjoin_utils.py:182): out = the entries of `m` (a table of genome g) whose k-mer is not in bf */
+int nts_mxs_drop_in_bf(nts_ctx* ctx, const nts_mxs* m, const nts_genome* g, const nts_bf* bf, uint32_t k, nts_mxs** out);
 /* row range [off[c], off[c+1]) of every contig of a table (off has n_contigs + 1 entries); a new table made of row
  * ranges of other tables in the given order -- used to put the tables of a contig-sharded sketch back in contig order */
 int nts_mxs_contig_offsets(nts_mxs* m, uint32_t n_contigs, uint64_t* off);

@@ -107,6 +107,7 @@ _SIGS = {
     "nts_p2p_reduce_scatter": (C.c_int, [vp, C.c_int]),
     "nts_p2p_all_gather": (C.c_int, [vp]),
     "nts_p2p_reduce_and_of_or": (C.c_int, [vpp, C.c_uint32, vp]),
+    "nts_mxs_drop_in_bf": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vpp]),
     "nts_mxs_contig_offsets": (C.c_int, [vp, C.c_uint32, u64p]),
     "nts_mxs_concat": (C.c_int, [vp, vpp, u64p, u64p, C.c_uint64, vpp]),
     "nts_mxs_allgather": (C.c_int, [vp, vp, u64p, vpp]),

@@ -3,6 +3,8 @@
    ntsynt_make_common_bf  src/ntsynt_make_common_bf.cpp:46-72 (flags), :107-164 (behaviour, log lines)
    indexlr                bin/ntsynt_run_pipeline.smk:83-85 and ntjoin_utils.py:197-198 (both spellings)
    ntsynt_run.py          bin/ntsynt_run.py:10-50
+   ntsynt_make_repeat_bfs.py   bin/ntsynt_make_repeat_bfs.py:10-69
+   denovo_synteny_block_stats.py   analysis_scripts/denovo_synteny_block_stats.py
 """
 import argparse
 import os
@@ -113,6 +115,8 @@ def main_make_common_bf(argv=None):
     ap.add_argument("--bf", type=int, help="Bloom filter size in bytes (optional)")
     ap.add_argument("-t", type=int, default=12, help="Number of threads (accepted for compatibility)")
     ap.add_argument("--gpu", type=int, default=0)
+    ap.add_argument("--bf-format", choices=["btllib", "native"], default="btllib",
+                    help="layout of the .bf file: btllib's header (default; unpinned by any reference fixture) or our own container")
     try:
         args = ap.parse_args(argv)
     except SystemExit as exc:
@@ -133,7 +137,7 @@ def main_make_common_bf(argv=None):
     genomes = [ctx.upload(fasta.read_fasta(g)) for g in args.genome]
     bf = pipeline.build_common_bf(ctx, genomes, list(args.genome), args.k, args.fpr, nbytes=nbytes, log=print)
     print(f"Final Bloom filter FPR: {bf.fpr()}")
-    io.save_bf(args.p + ".bf", bf, args.k)
+    io.save_bf(args.p + ".bf", bf, args.k, fmt=args.bf_format)
     print("Done!", flush=True)
     return 0
 
@@ -210,10 +214,8 @@ def main_ntsynt_run(argv=None):
     args = ap.parse_args(argv)
     if args.n not in (0, len(args.FILES)):
         raise SystemExit("ntsynt_b200: only -n = number of assemblies (the pipeline's setting) is supported")
-    if args.filter:
-        raise SystemExit("ntsynt_b200: --filter (experimental repeat filtering) is not supported")
-    if args.interarrivals:
-        raise SystemExit("ntsynt_b200: --interarrivals is not supported")
+    if args.filter and not args.repeat:                            # bin/ntsynt_synteny.py:601-602
+        raise ValueError("If --filter is specified, must supply repeat Bloom filter with --repeat")
     from . import device, fasta, io, pipeline
     from .synteny import FA_TSV_RE, SyntenyEngine
     files = sorted(args.FILES, reverse=True)                       # bin/ntsynt_synteny.py:34
@@ -237,12 +239,121 @@ def main_ntsynt_run(argv=None):
         genomes.append(ctx.upload(pk))
         tables.append(device.MinimizerTable.from_numpy(ctx, h1, pos, ctg, genomes[-1]))
     common = io.load_bf(ctx, args.common)[0] if args.common else None
+    repeat = io.load_bf(ctx, args.repeat)[0] if args.repeat and args.filter else None
     be = pipeline.CudaBackend(ctx, genomes, [os.path.basename(f) for f in files], [p.names for p in packed],
-                              [[int(x) for x in p.lengths] for p in packed], args.k, common=common, round0=tables)
+                              [[int(x) for x in p.lengths] for p in packed], args.k, common=common, round0=tables,
+                              repeat=repeat, filter_mode=args.filter)
     eng = SyntenyEngine(be, args.k, args.w, args.w_rounds, args.bp, args.collinear_merge, args.z, m=args.m,
-                        simplify=args.simplify_graph, prefix=args.p, dev=args.dev, write_files=True, quiet=False)
+                        simplify=args.simplify_graph, prefix=args.p, dev=args.dev, write_files=True, quiet=False,
+                        interarrivals=args.interarrivals)
     if os.environ.get("NTSYNT_B200_NO_DOT") != "1":
         eng.dot_path = f"{args.p}.mx.dot"
     eng.run()
     print("DONE!", flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ ntsynt_make_repeat_bfs.py
+def parse_bf_size(text, ap):
+    "bin/ntsynt_make_repeat_bfs.py:10-24: <num>[BkMG]"
+    m = re.search(r"^(\d+)([BkMG])$", text)
+    if not m:
+        ap.print_help()
+        ap.error(f"Invalid input value for --bf: {text}")
+    num, unit = int(m.group(1)), m.group(2)
+    return {"B": num, "k": int(num * 1e3), "M": int(num * 1e6), "G": int(num * 1e9)}[unit]
+
+
+def main_make_repeat_bfs(argv=None):
+    """Bloom filter of the k-mers seen twice or more within an input genome (bin/ntsynt_make_repeat_bfs.py:56-69):
+    per genome a fresh filter; a k-mer whose bit is already set goes to the repeat filter, else its bit is set.
+    With one hash function that is: bit i of the repeat filter is set iff two or more k-mer occurrences of one
+    genome hash to i -- what nts_bf_insert_repeats computes (order-free, bit-exact vs the sequential statement)."""
+    import math
+    ap = argparse.ArgumentParser(description="Generating BF of k-mer 2+ multiplicities")
+    ap.add_argument("--genome", help="Input genome file(s)", nargs="+")
+    ap.add_argument("-k", help="K-mer size (bp)", required=True, type=int)
+    ap.add_argument("--bf", help="Bloom filter size [accepted units: B (bytes), k (kilobytes), M (megabytes), G (gigabytes)]",
+                    type=str)
+    ap.add_argument("-t", help="Number of threads [4] (accepted for compatibility)", required=False, type=int, default=4)
+    ap.add_argument("-p", help="Prefix for output BF", default="out.bf", type=str)
+    ap.add_argument("--fpr", help="False positive rate for Bloom filter. Only used if --bf is not specified. [0.01]",
+                    default=0.01, type=float)
+    ap.add_argument("--gpu", type=int, default=0)
+    ap.add_argument("--bf-format", choices=["btllib", "native"], default="btllib", help="layout of the .bf file")
+    args = ap.parse_args(argv)
+    if not args.genome:
+        ap.error("--genome is required")
+    from . import device, fasta, io
+    ctx = device.Context(args.gpu)
+    first = fasta.read_fasta(args.genome[0])
+    if not args.bf:
+        # approximate_bf_size (:26-34): every base of the first genome counts, N included
+        size_bits = math.ceil((-1 * int(sum(int(x) for x in first.lengths))) / math.log(1 - args.fpr))
+        bf_bytes = int(size_bits / 8)
+        print(f"Calculated Bloom filter size: {bf_bytes} bytes")
+    else:
+        bf_bytes = parse_bf_size(args.bf, ap)
+    nbytes = max(int(math.ceil(bf_bytes / 8.0)) * 8, 8)           # btllib rounds the array up to whole 64-bit words
+    rep, scratch = ctx.bloom(nbytes), ctx.bloom(nbytes)
+    for i, path in enumerate(args.genome):
+        g = ctx.upload(first if i == 0 else fasta.read_fasta(path))
+        scratch.clear()
+        rep.insert_repeats(scratch, g, args.k)
+        g.close()
+    io.save_bf(f"{args.p}.bf", rep, args.k, fmt=args.bf_format)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ block stats
+def block_stats(tsv, fais):
+    """analysis_scripts/denovo_synteny_block_stats.py: the ten summary numbers of a synteny-block TSV.
+    Returns (header list, value list) exactly as that script prints them."""
+    sizes = {}
+    for fai in fais:
+        if (mt := re.search(r"^(\S+).fai", fai)):
+            with open(fai, "r", encoding="utf-8") as fh:
+                sizes[os.path.basename(mt.group(1))] = sum(int(line.strip().split("\t")[1]) for line in fh)
+    lens, ids, tally = {}, {}, {}
+    with open(tsv, "r", encoding="utf-8") as fh:
+        for line in fh:
+            f = line.strip().split("\t")
+            lens.setdefault(f[1], []).append(int(f[4]) - int(f[3]))
+            ids.setdefault(f[1], []).append(f[0])
+            tally.setdefault(f[0], set()).add(f[1])
+    G = len(fais)
+    full = {a: [l for l, b in zip(lens[a], ids[a]) if len(tally[b]) >= G] for a in lens}
+
+    def ng50(blocks, size):
+        acc = 0
+        for b in sorted(blocks, reverse=True):
+            acc += b
+            if acc >= size * 0.5:
+                return b
+        return 0
+
+    num_blocks = sum(len(v) for v in lens.values()) / G
+    num_all = sum(len(v) for v in full.values()) / G
+    total = sum(sum(v) for v in lens.values()) / G
+    cov = sum(sum(v) / sizes[a] * 100 for a, v in lens.items()) / G
+    min_size, min_asm = sorted(((s, a) for a, s in sizes.items()), key=lambda x: x[0])[0]
+    cov_min = sum(lens[min_asm]) / min_size * 100
+    cov_all = sum(sum(v) / sizes[a] * 100 for a, v in full.items()) / G
+    avg = sum(np.mean(v) for v in lens.values()) / G
+    med = sum(np.median(v) for v in lens.values()) / G
+    a_ng50 = sum(ng50(v, sizes[a]) for a, v in lens.items()) / G
+    a_n50 = sum(ng50(v, sum(v)) for v in lens.values()) / G
+    head = ["Number_blocks", "Number_blocks_all_asm", "Average_coverage", "Average_coverage_all_asm",
+            "Coverage_min_genome_size", "Average_length", "Median_length", "Total_length", "NG50_length", "N50_length"]
+    return head, [int(num_blocks), int(num_all), cov, cov_all, cov_min, avg, med, total, int(a_ng50), int(a_n50)]
+
+
+def main_block_stats(argv=None):
+    ap = argparse.ArgumentParser(description="Compute de novo stats on synteny blocks")
+    ap.add_argument("--tsv", help="ntSynt synteny block file", required=True)
+    ap.add_argument("--fai", help="FAI files for the compared genomes", nargs="+", required=True)
+    args = ap.parse_args(argv)
+    head, vals = block_stats(args.tsv, args.fai)
+    print(*head, sep="\t")
+    print("\t".join(str(v) for v in vals))
     return 0

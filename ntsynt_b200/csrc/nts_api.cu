@@ -858,7 +858,6 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     if (!ctx || !g || !out) return fail(NTS_ERR_ARG, "null argument");
     if (g->ctx != ctx || (common && common->ctx != ctx) || (repeat && repeat->ctx != ctx))
         return fail(NTS_ERR_ARG, "objects live on different contexts");
-    if (common && repeat && common->bytes != repeat->bytes) return fail(NTS_ERR_ARG, "common and repeat filters differ in size");
     if (w < 1) return fail(NTS_ERR_ARG, "w must be >= 1");
     NTS_CUDA(cudaSetDevice(ctx->device));
     constexpr int THREADS = 512;
@@ -887,7 +886,9 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
     if ((rc = wait_ready(g))) return rc;
 
     uint64_t m = 0, mp = 0;
-    if (common) mod_params(common, &m, &mp); else if (repeat) mod_params(repeat, &m, &mp);
+    uint64_t rm = 0, rmp = 0;       // the repeat filter's own size (sized from another genome: bin/ntsynt_make_repeat_bfs.py:51)
+    if (repeat) mod_params(repeat, &rm, &rmp);
+    if (common) mod_params(common, &m, &mp); else { m = rm; mp = rmp; }
     // how often does a k-mer of this view pass the filter?  (sampled; only steers the candidate density)
     double pass = 1.0;
     if ((common || repeat) && w >= 128 && v->total_valid > (1u << 20)) {
@@ -899,7 +900,7 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
             ProfScope prof(ctx, PROF_SKETCH, 0.0);
             sketch_sample_kernel<<<(unsigned)((n_samp + 255) / 256), 256, 0, ctx->stream>>>(
                 device_view(g, v), tabs, common ? common->words.p : nullptr, repeat ? repeat->words.p : nullptr, m, mp,
-                v->total_valid, stride, d_cnt2.p);
+                rm, rmp, v->total_valid, stride, d_cnt2.p);
             ctx->launches++;
         }
         NTS_CUDA(cudaGetLastError());
@@ -1012,7 +1013,7 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
             if (sparse) {
                 unsigned int* esc_count = reinterpret_cast<unsigned int*>(d_total.p + 1);
                 sketch_sparse_kernel<THREADS, SCAP, CCAP><<<n_tiles, THREADS, smem_s, ctx->stream>>>(
-                    gv, tabs, cw, rw, m, mp, d_tiles.p, w, NT_s, C_s, T, tau_hi, so, d_esc.p, esc_count);
+                    gv, tabs, cw, rw, m, mp, rm, rmp, d_tiles.p, w, NT_s, C_s, T, tau_hi, so, d_esc.p, esc_count);
                 ctx->launches++;
                 NTS_CUDA(cudaGetLastError());
                 unsigned int n_esc = 0;
@@ -1020,12 +1021,12 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
                 NTS_CUDA(cudaStreamSynchronize(ctx->stream));
                 ctx->sketch_escalated += n_esc;
                 if (n_esc) {       // tiles with an unresolved window: the dense selector, every slot queried
-                    sketch_kernel<THREADS><<<n_esc, THREADS, smem, ctx->stream>>>(gv, tabs, cw, rw, m, mp, d_esc.p, w, T,
-                                                                                 KEY_MAX, so);
+                    sketch_kernel<THREADS><<<n_esc, THREADS, smem, ctx->stream>>>(gv, tabs, cw, rw, m, mp, rm, rmp, d_esc.p, w,
+                                                                                 T, KEY_MAX, so);
                     ctx->launches++;
                 }
             } else {
-                sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(gv, tabs, cw, rw, m, mp, d_tiles.p, w, T, tau, so);
+                sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(gv, tabs, cw, rw, m, mp, rm, rmp, d_tiles.p, w, T, tau, so);
                 ctx->launches++;
             }
         }
@@ -1197,5 +1198,111 @@ extern "C" int nts_mxs_concat(nts_ctx* ctx, nts_mxs* const* parts, const uint64_
     }
     NTS_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = m;
+    return NTS_OK;
+}
+
+namespace nts {
+// keep[i] = the k-mer of minimizer i (contig, pos) is NOT in the filter: ntHash2 of the k-mer from the seed tables
+// (a minimizer is an all-ACGT k-mer), bit h0 mod m
+__global__ void mxs_bf_keep_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ contig_base /* base index of every contig */,
+                                   const HashTables* __restrict__ tabs, uint32_t k, const uint32_t* __restrict__ pos,
+                                   const uint32_t* __restrict__ contig, uint64_t n, const uint32_t* __restrict__ bits, uint64_t m,
+                                   uint64_t mprime, uint32_t* __restrict__ keep)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t b = contig_base[contig[i]] + pos[i];
+    uint64_t fwd = 0, rev = 0;
+    for (uint32_t j = 0; j < k; ++j) {
+        const unsigned c = base_at(packed, b + j);
+        fwd ^= __ldg(&tabs->init_f[j * 4 + c]);
+        rev ^= __ldg(&tabs->init_r[j * 4 + c]);
+    }
+    const uint64_t idx = fast_mod(fwd + rev, m, mprime);
+    keep[i] = ((__ldg(&bits[idx >> 5]) >> (idx & 31)) & 1u) ? 0u : 1u;
+}
+
+__global__ void mxs_compact_kernel(const uint64_t* __restrict__ h1, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ ctg,
+                                   const uint32_t* __restrict__ keep, uint64_t n, unsigned long long* __restrict__ cursor_unused,
+                                   const uint64_t* __restrict__ off, uint64_t* __restrict__ o_h1, uint32_t* __restrict__ o_pos,
+                                   uint32_t* __restrict__ o_ctg)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const uint64_t o = off[i];
+    o_h1[o] = h1[i]; o_pos[o] = pos[i]; o_ctg[o] = ctg[i];
+}
+
+// exclusive prefix of 0/1 flags into 64-bit offsets (single CTA pass per 2^20 block is plenty for minimizer tables)
+__global__ void flags_scan_kernel(const uint32_t* __restrict__ keep, uint64_t n, uint64_t* __restrict__ off, unsigned long long* __restrict__ total)
+{
+    __shared__ uint64_t s_part[1024];
+    const uint64_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint64_t a = threadIdx.x * per, b = min(a + per, n);
+    uint64_t sum = 0;
+    for (uint64_t i = a; i < b; ++i) sum += keep[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (uint32_t i = 0; i < blockDim.x; ++i) { const uint64_t v = s_part[i]; s_part[i] = run; run += v; }
+        *total = run;
+    }
+    __syncthreads();
+    uint64_t run = s_part[threadIdx.x];
+    for (uint64_t i = a; i < b; ++i) { off[i] = run; run += keep[i]; }
+}
+}  // namespace nts
+
+/* read_minimizers(tsv, repeat_bf) of the graph stage's --filter Filter mode (subprojects/ntJoin/bin/ntjoin_utils.py:182):
+ * a minimizer whose k-mer is in the repeat filter is dropped from its file.  out = the entries of `m` (a table of
+ * genome g, in (contig, position) order) whose k-mer is not in `bf`. */
+extern "C" int nts_mxs_drop_in_bf(nts_ctx* ctx, const nts_mxs* m, const nts_genome* g, const nts_bf* bf, uint32_t k, nts_mxs** out)
+{
+    using namespace nts;
+    if (!ctx || !m || !g || !bf || !out) return fail(NTS_ERR_ARG, "null argument");
+    if (m->ctx != ctx || g->ctx != ctx || bf->ctx != ctx) return fail(NTS_ERR_ARG, "objects live on different contexts");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    const HashTables* tabs = nullptr;
+    int rc = get_tables(ctx, k, &tabs);
+    if (rc || (rc = wait_ready(g))) return rc;
+    const uint64_t n = m->count;
+    nts_mxs* o = new (std::nothrow) nts_mxs();
+    if (!o) return fail(NTS_ERR_NOMEM, "host allocation failed");
+    struct Guard { nts_mxs* p; ~Guard() { delete p; } } guard{o};
+    o->ctx = ctx; o->n_contigs = m->n_contigs;
+    unsigned long long total = 0;
+    DevBuf<uint32_t> keep;
+    DevBuf<uint64_t> off, cbase;
+    DevBuf<unsigned long long> d_total;
+    if (n) {
+        std::vector<uint64_t> base(g->n_contigs);
+        for (uint32_t c = 0; c < g->n_contigs; ++c) base[c] = g->contig_word_off[c] * 32;
+        if (keep.alloc(n) != cudaSuccess || off.alloc(n) != cudaSuccess || cbase.alloc(g->n_contigs) != cudaSuccess || d_total.alloc(1) != cudaSuccess)
+            return fail(NTS_ERR_NOMEM, "device allocation failed (repeat filter)");
+        NTS_CUDA(copy_h2d(ctx, cbase.p, base.data(), base.size() * 8));
+        uint64_t mm, mp;
+        mod_params(bf, &mm, &mp);
+        ProfScope prof(ctx, PROF_BF_REPEAT, (double)n);
+        mxs_bf_keep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(g->packed.p, cbase.p, tabs, k, m->pos.p, m->contig.p, n,
+                                                                                bf->words.p, mm, mp, keep.p);
+        flags_scan_kernel<<<1, 1024, 0, ctx->stream>>>(keep.p, n, off.p, d_total.p);
+        ctx->launches += 2;
+        NTS_CUDA(cudaGetLastError());
+        NTS_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));       // (also: `base` goes out of scope)
+    }
+    o->count = total;
+    const uint64_t a = total ? total : 1;
+    if (o->h1.alloc(a) != cudaSuccess || o->pos.alloc(a) != cudaSuccess || o->contig.alloc(a) != cudaSuccess)
+        return fail(NTS_ERR_NOMEM, "device allocation failed (minimizer table)");
+    if (total) {
+        mxs_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(m->h1.p, m->pos.p, m->contig.p, keep.p, n, nullptr, off.p,
+                                                                                o->h1.p, o->pos.p, o->contig.p);
+        ctx->launches++;
+        NTS_CUDA(cudaGetLastError());
+        NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = o; guard.p = nullptr;
     return NTS_OK;
 }

@@ -232,7 +232,8 @@ __device__ __forceinline__ SegAgg cta_exclusive_carry(SegAgg own, SegAgg* s_warp
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 2)
 sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
-              const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, const TileDesc* __restrict__ tiles,
+              const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
+              const TileDesc* __restrict__ tiles,
               uint32_t w, uint32_t T, uint64_t tau, SketchOut out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -295,10 +296,14 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
         uint32_t li[4];
         uint64_t lx[4];
         uint32_t nl = 0;
-        auto probe = [&](uint64_t idx) -> bool {
+        // the repeat filter has its own size (made from another genome than the common one's: bin/ntsynt_make_repeat_bfs.py:51)
+        auto probe = [&](uint64_t h, uint64_t idx) -> bool {
             bool keep = true;
             if (common) keep = (__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u;
-            if (keep && repeat) keep = !((__ldg(&repeat[idx >> 5]) >> (idx & 31)) & 1u);
+            if (keep && repeat) {
+                const uint64_t ridx = fast_mod(h, rm, rmprime);
+                keep = !((__ldg(&repeat[ridx >> 5]) >> (ridx & 31)) & 1u);
+            }
             return keep;
         };
         for (uint32_t i = max(c0, i_lo); i < min(c0 + C, n_end); ++i) {
@@ -309,7 +314,7 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
 #pragma unroll
                 for (uint32_t u = 0; u < 4; ++u) if (u == nl) { li[u] = i; lx[u] = idx; }
                 ++nl;
-            } else if (!probe(idx)) {
+            } else if (!probe(h, idx)) {
                 s_key[i] = KEY_MAX;
             }
         }
@@ -319,7 +324,10 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
             cwv[u] = 0xFFFFFFFFu; rwv[u] = 0;
             if (u < nl) {
                 if (common) cwv[u] = __ldg(&common[lx[u] >> 5]) >> (lx[u] & 31);
-                if (repeat) rwv[u] = __ldg(&repeat[lx[u] >> 5]) >> (lx[u] & 31);
+                if (repeat) {
+                    const uint64_t ridx = fast_mod(s_key[li[u]], rm, rmprime);
+                    rwv[u] = __ldg(&repeat[ridx >> 5]) >> (ridx & 31);
+                }
             }
         }
 #pragma unroll
@@ -338,7 +346,10 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
                 cw[u] = 0xFFFFFFFFu; rw[u] = 0;
                 if (i < n_end && i >= i_lo) {
                     if (common) cw[u] = __ldg(&common[idx >> 5]) >> (idx & 31);
-                    if (repeat) rw[u] = __ldg(&repeat[idx >> 5]) >> (idx & 31);
+                    if (repeat) {
+                        const uint64_t ridx = fast_mod(h[u], rm, rmprime);
+                        rw[u] = __ldg(&repeat[ridx >> 5]) >> (ridx & 31);
+                    }
                 }
             }
 #pragma unroll
@@ -481,7 +492,8 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
 // A few thousand evenly spaced k-mers of the view are hashed and looked up: the fraction that passes the filter
 // decides how many candidates per window the sparse sketch kernel needs (its exactness never depends on it).
 __global__ void sketch_sample_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
-                                     const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t total_valid,
+                                     const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
+                                     uint64_t total_valid,
                                      uint64_t stride, unsigned int* __restrict__ counts /* [0] passed, [1] sampled */)
 {
     __shared__ HashTables s_tabs;
@@ -493,7 +505,10 @@ __global__ void sketch_sample_kernel(GenomeView g, const HashTables* __restrict_
         const uint64_t idx = fast_mod(h0, m, mprime);
         bool keep = true;
         if (common) keep = (__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u;
-        if (keep && repeat) keep = !((__ldg(&repeat[idx >> 5]) >> (idx & 31)) & 1u);
+        if (keep && repeat) {
+            const uint64_t ridx = fast_mod(h0, rm, rmprime);
+            keep = !((__ldg(&repeat[ridx >> 5]) >> (ridx & 31)) & 1u);
+        }
         atomicAdd(&counts[1], 1u);
         if (keep) atomicAdd(&counts[0], 1u);
     });
@@ -516,7 +531,8 @@ __global__ void sketch_sample_kernel(GenomeView g, const HashTables* __restrict_
 template <int THREADS, int SCAP, int CCAP>
 __global__ void __launch_bounds__(THREADS, 2)
 sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
-                     const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, const TileDesc* __restrict__ tiles,
+                     const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
+              const TileDesc* __restrict__ tiles,
                      uint32_t w, uint32_t NT, uint32_t C, uint32_t T_dense, uint32_t tau_hi, SketchOut out,
                      TileDesc* __restrict__ esc, unsigned int* __restrict__ esc_count)
 {
@@ -597,7 +613,10 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
             if (i < ncand) {
                 const uint64_t idx = fast_mod(c_key[i], m, mprime);
                 if (common) cw[u] = __ldg(&common[idx >> 5]) >> (idx & 31);
-                if (repeat) rw[u] = __ldg(&repeat[idx >> 5]) >> (idx & 31);
+                if (repeat) {
+                    const uint64_t ridx = fast_mod(c_key[i], rm, rmprime);
+                    rw[u] = __ldg(&repeat[ridx >> 5]) >> (ridx & 31);
+                }
             }
         }
 #pragma unroll

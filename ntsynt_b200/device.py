@@ -263,6 +263,12 @@ class MinimizerTable:
     def __len__(self):
         return int(lib.nts_mxs_count(self._h))
 
+    def drop_in_filter(self, genome, bf, k):
+        "a new table without the minimizers whose k-mer is in `bf` (the graph stage's --filter Filter)"
+        h = C.c_void_p()
+        check(lib.nts_mxs_drop_in_bf(self.ctx._h, self._h, genome._h, bf._h, int(k), C.byref(h)))
+        return MinimizerTable(self.ctx, h, genome)
+
     def contig_offsets(self, n_contigs):
         "off[n_contigs + 1]: rows [off[c], off[c+1]) belong to contig c"
         off = np.zeros(n_contigs + 1, dtype=np.uint64)

@@ -4,24 +4,58 @@ import struct
 import numpy as np
 
 BF_MAGIC = b"NTSB200BF1\n"
+# btllib's KmerBloomFilter::save as remembered from btllib >= 1.5 (bloom_filter.hpp): a cpptoml table named after the
+# signature with the keys below, the line "[HeaderEnd]", then the raw bit array.  NOT pinned by any fixture of the
+# reference: there is no .bf file in the tree and btllib is not installable here.
+BTL_KMER_SIGNATURE = "[BTLKmerBloomFilter_v6]"
+BTL_HASH_FN = "ntHash_v2"
 
 
-def save_bf(path, bloom, k):
-    """<prefix>.bf written by ntsynt_make_common_bf (src/ntsynt_make_common_bf.cpp:164).  btllib's own file
-    format is not pinned by any reference fixture, so this is our container: magic, uint64 byte
-    count, uint32 k, raw bit array (byte = idx >> 3, bit = idx & 7, identical to btllib's in-memory layout)."""
-    bits = bloom.to_numpy()
+def save_bf(path, bloom, k, fmt="btllib"):
+    """<prefix>.bf written by ntsynt_make_common_bf (src/ntsynt_make_common_bf.cpp:164) / ntsynt_make_repeat_bfs.py.
+    fmt "btllib": btllib's KmerBloomFilter file layout (unpinned, see above) so that a stock `indexlr -s` can read it;
+    fmt "native": our own container (magic, uint64 byte count, uint32 k).  The payload is the same in both: the raw
+    bit array, byte = idx >> 3, bit = idx & 7 (btllib's in-memory layout)."""
+    bits = bloom.to_numpy() if hasattr(bloom, "to_numpy") else np.asarray(bloom, dtype=np.uint8)
     with open(path, "wb") as fh:
-        fh.write(BF_MAGIC)
-        fh.write(struct.pack("<QI", bits.size, int(k)))
+        if fmt == "native":
+            fh.write(BF_MAGIC)
+            fh.write(struct.pack("<QI", bits.size, int(k)))
+        elif fmt == "btllib":
+            fh.write((f"{BTL_KMER_SIGNATURE}\nbytes = {bits.size}\nhash_num = 1\nhash_fn = \"{BTL_HASH_FN}\"\nk = {int(k)}\n"
+                      "[HeaderEnd]\n").encode())
+        else:
+            raise ValueError(f"unknown Bloom filter file format {fmt!r}")
         fh.write(bits.tobytes())
 
 
 def load_bf_bytes(path):
+    "(bit array, k) from either file layout save_bf writes (btllib files: any key order, blank lines allowed)"
     with open(path, "rb") as fh:
-        if fh.read(len(BF_MAGIC)) != BF_MAGIC:
-            raise ValueError(f"{path}: not an ntsynt_b200 Bloom filter file (btllib .bf interchange is not supported)")
-        n, k = struct.unpack("<QI", fh.read(12))
+        head = fh.read(len(BF_MAGIC))
+        if head == BF_MAGIC:
+            n, k = struct.unpack("<QI", fh.read(12))
+        elif head.startswith(b"[BTL"):
+            fh.seek(0)
+            sig = fh.readline().decode().strip()
+            if not (sig.startswith("[BTLKmerBloomFilter_v") or sig.startswith("[BTLBloomFilter_v")):
+                raise ValueError(f"{path}: unsupported btllib Bloom filter signature {sig}")
+            meta = {}
+            while True:
+                line = fh.readline()
+                if not line:
+                    raise ValueError(f"{path}: truncated btllib Bloom filter header")
+                line = line.decode().strip()
+                if line == "[HeaderEnd]":
+                    break
+                if "=" in line:
+                    key, val = (x.strip() for x in line.split("=", 1))
+                    meta[key] = val.strip('"')
+            if int(meta.get("hash_num", "1")) != 1:
+                raise ValueError(f"{path}: only Bloom filters with one hash function are supported (ntSynt uses 1)")
+            n, k = int(meta["bytes"]), int(meta.get("k", 0))
+        else:
+            raise ValueError(f"{path}: not a Bloom filter file this library can read")
         bits = np.frombuffer(fh.read(n), dtype=np.uint8)
         if bits.size != n:
             raise ValueError(f"{path}: truncated Bloom filter file")

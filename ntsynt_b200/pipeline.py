@@ -60,7 +60,16 @@ def build_common_bf(ctx, genomes, paths, k, fpr=0.025, nbytes=None, log=None):
 class CudaBackend:
     "SyntenyEngine backend on the CUDA library (the only backend the package ships)"
 
-    def __init__(self, ctx, genomes, names, contig_names, contig_lengths, k, common=None, repeat=None, round0=None):
+    def __init__(self, ctx, genomes, names, contig_names, contig_lengths, k, common=None, repeat=None, round0=None,
+                 filter_mode=None):
+        """filter_mode (bin/ntsynt_synteny.py:172-187,601-609): "Indexlr" hands the repeat filter to the sketch kernel
+        (indexlr -r: a k-mer in it is never a minimizer), "Filter" drops the minimizers of every sketch whose k-mer is
+        in it (read_minimizers(tsv, repeat_bf), ntjoin_utils.py:182)."""
+        if filter_mode not in (None, "Filter", "Indexlr"):
+            raise ValueError(f"unknown repeat filter mode {filter_mode!r}")
+        if filter_mode and repeat is None:
+            raise ValueError("If --filter is specified, must supply repeat Bloom filter with --repeat")
+        self.filter_mode = filter_mode
         self.ctx, self.genomes = ctx, genomes
         self.names = list(names)
         self.contig_names = contig_names
@@ -72,10 +81,11 @@ class CudaBackend:
         self.timing = {"sketch_ms": 0.0, "join_ms": 0.0}
 
     def sketch(self, a, w, masks):
-        if masks is None and self.round0 is not None:
-            return self.round0[a]
         t0 = time.perf_counter()
-        mx = self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, repeat=None, masks=masks)
+        if masks is None and self.round0 is not None:
+            mx = self._drop_repeats(a, self.round0[a])      # tables read from TSV files (bin/ntsynt_run.py)
+        else:
+            mx = self._sketch(a, w, masks)
         self.timing["sketch_ms"] += (time.perf_counter() - t0) * 1e3
         if masks is None:
             return mx                      # round 0: stays on the device for the join
@@ -86,9 +96,20 @@ class CudaBackend:
     def sketch_table(self, a, w, masks):
         "a masked refinement sketch that stays on the device (consumed by MinimizerGraph.refine_filter)"
         t0 = time.perf_counter()
-        mx = self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, repeat=None, masks=masks)
+        mx = self._sketch(a, w, masks)
         self.timing["sketch_ms"] += (time.perf_counter() - t0) * 1e3
         return mx
+
+    def _sketch(self, a, w, masks):
+        rep = self.repeat if self.filter_mode == "Indexlr" else None
+        return self._drop_repeats(a, self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, repeat=rep, masks=masks))
+
+    def _drop_repeats(self, a, mx):
+        if self.filter_mode != "Filter":
+            return mx
+        out = mx.drop_in_filter(self.genomes[a], self.repeat, self.k)
+        mx.close()
+        return out
 
     def join(self, tables, order_asm):
         t0 = time.perf_counter()

@@ -237,8 +237,9 @@ class SyntenyEngine:
     """
 
     def __init__(self, backend, k, w, w_rounds, bp, collinear_merge, z, m=90, simplify=True, prefix="out",
-                 dev=False, write_files=True, quiet=False):
+                 dev=False, write_files=True, quiet=False, interarrivals=False):
         self.be = backend
+        self.interarrivals = interarrivals
         self.G = len(backend.names)
         if self.G < 2:
             raise ValueError("at least two assemblies are required")
@@ -1228,6 +1229,54 @@ class SyntenyEngine:
                 fh.write(text)
         return text
 
+    def _print_interarrivals(self, blocks):
+        """print_interarrivals (bin/ntsynt_synteny.py:557-564): <prefix>.interarrivals.tsv, one distance per line between
+        consecutive minimizers of every block of the initial graph, block by block, assembly by assembly.  (The
+        reference's block order follows igraph vertex ids, which come from iterating a Python set of strings -- it is
+        not reproducible between runs; the file is a bag of distances.)"""
+        parts = []
+        if blocks:
+            ids = [np.concatenate([seg_ids(sg) for sg in b.segs]) if len(b.segs) > 1 else seg_ids(b.segs[0]) for b in blocks]
+            n = np.array([len(x) for x in ids], dtype=np.int64)
+            P = np.asarray(self.POS[:, np.concatenate(ids)], dtype=np.int64)
+            D = np.abs(np.diff(P, axis=1))
+            off = np.cumsum(n) - n
+            parts = [D[:, o:o + c - 1].ravel() for o, c in zip(off.tolist(), n.tolist()) if c > 1]
+        flat = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+        text = "".join(f"{v}\n" for v in flat.tolist())
+        self.outputs["interarrivals"] = text
+        if self.write_files:
+            with open(f"{self.prefix}.interarrivals.tsv", "w", encoding="utf-8") as fh:
+                fh.write(text)
+        return text
+
+    def _check_non_overlapping(self, blocks):
+        """check_non_overlapping (bin/ntsynt_synteny.py:234-253), the --dev check of the final blocks: walking the
+        blocks in output order, a block whose extent on some assembly shares >= z bases with an earlier block on the
+        same contig gets a warning on stderr (one per block and assembly).  Blocks shorter than z on any assembly are
+        neither checked nor remembered.  Returns the warnings as (assembly name, contig name, start, end)."""
+        warnings = []
+        if not blocks:
+            return warnings
+        st, en, ctg = self._block_coords(blocks)
+        ok = ((en - st) >= self.z).all(axis=1)
+        hits = []
+        for a in range(self.G):
+            seen = {}                                   # contig -> ([starts], [ends]) of the earlier blocks
+            for i in np.flatnonzero(ok).tolist():
+                c, s_, e_ = int(ctg[i, a]), int(st[i, a]), int(en[i, a])
+                ss, ee = seen.setdefault(c, ([], []))
+                if ss:
+                    ov = np.minimum(np.asarray(ee), e_) - np.maximum(np.asarray(ss), s_)
+                    if (ov >= max(self.z, 1)).any():
+                        hits.append((i, a, self.names[a], self.be.contig_names[a][c], s_, e_))
+                ss.append(s_); ee.append(e_)
+        for _, _, nm, cn, s_, e_ in sorted(hits):       # the reference walks block-major
+            print("WARNING: detected overlapping segments for this block:", nm, cn, s_, e_, "\n", file=sys.stderr, flush=True)
+            warnings.append((nm, cn, s_, e_))
+        self.outputs["overlap_warnings"] = warnings
+        return warnings
+
     # ------------------------------------------------------------------ merge (ntsynt_synteny.py:428-472)
     def _merge_collinear(self, blocks):
         out = []
@@ -1723,6 +1772,8 @@ class SyntenyEngine:
         self._tick("filter0")
         self.log("Finding synteny blocks")
         blocks = self._extract_blocks()
+        if self.interarrivals:
+            self._print_interarrivals(blocks)
         ordered = self._sort_blocks(blocks)
         self._tick("filter_sort")
         if not ordered:
@@ -1748,6 +1799,8 @@ class SyntenyEngine:
                 merged = self._merge_collinear(ordered) if ordered else []
                 merged = [b for b in merged if self._long_enough(b)]
                 merged = self._merge_collinear(merged) if merged else []
+                if self.dev:
+                    self._check_non_overlapping(merged)
                 self._emit("final", merged, verbose=True)
             prev_w = new_w
         self._tick("emit")

@@ -268,8 +268,18 @@ typedef struct { uint64_t min_hash, out_hash; size_t pos; } hashed_kmer;
  *                 1 = test-only alternative that restarts the window after every gap.
  * Returns the number of minimizers (may exceed cap; only cap are written).
  */
+size_t orc_minimize2(const char* seq, size_t n, unsigned k, unsigned w, const uint8_t* common, uint64_t m_bits,
+                     const uint8_t* repeat, uint64_t rep_bits, int restart_on_gap, uint64_t* out_h1, uint64_t* out_pos, size_t cap);
+
 size_t orc_minimize(const char* seq, size_t n, unsigned k, unsigned w, const uint8_t* common, const uint8_t* repeat,
                     uint64_t m_bits, int restart_on_gap, uint64_t* out_h1, uint64_t* out_pos, size_t cap)
+{
+    return orc_minimize2(seq, n, k, w, common, m_bits, repeat, m_bits, restart_on_gap, out_h1, out_pos, cap);
+}
+
+/* the same with the repeat filter's own size (indexlr -s common.bf -r repeat.bf: two independent filters) */
+size_t orc_minimize2(const char* seq, size_t n, unsigned k, unsigned w, const uint8_t* common, uint64_t m_bits,
+                     const uint8_t* repeat, uint64_t rep_bits, int restart_on_gap, uint64_t* out_h1, uint64_t* out_pos, size_t cap)
 {
     if (k > n || w > n - k + 1) return 0;
     size_t nout = 0;
@@ -291,7 +301,7 @@ size_t orc_minimize(const char* seq, size_t n, unsigned k, unsigned w, const uin
         hk->out_hash = orc_ext_hash(h0, 1, k);
         hk->pos = r.pos;
         if (common && !bf_get(common, m_bits, h0)) hk->min_hash = ORC_MAX;
-        if (repeat && bf_get(repeat, m_bits, h0)) hk->min_hash = ORC_MAX;
+        if (repeat && bf_get(repeat, rep_bits, h0)) hk->min_hash = ORC_MAX;
         if (idx + 1 >= w) {
             size_t left = idx + 1 - w, right = idx + 1;
             const hashed_kmer* ml = &buf[left % bufn];

@@ -76,7 +76,8 @@ def stage_fasta(src, workdir):
 
 
 def run_reference(fastas, workdir, prefix, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="10000",
-                  block_size=500, fpr=0.025, simplify=True, common=True, restart_on_gap=False, quiet=True):
+                  block_size=500, fpr=0.025, simplify=True, common=True, restart_on_gap=False, quiet=True,
+                  filter_mode=None, repeat_fpr=None, interarrivals=False, dev=False):
     """Full ntSynt run = oracle BF + oracle sketches + the reference's ntsynt_run.py.
     `fastas`: paths (may be .gz).  Mirrors bin/ntsynt_run_pipeline.smk:44-103.
     Returns dict of output paths."""
@@ -95,10 +96,21 @@ def run_reference(fastas, workdir, prefix, k=24, w=1000, w_rounds=(100, 10), ind
         bits = so.common_bf(genomes, k, fpr)
         bf_path = f"{prefix}.common.bf"
         save_bf(os.path.join(workdir, bf_path), bits)
+    rep_path = rep_bits = None
+    if filter_mode:
+        # rule make_repeat_bf (smk:65-72): ntsynt_make_repeat_bfs.py --genome <refs as given> -p <prefix>.repeat --fpr <fpr> -k <k>
+        # -> size from the FIRST genome as given (every base counts), bits = k-mers seen twice within a genome
+        import math
+        size_bits = math.ceil(-sum(len(s) for _, s in genomes[0][1]) / math.log(1 - (repeat_fpr or fpr)))
+        rep_bytes = max(int(math.ceil(int(size_bits / 8) / 8.0)) * 8, 8)
+        rep_bits = so.repeat_bf(genomes, k, rep_bytes)
+        rep_path = f"{prefix}.repeat.bf"
+        save_bf(os.path.join(workdir, rep_path), rep_bits)
     tsvs = []
     for b, recs in genomes:
         tsv = f"{b}.k{k}.w{w}.tsv"
-        so.write_sketch_tsv(os.path.join(workdir, tsv), recs, k, w, bits)
+        # rule indexlr (smk:74-85) passes -r only when the pipeline's `repeat` switch is on; we tie it to --filter Indexlr
+        so.write_sketch_tsv(os.path.join(workdir, tsv), recs, k, w, bits, rep_bits if filter_mode == "Indexlr" else None)
         tsvs.append(tsv)
     env = dict(os.environ)
     env["PYTHONPATH"] = os.pathsep.join([os.path.join(HERE, "shims"), os.path.join(REF, "bin"),
@@ -114,6 +126,12 @@ def run_reference(fastas, workdir, prefix, k=24, w=1000, w_rounds=(100, 10), ind
     if simplify:
         cmd += ["--simplify-graph"]
     cmd += ["--btllib_t", "1", "--fastas", *bases]
+    if filter_mode:
+        cmd += ["--filter", filter_mode, "--repeat", rep_path]
+    if interarrivals:
+        cmd += ["--interarrivals"]
+    if dev:
+        cmd += ["--dev"]
     res = subprocess.run(cmd, cwd=workdir, env=env, stdout=subprocess.PIPE if quiet else None,
                          stderr=subprocess.STDOUT if quiet else None, text=True)
     out = {
@@ -124,6 +142,9 @@ def run_reference(fastas, workdir, prefix, k=24, w=1000, w_rounds=(100, 10), ind
         "pre_merge": os.path.join(workdir, f"{prefix}.pre-collinear-merge.synteny_blocks.tsv"),
         "dot": os.path.join(workdir, f"{prefix}.mx.dot"),
         "bf": os.path.join(workdir, bf_path) if bf_path else None,
+        "repeat_bf": os.path.join(workdir, rep_path) if rep_path else None,
+        "repeat_bits": rep_bits,
+        "interarrivals": os.path.join(workdir, f"{prefix}.interarrivals.tsv"),
     }
     return out
 

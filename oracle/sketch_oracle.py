@@ -40,6 +40,8 @@ def lib():
         L.orc_bf_cascade_seq.argtypes = [u8p, u8p, u64, cp, sz, C.c_uint, C.c_int]
         L.orc_bf_repeat_seq.restype = None; L.orc_bf_repeat_seq.argtypes = [u8p, u8p, u64, cp, sz, C.c_uint]
         L.orc_bf_popcount.restype = u64; L.orc_bf_popcount.argtypes = [u8p, u64]
+        L.orc_minimize2.restype = sz
+        L.orc_minimize2.argtypes = [cp, sz, C.c_uint, C.c_uint, u8p, u64, u8p, u64, C.c_int, u64p, u64p, sz]
         L.orc_minimize.restype = sz
         L.orc_minimize.argtypes = [cp, sz, C.c_uint, C.c_uint, u8p, u8p, u64, C.c_int, u64p, u64p, sz]
         L.orc_common_bf_level1.restype = None
@@ -156,12 +158,13 @@ def repeat_bf(genomes, k, nbytes):
 def minimize(seq: bytes, k, w, common=None, repeat=None, restart_on_gap=False):
     "indexlr on one record: (h1 uint64[], pos uint64[]) in emission order."
     n = len(seq)
-    m = (common.size if common is not None else (repeat.size if repeat is not None else 0)) * 8
+    m = (common.size if common is not None else 0) * 8
+    rm = (repeat.size if repeat is not None else 0) * 8          # the repeat filter has its own size
     cap = max(16, 4 * (n // max(w, 1)) + 64)
     while True:
         h1 = np.empty(cap, dtype=np.uint64)
         pos = np.empty(cap, dtype=np.uint64)
-        cnt = lib().orc_minimize(seq, n, k, w, _u8p(common), _u8p(repeat), m, int(restart_on_gap),
+        cnt = lib().orc_minimize2(seq, n, k, w, _u8p(common), m, _u8p(repeat), rm, int(restart_on_gap),
                                  _u64p(h1), _u64p(pos), cap)
         if cnt <= cap:
             return h1[:cnt].copy(), pos[:cnt].copy()

@@ -100,12 +100,13 @@ class _HostTable(tuple):
 
 
 class OracleBackend:
-    def __init__(self, fasta_paths, tsv_names, k, fpr=0.025, common=True, lean=False):
+    def __init__(self, fasta_paths, tsv_names, k, fpr=0.025, common=True, lean=False, repeat_bits=None, filter_mode=None):
         """fasta_paths/tsv_names in the engine's processing order (reverse-sorted TSV names).
         lean=True hands the join to the engine in the form the CUDA backend uses (host-ready columns,
         sparse lists, lazily fetched pair masks; ntsynt_b200.device.MinimizerGraph.join_result)."""
         self.k = k
         self.lean = lean
+        self.repeat_bits, self.filter_mode = repeat_bits, filter_mode     # bin/ntsynt_synteny.py:172-187
         self.names = list(tsv_names)
         self.records = [so.read_fasta(p) for p in fasta_paths]
         self.contig_names = [[n for n, _ in recs] for recs in self.records]
@@ -128,7 +129,13 @@ class OracleBackend:
                     s, e = int(s), int(e)
                     buf[s:e] = b"N" * (e - s)
                 seq = bytes(buf)
-            h1, pos = so.minimize(seq, self.k, w, self.bits)
+            h1, pos = so.minimize(seq, self.k, w, self.bits, self.repeat_bits if self.filter_mode == "Indexlr" else None)
+            if self.filter_mode == "Filter" and len(h1):
+                # read_minimizers(tsv, repeat_bf): a minimizer whose k-mer is in the repeat filter is dropped
+                m = self.repeat_bits.size * 8
+                idx = np.array([so.kmer_hash(seq[int(p_):int(p_) + self.k].upper()) % m for p_ in pos], dtype=np.uint64)
+                hit = (self.repeat_bits[(idx >> np.uint64(3)).astype(np.int64)] >> (idx & np.uint64(7)).astype(np.uint8)) & 1
+                h1, pos = h1[hit == 0], pos[hit == 0]
             hs.append(h1); ps.append(pos.astype(np.uint32)); cs.append(np.full(len(h1), c, dtype=np.uint32))
         return np.concatenate(hs), np.concatenate(ps), np.concatenate(cs)
 

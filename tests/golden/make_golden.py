@@ -121,7 +121,87 @@ def presets():
         json.dump(meta, fh, indent=1)
 
 
+FILTER_FPR = 0.2      # a small repeat filter (many false positives) so that both modes change the result visibly
+
+
+def filters():
+    """tests/golden/mini/ABC_{filter,indexlr}/: the reference's graph stage with --filter Filter / --filter Indexlr
+    (bin/ntsynt_synteny.py:172-187,601-609) and --interarrivals (:557-564) on the mini genomes; the repeat filter is
+    bin/ntsynt_make_repeat_bfs.py's (oracle restatement).  interarrivals are stored sorted: the reference's order
+    follows a Python set of strings."""
+    names = ["miniA.fa", "miniB.fa", "miniC.fa"]
+    tmp = tempfile.mkdtemp(prefix="mkfilt_")
+    for n in names:
+        with gzip.open(os.path.join(MINI, n + ".gz"), "rb") as fin, open(os.path.join(tmp, n), "wb") as fout:
+            shutil.copyfileobj(fin, fout)
+    for tag, mode in (("ABC_filter", "Filter"), ("ABC_indexlr", "Indexlr"), ("ABC", None)):
+        wd = os.path.join(tmp, tag)
+        res = ref_harness.run_reference([os.path.join(tmp, n) for n in names], wd, f"mini-{tag}", filter_mode=mode,
+                                        repeat_fpr=FILTER_FPR, interarrivals=True, **MINI_PARAMS)
+        assert res["returncode"] == 0, res["log"][-2000:]
+        out = os.path.join(MINI, tag)
+        os.makedirs(out, exist_ok=True)
+        vals = sorted(int(x) for x in open(res["interarrivals"], encoding="utf-8").read().split())
+        with gzip.GzipFile(os.path.join(out, "interarrivals.sorted.txt.gz"), "wb", mtime=0) as fo:
+            fo.write(("\n".join(map(str, vals)) + "\n").encode())
+        if mode is None:
+            assert open(res["blocks"]).read() == open(os.path.join(out, "synteny_blocks.tsv")).read()
+            continue
+        shutil.copyfile(res["blocks"], os.path.join(out, "synteny_blocks.tsv"))
+        shutil.copyfile(res["pre_merge"], os.path.join(out, "pre-collinear-merge.synteny_blocks.tsv"))
+        with gzip.GzipFile(os.path.join(MINI, "repeat_bits.bin.gz"), "wb", mtime=0) as fo:      # same filter in both modes
+            fo.write(res["repeat_bits"].tobytes())
+    shutil.rmtree(tmp)
+
+
+def overlap_cases():
+    """tests/golden/overlap_cases.json: seeded block tables and the warnings the reference's own
+    NtSyntSynteny.check_non_overlapping (bin/ntsynt_synteny.py:234-253) prints for them"""
+    import contextlib
+    import io
+    import random
+    import types
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "shims"), os.path.join(REF, "bin"), os.path.join(REF, "subprojects", "ntJoin", "bin")]
+    import ntsynt_synteny as ref
+
+    class AB:
+        def __init__(self, c, s, e):
+            self.c, self.s, self.e = c, s, e
+
+        def get_block_contig_start_end(self):
+            return self.c, self.s, self.e
+
+        def get_block_length(self):
+            return self.e - self.s
+    cases = []
+    for seed in range(6):
+        rng = random.Random(seed)
+        G, z = rng.choice([2, 3]), rng.choice([50, 200])
+        blocks = []
+        for _ in range(rng.randrange(5, 40)):
+            row = []
+            for a in range(G):
+                s = rng.randrange(0, 3000)
+                row.append([f"ctg{rng.randrange(2)}", s, s + rng.randrange(10, 900)])
+            blocks.append(row)
+        objs = [types.SimpleNamespace(assembly_blocks={f"asm{a}": AB(*row[a]) for a in range(G)}) for row in blocks]
+        fake = types.SimpleNamespace(args=types.SimpleNamespace(z=z))
+        fake.get_overlapping_region = lambda s, e, iv, _f=fake: ref.NtSyntSynteny.get_overlapping_region(_f, s, e, iv)
+        err = io.StringIO()
+        with contextlib.redirect_stderr(err):
+            ref.NtSyntSynteny.check_non_overlapping(fake, objs)
+        warn = [ln.split("block: ", 1)[1].split() for ln in err.getvalue().splitlines() if ln.startswith("WARNING")]
+        cases.append({"G": G, "z": z, "blocks": blocks, "warnings": [[w[0], w[1], int(w[2]), int(w[3])] for w in warn]})
+    with open(os.path.join(HERE, "overlap_cases.json"), "w", encoding="utf-8") as fh:
+        json.dump({"made_by": "tests/golden/make_golden.py overlap_cases(): reference check_non_overlapping", "cases": cases}, fh)
+    return sum(len(c["warnings"]) for c in cases)
+
+
 if __name__ == "__main__":
+    if "--filters" in sys.argv:           # only the round-2 additions (the older fixtures are left untouched)
+        filters()
+        print("overlap warnings recorded:", overlap_cases())
+        sys.exit(0)
     print("hash KATs:", hash_kats())
     mini()
     print("mini fixtures written to", MINI)

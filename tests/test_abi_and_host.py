@@ -157,3 +157,57 @@ def test_reference_arm_runs_without_the_cuda_library():
     line = json.loads(res.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _run(cmd, cwd):
+    import subprocess
+    res = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-3000:]
+    return res.stdout
+
+
+def test_block_stats_utility(tmp_path):
+    import shutil
+    import sys
+    BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin")
+    "analysis_scripts/denovo_synteny_block_stats.py: same ten numbers (computed here by the script's own definitions)"
+    names = ["miniA.fa", "miniB.fa", "miniC.fa"]
+    shutil.copyfile(os.path.join(MINI, "ABC", "synteny_blocks.tsv"), tmp_path / "b.tsv")
+    for n in names:
+        shutil.copyfile(os.path.join(MINI, "ABC", n + ".fai"), tmp_path / (n + ".fai"))
+    out = _run([sys.executable, os.path.join(BIN, "denovo_synteny_block_stats.py"), "--tsv", "b.tsv", "--fai", *[n + ".fai" for n in names]],
+              tmp_path).splitlines()
+    assert out[0].split("\t")[:2] == ["Number_blocks", "Number_blocks_all_asm"] and len(out[1].split("\t")) == 10
+    with open(os.path.join(MINI, "ABC", "block_stats.txt"), encoding="utf-8") as fh:
+        assert out == fh.read().splitlines()
+
+
+def test_bf_file_formats_round_trip(tmp_path):
+    """<prefix>.bf (src/ntsynt_make_common_bf.cpp:164): btllib's header layout by default (unpinned: no .bf fixture in
+    the reference), our own container on request; both read back, and foreign files are refused"""
+    import numpy as np
+    from ntsynt_b200 import io
+    bits = np.random.default_rng(5).integers(0, 256, 4096, dtype=np.uint8)
+    for fmt in ("btllib", "native"):
+        path = str(tmp_path / f"x.{fmt}.bf")
+        io.save_bf(path, bits, 24, fmt=fmt)
+        got, k = io.load_bf_bytes(path)
+        assert k == 24 and np.array_equal(got, bits)
+    head = open(str(tmp_path / "x.btllib.bf"), "rb").read(200)
+    assert head.startswith(b"[BTLKmerBloomFilter_v") and b"[HeaderEnd]\n" in head and b"hash_num = 1" in head
+    (tmp_path / "junk.bf").write_bytes(b"not a filter")
+    with pytest.raises(ValueError):
+        io.load_bf_bytes(str(tmp_path / "junk.bf"))
+    (tmp_path / "cut.bf").write_bytes(open(str(tmp_path / "x.btllib.bf"), "rb").read()[:-10])
+    with pytest.raises(ValueError):
+        io.load_bf_bytes(str(tmp_path / "cut.bf"))
+
+
+def test_repeat_bf_size_argument():
+    "bin/ntsynt_make_repeat_bfs.py:10-24"
+    import argparse
+    from ntsynt_b200 import cli
+    ap = argparse.ArgumentParser()
+    assert [cli.parse_bf_size(x, ap) for x in ("17B", "3k", "5M", "2G")] == [17, 3000, 5000000, 2000000000]
+    with pytest.raises(SystemExit):
+        cli.parse_bf_size("12", ap)

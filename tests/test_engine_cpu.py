@@ -14,12 +14,13 @@ from oracle import sketch_oracle as so
 from oracle.graph_oracle import GraphOracle
 
 
-def run_engine(paths, k, w, w_rounds, indel, merge, z, lean=False, native=True):
+def run_engine(paths, k, w, w_rounds, indel, merge, z, lean=False, native=True, **kw):
     bases = [os.path.basename(p)[:-3] if p.endswith(".gz") else os.path.basename(p) for p in paths]
     tsv = [f"{b}.k{k}.w{w}.tsv" for b in bases]
     order = sorted(range(len(paths)), key=lambda i: tsv[i], reverse=True)
-    be = OracleBackend([paths[i] for i in order], [tsv[i] for i in order], k, lean=lean)
-    eng = SyntenyEngine(be, k, w, w_rounds, indel, merge, z, write_files=False, quiet=True)
+    be = OracleBackend([paths[i] for i in order], [tsv[i] for i in order], k, lean=lean,
+                       repeat_bits=kw.pop("repeat_bits", None), filter_mode=kw.pop("filter_mode", None))
+    eng = SyntenyEngine(be, k, w, w_rounds, indel, merge, z, write_files=False, quiet=True, **kw)
     eng.native = native      # C++ walks (csrc/nts_hostgraph.cu) or their Python statements
     eng.run()
     return eng, be
@@ -32,6 +33,47 @@ def test_mini_against_reference_fixture(tag, mini_params, lean):
     eng, _ = run_engine(mini_fastas(tag), p["k"], p["w"], p["w_rounds"], p["indel"], p["merge"], p["block_size"], lean)
     assert eng.outputs["final"] == mini_expected(tag, "synteny_blocks.tsv")
     assert eng.outputs["pre_merge"] == mini_expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
+
+
+def _repeat_bits():
+    import gzip
+    from conftest import MINI
+    with gzip.open(os.path.join(MINI, "repeat_bits.bin.gz"), "rb") as fh:
+        return np.frombuffer(fh.read(), dtype=np.uint8).copy()
+
+
+@pytest.mark.parametrize("lean", [False, "dev"])
+@pytest.mark.parametrize("tag,mode", [("ABC_filter", "Filter"), ("ABC_indexlr", "Indexlr"), ("ABC", None)])
+def test_repeat_filter_modes_and_interarrivals_against_reference_fixture(tag, mode, mini_params, lean):
+    "--filter Filter | Indexlr and --interarrivals (bin/ntsynt_synteny.py:172-187,557-564,601-609): files made by the reference's own code"
+    p = mini_params
+    eng, _ = run_engine(mini_fastas("ABC"), p["k"], p["w"], p["w_rounds"], p["indel"], p["merge"], p["block_size"], lean,
+                        repeat_bits=_repeat_bits() if mode else None, filter_mode=mode, interarrivals=True)
+    assert eng.outputs["final"] == mini_expected(tag, "synteny_blocks.tsv")
+    assert eng.outputs["pre_merge"] == mini_expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
+    got = sorted(int(x) for x in eng.outputs["interarrivals"].split())
+    assert got == [int(x) for x in mini_expected(tag, "interarrivals.sorted.txt.gz").split()]
+
+
+def test_dev_overlap_check_against_reference_cases():
+    "check_non_overlapping (bin/ntsynt_synteny.py:234-253): warnings recorded from the reference's own function"
+    import json
+    import types
+    from conftest import GOLDEN
+    from ntsynt_b200.synteny import Block
+    with open(os.path.join(GOLDEN, "overlap_cases.json"), encoding="utf-8") as fh:
+        cases = json.load(fh)["cases"]
+    assert sum(len(c["warnings"]) for c in cases) > 20
+    for c in cases:
+        G, k = c["G"], 24
+        eng = SyntenyEngine.__new__(SyntenyEngine)
+        eng.G, eng.k, eng.z, eng.outputs = G, k, c["z"], {}
+        eng.names = [f"asm{a}" for a in range(G)]
+        eng.be = types.SimpleNamespace(contig_names=[["ctg0", "ctg1"]] * G)
+        blocks = [Block(None, [int(r[a][0][3:]) for a in range(G)], ["+"] * G, 0, 0, [r[a][1] for a in range(G)],
+                        [r[a][2] - k for a in range(G)], 5) for r in c["blocks"]]
+        got = eng._check_non_overlapping(blocks)
+        assert [list(w) for w in got] == c["warnings"]
 
 
 @pytest.mark.slow

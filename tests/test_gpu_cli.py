@@ -92,3 +92,44 @@ def test_cli_argument_errors(tmp_path):
     res = subprocess.run([sys.executable, os.path.join(BIN, "ntsynt_make_common_bf"), "--genome", "x.fa"], cwd=tmp_path,
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 1
+
+
+@pytest.mark.parametrize("tag,mode", [("ABC_filter", "Filter"), ("ABC_indexlr", "Indexlr")])
+def test_repeat_filter_chain_reproduces_the_reference_fixture(tmp_path, mini_params, tag, mode):
+    """rule make_repeat_bf -> indexlr -s -r -> ntsynt_run.py --filter <mode> --repeat --interarrivals --dev
+    (bin/ntsynt_run_pipeline.smk:65-103; bin/ntsynt_synteny.py:172-187,557-564,601-609): block files and the
+    interarrival distances were written by the reference's own graph stage (tests/golden/make_golden.py filters())."""
+    import numpy as np
+    from ntsynt_b200 import io
+    p = mini_params
+    names = stage(tmp_path, "ABC")
+    k, w = p["k"], p["w"]
+    run([sys.executable, os.path.join(BIN, "ntsynt_make_common_bf"), "--genome", *names, "-p", "mini.common", "--fpr",
+         str(p["fpr"]), "-k", str(k), "-t", "4"], tmp_path)
+    out = run([sys.executable, os.path.join(BIN, "ntsynt_make_repeat_bfs.py"), "--genome", *names, "-p", "mini.repeat", "--fpr", "0.2",
+               "-k", str(k), "-t", "4"], tmp_path)
+    assert "Calculated Bloom filter size:" in out
+    bits, kk = io.load_bf_bytes(str(tmp_path / "mini.repeat.bf"))
+    with gzip.open(os.path.join(MINI, "repeat_bits.bin.gz"), "rb") as fh:
+        assert kk == k and np.array_equal(bits, np.frombuffer(fh.read(), dtype=np.uint8))      # == bin/ntsynt_make_repeat_bfs.py restated
+    for n in names:
+        rep = ["-r", "mini.repeat.bf"] if mode == "Indexlr" else []
+        run([sys.executable, os.path.join(BIN, "indexlr"), n, "--seq", "--long", "--pos", f"-k{k}", f"-w{w}", "-t4",
+             "-s", "mini.common.bf", *rep, "-o", f"{n}.k{k}.w{w}.tsv"], tmp_path)
+    log = run([sys.executable, os.path.join(BIN, "ntsynt_run.py"), *[f"{n}.k{k}.w{w}.tsv" for n in names], "-k", str(k), "-w", str(w),
+               "--w-rounds", *map(str, p["w_rounds"]), "-p", "mini-F", "--bp", str(p["indel"]), "--collinear-merge", p["merge"],
+               "-z", str(p["block_size"]), "--common", "mini.common.bf", "--simplify-graph", "--btllib_t", "4", "--fastas", *names,
+               "--filter", mode, "--repeat", "mini.repeat.bf", "--interarrivals", "--dev"], tmp_path)
+    assert "WARNING: detected overlapping" not in log
+    assert (tmp_path / "mini-F.synteny_blocks.tsv").read_text() == mini_expected(tag, "synteny_blocks.tsv")
+    assert (tmp_path / "mini-F.pre-collinear-merge.synteny_blocks.tsv").read_text() == \
+        mini_expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
+    got = sorted(int(x) for x in (tmp_path / "mini-F.interarrivals.tsv").read_text().split())
+    assert got == [int(x) for x in mini_expected(tag, "interarrivals.sorted.txt.gz").split()]
+
+
+def test_filter_without_repeat_is_the_reference_error(tmp_path):
+    res = subprocess.run([sys.executable, os.path.join(BIN, "ntsynt_run.py"), "a.fa.k24.w100.tsv", "b.fa.k24.w100.tsv", "-k", "24",
+                          "-w", "100", "--fastas", "a.fa", "b.fa", "--filter", "Filter"], cwd=tmp_path, stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True)
+    assert res.returncode != 0 and "must supply repeat Bloom filter with --repeat" in res.stdout
