@@ -7,6 +7,7 @@
 #include "nts_internal.h"
 #include "nts_part.cuh"
 #include "nts_bin.cuh"
+#include "nts_rank.cuh"
 
 namespace nts {
 
@@ -135,12 +136,27 @@ static int pair_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const G
     BinParams bp;
     bp.items = sc->items.p; bp.bucket_off = sc->bucket_off.p; bp.bucket_cap = sc->bucket_cap.p; bp.cursor = sc->cursor.p;
     bp.n_buckets = sc->P; bp.region_shift = sc->shift;
-    const size_t smem = sizeof(HashTables) + (size_t)BIN_TILE * 12 + (size_t)sc->P * 12 + 4;
-    NTS_CUDA(cudaFuncSetAttribute(bf_bin_kernel<BIN_THREADS, BIN_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t mprime = 0xFFFFFFFFFFFFFFFFull / m;
     const unsigned blocks = (unsigned)((total_valid + BIN_TILE - 1) / BIN_TILE);
     ProfScope prof(ctx, PROF_BF_PART1, (double)total_valid, false, st);
-    bf_bin_kernel<BIN_THREADS, BIN_ITEMS><<<blocks, BIN_THREADS, smem, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp);
+    // NTS_BF_BIN=2: ranking without shared-memory atomics (nts_rank.cuh; same output up to the order inside a bucket)
+    // where the item word has room for the high bucket digit.  Measured slower on B200 (34.8 against 21.2 ms per 3 Gbp
+    // genome, profiles/r02c_ncu_rank_bin.md): its two counting-sort passes issue 285 instructions and ~65 shared-memory
+    // wavefronts per k-mer row, which costs more than the one ATOMS they replace -- so the atomicAdd ranking stays the default.
+    const char* eb = getenv("NTS_BF_BIN");
+    const bool old_rank = !(eb && eb[0] == '2');
+    const size_t smem_r = RankSmem<BIN_THREADS, BIN_ITEMS>::bytes(sc->P);
+    if (!old_rank && sc->P <= 512 && sc->shift <= 28) {
+        NTS_CUDA(cudaFuncSetAttribute(bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+        bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 4><<<blocks, BIN_THREADS, smem_r, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp);
+    } else if (!old_rank && sc->P <= 1024 && sc->shift <= 27) {
+        NTS_CUDA(cudaFuncSetAttribute(bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+        bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 5><<<blocks, BIN_THREADS, smem_r, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp);
+    } else {
+        const size_t smem = sizeof(HashTables) + (size_t)BIN_TILE * 12 + (size_t)sc->P * 12 + 4;
+        NTS_CUDA(cudaFuncSetAttribute(bf_bin_kernel<BIN_THREADS, BIN_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bf_bin_kernel<BIN_THREADS, BIN_ITEMS><<<blocks, BIN_THREADS, smem, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp);
+    }
     ctx->launches++;
     NTS_CUDA(cudaGetLastError());
     return NTS_OK;

@@ -121,7 +121,7 @@ def test_three_pass_exhausted_overflow_list_falls_back_to_the_direct_kernel(cuda
         bf.close(); lvl.close()
 
 
-@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("impl", [2, 1, 3])
 def test_heavy_hitter_kmers(cuda_ctx, impl):
     "one k-mer repeated 2 M times (poly-A) plus a tandem repeat: far more copies than any bucket holds"
     rng = np.random.default_rng(5)
@@ -130,7 +130,7 @@ def test_heavy_hitter_kmers(cuda_ctx, impl):
     g = cuda_ctx.upload(fasta.pack_records(recs))
     nbytes = device.BloomFilter.size_for(g.total_bases, 0.025)
     want = so.genome_bits(recs, K, nbytes)
-    with env(NTS_BF_PARTITION=1, NTS_BF_IMPL=impl, NTS_BF_P1MAX=128, NTS_BF_P2=128, NTS_BF_REGION_SHIFT=18):
+    with env(NTS_BF_PARTITION=1, NTS_BF_IMPL=impl, NTS_BF_BIN=impl, NTS_BF_P1MAX=128, NTS_BF_P2=128, NTS_BF_REGION_SHIFT=18):
         bf = cuda_ctx.bloom(nbytes)
         o0, n0 = cuda_ctx.part_overflow_items, cuda_ctx.part_inserts
         bf.set_genome(g, K)
@@ -142,14 +142,17 @@ def test_heavy_hitter_kmers(cuda_ctx, impl):
 
 
 # ---------------------------------------------------------------------------------------- the production pair
+@pytest.mark.parametrize("rank", [2, 1])
 @pytest.mark.parametrize("shift", [14, 18, 21, 23, 27])
 @pytest.mark.parametrize("scale", [1.0, 0.6, 0.05])
-def test_pair_many_buckets_short_last_region_and_overflow_branch(cuda_ctx, small, shift, scale):
+def test_pair_many_buckets_short_last_region_and_overflow_branch(cuda_ctx, small, shift, scale, rank):
     """bf_bin_kernel + bf_apply_kernel with 2^shift-bit regions (m = 2.4e8 bits: 1024 buckets at shift 18 -- 14 asks
     for more than the 1024 the kernel supports and is widened --, 29 with a short last region at 23, 2 at 27) and
-    with capacities below the load (items past a bucket's capacity are applied with direct atomics)"""
+    with capacities below the load (items past a bucket's capacity are applied with direct atomics).
+    rank = 2: bf_rank_bin_kernel (csrc/nts_rank.cuh, ranking by private counters; 5-bit high digit above 512 buckets,
+    4-bit below), rank = 1: bf_bin_kernel (shared-memory atomicAdd ranking)"""
     gens, nbytes, per = small
-    with env(NTS_BF_PARTITION=1, NTS_BF_REGION_SHIFT=shift, NTS_BF_CAP_SCALE=scale):
+    with env(NTS_BF_PARTITION=1, NTS_BF_REGION_SHIFT=shift, NTS_BF_CAP_SCALE=scale, NTS_BF_BIN=rank):
         n0 = cuda_ctx.part_inserts
         bf, lvl = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
         bf.from_numpy(np.full(nbytes, 0xFF, dtype=np.uint8))
@@ -193,7 +196,8 @@ def test_default_plan_at_150_mbp_equals_direct_kernel_and_oracle(cuda_ctx):
     recs = _records(gens[0])
     assert np.array_equal(a, so.genome_bits(recs, K, nbytes))
     want = d0.to_numpy()
-    for knobs in (dict(NTS_BF_REGION_SHIFT=23), dict(NTS_BF_REGION_SHIFT=23, NTS_BF_CAP_SCALE=0.7), dict(NTS_BF_IMPL=3)):
+    for knobs in (dict(NTS_BF_REGION_SHIFT=23), dict(NTS_BF_REGION_SHIFT=23, NTS_BF_CAP_SCALE=0.7), dict(NTS_BF_IMPL=3),
+                  dict(NTS_BF_BIN=1), dict(NTS_BF_BIN=1, NTS_BF_REGION_SHIFT=24)):
         with env(**knobs):
             common.build_common(lvl, gens, K)
         assert np.array_equal(common.to_numpy(), want), knobs
