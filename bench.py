@@ -178,7 +178,7 @@ def cpu_sample_mbp(args, G):
     return args.cpu_sample_mbp * 2.0 / max(G, 2)
 
 
-def cpu_path(records_per_genome, file_names, divergence, threads):
+def cpu_path(records_per_genome, file_names, divergence, threads, log=None):
     """The reference's CPU path restated (oracle/): make_common_bf (OpenMP over records, atomic byte-OR;
     src/ntsynt_make_common_bf.cpp:122-160), indexlr per genome (5 threads, 2 genomes at a time;
     bin/ntsynt_run_pipeline.smk:79-80, bin/ntSynt:154), then the graph stage (single-threaded Python,
@@ -207,6 +207,8 @@ def cpu_path(records_per_genome, file_names, divergence, threads):
         seqs, lens = rec_arrays(records_per_genome[i])
         L.orc_common_bf_cascade(so._u8p(bits), so._u8p(nxt), m, seqs, lens, len(lens), K, threads)
         bits = nxt
+    if log:
+        log(f"common Bloom filter ({nbytes} bytes) after {time.perf_counter() - t0:.1f} s")
     # round-0 indexlr: a worker per record, 5 threads per genome, 2 genomes at a time (smk:79-80, bin/ntSynt:154)
     tsv = [f"{fn}.k{K}.w{W}.tsv" for fn in file_names]
     round0 = {}
@@ -233,6 +235,8 @@ def cpu_path(records_per_genome, file_names, divergence, threads):
             t.start()
         for t in ths:
             t.join()
+    if log:
+        log(f"round-0 sketches after {time.perf_counter() - t0:.1f} s")
     go = GraphOracle(list(zip(tsv, records_per_genome)), K, W, ps["w_rounds"], ps["indel"], ps["merge"],
                      ps["block_size"], bits)
     try:
@@ -398,15 +402,39 @@ def run_ours(args, dist):
             traffic = tj.get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
-    roofline = {"kernel": {"bf_insert": "bf_part1_kernel + bf_part2_kernel + bf_apply_kernel (one Bloom insert)",
-                           "sketch": "sketch_sparse_kernel<512,16,3072>"}.get(fam, fam),
+    three_pass = bool(prof.get("bf_part2", (0, 0, 0))[2])
+    insert_name = ("bf_part1_kernel + bf_part2_kernel + bf_apply3_kernel (one Bloom insert, NTS_BF_IMPL=3)" if three_pass
+                   else "bf_bin_kernel<512,16> + bf_apply_kernel (one Bloom insert)")
+    sm_clock = (clk.get("sm_mhz") or 1965.0) * 1e6
+    issue_peak = 148 * 128 * sm_clock                           # thread-instructions per second: 148 SMs x 4 schedulers x 32 lanes
+    roofline = {"kernel": {"bf_insert": insert_name, "sketch": "sketch_sparse_kernel<512,16,3072>"}.get(fam, fam),
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
                 "traffic": traffic, "peak_source": peak_src,
+                # what the kernel really moves (ncu dram__bytes of one launch) over the same launch time: the contract figure
+                # above assumes one random 32-byte sector read-modify-write per k-mer, which the partitioned insert avoids
+                "dram_frac": round(traffic / ((f_ms / f_n) / 1e3) / 1e9 / peak, 4) if traffic else None,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": f_ms / f_n,
                 "kernel_ms_per_step": {f: round(prof[f][0] / args.steps, 3) for f in prof if prof[f][2]},
                 "kernel_share_of_step": round(f_ms / ms, 4),
-                "note": "bf_insert = bf_part1 + bf_part2 + bf_apply (the three passes of one Bloom insert, also listed separately)"}
+                "note": ("bf_insert = bf_part1 (binning pass) + bf_apply (the two passes of one Bloom insert, also listed separately); "
+                         "the pair is bound by atomic issue (one shared-memory ATOMS and one global RED per k-mer at 2 LSU cycles "
+                         "per lane each), not by HBM -- see dram_frac and profiles/")}
+    # the sketch kernel is instruction-bound (it looks up 2.4 % of the k-mers): report it against the issue rate
+    sk = prof.get("sketch", (0, 0, 0))
+    sketch_roof = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json"), encoding="utf-8") as fh:
+            ipk = json.load(fh).get("sketch", {}).get("thread_instructions_per_kmer")
+    except (OSError, ValueError):
+        ipk = None
+    if sk[2] and ipk:
+        ach = ipk * sk[1] / (sk[0] / 1e3)
+        sketch_roof = {"kernel": "sketch_sparse_kernel<512,16,3072> (round-0 sketch of one genome)", "bound": "issue",
+                       "thread_instructions_per_kmer": ipk, "achieved": round(ach / 1e12, 3), "peak": round(issue_peak / 1e12, 3),
+                       "unit": "T thread-instr/s", "frac": round(ach / issue_peak, 4), "avg_launch_ms": round(sk[0] / sk[2], 3),
+                       "note": "instructions per k-mer from the committed ncu capture (profiles/traffic.json); launches include the small masked rounds"}
+    roofline["sketch_issue"] = sketch_roof
 
     # ---- CPU baseline on rank 0 (bounded sample of the same workload)
     cpu = None
@@ -418,7 +446,7 @@ def run_ours(args, dist):
         cpu = {"value": tot / dt, "unit": "bp/s", "cores": threads, "kind": "port",
                "sample": f"first {smbp:g} Mbp of each of the {G} genomes ({tot} bp): oracle/ C+OpenMP "
                          f"Bloom filter and sketch, pure-Python graph stage; {dt:.1f} s"}
-    ingest = ingest_probe(wl, 120.0) if (dist.rank == 0 and N == 1 and not args.no_cpu) else None
+    ingest = ingest_probe(wl, 600.0) if (dist.rank == 0 and N == 1 and not args.no_cpu) else None
     line = {
         "metric": METRIC, "value": value, "unit": "bp/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -476,10 +504,18 @@ def run_ours_multi(args, dist, ctx):
         peer = None
     use_p2p = args.merge == "p2p" and peer is not None
 
+    phase = {}
+
+    def tick(name, t0):
+        phase[name] = phase.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+
     def hot_path(gen_map):
+        t0 = time.perf_counter()
         mine.set_genome(gen_map[own[0]], K)
         for g in own[1:]:
             level.clear(); level.insert_genome(gen_map[g], K); mine.iand(level)
+        t0 = tick("insert", t0)
         if use_p2p:
             peer.merge("and", comm=comm)                           # NVLink peer loads: reduce-scatter + all-gather
         else:
@@ -496,6 +532,7 @@ def run_ours_multi(args, dist, ctx):
                     gathered[x] = tb
                 else:
                     tb.close()
+        t0 = tick("merge_sketch_gather", t0)                       # (the merge is asynchronous: it is waited for here)
         text, eng = None, None
         if rank == 0:
             be = distributed.GatheredBackend(ctx, [gen_map[i] for i in order], [names[i] for i in order], [wl.names] * G,
@@ -506,12 +543,16 @@ def run_ours_multi(args, dist, ctx):
             text = eng.run()
             for tb in gathered.values():
                 tb.close()
+            t0 = tick("graph_rank0", t0)
         dist.barrier()                                             # the step ends when the block table exists
+        tick("wait_for_rank0", t0)
+        phase["calls"] = phase.get("calls", 0) + 1
         return text, eng
 
     for _ in range(max(args.warmup, 0)):
         text, eng = hot_path(gens)
     ctx.prof_enable(True); ctx.prof_reset()
+    phase.clear()
     launches0 = ctx.launches
     clocks = ClockSampler(dist.local_rank)
     dist.barrier(); ctx.sync()
@@ -519,6 +560,8 @@ def run_ours_multi(args, dist, ctx):
     for _ in range(args.steps):
         text, eng = hot_path(gens)
     ms = ctx.timer_stop()
+    phase = dict(phase)                    # freeze: the e2e leg below would add to it
+    hot_phase, phase = phase, {}
     ctx.sync(); dist.barrier()
     ms = dist.max(ms)
     launches = dist.sum(ctx.launches - launches0)
@@ -606,6 +649,8 @@ def run_ours_multi(args, dist, ctx):
                          "traffic": traffic, "rank": 0,
                          "kernel_ms_per_step": {f: round(prof[f][0] / args.steps, 3) for f in prof if prof[f][2]}},
             "cpu_baseline": None,
+            "graph_stage_phase_ms": {k[2:]: round(v * 1e3, 1) for k, v in eng.stats.items() if k.startswith("t_")},
+            "phase_ms_rank0": {k: round(v / max(hot_phase.get("calls", 1), 1), 2) for k, v in hot_phase.items() if k != "calls"},
         }))
     if peer is not None:
         peer.close()

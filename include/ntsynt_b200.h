@@ -372,6 +372,10 @@ int nts_host_simplify_neigh(const int64_t* cand, int64_t n_cand, const int64_t* 
 int nts_fasta_scan(const char* buf, uint64_t n, uint64_t cap, uint64_t* name_off, uint32_t* name_len, uint64_t* n_bases,
                    uint64_t* seq_off, uint64_t* seq_end, uint32_t* linebases, uint32_t* linewidth, uint8_t* uniform,
                    uint64_t* n_records);
+/* the same records found by n_threads threads (0 = all cores): headers by buffer slice, record bodies in ~8 MB pieces */
+int nts_fasta_scan_mt(const char* buf, uint64_t n, uint64_t cap, uint64_t* name_off, uint32_t* name_len, uint64_t* n_bases,
+                   uint64_t* seq_off, uint64_t* seq_end, uint32_t* linebases, uint32_t* linewidth, uint8_t* uniform,
+                   uint64_t* n_records, uint32_t n_threads);
 /* nts_fasta_pack: 2-bit pack every record with n_threads threads (0 = hardware concurrency; records in parallel, long
  * uniform records split at 4 Mbp).  word_off[r] = even offset of record r in words_out (zero-initialised, sum of
  * nts_packed_words(n_bases[r]) words); N runs in record coordinates, record r owning [nrun_off[r], nrun_off[r+1]).

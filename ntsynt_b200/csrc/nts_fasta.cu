@@ -152,6 +152,140 @@ int nts_fasta_scan(const char* buf, uint64_t n, uint64_t cap, uint64_t* name_off
     return NTS_OK;
 }
 
+/* Pass 1 with threads: the same result as nts_fasta_scan for any input.
+ *   A. header lines ('>' first in the buffer or right after a newline) are found by all threads, a slice of the buffer each;
+ *   B. every record's head is walked with the serial rule through its first non-empty sequence line (which fixes the
+ *      .fai columns linebases / linewidth and the state of the uniformity test);
+ *   C. the rest of every record is cut at line starts into ~8 MB pieces that the threads scan with that state known:
+ *      bases, end of the last line, whether an odd line occurs and whether a non-empty line follows one;
+ *   D. the pieces of a record are merged in order (a non-empty line after an odd line anywhere makes it non-uniform). */
+int nts_fasta_scan_mt(const char* buf, uint64_t n, uint64_t cap, uint64_t* name_off, uint32_t* name_len, uint64_t* n_bases,
+                      uint64_t* seq_off, uint64_t* seq_end, uint32_t* linebases, uint32_t* linewidth, uint8_t* uniform,
+                      uint64_t* n_records, uint32_t n_threads)
+{
+    if ((!buf && n) || !n_records) return fail(NTS_ERR_ARG, "null argument");
+    if (n_threads == 0) n_threads = std::max(1u, std::thread::hardware_concurrency());
+    if (n_threads == 1 || n < (1ull << 24))
+        return nts_fasta_scan(buf, n, cap, name_off, name_len, n_bases, seq_off, seq_end, linebases, linewidth, uniform, n_records);
+    const char* const end = buf + n;
+    auto run_threads = [&](size_t n_jobs, auto&& job) {
+        std::atomic<size_t> next{0};
+        auto work = [&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= n_jobs) break; job(i); } };
+        std::vector<std::thread> pool;
+        const uint32_t nt = (uint32_t)std::min<size_t>(n_threads, std::max<size_t>(n_jobs, 1));
+        for (uint32_t t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    };
+    // ---- A: header positions
+    const size_t n_slices = (size_t)n_threads * 4;
+    const uint64_t slice = (n + n_slices - 1) / n_slices;
+    std::vector<std::vector<uint64_t>> found(n_slices);
+    run_threads(n_slices, [&](size_t i) {
+        const char* p = buf + std::min<uint64_t>(n, i * slice);
+        const char* const e = buf + std::min<uint64_t>(n, (i + 1) * slice);
+        while (p < e) {
+            const char* q = (const char*)memchr(p, '>', (size_t)(e - p));
+            if (!q) break;
+            if (q == buf || q[-1] == '\n') found[i].push_back((uint64_t)(q - buf));
+            p = q + 1;
+        }
+    });
+    std::vector<uint64_t> hdr;
+    for (auto& f : found) hdr.insert(hdr.end(), f.begin(), f.end());
+    const uint64_t nr = hdr.size();
+    *n_records = nr;
+    if (nr > cap) return NTS_OK;                      // the caller comes back with larger arrays
+    // ---- B: names, heads
+    struct Head { uint64_t lb, lw, bases, send, resume, span_end; bool short_seen, uni; };
+    std::vector<Head> heads(nr);
+    for (uint64_t r = 0; r < nr; ++r) {
+        const char* p = buf + hdr[r];
+        const char* const rec_end = r + 1 < nr ? buf + hdr[r + 1] : end;
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(rec_end - p));
+        const char* le = nl ? nl : rec_end;
+        auto is_ws = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
+        const char* q0 = p + 1;
+        while (q0 < le && is_ws(*q0)) ++q0;
+        const char* q = q0;
+        while (q < le && !is_ws(*q)) ++q;
+        name_off[r] = (uint64_t)(q0 - buf); name_len[r] = (uint32_t)(q - q0);
+        Head h{0, 0, 0, 0, 0, (uint64_t)(rec_end - buf), false, true};
+        const uint64_t soff = (uint64_t)((nl ? nl + 1 : rec_end) - buf);
+        seq_off[r] = soff;
+        h.send = soff;
+        p = buf + soff;
+        while (p < rec_end) {                          // the serial rule, until the first non-empty line has been taken
+            nl = (const char*)memchr(p, '\n', (size_t)(rec_end - p));
+            le = nl ? nl : rec_end;
+            const uint64_t raw = (uint64_t)(le - p) + (nl ? 1 : 0);
+            uint64_t len = (uint64_t)(le - p);
+            while (len && (p[len - 1] == '\r')) --len;
+            const bool first = h.lb == 0;
+            if (first) { h.lb = len; h.lw = raw; }
+            if (h.short_seen && len) h.uni = false;
+            if (len != h.lb || raw != h.lw) h.short_seen = true;
+            h.bases += len;
+            h.send = (uint64_t)(le - buf);
+            p = nl ? nl + 1 : rec_end;
+            if (first && len) break;
+        }
+        h.resume = (uint64_t)(p - buf);
+        heads[r] = h;
+    }
+    // ---- C: pieces of the record bodies
+    struct Piece { uint64_t rec, a, b, bases, send; bool any_line, odd, viol, nonempty; };
+    std::vector<Piece> pieces;
+    const uint64_t target = 8ull << 20;
+    for (uint64_t r = 0; r < nr; ++r) {
+        uint64_t a = heads[r].resume;
+        const uint64_t e = heads[r].span_end;
+        while (a < e) {
+            uint64_t b = std::min(e, a + target);
+            if (b < e) {                               // cut after the next newline
+                const char* nl = (const char*)memchr(buf + b, '\n', (size_t)(e - b));
+                b = nl ? (uint64_t)(nl + 1 - buf) : e;
+            }
+            pieces.push_back({r, a, b, 0, 0, false, false, false, false});
+            a = b;
+        }
+    }
+    run_threads(pieces.size(), [&](size_t i) {
+        Piece& pc = pieces[i];
+        const uint64_t lb = heads[pc.rec].lb, lw = heads[pc.rec].lw;
+        const char* p = buf + pc.a;
+        const char* const e = buf + pc.b;
+        while (p < e) {
+            const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+            const char* le = nl ? nl : e;
+            const uint64_t raw = (uint64_t)(le - p) + (nl ? 1 : 0);
+            uint64_t len = (uint64_t)(le - p);
+            while (len && (p[len - 1] == '\r')) --len;
+            if (pc.odd && len) pc.viol = true;
+            if (len != lb || raw != lw) pc.odd = true;
+            if (len) pc.nonempty = true;
+            pc.bases += len;
+            pc.send = (uint64_t)(le - buf);
+            pc.any_line = true;
+            p = nl ? nl + 1 : e;
+        }
+    });
+    // ---- D: merge
+    size_t pi = 0;
+    for (uint64_t r = 0; r < nr; ++r) {
+        Head& h = heads[r];
+        for (; pi < pieces.size() && pieces[pi].rec == r; ++pi) {
+            const Piece& pc = pieces[pi];
+            if ((h.short_seen && pc.nonempty) || pc.viol) h.uni = false;
+            if (pc.odd) h.short_seen = true;
+            h.bases += pc.bases;
+            if (pc.any_line) h.send = pc.send;
+        }
+        n_bases[r] = h.bases; seq_end[r] = h.send; linebases[r] = (uint32_t)h.lb; linewidth[r] = (uint32_t)h.lw; uniform[r] = h.uni ? 1 : 0;
+    }
+    return NTS_OK;
+}
+
 /* Pass 2: pack every record.  word_off[r] = offset (in 64-bit words, even) of record r in words_out, which holds
  * sum of nts_packed_words(n_bases[r]) words; N runs of all records go to nrun_start / nrun_len (record coordinates),
  * record r owning entries [nrun_off[r], nrun_off[r+1]).  If there are more runs than nrun_cap only the count is

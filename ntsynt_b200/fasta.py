@@ -122,9 +122,9 @@ def parse_fasta_bytes(data, path=None, threads=0):
         name_len, lb, lw = (np.zeros(cap, dtype=np.uint32) for _ in range(3))
         uni = np.zeros(cap, dtype=np.uint8)
         nrec = C.c_uint64()
-        check(lib.nts_fasta_scan(data, n, cap, ptr(name_off, C.c_uint64), ptr(name_len, C.c_uint32), ptr(n_bases, C.c_uint64),
-                                 ptr(seq_off, C.c_uint64), ptr(seq_end, C.c_uint64), ptr(lb, C.c_uint32), ptr(lw, C.c_uint32),
-                                 ptr(uni, C.c_uint8), C.byref(nrec)))
+        check(lib.nts_fasta_scan_mt(data, n, cap, ptr(name_off, C.c_uint64), ptr(name_len, C.c_uint32), ptr(n_bases, C.c_uint64),
+                                    ptr(seq_off, C.c_uint64), ptr(seq_end, C.c_uint64), ptr(lb, C.c_uint32), ptr(lw, C.c_uint32),
+                                    ptr(uni, C.c_uint8), C.byref(nrec), int(threads)))
         if nrec.value <= cap:
             break
         cap = int(nrec.value)
@@ -153,12 +153,89 @@ def parse_fasta_bytes(data, path=None, threads=0):
     return PackedGenome(names, n_bases, word_off[:R], words, nrun_off, rs[:nruns.value], rl[:nruns.value], fai, path)
 
 
+def _bgzf_blocks(raw):
+    """offsets [(start, end)] of the members of a BGZF file (bgzip: every gzip member carries its own compressed size in
+    a 'BC' extra field), or None when `raw` is not BGZF from the first to the last byte"""
+    out, off, n = [], 0, len(raw)
+    while off < n:
+        if n - off < 18 or raw[off:off + 4] != b"\x1f\x8b\x08\x04":
+            return None
+        xlen = int.from_bytes(raw[off + 10:off + 12], "little")
+        x, xend, bsize = off + 12, off + 12 + xlen, None
+        while x + 4 <= xend:
+            slen = int.from_bytes(raw[x + 2:x + 4], "little")
+            if raw[x:x + 2] == b"BC" and slen == 2:
+                bsize = int.from_bytes(raw[x + 4:x + 6], "little") + 1
+            x += 4 + slen
+        if bsize is None or off + bsize > n:
+            return None
+        out.append((off, off + bsize))
+        off += bsize
+    return out
+
+
+def inflate_gz(raw, threads=0):
+    """gzip bytes -> plain bytes.  BGZF input (independent members) is inflated by `threads` threads, a batch of
+    members each (zlib releases the GIL); anything else goes through one streaming inflate that follows concatenated
+    members, as `gzip -dc` does -- which is how btllib's SeqReader reads .gz too (one decompressor process per file)."""
+    import os
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    blocks = _bgzf_blocks(raw) if raw[:4] == b"\x1f\x8b\x08\x04" else None
+    threads = threads or os.cpu_count() or 1
+    if blocks and len(blocks) > 64 and threads > 1:
+        view = memoryview(raw)
+        per = max(64, (len(blocks) + 8 * threads - 1) // (8 * threads))
+
+        def job(i):
+            # deflate payload of a member: after the 12 + xlen byte header, before the 8 byte CRC32 / ISIZE trailer
+            parts = []
+            for a, b in blocks[i:i + per]:
+                xlen = int.from_bytes(view[a + 10:a + 12], "little")
+                parts.append(zlib.decompress(view[a + 12 + xlen:b - 8], -15))
+            return b"".join(parts)
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            return b"".join(ex.map(job, range(0, len(blocks), per)))
+    out, data = [], memoryview(raw)
+    while len(data):
+        d = zlib.decompressobj(31)
+        for i in range(0, len(data), 1 << 24):
+            out.append(d.decompress(data[i:i + (1 << 24)]))
+            if d.eof:
+                break
+        out.append(d.flush())
+        if not d.eof:
+            raise ValueError("truncated gzip stream")
+        data = memoryview(d.unused_data).toreadonly() if d.unused_data else data[:0]
+        while len(data) and data[0] == 0:          # zero padding between / after members is legal
+            data = data[1:]
+    return b"".join(out)
+
+
 def read_fasta(path, threads=0):
     "FASTA file (.gz accepted) -> PackedGenome through the native reader (csrc/nts_fasta.cu)"
-    op = gzip.open if str(path).endswith(".gz") else open
-    with op(path, "rb") as fh:
+    with open(path, "rb") as fh:
         data = fh.read()
+    if data[:2] == b"\x1f\x8b":
+        data = inflate_gz(data, threads)
     return parse_fasta_bytes(data, path=path, threads=threads)
+
+
+def read_fastas(paths, threads=0):
+    """the files of a run read CONCURRENTLY (one reader per file -- each inflates and scans on its own and shares the
+    packer's threads); yields (index, PackedGenome) in the order of `paths` as soon as each is ready, so that the caller
+    can upload and insert genome i while the later ones are still being parsed"""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    n = len(paths)
+    if n == 0:
+        return
+    total = threads or os.cpu_count() or 1
+    workers = min(n, max(1, total // 2))
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        futs = [ex.submit(read_fasta, p, max(1, total // workers)) for p in paths]
+        for i, f in enumerate(futs):
+            yield i, f.result()
 
 
 def write_fai(packed, out_path):

@@ -57,6 +57,44 @@ def build_common_bf(ctx, genomes, paths, k, fpr=0.025, nbytes=None, log=None):
     return common
 
 
+def ingest_and_build(ctx, fastas, k, fpr=0.025, common=True, timing=None):
+    """FASTA files -> device genomes + common Bloom filter as a pipeline: the files are read concurrently
+    (fasta.read_fastas: inflate + scan + multi-threaded pack per file); genome i is uploaded on the copy stream and
+    inserted into the filter as soon as it is parsed, in the sorted-path order of src/ntsynt_make_common_bf.cpp:107-160,
+    while the later files are still being read.  Returns (packed, genomes, bf) in the order of `fastas`."""
+    G = len(fastas)
+    bf_order = sorted(range(G), key=lambda i: str(fastas[i]))
+    packed, genomes = [None] * G, [None] * G
+    bf = level = None
+    t0 = time.perf_counter()
+    wait = 0.0
+    it = fasta.read_fastas([fastas[i] for i in bf_order])
+    for j in range(G):
+        tw = time.perf_counter()
+        _, pk = next(it)
+        wait += time.perf_counter() - tw
+        i = bf_order[j]
+        packed[i] = pk
+        genomes[i] = ctx.upload(pk, async_copy=True)
+        if not common:
+            continue
+        if j == 0:
+            bf = ctx.bloom(device.BloomFilter.size_for(genomes[i].total_bases, fpr))
+            bf.set_genome(genomes[i], k)
+        else:
+            if level is None:
+                level = ctx.bloom(bf.nbytes)
+            level.set_genome(genomes[i], k)
+            bf.iand(level)
+    if level is not None:
+        level.close()
+    ctx.sync()
+    if timing is not None:
+        timing["ingest_build_s"] = time.perf_counter() - t0
+        timing["waited_for_parser_s"] = wait
+    return packed, genomes, bf
+
+
 class CudaBackend:
     "SyntenyEngine backend on the CUDA library (the only backend the package ships)"
 
@@ -143,15 +181,17 @@ def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="100
     `packed`: optional pre-parsed fasta.PackedGenome list (same order as `fastas`)."""
     own_ctx = ctx is None
     ctx = ctx or device.Context(device_index)
-    if packed is None:
-        packed = [fasta.read_fasta(f) for f in fastas]
     bases = [os.path.basename(f)[:-3] if f.endswith(".gz") else os.path.basename(f) for f in fastas]
     names = [tsv_name(b, k, w) for b in bases]
     order = processing_order(names)
-    genomes = [ctx.upload(p) for p in packed]
-    # the filter is sized from the lexicographically first PATH STRING as given (src/ntsynt_make_common_bf.cpp:107,116),
-    # not from the first basename
-    bf = build_common_bf(ctx, genomes, [str(f) for f in fastas], k, fpr) if common else None
+    timing = {}
+    if packed is None:
+        packed, genomes, bf = ingest_and_build(ctx, fastas, k, fpr, common, timing)
+    else:
+        genomes = [ctx.upload(p) for p in packed]
+        # the filter is sized from the lexicographically first PATH STRING as given (src/ntsynt_make_common_bf.cpp:107,116),
+        # not from the first basename
+        bf = build_common_bf(ctx, genomes, [str(f) for f in fastas], k, fpr) if common else None
     be = CudaBackend(ctx, [genomes[i] for i in order], [names[i] for i in order],
                      [packed[i].names for i in order], [[int(x) for x in packed[i].lengths] for i in order], k,
                      common=bf)
@@ -173,6 +213,8 @@ def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="100
         eng.dot_path = f"{prefix}.mx.dot"
     out = eng.run()
     eng.backend_timing = be.timing
+    eng.ingest_timing = timing
+    eng.total_bases = sum(p.total_bases for p in packed)
     be.close()
     if bf is not None:
         bf.close()
