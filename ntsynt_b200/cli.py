@@ -5,6 +5,7 @@
    ntsynt_run.py          bin/ntsynt_run.py:10-50
    ntsynt_make_repeat_bfs.py   bin/ntsynt_make_repeat_bfs.py:10-69
    denovo_synteny_block_stats.py   analysis_scripts/denovo_synteny_block_stats.py
+   sort_ntsynt_blocks.py  visualization_scripts/sort_ntsynt_blocks.py
 """
 import argparse
 import os
@@ -357,4 +358,40 @@ def main_block_stats(argv=None):
     head, vals = block_stats(args.tsv, args.fai)
     print(*head, sep="\t")
     print("\t".join(str(v) for v in vals))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ sort blocks
+def sort_blocks_text(text, order):
+    """visualization_scripts/sort_ntsynt_blocks.py:16-41: the rows of every block re-ordered by the rank of their assembly
+    in `order` (dict name -> rank); 8-column rows keep all columns, other rows their first six."""
+    out, cur, cur_id = [], [], None
+
+    def flush():
+        for row in sorted(cur, key=lambda r: order[r[1]]):
+            out.append("\t".join(row) + "\n")
+    for line in text.splitlines():
+        f = line.strip().split("\t")
+        row = f if len(f) == 8 else f[:6]
+        if cur_id is not None and row[0] != cur_id:
+            flush()
+            cur = []
+        cur.append(row)
+        cur_id = row[0]
+    flush()
+    return "".join(out)
+
+
+def main_sort_blocks(argv=None):
+    ap = argparse.ArgumentParser(description="Sort the assemblies in the ntSynt synteny blocks in specified order")
+    ap.add_argument("--synteny_blocks", help="Input synteny blocks", required=True, type=str)
+    ap.add_argument("--sort_order", help="Desired assembly sort order", nargs="+", required=True)
+    ap.add_argument("--fais", help="The assembly sort order option lists the FAI files for the assemblies", action="store_true")
+    args = ap.parse_args(argv)
+    if args.fais:
+        order = {re.search(r"^(\S+)\.fai$", os.path.basename(os.path.realpath(a))).group(1): i for i, a in enumerate(args.sort_order)}
+    else:
+        order = {a: i for i, a in enumerate(args.sort_order)}
+    with open(args.synteny_blocks, "r", encoding="utf-8") as fh:
+        sys.stdout.write(sort_blocks_text(fh.read(), order))
     return 0

@@ -922,6 +922,9 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
         const double density = lambda / (double)w;
         uint32_t c_target = (uint32_t)(3.1 / density);
         c_target = std::max<uint32_t>(4, std::min<uint32_t>(c_target, 120));
+        // a thread's run = its seed + 16 j roll steps: hash_run then stays in its unrolled 16-step path (the generic
+        // remainder loop costs ~4 instructions per k-mer of the whole kernel at 120 slots per thread)
+        if (c_target >= 17) c_target = 16 * ((c_target - 1) / 16) + 1;
         const uint32_t nt_target = std::max<uint32_t>(THREADS * c_target, 2 * w);
         const uint32_t ts_target = nt_target - w;
         R = (ts_target + T - 1) / T;

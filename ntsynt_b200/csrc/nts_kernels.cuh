@@ -705,7 +705,9 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
                 if (e >= e1) break;
                 int neu;
                 if (e_out <= e_in) {
-                    neu = scan(lower(e + 1 - w), e, &nxt);   // the minimum left: look at the whole window again
+                    // the minimum left: every candidate before it has left too (smaller slot), so the new minimum is
+                    // among the candidates after it that have entered -- no search for the window's first candidate
+                    neu = scan((uint32_t)cur + 1u, e, &nxt);
                 } else {
                     const uint64_t kx = c_key[nxt];
                     neu = (kx != KEY_MAX && (cur < 0 || kx <= c_key[cur])) ? (int)nxt : cur;

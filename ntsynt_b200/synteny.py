@@ -224,6 +224,39 @@ class LazyVector:
                               np.atleast_1d(np.asarray(vals, dtype=np.uint64)).tolist()))
 
 
+class EdgeBirth:
+    """(u, v) -> (round, sequence number) of the edges added by the refinement rounds, in build_graph's insertion
+    order (an edge's id order in the reference's igraph object).  Kept as sorted key arrays per round; looked up one
+    edge at a time, and only for the few old edges the simplification has to order."""
+
+    def __init__(self):
+        self.rounds = []            # (round_no, sorted packed keys, sequence numbers in that order)
+
+    def add_round(self, round_no, eu, ev):
+        if len(eu):
+            key = (np.minimum(eu, ev).astype(np.int64) << np.int64(32)) | np.maximum(eu, ev).astype(np.int64)
+            o = np.argsort(key, kind="stable")
+            self.rounds.append((round_no, key[o], o))
+
+    def get(self, key):
+        u, v = key
+        pk = (min(u, v) << 32) | max(u, v)
+        for round_no, keys, seq in self.rounds:
+            i = int(np.searchsorted(keys, pk))
+            if i < len(keys) and int(keys[i]) == pk:
+                return (round_no, int(seq[i]))
+        return None
+
+    def __contains__(self, key):
+        return self.get(key) is not None
+
+    def __getitem__(self, key):
+        got = self.get(key)
+        if got is None:
+            raise KeyError(key)
+        return got
+
+
 class SyntenyEngine:
     """backend must provide:
          names[a]            TSV-style assembly names, ALREADY in the reference's processing order
@@ -1566,15 +1599,12 @@ class SyntenyEngine:
             eu, ev, cnt_ = eu[~has], ev[~has], cnt_[~has]
             if not (self.alive[eu].all() and self.alive[ev].all()):
                 raise RuntimeError("internal error: edge to a vertex that is not in the graph")
-        fresh = list(zip(eu.tolist(), ev.tolist()))
-        wt = dict(zip(fresh, cnt_.tolist()))
-        self._edge_birth.update(zip(fresh, ((round_no, seq) for seq in range(len(fresh)))))
-
-        def old_nbrs(x):
-            return [int(y) for y in self.nbr[x] if y >= 0]
-
+        cnt_ = cnt_.astype(np.int64)
+        self._edge_birth.add_round(round_no, eu, ev)
         # incident-weight guard (check_added_edges_incident_weights :70-80), per touched vertex
-        flagged, cand_v, inc_new = [], [], defaultdict(list)
+        fl = np.zeros(len(eu), dtype=bool)
+        cand = np.zeros(0, dtype=np.int64)
+        at_cand = np.zeros(0, dtype=np.int64)
         if len(eu):
             ends = np.concatenate([eu, ev])
             tv, inv_ = np.unique(ends, return_inverse=True)
@@ -1583,93 +1613,88 @@ class SyntenyEngine:
             old_deg = (self.nbr[tv] >= 0).sum(axis=1)
             heavy = (G * old_deg + new_w) > 2 * G
             fl = heavy[inv_[:len(eu)]] | heavy[inv_[len(eu):]]
-            flagged = [fresh[i] for i in np.flatnonzero(fl).tolist()]
             # simplification candidates: touched vertices with exactly three neighbours in the extended graph
             cand_mask = (old_deg + new_deg) == 3
-            cand_v = tv[cand_mask].tolist()
-            if cand_v:
-                at_cand = cand_mask[inv_[:len(eu)]] | cand_mask[inv_[len(eu):]]
-                for i in np.flatnonzero(at_cand).tolist():
-                    key = fresh[i]
-                    inc_new[key[0]].append(key); inc_new[key[1]].append(key)
-        flagged_set = set(flagged)
+            cand = tv[cand_mask]                       # sorted
+            if len(cand):
+                at_cand = np.flatnonzero(cand_mask[inv_[:len(eu)]] | cand_mask[inv_[len(eu):]])
         # --- simplification runs on the graph WITH the flagged edges; its weight bumps survive only
-        #     when nothing was flagged (same object), its vertex deletions never do
-        if self.simplify:
-            bumps = self._simplify_extended(fresh, wt, inc_new, old_nbrs, cand_v)
-            if not flagged:
-                for key in bumps:
-                    if key in wt:
-                        wt[key] = G
+        #     when nothing was flagged (same object), its vertex deletions never do -- so with a
+        #     flagged edge there is nothing to compute
+        if self.simplify and len(cand) and not fl.any():
+            cnt_[self._simplify_extended(eu, ev, cnt_, cand, at_cand)] = G
         self._tick("r_graph")
         # --- weight filter (+ flagged pairs on the last round)
-        surviving = [key for key in fresh if key not in flagged_set]
-        low = [key for key in surviving if wt[key] < G]
-        full = [key for key in surviving if wt[key] >= G]
-        if full:
-            fa = np.array(full, dtype=np.int64)
-            self._add_edges(fa[:, 0], fa[:, 1])
-        if last_round and low:
-            self._erode(low)
+        full = ~fl & (cnt_ >= G)
+        if full.any():
+            self._add_edges(eu[full], ev[full])
+        low = ~fl & (cnt_ < G)
+        if last_round and low.any():
+            self._erode(np.stack([eu[low], ev[low]], axis=1))
         return None
 
-    def _simplify_extended(self, fresh, wt, inc_new, old_nbrs, cand_v):
-        """run_graph_simplification on the extended graph; returns the edges whose weight it sets to G.
-        cand_v: the touched vertices with exactly three neighbours; inc_new: the new edges at those vertices."""
+    def _simplify_extended(self, eu, ev, wt, cand, at_cand):
+        """run_graph_simplification on the extended graph; returns the indices of the NEW edges whose weight it sets to G
+        (bumps of old edges change nothing: they are at full weight already).
+        eu / ev / wt: the new edges in insertion order and their weights; cand: the touched vertices with exactly three
+        neighbours (sorted); at_cand: indices of the new edges with an end in `cand`.
+
+        A candidate edge joins two candidates; it is bumped when both ends have exactly one full-weight edge at that
+        moment (a bump adds one at both ends) and share exactly one other neighbour.  The shared-neighbour test does
+        not depend on the visiting order, so it is taken for all candidate edges at once on [n, 3] neighbour tables;
+        only the edges that pass it are visited in edge-id order."""
         G = self.G
-
-        memo = {}
-
-        def nbrs(x):
-            res = memo.get(x)
-            if res is None:
-                row = rows.get(x)
-                res = {y: G for y in (row if row is not None else old_nbrs(x)) if y >= 0}
-                for e in inc_new.get(x, ()):
-                    y = e[1] if e[0] == x else e[0]
-                    res[y] = wt[e]
-                memo[x] = res
-            return res
-
-        if not cand_v:
+        n = len(cand)
+        # neighbour table: the old neighbours (weight G) and the other ends of the new edges, three per candidate
+        rows = self.nbr[cand]
+        ci_old, slot_old = np.nonzero(rows >= 0)
+        a_, b_ = eu[at_cand], ev[at_cand]
+        pa, pb = np.searchsorted(cand, a_), np.searchsorted(cand, b_)
+        pa[pa >= n] = 0; pb[pb >= n] = 0
+        ia, ib = cand[pa] == a_, cand[pb] == b_
+        ci = np.concatenate([ci_old, pa[ia], pb[ib]])
+        nb = np.concatenate([rows[ci_old, slot_old].astype(np.int64), b_[ia], a_[ib]])
+        ww = np.concatenate([np.full(len(ci_old), G, dtype=np.int64), wt[at_cand][ia], wt[at_cand][ib]])
+        eid = np.concatenate([np.full(len(ci_old), -1, dtype=np.int64), at_cand[ia], at_cand[ib]])     # new edge index, -1 = old
+        if len(ci) != 3 * n:
+            raise RuntimeError("internal error: a simplification candidate without exactly three neighbours")
+        o = np.argsort(ci, kind="stable")
+        N3, W3, E3 = nb[o].reshape(n, 3), ww[o].reshape(n, 3), eid[o].reshape(n, 3)
+        # candidate edges: (candidate, neighbour) entries whose neighbour is a candidate too, once per edge
+        pos = np.searchsorted(cand, N3)
+        pos[pos >= n] = 0
+        take = (cand[pos] == N3) & (cand[:, None] < N3)
+        si, sl = np.nonzero(take)
+        if not len(si):
             return []
-        rows = dict(zip(cand_v, self.nbr[np.asarray(cand_v, dtype=np.int64)].tolist()))    # old neighbours, one gather
-        cand_v = set(cand_v)
-        bumped = {}
-
-        fullc = {}          # number of full-weight edges at a candidate; a bump adds one at both ends
-
-        def anchored(u):
-            c = fullc.get(u)
-            if c is None:
-                c = fullc[u] = sum(1 for w_ in nbrs(u).values() if w_ == G)
-            return c == 1
-
-        # candidate edges in edge-id order: old edges first (their relative order only matters among
-        # themselves), then the new edges in insertion order
-        old_c, new_c = [], []
-        fresh_pos = {key: i for i, key in enumerate(fresh)}
-        for u in cand_v:
-            for x in nbrs(u):
-                if x in cand_v:
-                    key = (u, x) if u < x else (x, u)
-                    if key in fresh_pos:
-                        new_c.append(key)
-                    else:
-                        old_c.append(key)
-        old_c = set(old_c)
-        self._prefetch_edge_keys([e for e in old_c if e not in self._edge_birth])
-        old_c = sorted(old_c, key=self._old_edge_key)
-        new_c = sorted(set(new_c), key=lambda e: fresh_pos[e])
+        ti = pos[si, sl]
+        t_v = N3[si, sl]
+        A, B = N3[si], N3[ti]
+        shared = ((A[:, :, None] == B[:, None, :]).any(axis=2) & (A != t_v[:, None])).sum(axis=1)
+        ok = shared == 1
+        if not ok.any():
+            return []
+        si, sl, ti, t_v = si[ok], sl[ok], ti[ok], t_v[ok]
+        w_e, e_e = W3[si, sl], E3[si, sl]
+        # edge-id order: old edges first (their relative order only matters among themselves), then the new ones in
+        # insertion order
+        old_ix = np.flatnonzero(e_e < 0).tolist()
+        new_ix = np.flatnonzero(e_e >= 0)
+        new_ix = new_ix[np.argsort(e_e[new_ix], kind="stable")].tolist()
+        if old_ix:
+            keys = dict(zip(old_ix, zip(cand[si[old_ix]].tolist(), t_v[old_ix].tolist())))
+            self._prefetch_edge_keys([k_ for k_ in keys.values() if k_ not in self._edge_birth])
+            old_ix.sort(key=lambda i: self._old_edge_key(keys[i]))
+        fullc = (W3 == G).sum(axis=1).tolist()      # full-weight edges at a candidate; a bump adds one at both ends
+        si_l, ti_l, w_l, e_l = si.tolist(), ti.tolist(), w_e.tolist(), e_e.tolist()
         out = []
-        for s, t in old_c + new_c:
-            if anchored(s) and anchored(t):
-                common = [x for x in nbrs(s) if x != t and x in nbrs(t)]
-                if len(common) == 1:
-                    if (s, t) not in bumped and nbrs(s)[t] != G:
-                        fullc[s] += 1; fullc[t] += 1
-                    bumped[(s, t)] = G
-                    out.append((s, t))
+        for i in old_ix + new_ix:
+            a, b = si_l[i], ti_l[i]
+            if fullc[a] == 1 and fullc[b] == 1:
+                if w_l[i] != G:
+                    fullc[a] += 1; fullc[b] += 1
+                if e_l[i] >= 0:
+                    out.append(e_l[i])
         return out
 
     def _old_edge_key(self, key):
@@ -1685,8 +1710,17 @@ class SyntenyEngine:
         def name(x):
             return str(int(self.H[x]))
 
+        pos_memo = {}
+
+        def pos_of(x):
+            got = pos_memo.get(x)
+            if got is None:
+                got = pos_memo[x] = [int(v) for v in self.POS[:, x]]
+            return got
+
         def overlap(s, t):
-            return bool((np.abs(self.POS[:, s] - self.POS[:, t]) < self.k).any())
+            k = self.k
+            return any(abs(a - b) < k for a, b in zip(pos_of(s), pos_of(t)))
 
         # the graph is not modified inside the loop (removals are applied at the end), so the degree test of every
         # flagged pair can be taken up front
@@ -1701,6 +1735,8 @@ class SyntenyEngine:
                 nb = self.nbr[ring].ravel()
                 ring = np.unique(np.concatenate([ring, nb[nb >= 0]]))
             self.POS.prefetch(ring)
+            cols = np.asarray(self.POS[:, ring], dtype=np.int64)
+            pos_memo.update(zip(ring.tolist(), cols.T.tolist()))
         for (u, v), (hu, hv_) in zip(sel.tolist(), hv.tolist()):
             # igraph reports (source, target) = (min id, max id); the reference then orders by NAME string
             s, t = (u, v)
@@ -1745,7 +1781,7 @@ class SyntenyEngine:
             self.be.write_dot(self.dot_path, j)
         self._init_vertices(j)
         self._tick("init")
-        self._edge_birth = {}
+        self._edge_birth = EdgeBirth()
         V = self.V0
         # --- simplification, weight filter
         bumped, removed = ({}, [])
@@ -1797,7 +1833,9 @@ class SyntenyEngine:
                 self._emit("pre_merge", ordered)
             if last:
                 merged = self._merge_collinear(ordered) if ordered else []
-                merged = [b for b in merged if self._long_enough(b)]
+                if merged:
+                    st_, en_, _ = self._block_coords(merged)
+                    merged = [merged[i] for i in np.flatnonzero(((en_ - st_) >= self.z).all(axis=1)).tolist()]
                 merged = self._merge_collinear(merged) if merged else []
                 if self.dev:
                     self._check_non_overlapping(merged)

@@ -211,3 +211,21 @@ def test_repeat_bf_size_argument():
     assert [cli.parse_bf_size(x, ap) for x in ("17B", "3k", "5M", "2G")] == [17, 3000, 5000000, 2000000000]
     with pytest.raises(SystemExit):
         cli.parse_bf_size("12", ap)
+
+
+def test_sort_blocks_utility(tmp_path):
+    "visualization_scripts/sort_ntsynt_blocks.py: fixture written by the reference's own script (order C, A, B)"
+    import gzip
+    import shutil
+    import sys
+    BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin")
+    shutil.copyfile(os.path.join(MINI, "ABC", "synteny_blocks.tsv"), tmp_path / "b.tsv")
+    out = _run([sys.executable, os.path.join(BIN, "sort_ntsynt_blocks.py"), "--synteny_blocks", "b.tsv", "--sort_order",
+                "miniC.fa", "miniA.fa", "miniB.fa"], tmp_path)
+    with gzip.open(os.path.join(MINI, "ABC", "sorted_CAB.tsv.gz"), "rt") as fh:
+        assert out == fh.read()
+    for n in ("miniC.fa", "miniA.fa", "miniB.fa"):
+        (tmp_path / (n + ".fai")).write_text("x\t1\t0\t1\t2\n")
+    out2 = _run([sys.executable, os.path.join(BIN, "sort_ntsynt_blocks.py"), "--synteny_blocks", "b.tsv", "--fais", "--sort_order",
+                 "miniC.fa.fai", "miniA.fa.fai", "miniB.fa.fai"], tmp_path)
+    assert out2 == out
