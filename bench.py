@@ -307,10 +307,13 @@ def run_ours(args, dist):
     def hot_path(gen_list):
         # src/ntsynt_make_common_bf.cpp:107-160 on resident genomes, filters re-zeroed every step
         t_hp = time.perf_counter()
-        common.build_common(level, [gen_list[i] for i in size_sorted], K)      # zero-fill, insert x G, AND: pipelined
+        # zero-fills, insert x G, AND x (G - 2); the last level stays apart and the sketches look candidates up in both
+        # filters (nts_bf_build_common_lazy / nts_sketch2) instead of one more pass over 2 x 14.8 GB
+        apart = common.build_common(level, [gen_list[i] for i in size_sorted], K, lazy=True)
         phase["bf_wall_ms"] = phase.get("bf_wall_ms", 0.0) + (time.perf_counter() - t_hp) * 1e3
         be = pipeline.CudaBackend(ctx, [gen_list[i] for i in order], [names[i] for i in order], [wl.names] * G,
-                                  [[int(x) for x in gen_list[i].lengths] for i in order], K, common=common)
+                                  [[int(x) for x in gen_list[i].lengths] for i in order], K, common=common,
+                                  common2=level if apart else None)
         eng = SyntenyEngine(be, K, W, ps["w_rounds"], ps["indel"], ps["merge"], ps["block_size"], write_files=False,
                             quiet=True)
         text = eng.run()

@@ -162,6 +162,12 @@ int nts_bf_or(nts_bf* dst, const nts_bf* src);
  * zero-fill and no separate AND pass; the two filters may swap their device storage.  Result is bit-identical to
  * nts_bf_insert_genome + nts_bf_and. */
 int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k);
+/* the same without the last AND pass (one read + one write of both 14.8 GB arrays): on return, when *level_is_apart = 1,
+ * `common` = AND over genomes 0 .. n-2 and `level` = bits(genome n-1) -- their AND is the common filter of
+ * src/ntsynt_make_common_bf.cpp:136-160; nts_sketch2 takes the pair, nts_bf_and(common, level) makes it one filter when
+ * one is needed (saving it, merging across GPUs).  *level_is_apart = 0: `common` is complete, `level` is scratch. */
+int nts_bf_build_common_lazy(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k,
+                             int* level_is_apart);
 /* repeat filter, bin/ntsynt_make_repeat_bfs.py:56-69: rep |= k-mers seen >= 2x in g (kernel iii-d).
  * `scratch` is a per-genome filter of the same size that the call clears and uses. */
 int nts_bf_insert_repeats(nts_bf* rep, nts_bf* scratch, const nts_genome* g, uint32_t k);
@@ -178,6 +184,10 @@ int nts_bf_upload(nts_bf* bf, const uint8_t* bytes_in);
 int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common /*nullable*/, const nts_bf* repeat /*nullable*/,
                uint32_t k, uint32_t w, const uint64_t* mask_off, const uint64_t* mask_start,
                const uint64_t* mask_end, nts_mxs** out);
+/* nts_sketch with the common filter given as two filters of equal size whose AND it is (common2 may be null) */
+int nts_sketch2(nts_ctx* ctx, const nts_genome* g, const nts_bf* common /*nullable*/, const nts_bf* common2 /*nullable*/,
+                const nts_bf* repeat /*nullable*/, uint32_t k, uint32_t w, const uint64_t* mask_off, const uint64_t* mask_start,
+                const uint64_t* mask_end, nts_mxs** out);
 void nts_mxs_destroy(nts_mxs* m);
 uint64_t nts_mxs_count(const nts_mxs* m);
 /* h1 = second ntHash2 hash (what indexlr prints), pos = 0-based k-mer start, contig index */

@@ -83,11 +83,13 @@ _SIGS = {
     "nts_bf_and": (C.c_int, [vp, vp]),
     "nts_bf_or": (C.c_int, [vp, vp]),
     "nts_bf_build_common": (C.c_int, [vp, vp, vpp, C.c_uint32, C.c_uint32]),
+    "nts_bf_build_common_lazy": (C.c_int, [vp, vp, vpp, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]),
     "nts_bf_insert_repeats": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "nts_bf_popcount": (C.c_int, [vp, u64p]),
     "nts_bf_download": (C.c_int, [vp, u8p]),
     "nts_bf_upload": (C.c_int, [vp, u8p]),
     "nts_sketch": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, u64p, u64p, u64p, vpp]),
+    "nts_sketch2": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, u64p, u64p, u64p, vpp]),
     "nts_mxs_destroy": (None, [vp]),
     "nts_mxs_count": (C.c_uint64, [vp]),
     "nts_mxs_download": (C.c_int, [vp, u64p, u32p, u32p]),

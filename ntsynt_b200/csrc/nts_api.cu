@@ -274,6 +274,7 @@ int nts_ctx_create(int device, nts_ctx** out)
     NTS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     NTS_CUDA(cudaEventCreate(&ctx->ev0));
     NTS_CUDA(cudaEventCreate(&ctx->ev1));
+    NTS_CUDA(cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
     *out = ctx;
     return NTS_OK;
 }
@@ -288,6 +289,7 @@ void nts_ctx_destroy(nts_ctx* ctx)
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -560,12 +562,13 @@ uint64_t nts_bf_bytes(int64_t genome_size, double fpr)
     return bytes;
 }
 
-static int bf_fill(nts_bf* bf, uint32_t v)
+static int bf_fill(nts_bf* bf, uint32_t v, cudaStream_t st = nullptr)
 {
     nts_ctx* ctx = bf->ctx;
     uint64_t n16 = bf->alloc_bytes / 16;
-    ProfScope prof(ctx, PROF_FILL, (double)bf->alloc_bytes);
-    fill_u128_kernel<<<grid_for(ctx, n16, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<uint4*>(bf->words.p), n16, v);
+    if (!st) st = ctx->stream;
+    ProfScope prof(ctx, PROF_FILL, (double)bf->alloc_bytes, false, st);
+    fill_u128_kernel<<<grid_for(ctx, n16, 256, 16), 256, 0, st>>>(reinterpret_cast<uint4*>(bf->words.p), n16, v);
     ctx->launches++;
     NTS_CUDA(cudaGetLastError());
     return NTS_OK;
@@ -641,7 +644,7 @@ static int bf_insert_direct(nts_ctx* ctx, nts_bf* bf, const nts_genome* g, const
 // APPLY_SET: bf = bits; APPLY_AND: dst = dst & bits with bf as the scratch level filter of the same size (one level of the
 // cascade, cpp:136-160; `dst` is updated in place -- its device storage may be swapped with the scratch filter's).
 // Large filters take a partitioned path (nts_bin.cuh, or nts_part.cuh with NTS_BF_IMPL=3).
-static int bf_insert_mode(nts_bf* bf, nts_bf* dst, const nts_genome* g, uint32_t k, int mode)
+static int bf_insert_mode(nts_bf* bf, nts_bf* dst, const nts_genome* g, uint32_t k, int mode, cudaEvent_t prefilled = nullptr)
 {
     nts_ctx* ctx = bf->ctx;
     const HashTables* tabs = nullptr;
@@ -663,7 +666,9 @@ static int bf_insert_mode(nts_bf* bf, nts_bf* dst, const nts_genome* g, uint32_t
     }
     // zero-fill (SET / AND), then OR the genome in -- large filters with the binning + apply pair (nts_bin.cuh), small
     // ones with one RED.OR per k-mer; then the AND pass
-    if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
+    // (`prefilled`: the zero-fill already ran on another stream -- wait for it instead)
+    if (prefilled) NTS_CUDA(cudaStreamWaitEvent(ctx->stream, prefilled, 0));
+    else if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
     if (v->total_valid) {
         if ((rc = pair_insert(ctx, bf, device_view(g, v), tabs, v->total_valid, &done))) return rc;
         if (!done && (rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
@@ -755,8 +760,27 @@ int nts_bf_and_async(nts_bf* dst, const nts_bf* src) { return bf_combine(dst, sr
 /* src/ntsynt_make_common_bf.cpp:107-160 in one call: common = AND over the genomes of bits(genome), genomes in the
  * caller's (sorted-path) order.  Genome 0 goes into `common`; every further genome is built in `level` (the cascade
  * level) and ANDed into `common`.  On return `common` holds the result and `level` is scratch. */
+static int bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k, bool lazy,
+                           int* apart_out);
+
 int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k)
 {
+    return bf_build_common(common, level, genomes, n, k, false, nullptr);
+}
+
+/* The same without the last AND pass: on return `common` = AND over genomes 0 .. n-2 and `level` = bits(genome n-1); their
+ * AND is the common filter.  nts_sketch2 takes the pair; nts_bf_and(common, level) makes it one filter when one is needed. */
+int nts_bf_build_common_lazy(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k,
+                             int* level_is_apart)
+{
+    if (!level_is_apart) return fail(NTS_ERR_ARG, "null argument");
+    return bf_build_common(common, level, genomes, n, k, true, level_is_apart);
+}
+
+static int bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* genomes, uint32_t n, uint32_t k, bool lazy,
+                           int* apart_out)
+{
+    if (apart_out) *apart_out = 0;
     if (!common || !genomes || n < 1 || (n > 1 && !level)) return fail(NTS_ERR_ARG, "null argument");
     nts_ctx* ctx = common->ctx;
     if (n > 1 && (level->ctx != ctx || level->bytes != common->bytes)) return fail(NTS_ERR_ARG, "common and level filters differ");
@@ -764,11 +788,28 @@ int nts_bf_build_common(nts_bf* common, nts_bf* level, const nts_genome* const* 
         if (!genomes[i] || genomes[i]->ctx != ctx) return fail(NTS_ERR_ARG, "bad genome");
     NTS_CUDA(cudaSetDevice(ctx->device));
     ProfScope prof(ctx, PROF_BF_BUILD, 0.0, true);
+    // the zero-fill of `level` (a pure HBM write stream) runs on the side stream beside genome 0's insert, whose two
+    // passes sit on atomic issue and use a few per cent of the DRAM bandwidth
+    cudaEvent_t filled = nullptr;
+    const char* e3 = getenv("NTS_BF_IMPL");
+    if (n > 1 && !(e3 && e3[0] == '3')) {
+        if (!ctx->stream2) NTS_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        NTS_CUDA(cudaEventRecord(ctx->ev_side, ctx->stream));            // after whatever still uses `level` on the main stream
+        NTS_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_side, 0));
+        int rcf = bf_fill(level, 0, ctx->stream2);
+        if (rcf) return rcf;
+        NTS_CUDA(cudaEventRecord(ctx->ev_side, ctx->stream2));
+        filled = ctx->ev_side;
+    }
     int rc = bf_insert_mode(common, nullptr, genomes[0], k, APPLY_SET);
     if (rc || (rc = bf_finish_insert(common, nullptr, genomes[0], k, APPLY_SET))) return rc;
-    for (uint32_t i = 1; i < n; ++i)
-        if ((rc = bf_insert_mode(level, common, genomes[i], k, APPLY_AND)) || (rc = bf_finish_insert(level, common, genomes[i], k, APPLY_AND)))
+    for (uint32_t i = 1; i < n; ++i) {
+        const bool apart = lazy && i + 1 == n && !(e3 && e3[0] == '3');           // the last level stays a filter of its own
+        if ((rc = bf_insert_mode(level, common, genomes[i], k, apart ? APPLY_SET : APPLY_AND, i == 1 ? filled : nullptr)) ||
+            (rc = bf_finish_insert(level, common, genomes[i], k, apart ? APPLY_SET : APPLY_AND)))
             return rc;
+        if (apart && apart_out) *apart_out = 1;
+    }
     return NTS_OK;
 }
 
@@ -855,9 +896,19 @@ static size_t sketch_smem_bytes(uint32_t NT, int threads)
 int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nts_bf* repeat, uint32_t k, uint32_t w,
                const uint64_t* mask_off, const uint64_t* mask_start, const uint64_t* mask_end, nts_mxs** out)
 {
+    return nts_sketch2(ctx, g, common, nullptr, repeat, k, w, mask_off, mask_start, mask_end, out);
+}
+
+/* nts_sketch with the common filter given as TWO filters of equal size whose AND it is (nts_bf_build_common_lazy leaves
+ * the last cascade level apart): a candidate is looked up in the second only when the first holds it, which costs less
+ * than one more pass over both 14.8 GB arrays. */
+int nts_sketch2(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nts_bf* common2, const nts_bf* repeat, uint32_t k,
+                uint32_t w, const uint64_t* mask_off, const uint64_t* mask_start, const uint64_t* mask_end, nts_mxs** out)
+{
     if (!ctx || !g || !out) return fail(NTS_ERR_ARG, "null argument");
-    if (g->ctx != ctx || (common && common->ctx != ctx) || (repeat && repeat->ctx != ctx))
+    if (g->ctx != ctx || (common && common->ctx != ctx) || (repeat && repeat->ctx != ctx) || (common2 && common2->ctx != ctx))
         return fail(NTS_ERR_ARG, "objects live on different contexts");
+    if (common2 && (!common || common->bytes != common2->bytes)) return fail(NTS_ERR_ARG, "the two parts of the common filter differ in size");
     if (w < 1) return fail(NTS_ERR_ARG, "w must be >= 1");
     NTS_CUDA(cudaSetDevice(ctx->device));
     constexpr int THREADS = 512;
@@ -899,8 +950,8 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
         {
             ProfScope prof(ctx, PROF_SKETCH, 0.0);
             sketch_sample_kernel<<<(unsigned)((n_samp + 255) / 256), 256, 0, ctx->stream>>>(
-                device_view(g, v), tabs, common ? common->words.p : nullptr, repeat ? repeat->words.p : nullptr, m, mp,
-                rm, rmp, v->total_valid, stride, d_cnt2.p);
+                device_view(g, v), tabs, common ? common->words.p : nullptr, common2 ? common2->words.p : nullptr,
+                repeat ? repeat->words.p : nullptr, m, mp, rm, rmp, v->total_valid, stride, d_cnt2.p);
             ctx->launches++;
         }
         NTS_CUDA(cudaGetLastError());
@@ -1012,11 +1063,12 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
             ProfScope prof(ctx, PROF_SKETCH, (double)v->total_valid);
             const GenomeView gv = device_view(g, v);
             const uint32_t* cw = common ? common->words.p : nullptr;
+            const uint32_t* cw2 = common2 ? common2->words.p : nullptr;
             const uint32_t* rw = repeat ? repeat->words.p : nullptr;
             if (sparse) {
                 unsigned int* esc_count = reinterpret_cast<unsigned int*>(d_total.p + 1);
                 sketch_sparse_kernel<THREADS, SCAP, CCAP><<<n_tiles, THREADS, smem_s, ctx->stream>>>(
-                    gv, tabs, cw, rw, m, mp, rm, rmp, d_tiles.p, w, NT_s, C_s, T, tau_hi, so, d_esc.p, esc_count);
+                    gv, tabs, cw, cw2, rw, m, mp, rm, rmp, d_tiles.p, w, NT_s, C_s, T, tau_hi, so, d_esc.p, esc_count);
                 ctx->launches++;
                 NTS_CUDA(cudaGetLastError());
                 unsigned int n_esc = 0;
@@ -1024,12 +1076,12 @@ int nts_sketch(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const nt
                 NTS_CUDA(cudaStreamSynchronize(ctx->stream));
                 ctx->sketch_escalated += n_esc;
                 if (n_esc) {       // tiles with an unresolved window: the dense selector, every slot queried
-                    sketch_kernel<THREADS><<<n_esc, THREADS, smem, ctx->stream>>>(gv, tabs, cw, rw, m, mp, rm, rmp, d_esc.p, w,
+                    sketch_kernel<THREADS><<<n_esc, THREADS, smem, ctx->stream>>>(gv, tabs, cw, cw2, rw, m, mp, rm, rmp, d_esc.p, w,
                                                                                  T, KEY_MAX, so);
                     ctx->launches++;
                 }
             } else {
-                sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(gv, tabs, cw, rw, m, mp, rm, rmp, d_tiles.p, w, T, tau, so);
+                sketch_kernel<THREADS><<<n_tiles, THREADS, smem, ctx->stream>>>(gv, tabs, cw, cw2, rw, m, mp, rm, rmp, d_tiles.p, w, T, tau, so);
                 ctx->launches++;
             }
         }

@@ -73,6 +73,7 @@ struct nts_ctx {
     cudaStream_t stream2 = nullptr;  // side stream of the pipelined Bloom-filter build (created on first use)
     cudaStream_t stream_copy = nullptr;   // H2D stream of nts_genome_upload_async (created on first use)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_side = nullptr;   // orders the side stream against the main one (nts_bf_build_common)
     uint64_t launches = 0;
     uint64_t sketch_escalated = 0;   // dense sub-tiles the sparse sketch kernel handed to the dense one (statistics)
     uint64_t part_inserts = 0;       // Bloom inserts that took the partitioned path (statistics / tests)

@@ -232,7 +232,7 @@ __device__ __forceinline__ SegAgg cta_exclusive_carry(SegAgg own, SegAgg* s_warp
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 2)
 sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
-              const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
+              const uint32_t* __restrict__ common2, const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
               const TileDesc* __restrict__ tiles,
               uint32_t w, uint32_t T, uint64_t tau, SketchOut out)
 {
@@ -300,6 +300,7 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
         auto probe = [&](uint64_t h, uint64_t idx) -> bool {
             bool keep = true;
             if (common) keep = (__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u;
+            if (keep && common2) keep = (__ldg(&common2[idx >> 5]) >> (idx & 31)) & 1u;      // common = AND of two filters kept apart
             if (keep && repeat) {
                 const uint64_t ridx = fast_mod(h, rm, rmprime);
                 keep = !((__ldg(&repeat[ridx >> 5]) >> (ridx & 31)) & 1u);
@@ -324,6 +325,7 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
             cwv[u] = 0xFFFFFFFFu; rwv[u] = 0;
             if (u < nl) {
                 if (common) cwv[u] = __ldg(&common[lx[u] >> 5]) >> (lx[u] & 31);
+                if (common2) cwv[u] &= __ldg(&common2[lx[u] >> 5]) >> (lx[u] & 31);
                 if (repeat) {
                     const uint64_t ridx = fast_mod(s_key[li[u]], rm, rmprime);
                     rwv[u] = __ldg(&repeat[ridx >> 5]) >> (ridx & 31);
@@ -346,6 +348,7 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
                 cw[u] = 0xFFFFFFFFu; rw[u] = 0;
                 if (i < n_end && i >= i_lo) {
                     if (common) cw[u] = __ldg(&common[idx >> 5]) >> (idx & 31);
+                    if (common2) cw[u] &= __ldg(&common2[idx >> 5]) >> (idx & 31);
                     if (repeat) {
                         const uint64_t ridx = fast_mod(h[u], rm, rmprime);
                         rw[u] = __ldg(&repeat[ridx >> 5]) >> (ridx & 31);
@@ -492,7 +495,7 @@ sketch_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_
 // A few thousand evenly spaced k-mers of the view are hashed and looked up: the fraction that passes the filter
 // decides how many candidates per window the sparse sketch kernel needs (its exactness never depends on it).
 __global__ void sketch_sample_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
-                                     const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
+                                     const uint32_t* __restrict__ common2, const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
                                      uint64_t total_valid,
                                      uint64_t stride, unsigned int* __restrict__ counts /* [0] passed, [1] sampled */)
 {
@@ -505,6 +508,7 @@ __global__ void sketch_sample_kernel(GenomeView g, const HashTables* __restrict_
         const uint64_t idx = fast_mod(h0, m, mprime);
         bool keep = true;
         if (common) keep = (__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u;
+        if (keep && common2) keep = (__ldg(&common2[idx >> 5]) >> (idx & 31)) & 1u;
         if (keep && repeat) {
             const uint64_t ridx = fast_mod(h0, rm, rmprime);
             keep = !((__ldg(&repeat[ridx >> 5]) >> (ridx & 31)) & 1u);
@@ -531,7 +535,7 @@ __global__ void sketch_sample_kernel(GenomeView g, const HashTables* __restrict_
 template <int THREADS, int SCAP, int CCAP>
 __global__ void __launch_bounds__(THREADS, 2)
 sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
-                     const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
+                     const uint32_t* __restrict__ common2, const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
               const TileDesc* __restrict__ tiles,
                      uint32_t w, uint32_t NT, uint32_t C, uint32_t T_dense, uint32_t tau_hi, SketchOut out,
                      TileDesc* __restrict__ esc, unsigned int* __restrict__ esc_count)
@@ -613,6 +617,7 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
             if (i < ncand) {
                 const uint64_t idx = fast_mod(c_key[i], m, mprime);
                 if (common) cw[u] = __ldg(&common[idx >> 5]) >> (idx & 31);
+                if (common2) cw[u] &= __ldg(&common2[idx >> 5]) >> (idx & 31);
                 if (repeat) {
                     const uint64_t ridx = fast_mod(c_key[i], rm, rmprime);
                     rw[u] = __ldg(&repeat[ridx >> 5]) >> (ridx & 31);

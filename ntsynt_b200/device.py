@@ -83,8 +83,9 @@ class Context:
         return BloomFilter(self, nbytes)
 
     # -- sketch (indexlr)
-    def sketch(self, genome, k, w, common=None, repeat=None, masks=None):
-        """masks: optional list (per contig) of (start, end) arrays of extra N intervals."""
+    def sketch(self, genome, k, w, common=None, repeat=None, masks=None, common2=None):
+        """masks: optional list (per contig) of (start, end) arrays of extra N intervals.
+        common2: second part of the common filter (common AND common2; BloomFilter.build_common(lazy=True))."""
         mo = ms = me = None
         if masks is not None:
             off = [0]
@@ -103,9 +104,9 @@ class Context:
                 ms = np.zeros(1, dtype=np.uint64)
                 me = np.zeros(1, dtype=np.uint64)
         h = C.c_void_p()
-        check(lib.nts_sketch(self._h, genome._h, common._h if common else None, repeat._h if repeat else None,
-                             int(k), int(w), ptr(mo, C.c_uint64), ptr(ms, C.c_uint64), ptr(me, C.c_uint64),
-                             C.byref(h)))
+        check(lib.nts_sketch2(self._h, genome._h, common._h if common else None, common2._h if common2 else None,
+                              repeat._h if repeat else None, int(k), int(w), ptr(mo, C.c_uint64), ptr(ms, C.c_uint64),
+                              ptr(me, C.c_uint64), C.byref(h)))
         return MinimizerTable(self, h, genome)
 
     def hash_contig(self, genome, contig, k):
@@ -182,10 +183,17 @@ class BloomFilter:
         "self = bits(genome): clear + insert_genome without the zero-fill pass"
         check(lib.nts_bf_set_genome(self._h, genome._h, int(k)))
 
-    def build_common(self, level, genomes, k):
+    def build_common(self, level, genomes, k, lazy=False):
         """self = AND over the genomes of their k-mer bit arrays (src/ntsynt_make_common_bf.cpp:107-160); `level` is a
-        scratch filter of the same size (None for one genome); both are zeroed inside"""
+        scratch filter of the same size (None for one genome); both are zeroed inside.
+        lazy: the last AND pass is left out; returns True when `level` then holds the last genome's bits and the common
+        filter is the pair (self, level) -- what Context.sketch takes as common / common2 -- else self is complete."""
         arr = (C.c_void_p * len(genomes))(*[g._h for g in genomes])
+        if lazy:
+            apart = C.c_int(0)
+            check(lib.nts_bf_build_common_lazy(self._h, level._h if level is not None else None, arr, len(genomes), int(k),
+                                               C.byref(apart)))
+            return bool(apart.value)
         check(lib.nts_bf_build_common(self._h, level._h if level is not None else None, arr, len(genomes), int(k)))
         return self
 

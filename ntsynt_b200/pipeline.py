@@ -57,11 +57,13 @@ def build_common_bf(ctx, genomes, paths, k, fpr=0.025, nbytes=None, log=None):
     return common
 
 
-def ingest_and_build(ctx, fastas, k, fpr=0.025, common=True, timing=None):
+def ingest_and_build(ctx, fastas, k, fpr=0.025, common=True, timing=None, lazy=False):
     """FASTA files -> device genomes + common Bloom filter as a pipeline: the files are read concurrently
     (fasta.read_fastas: inflate + scan + multi-threaded pack per file); genome i is uploaded on the copy stream and
     inserted into the filter as soon as it is parsed, in the sorted-path order of src/ntsynt_make_common_bf.cpp:107-160,
-    while the later files are still being read.  Returns (packed, genomes, bf) in the order of `fastas`."""
+    while the later files are still being read.  Returns (packed, genomes, bf) in the order of `fastas`.
+    lazy: the last AND pass is left out and (packed, genomes, bf, last) comes back -- the common filter is bf AND last
+    (None with fewer than two genomes), which the sketches take as a pair (nts_sketch2)."""
     G = len(fastas)
     bf_order = sorted(range(G), key=lambda i: str(fastas[i]))
     packed, genomes = [None] * G, [None] * G
@@ -85,21 +87,23 @@ def ingest_and_build(ctx, fastas, k, fpr=0.025, common=True, timing=None):
             if level is None:
                 level = ctx.bloom(bf.nbytes)
             level.set_genome(genomes[i], k)
-            bf.iand(level)
-    if level is not None:
+            if j + 1 < G or not lazy:
+                bf.iand(level)
+    if level is not None and not lazy:
         level.close()
+        level = None
     ctx.sync()
     if timing is not None:
         timing["ingest_build_s"] = time.perf_counter() - t0
         timing["waited_for_parser_s"] = wait
-    return packed, genomes, bf
+    return (packed, genomes, bf, level) if lazy else (packed, genomes, bf)
 
 
 class CudaBackend:
     "SyntenyEngine backend on the CUDA library (the only backend the package ships)"
 
     def __init__(self, ctx, genomes, names, contig_names, contig_lengths, k, common=None, repeat=None, round0=None,
-                 filter_mode=None):
+                 filter_mode=None, common2=None):
         """filter_mode (bin/ntsynt_synteny.py:172-187,601-609): "Indexlr" hands the repeat filter to the sketch kernel
         (indexlr -r: a k-mer in it is never a minimizer), "Filter" drops the minimizers of every sketch whose k-mer is
         in it (read_minimizers(tsv, repeat_bf), ntjoin_utils.py:182)."""
@@ -114,6 +118,7 @@ class CudaBackend:
         self.contig_lengths = contig_lengths
         self.k = k
         self.common, self.repeat = common, repeat
+        self.common2 = common2    # the common filter is (common AND common2) when the last AND pass was left out
         self.round0 = round0      # optional pre-made round-0 tables (bin/ntsynt_run.py: sketches read from TSVs)
         self.graph = None
         self.timing = {"sketch_ms": 0.0, "join_ms": 0.0}
@@ -140,7 +145,8 @@ class CudaBackend:
 
     def _sketch(self, a, w, masks):
         rep = self.repeat if self.filter_mode == "Indexlr" else None
-        return self._drop_repeats(a, self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, repeat=rep, masks=masks))
+        return self._drop_repeats(a, self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, repeat=rep, masks=masks,
+                                                     common2=self.common2))
 
     def _drop_repeats(self, a, mx):
         if self.filter_mode != "Filter":
@@ -185,8 +191,13 @@ def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="100
     names = [tsv_name(b, k, w) for b in bases]
     order = processing_order(names)
     timing = {}
+    bf2 = None
     if packed is None:
-        packed, genomes, bf = ingest_and_build(ctx, fastas, k, fpr, common, timing)
+        packed, genomes, bf, bf2 = ingest_and_build(ctx, fastas, k, fpr, common, timing, lazy=True)
+        if intermediates and bf2 is not None:         # <prefix>.common.bf is one filter
+            bf.iand(bf2)
+            bf2.close()
+            bf2 = None
     else:
         genomes = [ctx.upload(p) for p in packed]
         # the filter is sized from the lexicographically first PATH STRING as given (src/ntsynt_make_common_bf.cpp:107,116),
@@ -194,7 +205,7 @@ def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="100
         bf = build_common_bf(ctx, genomes, [str(f) for f in fastas], k, fpr) if common else None
     be = CudaBackend(ctx, [genomes[i] for i in order], [names[i] for i in order],
                      [packed[i].names for i in order], [[int(x) for x in packed[i].lengths] for i in order], k,
-                     common=bf)
+                     common=bf, common2=bf2)
     eng = SyntenyEngine(be, k, w, list(w_rounds), indel, merge, block_size, simplify=simplify, prefix=prefix,
                         write_files=write_files, quiet=quiet)
     if intermediates:
@@ -218,6 +229,8 @@ def run_ntsynt(fastas, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="100
     be.close()
     if bf is not None:
         bf.close()
+    if bf2 is not None:
+        bf2.close()
     for g in genomes:
         g.close()
     if own_ctx:

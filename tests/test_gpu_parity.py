@@ -397,3 +397,39 @@ def test_oracle_generator_equals_device_genome(cuda_ctx):
             assert seq == dev.contig_ascii(c), (g, c)
         part = so.synth_records(lay, g, per_contig=12345)
         assert all(p[1] == r[1][:12345] for p, r in zip(part, recs))
+
+
+@pytest.mark.parametrize("G", [2, 3])
+def test_common_filter_kept_as_a_pair_gives_the_same_sketches(cuda_ctx, G):
+    """nts_bf_build_common_lazy leaves the last cascade level apart (common AND level = the common filter of
+    src/ntsynt_make_common_bf.cpp:136-160); nts_sketch2 looks candidates up in both.  Same bits, same minimizers, in the
+    sparse kernel, the dense kernel (small w, masked round) and with the partitioned insert forced."""
+    k = 24
+    wl = synth.Workload(G, 30_000_000, 1.0)
+    gens = [wl.materialize(cuda_ctx, g) for g in range(G)]
+    nbytes = device.BloomFilter.size_for(gens[0].total_bases, 0.025)
+    full, lvl = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
+    full.build_common(lvl, gens, k)
+    want_bits = full.to_numpy().copy()
+    for force in ("0", "1"):
+        os.environ["NTS_BF_PARTITION"] = force
+        try:
+            first, last = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
+            last.from_numpy(np.full(nbytes, 0x5A, dtype=np.uint8))               # stale contents must not matter
+            apart = first.build_common(last, gens, k, lazy=True)
+        finally:
+            del os.environ["NTS_BF_PARTITION"]
+        assert apart is True
+        assert np.array_equal(first.to_numpy() & last.to_numpy(), want_bits)
+        assert not np.array_equal(first.to_numpy(), want_bits)                   # the AND really was left out
+        masks = [(np.array([1000, 500000], dtype=np.uint64), np.array([200000, 900000], dtype=np.uint64))
+                 if c == 0 else (np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64)) for c in range(gens[0].n_contigs)]
+        for w, mk in ((1000, None), (250, None), (40, masks), (1000, masks)):
+            a = cuda_ctx.sketch(gens[-1], k, w, common=full, masks=mk).to_numpy()
+            b = cuda_ctx.sketch(gens[-1], k, w, common=first, common2=last, masks=mk).to_numpy()
+            assert len(a[0]) > 0
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+        first.close(); last.close()
+    one = cuda_ctx.bloom(nbytes)
+    assert one.build_common(None, gens[:1], k, lazy=True) is False              # a single genome: nothing to leave apart
