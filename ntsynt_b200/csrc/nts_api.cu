@@ -17,7 +17,8 @@ void part_scratch_release(nts_ctx* ctx);
 int part_insert(nts_ctx* ctx, cudaStream_t st, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, uint64_t m,
                 const uint32_t* prev, uint32_t* out, uint64_t alloc_bytes, int mode, bool* done);
 void part_check(nts_ctx* ctx, bool* overflowed, uint64_t* ovf_items);
-int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done);
+int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done,
+                const std::vector<UploadStage>* stages = nullptr);
 enum { APPLY_SET = 0, APPLY_AND = 1, APPLY_OR = 2 };      // nts_part.cuh
 
 static thread_local std::string g_err;
@@ -177,6 +178,7 @@ static int build_view(const nts_genome* g, uint32_t k, const uint64_t* mask_off,
     v->contig_v[g->n_contigs] = total;
     v->total_valid = total;
     v->n_seg = (uint32_t)seg_base.size();
+    v->h_seg_v = seg_v; v->h_seg_base = seg_base;
     if (seg_base.size() > 0xFFFFFFF0ull) { delete v; return fail(NTS_ERR_ARG, "too many islands"); }
     cudaError_t e1 = v->seg_v.alloc(seg_v.size());
     cudaError_t e2 = v->seg_base.alloc(seg_base.size() ? seg_base.size() : 1);
@@ -202,9 +204,9 @@ static int wait_ready(const nts_genome* g)
     return NTS_OK;
 }
 
-static int get_plain_view(const nts_genome* g, uint32_t k, const nts_view** out)
+static int get_plain_view(const nts_genome* g, uint32_t k, const nts_view** out, bool wait = true)
 {
-    { int rc = wait_ready(g); if (rc) return rc; }
+    if (wait) { int rc = wait_ready(g); if (rc) return rc; }
     nts_genome* gm = const_cast<nts_genome*>(g);
     auto it = gm->views.find(k);
     if (it == gm->views.end()) {
@@ -484,7 +486,23 @@ static int genome_upload_impl(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* 
         if (e == cudaSuccess) e = cudaMemsetAsync(g->packed.p + n_words, 0, 16, ctx->stream_copy);
         if (e == cudaSuccess && n_words) {
             ctx->h2d_bytes += n_words * 8;
-            e = cudaMemcpyAsync(g->packed.p, words, n_words * 8, cudaMemcpyHostToDevice, ctx->stream_copy);
+            // 1/8, 1/8, 1/4, 1/2 of the words: the first Bloom insert starts after an eighth of the copy
+            const uint64_t cuts[4] = {n_words / 8, n_words / 4, n_words / 2, n_words};
+            uint64_t from = 0;
+            for (int c = 0; c < 4 && e == cudaSuccess; ++c) {
+                const uint64_t to = c == 3 ? n_words : (cuts[c] & ~1ull);
+                if (to <= from) continue;
+                e = cudaMemcpyAsync(g->packed.p + from, words + from, (to - from) * 8, cudaMemcpyHostToDevice, ctx->stream_copy);
+                uint64_t stage_min = 1ull << 24;                 // stage events only where they can pay (>= 128 MB of words)
+                if (const char* es = getenv("NTS_UPLOAD_STAGE_MIN_WORDS")) stage_min = strtoull(es, nullptr, 10);   // test knob
+                if (c < 3 && n_words >= stage_min) {
+                    cudaEvent_t ev = nullptr;
+                    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                    if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->stream_copy);
+                    if (e == cudaSuccess) { g->chunk_ev.push_back(ev); g->chunk_end_word.push_back(to); }
+                }
+                from = to;
+            }
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(g->ready, ctx->stream_copy);
@@ -495,7 +513,12 @@ static int genome_upload_impl(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* 
             e = copy_h2d(ctx, g->packed.p, words, n_words * 8);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     }
-    if (e != cudaSuccess) { if (g->ready) cudaEventDestroy(g->ready); delete g; return fail(NTS_ERR_CUDA, std::string("genome upload: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) {
+        if (g->ready) cudaEventDestroy(g->ready);
+        for (cudaEvent_t ev : g->chunk_ev) cudaEventDestroy(ev);
+        delete g;
+        return fail(NTS_ERR_CUDA, std::string("genome upload: ") + cudaGetErrorString(e));
+    }
     *out = g;
     return NTS_OK;
 }
@@ -520,6 +543,7 @@ void nts_genome_destroy(nts_genome* g)
     if (!g) return;
     cudaSetDevice(g->ctx->device);
     if (g->ready) { cudaEventSynchronize(g->ready); cudaEventDestroy(g->ready); }   // the copy must not outlive the buffer
+    for (cudaEvent_t ev : g->chunk_ev) cudaEventDestroy(ev);
     for (auto& kv : g->views) delete kv.second;
     delete g;
 }
@@ -650,12 +674,39 @@ static int bf_insert_mode(nts_bf* bf, nts_bf* dst, const nts_genome* g, uint32_t
     const HashTables* tabs = nullptr;
     int rc = get_tables(ctx, k, &tabs);
     if (rc) return rc;
+    // a genome whose asynchronous upload nobody has waited for yet: the view needs only host data, and the binning pass
+    // of the partitioned insert can start on the head of the genome while the rest is still on its way
+    std::vector<UploadStage> stages;
+    const char* impl3 = getenv("NTS_BF_IMPL");
+    const bool staged = g->ready && !g->ready_waited && !g->chunk_ev.empty() && !(impl3 && impl3[0] == '3');
     const nts_view* v = nullptr;
-    rc = get_plain_view(g, k, &v);
+    rc = get_plain_view(g, k, &v, !staged);
     if (rc) return rc;
+    if (staged) {
+        bool monotone = true;
+        for (size_t i = 1; i < v->h_seg_base.size(); ++i) monotone = monotone && v->h_seg_base[i] > v->h_seg_base[i - 1];
+        if (monotone) {
+            for (size_t c = 0; c < g->chunk_ev.size(); ++c) {
+                // bases below `limit` are on the device after this chunk (the kernels pre-load a few words ahead: margin)
+                const uint64_t have = g->chunk_end_word[c] * 32;
+                const uint64_t limit = have > 256 ? have - 256 : 0;
+                uint64_t v_end = 0;
+                for (size_t s_ = 0; s_ < v->h_seg_base.size(); ++s_) {
+                    const uint64_t sb = v->h_seg_base[s_], n_s = v->h_seg_v[s_ + 1] - v->h_seg_v[s_];
+                    if (sb + k > limit) break;
+                    const uint64_t fit = std::min<uint64_t>(n_s, limit - k - sb + 1);
+                    v_end = v->h_seg_v[s_] + fit;
+                    if (fit < n_s) break;
+                }
+                stages.push_back({g->chunk_ev[c], v_end});
+            }
+            stages.push_back({g->ready, v->total_valid});
+        }
+    }
     const uint64_t n16 = bf->alloc_bytes / 16;
     bool done = false;
-    if (v->total_valid) {
+    if (v->total_valid && stages.empty()) {
+        if (staged && (rc = wait_ready(g))) return rc;
         rc = part_insert(ctx, ctx->stream, device_view(g, v), tabs, v->total_valid, bf->bytes * 8,
                          mode == APPLY_AND ? dst->words.p : bf->words.p, bf->words.p, bf->alloc_bytes, mode, &done);
         if (rc) return rc;
@@ -670,9 +721,10 @@ static int bf_insert_mode(nts_bf* bf, nts_bf* dst, const nts_genome* g, uint32_t
     if (prefilled) NTS_CUDA(cudaStreamWaitEvent(ctx->stream, prefilled, 0));
     else if (mode != APPLY_OR && (rc = bf_fill(bf, 0))) return rc;
     if (v->total_valid) {
-        if ((rc = pair_insert(ctx, bf, device_view(g, v), tabs, v->total_valid, &done))) return rc;
-        if (!done && (rc = bf_insert_direct(ctx, bf, g, v, tabs))) return rc;
-    }
+        if ((rc = pair_insert(ctx, bf, device_view(g, v), tabs, v->total_valid, &done, stages.empty() ? nullptr : &stages))) return rc;
+        if (!stages.empty()) const_cast<nts_genome*>(g)->ready_waited = done;     // the last stage waited for `ready`
+        if (!done && ((rc = wait_ready(g)) || (rc = bf_insert_direct(ctx, bf, g, v, tabs)))) return rc;
+    } else if (staged && (rc = wait_ready(g))) return rc;
     if (mode == APPLY_AND) {
         ProfScope prof(ctx, PROF_BF_COMBINE, (double)bf->alloc_bytes);
         bf_combine_kernel<<<grid_for(ctx, n16 / 4 + 1, 256, 16), 256, 0, ctx->stream>>>(

@@ -127,7 +127,8 @@ static int pair_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t total_valid
 }
 
 // pass 1 of a prepared slot on `st`: hash the genome, bin the bit indices by filter region
-static int pair_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid)
+static int pair_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid,
+                    const std::vector<UploadStage>* stages = nullptr)
 {
     PairScratch* sc = g_pair_scratch[{ctx, slot}];
     const uint64_t m = bf->bytes * 8;
@@ -137,8 +138,7 @@ static int pair_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const G
     bp.items = sc->items.p; bp.bucket_off = sc->bucket_off.p; bp.bucket_cap = sc->bucket_cap.p; bp.cursor = sc->cursor.p;
     bp.n_buckets = sc->P; bp.region_shift = sc->shift;
     const uint64_t mprime = 0xFFFFFFFFFFFFFFFFull / m;
-    const unsigned blocks = (unsigned)((total_valid + BIN_TILE - 1) / BIN_TILE);
-    ProfScope prof(ctx, PROF_BF_PART1, (double)total_valid, false, st);
+    const unsigned n_tiles = (unsigned)((total_valid + BIN_TILE - 1) / BIN_TILE);
     // NTS_BF_BIN=2: ranking without shared-memory atomics (nts_rank.cuh; same output up to the order inside a bucket)
     // where the item word has room for the high bucket digit.  Measured slower on B200 (34.8 against 21.2 ms per 3 Gbp
     // genome, profiles/r02c_ncu_rank_bin.md): its two counting-sort passes issue 285 instructions and ~65 shared-memory
@@ -146,18 +146,38 @@ static int pair_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const G
     const char* eb = getenv("NTS_BF_BIN");
     const bool old_rank = !(eb && eb[0] == '2');
     const size_t smem_r = RankSmem<BIN_THREADS, BIN_ITEMS>::bytes(sc->P);
-    if (!old_rank && sc->P <= 512 && sc->shift <= 28) {
+    const size_t smem = sizeof(HashTables) + (size_t)BIN_TILE * 12 + (size_t)sc->P * 12 + 4;
+    const int which = (!old_rank && sc->P <= 512 && sc->shift <= 28) ? 4 : (!old_rank && sc->P <= 1024 && sc->shift <= 27) ? 5 : 0;
+    if (which == 4)
         NTS_CUDA(cudaFuncSetAttribute(bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-        bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 4><<<blocks, BIN_THREADS, smem_r, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp);
-    } else if (!old_rank && sc->P <= 1024 && sc->shift <= 27) {
+    else if (which == 5)
         NTS_CUDA(cudaFuncSetAttribute(bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-        bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 5><<<blocks, BIN_THREADS, smem_r, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp);
-    } else {
-        const size_t smem = sizeof(HashTables) + (size_t)BIN_TILE * 12 + (size_t)sc->P * 12 + 4;
+    else
         NTS_CUDA(cudaFuncSetAttribute(bf_bin_kernel<BIN_THREADS, BIN_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bf_bin_kernel<BIN_THREADS, BIN_ITEMS><<<blocks, BIN_THREADS, smem, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp);
+    auto launch = [&](unsigned block0, unsigned blocks) {
+        if (which == 4)
+            bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 4><<<blocks, BIN_THREADS, smem_r, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp, block0);
+        else if (which == 5)
+            bf_rank_bin_kernel<BIN_THREADS, BIN_ITEMS, 5><<<blocks, BIN_THREADS, smem_r, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp, block0);
+        else
+            bf_bin_kernel<BIN_THREADS, BIN_ITEMS><<<blocks, BIN_THREADS, smem, st>>>(gv, tabs, bf->words.p, m, mprime, total_valid, bp, block0);
+        ctx->launches++;
+    };
+    ProfScope prof(ctx, PROF_BF_PART1, (double)total_valid, false, st);
+    if (!stages) {
+        launch(0, n_tiles);
+    } else {
+        // the genome is still being uploaded: after every stage's event, the tiles whose k-mers are all on the device
+        unsigned from = 0;
+        for (size_t i = 0; i < stages->size(); ++i) {
+            const UploadStage& sg = (*stages)[i];
+            const unsigned to = i + 1 == stages->size() ? n_tiles : (unsigned)std::min<uint64_t>(n_tiles, sg.v_end / BIN_TILE);
+            if (to <= from && i + 1 < stages->size()) continue;
+            NTS_CUDA(cudaStreamWaitEvent(st, sg.ev, 0));
+            if (to > from) launch(from, to - from);
+            from = std::max(from, to);
+        }
     }
-    ctx->launches++;
     NTS_CUDA(cudaGetLastError());
     return NTS_OK;
 }
@@ -175,7 +195,8 @@ static int pair_apply(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf)
 }
 
 // OR bits(genome) into bf with the pair; *done = false (nothing launched) when the pair does not apply
-int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done)
+int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid, bool* done,
+                const std::vector<UploadStage>* stages)
 {
     *done = false;
     bool ok = false;
@@ -183,7 +204,7 @@ int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables
     if (rc || !ok) return rc;
     {
         ProfScope prof(ctx, PROF_BF_INSERT, (double)total_valid);
-        if ((rc = pair_bin(ctx, 0, ctx->stream, bf, gv, tabs, total_valid)) || (rc = pair_apply(ctx, 0, ctx->stream, bf))) return rc;
+        if ((rc = pair_bin(ctx, 0, ctx->stream, bf, gv, tabs, total_valid, stages)) || (rc = pair_apply(ctx, 0, ctx->stream, bf))) return rc;
     }
     ctx->part_inserts++;
     *done = true;

@@ -37,7 +37,7 @@ struct BinParams {
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const HashTables* __restrict__ g_tabs,
                                                              uint32_t* __restrict__ bits, uint64_t m, uint64_t mprime,
-                                                             uint64_t total_valid, BinParams bp)
+                                                             uint64_t total_valid, BinParams bp, uint32_t block0)
 {
     constexpr int TILE = THREADS * ITEMS;
     extern __shared__ __align__(16) unsigned char smem_bin[];
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const 
     stage_tables_bin(s_tabs, g_tabs, g.k);
     for (uint32_t b = threadIdx.x; b <= bp.n_buckets; b += THREADS) s_cnt[b] = 0;
     __syncthreads();
-    const uint64_t tile0 = (uint64_t)blockIdx.x * TILE;
+    const uint64_t tile0 = (uint64_t)(blockIdx.x + block0) * TILE;     // block0: first tile of this launch (staged inserts)
     const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, total_valid - tile0);
     const uint64_t v0 = tile0 + (uint64_t)threadIdx.x * ITEMS;
     const uint32_t n_mine = v0 < total_valid ? (uint32_t)min((uint64_t)ITEMS, total_valid - v0) : 0;

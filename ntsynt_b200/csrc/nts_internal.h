@@ -118,6 +118,7 @@ struct nts_view {
     uint32_t n_seg = 0;
     std::vector<uint64_t> contig_v;   // [n_contigs + 1] valid-index range of each contig
     uint64_t total_valid = 0;
+    std::vector<uint64_t> h_seg_v, h_seg_base;   // host copies of the island table (a few thousand entries)
 };
 
 struct nts_genome {
@@ -132,7 +133,15 @@ struct nts_genome {
     std::map<uint32_t, nts_view*> views;     // unmasked views per k
     cudaEvent_t ready = nullptr;             // async upload: recorded after the H2D copy on ctx->stream_copy
     bool ready_waited = true;                // ctx->stream already ordered after `ready`
+    // the async copy goes in growing chunks, an event after each: words [0, chunk_end_word[i]) are on the device once
+    // chunk_ev[i] has fired (the last one is `ready`), so the first consumer can start on the head of the genome
+    std::vector<cudaEvent_t> chunk_ev;
+    std::vector<uint64_t> chunk_end_word;
 };
+
+// one stage of a Bloom insert that starts while the genome is still being uploaded: after `ev`, the k-mers with valid
+// index < v_end have all their bases on the device
+struct UploadStage { cudaEvent_t ev; uint64_t v_end; };
 
 struct nts_bf {
     nts_ctx* ctx = nullptr;

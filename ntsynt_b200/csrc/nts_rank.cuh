@@ -101,7 +101,7 @@ struct RankSmem {
 template <int THREADS, int ITEMS, int HB>
 __global__ void __launch_bounds__(THREADS, 2) bf_rank_bin_kernel(GenomeView g, const HashTables* __restrict__ g_tabs,
                                                                   uint32_t* __restrict__ bits, uint64_t m, uint64_t mprime,
-                                                                  uint64_t total_valid, BinParams bp)
+                                                                  uint64_t total_valid, BinParams bp, uint32_t block0)
 {
     static_assert(ITEMS == 16, "the pass-two rank word holds sixteen 4-bit ranks");
     using L = RankSmem<THREADS, ITEMS>;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(THREADS, 2) bf_rank_bin_kernel(GenomeView g, c
     for (int qd = 0; qd < 8; ++qd) CNT[qd * THREADS + tid] = 0;
     for (uint32_t b = tid; b < bp.n_buckets; b += THREADS) { s_start[b] = 0; s_dst[b] = 0; }
     __syncthreads();
-    const uint64_t tile0 = (uint64_t)blockIdx.x * TILE;
+    const uint64_t tile0 = (uint64_t)(blockIdx.x + block0) * TILE;     // block0: first tile of this launch (staged inserts)
     const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, total_valid - tile0);
     const uint64_t v0 = tile0 + (uint64_t)tid * ITEMS;
     const uint32_t n_mine = v0 < total_valid ? (uint32_t)min((uint64_t)ITEMS, total_valid - v0) : 0;

@@ -433,3 +433,47 @@ def test_common_filter_kept_as_a_pair_gives_the_same_sketches(cuda_ctx, G):
         first.close(); last.close()
     one = cuda_ctx.bloom(nbytes)
     assert one.build_common(None, gens[:1], k, lazy=True) is False              # a single genome: nothing to leave apart
+
+
+def test_insert_that_starts_during_the_upload_gives_the_same_bits(cuda_ctx):
+    """nts_genome_upload_async copies in growing chunks with an event after each; the first partitioned insert bins the
+    tiles whose bases have arrived while the rest is still on its way (staged launches of the binning kernel).  Same
+    bits as a synchronous upload, for SET, AND and the lazy pair, and the sketch that follows sees the whole genome."""
+    k, w = 24, 500
+    wl = synth.Workload(2, 48_000_000, 1.0)
+    sync_g = [wl.materialize(cuda_ctx, g) for g in range(2)]
+    nbytes = device.BloomFilter.size_for(sync_g[0].total_bases, 0.025)
+    want, lvl = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
+    want.build_common(lvl, sync_g, k)
+    want_bits = want.to_numpy().copy()
+    want_mx = [x.copy() for x in cuda_ctx.sketch(sync_g[1], k, w, common=want).to_numpy()]
+    pins = []
+    for g in sync_g:
+        pk = g.to_packed()
+        pin = device.PinnedU64(len(pk.words)); pin.array[:] = pk.words; pk.words = pin.array
+        pins.append((pk, pin))
+    os.environ["NTS_UPLOAD_STAGE_MIN_WORDS"] = "1"
+    os.environ["NTS_BF_PARTITION"] = "1"
+    try:
+        for rep in range(3):                                   # (timing-dependent paths: a few rounds)
+            n0 = cuda_ctx.part_inserts
+            fresh = [cuda_ctx.upload(pk, async_copy=True) for pk, _ in pins]
+            got, l2 = cuda_ctx.bloom(nbytes), cuda_ctx.bloom(nbytes)
+            if rep == 2:
+                assert got.build_common(l2, fresh, k, lazy=True) is True
+                bits = got.to_numpy() & l2.to_numpy()
+                mx = cuda_ctx.sketch(fresh[1], k, w, common=got, common2=l2).to_numpy()
+            else:
+                got.build_common(l2, fresh, k)
+                bits = got.to_numpy()
+                mx = cuda_ctx.sketch(fresh[1], k, w, common=got).to_numpy()
+            assert cuda_ctx.part_inserts - n0 == 2
+            assert np.array_equal(bits, want_bits)
+            for x, y in zip(mx, want_mx):
+                assert np.array_equal(x, y)
+            for f in fresh:
+                f.close()
+            got.close(); l2.close()
+    finally:
+        del os.environ["NTS_UPLOAD_STAGE_MIN_WORDS"]
+        del os.environ["NTS_BF_PARTITION"]
