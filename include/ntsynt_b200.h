@@ -55,6 +55,8 @@ int nts_timer_stop(nts_ctx* ctx, float* ms_out);
 uint64_t nts_launch_count(const nts_ctx* ctx);
 /* statistics: dense sub-tiles the sparse sketch kernel handed to the dense selector (unresolved windows) since creation */
 uint64_t nts_sketch_escalated(const nts_ctx* ctx);
+/* sketches that looked EVERY slot up because the filter passes < 10 % of the k-mers (statistics) */
+uint64_t nts_sketch_queried_all(const nts_ctx* ctx);
 /* statistics: Bloom inserts that took the partitioned path (csrc/nts_part.cuh), and the items those inserts applied
  * through their overflow lists (heavy-hitter k-mers), since creation */
 uint64_t nts_part_inserts(const nts_ctx* ctx);

@@ -49,6 +49,7 @@ _SIGS = {
     "nts_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "nts_launch_count": (C.c_uint64, [vp]),
     "nts_sketch_escalated": (C.c_uint64, [vp]),
+    "nts_sketch_queried_all": (C.c_uint64, [vp]),
     "nts_part_inserts": (C.c_uint64, [vp]),
     "nts_part_overflow_items": (C.c_uint64, [vp]),
     "nts_mem_info": (C.c_int, [vp, u64p, u64p]),

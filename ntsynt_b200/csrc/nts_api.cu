@@ -327,6 +327,7 @@ int nts_timer_stop(nts_ctx* ctx, float* ms_out)
 
 uint64_t nts_launch_count(const nts_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t nts_sketch_escalated(const nts_ctx* ctx) { return ctx ? ctx->sketch_escalated : 0; }
+uint64_t nts_sketch_queried_all(const nts_ctx* ctx) { return ctx ? ctx->sketch_qall : 0; }
 
 int nts_mem_info(nts_ctx* ctx, uint64_t* free_b, uint64_t* total_b)
 {
@@ -1019,9 +1020,20 @@ int nts_sketch2(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const n
     // sparse tiles (sketch_sparse_kernel): R dense tiles each, sized so that a thread stages ~3 candidates
     constexpr int SCAP = 16, CCAP = 3072;
     bool sparse = w >= 128 && lambda <= 192.0 && lambda / (double)w <= 0.25;
-    if (const char* env = getenv("NTS_SKETCH_DENSE")) { if (env[0] == '1') sparse = false; }
+    // a filter that passes < 10 % of the k-mers: no hash threshold keeps ~19 survivors per window, so every slot is
+    // looked up and only the survivors are listed (sketch_sparse_kernel<.., QALL>); 16 slots per thread = the capacity
+    // of a staging column, tiles of 8192 slots (so w <= 4096)
+    bool qall = !sparse && (common || repeat) && w >= 128 && w <= 4096 && pass < 0.1 && !getenv("NTS_SKETCH_LAMBDA");
+    if (const char* env = getenv("NTS_SKETCH_QALL")) { if (env[0] == '0') qall = false; }
+    if (const char* env = getenv("NTS_SKETCH_DENSE")) { if (env[0] == '1') sparse = qall = false; }
     uint32_t R = 1, NT_s = 0, C_s = 0, tau_hi = 0;
-    if (sparse) {
+    if (qall) {
+        sparse = true;
+        C_s = SCAP;
+        NT_s = THREADS * SCAP;
+        T = NT_s - w;
+        R = 1;
+    } else if (sparse) {
         const double density = lambda / (double)w;
         uint32_t c_target = (uint32_t)(3.1 / density);
         c_target = std::max<uint32_t>(4, std::min<uint32_t>(c_target, 120));
@@ -1088,10 +1100,33 @@ int nts_sketch2(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const n
     const size_t smem = sketch_smem_bytes(NT, THREADS);
     NTS_CUDA(cudaFuncSetAttribute(sketch_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t smem_s = sizeof(HashTables) + (size_t)SCAP * THREADS * 9 + (size_t)CCAP * 10;
-    if (sparse)
-        NTS_CUDA(cudaFuncSetAttribute(sketch_sparse_kernel<THREADS, SCAP, CCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (sparse && qall)
+        NTS_CUDA(cudaFuncSetAttribute(sketch_sparse_kernel<THREADS, SCAP, CCAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_s));
+    else if (sparse)
+        NTS_CUDA(cudaFuncSetAttribute(sketch_sparse_kernel<THREADS, SCAP, CCAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem_s));
 
+    // query-everything mode on a nearly empty filter: one bit per 32-byte sector (L2-resident) answers most lookups.
+    // Rebuilt per call (one streaming read of the filter, ~2.3 ms at 14.8 GB): nothing to keep coherent with later inserts.
+    DevBuf<uint32_t> d_summary;
+    uint32_t sum_shift = 10;         // one bit per 128-byte line of the filter (14.5 MB for 14.8 GB): measured best of 8 / 10 / 12
+    if (qall && common && pass < 0.01 && !(getenv("NTS_SKETCH_SUMMARY") && getenv("NTS_SKETCH_SUMMARY")[0] == '0')) {
+        if (const char* es = getenv("NTS_SKETCH_SUMMARY_SHIFT")) { const int x = atoi(es); if (x >= 8 && x <= 14) sum_shift = (uint32_t)x; }
+        const uint64_t unit_bytes = 1ull << (sum_shift - 3);
+        const uint64_t n_sectors = common->alloc_bytes / unit_bytes;      // whole units; what lies past them reads as "look"
+        if (n_sectors && d_summary.alloc((n_sectors + 31) / 32 + 1) == cudaSuccess) {
+            NTS_CUDA(cudaMemsetAsync(d_summary.p + (n_sectors + 31) / 32, 0xFF, 4, ctx->stream));
+            ProfScope prof(ctx, PROF_SKETCH, 0.0);
+            bf_summary_kernel<<<grid_for(ctx, n_sectors, 256, 8), 256, 0, ctx->stream>>>(
+                reinterpret_cast<const uint4*>(common->words.p), n_sectors, (uint32_t)(unit_bytes / 16), d_summary.p);
+            ctx->launches++;
+            NTS_CUDA(cudaGetLastError());
+        } else {
+            cudaGetLastError();
+            d_summary.release();
+        }
+    }
     // expected density of minimizers is 2/(w+1) per window; start with 2.5x that
     uint64_t n_win_total = 0;
     for (uint32_t c = 0; c < g->n_contigs; ++c) {
@@ -1119,8 +1154,13 @@ int nts_sketch2(nts_ctx* ctx, const nts_genome* g, const nts_bf* common, const n
             const uint32_t* rw = repeat ? repeat->words.p : nullptr;
             if (sparse) {
                 unsigned int* esc_count = reinterpret_cast<unsigned int*>(d_total.p + 1);
-                sketch_sparse_kernel<THREADS, SCAP, CCAP><<<n_tiles, THREADS, smem_s, ctx->stream>>>(
-                    gv, tabs, cw, cw2, rw, m, mp, rm, rmp, d_tiles.p, w, NT_s, C_s, T, tau_hi, so, d_esc.p, esc_count);
+                if (qall && attempt == 0) ctx->sketch_qall++;
+                if (qall)
+                    sketch_sparse_kernel<THREADS, SCAP, CCAP, true><<<n_tiles, THREADS, smem_s, ctx->stream>>>(
+                        gv, tabs, cw, d_summary.p, cw2, rw, m, mp, rm, rmp, d_tiles.p, w, NT_s, C_s, T, tau_hi, so, d_esc.p, esc_count, sum_shift);
+                else
+                    sketch_sparse_kernel<THREADS, SCAP, CCAP, false><<<n_tiles, THREADS, smem_s, ctx->stream>>>(
+                        gv, tabs, cw, nullptr, cw2, rw, m, mp, rm, rmp, d_tiles.p, w, NT_s, C_s, T, tau_hi, so, d_esc.p, esc_count, 8u);
                 ctx->launches++;
                 NTS_CUDA(cudaGetLastError());
                 unsigned int n_esc = 0;

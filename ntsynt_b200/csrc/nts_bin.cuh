@@ -50,11 +50,14 @@ __global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const 
     uint32_t* s_fit = s_dst + bp.n_buckets;                      // [P] how many items of the run fit the bucket
     __shared__ uint16_t s_wb[TILE / 32];                         // bucket of the item at sorted position 32 * w
     __shared__ uint32_t s_wsum[THREADS / 32];
+    __shared__ uint32_t s_isl[2];                                  // islands of the tile's first and last k-mer
+    const uint64_t tile0 = (uint64_t)(blockIdx.x + block0) * TILE;     // block0: first tile of this launch (staged inserts)
+    const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, total_valid - tile0);
+    if (threadIdx.x == 0) s_isl[0] = find_island(g, tile0);
+    if (threadIdx.x == 32) s_isl[1] = find_island(g, tile0 + n_tile - 1);
     stage_tables_bin(s_tabs, g_tabs, g.k);
     for (uint32_t b = threadIdx.x; b <= bp.n_buckets; b += THREADS) s_cnt[b] = 0;
     __syncthreads();
-    const uint64_t tile0 = (uint64_t)(blockIdx.x + block0) * TILE;     // block0: first tile of this launch (staged inserts)
-    const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, total_valid - tile0);
     const uint64_t v0 = tile0 + (uint64_t)threadIdx.x * ITEMS;
     const uint32_t n_mine = v0 < total_valid ? (uint32_t)min((uint64_t)ITEMS, total_valid - v0) : 0;
     const uint32_t low_mask = bp.region_shift >= 32 ? 0xFFFFFFFFu : ((1u << bp.region_shift) - 1);
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const 
             const uint32_t slot = j * THREADS + threadIdx.x;
             s_low[slot] = (uint32_t)idx & low_mask;
             s_br[slot] = (b << 16) | atomicAdd(&s_cnt[b], 1u);
-        });
+        }, s_isl[0], s_isl[1]);
     __syncthreads();
     // reserve the runs (one global atomic per non-empty bucket)
     for (uint32_t b = threadIdx.x; b < bp.n_buckets; b += THREADS) {

@@ -87,6 +87,17 @@ __device__ __forceinline__ uint32_t find_island(const GenomeView& g, uint64_t v)
     return lo;
 }
 
+// the same, searched only among islands [lo, hi] (lo <= answer <= hi): a tile's threads share the two ends of the tile
+__device__ __forceinline__ uint32_t find_island_in(const GenomeView& g, uint64_t v, uint32_t lo, uint32_t hi)
+{
+    ++hi;                           // invariant: seg_v[lo] <= v < seg_v[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&g.seg_v[mid]) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 __device__ __forceinline__ unsigned base_at(const uint64_t* __restrict__ packed, uint64_t b)
 {
     return (unsigned)((__ldg(&packed[b >> 5]) >> ((b & 31) * 2)) & 3ull);
@@ -116,14 +127,17 @@ __device__ __forceinline__ void sror32(uint32_t& lo, uint32_t& hi)
 // each, one funnel shift per group), merged into two words whose nibbles are the (in,out) table indices
 // of the even / odd steps, and 16 roll steps are unrolled with static shifts: per k-mer one LDS.128,
 // two 5-instruction split rotates, four XORs and a 64-bit add.
+// isl_lo / isl_hi: islands known to bracket the run's first k-mer (a tile looks its two ends up once; most tiles lie
+// inside one island, and their threads then start without any search).
 template <typename F>
-__device__ __forceinline__ void hash_run(const GenomeView& g, const HashTables* tabs, uint64_t v, uint32_t count, F&& f)
+__device__ __forceinline__ void hash_run(const GenomeView& g, const HashTables* tabs, uint64_t v, uint32_t count, F&& f,
+                                         uint32_t isl_lo = 0, uint32_t isl_hi = 0xFFFFFFFFu)
 {
     if (count == 0) return;
     const uint32_t k = g.k;
     const uint32_t* __restrict__ p32 = reinterpret_cast<const uint32_t*>(g.packed);
     const char* roll = reinterpret_cast<const char*>(tabs->roll);
-    uint32_t s = find_island(g, v);
+    uint32_t s = isl_hi == 0xFFFFFFFFu ? find_island(g, v) : find_island_in(g, v, isl_lo, isl_hi);
     uint32_t j = 0;
     while (j < count) {
         const uint64_t sv0 = __ldg(&g.seg_v[s]);

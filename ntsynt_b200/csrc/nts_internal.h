@@ -76,6 +76,7 @@ struct nts_ctx {
     cudaEvent_t ev_side = nullptr;   // orders the side stream against the main one (nts_bf_build_common)
     uint64_t launches = 0;
     uint64_t sketch_escalated = 0;   // dense sub-tiles the sparse sketch kernel handed to the dense one (statistics)
+    uint64_t sketch_qall = 0;        // sketches that looked every slot up (low pass rate; statistics)
     uint64_t part_inserts = 0;       // Bloom inserts that took the partitioned path (statistics / tests)
     uint64_t part_overflow_items = 0;   // items those inserts applied through the overflow list
     int sm_count = 148;

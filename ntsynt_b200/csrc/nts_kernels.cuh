@@ -47,6 +47,29 @@ __global__ void bf_combine_kernel(uint4* __restrict__ dst, const uint4* __restri
     }
 }
 
+// one bit per unit of 2^shift filter bits (a 32-byte sector or a few of them): is any bit of the unit set?  For a nearly empty filter (the AND of several
+// diverged genomes) the summary is 1/256 of the filter -- 58 MB for 14.8 GB, resident in L2 -- and answers most lookups
+// of the query-everything sketch without touching HBM (sketch_sparse_kernel<.., QALL>).
+__global__ void bf_summary_kernel(const uint4* __restrict__ words, uint64_t n_units, uint32_t per_unit /* 16-byte words per unit */,
+                                  uint32_t* __restrict__ summary)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_units + 31) & ~31ull;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += stride) {
+        bool any = true;                                    // past the last whole unit: "look it up"
+        if (s < n_units) {
+            uint32_t acc = 0;
+            for (uint32_t i = 0; i < per_unit; i += 2) {
+                const uint4 a = __ldg(&words[s * per_unit + i]), b = __ldg(&words[s * per_unit + i + 1]);
+                acc |= a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w;
+            }
+            any = acc != 0;
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, any);
+        if ((threadIdx.x & 31) == 0) summary[s >> 5] = mask;
+    }
+}
+
 __global__ void bf_popcount_kernel(const uint4* __restrict__ p, uint64_t n16, unsigned long long* __restrict__ out)
 {
     unsigned long long c = 0;
@@ -532,13 +555,19 @@ __global__ void sketch_sample_kernel(GenomeView g, const HashTables* __restrict_
 // Exactness needs every window of the tile (and the one before its first) to hold a survivor: gaps between
 // consecutive survivors are checked, and a tile with an unresolved window (or a staging overflow) hands its
 // `n_sub` dense sub-tiles to sketch_kernel through the escalation list instead of emitting anything.
-template <int THREADS, int SCAP, int CCAP>
+// QALL (filters that pass < 10 % of the k-mers, where a hash threshold would have to let nearly everything through):
+// EVERY slot is looked up -- a thread hashes its 16 slots into its staging column, then issues the sector loads of
+// eight slots at a time -- and only the survivors are staged, so the candidate list is the complete list of survivors:
+// a window without one emits nothing (its slots are all UINT64_MAX sentinels), no window has to be handed to the dense
+// selector, and the window pass runs over a list ~1/pass-rate shorter than the slots.
+template <int THREADS, int SCAP, int CCAP, bool QALL>
 __global__ void __launch_bounds__(THREADS, 2)
 sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const uint32_t* __restrict__ common,
+                     const uint32_t* __restrict__ summary /* QALL: one bit per 2^sum_shift bits of `common`, nullable */,
                      const uint32_t* __restrict__ common2, const uint32_t* __restrict__ repeat, uint64_t m, uint64_t mprime, uint64_t rm, uint64_t rmprime,
               const TileDesc* __restrict__ tiles,
                      uint32_t w, uint32_t NT, uint32_t C, uint32_t T_dense, uint32_t tau_hi, SketchOut out,
-                     TileDesc* __restrict__ esc, unsigned int* __restrict__ esc_count)
+                     TileDesc* __restrict__ esc, unsigned int* __restrict__ esc_count, uint32_t sum_shift)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HashTables* s_tabs = reinterpret_cast<HashTables*>(smem_raw);
@@ -550,13 +579,16 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
     __shared__ uint32_t s_bcast[2];
 
     const TileDesc td = tiles[blockIdx.x];
-    stage_tables(s_tabs, g_tabs, g.k);
-    __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t vbase = td.vfirst - 1;
     const uint32_t i_lo = td.has_prev ? 0u : 1u;
     const uint64_t avail = td.vend - td.vfirst + 1;
     const uint32_t n_end = (uint32_t)min((uint64_t)NT, avail);
+    __shared__ uint32_t s_isl[2];                          // islands of the tile's first and last slot
+    if (tid == 0) s_isl[0] = find_island(g, vbase + i_lo);
+    if (tid == 32) s_isl[1] = find_island(g, vbase + max(n_end, i_lo + 1u) - 1);
+    stage_tables(s_tabs, g_tabs, g.k);
+    __syncthreads();
 
     // CTA-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = sum
     auto cta_scan = [&](uint32_t val, uint32_t* total) -> uint32_t {
@@ -583,15 +615,62 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
         const uint32_t a = max(c0, i_lo), b = min(c0 + C, n_end);
         if (a < b) {
             const uint32_t j0 = a - c0;
-            hash_run(g, s_tabs, vbase + a, b - a, [&](uint32_t j, uint64_t h0, uint64_t) {
-                if ((uint32_t)(h0 >> 32) < tau_hi) {
-                    if (n_st < SCAP) {
-                        s_skey[n_st * THREADS + tid] = h0;
-                        s_sj[n_st * THREADS + tid] = (uint8_t)(j0 + j);
+            if constexpr (QALL) {
+                // C <= SCAP: every slot's hash fits the thread's column
+                hash_run(g, s_tabs, vbase + a, b - a, [&](uint32_t j, uint64_t h0, uint64_t) { s_skey[j * THREADS + tid] = h0; },
+                         s_isl[0], s_isl[1]);
+                const uint32_t cnt = b - a;
+#pragma unroll
+                for (int half = 0; half < (SCAP + 7) / 8; ++half) {
+                    uint32_t ok[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t jj = half * 8 + u;
+                        ok[u] = 0;
+                        if (jj < cnt) {
+                            const uint64_t h = s_skey[jj * THREADS + tid];
+                            const uint64_t idx = fast_mod(h, m, mprime);
+                            // eight independent loads from the selective filter are in flight together; the second part of
+                            // the common filter and the repeat filter are looked up only for the few that passed
+                            if (summary) {              // L2-resident: does the k-mer's sector hold any bit at all?
+                                const uint64_t sec = idx >> sum_shift;
+                                ok[u] = (__ldg(&summary[sec >> 5]) >> (sec & 31)) & 1u;
+                            } else {
+                                ok[u] = common ? (__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u : 1u;
+                            }
+                        }
                     }
-                    ++n_st;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t jj = half * 8 + u;
+                        if (jj < cnt && (ok[u] & 1u)) {                 // (n_st <= jj: the write never passes the read)
+                            const uint64_t h = s_skey[jj * THREADS + tid];
+                            if (summary || common2) {
+                                const uint64_t idx = fast_mod(h, m, mprime);
+                                if (summary && !((__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u)) continue;
+                                if (common2 && !((__ldg(&common2[idx >> 5]) >> (idx & 31)) & 1u)) continue;
+                            }
+                            if (repeat) {
+                                const uint64_t ridx = fast_mod(h, rm, rmprime);
+                                if ((__ldg(&repeat[ridx >> 5]) >> (ridx & 31)) & 1u) continue;
+                            }
+                            s_skey[n_st * THREADS + tid] = h;
+                            s_sj[n_st * THREADS + tid] = (uint8_t)(j0 + jj);
+                            ++n_st;
+                        }
+                    }
                 }
-            });
+            } else {
+                hash_run(g, s_tabs, vbase + a, b - a, [&](uint32_t j, uint64_t h0, uint64_t) {
+                    if ((uint32_t)(h0 >> 32) < tau_hi) {
+                        if (n_st < SCAP) {
+                            s_skey[n_st * THREADS + tid] = h0;
+                            s_sj[n_st * THREADS + tid] = (uint8_t)(j0 + j);
+                        }
+                        ++n_st;
+                    }
+                }, s_isl[0], s_isl[1]);
+            }
         }
     }
     int bad = n_st > SCAP;                     // staging overflow: escalate
@@ -607,7 +686,7 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
     __syncthreads();
 
     // ---- phase B: Bloom query of the candidates (kernel iii-c)
-    if ((common != nullptr || repeat != nullptr) && ncand) {
+    if (!QALL && (common != nullptr || repeat != nullptr) && ncand) {
         constexpr int PER = (CCAP + THREADS - 1) / THREADS;
         uint32_t cw[PER], rw[PER];
 #pragma unroll
@@ -643,9 +722,9 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
         int j = (int)i - 1;
         while (j >= 0 && c_key[j] == KEY_MAX) --j;
         const int prev_p = j >= 0 ? (int)c_slot[j] : e_lo - (int)w;
-        if ((int)c_slot[i] - prev_p > (int)w) bad = 1;
+        if (!QALL && (int)c_slot[i] - prev_p > (int)w) bad = 1;      // (QALL: the list is complete, empty windows are real)
     }
-    if (tid == 0 && !bad) {
+    if (!QALL && tid == 0 && !bad) {
         int j = (int)ncand - 1;
         while (j >= 0 && c_key[j] == KEY_MAX) --j;
         const int last_p = j >= 0 ? (int)c_slot[j] : e_lo - (int)w;

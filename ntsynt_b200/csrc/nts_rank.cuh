@@ -123,6 +123,13 @@ __global__ void __launch_bounds__(THREADS, 2) bf_rank_bin_kernel(GenomeView g, c
     uint32_t* s_dst = s_start + bp.n_buckets;                    // first the end of the run, then its global item index
     uint32_t* s_fit = s_dst + bp.n_buckets;
     const int tid = threadIdx.x;
+    __shared__ uint32_t s_isl[2];                                  // islands of the tile's first and last k-mer
+    {
+        const uint64_t t0 = (uint64_t)(blockIdx.x + block0) * TILE;
+        const uint64_t nt = min((uint64_t)TILE, total_valid - t0);
+        if (tid == 0) s_isl[0] = find_island(g, t0);
+        if (tid == 32) s_isl[1] = find_island(g, t0 + nt - 1);
+    }
     stage_tables_bin(s_tabs, g_tabs, g.k);
 #pragma unroll
     for (int qd = 0; qd < 8; ++qd) CNT[qd * THREADS + tid] = 0;
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 2) bf_rank_bin_kernel(GenomeView g, c
             const uint32_t slot = j * THREADS + tid;
             W0[slot] = ((uint32_t)idx & rmask) | ((b >> 5) << LOW_BITS);
             S0[slot] = (uint16_t)(d | (((w >> sh) & 0xFFu) << 5));
-        });
+        }, s_isl[0], s_isl[1]);
     __syncthreads();
     rank_scan<THREADS, 32>(CNT, SEG, s_baseA, s_wtot);
     // ---- scatter one: stable by b_lo

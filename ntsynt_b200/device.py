@@ -58,6 +58,11 @@ class Context:
         return int(lib.nts_sketch_escalated(self._h))
 
     @property
+    def sketch_queried_all(self):
+        "sketches that looked every slot up (filters passing < 10 % of the k-mers; statistics)"
+        return int(lib.nts_sketch_queried_all(self._h))
+
+    @property
     def part_inserts(self):
         "Bloom inserts that took the partitioned path so far (statistics)"
         return int(lib.nts_part_inserts(self._h))

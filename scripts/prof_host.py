@@ -1,5 +1,5 @@
 """cProfile of the host side of one full-size hot-path step (run on the GPU box):
-    python scripts/prof_host.py [genome_mbp] > gpurun_out/prof_host.txt"""
+    python scripts/prof_host.py [genome_mbp] [genomes] [divergence] > gpurun_out/prof_host.txt"""
 import cProfile
 import io
 import os
@@ -13,9 +13,11 @@ from ntsynt_b200 import device, pipeline, synth  # noqa: E402
 from ntsynt_b200.synteny import SyntenyEngine  # noqa: E402
 
 mbp = float(sys.argv[1]) if len(sys.argv) > 1 else 3000.0
-K, W, G, d = 24, 1000, (int(sys.argv[2]) if len(sys.argv) > 2 else 2), 1.0
+K, W, G = 24, 1000, (int(sys.argv[2]) if len(sys.argv) > 2 else 2)
+d = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 ps = bench.presets(d)
 ctx = device.Context(0)
+ctx.prof_enable(True)
 wl = synth.Workload(G, int(mbp * 1e6), d, seed=20260117)
 file_names = [wl.file_name(g) for g in range(G)]
 names = [pipeline.tsv_name(f, K, W) for f in file_names]
@@ -65,7 +67,10 @@ for n, o in _origs.items():
     setattr(_np, n, o)
 for key, (cnt, tot, size) in sorted(_acc.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{key[0]:14s} {key[1]}:{key[2]:<5d} calls {cnt:5d}  {tot * 1e3:8.2f} ms  max operand {size}")
-print({k: (round(v * 1e3, 1) if k.startswith("t_") else v) for k, v in eng.stats.items()})
+print({k: (round(v * 1e3, 1) if k.startswith("t_") else v) for k, v in eng.stats.items() if k != "dev_runs"})
+ctx.prof_reset()
+step()
+print("kernel ms per step:", {k: round(v[0], 2) for k, v in ctx.prof().items() if v[0] > 0})
 pr = cProfile.Profile()
 pr.enable()
 eng = step()

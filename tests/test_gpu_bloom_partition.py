@@ -46,13 +46,14 @@ def small(cuda_ctx):
     gens = [wl.materialize(cuda_ctx, g) for g in range(3)]
     nbytes = device.BloomFilter.size_for(gens[0].total_bases, 0.025)
     per = []
+    n0 = cuda_ctx.part_inserts
     with env(NTS_BF_PARTITION=0):
         for g in gens:
             bf = cuda_ctx.bloom(nbytes)
             bf.insert_genome(g, K)
             per.append(bf.to_numpy().copy())
             bf.close()
-    assert cuda_ctx.part_inserts == 0
+    assert cuda_ctx.part_inserts == n0
     want0 = so.genome_bits(_records(gens[0]), K, nbytes)
     assert np.array_equal(per[0], want0)                      # direct kernel == C oracle
     return gens, nbytes, per

@@ -284,7 +284,7 @@ def test_sparse_and_dense_sketch_kernels_agree(cuda_ctx, w):
     thin[len(thin) // 16:] = 0                       # 15/16 of the hash space never passes: many windows without a survivor
     thin_bf = cuda_ctx.bloom(nbytes).from_numpy(thin)
     for bf, must_escalate in ((a, False), (thin_bf, True), (thin_bf, False), (None, False)):
-        e0 = cuda_ctx.sketch_escalated
+        e0, q0 = cuda_ctx.sketch_escalated, cuda_ctx.sketch_queried_all
         if must_escalate:                            # pin the candidate density: the sampled pass rate would raise it
             os.environ["NTS_SKETCH_LAMBDA"] = "24"   # (or choose the dense kernel outright)
         try:
@@ -302,6 +302,9 @@ def test_sparse_and_dense_sketch_kernels_agree(cuda_ctx, w):
             assert np.array_equal(x, y)
         if must_escalate:
             assert esc > 0
+        elif bf is thin_bf:
+            # < 10 % of the k-mers pass: every slot looked up, survivors listed, nothing handed to the dense selector
+            assert cuda_ctx.sketch_queried_all - q0 == 1 and esc == 0
         elif bf is a and w >= 500:
             n_tiles_dense = gens[1].total_bases / (8960 - w)
             assert esc < 0.02 * n_tiles_dense        # the sparse kernel did the work
