@@ -16,6 +16,12 @@ import time
 import numpy as np
 
 NTSYNT_VERSION = "ntSynt v1.0.4 (ntsynt_b200)"
+MAX_W = 9216      # the window selector keeps a window in shared memory (limits)
+
+
+def check_w(w, what="-w"):
+    if w > MAX_W:
+        raise SystemExit(f"ntsynt_b200: {what} {w} is above the largest window this build supports ({MAX_W})")
 
 
 # ------------------------------------------------------------------------------------------------ ntSynt
@@ -66,6 +72,7 @@ def main_ntsynt(argv=None):
     for w in args.w_rounds:
         if w > args.w:
             ap.error("All values specified for --w_rounds must be smaller than -w")
+    check_w(args.w)
     if not args.fastas and not args.fastas_list:
         ap.error("Please supply the input genome fasta files as positional arguments, "
                  "or specify a file listing the files (one fasta per line) with --fastas_list")
@@ -171,6 +178,7 @@ def parse_indexlr_args(argv):
         i += 1
     if opt["k"] is None or opt["w"] is None or opt["fa"] is None:
         raise SystemExit("indexlr: -k, -w and a FASTA file are required")
+    check_w(opt["w"])
     return opt
 
 
@@ -216,6 +224,7 @@ def main_ntsynt_run(argv=None):
     args = ap.parse_args(argv)
     if args.n not in (0, len(args.FILES)):
         raise SystemExit("ntsynt_b200: only -n = number of assemblies (the pipeline's setting) is supported")
+    check_w(max([args.w] + list(args.w_rounds)), "-w / --w-rounds")
     if args.filter and not args.repeat:                            # bin/ntsynt_synteny.py:601-602
         raise ValueError("If --filter is specified, must supply repeat Bloom filter with --repeat")
     from . import device, fasta, io, pipeline
