@@ -484,6 +484,10 @@ static int genome_upload_impl(nts_ctx* ctx, uint32_t n_contigs, const uint64_t* 
     if (async_copy) {
         // copy on the context's H2D stream; consumers order themselves after `ready` (wait_ready)
         if (!ctx->stream_copy) e = cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
+        // the block may have been recycled from something the main stream is still using (the pool frees without
+        // tracking streams): the copy starts after the work queued on the main stream so far
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_side, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_side, 0);
         if (e == cudaSuccess) e = cudaMemsetAsync(g->packed.p + n_words, 0, 16, ctx->stream_copy);
         if (e == cudaSuccess && n_words) {
             ctx->h2d_bytes += n_words * 8;

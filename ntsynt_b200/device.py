@@ -28,6 +28,7 @@ class Context:
 
     def close(self):
         if self._h:
+            PinnedPool.release(id(self))
             lib.nts_ctx_destroy(self._h)
             self._h = None
 
@@ -321,24 +322,37 @@ class MinimizerTable:
 
 
 class PinnedPool:
-    """page-locked host arrays reused across calls (D2H into pageable memory runs at a few GB/s; the join
-    hands ~400 MB of vertex columns to the host every step)"""
+    """page-locked host arrays reused across calls (D2H into pageable memory runs at a few GB/s).  One set of buffers
+    per Context (two GPUs or two threads never share one); a buffer that has to grow is retired, not freed, so numpy
+    views handed out earlier stay valid memory until the context is closed.  A view's CONTENTS are valid until the next
+    MinimizerGraph of the same context downloads into the same buffer (the engine of a finished run keeps no live
+    dependency on them: its results are the output texts)."""
     _bufs = {}
+    _retired = {}
 
     @classmethod
-    def get(cls, key, shape, dtype):
+    def get(cls, key, shape, dtype, owner=None):
         dtype = np.dtype(dtype)
         n = int(np.prod(shape)) * dtype.itemsize
+        key = (owner, key)
         ent = cls._bufs.get(key)
         if ent is None or ent[1] < n:
             if ent is not None:
-                lib.nts_host_free(ent[0])
+                cls._retired.setdefault(owner, []).append(ent[0])
             p = C.c_void_p()
             check(lib.nts_host_alloc(max(n, 1) + 64, C.byref(p)))
             ent = (p, n + 64)
             cls._bufs[key] = ent
         raw = (C.c_uint8 * max(n, 1)).from_address(ent[0].value)
         return np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    @classmethod
+    def release(cls, owner):
+        "free every buffer of a context (Context.close)"
+        for key in [k for k in cls._bufs if k[0] == owner]:
+            lib.nts_host_free(cls._bufs.pop(key)[0])
+        for p in cls._retired.pop(owner, []):
+            lib.nts_host_free(p)
 
 
 class MinimizerGraph:
@@ -361,12 +375,12 @@ class MinimizerGraph:
         "h1[V] u64, pos[G,V] u32, contig[G,V] u32, rank[G,V] u32, link[V] u8, degree[V] u8"
         V, G = len(self), self.n_asm
         n = max(V, 1)
-        h1 = PinnedPool.get("h1", (n,), np.uint64)
-        pos = PinnedPool.get("pos", (G, n), np.uint32)
-        ctg = PinnedPool.get("ctg", (G, n), np.uint32)
-        rank = PinnedPool.get("rank", (G, n), np.uint32)
-        link = PinnedPool.get("link", (n,), np.uint8)
-        deg = PinnedPool.get("deg", (n,), np.uint8)
+        h1 = PinnedPool.get("h1", (n,), np.uint64, owner=id(self.ctx))
+        pos = PinnedPool.get("pos", (G, n), np.uint32, owner=id(self.ctx))
+        ctg = PinnedPool.get("ctg", (G, n), np.uint32, owner=id(self.ctx))
+        rank = PinnedPool.get("rank", (G, n), np.uint32, owner=id(self.ctx))
+        link = PinnedPool.get("link", (n,), np.uint8, owner=id(self.ctx))
+        deg = PinnedPool.get("deg", (n,), np.uint8, owner=id(self.ctx))
         if V:
             check(lib.nts_graph_download_vertices(self._h, ptr(h1, C.c_uint64), ptr(pos, C.c_uint32),
                                                   ptr(ctg, C.c_uint32), ptr(rank, C.c_uint32), ptr(link, C.c_uint8),
@@ -377,10 +391,10 @@ class MinimizerGraph:
         "inv[G,V] u32, incmask[V], decmask[V], spread[V] u32: per-pair arrays of (i, i+1)"
         V, G = len(self), self.n_asm
         n = max(V, 1)
-        inv = PinnedPool.get("inv", (G, n), np.uint32)
-        inc = PinnedPool.get("inc", (n,), np.uint32)
-        dec = PinnedPool.get("dec", (n,), np.uint32)
-        spread = PinnedPool.get("spread", (n,), np.uint32)
+        inv = PinnedPool.get("inv", (G, n), np.uint32, owner=id(self.ctx))
+        inc = PinnedPool.get("inc", (n,), np.uint32, owner=id(self.ctx))
+        dec = PinnedPool.get("dec", (n,), np.uint32, owner=id(self.ctx))
+        spread = PinnedPool.get("spread", (n,), np.uint32, owner=id(self.ctx))
         if V:
             check(lib.nts_graph_download_links(self._h, ptr(inv, C.c_uint32), ptr(inc, C.c_uint32), ptr(dec, C.c_uint32),
                                                ptr(spread, C.c_uint32)))
@@ -397,8 +411,8 @@ class MinimizerGraph:
     def cums(self):
         "CI, CD int32 [G, V+1]: device prefix sums of the per-pair direction bits"
         V, G = len(self), self.n_asm
-        ci = PinnedPool.get("ci", (G, V + 1), np.uint32)
-        cd = PinnedPool.get("cd", (G, V + 1), np.uint32)
+        ci = PinnedPool.get("ci", (G, V + 1), np.uint32, owner=id(self.ctx))
+        cd = PinnedPool.get("cd", (G, V + 1), np.uint32, owner=id(self.ctx))
         ci[:, 0] = 0; cd[:, 0] = 0
         if V:
             check(lib.nts_graph_download_cums(self._h, ptr(ci, C.c_uint32), ptr(cd, C.c_uint32)))
@@ -409,11 +423,11 @@ class MinimizerGraph:
         columns in their final dtypes, written by the device into pinned buffers with room for later vertices"""
         V, G = len(self), self.n_asm
         cap = max(int(cap), V, 1)
-        H = PinnedPool.get("H", (cap,), np.uint64)
-        POS = PinnedPool.get("POS64", (G, cap), np.int64)
-        CTG = PinnedPool.get("CTG32", (G, cap), np.int32)
-        nbr = PinnedPool.get("nbr", (cap, 2), np.int32)
-        conn = PinnedPool.get("conn", (cap,), np.uint8)
+        H = PinnedPool.get("H", (cap,), np.uint64, owner=id(self.ctx))
+        POS = PinnedPool.get("POS64", (G, cap), np.int64, owner=id(self.ctx))
+        CTG = PinnedPool.get("CTG32", (G, cap), np.int32, owner=id(self.ctx))
+        nbr = PinnedPool.get("nbr", (cap, 2), np.int32, owner=id(self.ctx))
+        conn = PinnedPool.get("conn", (cap,), np.uint8, owner=id(self.ctx))
         if V:
             check(lib.nts_graph_download_host_arrays(self._h, cap, ptr(H, C.c_uint64), ptr(POS, C.c_longlong),
                                                      ptr(CTG, C.c_int32), ptr(nbr, C.c_int32), ptr(conn, C.c_uint8)))
@@ -438,8 +452,8 @@ class MinimizerGraph:
         "RANK[G,V], INV[G,V] u32 (round-0 neighbourhoods of the simplification candidates)"
         V, G = len(self), self.n_asm
         n = max(V, 1)
-        rank = PinnedPool.get("rank", (G, n), np.uint32)
-        inv = PinnedPool.get("inv", (G, n), np.uint32)
+        rank = PinnedPool.get("rank", (G, n), np.uint32, owner=id(self.ctx))
+        inv = PinnedPool.get("inv", (G, n), np.uint32, owner=id(self.ctx))
         if V:
             check(lib.nts_graph_download_vertices(self._h, None, None, None, ptr(rank, C.c_uint32), None, None))
             check(lib.nts_graph_download_links(self._h, ptr(inv, C.c_uint32), None, None, None))
@@ -449,9 +463,9 @@ class MinimizerGraph:
         "incmask, decmask, spread [V] u32 of the pairs (i, i+1) (fetched only when a refinement round overwrites positions)"
         V = len(self)
         n = max(V, 1)
-        inc = PinnedPool.get("inc", (n,), np.uint32)
-        dec = PinnedPool.get("dec", (n,), np.uint32)
-        spread = PinnedPool.get("spread", (n,), np.uint32)
+        inc = PinnedPool.get("inc", (n,), np.uint32, owner=id(self.ctx))
+        dec = PinnedPool.get("dec", (n,), np.uint32, owner=id(self.ctx))
+        spread = PinnedPool.get("spread", (n,), np.uint32, owner=id(self.ctx))
         if V:
             check(lib.nts_graph_download_links(self._h, None, ptr(inc, C.c_uint32), ptr(dec, C.c_uint32), ptr(spread, C.c_uint32)))
         return inc[:V], dec[:V], spread[:V]
@@ -496,8 +510,8 @@ class MinimizerGraph:
         "nbr[cap, 2] i32, conn[cap] u8 of the weight-filtered graph (pinned, room for later vertices)"
         V = len(self)
         cap = max(int(cap), V, 1)
-        nbr = PinnedPool.get("nbr", (cap, 2), np.int32)
-        conn = PinnedPool.get("conn", (cap,), np.uint8)
+        nbr = PinnedPool.get("nbr", (cap, 2), np.int32, owner=id(self.ctx))
+        conn = PinnedPool.get("conn", (cap,), np.uint8, owner=id(self.ctx))
         if V:
             check(lib.nts_graph_download_links_nbr(self._h, cap, ptr(nbr, C.c_int32), ptr(conn, C.c_uint8)))
         return nbr, conn

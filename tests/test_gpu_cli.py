@@ -85,6 +85,22 @@ def test_ntsynt_cli_end_to_end(tmp_path, mini_params):
     assert (tmp_path / "mini-fof.synteny_blocks.tsv").read_text() == mini_expected("AB", "synteny_blocks.tsv")
 
 
+def test_ntsynt_cli_reads_gz_inputs_through_the_ingest_pipeline(tmp_path, mini_params):
+    "bin/ntSynt on .fa.gz paths in another directory: files parsed concurrently, genome i inserted while the next is read"
+    p = mini_params
+    src = tmp_path / "data"
+    src.mkdir()
+    paths = []
+    for f in mini_fastas("ABC"):
+        shutil.copyfile(f, src / os.path.basename(f))
+        paths.append(os.path.join("data", os.path.basename(f)))
+    out = run([sys.executable, os.path.join(BIN, "ntSynt"), *paths, f"-k{p['k']}", "-w", str(p["w"]), "-d", "0.5",
+               "--prefix", "gz-ABC", "--indel", str(p["indel"]), "--merge", p["merge"], "--block_size", str(p["block_size"]),
+               "--w_rounds", *map(str, p["w_rounds"]), "--benchmark"], tmp_path)
+    assert "ingest + Bloom filter (pipelined)" in out
+    assert (tmp_path / "gz-ABC.synteny_blocks.tsv").read_text() == mini_expected("ABC", "synteny_blocks.tsv")
+
+
 def test_cli_argument_errors(tmp_path):
     res = subprocess.run([sys.executable, os.path.join(BIN, "ntSynt"), "a.fa", "-d", "1"], cwd=tmp_path, stdout=subprocess.PIPE,
                          stderr=subprocess.STDOUT, text=True)
