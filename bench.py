@@ -139,6 +139,14 @@ class Dist:
         self.td.broadcast(t, 0)
         return bytes(t.numpy().tobytes())
 
+    def bcast_object(self, obj):
+        "rank 0's object on every rank"
+        if not self.td:
+            return obj
+        box = [obj]
+        self.td.broadcast_object_list(box, src=0)
+        return box[0]
+
     def gather_objects(self, obj):
         if not self.td:
             return [obj]
@@ -665,8 +673,8 @@ def run_ours_sharded(args, dist, ctx):
     """N > 1, contig-sharded ownership (BASELINE configs 3 and 4): every rank holds its contigs of every
     genome; per genome it builds the bits of those contigs; common = AND over genomes of (OR over ranks) with the
     peer-memory kernel (or, --merge nccl, one NCCL counter all-reduce per genome and a local AND); every rank sketches
-    its contigs; the tables are all-gathered and put back in contig order; rank 0 runs the join + graph stage (it also
-    keeps whole genomes for the masked refinement sketches, < 1 % of the bases)."""
+    its contigs; the tables are all-gathered and put back in contig order; rank 0 runs the join + graph stage; the masked
+    refinement rounds are sketched by every rank on its own contigs as well (distributed.ShardedSketcher)."""
     nccl_env()
     import numpy as np
     from ntsynt_b200 import device, distributed, pipeline, synth
@@ -684,8 +692,9 @@ def run_ours_sharded(args, dist, ctx):
     owner_of_contig = [next(r for r in range(N) if c in own_of[r]) for c in range(n_contigs)]
     mine_c = own_of[rank]
     shards = [wl.materialize(ctx, g, contigs=mine_c) for g in range(G)]
-    whole = [wl.materialize(ctx, g) for g in range(G)] if rank == 0 else None
-    sizes = [int(wl.segments(g)[0].sum()) for g in range(G)]
+    whole = None                                       # (rank 0 no longer keeps whole genomes: the masked rounds are sharded too)
+    contig_lengths = [wl.segments(g)[0] for g in range(G)]
+    sizes = [int(x.sum()) for x in contig_lengths]
     total_bp = sum(sizes)
     first = sorted(range(G), key=lambda i: file_names[i])[0]
     nbytes = device.BloomFilter.size_for(sizes[first], 0.025)
@@ -721,14 +730,21 @@ def run_ours_sharded(args, dist, ctx):
             t.close()
         tick("sketch_gather", t0); t0 = time.perf_counter()
         text, eng = None, None
+        # the masked refinement rounds are sketched by every rank on its own contigs (distributed.ShardedSketcher)
+        svc = distributed.ShardedSketcher(comm, ctx, shard_list, K, common, n_contigs, owner_of_contig, dist.bcast_object,
+                                          dist.gather_objects)
         if rank == 0:
-            be = distributed.GatheredBackend(ctx, [whole_list[i] for i in order], [names[i] for i in order], [wl.names] * G,
-                                             [[int(x) for x in whole_list[i].lengths] for i in order], K, common,
-                                             [tables[i] for i in order])
+            be = distributed.GatheredBackend(ctx, None, [names[i] for i in order], [wl.names] * G,
+                                             [[int(x) for x in contig_lengths[i]] for i in order], K, common,
+                                             [tables[i] for i in order],
+                                             masked_sketch=lambda a, w_, masks: svc.sketch(order[a], w_, masks))
             eng = SyntenyEngine(be, K, W, ps["w_rounds"], ps["indel"], ps["merge"], ps["block_size"], write_files=False,
                                 quiet=True)
             text = eng.run()
+            svc.done()
             be.close()
+        else:
+            svc.serve()
         for t in tables:
             t.close()
         dist.barrier()
@@ -753,22 +769,20 @@ def run_ours_sharded(args, dist, ctx):
     ctx.prof_enable(False)
     phase_ms = {k: round(v / args.steps, 2) for k, v in phase.items()}
     value = total_bp * args.steps / (ms / 1e3)
-    # e2e: shards (and rank 0's whole genomes) start in pinned host memory
+    # e2e: the shards start in pinned host memory
     def pin(gen):
         pk = gen.to_packed()
         pb = device.PinnedU64(len(pk.words)); pb.array[:] = pk.words; pk.words = pb.array
         return pk, pb
     pinned_sh = [pin(x) for x in shards]
-    pinned_wh = [pin(x) for x in whole] if rank == 0 else None
     ctx.prof_reset()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     dist.barrier(); ctx.sync()
     ctx.timer_start()
     for _ in range(e2e_steps):
         fs = [ctx.upload(pk, async_copy=True) for pk, _ in pinned_sh]
-        fw = [ctx.upload(pk, async_copy=True) for pk, _ in pinned_wh] if rank == 0 else None
-        text_e2e, _ = hot_path(fs, fw)
-        for f in fs + (fw or []):
+        text_e2e, _ = hot_path(fs, None)
+        for f in fs:
             f.close()
     ms_e2e = dist.max(ctx.timer_stop())
     h2d, d2h = ctx.xfer_bytes()

@@ -191,12 +191,48 @@ def gather_sharded_table(comm, table, n_contigs, owner_of_contig, gather_objects
     return out
 
 
+class ShardedSketcher:
+    """Refinement-round sketches of a contig-sharded run: rank 0 (which runs the graph stage) announces (genome, w,
+    masks) over the host side channel, EVERY rank sketches its own contigs of that genome under the masks, and the
+    tables are all-gathered and put back in contig order -- the masked rounds are sharded like round 0 instead of
+    being re-sketched by rank 0 alone.  The other ranks sit in serve() until rank 0 says done()."""
+
+    def __init__(self, comm, ctx, shards, k, common, n_contigs, owner_of_contig, bcast_object, gather_objects):
+        self.comm, self.ctx, self.shards, self.k, self.common = comm, ctx, shards, k, common
+        self.n_contigs, self.owner_of_contig = n_contigs, owner_of_contig
+        self.bcast, self.gather_objects = bcast_object, gather_objects
+
+    def _do(self, g, w, masks):
+        t = self.ctx.sketch(self.shards[g], self.k, w, common=self.common, masks=masks)
+        whole = gather_sharded_table(self.comm, t, self.n_contigs, self.owner_of_contig, self.gather_objects)
+        t.close()
+        return whole
+
+    def sketch(self, g, w, masks):
+        "rank 0: the whole genome's masked table"
+        self.bcast(("sketch", g, w, masks))
+        return self._do(g, w, masks)
+
+    def done(self):
+        self.bcast(("done",))
+
+    def serve(self):
+        "ranks > 0: take part in every sketch rank 0 asks for"
+        while True:
+            cmd = self.bcast(None)
+            if cmd[0] == "done":
+                return
+            self._do(cmd[1], cmd[2], cmd[3]).close()
+
+
 class GatheredBackend:
     """SyntenyEngine backend for rank 0 of a one-genome-per-GPU run: round-0 tables were sketched on
     their owner ranks and all-gathered; refinement sketches (tiny, <1 % unmasked) run locally on the
     copies of the genomes rank 0 holds."""
 
-    def __init__(self, ctx, genomes, names, contig_names, contig_lengths, k, common, round0_tables):
+    def __init__(self, ctx, genomes, names, contig_names, contig_lengths, k, common, round0_tables, masked_sketch=None):
+        "masked_sketch(a, w, masks) -> device table: where the refinement sketches come from (default: local copies)"
+        self.masked_sketch = masked_sketch
         self.ctx, self.genomes = ctx, genomes
         self.names = list(names)
         self.contig_names, self.contig_lengths = contig_names, contig_lengths
@@ -206,12 +242,14 @@ class GatheredBackend:
     def sketch(self, a, w, masks):
         if masks is None:
             return self.round0[a]
-        mx = self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, masks=masks)
+        mx = self.sketch_table(a, w, masks)
         out = mx.to_numpy()
         mx.close()
         return out
 
     def sketch_table(self, a, w, masks):
+        if self.masked_sketch is not None:
+            return self.masked_sketch(a, w, masks)
         return self.ctx.sketch(self.genomes[a], self.k, w, common=self.common, masks=masks)
 
     def join(self, tables, order_asm):

@@ -49,6 +49,9 @@ WORKER = textwrap.dedent("""
     a, b = (np.frombuffer(x, dtype=np.uint8) for x in all_bits)
     assert np.array_equal(and_bits, a & b) and np.array_equal(or_bits, a | b)
     assert d.max(d.rank + 1.0) == 2.0 and d.sum(1.0) == 2.0
+    # rank 0's command reaches rank 1 (the side channel of distributed.ShardedSketcher)
+    cmd = d.bcast_object(("sketch", 2, 250, [np.arange(3)]) if d.rank == 0 else None)
+    assert cmd[0] == "sketch" and cmd[1] == 2 and cmd[2] == 250 and cmd[3][0].tolist() == [0, 1, 2]
     d.barrier(); d.close()
     print("rank", d.rank, "ok")
 """)
