@@ -5,8 +5,10 @@
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
 
 A step = one pass of the whole hot path over one batch of synthetic genomes: Bloom-filter zero-fill,
-per-genome insert, merge, round-0 sketch, minimizer join + graph, every refinement round (masked
-re-sketch + graph), erosion, collinear merges, final block table as TSV text.
+per-genome insert, merge (the AND of the cascade: all levels but the last are ANDed, the last stays apart and the
+sketches look candidates up in both parts -- nts_bf_build_common_lazy / nts_sketch2), round-0 sketch, minimizer
+join + graph, every refinement round (masked re-sketch + graph), erosion, collinear merges, final block table
+as TSV text.
 
 N = 1  : BASELINE.json configs[1]: 2 synthetic ~3 Gbp human-like genomes, d = 1 %, k = 24, w = 1000,
          presets of bin/ntSynt:92-94 (block_size 1000, indel 50000, merge 100000, w_rounds 250 100).
@@ -18,11 +20,12 @@ N > 1  : configs[4] (default, G = N or a multiple): one 3 Gbp genome per GPU, pe
          configs[2] / configs[3] (--genomes 3 --divergence 1.3, --genomes 5 --divergence 12; any G that is not a
          multiple of N, or --shard contig): CONTIG-sharded ownership -- every rank inserts its contigs of every genome,
          common = AND over genomes of (OR over ranks) in one peer-memory kernel, every rank sketches its contigs, the
-         tables are put back in contig order on rank 0.  Strong scaling: the job is fixed.
+         tables are put back in contig order on rank 0; the masked refinement rounds are sketched by every rank on
+         its own contigs too.  Strong scaling: the job is fixed.
 
 `value` times the path with the packed genomes already resident in HBM; `e2e` times the same call
-chain starting from packed genomes in PINNED HOST memory (H2D inside the timed region) and ending
-with the TSV text on the host.  Timing: CUDA events on the library's stream, bracketed by barriers,
+chain starting from packed genomes in PINNED HOST memory (H2D inside the timed region, in growing chunks so that
+the first Bloom insert starts during the copy) and ending with the TSV text on the host.  Timing: CUDA events on the library's stream, bracketed by barriers,
 max over ranks.  Inputs (1.5 GB of bases, 2 x 14.8 GB of filter) are far larger than the 126 MB L2,
 so no explicit L2 flush is needed between iterations.
 """
