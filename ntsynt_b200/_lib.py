@@ -133,9 +133,9 @@ _SIGS = {
                                            C.POINTER(C.c_int8), i64p, i64p, i64p, i64p, i64p]),
     "nts_host_simplify": (C.c_int, [i64p, C.c_int64, u32p, u32p, C.POINTER(C.c_int32), C.c_int64, C.c_int64, C.c_uint32,
                                     i64p, i64p, i64p, C.c_int64, i64p]),
-    "nts_fasta_scan": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, u64p, u32p, u64p, u64p, u64p, u32p, u32p, u8p, u64p]),
-    "nts_fasta_scan_mt": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, u64p, u32p, u64p, u64p, u64p, u32p, u32p, u8p, u64p, C.c_uint32]),
-    "nts_fasta_pack": (C.c_int, [C.c_char_p, C.c_uint64, u64p, u64p, u64p, u32p, u32p, u8p, u64p, u64p, u64p, u64p, u64p,
+    "nts_fasta_scan": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, u64p, u32p, u64p, u64p, u64p, u32p, u32p, u8p, u64p]),
+    "nts_fasta_scan_mt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, u64p, u32p, u64p, u64p, u64p, u32p, u32p, u8p, u64p, C.c_uint32]),
+    "nts_fasta_pack": (C.c_int, [C.c_void_p, C.c_uint64, u64p, u64p, u64p, u32p, u32p, u8p, u64p, u64p, u64p, u64p, u64p,
                                  C.c_uint64, u64p, C.c_uint32]),
     "nts_graph_lookup": (C.c_int, [vp, u64p, C.c_uint64, u32p]),
     "nts_graph_edges": (C.c_int, [vp, u64p]),

@@ -116,13 +116,15 @@ def parse_fasta_bytes(data, path=None, threads=0):
     """FASTA text (bytes) -> PackedGenome with the native reader: one memchr scan for the records, then the records
     (and the 4 Mbp pieces of long uniform-width records) packed by `threads` threads (0 = all cores)"""
     n = len(data)
+    view = np.frombuffer(data, dtype=np.uint8) if n else np.zeros(1, dtype=np.uint8)    # bytes, mmap, ... : no copy
+    dptr = C.c_void_p(view.ctypes.data)
     cap = 4096
     while True:
         name_off, n_bases, seq_off, seq_end = (np.zeros(cap, dtype=np.uint64) for _ in range(4))
         name_len, lb, lw = (np.zeros(cap, dtype=np.uint32) for _ in range(3))
         uni = np.zeros(cap, dtype=np.uint8)
         nrec = C.c_uint64()
-        check(lib.nts_fasta_scan_mt(data, n, cap, ptr(name_off, C.c_uint64), ptr(name_len, C.c_uint32), ptr(n_bases, C.c_uint64),
+        check(lib.nts_fasta_scan_mt(dptr, n, cap, ptr(name_off, C.c_uint64), ptr(name_len, C.c_uint32), ptr(n_bases, C.c_uint64),
                                     ptr(seq_off, C.c_uint64), ptr(seq_end, C.c_uint64), ptr(lb, C.c_uint32), ptr(lw, C.c_uint32),
                                     ptr(uni, C.c_uint8), C.byref(nrec), int(threads)))
         if nrec.value <= cap:
@@ -130,7 +132,7 @@ def parse_fasta_bytes(data, path=None, threads=0):
         cap = int(nrec.value)
     R = int(nrec.value)
     n_bases, seq_off, seq_end, lb, lw, uni = n_bases[:R], seq_off[:R], seq_end[:R], lb[:R], lw[:R], uni[:R]
-    names = [data[int(o):int(o) + int(l)].decode() for o, l in zip(name_off[:R], name_len[:R])]
+    names = [bytes(view[int(o):int(o) + int(l)]).decode() for o, l in zip(name_off[:R], name_len[:R])]
     nw = ((n_bases + np.uint64(63)) // np.uint64(64)) * np.uint64(2)
     word_off = np.zeros(R + 1, dtype=np.uint64)
     np.cumsum(nw, out=word_off[1:])
@@ -141,7 +143,7 @@ def parse_fasta_bytes(data, path=None, threads=0):
     while True:
         rs, rl = np.zeros(rcap, dtype=np.uint64), np.zeros(rcap, dtype=np.uint64)
         nruns = C.c_uint64()
-        check(lib.nts_fasta_pack(data, R, ptr(n_bases if R else z64, C.c_uint64), ptr(seq_off if R else z64, C.c_uint64),
+        check(lib.nts_fasta_pack(dptr, R, ptr(n_bases if R else z64, C.c_uint64), ptr(seq_off if R else z64, C.c_uint64),
                                  ptr(seq_end if R else z64, C.c_uint64), ptr(lb if R else np.zeros(1, np.uint32), C.c_uint32),
                                  ptr(lw if R else np.zeros(1, np.uint32), C.c_uint32), ptr(uni if R else np.zeros(1, np.uint8), C.c_uint8),
                                  ptr(word_off, C.c_uint64), ptr(words if words.size else z64, C.c_uint64), ptr(nrun_off, C.c_uint64),
@@ -214,11 +216,17 @@ def inflate_gz(raw, threads=0):
 
 def read_fasta(path, threads=0):
     "FASTA file (.gz accepted) -> PackedGenome through the native reader (csrc/nts_fasta.cu)"
+    import mmap
     with open(path, "rb") as fh:
-        data = fh.read()
-    if data[:2] == b"\x1f\x8b":
-        data = inflate_gz(data, threads)
-    return parse_fasta_bytes(data, path=path, threads=threads)
+        if fh.read(2) == b"\x1f\x8b":
+            fh.seek(0)
+            return parse_fasta_bytes(inflate_gz(fh.read(), threads), path=path, threads=threads)
+        size = fh.seek(0, 2)
+        if size == 0:
+            return parse_fasta_bytes(b"", path=path, threads=threads)
+        # plain text: the scanner and the packer read the page cache through a mapping (no 3 GB copy into a bytes object)
+        with mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            return parse_fasta_bytes(mm, path=path, threads=threads)
 
 
 def read_fastas(paths, threads=0):

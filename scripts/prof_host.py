@@ -54,7 +54,7 @@ def _wrap(name):
         fr = sys._getframe(1)
         e = _acc[(name, os.path.basename(fr.f_code.co_filename), fr.f_lineno)]
         e[0] += 1; e[1] += time.perf_counter() - t0
-        e[2] = max(e[2], max((getattr(x, "size", 0) for x in a), default=0))
+        e[2] = max(e[2], max((x.size for x in a if isinstance(x, _np.ndarray)), default=0))
         return r
     setattr(_np, name, f)
     return orig

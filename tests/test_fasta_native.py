@@ -128,7 +128,8 @@ def _scan(data, mt_threads=None):
     name_len, lb, lw = (np.zeros(cap, dtype=np.uint32) for _ in range(3))
     uni = np.zeros(cap, dtype=np.uint8)
     nrec = C.c_uint64()
-    args = [data, len(data), cap, ptr(name_off, C.c_uint64), ptr(name_len, C.c_uint32), ptr(n_bases, C.c_uint64),
+    keep = np.frombuffer(data, dtype=np.uint8)
+    args = [C.c_void_p(keep.ctypes.data), len(data), cap, ptr(name_off, C.c_uint64), ptr(name_len, C.c_uint32), ptr(n_bases, C.c_uint64),
             ptr(seq_off, C.c_uint64), ptr(seq_end, C.c_uint64), ptr(lb, C.c_uint32), ptr(lw, C.c_uint32), ptr(uni, C.c_uint8), C.byref(nrec)]
     if mt_threads is None:
         check(lib.nts_fasta_scan(*args))
