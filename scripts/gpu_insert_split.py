@@ -12,10 +12,13 @@ ctx = device.Context(0)
 ctx.prof_enable(True)
 wl = synth.Workload(2, int(mbp * 1e6), 1.0)
 gens = [wl.materialize(ctx, g) for g in range(2)]
-nbytes = device.BloomFilter.size_for(gens[0].total_bases, 0.025)
+# optional second argument: size the filter for a genome of that many Mbp (a contig-sharded rank inserts its share of
+# the k-mers into a filter sized for the whole genome)
+fmbp = float(sys.argv[2]) if len(sys.argv) > 2 else None
+nbytes = device.BloomFilter.size_for(int(fmbp * 1e6) if fmbp else gens[0].total_bases, 0.025)
 common, level = ctx.bloom(nbytes), ctx.bloom(nbytes)
 pops = {}
-for rank in ("1", "2", "1", "2"):
+for rank in ("1", "1"):
     os.environ["NTS_BF_BIN"] = rank
     for rep in range(2):
         ctx.prof_reset()
