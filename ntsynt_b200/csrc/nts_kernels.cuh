@@ -640,15 +640,26 @@ sketch_sparse_kernel(GenomeView g, const HashTables* __restrict__ g_tabs, const 
                             }
                         }
                     }
+                    if (summary) {
+                        // the slots whose line holds a bit: their real lookups go out together as well (a warp nearly
+                        // always has some, and one after the other they would each cost a trip to HBM)
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const uint32_t jj = half * 8 + u;
+                            if (jj < cnt && (ok[u] & 1u)) {
+                                const uint64_t idx = fast_mod(s_skey[jj * THREADS + tid], m, mprime);
+                                ok[u] = (__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u;
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const uint32_t jj = half * 8 + u;
                         if (jj < cnt && (ok[u] & 1u)) {                 // (n_st <= jj: the write never passes the read)
                             const uint64_t h = s_skey[jj * THREADS + tid];
-                            if (summary || common2) {
+                            if (common2) {
                                 const uint64_t idx = fast_mod(h, m, mprime);
-                                if (summary && !((__ldg(&common[idx >> 5]) >> (idx & 31)) & 1u)) continue;
-                                if (common2 && !((__ldg(&common2[idx >> 5]) >> (idx & 31)) & 1u)) continue;
+                                if (!((__ldg(&common2[idx >> 5]) >> (idx & 31)) & 1u)) continue;
                             }
                             if (repeat) {
                                 const uint64_t ridx = fast_mod(h, rm, rmprime);
