@@ -701,11 +701,18 @@ def run_ours_sharded(args, dist, ctx):
     total_bp = sum(sizes)
     first = sorted(range(G), key=lambda i: file_names[i])[0]
     nbytes = device.BloomFilter.size_for(sizes[first], 0.025)
-    parts = [ctx.bloom(nbytes) for _ in range(G)]
     common = ctx.bloom(nbytes)
     ident = distributed.Comm.new_unique_id() if rank == 0 else b""
     comm = distributed.Comm(ctx, rank, N, dist.bcast_bytes(ident, 128))
-    peer = distributed.ShardedMerge(parts, common, rank, N, dist.gather_objects, dist.barrier) if N <= 16 and G <= 8 else None
+    owned = None
+    if args.merge == "owned" and N <= 16:
+        plan_valid = int(dist.max(max(int(x.total_bases) for x in shards)))
+        owned = distributed.OwnedBuild(common, ctx.bloom(nbytes), rank, N, K, plan_valid, dist.gather_objects, dist.barrier, comm)
+        if not owned.ok:
+            owned = None
+    parts = [ctx.bloom(nbytes) for _ in range(G)] if owned is None else []
+    peer = (distributed.ShardedMerge(parts, common, rank, N, dist.gather_objects, dist.barrier)
+            if owned is None and N <= 16 and G <= 8 else None)
     if peer is not None and not peer.ok:
         peer = None
     use_p2p = args.merge == "p2p" and peer is not None
@@ -716,10 +723,18 @@ def run_ours_sharded(args, dist, ctx):
 
     def hot_path(shard_list, whole_list):
         t0 = time.perf_counter()
-        for g in range(G):
+        if owned is not None:
+            over = owned.build(shard_list)                         # bin everywhere, apply on the owner over peer memory, all-gather
+            if dist.sum(over):
+                raise SystemExit("owned build: bucket overflow (heavy-hitter k-mers); use --merge p2p")
+            ctx.sync(); tick("owned_build", t0); t0 = time.perf_counter()
+        for g in (range(G) if owned is None else ()):
             parts[g].set_genome(shard_list[g], K)                  # bits of my contigs of genome g
-        ctx.sync(); tick("insert", t0); t0 = time.perf_counter()
-        if use_p2p:
+        if owned is None:
+            ctx.sync(); tick("insert", t0); t0 = time.perf_counter()
+        if owned is not None:
+            pass
+        elif use_p2p:
             peer.merge(comm=comm)                                  # AND_g OR_r over NVLink peer memory, then all-gather
         else:
             for g in range(G):                                     # north-star form: counter all-reduce per genome
@@ -811,11 +826,12 @@ def run_ours_sharded(args, dist, ctx):
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"{G} synthetic ~{args.genome_mbp:g} Mbp genomes, contigs sharded over {N}xB200, d={d:g}, "
                                    f"k={K} w={W}, w_rounds {ps['w_rounds']}; common = AND_g OR_rank over NVLink "
-                                   f"({'peer-memory kernel' if use_p2p else 'NCCL counter all-reduce per genome'})",
+                                   f"({'owned build: buckets applied by the slice owner over peer memory, no merge' if owned is not None else 'peer-memory kernel' if use_p2p else 'NCCL counter all-reduce per genome'})",
                        "genomes": G, "genome_bp": sizes[0], "k": K, "w": W, "fpr": 0.025, "bloom_bytes": nbytes,
                        "shard": "contig", "contigs_per_rank": [len(x) for x in own_of],
                        "bases_per_rank_of_genome0": [int(sum(int(wl.segments(0)[0][c]) for c in x)) for x in own_of],
-                       "merge": "p2p" if use_p2p else "nccl", "merge_wire_bytes_per_rank": int(wire),
+                       "merge": "owned" if owned is not None else "p2p" if use_p2p else "nccl",
+                       "merge_wire_bytes_per_rank": int(wire) if owned is None else int(nbytes * (N - 1) / N + 4 * total_bp * (N - 1) / N / N),
                        "phase_ms_rank0": phase_ms,
                        "l2": "inputs (bases + filters) are larger than L2; no flush needed",
                        "blocks": text.count("\n") // G, "blocks_sha1": sha1_text(text), "vertices": eng.stats.get("vertices"),
@@ -833,6 +849,8 @@ def run_ours_sharded(args, dist, ctx):
         }))
     if peer is not None:
         peer.close()
+    if owned is not None:
+        owned.close()
     comm.close()
 
 def run_reference(args, dist):
@@ -893,10 +911,12 @@ def main():
     ap.add_argument("--shard", choices=["genome", "contig"], default=None,
                     help="multi-GPU ownership: one genome per GPU (default when --genomes is a multiple of --gpus) or the "
                          "contigs of every genome spread over the GPUs (default otherwise: BASELINE configs 3 and 4)")
-    ap.add_argument("--merge", choices=["nccl", "p2p"], default="p2p",
+    ap.add_argument("--merge", choices=["nccl", "p2p", "owned"], default="p2p",
                     help="multi-GPU filter merge: peer-memory reduce-scatter/all-gather kernels over NVLink (default; "
-                         "bit-identical and ~4x less wire volume) or NCCL all-reduce(sum) of packed counters (the "
-                         "north-star form; also timed alone in config.merge_alone_ms)")
+                         "bit-identical and ~4x less wire volume), NCCL all-reduce(sum) of packed counters (the "
+                         "north-star form; also timed alone in config.merge_alone_ms), or -- contig-sharded runs -- no "
+                         "merge at all: hash-range owned build (every GPU bins, the owner of a filter slice applies "
+                         "every GPU's buckets over peer memory)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: fewer than 3 warm-up steps; the number is not reportable", file=sys.stderr)

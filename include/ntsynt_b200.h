@@ -235,6 +235,30 @@ int nts_p2p_all_gather(nts_p2p* p);
  * computes common = AND over genomes of (OR over ranks) -- src/ntsynt_make_common_bf.cpp:136-160 and the cross-GPU
  * merge in one kernel that reads peer HBM; up to 8 genomes. */
 int nts_p2p_reduce_and_of_or(nts_p2p* const* sets, uint32_t n_sets, nts_p2p* out);
+
+/* ---- hash-range OWNED build of the common filter (multi-GPU; replaces building whole per-GPU filters and merging them,
+ * src/ntsynt_make_common_bf.cpp:122-160 across GPUs).  Every GPU bins its k-mers with one agreed plan (pass 1 of the
+ * partitioned insert); the GPU that owns a byte range of the filter -- the slices of nts_p2p_all_gather -- applies the
+ * buckets of every GPU to it, reading them over NVLink peer memory (4 bytes per k-mer on the wire), ORs per genome, ANDs
+ * across genomes on its slice (nts_bf_range_op), and nts_p2p_all_gather distributes the finished filter. */
+typedef struct nts_binpeer nts_binpeer;
+/* plan + scratch of `slot` for filters of sized_like's size and up to plan_valid k-mers per binning pass (same values on
+ * every rank); the scratch is what nts_bin_ipc_handles exports */
+int nts_bin_prepare(nts_bf* sized_like, int slot, uint64_t plan_valid);
+/* pass 1 only, asynchronous: the genome's k-mers binned by filter region into the slot's buckets */
+int nts_bin_genome(nts_bf* sized_like, const nts_genome* g, uint32_t k, int slot);
+/* k-mers that did not fit their bucket since nts_bin_prepare (heavy hitters; they were NOT applied: redo with the merge) */
+int nts_bin_overflow(nts_ctx* ctx, int slot, uint64_t* n);
+int nts_bin_ipc_handles(nts_ctx* ctx, int slot, uint8_t items_handle[64], uint8_t cursor_handle[64]);
+int nts_binpeer_open(nts_ctx* ctx, const uint8_t* items_handles /* world x 64 */, const uint8_t* cursor_handles, int rank, int world,
+                     int slot, nts_binpeer** out);
+void nts_binpeer_close(nts_binpeer* p);
+/* bf[off16 .. off16 + n16) |= bits of what rank `source` binned (units of 16 bytes; asynchronous) */
+int nts_bf_apply_owned(nts_bf* bf, nts_binpeer* p, int source, uint64_t off16, uint64_t n16);
+/* dst[range] op= src[range]: op 0 AND, 1 OR, 2 COPY (src null: zero); asynchronous */
+int nts_bf_range_op(nts_bf* dst, const nts_bf* src, uint64_t off16, uint64_t n16, int op);
+/* the slice rank s owns in nts_p2p_reduce_scatter / nts_p2p_all_gather */
+int nts_p2p_slice(const nts_p2p* p, int s, uint64_t* off16, uint64_t* n16);
 /* all-gather of minimizer tables (ncclAllGather over padded columns): out[r] = rank r's table, as a
  * new nts_mxs on this rank; counts[world] must hold every rank's table size. */
 int nts_mxs_allgather(nts_comm* comm, const nts_mxs* mine, const uint64_t* counts, nts_mxs** out);

@@ -110,6 +110,15 @@ _SIGS = {
     "nts_p2p_reduce_scatter": (C.c_int, [vp, C.c_int]),
     "nts_p2p_all_gather": (C.c_int, [vp]),
     "nts_p2p_reduce_and_of_or": (C.c_int, [vpp, C.c_uint32, vp]),
+    "nts_bin_prepare": (C.c_int, [vp, C.c_int, C.c_uint64]),
+    "nts_bin_genome": (C.c_int, [vp, vp, C.c_uint32, C.c_int]),
+    "nts_bin_overflow": (C.c_int, [vp, C.c_int, u64p]),
+    "nts_bin_ipc_handles": (C.c_int, [vp, C.c_int, u8p, u8p]),
+    "nts_binpeer_open": (C.c_int, [vp, u8p, u8p, C.c_int, C.c_int, C.c_int, vpp]),
+    "nts_binpeer_close": (None, [vp]),
+    "nts_bf_apply_owned": (C.c_int, [vp, vp, C.c_int, C.c_uint64, C.c_uint64]),
+    "nts_bf_range_op": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_int]),
+    "nts_p2p_slice": (C.c_int, [vp, C.c_int, u64p, u64p]),
     "nts_mxs_drop_in_bf": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vpp]),
     "nts_mxs_contig_offsets": (C.c_int, [vp, C.c_uint32, u64p]),
     "nts_mxs_concat": (C.c_int, [vp, vpp, u64p, u64p, C.c_uint64, vpp]),

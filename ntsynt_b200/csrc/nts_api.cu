@@ -652,6 +652,18 @@ static int mod_params(const nts_bf* bf, uint64_t* m, uint64_t* mprime)
 
 static int bf_combine(nts_bf* dst, const nts_bf* src, int op, bool sync);
 
+// what code outside this file needs to hash a genome's k-mers (csrc/nts_p2p.cu: owned builds)
+int genome_plain_view(const nts_genome* g, uint32_t k, GenomeView* gv, uint64_t* total_valid, const HashTables** tabs)
+{
+    int rc = get_tables(g->ctx, k, tabs);
+    if (rc) return rc;
+    const nts_view* v = nullptr;
+    if ((rc = get_plain_view(g, k, &v))) return rc;
+    *gv = device_view(g, v);
+    *total_valid = v->total_valid;
+    return NTS_OK;
+}
+
 // direct insert: one RED.OR per k-mer (small filters; the fallback of the partitioned path)
 static int bf_insert_direct(nts_ctx* ctx, nts_bf* bf, const nts_genome* g, const nts_view* v, const HashTables* tabs)
 {

@@ -53,6 +53,9 @@ struct PairScratch {
     DevBuf<uint64_t> bucket_off, chunk_first;
     DevBuf<uint32_t> bucket_cap;
     DevBuf<unsigned int> cursor;
+    DevBuf<unsigned int> ovf;                  // owned builds: items that did not fit their bucket (counted, not applied)
+    std::vector<uint64_t> h_chunk_first;       // host copy of chunk_first
+    uint64_t plan_m = 0, plan_valid = 0;       // what the tables were planned for
     // plan of the current use
     uint32_t P = 0, shift = 0;
     uint64_t n_chunks = 0, n_items = 0;
@@ -78,12 +81,12 @@ static void scratch_drop(nts_ctx* ctx, int slot)
 // Plan the buckets of one insert (m filter bits, total_valid k-mers) and upload the tables of `slot`.
 // *ok = false when the partitioned path does not apply (small filter, too little work, no memory).
 // Synchronises ctx->stream (the host tables go out of scope).
-static int pair_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t total_valid, bool* ok)
+static int pair_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t total_valid, bool* ok, bool always = false)
 {
     *ok = false;
     const char* env = getenv("NTS_BF_PARTITION");
-    const bool force = env && env[0] == '1';
-    if (env && env[0] == '0') return NTS_OK;
+    const bool force = always || (env && env[0] == '1');
+    if (!always && env && env[0] == '0') return NTS_OK;
     // only worth it when the filter is far larger than L2 and there is enough work
     if (!force && (m < (1ull << 32) || total_valid < (1ull << 26))) return NTS_OK;
     if (m >= (1ull << 42)) return NTS_OK;
@@ -122,13 +125,14 @@ static int pair_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t total_valid
     NTS_CUDA(cudaMemcpyAsync(sc->bucket_cap.p, cap.data(), P * 4, cudaMemcpyHostToDevice, ctx->stream));
     NTS_CUDA(cudaStreamSynchronize(ctx->stream));          // host vectors go out of scope
     sc->P = P; sc->shift = shift; sc->n_chunks = chunk_first[P];
+    sc->h_chunk_first = chunk_first; sc->plan_m = m; sc->plan_valid = total_valid;
     *ok = true;
     return NTS_OK;
 }
 
 // pass 1 of a prepared slot on `st`: hash the genome, bin the bit indices by filter region
 static int pair_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid,
-                    const std::vector<UploadStage>* stages = nullptr)
+                    const std::vector<UploadStage>* stages = nullptr, unsigned int* ovf_count = nullptr)
 {
     PairScratch* sc = g_pair_scratch[{ctx, slot}];
     const uint64_t m = bf->bytes * 8;
@@ -136,7 +140,7 @@ static int pair_bin(nts_ctx* ctx, int slot, cudaStream_t st, nts_bf* bf, const G
     NTS_CUDA(cudaMemsetAsync(sc->cursor.p, 0, sc->P * 4, st));
     BinParams bp;
     bp.items = sc->items.p; bp.bucket_off = sc->bucket_off.p; bp.bucket_cap = sc->bucket_cap.p; bp.cursor = sc->cursor.p;
-    bp.n_buckets = sc->P; bp.region_shift = sc->shift;
+    bp.n_buckets = sc->P; bp.region_shift = sc->shift; bp.ovf_count = ovf_count;
     const uint64_t mprime = 0xFFFFFFFFFFFFFFFFull / m;
     const unsigned n_tiles = (unsigned)((total_valid + BIN_TILE - 1) / BIN_TILE);
     // NTS_BF_BIN=2: ranking without shared-memory atomics (nts_rank.cuh; same output up to the order inside a bucket)
@@ -208,6 +212,86 @@ int pair_insert(nts_ctx* ctx, nts_bf* bf, const GenomeView& gv, const HashTables
     }
     ctx->part_inserts++;
     *done = true;
+    return NTS_OK;
+}
+
+// ================================================================================================================
+// (A') hash-range OWNED builds (multi-GPU, csrc/nts_p2p.cu): every GPU bins its k-mers with the same plan; the GPU that
+//      owns a range of the filter applies the buckets of every GPU -- read over NVLink peer memory -- to that range
+// ================================================================================================================
+int owned_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t plan_valid)
+{
+    bool ok = false;
+    auto it = g_pair_scratch.find({ctx, slot});
+    if (it != g_pair_scratch.end() && it->second->plan_m == m && it->second->plan_valid == plan_valid && it->second->ovf.p) return NTS_OK;
+    int rc = pair_prepare(ctx, slot, m, plan_valid, &ok, true);
+    if (rc) return rc;
+    if (!ok) return fail(NTS_ERR_ARG, "owned build: this filter size / amount of work cannot be planned (too many regions or no memory)");
+    PairScratch* sc = g_pair_scratch[{ctx, slot}];
+    if (!sc->ovf.p && sc->ovf.alloc(4) != cudaSuccess) return fail(NTS_ERR_NOMEM, "device allocation failed (overflow counter)");
+    NTS_CUDA(cudaMemsetAsync(sc->ovf.p, 0, 16, ctx->stream));
+    return NTS_OK;
+}
+
+int owned_bin(nts_ctx* ctx, int slot, nts_bf* sized_like, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid)
+{
+    auto it = g_pair_scratch.find({ctx, slot});
+    if (it == g_pair_scratch.end() || it->second->plan_m != sized_like->bytes * 8) return fail(NTS_ERR_STATE, "owned build: slot not prepared for this filter");
+    PairScratch* sc = it->second;
+    if (total_valid > sc->plan_valid) return fail(NTS_ERR_ARG, "owned build: more k-mers than the plan was made for");
+    if (!total_valid) { NTS_CUDA(cudaMemsetAsync(sc->cursor.p, 0, sc->P * 4, ctx->stream)); return NTS_OK; }
+    return pair_bin(ctx, slot, ctx->stream, sized_like, gv, tabs, total_valid, nullptr, sc->ovf.p);
+}
+
+int owned_buffers(nts_ctx* ctx, int slot, void** items, void** cursor)
+{
+    auto it = g_pair_scratch.find({ctx, slot});
+    if (it == g_pair_scratch.end()) return fail(NTS_ERR_STATE, "owned build: slot not prepared");
+    *items = it->second->items.p; *cursor = it->second->cursor.p;
+    return NTS_OK;
+}
+
+int owned_overflow(nts_ctx* ctx, int slot, uint64_t* n)
+{
+    auto it = g_pair_scratch.find({ctx, slot});
+    if (it == g_pair_scratch.end()) return fail(NTS_ERR_STATE, "owned build: slot not prepared");
+    unsigned int h = 0;
+    NTS_CUDA(cudaMemcpyAsync(&h, it->second->ovf.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n = h;
+    return NTS_OK;
+}
+
+// apply the buckets (`items`, `cursor`: this GPU's or a peer's, same plan) to words [off16, off16 + n16) x 16 bytes of bf
+int owned_apply(nts_ctx* ctx, int slot, const uint32_t* items, const unsigned int* cursor, nts_bf* bf, uint64_t off16, uint64_t n16)
+{
+    auto it = g_pair_scratch.find({ctx, slot});
+    if (it == g_pair_scratch.end() || it->second->plan_m != bf->bytes * 8) return fail(NTS_ERR_STATE, "owned build: slot not prepared for this filter");
+    PairScratch* sc = it->second;
+    if (!n16) return NTS_OK;
+    const uint64_t bit_lo = off16 * 128, bit_hi = std::min<uint64_t>((off16 + n16) * 128, bf->alloc_bytes * 8);
+    const uint32_t b_lo = (uint32_t)(bit_lo >> sc->shift);
+    const uint32_t b_hi = (uint32_t)std::min<uint64_t>(sc->P, ((bit_hi - 1) >> sc->shift) + 1);       // one past the last region
+    if (b_lo >= b_hi) return NTS_OK;
+    const uint64_t c0 = sc->h_chunk_first[b_lo], c1 = sc->h_chunk_first[b_hi];
+    if (c1 <= c0) return NTS_OK;
+    ProfScope prof(ctx, PROF_BF_APPLY, 0.0);
+    bf_apply_owned_kernel<<<(unsigned)(c1 - c0), 256, 0, ctx->stream>>>(items, sc->bucket_off.p, sc->bucket_cap.p, cursor,
+                                                                       sc->chunk_first.p, sc->P, sc->shift, CHUNK_ITEMS, bf->words.p,
+                                                                       c0, bit_lo, bit_hi);
+    ctx->launches++;
+    NTS_CUDA(cudaGetLastError());
+    return NTS_OK;
+}
+
+int bf_range_op(nts_ctx* ctx, nts_bf* dst, const nts_bf* src, uint64_t off16, uint64_t n16, int op)
+{
+    if (!n16) return NTS_OK;
+    ProfScope prof(ctx, src ? PROF_BF_COMBINE : PROF_FILL, (double)n16 * 16);
+    bf_range_kernel<<<(unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+        reinterpret_cast<uint4*>(dst->words.p), src ? reinterpret_cast<const uint4*>(src->words.p) : nullptr, off16, n16, op);
+    ctx->launches++;
+    NTS_CUDA(cudaGetLastError());
     return NTS_OK;
 }
 

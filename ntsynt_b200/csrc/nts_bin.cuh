@@ -26,6 +26,8 @@ __device__ __forceinline__ void stage_tables_bin(HashTables* s_tabs, const HashT
 }
 
 struct BinParams {
+    unsigned int* ovf_count = nullptr;   // not null: items past a bucket's capacity are only COUNTED (hash-range owned builds, where
+                                         // the bits of a region belong to another GPU; the caller falls back if any were counted)
     uint32_t* items;               // bucket storage, bucket b at [bucket_off[b], bucket_off[b] + bucket_cap[b])
     const uint64_t* bucket_off;    // [P]
     const uint32_t* bucket_cap;    // [P]
@@ -122,6 +124,8 @@ __global__ void __launch_bounds__(THREADS, 2) bf_bin_kernel(GenomeView g, const 
         const uint32_t x = s_sorted[i];
         if (r < s_fit[b]) {
             bp.items[(uint64_t)s_dst[b] + r] = x;
+        } else if (bp.ovf_count) {
+            atomicAdd(bp.ovf_count, 1u);
         } else {                                                   // overflow (heavy hitters): apply directly
             const uint64_t idx = ((uint64_t)b << bp.region_shift) + x;
             atomicOr(&bits[idx >> 5], 1u << (idx & 31));
@@ -176,5 +180,60 @@ __global__ void __launch_bounds__(256) bf_apply_kernel(const uint32_t* __restric
     }
 }
 
+// pass 2 of a hash-range OWNED build (multi-GPU): this GPU owns the filter bits [bit_lo, bit_hi); `items` / `cursor` are the
+// buckets of ANOTHER GPU's binning pass, read over NVLink peer memory (coalesced 128-bit loads, 4 bytes per k-mer on the
+// wire instead of the partial filters themselves).  CTA c applies chunk chunk0 + c; the launch covers the regions that
+// overlap the owned range, and the items of the two boundary regions are filtered by bit index.
+__global__ void __launch_bounds__(256) bf_apply_owned_kernel(const uint32_t* __restrict__ items, const uint64_t* __restrict__ bucket_off,
+                                const uint32_t* __restrict__ bucket_cap, const unsigned int* __restrict__ cursor,
+                                const uint64_t* __restrict__ chunk_first, uint32_t n_buckets, uint32_t region_shift,
+                                uint32_t chunk_items, uint32_t* __restrict__ bits, uint64_t chunk0, uint64_t bit_lo, uint64_t bit_hi)
+{
+    const uint64_t chunk = (uint64_t)blockIdx.x + chunk0;
+    uint32_t lo = 0, hi = n_buckets;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (chunk_first[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    const uint32_t b = lo;
+    const uint32_t n = min(cursor[b], bucket_cap[b]);
+    const uint64_t start = (chunk - chunk_first[b]) * chunk_items;
+    if (start >= n) return;
+    const uint32_t cnt = (uint32_t)min((uint64_t)chunk_items, n - start);
+    const uint32_t* src = items + bucket_off[b] + start;
+    const uint64_t rbase = (uint64_t)b << region_shift;
+    uint32_t* region = bits + (rbase >> 5);
+    // the region lies inside the owned range unless it is one of the two at its ends
+    const uint64_t rlo = bit_lo > rbase ? bit_lo - rbase : 0;
+    const uint64_t rhi = bit_hi - rbase;                         // (bit_hi > rbase for every launched region)
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);
+    const uint32_t n4 = cnt >> 2;
+    auto put = [&](uint32_t x) { if (x >= rlo && x < rhi) atomicOr(&region[x >> 5], 1u << (x & 31)); };
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t i = threadIdx.x + u * 256;
+        if (i < n4) v[u] = src4[i];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t i = threadIdx.x + u * 256;
+        if (i < n4) { put(v[u].x); put(v[u].y); put(v[u].z); put(v[u].w); }
+    }
+    const uint32_t i = (n4 << 2) + threadIdx.x;
+    if (i < cnt) put(src[i]);
+}
+
+// dst[off16 .. off16 + n16) op= src[...]: 0 AND, 1 OR, 2 COPY (slices of filters: owned builds)
+__global__ void bf_range_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, uint64_t off16, uint64_t n16, int op)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        uint4 a = src ? src[off16 + i] : make_uint4(0u, 0u, 0u, 0u);
+        if (op == 0) { const uint4 d = dst[off16 + i]; a.x &= d.x; a.y &= d.y; a.z &= d.z; a.w &= d.w; }
+        else if (op == 1) { const uint4 d = dst[off16 + i]; a.x |= d.x; a.y |= d.y; a.z |= d.z; a.w |= d.w; }
+        dst[off16 + i] = a;
+    }
+}
 
 }  // namespace nts

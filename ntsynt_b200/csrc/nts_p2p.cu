@@ -15,6 +15,13 @@
 #include "nts_internal.h"
 
 namespace nts {
+// csrc/nts_bf_part.cu: hash-range owned builds
+int owned_prepare(nts_ctx* ctx, int slot, uint64_t m, uint64_t plan_valid);
+int owned_bin(nts_ctx* ctx, int slot, nts_bf* sized_like, const GenomeView& gv, const HashTables* tabs, uint64_t total_valid);
+int owned_buffers(nts_ctx* ctx, int slot, void** items, void** cursor);
+int owned_overflow(nts_ctx* ctx, int slot, uint64_t* n);
+int owned_apply(nts_ctx* ctx, int slot, const uint32_t* items, const unsigned int* cursor, nts_bf* bf, uint64_t off16, uint64_t n16);
+int bf_range_op(nts_ctx* ctx, nts_bf* dst, const nts_bf* src, uint64_t off16, uint64_t n16, int op);
 
 constexpr int P2P_MAX_RANKS = 16;
 struct PeerPtrs { const uint4* p[P2P_MAX_RANKS]; };
@@ -81,6 +88,9 @@ __global__ void p2p_and_of_or_kernel(uint4* __restrict__ out, MultiPtrs mp, int 
 }  // namespace nts
 
 using namespace nts;
+
+// csrc/nts_api.cu (defined inside its extern "C" block; not part of the public header)
+extern "C" int genome_plain_view(const nts_genome* g, uint32_t k, nts::GenomeView* gv, uint64_t* total_valid, const nts::HashTables** tabs);
 
 struct nts_p2p {
     nts_ctx* ctx = nullptr;
@@ -215,6 +225,133 @@ int nts_p2p_all_gather(nts_p2p* p)
         NTS_CUDA(cudaGetLastError());
     }
     NTS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NTS_OK;
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Hash-range OWNED build of the common filter (multi-GPU): instead of every GPU building whole (partial) filters and the
+ * filters being merged -- G x (P-1)/P x 14.8 GB over NVLink per GPU in a contig-sharded run --, every GPU only BINS its
+ * k-mers (pass 1 of the partitioned insert, same plan everywhere), and the GPU that owns a byte range of the filter
+ * applies the buckets of EVERY GPU to that range, reading them over NVLink peer memory: 4 bytes per k-mer on the wire.
+ * The owned slices are the slices of nts_p2p_all_gather, which then distributes the finished common filter. */
+struct nts_binpeer {
+    nts_ctx* ctx = nullptr;
+    int rank = 0, world = 1, slot = 0;
+    void* items[P2P_MAX_RANKS] = {nullptr};
+    void* cursor[P2P_MAX_RANKS] = {nullptr};
+};
+
+int nts_bin_prepare(nts_bf* sized_like, int slot, uint64_t plan_valid)
+{
+    if (!sized_like || slot < 0 || slot > 7) return fail(NTS_ERR_ARG, "bad argument");
+    NTS_CUDA(cudaSetDevice(sized_like->ctx->device));
+    return owned_prepare(sized_like->ctx, slot, sized_like->bytes * 8, plan_valid);
+}
+
+int nts_bin_genome(nts_bf* sized_like, const nts_genome* g, uint32_t k, int slot)
+{
+    if (!sized_like || !g || g->ctx != sized_like->ctx) return fail(NTS_ERR_ARG, "bad argument");
+    nts_ctx* ctx = sized_like->ctx;
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    GenomeView gv;
+    uint64_t total_valid = 0;
+    const HashTables* tabs = nullptr;
+    int rc = genome_plain_view(g, k, &gv, &total_valid, &tabs);
+    if (rc) return rc;
+    return owned_bin(ctx, slot, sized_like, gv, tabs, total_valid);
+}
+
+int nts_bin_overflow(nts_ctx* ctx, int slot, uint64_t* n)
+{
+    if (!ctx || !n) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    return owned_overflow(ctx, slot, n);
+}
+
+int nts_bin_ipc_handles(nts_ctx* ctx, int slot, uint8_t items_handle[64], uint8_t cursor_handle[64])
+{
+    if (!ctx || !items_handle || !cursor_handle) return fail(NTS_ERR_ARG, "null argument");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    void *it = nullptr, *cu = nullptr;
+    int rc = owned_buffers(ctx, slot, &it, &cu);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    NTS_CUDA(cudaIpcGetMemHandle(&h, it));
+    memcpy(items_handle, &h, 64);
+    NTS_CUDA(cudaIpcGetMemHandle(&h, cu));
+    memcpy(cursor_handle, &h, 64);
+    return NTS_OK;
+}
+
+int nts_binpeer_open(nts_ctx* ctx, const uint8_t* items_handles, const uint8_t* cursor_handles, int rank, int world, int slot,
+                     nts_binpeer** out)
+{
+    if (!ctx || !items_handles || !cursor_handles || !out || world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world)
+        return fail(NTS_ERR_ARG, "bad argument");
+    NTS_CUDA(cudaSetDevice(ctx->device));
+    nts_binpeer* p = new (std::nothrow) nts_binpeer();
+    if (!p) return fail(NTS_ERR_NOMEM, "host allocation failed");
+    p->ctx = ctx; p->rank = rank; p->world = world; p->slot = slot;
+    int rc = owned_buffers(ctx, slot, &p->items[rank], &p->cursor[rank]);
+    if (rc) { delete p; return rc; }
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, items_handles + (size_t)r * 64, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&p->items[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) {
+            memcpy(&h, cursor_handles + (size_t)r * 64, 64);
+            e = cudaIpcOpenMemHandle(&p->cursor[r], h, cudaIpcMemLazyEnablePeerAccess);
+        }
+        if (e != cudaSuccess) {
+            nts_binpeer_close(p);
+            return fail(NTS_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer buckets): ") + cudaGetErrorString(e));
+        }
+    }
+    *out = p;
+    return NTS_OK;
+}
+
+void nts_binpeer_close(nts_binpeer* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    for (int r = 0; r < p->world; ++r) {
+        if (r == p->rank) continue;
+        if (p->items[r]) cudaIpcCloseMemHandle(p->items[r]);
+        if (p->cursor[r]) cudaIpcCloseMemHandle(p->cursor[r]);
+    }
+    delete p;
+}
+
+/* bf[off16 .. off16 + n16) |= bits of the k-mers rank `source` binned (asynchronous on the context's stream; the caller
+ * orders it after the source's binning pass with a stream-ordered barrier) */
+int nts_bf_apply_owned(nts_bf* bf, nts_binpeer* p, int source, uint64_t off16, uint64_t n16)
+{
+    if (!bf || !p || source < 0 || source >= p->world || bf->ctx != p->ctx) return fail(NTS_ERR_ARG, "bad argument");
+    if ((off16 + n16) * 16 > bf->alloc_bytes) return fail(NTS_ERR_ARG, "range outside the filter");
+    NTS_CUDA(cudaSetDevice(p->ctx->device));
+    return owned_apply(p->ctx, p->slot, static_cast<const uint32_t*>(p->items[source]), static_cast<const unsigned int*>(p->cursor[source]),
+                       bf, off16, n16);
+}
+
+/* dst[off16 .. off16 + n16) op= src[same range], in units of 16 bytes: op 0 AND, 1 OR, 2 COPY; src null with op 2 = zero
+ * (asynchronous on the context's stream) */
+int nts_bf_range_op(nts_bf* dst, const nts_bf* src, uint64_t off16, uint64_t n16, int op)
+{
+    if (!dst || op < 0 || op > 2 || (!src && op != 2)) return fail(NTS_ERR_ARG, "bad argument");
+    if (src && (src->ctx != dst->ctx || src->bytes != dst->bytes)) return fail(NTS_ERR_ARG, "filters differ");
+    if ((off16 + n16) * 16 > dst->alloc_bytes) return fail(NTS_ERR_ARG, "range outside the filter");
+    NTS_CUDA(cudaSetDevice(dst->ctx->device));
+    return bf_range_op(dst->ctx, dst, src, off16, n16, op);
+}
+
+/* the slice of the filter rank `s` owns in nts_p2p_reduce_scatter / nts_p2p_all_gather (units of 16 bytes) */
+int nts_p2p_slice(const nts_p2p* p, int s, uint64_t* off16, uint64_t* n16)
+{
+    if (!p || !off16 || !n16 || s < 0 || s >= p->world) return fail(NTS_ERR_ARG, "bad argument");
+    slice_of(p, s, off16, n16);
     return NTS_OK;
 }
 

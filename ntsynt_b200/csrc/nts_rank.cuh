@@ -238,6 +238,8 @@ __global__ void __launch_bounds__(THREADS, 2) bf_rank_bin_kernel(GenomeView g, c
         const uint32_t x = W0[i];
         if (r < s_fit[b]) {
             bp.items[(uint64_t)s_dst[b] + r] = x;
+        } else if (bp.ovf_count) {
+            atomicAdd(bp.ovf_count, 1u);
         } else {                                                   // overflow (heavy hitters): apply directly
             const uint64_t idx = ((uint64_t)b << bp.region_shift) + x;
             atomicOr(&bits[idx >> 5], 1u << (idx & 31));

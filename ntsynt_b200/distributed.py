@@ -174,6 +174,103 @@ class ShardedMerge:
         self._sets, self._out = [], None
 
 
+class OwnedBuild:
+    """Common filter of a multi-GPU run WITHOUT building per-GPU filters and merging them (nts_bin_* / nts_bf_apply_owned):
+    every rank bins the k-mers it holds of genome g (pass 1 of the partitioned insert, one plan agreed by all ranks), a
+    stream-ordered barrier, then the rank that owns a slice of the filter applies the buckets of EVERY rank to that slice,
+    reading them over NVLink peer memory -- 4 bytes per k-mer on the wire instead of G x (P - 1) / P partial filters --,
+    ORs within the genome and ANDs across genomes on its slice; one all-gather distributes the finished filter.
+    `shards_of_genome[g]` = what this rank holds of genome g (a contig shard; or, with one genome per GPU, the whole
+    genome on its owner and None elsewhere).  Bucket scratch is double-buffered, so one barrier per genome suffices."""
+
+    SLOTS = (2, 3)          # scratch slots of their own (slot 0 belongs to the single-GPU insert)
+
+    def __init__(self, common, level, rank, world, k, plan_valid, gather, barrier, comm):
+        self.common, self.level, self.rank, self.world, self.k = common, level, rank, world, int(k)
+        self.comm, self.barrier = comm, barrier
+        ctx = common.ctx
+        self.ctx = ctx
+        self._peers = []
+        self._p2p = None
+        ok = True
+        try:
+            for slot in self.SLOTS:
+                check(lib.nts_bin_prepare(common._h, slot, int(plan_valid)))
+        except Exception:              # pylint: disable=broad-except
+            ok = False
+        ok = all(gather(ok))
+        if ok:
+            for slot in self.SLOTS:
+                hi, hc = (C.c_uint8 * 64)(), (C.c_uint8 * 64)()
+                check(lib.nts_bin_ipc_handles(ctx._h, slot, hi, hc))
+                got = gather((bytes(hi), bytes(hc)))
+                items = b"".join(x[0] for x in got)
+                curs = b"".join(x[1] for x in got)
+                h = C.c_void_p()
+                rc = lib.nts_binpeer_open(ctx._h, (C.c_uint8 * len(items)).from_buffer_copy(items),
+                                          (C.c_uint8 * len(curs)).from_buffer_copy(curs), int(rank), int(world), slot, C.byref(h))
+                ok = ok and rc == 0
+                self._peers.append(h if rc == 0 else None)
+            mine = (C.c_uint8 * 64)()
+            check(lib.nts_bf_ipc_handle(common._h, mine))
+            handles = b"".join(gather(bytes(mine)))
+            h = C.c_void_p()
+            rc = lib.nts_p2p_open(common._h, (C.c_uint8 * len(handles)).from_buffer_copy(handles), int(rank), int(world), C.byref(h))
+            ok = ok and rc == 0
+            self._p2p = h if rc == 0 else None
+        self.ok = all(gather(ok))
+        if self.ok:
+            off, n = C.c_uint64(), C.c_uint64()
+            check(lib.nts_p2p_slice(self._p2p, int(rank), C.byref(off), C.byref(n)))
+            self.off16, self.n16 = int(off.value), int(n.value)
+        else:
+            self.close()
+        barrier()
+
+    def build(self, shards_of_genome, genomes_are_sources=False):
+        """common := AND_g OR_rank bits; returns the number of k-mers (over all ranks: caller sums) that overflowed their
+        bucket -- if it is not zero on every rank the result is incomplete and the caller must fall back to a merge.
+        genomes_are_sources: one genome per GPU (shards_of_genome = [my genome]); every source is a genome of its own, so
+        the AND is taken across the sources instead of across the calls."""
+        lv, cm, off, n = self.level._h, self.common._h, self.off16, self.n16
+        first = True
+        for g, shard in enumerate(shards_of_genome):
+            slot = g & 1
+            check(lib.nts_bin_genome(cm, shard._h, self.k, self.SLOTS[slot]))
+            self.comm.barrier()                                  # every rank's buckets of this genome are complete
+            if not genomes_are_sources:
+                check(lib.nts_bf_range_op(lv, None, off, n, 2))                       # level[slice] = 0
+            for i in range(self.world):
+                s = (self.rank + i) % self.world                 # rotated: every source serves one reader at a time
+                if genomes_are_sources:
+                    check(lib.nts_bf_range_op(lv, None, off, n, 2))
+                check(lib.nts_bf_apply_owned(lv, self._peers[slot], s, off, n))
+                if genomes_are_sources:
+                    check(lib.nts_bf_range_op(cm, lv, off, n, 2 if first else 0))
+                    first = False
+            if not genomes_are_sources:
+                check(lib.nts_bf_range_op(cm, lv, off, n, 2 if first else 0))         # common[slice] = / &= level[slice]
+                first = False
+        self.comm.barrier()                                      # every slice is final (and nobody still reads my buckets)
+        check(lib.nts_p2p_all_gather(self._p2p))
+        self.comm.barrier()
+        over = 0
+        for slot in self.SLOTS:
+            n_over = C.c_uint64()
+            check(lib.nts_bin_overflow(self.ctx._h, slot, C.byref(n_over)))
+            over += int(n_over.value)
+        return over
+
+    def close(self):
+        for h in self._peers:
+            if h:
+                lib.nts_binpeer_close(h)
+        self._peers = []
+        if self._p2p:
+            lib.nts_p2p_close(self._p2p)
+            self._p2p = None
+
+
 def gather_sharded_table(comm, table, n_contigs, owner_of_contig, gather_objects, genome=None):
     """every rank sketched its own contigs of one genome (empty records elsewhere, global contig numbering): all-gather
     the tables and put the contigs back in order.  Returns the whole genome's table on this rank."""

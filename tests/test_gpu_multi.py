@@ -113,6 +113,20 @@ SHARD_WORKER = textwrap.dedent("""
         sm.merge(comm=comm if rep else None)
         assert np.array_equal(common.to_numpy(), ref.to_numpy()), "AND_g OR_rank over peer memory != single-GPU filter"
     sm.close()
+    # hash-range owned build: every rank only bins; the owner of a slice applies every rank's buckets over peer memory
+    lvl = ctx.bloom(nbytes)
+    plan = int(d.max(max(int(x.total_bases) for x in shards)))
+    os.environ["NTS_BF_REGION_SHIFT"] = "22"          # 2^22-bit regions: 40 of them, slices cut through regions
+    ob = distributed.OwnedBuild(common, lvl, d.rank, d.world, k, plan, d.gather_objects, d.barrier, comm)
+    del os.environ["NTS_BF_REGION_SHIFT"]
+    assert ob.ok
+    for rep in range(2):
+        common.from_numpy(np.full(nbytes, 0xA5, dtype=np.uint8))
+        lvl.from_numpy(np.full(nbytes, 0x3C, dtype=np.uint8))
+        over = ob.build(shards)
+        assert over == 0
+        assert np.array_equal(common.to_numpy(), ref.to_numpy()), "owned build != single-GPU filter"
+    ob.close()
     # the north-star form: one counter all-reduce per genome, AND locally
     for g in range(G):
         parts[g].set_genome(shards[g], k)
