@@ -306,6 +306,8 @@ def run_ours(args, dist):
     my_ids = list(range(G)) if N == 1 else [g for g in range(G) if g % N == dist.rank]
     if N > 1:
         shard = args.shard or ("genome" if G % N == 0 else "contig")
+        if args.merge is None:
+            args.merge = "owned" if shard == "contig" else "p2p"
         return run_ours_sharded(args, dist, ctx) if shard == "contig" else run_ours_multi(args, dist, ctx)
     gens = {g: wl.materialize(ctx, g) for g in my_ids}
     total_bp = sum(int(x.total_bases) for x in gens.values())
@@ -516,7 +518,7 @@ def run_ours_multi(args, dist, ctx):
     peer = distributed.PeerMerge(mine, rank, N, dist.gather_objects, dist.barrier) if N <= 16 else None
     if peer is not None and not peer.ok:           # no peer access on some rank: the NCCL form is the fallback
         peer = None
-    use_p2p = args.merge == "p2p" and peer is not None
+    use_p2p = args.merge in ("p2p", "owned") and peer is not None     # (owned not available: the peer-memory merge)
 
     phase = {}
 
@@ -715,7 +717,7 @@ def run_ours_sharded(args, dist, ctx):
             if owned is None and N <= 16 and G <= 8 else None)
     if peer is not None and not peer.ok:
         peer = None
-    use_p2p = args.merge == "p2p" and peer is not None
+    use_p2p = args.merge in ("p2p", "owned") and peer is not None     # (owned not available: the peer-memory merge)
     phase = {}
 
     def tick(name, t0):
@@ -911,12 +913,12 @@ def main():
     ap.add_argument("--shard", choices=["genome", "contig"], default=None,
                     help="multi-GPU ownership: one genome per GPU (default when --genomes is a multiple of --gpus) or the "
                          "contigs of every genome spread over the GPUs (default otherwise: BASELINE configs 3 and 4)")
-    ap.add_argument("--merge", choices=["nccl", "p2p", "owned"], default="p2p",
+    ap.add_argument("--merge", choices=["nccl", "p2p", "owned"], default=None,
                     help="multi-GPU filter merge: peer-memory reduce-scatter/all-gather kernels over NVLink (default; "
                          "bit-identical and ~4x less wire volume), NCCL all-reduce(sum) of packed counters (the "
                          "north-star form; also timed alone in config.merge_alone_ms), or -- contig-sharded runs -- no "
                          "merge at all: hash-range owned build (every GPU bins, the owner of a filter slice applies "
-                         "every GPU's buckets over peer memory)")
+                         "every GPU's buckets over peer memory).  Default: owned for contig-sharded runs, p2p otherwise")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: fewer than 3 warm-up steps; the number is not reportable", file=sys.stderr)
