@@ -53,6 +53,19 @@ WORKER = textwrap.dedent("""
         pm.merge("and", comm=comm)
     assert np.array_equal(pm_bf.to_numpy(), ref.to_numpy()), "peer-memory merge (stream barriers) != AND"
     pm.close()
+    # one genome per GPU WITHOUT per-GPU filters: every rank bins its genome, the owner of a slice applies every rank's
+    # buckets (each source is a genome of its own: AND across the sources)
+    ob_c, ob_l = ctx.bloom(nbytes), ctx.bloom(nbytes)
+    os.environ["NTS_BF_REGION_SHIFT"] = "22"
+    ob = distributed.OwnedBuild(ob_c, ob_l, d.rank, d.world, k, int(d.max(int(gens[d.rank].total_bases))), d.gather_objects,
+                                d.barrier, comm)
+    del os.environ["NTS_BF_REGION_SHIFT"]
+    assert ob.ok
+    for rep in range(2):
+        ob_c.from_numpy(np.full(nbytes, 0x77, dtype=np.uint8))
+        assert ob.build([gens[d.rank]], genomes_are_sources=True) == 0
+        assert np.array_equal(ob_c.to_numpy(), ref.to_numpy()), "owned build (one genome per GPU) != AND"
+    ob.close()
     t = ctx.sketch(gens[d.rank], k, 1000, common=mine)
     counts = d.gather_objects(len(t))
     tabs = comm.allgather_tables(t, counts, gens)
