@@ -760,8 +760,10 @@ def run_ours_sharded(args, dist, ctx):
                                              masked_sketch=lambda a, w_, masks: svc.sketch(order[a], w_, masks))
             eng = SyntenyEngine(be, K, W, ps["w_rounds"], ps["indel"], ps["merge"], ps["block_size"], write_files=False,
                                 quiet=True)
-            text = eng.run()
-            svc.done()
+            try:
+                text = eng.run()
+            finally:
+                svc.done()                                         # (the other ranks sit in serve(): never leave them there)
             be.close()
         else:
             svc.serve()
