@@ -52,6 +52,46 @@ WORKER = textwrap.dedent("""
     # rank 0's command reaches rank 1 (the side channel of distributed.ShardedSketcher)
     cmd = d.bcast_object(("sketch", 2, 250, [np.arange(3)]) if d.rank == 0 else None)
     assert cmd[0] == "sketch" and cmd[1] == 2 and cmd[2] == 250 and cmd[3][0].tolist() == [0, 1, 2]
+    # ShardedSketcher protocol and gather_sharded_table's contig re-ordering, with stand-ins for the device tables:
+    # rank 0 asks for two sketches, rank 1 serves them, both see the whole genome's rows in contig order
+    from ntsynt_b200 import device
+    n_contigs, owner = 5, [0, 1, 1, 0, 1]
+    class Tab:
+        def __init__(self, rows): self.rows = rows                    # list of (contig, value)
+        def __len__(self): return len(self.rows)
+        def contig_offsets(self, n):
+            cnt = np.bincount([c for c, _ in self.rows], minlength=n)
+            return np.concatenate([[0], np.cumsum(cnt)])
+        def close(self): pass
+    class Comm:
+        world, ctx = d.world, None
+        def allgather_tables(self, t, sizes, _):
+            got = d.gather_objects(t.rows)
+            assert [len(x) for x in got] == sizes
+            return [Tab(x) for x in got]
+    class Ctx:
+        def sketch(self, shard, k, w, common=None, masks=None):
+            # rows of my contigs only; the value encodes (genome, w, mask) so a mixed-up command would show
+            return Tab([(c, (shard, w, int(masks[c]), i)) for c in range(n_contigs) if owner[c] == d.rank for i in range(c + 1)])
+    def concat(ctx, parts, src, cnt, genome):
+        return Tab([row for p_, s_, n_ in zip(parts, src, cnt) for row in p_.rows[s_:s_ + n_]])
+    device.MinimizerTable.concat = staticmethod(concat)
+    seen = []
+    svc = distributed.ShardedSketcher(Comm(), Ctx(), ["g0", "g1"], 24, None, n_contigs, owner, d.bcast_object, d.gather_objects)
+    real_do = svc._do
+    def spy(g, w, masks):
+        out = real_do(g, w, masks); seen.append((g, w, out.rows)); return out
+    svc._do = spy
+    if d.rank == 0:
+        m = np.arange(10, 15)
+        a = svc.sketch(1, 250, m)
+        b = svc.sketch(0, 100, m + 5)
+        svc.done()
+    else:
+        svc.serve()
+    assert [(g, w) for g, w, _ in seen] == [(1, 250), (0, 100)]
+    for (g, w, rows), base in zip(seen, (10, 15)):
+        assert rows == [(c, ("g%d" % g, w, base + c, i)) for c in range(n_contigs) for i in range(c + 1)]
     d.barrier(); d.close()
     print("rank", d.rank, "ok")
 """)
