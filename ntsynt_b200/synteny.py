@@ -39,6 +39,9 @@ import numpy as np
 FA_TSV_RE = re.compile(r"^(\S+)\.k\d+\.w\d+.tsv")
 
 
+_NO_U64 = np.zeros(0, dtype=np.uint64)
+
+
 def _log(*a):
     print(datetime.datetime.today(), ":", *a, file=sys.stdout, flush=True)
 
@@ -1142,7 +1145,7 @@ class SyntenyEngine:
         self._tick("bh_c")
         segs = list(zip(o_lo[:no].tolist(), o_hi[:no].tolist(), o_dir[:no].tolist()))
         off = b_off[:nb + 1].tolist()
-        ori = [[chr(c) for c in row] for row in b_ori[:nb].tolist()]
+        ori = b_ori[:nb].view("S1").astype("U1").tolist()             # '+' / '-' per assembly
         ctg_l, fp, lp = b_ctg[:nb].tolist(), b_fpos[:nb].tolist(), b_lpos[:nb].tolist()
         blocks = [Block(segs[off[i]:off[i + 1]], ctg_l[i], ori[i], f, l, fp[i], lp[i], n)
                   for i, (f, l, n) in enumerate(zip(b_first[:nb].tolist(), b_last[:nb].tolist(), b_n[:nb].tolist()))]
@@ -1202,7 +1205,7 @@ class SyntenyEngine:
             pos = self.POS[:, both]
             ctg_f = self.CTG[:, f_id].T.tolist()
             pos_f, pos_l = pos[:, :len(lo)].T.tolist(), pos[:, len(lo):].T.tolist()
-            ori = [["+" if (p >> a) & 1 else "-" for a in range(self.G)] for p in plus.tolist()]
+            ori = np.where((plus.astype(np.int64)[:, None] >> np.arange(self.G)) & 1, "+", "-").tolist()
             for i, (l_, h_, u_, f_, e_) in enumerate(zip(lo.tolist(), hi.tolist(), up.tolist(), f_id.tolist(), l_id.tolist())):
                 blocks.append(Block([(l_, h_, 1 if u_ else -1)], ctg_f[i], ori[i], f_, e_, pos_f[i], pos_l[i], h_ - l_ + 1))
         self._tick("b_make")
@@ -1373,18 +1376,19 @@ class SyntenyEngine:
             o = np.lexsort((e2, s2, c2))
             s2, e2, c2 = s2[o], e2[o], c2[o]
             # union per contig (bedtools maskfasta semantics): an interval starts a new run unless it begins at or
-            # before the furthest end seen so far in its contig
-            lst = [(np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64)) for _ in self.be.contig_names[a]]
+            # before the furthest end seen so far in its contig.  All contigs at once on one axis (contig << 40 | pos):
+            # a contig's intervals lie above everything of the contigs before it, so one running maximum serves all
+            lst = [(_NO_U64, _NO_U64)] * len(self.be.contig_names[a])
             if len(s2):
-                cb = np.flatnonzero(np.r_[True, c2[1:] != c2[:-1]])           # first interval of each contig
-                ce = np.r_[cb[1:], len(c2)]
-                for i0, i1 in zip(cb.tolist(), ce.tolist()):
-                    ss, ee = s2[i0:i1], e2[i0:i1]
-                    run_max = np.maximum.accumulate(ee)
-                    new_run = np.r_[True, ss[1:] > run_max[:-1]]
-                    heads = np.flatnonzero(new_run)
-                    ends_ = run_max[np.r_[heads[1:] - 1, len(ss) - 1]]
-                    lst[int(c2[i0])] = (ss[heads].astype(np.uint64), ends_.astype(np.uint64))
+                base = c2 << np.int64(40)
+                run_max = np.maximum.accumulate(e2 + base)
+                heads = np.flatnonzero(np.r_[True, (s2 + base)[1:] > run_max[:-1]])
+                ends_ = (run_max[np.r_[heads[1:] - 1, len(s2) - 1]] - base[heads]).astype(np.uint64)
+                starts_ = s2[heads].astype(np.uint64)
+                ch = c2[heads]
+                cb = np.flatnonzero(np.r_[True, ch[1:] != ch[:-1]])           # first run of each contig
+                for c_, i0, i1 in zip(ch[cb].tolist(), cb.tolist(), np.r_[cb[1:], len(ch)].tolist()):
+                    lst[c_] = (starts_[i0:i1], ends_[i0:i1])
             masks.append(lst)
         return masks
 
@@ -1540,9 +1544,15 @@ class SyntenyEngine:
             # pass 1: which base vertices get a new position / contig (assembly a only writes row a)
             touched, changed_per_asm = [], []
             cur_P, cur_C = self.POS[:, cid], self.CTG[:, cid]                     # one gather each, in `common` order
+            ar_ = np.arange(len(common))
             for a in range(G):
                 kh, kp, kc, _ = lists[a]
-                j_ = np.searchsorted(common, kh)
+                # every list holds exactly the common keys, each once: its rank order IS the index into `common`
+                # (an argsort and a scatter instead of a binary search per key)
+                if len(kh) != len(common):
+                    raise RuntimeError("internal error: a filtered minimizer list is not a permutation of the common keys")
+                j_ = np.empty(len(kh), dtype=np.int64)
+                j_[np.argsort(kh)] = ar_
                 vid = cid[j_]
                 cur_c = cur_C[a, j_]
                 changed = (cur_P[a, j_] != kp) | (cur_c != kc)
@@ -1582,12 +1592,22 @@ class SyntenyEngine:
         S = np.concatenate(S) if S else np.zeros(0, dtype=np.int64)
         T = np.concatenate(T) if T else np.zeros(0, dtype=np.int64)
         lo_, hi_ = np.minimum(S, T), np.maximum(S, T)
-        _, first_ix, cnt_ = np.unique((lo_ << np.int64(32)) | hi_, return_index=True, return_counts=True)
-        eo = np.argsort(first_ix, kind="stable")
+        # distinct pairs with their first appearance and multiplicity: an (unstable) argsort of the keys, group
+        # boundaries, and the smallest original index of every group
+        ekey = (lo_ << np.int64(32)) | hi_
+        if len(ekey):
+            so_ = np.argsort(ekey)
+            ks_ = ekey[so_]
+            gb = np.flatnonzero(np.r_[True, ks_[1:] != ks_[:-1]])
+            first_ix = np.minimum.reduceat(so_, gb)
+            cnt_ = np.diff(np.r_[gb, len(ks_)])
+        else:
+            first_ix = cnt_ = np.zeros(0, dtype=np.int64)
+        eo = np.argsort(first_ix)
         first_ix, cnt_ = first_ix[eo], cnt_[eo]
         eu, ev = lo_[first_ix], hi_[first_ix]                           # distinct new pairs in insertion order
         # add_vertices: new (or previously deleted) vertices, except the blocks' terminal minimizers
-        allv = np.unique(np.concatenate(ids_per_asm)) if ids_per_asm else np.zeros(0, dtype=np.int64)
+        allv = np.sort(cid) if len(common) else np.zeros(0, dtype=np.int64)     # every list names the same vertices
         if len(allv):
             term_arr = np.unique(self.H[term_ids]) if len(term_ids) else np.zeros(0, dtype=np.uint64)
             revive = allv[~self.alive[allv] & ~np.isin(self.H[allv], term_arr)]
@@ -1727,6 +1747,11 @@ class SyntenyEngine:
         la = np.array(low, dtype=np.int64).reshape(-1, 2)
         both1 = ((self.nbr[la[:, 0]] >= 0).sum(axis=1) == 1) & ((self.nbr[la[:, 1]] >= 0).sum(axis=1) == 1)
         sel = la[both1]
+        if len(sel):
+            # the walk of a pair starts only if its two vertices are less than k apart in some assembly: that first
+            # test for all pairs at once, the walk for the few that pass it
+            P = np.asarray(self.POS[:, sel.ravel()], dtype=np.int64).reshape(self.G, -1, 2)
+            sel = sel[(np.abs(P[:, :, 0] - P[:, :, 1]) < self.k).any(axis=0)]
         hv = self.H[sel.ravel()].reshape(-1, 2) if len(sel) else np.zeros((0, 2), dtype=np.uint64)
         if self._dev is not None and len(sel):
             # positions around the flagged pairs in one gather (the walk below reads them one vertex at a time)
@@ -1764,6 +1789,19 @@ class SyntenyEngine:
 
     # ------------------------------------------------------------------ driver (main_synteny :593-647)
     def run(self):
+        """the whole graph stage.  The cyclic collector is paused for its duration: the stage makes a few hundred
+        thousand small objects and no reference cycles, and one full collection in a process with large libraries
+        loaded costs tens of milliseconds"""
+        import gc
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            return self._run()
+        finally:
+            if was_enabled:
+                gc.enable()
+
+    def _run(self):
         G = self.G
         if len(self.w_rounds) != len(set(self.w_rounds)):
             print("Error: duplicate values found in w_rounds!", file=sys.stderr, flush=True)
