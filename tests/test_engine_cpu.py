@@ -140,3 +140,43 @@ def test_numpy_join_semantics():
     assert list(POS[0]) == [40, 30, 0] and list(POS[1]) == [0, 10, 20]
     assert list(RANK[0]) == [2, 1, 0]
     assert list(link) == [1, 1, 0]
+
+
+def test_block_masks_match_a_bruteforce_union():
+    "get_synteny_bed_lists + slop + maskfasta (bin/ntsynt_synteny.py:117-157): per contig, the union of the shrunk block extents"
+    import types
+    from ntsynt_b200.synteny import Block
+    rng = np.random.default_rng(11)
+    G, k, prev_w, n_ctg = 3, 24, 100, 6
+    lens = [[int(x) for x in rng.integers(20000, 60000, n_ctg)] for _ in range(G)]
+    eng = SyntenyEngine.__new__(SyntenyEngine)
+    eng.G, eng.k = G, k
+    eng.be = types.SimpleNamespace(contig_names=[[f"c{c}" for c in range(n_ctg)]] * G, contig_lengths=lens)
+    blocks = []
+    for _ in range(400):
+        ctg = [int(c) for c in rng.integers(0, n_ctg - 1, G)]          # the last contig never gets a block
+        fp = [int(rng.integers(0, lens[a][ctg[a]])) for a in range(G)]
+        lp = [int(f + rng.integers(-3000, 3000)) for f in fp]          # some shorter than the threshold, some reach past the end
+        blocks.append(Block(None, ctg, ["+"] * G, 0, 0, fp, lp, 5))
+    masks = eng._masks_for(blocks, prev_w)
+    thr, shrink = max(2 * prev_w, prev_w + k + 1), prev_w + k
+    assert len(masks) == G
+    for a in range(G):
+        assert len(masks[a]) == n_ctg and len(masks[a][n_ctg - 1][0]) == 0
+        for c in range(n_ctg):
+            want = np.zeros(lens[a][c] + 4000, dtype=bool)
+            for b in blocks:
+                if b.ctg[a] != c:
+                    continue
+                s, e = min(b.first_pos[a], b.last_pos[a]), max(b.first_pos[a], b.last_pos[a]) + k
+                if e - s > thr:
+                    s2, e2 = max(s + shrink, 0), min(e - shrink, lens[a][c])
+                    if s2 < e2:
+                        want[s2:e2] = True
+            got = np.zeros_like(want)
+            ss, ee = masks[a][c]
+            assert ss.dtype == np.uint64 and ee.dtype == np.uint64
+            assert (ss[1:] > ee[:-1]).all()                             # sorted, disjoint, not even touching
+            for s, e in zip(ss.tolist(), ee.tolist()):
+                got[s:e] = True
+            assert np.array_equal(got, want)
