@@ -180,3 +180,15 @@ def test_block_masks_match_a_bruteforce_union():
             for s, e in zip(ss.tolist(), ee.tolist()):
                 got[s:e] = True
             assert np.array_equal(got, want)
+
+
+def test_randomised_cases_engine_equals_graph_oracle():
+    """the three vertex-storage forms of the engine against oracle/graph_oracle.py on cases that draw the genome count (2-6),
+    rearrangements, N runs, k, w, the rounds (none to three), --indel, --collinear-merge, -z and --simplify-graph at random
+    (scripts/fuzz_graph_stage.py engine)"""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "fuzz_graph_stage.py")
+    spec = importlib.util.spec_from_file_location("fuzz_graph_stage", path)
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    assert all(fz.check_seed("engine", seed) for seed in range(1000, 1012))

@@ -82,3 +82,25 @@ def test_presets_fixture_is_what_the_reference_writes(tag, tmp_path):
     assert res["returncode"] == 0, res["log"][-2000:]
     assert open(res["blocks"], encoding="utf-8").read() == pc.expected(tag)
     assert open(res["pre_merge"], encoding="utf-8").read() == pc.expected(tag, "pre-collinear-merge.synteny_blocks.tsv")
+
+
+def _fuzz_module():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "fuzz_graph_stage.py")
+    spec = importlib.util.spec_from_file_location("fuzz_graph_stage", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_randomised_cases_graph_oracle_equals_the_reference():
+    """build container only: oracle/graph_oracle.py against the reference's own bin/ntsynt_run.py on cases that draw the
+    genome count, rearrangements, k, w, rounds, --indel, --collinear-merge, -z and --simplify-graph at random
+    (scripts/fuzz_graph_stage.py oracle; several hundred seeds were run when the oracle was pinned, a few are kept here)"""
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("needs /root/reference (build container)")
+    fz = _fuzz_module()
+    got = [fz.check_seed("oracle", seed) for seed in range(2000, 2008)]
+    assert got.count(True) >= 4 and False not in got
