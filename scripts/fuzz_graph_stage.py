@@ -5,6 +5,8 @@
                                                                            forms, fed by the test backend) vs oracle/graph_oracle.py
     python scripts/fuzz_graph_stage.py oracle  <first seed> <last seed>    oracle/graph_oracle.py vs the reference's OWN
                                                                            bin/ntsynt_run.py under oracle/ref_harness.py (build container only)
+    python scripts/fuzz_graph_stage.py direct  <first seed> <last seed>    product engine vs the reference's own code, with
+                                                                           --filter Filter | Indexlr | none drawn as well
 
 Every seed draws the number of genomes (2-6), contigs, divergence, indels, inversions, translocations, duplications, N
 runs, soft-masking, k, w, the refinement rounds, --indel, --collinear-merge, -z and --simplify-graph.  TEST INFRASTRUCTURE:
@@ -61,7 +63,7 @@ def run_oracle(paths, par, bits):
     return go.outputs
 
 
-def engine_outputs(paths, par):
+def engine_outputs(paths, par, forms=("dev", True, False), repeat_bits=None, filter_mode=None):
     "the product engine in its three vertex-storage forms; returns ([outputs per form], common filter bits)"
     from backends import OracleBackend
     from ntsynt_b200.synteny import SyntenyEngine
@@ -69,8 +71,9 @@ def engine_outputs(paths, par):
     tsv = [f"{os.path.basename(p)}.k{k}.w{w}.tsv" for p in paths]
     order = sorted(range(len(paths)), key=lambda i: tsv[i], reverse=True)
     outs = []
-    for lean in ("dev", True, False):
-        be = OracleBackend([paths[i] for i in order], [tsv[i] for i in order], k, lean=lean)
+    for lean in forms:
+        be = OracleBackend([paths[i] for i in order], [tsv[i] for i in order], k, lean=lean, repeat_bits=repeat_bits,
+                           filter_mode=filter_mode)
         eng = SyntenyEngine(be, k, w, par["w_rounds"], par["indel"], par["merge"], par["z"], write_files=False, quiet=True,
                             simplify=par["simplify"])
         try:
@@ -81,11 +84,14 @@ def engine_outputs(paths, par):
     return outs, be.bits
 
 
-def reference_outputs(paths, par, tmp):
+def reference_outputs(paths, par, tmp, filter_mode=None):
     from oracle import ref_harness
     res = ref_harness.run_reference(paths, os.path.join(tmp, "wd"), "fz", k=par["k"], w=par["w"], w_rounds=par["w_rounds"],
-                                    indel=par["indel"], merge=par["merge"], block_size=par["z"], simplify=par["simplify"])
-    return {key: (open(f).read() if os.path.exists(f) else None) for key, f in (("final", res["blocks"]), ("pre_merge", res["pre_merge"]))}
+                                    indel=par["indel"], merge=par["merge"], block_size=par["z"], simplify=par["simplify"],
+                                    filter_mode=filter_mode, repeat_fpr=0.1 if filter_mode else None)
+    out = {key: (open(f).read() if os.path.exists(f) else None) for key, f in (("final", res["blocks"]), ("pre_merge", res["pre_merge"]))}
+    out["repeat_bits"] = res["repeat_bits"]
+    return out
 
 
 def check_seed(mode, seed):
@@ -101,6 +107,12 @@ def check_seed(mode, seed):
             return all(o.get(kk) == want.get(kk) for o in outs for kk in keys)
         if not par["w_rounds"]:
             return None                # bin/ntsynt_run.py always runs refinement rounds
+        if mode == "direct":
+            filter_mode = [None, "Filter", "Indexlr"][seed % 3]
+            ref = reference_outputs(paths, par, tmp, filter_mode)
+            outs, _ = engine_outputs(paths, par, forms=(["dev", False][seed % 2],), repeat_bits=ref["repeat_bits"],
+                                     filter_mode=filter_mode)
+            return all(outs[0].get(kk) == ref[kk] for kk in keys)
         ref = reference_outputs(paths, par, tmp)
         bits = so.common_bf([(os.path.basename(p), so.read_fasta(p)) for p in paths], par["k"], 0.025)
         want = run_oracle(paths, par, bits)
@@ -111,7 +123,7 @@ def check_seed(mode, seed):
 
 def main():
     mode, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    assert mode in ("engine", "oracle")
+    assert mode in ("engine", "oracle", "direct")
     t0, bad, n = time.time(), 0, 0
     for seed in range(lo, hi):
         ok = check_seed(mode, seed)
