@@ -112,7 +112,7 @@ class GraphOracle:
     records = [(contig, seq_bytes)]; order as given by the user (re-sorted like the reference)."""
 
     def __init__(self, genomes, k, w, w_rounds, bp, collinear_merge, z, common, m=90, simplify=True,
-                 restart_on_gap=False):
+                 restart_on_gap=False, n=0):
         self.k, self.w, self.w_rounds, self.bp, self.z, self.m = k, w, list(w_rounds), bp, z, m
         cm = str(collinear_merge)
         self.collinear_merge = int(cm[:-1]) * w if cm.endswith("w") else int(cm)
@@ -121,7 +121,7 @@ class GraphOracle:
         self.genomes = dict(genomes)
         self.files = sorted(self.genomes, reverse=True)          # bin/ntsynt_synteny.py:34
         self.weights = {f: 1 for f in self.files}
-        self.n = len(self.files)
+        self.n = n or len(self.files)                            # -n, minimum edge weight (bin/ntsynt_synteny.py:46-47)
         self.info, self.lists = {}, {}
         self.graph = None
         self.outputs = {}
@@ -264,6 +264,8 @@ class GraphOracle:
 
     def weight_filter(self, graph, flag=False):
         "subprojects/ntJoin/bin/ntjoin.py:78-87; bin/ntsynt_synteny.py:292-303"
+        if not flag and self.n <= min(self.weights.values()):
+            return graph
         low = [e.index for e in graph.es if e["weight"] < self.n]
         pairs = [(graph.es[i].source, graph.es[i].target) for i in low]
         g = graph.copy()
@@ -271,22 +273,30 @@ class GraphOracle:
         return (g, pairs) if flag else g
 
     def find_paths(self):
-        "subprojects/ntJoin/bin/ntjoin.py:89-151 (n = number of assemblies: the branch loop is a no-op)"
+        """subprojects/ntJoin/bin/ntjoin.py:68-76,89-151.  With n = number of assemblies every component is linear already;
+        below that, edges lighter than a rising threshold are taken off the branch vertices of a component until it is"""
         ref = self.files[-1]       # .pop() of the equally weighted assemblies
         out = []
         for comp in self.graph.components():
-            sub = self.graph.subgraph(comp)
-            if any(v.degree() > 2 for v in sub.vs):
-                raise NotImplementedError("branching component: only -n = #assemblies is restated")
-            ends = [v.index for v in sub.vs if v.degree() == 1]
-            if len(ends) != 2:
-                continue
-            pos = [self.info[ref][sub.vs[v]["name"]][1] for v in ends]
-            src = [v for v, p in zip(ends, pos) if p == min(pos)].pop()
-            dst = [v for v, p in zip(ends, pos) if p == max(pos)].pop()
-            path = sub.get_shortest_paths(src, dst)[0]
-            if len(path) == sub.vcount() and len(path) - 1 == sub.ecount() and len(set(path)) == len(path):
-                out.append([sub.vs[v]["name"] for v in path])
+            whole = self.graph.subgraph(comp)
+            floor, top = self.n, sum(self.weights.values())
+            while any(v.degree() > 2 for v in whole.vs) and floor <= top:
+                light = [e for v in whole.vs if v.degree() > 2 for e in whole.incident(v.index) if whole.es[e]["weight"] < floor]
+                g = whole.copy()
+                g.delete_edges(light)
+                whole = g
+                floor += 1
+            for part in whole.components():
+                sub = whole.subgraph(part)
+                ends = [v.index for v in sub.vs if v.degree() == 1]
+                if len(ends) != 2:
+                    continue
+                pos = [self.info[ref][sub.vs[v]["name"]][1] for v in ends]
+                src = [v for v, p in zip(ends, pos) if p == min(pos)].pop()
+                dst = [v for v, p in zip(ends, pos) if p == max(pos)].pop()
+                path = sub.get_shortest_paths(src, dst)[0]
+                if len(path) == sub.vcount() and len(path) - 1 == sub.ecount() and len(set(path)) == len(path):
+                    out.append([sub.vs[v]["name"] for v in path])
         return out
 
     def _blocks(self):

@@ -77,7 +77,7 @@ def stage_fasta(src, workdir):
 
 def run_reference(fastas, workdir, prefix, k=24, w=1000, w_rounds=(100, 10), indel=10000, merge="10000",
                   block_size=500, fpr=0.025, simplify=True, common=True, restart_on_gap=False, quiet=True,
-                  filter_mode=None, repeat_fpr=None, interarrivals=False, dev=False):
+                  filter_mode=None, repeat_fpr=None, interarrivals=False, dev=False, n=0):
     """Full ntSynt run = oracle BF + oracle sketches + the reference's ntsynt_run.py.
     `fastas`: paths (may be .gz).  Mirrors bin/ntsynt_run_pipeline.smk:44-103.
     Returns dict of output paths."""
@@ -130,6 +130,8 @@ def run_reference(fastas, workdir, prefix, k=24, w=1000, w_rounds=(100, 10), ind
         cmd += ["--filter", filter_mode, "--repeat", rep_path]
     if interarrivals:
         cmd += ["--interarrivals"]
+    if n:
+        cmd += ["-n", str(n)]
     if dev:
         cmd += ["--dev"]
     res = subprocess.run(cmd, cwd=workdir, env=env, stdout=subprocess.PIPE if quiet else None,

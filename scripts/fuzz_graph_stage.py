@@ -5,6 +5,9 @@
                                                                            forms, fed by the test backend) vs oracle/graph_oracle.py
     python scripts/fuzz_graph_stage.py oracle  <first seed> <last seed>    oracle/graph_oracle.py vs the reference's OWN
                                                                            bin/ntsynt_run.py under oracle/ref_harness.py (build container only)
+    python scripts/fuzz_graph_stage.py oracle-n <first seed> <last seed>   the same with -n (minimum edge weight) drawn below the
+                                                                           number of assemblies: the branch-resolution loop of
+                                                                           ntjoin.py:68-76,114-123 (restated in the oracle only)
     python scripts/fuzz_graph_stage.py direct  <first seed> <last seed>    product engine vs the reference's own code, with
                                                                            --filter Filter | Indexlr | none drawn as well
 
@@ -53,9 +56,9 @@ def write_case(gens, tmp):
     return paths
 
 
-def run_oracle(paths, par, bits):
+def run_oracle(paths, par, bits, n=0):
     go = GraphOracle([(os.path.basename(p) + f".k{par['k']}.w{par['w']}.tsv", so.read_fasta(p)) for p in paths], par["k"], par["w"],
-                     par["w_rounds"], par["indel"], par["merge"], par["z"], bits, simplify=par["simplify"])
+                     par["w_rounds"], par["indel"], par["merge"], par["z"], bits, simplify=par["simplify"], n=n)
     try:
         go.run()
     except SystemExit:                 # "no paths found"
@@ -84,11 +87,13 @@ def engine_outputs(paths, par, forms=("dev", True, False), repeat_bits=None, fil
     return outs, be.bits
 
 
-def reference_outputs(paths, par, tmp, filter_mode=None):
+def reference_outputs(paths, par, tmp, filter_mode=None, n=0):
     from oracle import ref_harness
     res = ref_harness.run_reference(paths, os.path.join(tmp, "wd"), "fz", k=par["k"], w=par["w"], w_rounds=par["w_rounds"],
                                     indel=par["indel"], merge=par["merge"], block_size=par["z"], simplify=par["simplify"],
-                                    filter_mode=filter_mode, repeat_fpr=0.1 if filter_mode else None)
+                                    filter_mode=filter_mode, repeat_fpr=0.1 if filter_mode else None, n=n)
+    if res["returncode"] != 0 and "no paths found" not in res["log"]:
+        raise RuntimeError("the reference run failed:\n" + res["log"][-2000:])
     out = {key: (open(f).read() if os.path.exists(f) else None) for key, f in (("final", res["blocks"]), ("pre_merge", res["pre_merge"]))}
     out["repeat_bits"] = res["repeat_bits"]
     return out
@@ -113,9 +118,14 @@ def check_seed(mode, seed):
             outs, _ = engine_outputs(paths, par, forms=(["dev", False][seed % 2],), repeat_bits=ref["repeat_bits"],
                                      filter_mode=filter_mode)
             return all(outs[0].get(kk) == ref[kk] for kk in keys)
-        ref = reference_outputs(paths, par, tmp)
+        n = 0
+        if mode == "oracle-n":
+            if len(gens) < 3:
+                return None
+            n = 1 + seed % (len(gens) - 1)
+        ref = reference_outputs(paths, par, tmp, n=n)
         bits = so.common_bf([(os.path.basename(p), so.read_fasta(p)) for p in paths], par["k"], 0.025)
-        want = run_oracle(paths, par, bits)
+        want = run_oracle(paths, par, bits, n=n)
         return all(ref[kk] == want.get(kk) for kk in keys)
     finally:
         shutil.rmtree(tmp)
@@ -123,7 +133,7 @@ def check_seed(mode, seed):
 
 def main():
     mode, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    assert mode in ("engine", "oracle", "direct")
+    assert mode in ("engine", "oracle", "oracle-n", "direct")
     t0, bad, n = time.time(), 0, 0
     for seed in range(lo, hi):
         ok = check_seed(mode, seed)

@@ -104,6 +104,9 @@ def test_randomised_cases_graph_oracle_equals_the_reference():
     fz = _fuzz_module()
     got = [fz.check_seed("oracle", seed) for seed in range(2000, 2008)]
     assert got.count(True) >= 4 and False not in got
+    # -n below the number of assemblies (branch-resolution loop of ntjoin.py:68-76,114-123; oracle only)
+    got = [fz.check_seed("oracle-n", seed) for seed in range(5000, 5006)]
+    assert got.count(True) >= 3 and False not in got
     # and the product's host engine against the reference directly, --filter Filter | Indexlr | none drawn with the case
     got = [fz.check_seed("direct", seed) for seed in range(3000, 3006)]
     assert got.count(True) >= 3 and False not in got
