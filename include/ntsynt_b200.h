@@ -412,6 +412,12 @@ int nts_fasta_scan(const char* buf, uint64_t n, uint64_t cap, uint64_t* name_off
 int nts_fasta_scan_mt(const char* buf, uint64_t n, uint64_t cap, uint64_t* name_off, uint32_t* name_len, uint64_t* n_bases,
                    uint64_t* seq_off, uint64_t* seq_end, uint32_t* linebases, uint32_t* linewidth, uint8_t* uniform,
                    uint64_t* n_records, uint32_t n_threads);
+/* nts_gz_inflate: gzip bytes (one member or several, zero padding after a member allowed) -> plain bytes, whole buffer in,
+ * whole buffer out; the decompressor in front of the FASTA reader (btllib::SeqReader pipes .gz input through one,
+ * src/ntsynt_make_common_bf.cpp:32-36,125,143).  *n_out = bytes written.  Returns NTS_OK, 1 when `cap` is too small (call
+ * again with a larger buffer; the ISIZE trailer of a single-member file is its exact size), NTS_ERR_STATE for a truncated
+ * or corrupt stream.  verify_crc: check every member's CRC-32 (computed by a second thread behind the decoder). */
+int nts_gz_inflate(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap, uint64_t* n_out, int verify_crc);
 /* nts_fasta_pack: 2-bit pack every record with n_threads threads (0 = hardware concurrency; records in parallel, long
  * uniform records split at 4 Mbp).  word_off[r] = even offset of record r in words_out (zero-initialised, sum of
  * nts_packed_words(n_bases[r]) words); N runs in record coordinates, record r owning [nrun_off[r], nrun_off[r+1]).

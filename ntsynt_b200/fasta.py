@@ -198,6 +198,8 @@ def inflate_gz(raw, threads=0):
             return b"".join(parts)
         with ThreadPoolExecutor(max_workers=threads) as ex:
             return b"".join(ex.map(job, range(0, len(blocks), per)))
+    if os.environ.get("NTS_GZ_INFLATE", "native") != "zlib":
+        return inflate_gz_native(raw)
     out, data = [], memoryview(raw)
     while len(data):
         d = zlib.decompressobj(31)
@@ -214,13 +216,44 @@ def inflate_gz(raw, threads=0):
     return b"".join(out)
 
 
+def inflate_gz_native(raw, verify_crc=True):
+    """gzip bytes -> plain bytes (a uint8 array) with the library's own decoder (csrc/nts_inflate.cu: nts_gz_inflate), which
+    follows concatenated members and checks every member's length and CRC-32.  The output buffer is sized from the ISIZE
+    trailer -- exact for a file of one member below 4 GB -- and grown when the decoder says it does not fit."""
+    n = len(raw)
+    src = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(1, dtype=np.uint8)
+    if n < 18:
+        raise ValueError("truncated gzip stream")
+    cap = int.from_bytes(bytes(src[n - 4:n]), "little")
+    if n > (1 << 30):
+        while cap < n:                     # ISIZE is the size modulo 2^32
+            cap += 1 << 32
+    for _ in range(8):
+        out = np.empty(cap + 8, dtype=np.uint8)
+        got = C.c_uint64()
+        rc = lib.nts_gz_inflate(C.c_void_p(src.ctypes.data), n, C.c_void_p(out.ctypes.data), cap, C.byref(got), int(bool(verify_crc)))
+        if rc == 0:
+            return out[:got.value]
+        if rc != 1:
+            raise ValueError(lib.nts_last_error().decode() or "corrupt gzip stream")
+        cap = max(2 * cap, 6 * n)          # several members (ISIZE names the last one only)
+    raise ValueError("gzip stream expands more than 700 times")
+
+
 def read_fasta(path, threads=0):
     "FASTA file (.gz accepted) -> PackedGenome through the native reader (csrc/nts_fasta.cu)"
     import mmap
     with open(path, "rb") as fh:
         if fh.read(2) == b"\x1f\x8b":
-            fh.seek(0)
-            return parse_fasta_bytes(inflate_gz(fh.read(), threads), path=path, threads=threads)
+            mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)        # the compressed bytes are read through a mapping
+            try:
+                text = inflate_gz(mm, threads)
+            finally:
+                try:
+                    mm.close()
+                except BufferError:        # the traceback of a failed inflate may still hold a view: the mapping goes with it
+                    pass
+            return parse_fasta_bytes(text, path=path, threads=threads)
         size = fh.seek(0, 2)
         if size == 0:
             return parse_fasta_bytes(b"", path=path, threads=threads)

@@ -1,0 +1,105 @@
+"""nts_gz_inflate (csrc/nts_inflate.cu), the decompressor in front of the FASTA reader (btllib::SeqReader pipes .gz input
+through one: src/ntsynt_make_common_bf.cpp:32-36,125,143), against zlib: every block type and compressor strategy, several
+members, header fields, exact / short output buffers, truncation, corruption, garbage -- host code, no GPU."""
+import ctypes as C
+import glob
+import gzip
+import io
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from ntsynt_b200 import fasta
+from ntsynt_b200._lib import lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def native(raw, cap, crc=1):
+    raw = bytes(raw)
+    a = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, np.uint8)
+    out = np.full(cap + 8, 0xEE, dtype=np.uint8)
+    n = C.c_uint64()
+    rc = lib.nts_gz_inflate(C.c_void_p(a.ctypes.data), len(raw), C.c_void_p(out.ctypes.data), cap, C.byref(n), crc)
+    assert n.value <= cap and (out[cap:] == 0xEE).all()            # never writes past the capacity it was given
+    return rc, bytes(out[:n.value])
+
+
+def _cases():
+    rng = np.random.default_rng(0)
+    cases = []
+    for n in (0, 1, 2, 100, 5000, 70000, 400000):
+        cases.append(bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n)))
+        cases.append(bytes(rng.integers(0, 256, n, dtype=np.uint8)))                       # incompressible: stored blocks
+        cases.append(bytes(rng.choice(np.frombuffer(b"ACGTN\n", dtype=np.uint8), n, p=[.24, .24, .24, .24, .02, .02])))
+    cases.append(b"A" * 300000)                                                            # matches at distance 1
+    cases.append(b"ACGTTGCA" * 50000)
+    cases.append(b"ACG" * 70000)                                                           # distance 3: byte-wise overlap copy
+    cases.append(bytes(rng.integers(0, 256, 300, dtype=np.uint8)) * 1000)                  # long matches
+    cases.append(b"".join(bytes([i % 251]) * (i % 7 + 1) for i in range(60000)))           # many symbols: long codes
+    return cases
+
+
+def test_every_block_type_and_strategy_matches_zlib():
+    for data in _cases():
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                c = zlib.compressobj(level, zlib.DEFLATED, 31, 9, strategy)
+                raw = c.compress(data) + c.flush()
+                rc, out = native(raw, len(data), crc=level & 1)
+                assert rc == 0 and out == data, (len(data), level, strategy, rc)
+
+
+def test_members_header_fields_and_capacity():
+    data = _cases()[17]
+    raw = gzip.compress(data[:1000]) + gzip.compress(data[1000:]) + b"\0\0\0"              # concatenated members, zero padding
+    assert native(raw, len(data)) == (0, data)
+    bio = io.BytesIO()
+    with gzip.GzipFile(filename="some_name.fa", mode="wb", fileobj=bio, mtime=5) as fh:   # FNAME field
+        fh.write(data)
+    assert native(bio.getvalue(), len(data)) == (0, data)
+    hdr = b"\x1f\x8b\x08\x1e" + b"\0" * 6 + b"\x03\0abc" + b"name\0" + b"comment\0" + b"\x12\x34"   # FEXTRA FNAME FCOMMENT FHCRC
+    body = gzip.compress(data)[10:]
+    assert native(hdr + body, len(data)) == (0, data)
+    raw = gzip.compress(data)
+    assert native(raw, len(data))[0] == 0
+    assert native(raw, len(data) - 1)[0] == 1 and native(raw, 10)[0] == 1 and native(raw, 0)[0] == 1     # "does not fit"
+    assert native(gzip.compress(b""), 0) == (0, b"")
+    # the wrapper sizes the buffer itself (several members: it has to grow it) and returns an array
+    assert bytes(fasta.inflate_gz_native(gzip.compress(data[:100000]) + gzip.compress(data[100000:]))) == data
+    assert bytes(fasta.inflate_gz_native(gzip.compress(b""))) == b""
+
+
+def test_truncated_corrupt_and_random_input_is_refused_not_crashed_on():
+    rng = np.random.default_rng(1)
+    data = _cases()[15]
+    raw = gzip.compress(data)
+    for cut in list(range(1, 40)) + [len(raw) // 2, len(raw) - 5]:
+        assert native(raw[:-cut], len(data))[0] < 0, cut
+    with pytest.raises(ValueError):
+        fasta.inflate_gz_native(raw[:-20])
+    detected = 0
+    for _ in range(300):
+        b = bytearray(raw)
+        b[int(rng.integers(10, len(raw)))] ^= 1 << int(rng.integers(0, 8))
+        rc, out = native(bytes(b), len(data) + 1000)
+        assert rc != 0 or out == data                      # a flipped bit is either noticed (CRC, length, code) or harmless
+        detected += rc != 0
+    assert detected >= 290
+    b = bytearray(raw); b[-6] ^= 1                          # the CRC field itself
+    assert native(bytes(b), len(data), crc=1)[0] < 0 and native(bytes(b), len(data), crc=0)[0] == 0
+    for trial in range(2000):
+        g = b"\x1f\x8b\x08\x00\0\0\0\0\0\x03" + bytes(rng.integers(0, 256, int(rng.integers(0, 400)), dtype=np.uint8))
+        native(g, 100000, crc=trial & 1)
+    assert native(b"\x1f\x8b\x08", 10)[0] < 0 and native(b"plain text, not gzip at all", 100)[0] < 0 and native(b"", 10)[0] < 0
+
+
+def test_every_gz_fixture_inflates_like_zlib():
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "**", "*.gz"), recursive=True))
+    assert len(files) >= 4
+    for f in files:
+        raw = open(f, "rb").read()
+        want = gzip.decompress(raw)
+        assert bytes(fasta.inflate_gz_native(raw)) == want, f
