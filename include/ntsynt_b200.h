@@ -418,6 +418,11 @@ int nts_fasta_scan_mt(const char* buf, uint64_t n, uint64_t cap, uint64_t* name_
  * again with a larger buffer; the ISIZE trailer of a single-member file is its exact size), NTS_ERR_STATE for a truncated
  * or corrupt stream.  verify_crc: check every member's CRC-32 (computed by a second thread behind the decoder). */
 int nts_gz_inflate(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap, uint64_t* n_out, int verify_crc);
+/* the same by n_threads threads (0 = all cores): a member of >= 16 MB is cut into chunks; every chunk but the first finds a
+ * block boundary by trial, is decoded without its history into 16-bit symbols (what it copies out of the unknown 32 KB in
+ * front of it stays symbolic) and is resolved once its predecessor is done.  Same checks, same result. */
+int nts_gz_inflate_mt(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap, uint64_t* n_out, int verify_crc,
+                      uint32_t n_threads);
 /* nts_fasta_pack: 2-bit pack every record with n_threads threads (0 = hardware concurrency; records in parallel, long
  * uniform records split at 4 Mbp).  word_off[r] = even offset of record r in words_out (zero-initialised, sum of
  * nts_packed_words(n_bases[r]) words); N runs in record coordinates, record r owning [nrun_off[r], nrun_off[r+1]).

@@ -5,7 +5,9 @@
 // decoding per symbol: a 64-bit bit buffer refilled eight bytes at a time, an 11-bit first-level table for the
 // literal/length code and an 8-bit one for the distance code (second-level tables behind the long codes), matches copied
 // eight bytes at a time.  The CRC-32 of the output is checked by a second thread that follows the decoder.
+#include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -168,12 +170,15 @@ inline uint32_t decode(Reader& r, const uint32_t* table, int table_bits) {
 // that sits in memory, so state kept behind a reference would be reloaded after every literal).  Returns OK when it ran out
 // of room (the careful loop below finishes the block), K_END + 16 when it met the end-of-block code, BAD on invalid data
 constexpr int FAST_DONE = 16;
-int inflate_block_fast(Reader& r_, const Tables& t, uint8_t* out_begin, uint8_t*& out_, uint8_t* out_end) {
+// O = uint8_t: the text itself.  O = uint16_t: the symbolic form of a chunk decoded without its history (parallel decode,
+// below): literals are 0..255, everything copied out of the unknown 32 KB before the chunk is a placeholder >= 0x8000
+template <typename O>
+int inflate_block_fast(Reader& r_, const Tables& t, O* out_begin, O*& out_, O* out_end) {
     const uint8_t* p = r_.p;
     const uint8_t* const end = r_.end;
     uint64_t buf = r_.buf;
     int bits = r_.bits;
-    uint8_t* o = out_;
+    O* o = out_;
     const uint32_t* const lit = t.lit;
     const uint32_t* const dist = t.dist;
     int rc = OK;
@@ -190,16 +195,16 @@ int inflate_block_fast(Reader& r_, const Tables& t, uint8_t* out_begin, uint8_t*
         NTS_REFILL();
         uint32_t e = lit[buf & ((1u << LIT_BITS) - 1)];
         if (e_kind(e) == K_LITERAL) {                        // up to four literals from one refill (4 x 11 bits <= 56)
-            NTS_DROP(e_len(e)); *o++ = (uint8_t)e_base(e);
+            NTS_DROP(e_len(e)); *o++ = (O)e_base(e);
             e = lit[buf & ((1u << LIT_BITS) - 1)];
             if (e_kind(e) == K_LITERAL) {
-                NTS_DROP(e_len(e)); *o++ = (uint8_t)e_base(e);
+                NTS_DROP(e_len(e)); *o++ = (O)e_base(e);
                 e = lit[buf & ((1u << LIT_BITS) - 1)];
                 if (e_kind(e) == K_LITERAL) {
-                    NTS_DROP(e_len(e)); *o++ = (uint8_t)e_base(e);
+                    NTS_DROP(e_len(e)); *o++ = (O)e_base(e);
                     e = lit[buf & ((1u << LIT_BITS) - 1)];
                     if (e_kind(e) == K_LITERAL) {
-                        NTS_DROP(e_len(e)); *o++ = (uint8_t)e_base(e);
+                        NTS_DROP(e_len(e)); *o++ = (O)e_base(e);
                         continue;
                     }
                 }
@@ -210,7 +215,7 @@ int inflate_block_fast(Reader& r_, const Tables& t, uint8_t* out_begin, uint8_t*
             NTS_DROP(LIT_BITS);
             e = lit[e_base(e) + (uint32_t)(buf & ((1u << e_extra(e)) - 1))];
             if (e_kind(e) == K_LITERAL) {
-                NTS_DROP(e_len(e)); *o++ = (uint8_t)e_base(e);
+                NTS_DROP(e_len(e)); *o++ = (O)e_base(e);
                 continue;
             }
         }
@@ -231,18 +236,19 @@ int inflate_block_fast(Reader& r_, const Tables& t, uint8_t* out_begin, uint8_t*
         uint32_t off = e_base(d) + (uint32_t)(buf & ((1u << e_extra(d)) - 1));
         NTS_DROP(e_extra(d));
         if (off > (uint64_t)(o - out_begin)) { rc = BAD; break; }
-        const uint8_t* src = o - off;
-        uint8_t* stop = o + len;
-        if (off >= 8) {
+        const O* src = o - off;
+        O* stop = o + len;
+        constexpr uint32_t PER_WORD = 8 / sizeof(O);
+        if (off >= PER_WORD) {
             do {
                 uint64_t w;
                 memcpy(&w, src, 8);
                 memcpy(o, &w, 8);
-                src += 8;
-                o += 8;
+                src += PER_WORD;
+                o += PER_WORD;
             } while (o < stop);
-        } else if (off == 1) {
-            memset(o, *src, len);
+        } else if (off == 1 && sizeof(O) == 1) {
+            memset(o, (int)*src, len);
         } else {
             do { *o++ = *src++; } while (o < stop);
         }
@@ -258,25 +264,27 @@ int inflate_block_fast(Reader& r_, const Tables& t, uint8_t* out_begin, uint8_t*
 }
 
 // one Huffman-coded block.  out_begin: start of the member's output (matches may reach back to it)
-int inflate_block(Reader& r, const Tables& t, uint8_t* out_begin, uint8_t*& out, uint8_t* out_end) {
+template <typename O>
+int inflate_block(Reader& r, const Tables& t, O* out_begin, O*& out, O* out_end) {
     for (;;) {
         if (r.end - r.p >= 16 && out_end - out >= 320) {
-            int rc = inflate_block_fast(r, t, out_begin, out, out_end);
+            int rc = inflate_block_fast<O>(r, t, out_begin, out, out_end);
             if (rc == FAST_DONE) return OK;
             if (rc != OK) return rc;
         }
         r.refill();                        // >= 56 bits, or everything that is left: a symbol needs at most 15 + 5 + 15 + 13 = 48
         uint32_t e = decode(r, t.lit, LIT_BITS);
+        if (r.overrun) return TRUNCATED;         // (before anything else: a cut stream must not read as "output full")
         uint32_t kind = e_kind(e);
         if (kind == K_LITERAL) {
             if (out == out_end) return OUTPUT_FULL;
-            *out++ = (uint8_t)e_base(e);
+            *out++ = (O)e_base(e);
             // literals come in runs: take more of them from the bits already loaded
             while (r.bits >= 30) {
                 uint32_t e2 = t.lit[r.peek(LIT_BITS)];
                 if (e_kind(e2) != K_LITERAL || out == out_end) break;
                 r.drop(e_len(e2));
-                *out++ = (uint8_t)e_base(e2);
+                *out++ = (O)e_base(e2);
             }
             if (r.overrun) return TRUNCATED;
             continue;
@@ -290,16 +298,17 @@ int inflate_block(Reader& r, const Tables& t, uint8_t* out_begin, uint8_t*& out,
         if (r.overrun) return TRUNCATED;
         if (off > (uint64_t)(out - out_begin)) return BAD;
         if ((uint64_t)(out_end - out) < len) return OUTPUT_FULL;
-        const uint8_t* src = out - off;
-        if (off >= 8 && (uint64_t)(out_end - out) >= len + 8) {
-            uint8_t* dst = out;
-            uint8_t* stop = out + len;
+        const O* src = out - off;
+        constexpr uint32_t PER_WORD = 8 / sizeof(O);
+        if (off >= PER_WORD && (uint64_t)(out_end - out) >= len + PER_WORD) {
+            O* dst = out;
+            O* stop = out + len;
             do {
                 uint64_t w;
                 memcpy(&w, src, 8);
                 memcpy(dst, &w, 8);
-                src += 8;
-                dst += 8;
+                src += PER_WORD;
+                dst += PER_WORD;
             } while (dst < stop);
             out = stop;
         } else {
@@ -365,41 +374,49 @@ void fixed_tables(Tables& t) {
     build_table(DIST, dl, 32, t.dist, DIST_BITS);
 }
 
-// one DEFLATE stream starting at r.p; leaves r.p on the byte after it.  out_begin: where this stream's output starts;
-// progress (optional): bytes of it that are final, published after every block
+// one block of any type at the reader's position; last = its BFINAL bit.  After the final block the reader is byte aligned
+template <typename O>
+int inflate_one_block(Reader& r, Tables& t, O* out_begin, O*& out, O* out_end, bool& last) {
+    r.refill();
+    last = r.take(1) != 0;
+    uint32_t type = r.take(2);
+    if (r.overrun) return TRUNCATED;
+    if (type == 0) {
+        r.align_to_byte();
+        if (r.end - r.p < 4) return TRUNCATED;
+        uint32_t len = r.p[0] | (r.p[1] << 8), nlen = r.p[2] | (r.p[3] << 8);
+        if ((len ^ nlen) != 0xFFFFu) return BAD;
+        r.p += 4;
+        if ((uint64_t)(r.end - r.p) < len) return TRUNCATED;
+        if ((uint64_t)(out_end - out) < len) return OUTPUT_FULL;
+        for (uint32_t i = 0; i < len; ++i) out[i] = (O)r.p[i];
+        out += len;
+        r.p += len;
+    } else if (type == 1 || type == 2) {
+        if (type == 1) {
+            fixed_tables(t);
+        } else {
+            int rc = read_dynamic_tables(r, t);
+            if (rc != OK) return rc;
+        }
+        int rc = inflate_block<O>(r, t, out_begin, out, out_end);
+        if (rc != OK) return rc;
+    } else {
+        return BAD;
+    }
+    if (last) r.align_to_byte();
+    return OK;
+}
+
+// one DEFLATE stream starting at the reader's position; leaves r.p on the byte after it.  out_begin: where this stream's
+// output starts; progress (optional): bytes of it that are final, published after every block
 int inflate_stream(Reader& r, Tables& t, uint8_t* out_begin, uint8_t*& out, uint8_t* out_end, std::atomic<uint64_t>* progress) {
     for (;;) {
         if (progress) progress->store((uint64_t)(out - out_begin), std::memory_order_release);
-        r.refill();
-        uint32_t last = r.take(1), type = r.take(2);
-        if (r.overrun) return TRUNCATED;
-        if (type == 0) {
-            r.align_to_byte();
-            if (r.end - r.p < 4) return TRUNCATED;
-            uint32_t len = r.p[0] | (r.p[1] << 8), nlen = r.p[2] | (r.p[3] << 8);
-            if ((len ^ nlen) != 0xFFFFu) return BAD;
-            r.p += 4;
-            if ((uint64_t)(r.end - r.p) < len) return TRUNCATED;
-            if ((uint64_t)(out_end - out) < len) return OUTPUT_FULL;
-            memcpy(out, r.p, len);
-            out += len;
-            r.p += len;
-        } else if (type == 1 || type == 2) {
-            if (type == 1) {
-                fixed_tables(t);
-            } else {
-                int rc = read_dynamic_tables(r, t);
-                if (rc != OK) return rc;
-            }
-            int rc = inflate_block(r, t, out_begin, out, out_end);
-            if (rc != OK) return rc;
-        } else {
-            return BAD;
-        }
-        if (last) {
-            r.align_to_byte();
-            return OK;
-        }
+        bool last;
+        int rc = inflate_one_block<uint8_t>(r, t, out_begin, out, out_end, last);
+        if (rc != OK) return rc;
+        if (last) return OK;
     }
 }
 
@@ -465,12 +482,259 @@ struct CrcFollower {
     }
 };
 
+// crc of the concatenation A|B from crc(A), crc(B) and len(B): the operator "append one zero bit" as a 32 x 32 matrix over
+// GF(2), squared up to len(B) zero bytes (the construction zlib documents for crc32_combine)
+uint32_t gf2_times(const uint32_t* mat, uint32_t vec) {
+    uint32_t sum = 0;
+    for (int i = 0; vec; vec >>= 1, ++i)
+        if (vec & 1) sum ^= mat[i];
+    return sum;
+}
+void gf2_square(uint32_t* sq, const uint32_t* mat) {
+    for (int i = 0; i < 32; ++i) sq[i] = gf2_times(mat, mat[i]);
+}
+uint32_t crc32_concat(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) {
+    if (!len_b) return crc_a;
+    uint32_t even[32], odd[32];
+    odd[0] = 0xEDB88320u;
+    for (int i = 1; i < 32; ++i) odd[i] = 1u << (i - 1);
+    gf2_square(even, odd);      // two zero bits
+    gf2_square(odd, even);      // four zero bits
+    do {
+        gf2_square(even, odd);  // first round: one zero byte
+        if (len_b & 1) crc_a = gf2_times(even, crc_a);
+        len_b >>= 1;
+        if (!len_b) break;
+        gf2_square(odd, even);
+        if (len_b & 1) crc_a = gf2_times(odd, crc_a);
+        len_b >>= 1;
+    } while (len_b);
+    return crc_a ^ crc_b;
+}
+
+// ---- one long member decoded by several threads --------------------------------------------------------------------------
+// The compressed bytes are cut into chunks.  The first chunk of a wave starts at a known block boundary with its history in
+// place and is decoded straight into the output.  Every other chunk looks for a position at or after its cut where a
+// dynamic-Huffman block starts and decodes (the three code tables of a block header are complete prefix codes -- random bits
+// almost never are), and decodes from there WITHOUT its history: into 16-bit symbols, literals as themselves and whatever a
+// match copies out of the unknown 32 KB before the chunk as "byte i of that window".  A chunk runs until it stands exactly
+// on the position its successor started from.  Afterwards the windows are filled in in order (only the last 32 KB of every
+// chunk have to be resolved one after the other), the chunks are translated to bytes in parallel and their CRCs combined.
+// Nothing is trusted: a chunk whose start does not coincide with its predecessor's end, or that fails, is dropped, and the
+// next wave starts, with history, where the last good chunk ended; length and CRC-32 of the member are checked as always.
+constexpr uint32_t WINDOW = 32768;
+constexpr uint16_t PLACEHOLDER = 0x8000;
+constexpr uint64_t NO_END = ~0ull;
+
+inline uint64_t bit_position(const Reader& r, const uint8_t* base) { return (uint64_t)(r.p - base) * 8 - (uint64_t)r.bits; }
+
+inline void reader_at(Reader& r, const uint8_t* base, const uint8_t* end, uint64_t bit) {
+    r.p = base + (bit >> 3);
+    r.end = end;
+    r.buf = 0;
+    r.bits = 0;
+    r.overrun = false;
+    r.refill();
+    r.drop((int)(bit & 7));
+}
+
+struct Chunk {
+    uint64_t target_bit = 0;              // symbolic chunks: look for a block start from here on
+    uint64_t end_target_bit = 0;          // stop at a block boundary at or after this (NO_END: run to the final block)
+    std::atomic<int64_t> start_bit{-1};   // -1 not known yet, -2 none found
+    uint64_t end_bit = 0;
+    int rc = BAD;
+    bool final_block = false;
+    uint64_t n = 0;                       // elements decoded
+    uint32_t crc = 0;
+};
+
+template <typename O>
+void run_chunk(const uint8_t* base, const uint8_t* end, Chunk& c, Chunk* next, Tables& t, O* out_begin, O* o_start, O* o_end,
+               bool search) {
+    Reader r;
+    O* o = o_start;
+    if (search) {
+        const uint64_t n_bits = (uint64_t)(end - base) * 8;
+        const uint64_t reach = std::min<uint64_t>(8ull << 20, 4 * (c.end_target_bit == NO_END ? (8ull << 20) : c.end_target_bit - c.target_bit));
+        const uint64_t limit = std::min<uint64_t>(c.target_bit + reach, n_bits > 128 ? n_bits - 128 : 0);
+        int64_t found = -2;
+        for (uint64_t b = c.target_bit; b < limit; ++b) {
+            const uint8_t* q = base + (b >> 3);
+            if (((((uint32_t)q[0] | ((uint32_t)q[1] << 8)) >> (b & 7)) & 7u) != 4u) continue;     // BFINAL 0, BTYPE 2 (dynamic)
+            reader_at(r, base, end, b);
+            o = o_start;
+            bool last;
+            if (inflate_one_block<O>(r, t, out_begin, o, o_end, last) == OK && o - o_start >= 256) {
+                found = (int64_t)b;
+                break;
+            }
+        }
+        c.start_bit.store(found, std::memory_order_release);
+        if (found < 0) return;
+    } else {
+        reader_at(r, base, end, (uint64_t)c.start_bit.load());
+    }
+    for (;;) {
+        uint64_t pos = bit_position(r, base);
+        if (pos >= c.end_target_bit) {
+            if (!next) break;
+            int64_t s;
+            while ((s = next->start_bit.load(std::memory_order_acquire)) == -1) std::this_thread::yield();
+            if (s < 0 || pos >= (uint64_t)s) break;      // equal: the successor takes over here; otherwise it is dropped
+        }
+        bool last;
+        int rc = inflate_one_block<O>(r, t, out_begin, o, o_end, last);
+        if (rc != OK) {
+            c.rc = rc;
+            c.n = (uint64_t)(o - o_start);
+            return;
+        }
+        if (last) {
+            c.final_block = true;
+            break;
+        }
+    }
+    c.end_bit = bit_position(r, base);
+    c.n = (uint64_t)(o - o_start);
+    c.rc = OK;
+}
+
+// member whose DEFLATE data starts at byte `start`; on OK `after` = first byte behind the data, crc = CRC-32 of the output
+int inflate_member_parallel(const uint8_t* base, const uint8_t* end, uint64_t start, uint8_t* member_start, uint8_t*& o,
+                            uint8_t* o_end, int n_threads, uint64_t chunk_bytes, bool want_crc, uint32_t& crc, const uint8_t*& after) {
+    const uint64_t n_bits = (uint64_t)(end - base) * 8, chunk_bits = chunk_bytes * 8;
+    const uint64_t sym_cap = WINDOW + 16 * chunk_bytes + 4096;          // elements; a chunk that needs more is dropped
+    std::vector<Tables> tables((size_t)n_threads);
+    std::vector<uint16_t*> sym((size_t)n_threads, nullptr);
+    struct Free {
+        std::vector<uint16_t*>& v;
+        ~Free() { for (uint16_t* p : v) free(p); }
+    } free_sym{sym};
+    std::vector<uint8_t> windows((size_t)n_threads * WINDOW), lut((size_t)n_threads * 65536);
+    uint64_t pos = start * 8;
+    uint32_t crc_all = 0;
+    // a stream without dynamic blocks (stored or fixed-Huffman data) gives the searching chunks nothing to find: after a wave
+    // in which only the first chunk counted, that many chunks are decoded by one thread before the next attempt, doubling
+    int fails = 0;
+    bool solo = false;
+    for (;;) {
+        uint64_t left = n_bits - pos;
+        int nc = (int)std::min<uint64_t>((uint64_t)n_threads, left / chunk_bits);
+        uint64_t span = 1;
+        if (solo) {
+            nc = 1;
+            span = 1ull << std::min(fails, 6);
+        }
+        if (nc < 2) nc = 1;
+        const bool to_the_end = left <= ((uint64_t)nc * span + 1) * chunk_bits;
+        std::vector<Chunk> ch((size_t)nc);
+        for (int j = 0; j < nc; ++j) {
+            ch[j].target_bit = pos + (uint64_t)j * chunk_bits;
+            ch[j].end_target_bit = (j == nc - 1 && to_the_end) ? NO_END : pos + (uint64_t)(j + 1) * span * chunk_bits;
+            if (j && !sym[j]) {
+                sym[j] = (uint16_t*)malloc(sym_cap * sizeof(uint16_t));
+                if (!sym[j]) return BAD;
+                for (uint32_t i = 0; i < WINDOW; ++i) sym[j][i] = (uint16_t)(PLACEHOLDER + i);
+            }
+        }
+        ch[0].start_bit.store((int64_t)pos);
+        uint8_t* const wave_out = o;
+        {
+            std::vector<std::thread> th;
+            for (int j = 1; j < nc; ++j)
+                th.emplace_back([&, j] {
+                    run_chunk<uint16_t>(base, end, ch[j], j + 1 < nc ? &ch[j + 1] : nullptr, tables[j], sym[j], sym[j] + WINDOW,
+                                        sym[j] + sym_cap, true);
+                });
+            run_chunk<uint8_t>(base, end, ch[0], nc > 1 ? &ch[1] : nullptr, tables[0], member_start, wave_out, o_end, false);
+            for (auto& x : th) x.join();
+        }
+        if (ch[0].rc != OK) {
+            o = wave_out + ch[0].n;
+            return ch[0].rc;
+        }
+        int valid = 1;
+        while (valid < nc && !ch[valid - 1].final_block && ch[valid].rc == OK &&
+               ch[valid].start_bit.load() == (int64_t)ch[valid - 1].end_bit)
+            ++valid;
+        std::vector<uint8_t*> dst((size_t)valid + 1);
+        dst[0] = wave_out;
+        for (int j = 0; j < valid; ++j) dst[j + 1] = dst[j] + ch[j].n;
+        if (valid > 1 && (uint64_t)(dst[1] - member_start) < WINDOW) valid = 1;      // (cannot happen with chunks of megabytes)
+        if (dst[valid] > o_end) {
+            o = wave_out + ch[0].n;
+            return OUTPUT_FULL;
+        }
+        // windows, one after the other: the 32 KB in front of chunk j are the resolved tail of chunk j - 1
+        for (int j = 1; j < valid; ++j) {
+            uint8_t* w = &windows[(size_t)j * WINDOW];
+            uint8_t* l = &lut[(size_t)j * 65536];
+            if (j == 1) {
+                memcpy(w, dst[1] - WINDOW, WINDOW);
+            } else {
+                const uint8_t* pw = &windows[(size_t)(j - 1) * WINDOW];
+                const uint8_t* pl = &lut[(size_t)(j - 1) * 65536];
+                const uint16_t* ps = sym[j - 1] + WINDOW;
+                uint64_t pn = ch[j - 1].n;
+                if (pn >= WINDOW) {
+                    for (uint32_t i = 0; i < WINDOW; ++i) w[i] = pl[ps[pn - WINDOW + i]];
+                } else {
+                    memcpy(w, pw + pn, WINDOW - pn);
+                    for (uint64_t i = 0; i < pn; ++i) w[WINDOW - pn + i] = pl[ps[i]];
+                }
+            }
+            for (uint32_t v = 0; v < 256; ++v) l[v] = (uint8_t)v;
+            memset(l + 256, 0, PLACEHOLDER - 256);
+            memcpy(l + PLACEHOLDER, w, WINDOW);
+        }
+        {
+            std::vector<std::thread> th;
+            for (int j = 1; j < valid; ++j)
+                th.emplace_back([&, j] {
+                    const uint8_t* l = &lut[(size_t)j * 65536];
+                    const uint16_t* ps = sym[j] + WINDOW;
+                    uint8_t* d = dst[j];
+                    for (uint64_t i = 0, n = ch[j].n; i < n; ++i) d[i] = l[ps[i]];
+                    if (want_crc) ch[j].crc = crc32_update(0, d, ch[j].n);
+                });
+            if (want_crc) ch[0].crc = crc32_update(0, dst[0], ch[0].n);
+            for (auto& x : th) x.join();
+        }
+        if (want_crc)
+            for (int j = 0; j < valid; ++j) crc_all = crc32_concat(crc_all, ch[j].crc, ch[j].n);
+        if (solo) {
+            solo = false;
+        } else if (nc > 1 && valid == 1) {
+            ++fails;
+            solo = true;
+        } else {
+            fails = 0;
+        }
+        o = dst[valid];
+        pos = ch[valid - 1].end_bit;
+        if (ch[valid - 1].final_block) {
+            after = base + (pos >> 3);
+            crc = crc_all;
+            return OK;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
 
 int nts_gz_inflate(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap, uint64_t* n_out, int verify_crc) {
+    return nts_gz_inflate_mt(in, n_in, out, cap, n_out, verify_crc, 1);
+}
+
+int nts_gz_inflate_mt(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap, uint64_t* n_out, int verify_crc, uint32_t n_threads) {
     using nts::fail;
+    if (!n_threads) n_threads = std::max(1u, std::thread::hardware_concurrency());
+    n_threads = std::min(n_threads, 32u);
+    uint64_t chunk_bytes = 4ull << 20;
+    if (const char* e = getenv("NTS_GZ_CHUNK_BYTES")) chunk_bytes = std::max<uint64_t>(4096, strtoull(e, nullptr, 10));
     if ((!in && n_in) || (!out && cap) || !n_out) return fail(NTS_ERR_ARG, "null argument");
     *n_out = 0;
     std::vector<Tables> tables(1);
@@ -508,7 +772,12 @@ int nts_gz_inflate(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap,
         uint8_t* member_start = o;
         int rc;
         uint32_t crc = 0;
-        if (verify_crc) {
+        if (n_threads > 1 && (uint64_t)(end - p) >= 4 * chunk_bytes) {
+            const uint8_t* after = nullptr;
+            rc = inflate_member_parallel(in, end, (uint64_t)(p - in), member_start, o, o_end, (int)n_threads, chunk_bytes,
+                                         verify_crc != 0, crc, after);
+            if (rc == OK) r.p = after;
+        } else if (verify_crc) {
             CrcFollower follower(member_start);         // reads what the decoder has published as final, block by block
             rc = inflate_stream(r, t, member_start, o, o_end, &follower.done);
             crc = follower.finish(rc == OK ? (uint64_t)(o - member_start) : follower.done.load());

@@ -178,8 +178,9 @@ def _bgzf_blocks(raw):
 
 def inflate_gz(raw, threads=0):
     """gzip bytes -> plain bytes.  BGZF input (independent members) is inflated by `threads` threads, a batch of
-    members each (zlib releases the GIL); anything else goes through one streaming inflate that follows concatenated
-    members, as `gzip -dc` does -- which is how btllib's SeqReader reads .gz too (one decompressor process per file)."""
+    members each (zlib releases the GIL); anything else goes through the library's own decoder (inflate_gz_native), which
+    also spreads one long member over the threads.  NTS_GZ_INFLATE=zlib: one streaming zlib inflate instead, as `gzip -dc`
+    does -- which is how btllib's SeqReader reads .gz (one decompressor process per file)."""
     import os
     import zlib
     from concurrent.futures import ThreadPoolExecutor
@@ -199,7 +200,7 @@ def inflate_gz(raw, threads=0):
         with ThreadPoolExecutor(max_workers=threads) as ex:
             return b"".join(ex.map(job, range(0, len(blocks), per)))
     if os.environ.get("NTS_GZ_INFLATE", "native") != "zlib":
-        return inflate_gz_native(raw)
+        return inflate_gz_native(raw, threads=threads)
     out, data = [], memoryview(raw)
     while len(data):
         d = zlib.decompressobj(31)
@@ -216,10 +217,11 @@ def inflate_gz(raw, threads=0):
     return b"".join(out)
 
 
-def inflate_gz_native(raw, verify_crc=True):
-    """gzip bytes -> plain bytes (a uint8 array) with the library's own decoder (csrc/nts_inflate.cu: nts_gz_inflate), which
-    follows concatenated members and checks every member's length and CRC-32.  The output buffer is sized from the ISIZE
-    trailer -- exact for a file of one member below 4 GB -- and grown when the decoder says it does not fit."""
+def inflate_gz_native(raw, verify_crc=True, threads=0):
+    """gzip bytes -> plain bytes (a uint8 array) with the library's own decoder (csrc/nts_inflate.cu: nts_gz_inflate_mt), which
+    follows concatenated members and checks every member's length and CRC-32; a long member is decoded by `threads`
+    threads (0 = all cores).  The output buffer is sized from the ISIZE trailer -- exact for a file of one member below
+    4 GB -- and grown when the decoder says it does not fit."""
     n = len(raw)
     src = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(1, dtype=np.uint8)
     if n < 18:
@@ -231,7 +233,8 @@ def inflate_gz_native(raw, verify_crc=True):
     for _ in range(8):
         out = np.empty(cap + 8, dtype=np.uint8)
         got = C.c_uint64()
-        rc = lib.nts_gz_inflate(C.c_void_p(src.ctypes.data), n, C.c_void_p(out.ctypes.data), cap, C.byref(got), int(bool(verify_crc)))
+        rc = lib.nts_gz_inflate_mt(C.c_void_p(src.ctypes.data), n, C.c_void_p(out.ctypes.data), cap, C.byref(got),
+                                   int(bool(verify_crc)), int(threads))
         if rc == 0:
             return out[:got.value]
         if rc != 1:

@@ -103,3 +103,62 @@ def test_every_gz_fixture_inflates_like_zlib():
         raw = open(f, "rb").read()
         want = gzip.decompress(raw)
         assert bytes(fasta.inflate_gz_native(raw)) == want, f
+
+
+def native_mt(raw, cap, threads, crc=1):
+    raw = bytes(raw)
+    a = np.frombuffer(raw, dtype=np.uint8)
+    out = np.full(cap + 8, 0xEE, dtype=np.uint8)
+    n = C.c_uint64()
+    rc = lib.nts_gz_inflate_mt(C.c_void_p(a.ctypes.data), len(raw), C.c_void_p(out.ctypes.data), cap, C.byref(n), crc, threads)
+    assert n.value <= cap and (out[cap:] == 0xEE).all()
+    return rc, bytes(out[:n.value])
+
+
+def _fasta_text(rng, n, nruns=()):
+    a = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n)
+    for s_, l_ in nruns:
+        a[s_:s_ + l_] = ord("N")
+    rows = a[: n // 60 * 60].reshape(-1, 60)
+    buf = np.empty((rows.shape[0], 61), dtype=np.uint8)
+    buf[:, :60], buf[:, 60] = rows, 10
+    return b">chr1 test\n" + buf.tobytes()
+
+
+def test_one_member_decoded_by_several_threads(monkeypatch):
+    """nts_gz_inflate_mt: chunks that start without their history (16-bit symbols, resolved afterwards).  Small chunk sizes
+    bring the machinery down to test size: boundaries found by trial, chunks longer / shorter than a block, N runs that
+    expand a thousand times, streams with no dynamic block at all (stored, fixed Huffman: every searching chunk is
+    dropped), sync-flush markers, several members, short buffers, truncation, corruption"""
+    rng = np.random.default_rng(5)
+    cases = {"dna": _fasta_text(rng, 1_500_000), "n_runs": _fasta_text(rng, 3_000_000, [(100000, 1_000_000), (2_000_000, 700_000)]),
+             "random": bytes(rng.integers(0, 256, 600_000, dtype=np.uint8)),
+             "soft_masked": bytes(rng.choice(np.frombuffer(b"ACGTacgtN\n", dtype=np.uint8), 1_000_000))}
+    for name, data in cases.items():
+        for level, strategy in ((1, 0), (6, 0), (9, 0), (0, 0), (6, zlib.Z_FIXED)):
+            c = zlib.compressobj(level, zlib.DEFLATED, 31, 9, strategy)
+            raw = c.compress(data) + c.flush()
+            for chunk, th in ((4096, 3), (20000, 2), (20000, 8), (65536, 4)):
+                monkeypatch.setenv("NTS_GZ_CHUNK_BYTES", str(chunk))
+                assert native_mt(raw, len(data), th) == (0, data), (name, level, strategy, chunk, th)
+    monkeypatch.setenv("NTS_GZ_CHUNK_BYTES", "20000")
+    data = cases["dna"]
+    raw = gzip.compress(data)
+    assert native_mt(gzip.compress(data[:500_000]) + gzip.compress(data[500_000:]) + b"\0\0", len(data), 4) == (0, data)
+    assert native_mt(raw, len(data) - 1, 4)[0] == 1 and native_mt(raw, 1000, 4)[0] == 1 and native_mt(raw, len(data) // 2, 4)[0] == 1
+    for cut in (1, 5, 9, 100, len(raw) // 3, len(raw) - 100):
+        assert native_mt(raw[:-cut], len(data), 4)[0] < 0, cut
+    for _ in range(60):
+        b = bytearray(raw)
+        b[int(rng.integers(10, len(raw)))] ^= 1 << int(rng.integers(0, 8))
+        rc, out = native_mt(bytes(b), len(data) + 5000, 4)
+        assert rc != 0 or out == data
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)                   # pigz-like stream: flush markers (empty stored blocks) inside
+    parts = []
+    for i in range(0, len(data), 131072):
+        parts.append(c.compress(data[i:i + 131072]))
+        parts.append(c.flush(zlib.Z_FULL_FLUSH if i % 3 else zlib.Z_SYNC_FLUSH))
+    parts.append(c.flush())
+    assert native_mt(b"".join(parts), len(data), 8) == (0, data)
+    # and through the reader
+    assert bytes(fasta.inflate_gz(raw, threads=4)) == data
