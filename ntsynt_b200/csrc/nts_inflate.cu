@@ -627,16 +627,20 @@ int inflate_member_parallel(const uint8_t* base, const uint8_t* end, uint64_t st
             span = 1ull << std::min(fails, 6);
         }
         if (nc < 2) nc = 1;
+        for (int j = 1; j < nc; ++j)
+            if (!sym[j]) {
+                sym[j] = (uint16_t*)malloc(sym_cap * sizeof(uint16_t));
+                if (!sym[j]) {                   // no memory for another symbolic chunk: fewer chunks in flight
+                    nc = j;
+                    break;
+                }
+                for (uint32_t i = 0; i < WINDOW; ++i) sym[j][i] = (uint16_t)(PLACEHOLDER + i);
+            }
         const bool to_the_end = left <= ((uint64_t)nc * span + 1) * chunk_bits;
         std::vector<Chunk> ch((size_t)nc);
         for (int j = 0; j < nc; ++j) {
             ch[j].target_bit = pos + (uint64_t)j * chunk_bits;
             ch[j].end_target_bit = (j == nc - 1 && to_the_end) ? NO_END : pos + (uint64_t)(j + 1) * span * chunk_bits;
-            if (j && !sym[j]) {
-                sym[j] = (uint16_t*)malloc(sym_cap * sizeof(uint16_t));
-                if (!sym[j]) return BAD;
-                for (uint32_t i = 0; i < WINDOW; ++i) sym[j][i] = (uint16_t)(PLACEHOLDER + i);
-            }
         }
         ch[0].start_bit.store((int64_t)pos);
         uint8_t* const wave_out = o;
