@@ -737,8 +737,14 @@ int nts_gz_inflate_mt(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t c
     using nts::fail;
     if (!n_threads) n_threads = std::max(1u, std::thread::hardware_concurrency());
     n_threads = std::min(n_threads, 32u);
-    uint64_t chunk_bytes = 4ull << 20;
-    if (const char* e = getenv("NTS_GZ_CHUNK_BYTES")) chunk_bytes = std::max<uint64_t>(4096, strtoull(e, nullptr, 10));
+    // chunk of compressed bytes per thread and wave: 4 MB keeps the boundary search a small part of a chunk's work; files
+    // of tens of megabytes get smaller chunks so that every thread has one (NTS_GZ_CHUNK_BYTES: fixed size, for tests)
+    uint64_t chunk_bytes = std::min<uint64_t>(4ull << 20, std::max<uint64_t>(1ull << 20, n_in / (4ull * n_threads)));
+    uint64_t parallel_from = 16ull << 20;
+    if (const char* e = getenv("NTS_GZ_CHUNK_BYTES")) {
+        chunk_bytes = std::max<uint64_t>(4096, strtoull(e, nullptr, 10));
+        parallel_from = 4 * chunk_bytes;
+    }
     if ((!in && n_in) || (!out && cap) || !n_out) return fail(NTS_ERR_ARG, "null argument");
     *n_out = 0;
     std::vector<Tables> tables(1);
@@ -776,7 +782,7 @@ int nts_gz_inflate_mt(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t c
         uint8_t* member_start = o;
         int rc;
         uint32_t crc = 0;
-        if (n_threads > 1 && (uint64_t)(end - p) >= 4 * chunk_bytes) {
+        if (n_threads > 1 && (uint64_t)(end - p) >= parallel_from) {
             const uint8_t* after = nullptr;
             rc = inflate_member_parallel(in, end, (uint64_t)(p - in), member_start, o, o_end, (int)n_threads, chunk_bytes,
                                          verify_crc != 0, crc, after);
