@@ -4,7 +4,8 @@
 // genomes through it).  A genome's .gz is one long stream of mostly literals and short matches, so the cost is Huffman
 // decoding per symbol: a 64-bit bit buffer refilled eight bytes at a time, an 11-bit first-level table for the
 // literal/length code and an 8-bit one for the distance code (second-level tables behind the long codes), matches copied
-// eight bytes at a time.  The CRC-32 of the output is checked by a second thread that follows the decoder.
+// eight bytes at a time.  The CRC-32 of the output is checked by a second thread that follows the decoder.  A long member is
+// decoded by several threads (inflate_member_parallel, further down): chunks that start without their history.
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
