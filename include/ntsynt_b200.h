@@ -423,6 +423,10 @@ int nts_gz_inflate(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap,
  * front of it stays symbolic) and is resolved once its predecessor is done.  Same checks, same result. */
 int nts_gz_inflate_mt(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap, uint64_t* n_out, int verify_crc,
                       uint32_t n_threads);
+/* members whose spans are known without decoding (BGZF, `bgzip`: every member names its compressed size): member i is
+ * in[member_off[i] .. member_off[i + 1]); the members are decoded independently, a contiguous range per thread. */
+int nts_gz_inflate_members(const uint8_t* in, const uint64_t* member_off, uint64_t n_members, uint8_t* out, uint64_t cap,
+                           uint64_t* n_out, int verify_crc, uint32_t n_threads);
 /* nts_fasta_pack: 2-bit pack every record with n_threads threads (0 = hardware concurrency; records in parallel, long
  * uniform records split at 4 Mbp).  word_off[r] = even offset of record r in words_out (zero-initialised, sum of
  * nts_packed_words(n_bases[r]) words); N runs in record coordinates, record r owning [nrun_off[r], nrun_off[r+1]).

@@ -146,6 +146,7 @@ _SIGS = {
     "nts_fasta_scan_mt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, u64p, u32p, u64p, u64p, u64p, u32p, u32p, u8p, u64p, C.c_uint32]),
     "nts_gz_inflate": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.c_int]),
     "nts_gz_inflate_mt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.c_int, C.c_uint32]),
+    "nts_gz_inflate_members": (C.c_int, [C.c_void_p, u64p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.c_int, C.c_uint32]),
     "nts_fasta_pack": (C.c_int, [C.c_void_p, C.c_uint64, u64p, u64p, u64p, u32p, u32p, u8p, u64p, u64p, u64p, u64p, u64p,
                                  C.c_uint64, u64p, C.c_uint32]),
     "nts_graph_lookup": (C.c_int, [vp, u64p, C.c_uint64, u32p]),

@@ -734,6 +734,47 @@ int nts_gz_inflate(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap,
     return nts_gz_inflate_mt(in, n_in, out, cap, n_out, verify_crc, 1);
 }
 
+// members that can be found without decoding (BGZF: every member names its own compressed size): member i spans
+// [member_off[i], member_off[i + 1]); its ISIZE trailer gives its place in the output, so the members are decoded
+// independently, a contiguous range per thread
+int nts_gz_inflate_members(const uint8_t* in, const uint64_t* member_off, uint64_t n_members, uint8_t* out, uint64_t cap,
+                           uint64_t* n_out, int verify_crc, uint32_t n_threads) {
+    using nts::fail;
+    if (!in || !member_off || !n_out || (!out && cap)) return fail(NTS_ERR_ARG, "null argument");
+    if (!n_threads) n_threads = std::max(1u, std::thread::hardware_concurrency());
+    std::vector<uint64_t> at(n_members + 1, 0);
+    for (uint64_t i = 0; i < n_members; ++i) {
+        if (member_off[i + 1] < member_off[i] + 18) return fail(NTS_ERR_STATE, "truncated gzip stream");
+        const uint8_t* t = in + member_off[i + 1] - 4;
+        at[i + 1] = at[i] + (t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24));
+    }
+    *n_out = at[n_members];
+    if (at[n_members] > cap) return 1;
+    n_threads = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_threads, n_members / 16));
+    std::vector<int> status(n_threads, NTS_OK);
+    std::vector<std::string> message(n_threads);
+    std::vector<std::thread> th;
+    for (uint32_t k = 0; k < n_threads; ++k)
+        th.emplace_back([&, k] {
+            uint64_t lo = n_members * k / n_threads, hi = n_members * (k + 1) / n_threads;
+            for (uint64_t i = lo; i < hi; ++i) {
+                uint64_t got = 0;
+                int rc = nts_gz_inflate_mt(in + member_off[i], member_off[i + 1] - member_off[i], out + at[i], at[i + 1] - at[i],
+                                           &got, verify_crc, 1);
+                if (rc == NTS_OK && got != at[i + 1] - at[i]) rc = 1;
+                if (rc != NTS_OK) {
+                    status[k] = rc;
+                    message[k] = rc == 1 ? "gzip length check failed" : nts_last_error();
+                    return;
+                }
+            }
+        });
+    for (auto& x : th) x.join();
+    for (uint32_t k = 0; k < n_threads; ++k)
+        if (status[k] != NTS_OK) return fail(NTS_ERR_STATE, message[k]);
+    return NTS_OK;
+}
+
 int nts_gz_inflate_mt(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t cap, uint64_t* n_out, int verify_crc, uint32_t n_threads) {
     using nts::fail;
     if (!n_threads) n_threads = std::max(1u, std::thread::hardware_concurrency());
@@ -788,6 +829,9 @@ int nts_gz_inflate_mt(const uint8_t* in, uint64_t n_in, uint8_t* out, uint64_t c
             rc = inflate_member_parallel(in, end, (uint64_t)(p - in), member_start, o, o_end, (int)n_threads, chunk_bytes,
                                          verify_crc != 0, crc, after);
             if (rc == OK) r.p = after;
+        } else if (verify_crc && (uint64_t)(end - p) < (1ull << 20)) {
+            rc = inflate_stream(r, t, member_start, o, o_end, nullptr);        // small member: not worth a second thread
+            if (rc == OK) crc = crc32_update(0, member_start, (uint64_t)(o - member_start));
         } else if (verify_crc) {
             CrcFollower follower(member_start);         // reads what the decoder has published as final, block by block
             rc = inflate_stream(r, t, member_start, o, o_end, &follower.done);

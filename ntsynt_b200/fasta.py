@@ -186,6 +186,18 @@ def inflate_gz(raw, threads=0):
     from concurrent.futures import ThreadPoolExecutor
     blocks = _bgzf_blocks(raw) if raw[:4] == b"\x1f\x8b\x08\x04" else None
     threads = threads or os.cpu_count() or 1
+    if blocks and len(blocks) > 64 and os.environ.get("NTS_GZ_INFLATE", "native") != "zlib":
+        # members decoded independently by the library's decoder, each at its place in one output buffer
+        src = np.frombuffer(raw, dtype=np.uint8)
+        off = np.array([a for a, _ in blocks] + [blocks[-1][1]], dtype=np.uint64)
+        isz = sum(int.from_bytes(raw[b - 4:b], "little") for _, b in blocks)
+        out = np.empty(isz + 8, dtype=np.uint8)
+        got = C.c_uint64()
+        rc = lib.nts_gz_inflate_members(C.c_void_p(src.ctypes.data), ptr(off, C.c_uint64), len(blocks), C.c_void_p(out.ctypes.data),
+                                        isz, C.byref(got), 1, int(threads))
+        if rc != 0:
+            raise ValueError(lib.nts_last_error().decode() or "corrupt gzip stream")
+        return out[:got.value]
     if blocks and len(blocks) > 64 and threads > 1:
         view = memoryview(raw)
         per = max(64, (len(blocks) + 8 * threads - 1) // (8 * threads))

@@ -162,3 +162,24 @@ def test_one_member_decoded_by_several_threads(monkeypatch):
     assert native_mt(b"".join(parts), len(data), 8) == (0, data)
     # and through the reader
     assert bytes(fasta.inflate_gz(raw, threads=4)) == data
+
+
+def test_bgzf_members_decoded_independently():
+    "bgzip files: every member names its compressed size, so the members are found without decoding and inflated in parallel"
+    from test_fasta_native import _bgzf
+    rng = np.random.default_rng(8)
+    data = _fasta_text(rng, 2_000_000, [(300000, 400000)])
+    raw = _bgzf(data, 65280)
+    blocks = fasta._bgzf_blocks(raw)
+    assert len(blocks) > 30
+    for th in (1, 3, 8):
+        assert bytes(fasta.inflate_gz(raw, threads=th)) == data
+    b = bytearray(raw)
+    a0, a1 = blocks[len(blocks) // 2]
+    b[(a0 + a1) // 2] ^= 0x10                                      # damage inside one member: its CRC (or its codes) notice
+    with pytest.raises(ValueError):
+        fasta.inflate_gz(bytes(b), threads=4)
+    b = bytearray(raw)
+    b[blocks[3][1] - 4] ^= 1                                       # a member's ISIZE: the member no longer fills its place
+    with pytest.raises(ValueError):
+        fasta.inflate_gz(bytes(b), threads=4)
